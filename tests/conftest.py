@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def port():
+    from oracle.oracle import PortOracle, build
+
+    build()
+    return PortOracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    from oracle.oracle import RefOracle, build, have_ref
+
+    build()
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here and no prebuilt .so)")
+    return RefOracle()
