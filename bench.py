@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the Fitch/Sankoff construction pass (BASELINE.json metric: node x column updates / s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME] [--algo fitch|sankoff] [--impl reference]
+
+A "step" is one pass of the hot path (forward + backward + ordered mutation compaction) over one batch of
+synthetic columns. N=1 runs BASELINE.json configs[1] (synthetic SARS-CoV-2-like MSA, 20k leaves x 30k columns,
+random binary tree, Fitch). For N>1 (launched by torch.distributed.run, one rank per GPU) every rank owns one such
+30k-column range of an N x 30k-column alignment on the replicated tree -- per-GPU work is fixed, scaling "weak" --
+and each step ends with the column-range gather of the per-rank mutation lists to rank 0 over NCCL.
+Prints ONE JSON line (rank 0).  --impl reference times the reference's own CPU implementation instead.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="sars20k")
+    ap.add_argument("--algo", default=None)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cols", type=int, default=0, help="override the column count (debug)")
+    ap.add_argument("--leaves", type=int, default=0, help="override the leaf count (debug)")
+    ap.add_argument("--chunk-nodes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload(args):
+    from panman_b200 import synth
+
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.cols:
+        cfg["n_cols"] = args.cols
+    if args.leaves:
+        cfg["n_leaves"] = args.leaves
+    algo = args.algo or cfg["algos"][0]
+    return cfg, algo
+
+
+# ----------------------------------------------------------------------------- clocks (sampled during the timed region)
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, k), int)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bit and (r & bit) and name not in ("nvmlClocksThrottleReasonNone", "nvmlClocksThrottleReasonAll"):
+                        self.reasons.add(name.replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- reference / oracle CPU timing
+def cpu_reference_run(tree, codes_sample, parent_code_sample, algo, seconds, threads):
+    """Times the reference's own CPU implementation of the path on a bounded column sample: oracle/_ref (the
+    verbatim fitchSankoff.cpp + restated string-keyed drivers) when it was built, else the oracle port."""
+    from oracle.oracle import CHAR_OF, PortOracle, RefOracle, have_ref
+
+    n_cols = codes_sample.shape[1]
+    algo_i = 0 if algo == "fitch" else 1
+    names = tree.names()
+    if have_ref():
+        ref = RefOracle()
+
+        class T:  # the fields RefOracle.tree needs
+            pass
+
+        t = T()
+        t.n_nodes, t.names, t.parent, t.child_off, t.child_idx = tree.n_nodes, names, tree.parent, tree.child_off, tree.child_idx
+        h = ref.tree(t)
+        leaf_names = [names[v] for v in tree.leaves]
+        rows = CHAR_OF[codes_sample]
+        cons = CHAR_OF[parent_code_sample]
+
+        def run(nc):
+            t0 = time.perf_counter()
+            ref.msa_run(h, t, algo_i, leaf_names, [bytes(r[:nc]) for r in rows], bytes(cons[:nc]), "", n_threads=threads)
+            return time.perf_counter() - t0
+
+        kind = "reference"
+    else:
+        port = PortOracle()
+
+        def run(nc):
+            t0 = time.perf_counter()
+            port.run(tree, algo_i, codes_sample[:, :nc], parent_code_sample[:nc], n_threads=threads)
+            return time.perf_counter() - t0
+
+        kind = "port"
+    probe = min(n_cols, max(threads, 8))
+    dt = run(probe)
+    nc = int(min(n_cols, max(probe, probe * seconds / max(dt, 1e-6))))
+    dt = run(nc)
+    return dict(value=tree.n_nodes * nc / dt, unit="node*col/s", cores=threads, kind=kind,
+                sample=f"first {nc} columns of the workload ({tree.n_nodes} nodes), {dt:.1f} s, "
+                       f"{'string-keyed reference drivers' if kind == 'reference' else 'array port'}, {threads} threads")
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------- main arms
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from panman_b200 import synth
+
+    cfg, algo = workload(args)
+    tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    sample_cols = min(cfg["n_cols"], 2048)
+    codes4, pc = synth.simulate_msa(tree, 0, sample_cols, synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]))
+    codes = synth.unpack_nibbles(codes4, sample_cols).numpy()
+    threads = host_threads()
+    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_run(tree, codes, pc.numpy(), algo, per_step, threads)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    value = float(np.mean(vals))
+    last["value"] = value
+    line = {
+        "impl": "reference", "metric": "fitch_sankoff_node_column_updates_per_sec", "value": value, "unit": "node*col/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tree.n_nodes * cfg["n_cols"] / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16 sets / int32 costs (CPU)", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['n_leaves']} leaves x {cfg['n_cols']} columns, {cfg['kind']} tree, {algo}; "
+                               "each step = bounded column sample, rate extrapolated (columns are independent)"},
+        "cpu_baseline": last,
+        "e2e": {"value": value, "unit": "node*col/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_b200_arm(args):
+    import torch
+
+    import panman_b200 as pb
+    from panman_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libpanman_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, algo = workload(args)
+    algo_i = pb.ALGO_FITCH if algo == "fitch" else pb.ALGO_SANKOFF
+    C = cfg["n_cols"]
+    c0 = rank * C  # weak scaling: rank r owns columns [r*C, (r+1)*C) of a world*C-column alignment
+    tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    spec = synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"])
+    dev = torch.device("cuda", local)
+    codes4, pc = synth.simulate_msa(tree, c0, c0 + C, spec, device=dev)
+    ro = None
+    if algo == "sankoff":  # Sankoff runs with --reference = leaf 0
+        ro = (synth.unpack_nibbles(codes4[:1], C)[0]).to(torch.int8).contiguous()
+    torch.cuda.synchronize()
+
+    ctx = pb.Context(local)
+    if args.chunk_nodes:
+        ctx.set_option("chunk_nodes", args.chunk_nodes)
+    ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro, None, None, c0)
+
+    N = tree.n_nodes
+
+    def gather_lists():
+        """Column-range gather of the per-rank lists to rank 0 (NCCL), then concatenation per node in rank order."""
+        r = ctx.result_device()
+        n = int(r.n_mut)
+        off = torch.as_tensor(_DevArray(r.node_offsets, N + 1, "<i8"), device=dev)
+        pos = torch.as_tensor(_DevArray(r.pos, max(n, 1), "<i4"), device=dev)[:n]
+        tc = torch.as_tensor(_DevArray(r.type_code, max(n, 1), "|u1"), device=dev)[:n]
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=dev))
+        cl = counts.tolist()
+        offs = [torch.empty(N + 1, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(off, offs, dst=0)
+        if rank == 0:
+            poss = [pos] + [torch.empty(cl[k], dtype=torch.int32, device=dev) for k in range(1, world)]
+            tcs = [tc] + [torch.empty(cl[k], dtype=torch.uint8, device=dev) for k in range(1, world)]
+            ops = []
+            for k in range(1, world):
+                if cl[k]:
+                    ops += [dist.P2POp(dist.irecv, poss[k], k), dist.P2POp(dist.irecv, tcs[k], k)]
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            cnt = torch.stack([o[1:] - o[:-1] for o in offs])  # world x N
+            before = torch.cumsum(cnt, 0) - cnt
+            merged_off = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+            merged_off[1:] = torch.cumsum(cnt.sum(0), 0)
+            total = int(merged_off[-1])
+            mpos = torch.empty(total, dtype=torch.int32, device=dev)
+            mtc = torch.empty(total, dtype=torch.uint8, device=dev)
+            for k in range(world):
+                if cl[k] == 0:
+                    continue
+                shift = merged_off[:-1] + before[k] - offs[k][:-1]
+                idx = torch.repeat_interleave(shift, cnt[k]) + torch.arange(cl[k], device=dev)
+                mpos[idx] = poss[k]
+                mtc[idx] = tcs[k]
+            return merged_off, mpos, mtc
+        if n:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, pos, 0), dist.P2POp(dist.isend, tc, 0)]):
+                w.wait()
+        return None
+
+    def step():
+        t = ctx.run_resident(algo_i)
+        if world > 1:
+            gather_lists()
+        return t
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    fwd = bwd = cmp_ = tot = 0.0
+    launches = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t = step()
+        fwd += t.forward_ms
+        bwd += t.backward_ms
+        cmp_ += t.compact_ms
+        tot += t.total_ms
+        launches += t.n_launches
+    barrier()
+    elapsed = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    n_mut = ctx.download(copy=False).n_mut
+    alg_bytes = ctx.algorithmic_bytes(algo_i)
+    el = torch.tensor([elapsed, tot / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed, dev_total = float(el[0]), float(el[1])
+    K = args.steps
+    units = N * C * world
+    value = units * K / elapsed
+
+    # ---- end to end through the reference-facing C-ABI call with HOST buffers (H2D and D2H inside the timed region)
+    h_codes = torch.empty(codes4.shape, dtype=torch.uint8, pin_memory=True).copy_(codes4)
+    h_pc = torch.empty(pc.shape, dtype=torch.uint8, pin_memory=True).copy_(pc)
+    h_ro = None if ro is None else torch.empty(ro.shape, dtype=torch.int8, pin_memory=True).copy_(ro)
+    torch.cuda.synchronize()
+    e2e_steps = max(2, min(K, 5))
+    res = ctx.run_nuc(algo_i, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro, None, None, c0, 0, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = ctx.run_nuc(algo_i, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro, None, None, c0, 0, copy=False)
+        if world > 1:
+            gather_lists()
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    e2 = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+    e2e_value = units * e2e_steps / float(e2[0])
+    h2d = int(h_codes.numel() + h_pc.numel() + (0 if h_ro is None else h_ro.numel()))
+    d2h = int((N + 1) * 8 + res.n_mut * 5)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    pass_ms = (fwd + bwd + cmp_) / K
+    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.config}:{algo}")
+    except Exception:
+        pass
+    line = {
+        "metric": "fitch_sankoff_node_column_updates_per_sec", "value": value, "unit": "node*col/s", "n_gpus": world,
+        "steps": K, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16 Fitch sets as 16 bit-planes" if algo == "fitch" else "2-bit Sankoff excess as 32 bit-planes", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['n_leaves']} leaves ({N} nodes) x {C} columns per GPU, {cfg['kind']} tree, "
+                               f"{algo}, seed {cfg['seed']}; rank r owns columns [r*{C},(r+1)*{C})",
+                   "l2": "inputs larger than L2: leaf planes + set matrix = "
+                         f"{(tree.n_leaves * 0.5 + (N - tree.n_leaves) * (2 if algo == 'fitch' else 4)) * C / 1e6:.0f} MB per pass",
+                   "parallelism": f"column ranges x{world}, tree replicated, NCCL gather of mutation lists" if world > 1 else "single GPU",
+                   "n_mut_rank0": int(n_mut)},
+        "device_ms_per_step": 1e3 * dev_total / K,
+        "phases_ms": {"forward": fwd / K, "backward": bwd / K, "compact": cmp_ / K},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "node*col/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "pmb_run_nuc with pinned host buffers"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "forward + backward level launches + compaction of one pass (CUDA events on the library stream)",
+                     "algorithmic_bytes_per_pass": int(alg_bytes)},
+    }
+    if not args.no_cpu_baseline:
+        sample_cols = min(C, 512)
+        codes = synth.unpack_nibbles(codes4[:, :(sample_cols + 1) // 2], sample_cols).cpu().numpy()
+        line["cpu_baseline"] = cpu_reference_run(tree, codes, pc[:sample_cols].cpu().numpy(), algo, args.cpu_seconds, host_threads())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+/* libpanman_b200 -- C ABI of the B200-native Fitch/Sankoff construction pass of PanMAN.
+ *
+ * This is the drop-in boundary for the per-column loops of the reference's Tree constructor
+ * (reference src/panman.cpp:873-963, 1004-1233, 1381-1435, 1568-1613; later src/reroot.cpp:54-224).
+ * The reference has no plugin/FFI layer: its hot path is 19 member functions of panmanUtils::Tree
+ * (declared src/panman.hpp:846-902, defined src/fitchSankoff.cpp:5-818) called once per alignment
+ * column with std::unordered_map<std::string,...> state maps. This library replaces a whole BATCH of
+ * those per-column call triples by one call:
+ *
+ *   nucFitchForwardPass / nucFitchBackwardPass / nucFitchAssignMutations      (fitchSankoff.cpp:30-171)
+ *   nucSankoffForwardPass / nucSankoffBackwardPass / nucSankoffAssignMutations (fitchSankoff.cpp:359-531, 676-703)
+ *   blockFitch*New / blockSankoff*                                              (fitchSankoff.cpp:224-308, 707-818)
+ *
+ * Everything before (parsing, consensus, block order) and after (run-merge into NucMut, the capnp
+ * writer) stays host code; see INTEGRATION.md for the binding a maintainer adds to panman.cpp.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no allocation crosses the boundary. Inputs are borrowed for the
+ *     duration of the call; outputs are owned by the context and stay valid until the next
+ *     pmb_run_* / pmb_upload_* / pmb_destroy on that context.
+ *   - every call returns PMB_OK (0) or a negative code; text via pmb_last_error. The library never
+ *     exits or throws (the reference exit()s / asserts, e.g. fitchSankoff.cpp:505).
+ *   - a context is bound to ONE CUDA device and is not thread-safe; use one per host thread / rank.
+ *   - codes are the 4-bit IUPAC codes of reference src/panman.hpp:27-44 ('-' = 0, A1 C2 M3 G4 R5 S6 V7
+ *     T8 W9 Y10 H11 K12 D13 B14 N15); a Fitch leaf set is 1 << code (src/panman.cpp:1409-1417), a
+ *     Sankoff leaf vector is 0 at its code and SANKOFF_INF elsewhere (src/panman.cpp:1574-1582).
+ *   - record types: NS=0 (substitution), ND=1 (deletion), NI=2 (insertion)  (src/panman.hpp:46-61).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns PMB_ERR_CUDA.
+ */
+#ifndef PANMAN_B200_H
+#define PANMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmb_ctx pmb_ctx;
+
+enum {
+    PMB_OK = 0,
+    PMB_ERR_INVALID = -1,      /* bad argument / malformed tree */
+    PMB_ERR_CUDA = -2,         /* CUDA runtime failure or no device */
+    PMB_ERR_NO_TREE = -3,      /* pmb_set_tree not called */
+    PMB_ERR_SANKOFF_ROOT = -4, /* a column's root has no finite cost and no override: the reference
+                                  would fail assert(minPtr != -1), src/fitchSankoff.cpp:505 */
+    PMB_ERR_NO_INPUT = -5,     /* pmb_run_resident without pmb_upload_nuc */
+    PMB_ERR_OOM = -6,          /* device memory */
+    PMB_ERR_INTERNAL = -7      /* scheduler watchdog fired; never expected */
+};
+
+enum { PMB_ALGO_FITCH = 0, PMB_ALGO_SANKOFF = 1 };
+
+enum {
+    PMB_FLAG_WANT_STATES = 1, /* also return the assigned state of every node x column */
+    PMB_FLAG_BLOCK_MODE = 2   /* 3-state block columns (0 absent, 1 forward, 2 reverse strand):
+                                 Fitch root gets no take-lowest-bit special case (fitchSankoff.cpp:247-270),
+                                 Sankoff treats an omitted leaf as "absent" not "unknown" (:711-714).
+                                 Records come back nuc-style: NI = block insertion (code 2 => inverted),
+                                 ND = block deletion, NS = inversion (:272-308, :788-818). */
+};
+
+/* Result of one batch: per-node mutation lists, node-major, each list in ascending column order
+ * (what the reference obtains by std::sort of its per-node tuples, src/panman.cpp:1447). */
+typedef struct pmb_result {
+    int64_t n_mut;               /* total records */
+    int32_t n_nodes;
+    int32_t reserved;
+    const int64_t* node_offsets; /* n_nodes + 1; node v owns [node_offsets[v], node_offsets[v+1]) */
+    const int32_t* pos;          /* column index (col_base + local column) */
+    const uint8_t* type_code;    /* (type << 4) | code */
+    const uint8_t* states;       /* PMB_FLAG_WANT_STATES: n_nodes x n_cols codes, 0xFF = not assigned; else NULL */
+    int64_t n_cols;
+} pmb_result;
+
+/* Device-time breakdown of the last pmb_run_resident, CUDA events on the library's stream. */
+typedef struct pmb_timings {
+    float forward_ms;   /* post-order pass (all levels) */
+    float backward_ms;  /* pre-order pass + mutation detection + staging append (all levels) */
+    float compact_ms;   /* directory scan + ordered gather into the final lists */
+    float total_ms;     /* first kernel start to last kernel end */
+    int32_t n_launches; /* kernels launched by the last run */
+    int32_t n_levels;   /* dependency levels of the tree schedule */
+} pmb_timings;
+
+/* ---- lifecycle ---- */
+int pmb_create(pmb_ctx** ctx, int device);
+void pmb_destroy(pmb_ctx* ctx);
+const char* pmb_last_error(const pmb_ctx* ctx);
+/* Tuning knobs (all optional): "chunk_nodes" (internal nodes per sequential chunk), "staging_records"
+ * (initial capacity of the mutation staging pool), "use_graph" (1 = replay the level schedule as a CUDA graph). */
+int pmb_set_option(pmb_ctx* ctx, const char* key, int64_t value);
+
+/* ---- tree: replaces the Node* tree walked by every reference call ----
+ * CSR children in Newick order (reference src/panman.cpp:223-229 appends children in that order).
+ * leaf_row[v] = row of leaf v in the code matrix, -1 for internal nodes. Unary nodes and polytomies are legal.
+ * The library flattens this into a level-ordered chunk schedule replicated on the device. */
+int pmb_set_tree(pmb_ctx* ctx, int32_t n_nodes, int32_t root, const int32_t* child_offsets,
+                 const int32_t* child_index, const int32_t* leaf_row);
+
+/* ---- one batch of columns, host or device buffers in, host lists out (the end-to-end entry) ----
+ * leaf_codes_4bit : n_rows x row_stride_bytes, row-major; column c of a row is the low nibble of byte c/2 when
+ *                   c is even, the high nibble when odd. May be host or device memory (UVA decides).
+ * leaf_present    : n_rows bytes or NULL; 0 => the leaf is omitted from the state map for every column of
+ *                   this call (reference: sequences lacking a block, src/panman.cpp:1027-1030).
+ * parent_code     : n_cols; code of the consensus character = parentState handed to the root
+ *                   (src/panman.cpp:1424-1425, 1600-1606).
+ * root_override   : n_cols or NULL; -1 none, else the code the root is forced to (defaultState,
+ *                   src/panman.cpp:1057-1079, 1583-1604; src/reroot.cpp:189-190).
+ * fwd_root_ref    : n_cols or NULL; -1 none, else the forward-pass root reference code (refState,
+ *                   src/panman.cpp:1419-1420). Fitch only.
+ * col_base        : added to every emitted position (column-range sharding across GPUs). */
+int pmb_run_nuc(pmb_ctx* ctx, int algo, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit,
+                int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* parent_code,
+                const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base, int flags,
+                pmb_result* out);
+
+/* ---- the same, split so that the pass can be timed with inputs resident in HBM ----
+ * pmb_upload_nuc copies + bit-plane-packs the inputs into device memory (the "packed leaf matrix resident in
+ * HBM"); pmb_run_resident runs forward + backward + compaction on it, leaving the lists in device memory;
+ * pmb_download copies them to host memory owned by the context. pmb_run_nuc = the three in a row. */
+int pmb_upload_nuc(pmb_ctx* ctx, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit,
+                   int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* parent_code,
+                   const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base);
+int pmb_run_resident(pmb_ctx* ctx, int algo, int flags);
+int pmb_download(pmb_ctx* ctx, pmb_result* out);
+
+/* Device-side view of the last result (for an NCCL gather straight from HBM). Pointers are device memory. */
+int pmb_result_device(pmb_ctx* ctx, pmb_result* out);
+
+/* ---- introspection ---- */
+int pmb_last_timings(const pmb_ctx* ctx, pmb_timings* out);
+/* Bytes the roofline is computed on, for the resident input and `algo`:
+ * Fitch n_cols*(1.0*L + 4*I), Sankoff n_cols*(1.0*L + 8*I), plus 8 bytes per emitted record. */
+int64_t pmb_algorithmic_bytes(const pmb_ctx* ctx, int algo);
+const char* pmb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANMAN_B200_H */

@@ -1,0 +1,165 @@
+"""ctypes mirror of include/panman_b200.h (same names, argument meaning and error behaviour)."""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lib import load_library, pmb_result, pmb_timings
+
+ALGO_FITCH, ALGO_SANKOFF = 0, 1
+FLAG_WANT_STATES, FLAG_BLOCK_MODE = 1, 2
+
+
+class PanmanError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpanman_b200 error {code}: {msg}")
+        self.code = code
+
+
+@dataclass
+class Result:
+    node_offsets: np.ndarray  # int64 n_nodes+1
+    pos: np.ndarray  # int32
+    type_code: np.ndarray  # uint8 (type<<4)|code
+    states: np.ndarray = None  # uint8 n_nodes x n_cols, 0xFF = none
+
+    @property
+    def n_mut(self):
+        return int(self.node_offsets[-1])
+
+
+@dataclass
+class Timings:
+    forward_ms: float
+    backward_ms: float
+    compact_ms: float
+    total_ms: float
+    n_launches: int
+    n_levels: int
+
+
+def pack_nibbles(codes: np.ndarray) -> np.ndarray:
+    """(n_rows, n_cols) uint8 codes -> (n_rows, ceil(n_cols/2)) bytes; column c is the low nibble of byte c//2 when c is
+    even, the high nibble when odd (the pmb_run_nuc convention)."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    n_rows, n_cols = codes.shape
+    if n_cols % 2:
+        codes = np.concatenate([codes, np.zeros((n_rows, 1), np.uint8)], 1)
+    return np.ascontiguousarray((codes[:, 0::2] & 15) | ((codes[:, 1::2] & 15) << 4))
+
+
+def _ptr(x):
+    """numpy array / torch tensor (host or device) / int / None -> raw address."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+class Context:
+    """One context per CUDA device / rank (pmb_ctx). Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.pmb_create(C.byref(self.h), device)
+        if rc != 0:
+            msg = self.L.pmb_last_error(self.h).decode() if self.h else "pmb_create failed"
+            if self.h:
+                self.L.pmb_destroy(self.h)
+                self.h = None
+            raise PanmanError(rc, msg)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pmb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PanmanError(rc, self.L.pmb_last_error(self.h).decode())
+
+    def set_option(self, key: str, value: int):
+        self._check(self.L.pmb_set_option(self.h, key.encode(), int(value)))
+
+    def set_tree(self, n_nodes, root, child_off, child_idx, leaf_row):
+        co = np.ascontiguousarray(child_off, np.int32)
+        ci = np.ascontiguousarray(child_idx, np.int32)
+        lr = np.ascontiguousarray(leaf_row, np.int32)
+        self.n_nodes = int(n_nodes)
+        self._check(self.L.pmb_set_tree(self.h, int(n_nodes), int(root), _ptr(co), _ptr(ci), _ptr(lr)))
+
+    def upload(self, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None,
+               col_base=0):
+        self._check(self.L.pmb_upload_nuc(self.h, int(n_cols), int(n_rows), _ptr(codes4), int(row_stride), _ptr(leaf_present),
+                                          _ptr(parent_code), _ptr(root_override), _ptr(fwd_root_ref), int(col_base)))
+
+    def run_resident(self, algo=ALGO_FITCH, flags=0) -> Timings:
+        self._check(self.L.pmb_run_resident(self.h, int(algo), int(flags)))
+        return self.timings()
+
+    def timings(self) -> Timings:
+        t = pmb_timings()
+        self._check(self.L.pmb_last_timings(self.h, C.byref(t)))
+        return Timings(t.forward_ms, t.backward_ms, t.compact_ms, t.total_ms, t.n_launches, t.n_levels)
+
+    def algorithmic_bytes(self, algo=ALGO_FITCH) -> int:
+        return int(self.L.pmb_algorithmic_bytes(self.h, int(algo)))
+
+    def _result(self, r: pmb_result, copy=True) -> Result:
+        n, N = int(r.n_mut), int(r.n_nodes)
+
+        def view(addr, ctype, count, dtype):
+            if count == 0 or not addr:
+                return np.empty(0, dtype)
+            a = np.ctypeslib.as_array(C.cast(addr, C.POINTER(ctype)), (count,))
+            return a.copy() if copy else a
+
+        off = view(r.node_offsets, C.c_int64, N + 1, np.int64)
+        pos = view(r.pos, C.c_int32, n, np.int32)
+        tc = view(r.type_code, C.c_uint8, n, np.uint8)
+        states = None
+        if r.states:
+            states = view(r.states, C.c_uint8, N * int(r.n_cols), np.uint8).reshape(N, int(r.n_cols))
+        return Result(off, pos, tc, states)
+
+    def download(self, copy=True) -> Result:
+        r = pmb_result()
+        self._check(self.L.pmb_download(self.h, C.byref(r)))
+        return self._result(r, copy)
+
+    def result_device(self) -> pmb_result:
+        r = pmb_result()
+        self._check(self.L.pmb_result_device(self.h, C.byref(r)))
+        return r
+
+    def run_nuc(self, algo, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
+                leaf_present=None, col_base=0, flags=0, copy=True) -> Result:
+        r = pmb_result()
+        self._check(self.L.pmb_run_nuc(self.h, int(algo), int(n_cols), int(n_rows), _ptr(codes4), int(row_stride),
+                                       _ptr(leaf_present), _ptr(parent_code), _ptr(root_override), _ptr(fwd_root_ref),
+                                       int(col_base), int(flags), C.byref(r)))
+        return self._result(r, copy)
+
+    # convenience for tests: unpacked codes, numpy everywhere
+    def run_codes(self, tree, algo, codes, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None, block_mode=0,
+                  want_states=False, col_base=0) -> Result:
+        codes4 = pack_nibbles(codes)
+        n_rows, n_cols = codes.shape
+        pc = np.ascontiguousarray(parent_code, np.uint8)
+        ro = None if root_override is None else np.ascontiguousarray(root_override, np.int8)
+        fr = None if fwd_root_ref is None else np.ascontiguousarray(fwd_root_ref, np.int8)
+        lp = None if leaf_present is None else np.ascontiguousarray(leaf_present, np.uint8)
+        flags = (FLAG_WANT_STATES if want_states else 0) | (FLAG_BLOCK_MODE if block_mode else 0)
+        return self.run_nuc(algo, n_cols, n_rows, codes4, codes4.shape[1], pc, ro, fr, lp, col_base, flags)

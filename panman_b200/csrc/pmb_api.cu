@@ -1,0 +1,493 @@
+// C-ABI implementation of libpanman_b200 (see include/panman_b200.h).
+// Host side: context, device buffers, the level schedule of kernel launches, result download.
+// There is deliberately no CPU compute path here: without a device every compute call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/panman_b200.h"
+#include "pmb_kernels.cuh"
+#include "tree_program.h"
+
+using namespace pmb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct pmb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // options
+    int64_t opt_chunk_nodes = 0;      // 0 = choose from the tile count
+    int64_t opt_staging_records = 0;  // 0 = choose from the problem size
+    int64_t opt_use_graph = 0;
+
+    // tree
+    bool have_tree = false;
+    int32_t n_nodes = 0, root = -1;
+    std::vector<int32_t> child_off, child_idx, leaf_row;
+    TreeProgram prog;
+    int32_t prog_chunk_nodes = -1;
+    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks;
+
+    // resident input
+    bool have_input = false;
+    int64_t n_cols = 0, col_base = 0;
+    int32_t T = 0;
+    bool have_present = false;
+    DevBuf d_leaf_planes, d_present, d_colparams, d_tmp_codes, d_tmp_cols;
+
+    // work + result
+    DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_node_counts, d_offsets, d_pos, d_tc,
+        d_states_u8;
+    unsigned long long staging_cap = 0;
+    bool have_result = false;
+    int last_algo = 0, last_flags = 0;
+    int64_t n_mut = 0;
+    pmb_timings timings{};
+    HostBuf h_offsets, h_pos, h_tc, h_states, h_counters;
+};
+
+namespace {
+
+int fail(pmb_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+int cuda_fail(pmb_ctx* c, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return fail(c, e == cudaErrorMemoryAllocation ? PMB_ERR_OOM : PMB_ERR_CUDA, m);
+}
+
+#define PMB_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
+    } while (0)
+
+template <class T>
+int upload_vec(pmb_ctx* c, DevBuf& buf, const std::vector<T>& v) {
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    PMB_CUDA(buf.ensure(bytes));
+    if (!v.empty()) PMB_CUDA(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return PMB_OK;
+}
+
+// The chunk size trades tree-level parallelism against per-chunk scheduling overhead: aim for enough
+// (chunk x tile) warps to fill 148 SMs several times over at the widest level.
+int32_t pick_chunk_nodes(const pmb_ctx* c) {
+    if (c->opt_chunk_nodes > 0) return int32_t(std::min<int64_t>(c->opt_chunk_nodes, 1 << 30));
+    const int64_t target_warps = 148LL * 64;
+    int64_t want_chunks = std::max<int64_t>(1, (target_warps + c->T - 1) / std::max(1, c->T));
+    int64_t n_internal = 0;
+    for (int32_t v = 0; v < c->n_nodes; v++) n_internal += c->child_off[v + 1] > c->child_off[v];
+    int64_t k = n_internal / want_chunks;
+    return int32_t(std::max<int64_t>(8, std::min<int64_t>(k, 1 << 30)));
+}
+
+int ensure_program(pmb_ctx* c) {
+    int32_t k = pick_chunk_nodes(c);
+    if (k == c->prog_chunk_nodes) return PMB_OK;
+    std::string e = build_tree_program(c->n_nodes, c->root, c->child_off.data(), c->child_idx.data(), c->leaf_row.data(), k,
+                                       &c->prog);
+    if (!e.empty()) return fail(c, PMB_ERR_INVALID, e);
+    int rc;
+    if ((rc = upload_vec(c, c->d_fwd_ops, c->prog.fwd_ops))) return rc;
+    if ((rc = upload_vec(c, c->d_refs, c->prog.refs))) return rc;
+    if ((rc = upload_vec(c, c->d_bwd_ops, c->prog.bwd_ops))) return rc;
+    if ((rc = upload_vec(c, c->d_bwd_leaves, c->prog.bwd_leaves))) return rc;
+    if ((rc = upload_vec(c, c->d_chunks, c->prog.chunks))) return rc;
+    PMB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above may be rebuilt before the copies ran
+    c->prog_chunk_nodes = k;
+    return PMB_OK;
+}
+
+int launch_levels(pmb_ctx* c, const RunParams& rp, int algo, bool forward, int* n_launches) {
+    const TreeProgram& P = c->prog;
+    const int L = P.n_levels();
+    for (int i = 0; i < L; i++) {
+        int l = forward ? i : L - 1 - i;
+        int cb = P.level_chunk_begin[l], nc = P.level_chunk_begin[l + 1] - cb;
+        if (nc <= 0) continue;
+        long long warps = (long long)nc * c->T;
+        unsigned blocks = unsigned((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        dim3 block(WARPS_PER_BLOCK * 32);
+        if (algo == PMB_ALGO_FITCH) {
+            if (forward) fitch_forward_kernel<<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+            else fitch_backward_kernel<<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+        } else {
+            if (!forward) sankoff_backward_kernel<<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+            else if (P.max_arity <= 3) sankoff_forward_kernel<2><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+            else if (P.max_arity <= 15) sankoff_forward_kernel<4><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+            else if (P.max_arity <= 255) sankoff_forward_kernel<8><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+            else sankoff_forward_kernel<20><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+        }
+        (*n_launches)++;
+    }
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pmb_version(void) { return "panman_b200 0.1 (sm_100a)"; }
+
+int pmb_create(pmb_ctx** out, int device) {
+    if (!out) return PMB_ERR_INVALID;
+    *out = nullptr;
+    pmb_ctx* c = new pmb_ctx();
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess) {
+        // keep the context so that pmb_last_error can say why; every compute call will refuse to run
+        c->err = std::string("no usable CUDA device: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        c->stream = nullptr;
+        *out = c;
+        return PMB_ERR_CUDA;
+    }
+    *out = c;
+    return PMB_OK;
+}
+
+void pmb_destroy(pmb_ctx* c) {
+    if (!c) return;
+    if (c->stream) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_leaf_planes,
+                          &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
+                          &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
+                          &c->d_pos, &c->d_tc, &c->d_states_u8})
+            b->release();
+        for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters}) b->release();
+        for (int i = 0; i < 4; i++)
+            if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+const char* pmb_last_error(const pmb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
+    if (!c || !key) return PMB_ERR_INVALID;
+    std::string k(key);
+    if (k == "chunk_nodes") c->opt_chunk_nodes = value;
+    else if (k == "staging_records") c->opt_staging_records = value;
+    else if (k == "use_graph") c->opt_use_graph = value;
+    else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
+    return PMB_OK;
+}
+
+int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child_offsets, const int32_t* child_index,
+                 const int32_t* leaf_row) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device (pmb_create failed); there is no CPU fallback");
+    if (n_nodes < 2 || !child_offsets || !child_index || !leaf_row) return fail(c, PMB_ERR_INVALID, "bad tree arguments");
+    // validate with a throw-away build (chunk size does not matter for validity)
+    TreeProgram probe;
+    std::string e = build_tree_program(n_nodes, root, child_offsets, child_index, leaf_row, 64, &probe);
+    if (!e.empty()) return fail(c, PMB_ERR_INVALID, e);
+    c->n_nodes = n_nodes;
+    c->root = root;
+    c->child_off.assign(child_offsets, child_offsets + n_nodes + 1);
+    c->child_idx.assign(child_index, child_index + child_offsets[n_nodes]);
+    c->leaf_row.assign(leaf_row, leaf_row + n_nodes);
+    c->prog = std::move(probe);
+    c->prog_chunk_nodes = -1;  // (re)built for the tile count at upload time
+    c->have_tree = true;
+    c->have_input = false;
+    c->have_result = false;
+    return PMB_OK;
+}
+
+int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                   const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                   const int8_t* fwd_root_ref, int64_t col_base) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
+    if (n_cols <= 0 || !leaf_codes_4bit || !parent_code) return fail(c, PMB_ERR_INVALID, "bad input arguments");
+    if (n_rows != c->prog.n_rows) return fail(c, PMB_ERR_INVALID, "n_rows does not match the tree's leaf count");
+    if (row_stride_bytes < (n_cols + 1) / 2) return fail(c, PMB_ERR_INVALID, "row_stride_bytes too small");
+    if (n_cols > (int64_t(1) << 40)) return fail(c, PMB_ERR_INVALID, "n_cols too large");
+    PMB_CUDA(cudaSetDevice(c->device));
+    c->have_input = false;
+    c->have_result = false;
+    c->staging_cap = 0;
+    c->n_cols = n_cols;
+    c->col_base = col_base;
+    c->T = int32_t((n_cols + TILE_COLS - 1) / TILE_COLS);
+    int rc = ensure_program(c);
+    if (rc) return rc;
+    const size_t plane_bytes = size_t(n_rows) * c->T * 32 * sizeof(uint4);
+    PMB_CUDA(c->d_leaf_planes.ensure(plane_bytes));
+    // rows in slabs so the temporary nibble buffer stays bounded
+    const size_t slab_budget = size_t(1) << 30;
+    int32_t slab_rows = int32_t(std::max<size_t>(1, std::min<size_t>(size_t(n_rows), slab_budget / size_t(row_stride_bytes))));
+    PMB_CUDA(c->d_tmp_codes.ensure(size_t(slab_rows) * size_t(row_stride_bytes)));
+    for (int32_t r0 = 0; r0 < n_rows; r0 += slab_rows) {
+        int32_t nr = std::min(slab_rows, n_rows - r0);
+        PMB_CUDA(cudaMemcpyAsync(c->d_tmp_codes.p, leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes),
+                                 size_t(nr) * size_t(row_stride_bytes), cudaMemcpyDefault, c->stream));
+        long long total = (long long)nr * c->T * 32;
+        unsigned blocks = unsigned((total + 255) / 256);
+        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tmp_codes.as<uint8_t>(), row_stride_bytes, nr, n_cols, c->T,
+                                                          c->d_leaf_planes.as<uint4>() + size_t(r0) * c->T * 32);
+    }
+    PMB_CUDA(cudaGetLastError());
+    c->have_present = leaf_present != nullptr;
+    if (leaf_present) {
+        PMB_CUDA(c->d_present.ensure(size_t(n_rows)));
+        PMB_CUDA(cudaMemcpyAsync(c->d_present.p, leaf_present, size_t(n_rows), cudaMemcpyDefault, c->stream));
+    }
+    PMB_CUDA(c->d_tmp_cols.ensure(size_t(n_cols) * 3));
+    uint8_t* t = c->d_tmp_cols.as<uint8_t>();
+    PMB_CUDA(cudaMemcpyAsync(t, parent_code, size_t(n_cols), cudaMemcpyDefault, c->stream));
+    if (root_override) PMB_CUDA(cudaMemcpyAsync(t + n_cols, root_override, size_t(n_cols), cudaMemcpyDefault, c->stream));
+    if (fwd_root_ref) PMB_CUDA(cudaMemcpyAsync(t + 2 * n_cols, fwd_root_ref, size_t(n_cols), cudaMemcpyDefault, c->stream));
+    PMB_CUDA(c->d_colparams.ensure(size_t(c->T) * 128 * sizeof(uint4)));
+    {
+        long long threads = (long long)c->T * 32 * 32;
+        unsigned blocks = unsigned((threads + 255) / 256);
+        pack_colparams_kernel<<<blocks, 256, 0, c->stream>>>(t, root_override ? reinterpret_cast<const int8_t*>(t + n_cols) : nullptr,
+                                                             fwd_root_ref ? reinterpret_cast<const int8_t*>(t + 2 * n_cols) : nullptr,
+                                                             n_cols, c->T, c->d_colparams.as<uint4>());
+    }
+    PMB_CUDA(cudaGetLastError());
+    PMB_CUDA(cudaStreamSynchronize(c->stream));  // inputs were borrowed: they may be released on return
+    c->have_input = true;
+    return PMB_OK;
+}
+
+int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
+    if (!c->have_input) return fail(c, PMB_ERR_NO_INPUT, "pmb_upload_nuc has not been called");
+    if (algo != PMB_ALGO_FITCH && algo != PMB_ALGO_SANKOFF) return fail(c, PMB_ERR_INVALID, "unknown algo");
+    PMB_CUDA(cudaSetDevice(c->device));
+    c->have_result = false;
+    const TreeProgram& P = c->prog;
+    const size_t T = size_t(c->T);
+    const size_t set_bytes_per = (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
+    PMB_CUDA(c->d_sets.ensure(size_t(P.n_internal) * T * set_bytes_per));
+    PMB_CUDA(c->d_fstore.ensure(std::max<size_t>(16, size_t(P.n_fslots) * T * 64 * sizeof(uint4))));
+    const bool want_states = flags & PMB_FLAG_WANT_STATES;
+    if (want_states) PMB_CUDA(c->d_states_planes.ensure(size_t(P.n_nodes) * T * 64 * sizeof(uint4)));
+    PMB_CUDA(c->d_dir.ensure(size_t(P.n_nodes) * T * sizeof(unsigned long long)));
+    PMB_CUDA(c->d_counters.ensure(64));
+    PMB_CUDA(c->h_counters.ensure(64));
+    PMB_CUDA(c->d_node_counts.ensure(size_t(P.n_nodes) * sizeof(unsigned long long)));
+    PMB_CUDA(c->d_offsets.ensure(size_t(P.n_nodes + 1) * sizeof(long long)));
+    if (c->staging_cap == 0) {
+        unsigned long long cells = (unsigned long long)P.n_nodes * (unsigned long long)c->n_cols;
+        unsigned long long cap = c->opt_staging_records > 0 ? (unsigned long long)c->opt_staging_records
+                                                            : std::max<unsigned long long>(1ull << 20, cells / 32);
+        c->staging_cap = cap;
+    }
+
+    RunParams rp{};
+    rp.fwd_ops = c->d_fwd_ops.as<FwdOp>();
+    rp.refs = c->d_refs.as<uint32_t>();
+    rp.bwd_ops = c->d_bwd_ops.as<BwdOp>();
+    rp.bwd_leaves = c->d_bwd_leaves.as<BwdLeaf>();
+    rp.chunks = c->d_chunks.as<Chunk>();
+    rp.leaf_planes = c->d_leaf_planes.as<uint4>();
+    rp.leaf_present = c->have_present ? c->d_present.as<uint8_t>() : nullptr;
+    rp.sets = c->d_sets.as<uint4>();
+    rp.fstore = c->d_fstore.as<uint4>();
+    rp.colparams = c->d_colparams.as<uint4>();
+    rp.states = want_states ? c->d_states_planes.as<uint4>() : nullptr;
+    rp.dir = c->d_dir.as<unsigned long long>();
+    rp.pool_count = c->d_counters.as<unsigned long long>();
+    rp.error = reinterpret_cast<unsigned int*>(c->d_counters.as<unsigned long long>() + 1);
+    rp.T = c->T;
+    rp.flags = ((flags & PMB_FLAG_BLOCK_MODE) ? RUN_BLOCK_MODE : 0) | (want_states ? RUN_WANT_STATES : 0);
+
+    int n_launches = 0;
+    PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    int rc = launch_levels(c, rp, algo, true, &n_launches);
+    if (rc) return rc;
+    PMB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    for (int attempt = 0;; attempt++) {
+        PMB_CUDA(c->d_staging.ensure(size_t(c->staging_cap) * sizeof(uint16_t)));
+        PMB_CUDA(c->d_pos.ensure(size_t(c->staging_cap) * sizeof(int32_t)));
+        PMB_CUDA(c->d_tc.ensure(size_t(c->staging_cap)));
+        rp.staging = c->d_staging.as<uint16_t>();
+        rp.staging_cap = c->staging_cap;
+        PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, size_t(P.n_nodes) * T * sizeof(unsigned long long), c->stream));
+        unsigned int init[4] = {0, 0, 0, 0xFFFFFFFFu};  // pool_count (64 bit), error flags, first bad column
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = launch_levels(c, rp, algo, false, &n_launches))) return rc;
+        PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        {
+            unsigned blocks = unsigned(((long long)P.n_nodes * 32 + 255) / 256);
+            node_count_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, P.n_nodes, c->T, c->d_node_counts.as<unsigned long long>());
+            scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_node_counts.as<unsigned long long>(), P.n_nodes, c->d_offsets.as<long long>());
+            gather_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, rp.staging, c->d_offsets.as<long long>(), P.n_nodes, c->T,
+                                                         c->col_base, c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>());
+            n_launches += 3;
+        }
+        PMB_CUDA(cudaGetLastError());
+        PMB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned long long total = *c->h_counters.as<unsigned long long>();
+        unsigned int eflags = c->h_counters.as<unsigned int>()[2], ecol = c->h_counters.as<unsigned int>()[3];
+        if (eflags & 1u) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "Sankoff root has no finite cost at column %lld and no root override was given",
+                     (long long)ecol + (long long)c->col_base);
+            return fail(c, PMB_ERR_SANKOFF_ROOT, buf);
+        }
+        if (total > c->staging_cap) {  // denser than provisioned: size exactly and redo the backward pass
+            if (attempt >= 2) return fail(c, PMB_ERR_INTERNAL, "staging pool overflow persisted");
+            c->staging_cap = total;
+            continue;
+        }
+        c->n_mut = int64_t(total);
+        break;
+    }
+    PMB_CUDA(cudaEventElapsedTime(&c->timings.forward_ms, c->ev[0], c->ev[1]));
+    PMB_CUDA(cudaEventElapsedTime(&c->timings.backward_ms, c->ev[1], c->ev[2]));
+    PMB_CUDA(cudaEventElapsedTime(&c->timings.compact_ms, c->ev[2], c->ev[3]));
+    PMB_CUDA(cudaEventElapsedTime(&c->timings.total_ms, c->ev[0], c->ev[3]));
+    c->timings.n_launches = n_launches;
+    c->timings.n_levels = P.n_levels();
+    c->last_algo = algo;
+    c->last_flags = flags;
+    c->have_result = true;
+    return PMB_OK;
+}
+
+int pmb_result_device(pmb_ctx* c, pmb_result* out) {
+    if (!c || !out) return PMB_ERR_INVALID;
+    if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
+    out->n_mut = c->n_mut;
+    out->n_nodes = c->prog.n_nodes;
+    out->reserved = 0;
+    out->node_offsets = reinterpret_cast<const int64_t*>(c->d_offsets.p);
+    out->pos = c->d_pos.as<int32_t>();
+    out->type_code = c->d_tc.as<uint8_t>();
+    out->states = nullptr;
+    out->n_cols = c->n_cols;
+    return PMB_OK;
+}
+
+int pmb_download(pmb_ctx* c, pmb_result* out) {
+    if (!c || !out) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
+    PMB_CUDA(cudaSetDevice(c->device));
+    const size_t n = size_t(c->n_mut), N = size_t(c->prog.n_nodes);
+    PMB_CUDA(c->h_offsets.ensure((N + 1) * sizeof(int64_t)));
+    PMB_CUDA(c->h_pos.ensure(std::max<size_t>(n, 1) * sizeof(int32_t)));
+    PMB_CUDA(c->h_tc.ensure(std::max<size_t>(n, 1)));
+    PMB_CUDA(cudaMemcpyAsync(c->h_offsets.p, c->d_offsets.p, (N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (n) {
+        PMB_CUDA(cudaMemcpyAsync(c->h_pos.p, c->d_pos.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_tc.p, c->d_tc.p, n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    out->states = nullptr;
+    if (c->last_flags & PMB_FLAG_WANT_STATES) {
+        const size_t cells = N * size_t(c->n_cols);
+        PMB_CUDA(c->d_states_u8.ensure(cells));
+        PMB_CUDA(c->h_states.ensure(cells));
+        unsigned blocks = unsigned((cells + 255) / 256);
+        unpack_states_kernel<<<blocks, 256, 0, c->stream>>>(c->d_states_planes.as<uint4>(), c->prog.n_nodes, c->n_cols, c->T,
+                                                            c->d_states_u8.as<uint8_t>());
+        PMB_CUDA(cudaGetLastError());
+        PMB_CUDA(cudaMemcpyAsync(c->h_states.p, c->d_states_u8.p, cells, cudaMemcpyDeviceToHost, c->stream));
+        out->states = c->h_states.as<uint8_t>();
+    }
+    PMB_CUDA(cudaStreamSynchronize(c->stream));
+    out->n_mut = c->n_mut;
+    out->n_nodes = c->prog.n_nodes;
+    out->reserved = 0;
+    out->node_offsets = c->h_offsets.as<int64_t>();
+    out->pos = c->h_pos.as<int32_t>();
+    out->type_code = c->h_tc.as<uint8_t>();
+    out->n_cols = c->n_cols;
+    return PMB_OK;
+}
+
+int pmb_run_nuc(pmb_ctx* c, int algo, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                const int8_t* fwd_root_ref, int64_t col_base, int flags, pmb_result* out) {
+    int rc = pmb_upload_nuc(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override,
+                            fwd_root_ref, col_base);
+    if (rc) return rc;
+    if ((rc = pmb_run_resident(c, algo, flags))) return rc;
+    return pmb_download(c, out);
+}
+
+int pmb_last_timings(const pmb_ctx* c, pmb_timings* out) {
+    if (!c || !out) return PMB_ERR_INVALID;
+    *out = c->timings;
+    return PMB_OK;
+}
+
+int64_t pmb_algorithmic_bytes(const pmb_ctx* c, int algo) {
+    if (!c || !c->have_tree || !c->have_input) return 0;
+    const int64_t L = c->prog.n_rows, I = c->prog.n_internal;
+    const int64_t per_col = L + (algo == PMB_ALGO_SANKOFF ? 8 : 4) * I;
+    return c->n_cols * per_col + 8 * (c->have_result ? c->n_mut : 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,492 @@
+// sm_100a kernels of libpanman_b200: level-synchronous Fitch / Sankoff passes over bit-plane matrices,
+// mutation staging with warp-ballot + prefix-sum compaction, ordered gather, and the ingest packers.
+//
+// Work decomposition: one WARP owns (chunk of the tree) x (tile of 1024 columns). Lane l holds, for every
+// node it touches, one 32-bit word per bit-plane = columns [tile*1024 + l*32, +32). All HBM traffic is
+// 128-bit per lane, 512 contiguous bytes per warp instruction:
+//   leaf matrix   uint4 [row][tile][lane]            4 code planes            (0.5 B / column)
+//   set matrix    uint4 [op][tile][J][lane]          J=4 Fitch (16 planes),   (2 B / column)
+//                                                    J=8 Sankoff (G,H planes) (4 B / column)
+// Reference semantics implemented here: src/fitchSankoff.cpp:30-171 (nuc Fitch), :224-308 (block Fitch),
+// :359-531 + :676-703 (nuc Sankoff), :707-818 (block Sankoff); see plane_math.h for the per-op logic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plane_math.h"
+#include "tree_program.h"
+
+namespace pmb {
+
+constexpr int TILE_COLS = 1024;
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+enum : int { RUN_BLOCK_MODE = 1, RUN_WANT_STATES = 2 };
+
+struct RunParams {
+    const FwdOp* fwd_ops;
+    const uint32_t* refs;
+    const BwdOp* bwd_ops;
+    const BwdLeaf* bwd_leaves;
+    const Chunk* chunks;
+    const uint4* leaf_planes;
+    const uint8_t* leaf_present;  // device, n_rows bytes, or nullptr = all present
+    uint4* sets;
+    uint4* fstore;                // [fslot][tile][2][lane]
+    const uint4* colparams;       // [tile][4][lane]: parent code, override code, fwd ref code, {ov_valid, ref_valid, col_valid, 0}
+    uint4* states;                // [node][tile][2][lane] or nullptr
+    unsigned long long* dir;      // [node][tile]: (staging base << 11) | count
+    uint16_t* staging;
+    unsigned long long* pool_count;
+    unsigned long long staging_cap;
+    unsigned int* error;          // [0] flags, [1] first offending column
+    int T;
+    int flags;
+    long long col_base_tile0;     // unused by kernels that emit tile-local columns; kept for diagnostics
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint4 ld_l2(const uint4* p) { return __ldcg(p); }
+
+__device__ __forceinline__ void load_planes16(const uint4* base, int lane, uint32_t S[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint4 v = ld_l2(base + j * 32 + lane);
+        S[4 * j + 0] = v.x; S[4 * j + 1] = v.y; S[4 * j + 2] = v.z; S[4 * j + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void store_planes16(uint4* base, int lane, const uint32_t S[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) base[j * 32 + lane] = make_uint4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
+}
+
+__device__ __forceinline__ bool warp_item(const RunParams& p, int chunk_begin, int n_chunks, int& chunk, int& tile, int& lane) {
+    long long warp = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    lane = threadIdx.x & 31;
+    if (warp >= (long long)n_chunks * p.T) return false;
+    chunk = chunk_begin + int(warp / p.T);
+    tile = int(warp % p.T);
+    return true;
+}
+
+__device__ __forceinline__ uint32_t leaf_present_mask(const RunParams& p, int row) {
+    if (p.leaf_present == nullptr) return FULL;
+    return __ldg(p.leaf_present + row) ? FULL : 0u;
+}
+
+// ------------------------------------------------------------------ mutation staging
+// Appends the records of one (node, tile) in ascending column order: warp ballot to skip the common empty
+// case, shuffle prefix sum over per-lane popcounts, one atomic reservation per warp.
+// Record: column-in-tile (10 bits) | code << 10 | type << 14.
+__device__ __forceinline__ void emit(const RunParams& p, int node, int tile, int lane, uint32_t mut, const uint32_t P[4],
+                                     const uint32_t F[4]) {
+    if (__ballot_sync(FULL, mut != 0) == 0) return;
+    int cnt = __popc(mut);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    int total = __shfl_sync(FULL, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(p.pool_count, (unsigned long long)total);
+        p.dir[(size_t)node * p.T + tile] = (base << 11) | (unsigned long long)total;
+    }
+    base = __shfl_sync(FULL, base, 0);
+    if (base + (unsigned long long)total > p.staging_cap) return;  // host grows the pool and reruns the pass
+    uint32_t t0, t1;
+    mutation_type(P, F, t0, t1);
+    uint16_t* dst = p.staging + base + (incl - cnt);
+    uint32_t m = mut;
+    while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        uint32_t code = ((F[0] >> b) & 1u) | (((F[1] >> b) & 1u) << 1) | (((F[2] >> b) & 1u) << 2) | (((F[3] >> b) & 1u) << 3);
+        uint32_t type = ((t0 >> b) & 1u) | (((t1 >> b) & 1u) << 1);
+        *dst++ = uint16_t((lane * 32 + b) | (code << 10) | (type << 14));
+    }
+}
+
+__device__ __forceinline__ void store_state(const RunParams& p, int node, int tile, int lane, const uint32_t F[4], uint32_t vis) {
+    uint4* s = p.states + ((size_t)node * p.T + tile) * 64;
+    s[lane] = make_uint4(F[0], F[1], F[2], F[3]);
+    s[32 + lane] = make_uint4(vis, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------ Fitch forward
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
+    int chunk, tile, lane;
+    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
+    const Chunk ck = p.chunks[chunk];
+    const size_t T = p.T;
+    uint32_t acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0;
+    for (int op = ck.op_begin; op < ck.op_end; op++) {
+        const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));  // ref_begin, n_refs, flags, bits
+        FitchFold fold;
+        fold.reset();
+        for (int r = 0; r < f.y; r++) {
+            const uint32_t ref = __ldg(p.refs + f.x + r);
+            const uint32_t kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+            if (kind == REF_LEAF) {
+                uint4 c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+                uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                fold.add_leaf(cc, leaf_present_mask(p, idx));
+            } else if (kind == REF_ACC) {
+                fold.add_set(acc);
+            } else {
+                uint32_t S[16];
+                load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
+                fold.add_set(S);
+            }
+        }
+        fold.finish(acc);
+        if ((f.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
+            // refState: the root's forward value is replaced (fitchSankoff.cpp:45-47)
+            const uint4* cp = p.colparams + (size_t)tile * 128;
+            uint4 rc = __ldg(cp + 64 + lane);
+            uint32_t rv = __ldg(cp + 96 + lane).y;
+            uint32_t r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
+            decode16(r4, d);
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[k] = (rv & d[k]) | (~rv & acc[k]);
+        }
+        store_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, acc);
+    }
+}
+
+// ------------------------------------------------------------------ Fitch backward + mutation detection
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
+    int chunk, tile, lane;
+    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
+    const Chunk ck = p.chunks[chunk];
+    const size_t T = p.T;
+    uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
+    for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
+        const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));      // node, parent_ref, fslot_out, leaf_begin
+        const int4 b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);  // n_leaves, flags
+        uint32_t S[16];
+        load_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, S);
+        uint32_t P[4], F[4], vis;
+        if (b0.y == PARENT_ROOT) {
+            const uint4* cp = p.colparams + (size_t)tile * 128;
+            uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
+            P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
+            uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w};
+            const uint32_t ov_valid = fl.x & fl.z, colmask = fl.z;
+            if (p.flags & RUN_BLOCK_MODE) {
+                // blockFitchBackwardPassNew: the root is treated like any node with parentState (:249-263)
+                uint32_t v0;
+                fitch_assign(S, P, colmask, F, v0);
+                vis = (v0 | ov_valid) & colmask;
+#pragma unroll
+                for (int k = 0; k < 4; k++) F[k] = ((ov_valid & o4[k]) | (~ov_valid & F[k])) & vis;
+            } else {
+                fitch_assign_root(S, o4, ov_valid, colmask, F, vis);
+            }
+        } else {
+            uint32_t pvis;
+            if (b0.y == PARENT_ACC) {
+                P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
+                pvis = accVis;
+            } else {
+                const uint4* fs = p.fstore + ((size_t)b0.y * T + tile) * 64;
+                uint4 a = ld_l2(fs + lane);
+                pvis = ld_l2(fs + 32 + lane).x;
+                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
+            }
+            fitch_assign(S, P, pvis, F, vis);
+        }
+        emit(p, b0.x, tile, lane, vis & differs4(F, P), P, F);
+        if (b0.z >= 0) {
+            uint4* fs = p.fstore + ((size_t)b0.z * T + tile) * 64;
+            fs[lane] = make_uint4(F[0], F[1], F[2], F[3]);
+            fs[32 + lane] = make_uint4(vis, 0, 0, 0);
+        }
+        if (p.states) store_state(p, b0.x, tile, lane, F, vis);
+        for (int l = 0; l < b1.x; l++) {
+            const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + b0.w + l));  // row, node
+            uint4 c = ld_stream(p.leaf_planes + ((size_t)lf.x * T + tile) * 32 + lane);
+            uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            // a present leaf's set is one-hot: assigned state = its own code wherever the parent was assigned
+            const uint32_t lvis = vis & leaf_present_mask(p, lf.x);
+            emit(p, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
+            if (p.states) {
+                uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
+                store_state(p, lf.y, tile, lane, m4, lvis);
+            }
+        }
+        accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
+        accVis = vis;
+    }
+}
+
+// ------------------------------------------------------------------ Sankoff forward
+template <int B>
+__device__ __forceinline__ void sankoff_forward_op(const RunParams& p, const int4 f, int tile, int lane, uint32_t accG[16],
+                                                   uint32_t accH[16]) {
+    const size_t T = p.T;
+    SankoffFold<B> fold;
+    fold.reset();
+    for (int r = 0; r < f.y; r++) {
+        const uint32_t ref = __ldg(p.refs + f.x + r);
+        const uint32_t kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+        if (kind == REF_LEAF) {
+            uint4 c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+            uint32_t present = leaf_present_mask(p, idx);
+            uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            if ((p.flags & RUN_BLOCK_MODE) && !present) {  // omitted block leaf = "absent" state (:711-714)
+                cc[0] = cc[1] = cc[2] = cc[3] = 0;
+                present = FULL;
+            }
+            fold.add_leaf(cc, present);
+        } else if (kind == REF_ACC) {
+            fold.add_set(accG, sankoff_none(accG, accH));
+        } else {
+            const uint4* base = p.sets + ((size_t)idx * T + tile) * 256;
+            uint32_t G[16];
+            load_planes16(base, lane, G);
+            uint32_t h0 = ld_l2(base + 128 + lane).x;
+            fold.add_set(G, h0 & ~G[0]);
+        }
+    }
+    fold.finish(accG, accH);
+}
+
+// MAXB = widest child counter any op of this tree needs (2: up to 3 children, 4: 15, 8: 255, 20: more), so
+// that binary trees do not pay registers for polytomy paths.
+template <int MAXB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
+    int chunk, tile, lane;
+    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
+    const Chunk ck = p.chunks[chunk];
+    const size_t T = p.T;
+    uint32_t accG[16], accH[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
+    for (int op = ck.op_begin; op < ck.op_end; op++) {
+        const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+        if (MAXB == 2 || f.w == 2) sankoff_forward_op<2>(p, f, tile, lane, accG, accH);
+        else if (MAXB == 4 || f.w == 4) sankoff_forward_op<4>(p, f, tile, lane, accG, accH);
+        else if (MAXB == 8 || f.w == 8) sankoff_forward_op<8>(p, f, tile, lane, accG, accH);
+        else sankoff_forward_op<20>(p, f, tile, lane, accG, accH);
+        uint4* base = p.sets + ((size_t)op * T + tile) * 256;
+        store_planes16(base, lane, accG);
+        store_planes16(base + 128, lane, accH);
+    }
+}
+
+// ------------------------------------------------------------------ Sankoff backward + mutation detection
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
+    int chunk, tile, lane;
+    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
+    const Chunk ck = p.chunks[chunk];
+    const size_t T = p.T;
+    uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
+    for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
+        const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
+        const int4 b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
+        uint32_t G[16], H[16];
+        const uint4* base = p.sets + ((size_t)op * T + tile) * 256;
+        load_planes16(base, lane, G);
+        load_planes16(base + 128, lane, H);
+        uint32_t P[4], F[4], vis;
+        if (b0.y == PARENT_ROOT) {
+            const uint4* cp = p.colparams + (size_t)tile * 128;
+            uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
+            P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
+            uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w}, undefined;
+            sankoff_assign_root(G, H, o4, fl.x & fl.z, fl.z, F, vis, undefined);
+            if (undefined) {  // reference: assert(minPtr != -1), fitchSankoff.cpp:505 (block variant returns, :754-757)
+                if (!(p.flags & RUN_BLOCK_MODE)) {
+                    atomicOr(p.error, 1u);
+                    atomicMin(p.error + 1, (unsigned)(tile * TILE_COLS + lane * 32 + (__ffs(undefined) - 1)));
+                }
+            }
+        } else {
+            uint32_t pvis;
+            if (b0.y == PARENT_ACC) {
+                P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
+                pvis = accVis;
+            } else {
+                const uint4* fs = p.fstore + ((size_t)b0.y * T + tile) * 64;
+                uint4 a = ld_l2(fs + lane);
+                pvis = ld_l2(fs + 32 + lane).x;
+                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
+            }
+            sankoff_assign(G, H, P, pvis, F, vis);
+        }
+        emit(p, b0.x, tile, lane, vis & differs4(F, P), P, F);
+        if (b0.z >= 0) {
+            uint4* fs = p.fstore + ((size_t)b0.z * T + tile) * 64;
+            fs[lane] = make_uint4(F[0], F[1], F[2], F[3]);
+            fs[32 + lane] = make_uint4(vis, 0, 0, 0);
+        }
+        if (p.states) store_state(p, b0.x, tile, lane, F, vis);
+        for (int l = 0; l < b1.x; l++) {
+            const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + b0.w + l));
+            uint4 c = ld_stream(p.leaf_planes + ((size_t)lf.x * T + tile) * 32 + lane);
+            uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            uint32_t present = leaf_present_mask(p, lf.x);
+            if ((p.flags & RUN_BLOCK_MODE) && !present) {
+                cc[0] = cc[1] = cc[2] = cc[3] = 0;
+                present = FULL;
+            }
+            // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
+            const uint32_t lvis = vis & present;
+            emit(p, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
+            if (p.states) {
+                uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
+                store_state(p, lf.y, tile, lane, m4, lvis);
+            }
+        }
+        accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
+        accVis = vis;
+    }
+}
+
+// ------------------------------------------------------------------ ordered compaction
+// 1) per-node totals from the (node, tile) directory
+__global__ void node_count_kernel(const unsigned long long* dir, int n_nodes, int T, unsigned long long* counts) {
+    int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    unsigned long long s = 0;
+    for (int t = lane; t < T; t += 32) s += dir[(size_t)node * T + t] & 0x7FFull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(FULL, s, d);
+    if (lane == 0) counts[node] = s;
+}
+
+// 2) exclusive scan of n values by ONE block (n_nodes is at most a few hundred thousand): each thread owns a
+//    contiguous segment; block-wide scan of the segment sums through shared memory.
+__global__ void __launch_bounds__(1024) scan_kernel(const unsigned long long* counts, int n, long long* offsets) {
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x;
+    const int seg = (n + 1023) / 1024;
+    const int b = min(n, tid * seg), e = min(n, b + seg);
+    unsigned long long s = 0;
+    for (int i = b; i < e; i++) s += counts[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned long long t = tid >= d ? part[tid - d] : 0;
+        __syncthreads();
+        part[tid] += t;
+        __syncthreads();
+    }
+    unsigned long long run = part[tid] - s;
+    for (int i = b; i < e; i++) {
+        offsets[i] = (long long)run;
+        run += counts[i];
+    }
+    if (tid == 1023) offsets[n] = (long long)part[1023];
+}
+
+// 3) gather: a warp walks one node's tiles in order and copies each staged segment to its final place.
+__global__ void gather_kernel(const unsigned long long* dir, const uint16_t* staging, const long long* offsets, int n_nodes,
+                              int T, long long col_base, int32_t* pos, uint8_t* type_code) {
+    int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    long long run = offsets[node];
+    if (offsets[node + 1] == run) return;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        int t = t0 + lane;
+        unsigned long long d = t < T ? dir[(size_t)node * T + t] : 0ull;
+        int cnt = int(d & 0x7FFull);
+        unsigned has = __ballot_sync(FULL, cnt != 0);
+        while (has) {
+            int src = __ffs(has) - 1;
+            has &= has - 1;
+            unsigned long long sd = __shfl_sync(FULL, d, src);
+            int n = int(sd & 0x7FFull);
+            const uint16_t* s = staging + (sd >> 11);
+            long long cb = col_base + (long long)(t0 + src) * TILE_COLS;
+            for (int i = lane; i < n; i += 32) {
+                uint32_t r = s[i];
+                pos[run + i] = int32_t(cb + (r & 1023u));
+                type_code[run + i] = uint8_t(((r >> 14) << 4) | ((r >> 10) & 15u));
+            }
+            run += n;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ingest
+// nibble-packed rows -> code planes. One thread per (row, 32-column group).
+__global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, int n_rows, long long n_cols, int T, uint4* planes) {
+    const long long groups = (long long)T * 32;  // 32-column groups per row, padded to whole tiles
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * n_rows) return;
+    const long long row = idx / groups, g = idx % groups;
+    uint32_t pl[4] = {0, 0, 0, 0};
+    const uint8_t* src = codes + (size_t)row * row_stride;
+    long long c0 = g * 32;
+    for (int w = 0; w < 4; w++) {  // 8 columns = 4 bytes per step
+        uint32_t x = 0;
+        long long cb = c0 + w * 8;
+        if (cb < n_cols) {
+            long long byte = cb >> 1;
+            long long ncol = min(n_cols, cb + 8) - cb;
+            long long nbytes = (ncol + 1) >> 1;
+            for (int k = 0; k < nbytes; k++) x |= uint32_t(src[byte + k]) << (8 * k);
+            if (ncol < 8) x &= (1u << (4 * ncol)) - 1u;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            uint32_t y = (x >> b) & 0x11111111u;       // bit b of each of the 8 nibbles, at stride 4
+            y = (y | (y >> 3)) & 0x03030303u;
+            y = (y | (y >> 6)) & 0x000F000Fu;
+            y = (y | (y >> 12)) & 0xFFu;
+            pl[b] |= y << (8 * w);
+        }
+    }
+    planes[idx] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// per-column parameters -> planes; one warp per 32-column group (ballot builds the planes)
+__global__ void pack_colparams_kernel(const uint8_t* parent_code, const int8_t* root_override, const int8_t* fwd_root_ref,
+                                      long long n_cols, int T, uint4* colparams) {
+    long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int l = threadIdx.x & 31;
+    if (g >= (long long)T * 32) return;
+    long long c = g * 32 + l;
+    bool valid = c < n_cols;
+    int pc = valid ? parent_code[c] & 15 : 0;
+    int ov = (valid && root_override) ? root_override[c] : -1;
+    int fr = (valid && fwd_root_ref) ? fwd_root_ref[c] : -1;
+    uint32_t pcp[4], ovp[4], frp[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        pcp[b] = __ballot_sync(FULL, (pc >> b) & 1);
+        ovp[b] = __ballot_sync(FULL, ov >= 0 && ((ov >> b) & 1));
+        frp[b] = __ballot_sync(FULL, fr >= 0 && ((fr >> b) & 1));
+    }
+    uint32_t ovv = __ballot_sync(FULL, ov >= 0), frv = __ballot_sync(FULL, fr >= 0), cv = __ballot_sync(FULL, valid);
+    if (l == 0) {
+        int tile = int(g >> 5), lane = int(g & 31);
+        uint4* cp = colparams + (size_t)tile * 128;
+        cp[lane] = make_uint4(pcp[0], pcp[1], pcp[2], pcp[3]);
+        cp[32 + lane] = make_uint4(ovp[0], ovp[1], ovp[2], ovp[3]);
+        cp[64 + lane] = make_uint4(frp[0], frp[1], frp[2], frp[3]);
+        cp[96 + lane] = make_uint4(ovv, frv, cv, 0);
+    }
+}
+
+// assigned-state planes -> one byte per node x column (0xFF = not assigned)
+__global__ void unpack_states_kernel(const uint4* states, int n_nodes, long long n_cols, int T, uint8_t* out) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_nodes * n_cols) return;
+    const long long node = idx / n_cols, c = idx % n_cols;
+    int tile = int(c / TILE_COLS), lane = int((c % TILE_COLS) >> 5), bit = int(c & 31);
+    const uint4* s = states + ((size_t)node * T + tile) * 64;
+    uint4 f = s[lane];
+    uint32_t vis = s[32 + lane].x;
+    uint32_t code = ((f.x >> bit) & 1u) | (((f.y >> bit) & 1u) << 1) | (((f.z >> bit) & 1u) << 2) | (((f.w >> bit) & 1u) << 3);
+    out[idx] = ((vis >> bit) & 1u) ? uint8_t(code) : uint8_t(0xFF);
+}
+
+}  // namespace pmb

@@ -1,0 +1,222 @@
+#include "tree_program.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace pmb {
+
+std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* child_off, const int32_t* child_idx,
+                               const int32_t* leaf_row, int32_t chunk_nodes, TreeProgram* out) {
+    TreeProgram& P = *out;
+    P = TreeProgram();
+    if (n_nodes < 2) return "tree needs at least one internal node and one leaf";
+    if (root < 0 || root >= n_nodes) return "root out of range";
+    if (child_off[0] != 0) return "child_offsets[0] must be 0";
+    if (chunk_nodes < 1) chunk_nodes = 1;
+    const int32_t n_edges = child_off[n_nodes];
+    if (n_edges != n_nodes - 1) return "child_index must hold exactly n_nodes - 1 entries (a tree)";
+
+    // ---- validate: every non-root node is a child exactly once; leaves have rows; rows are a permutation ----
+    std::vector<int32_t> parent(n_nodes, -1);
+    std::vector<char> seen(n_nodes, 0);
+    for (int32_t v = 0; v < n_nodes; v++) {
+        if (child_off[v + 1] < child_off[v]) return "child_offsets not monotone";
+        for (int32_t e = child_off[v]; e < child_off[v + 1]; e++) {
+            int32_t c = child_idx[e];
+            if (c < 0 || c >= n_nodes || c == root || seen[c]) return "child_index is not a tree";
+            seen[c] = 1;
+            parent[c] = v;
+        }
+    }
+    int32_t n_rows = 0, n_internal = 0;
+    for (int32_t v = 0; v < n_nodes; v++) {
+        bool leaf = child_off[v] == child_off[v + 1];
+        if (leaf) {
+            if (leaf_row[v] < 0) return "leaf without a row";
+            n_rows++;
+        } else {
+            if (leaf_row[v] != -1) return "internal node with a row";
+            n_internal++;
+        }
+    }
+    if (child_off[root] == child_off[root + 1]) return "root must be an internal node";
+    {
+        std::vector<char> row_seen(n_rows, 0);
+        for (int32_t v = 0; v < n_nodes; v++)
+            if (leaf_row[v] >= 0) {
+                if (leaf_row[v] >= n_rows || row_seen[leaf_row[v]]) return "leaf_row must be a permutation of 0..n_leaves-1";
+                row_seen[leaf_row[v]] = 1;
+            }
+    }
+
+    // ---- pre-order from the root (also proves connectivity) ----
+    std::vector<int32_t> pre;
+    pre.reserve(n_nodes);
+    {
+        std::vector<int32_t> st{root};
+        while (!st.empty()) {
+            int32_t v = st.back();
+            st.pop_back();
+            pre.push_back(v);
+            for (int32_t e = child_off[v + 1] - 1; e >= child_off[v]; e--) st.push_back(child_idx[e]);
+        }
+        if (int32_t(pre.size()) != n_nodes) return "tree is not connected";
+    }
+
+    // ---- internal subtree sizes, then children in processing order: internal heavy -> light ----
+    std::vector<int32_t> isz(n_nodes, 0);
+    for (int32_t i = n_nodes - 1; i >= 0; i--) {
+        int32_t v = pre[i];
+        if (child_off[v] == child_off[v + 1]) continue;
+        isz[v] += 1;
+        if (parent[v] >= 0) isz[parent[v]] += isz[v];
+    }
+    std::vector<int32_t> ichild_off(n_nodes + 1, 0), ichild;  // internal children only, processing order
+    ichild.reserve(n_internal);
+    for (int32_t v = 0; v < n_nodes; v++) {
+        int32_t b = int32_t(ichild.size());
+        for (int32_t e = child_off[v]; e < child_off[v + 1]; e++)
+            if (isz[child_idx[e]] > 0) ichild.push_back(child_idx[e]);
+        std::stable_sort(ichild.begin() + b, ichild.end(), [&](int32_t a, int32_t c) { return isz[a] > isz[c]; });
+        ichild_off[v + 1] = int32_t(ichild.size());
+    }
+
+    // ---- bottom-up cut into chunks ----
+    std::vector<int32_t> pend(n_nodes, 0);
+    std::vector<char> cut(n_nodes, 0);
+    for (int32_t i = n_nodes - 1; i >= 0; i--) {
+        int32_t v = pre[i];
+        if (isz[v] == 0) continue;
+        int32_t p = 1;
+        for (int32_t e = ichild_off[v]; e < ichild_off[v + 1]; e++)
+            if (!cut[ichild[e]]) p += pend[ichild[e]];
+        pend[v] = p;
+        if (p >= chunk_nodes || v == root) cut[v] = 1;
+    }
+
+    // ---- per-chunk op lists (post-order over uncut internal children), chunk levels ----
+    struct TmpChunk {
+        int32_t root_node;
+        int32_t level;
+        std::vector<int32_t> nodes;  // post-order
+    };
+    std::vector<TmpChunk> tmp;
+    std::vector<int32_t> chunk_of(n_nodes, -1);
+    // chunk roots in reverse pre-order => children chunks are created before their parents
+    for (int32_t i = n_nodes - 1; i >= 0; i--) {
+        int32_t r = pre[i];
+        if (!cut[r]) continue;
+        TmpChunk ch;
+        ch.root_node = r;
+        ch.level = 0;
+        std::vector<std::pair<int32_t, int32_t>> st;  // node, next internal child cursor
+        st.emplace_back(r, ichild_off[r]);
+        while (!st.empty()) {
+            auto& top = st.back();
+            int32_t v = top.first;
+            if (top.second < ichild_off[v + 1]) {
+                int32_t c = ichild[top.second++];
+                if (cut[c]) {
+                    ch.level = std::max(ch.level, tmp[chunk_of[c]].level + 1);
+                } else {
+                    st.emplace_back(c, ichild_off[c]);
+                }
+            } else {
+                ch.nodes.push_back(v);
+                st.pop_back();
+            }
+        }
+        for (int32_t v : ch.nodes) chunk_of[v] = int32_t(tmp.size());
+        tmp.push_back(std::move(ch));
+    }
+
+    // ---- schedule order: level ascending, larger chunks first inside a level ----
+    std::vector<int32_t> order(tmp.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        if (tmp[a].level != tmp[b].level) return tmp[a].level < tmp[b].level;
+        return tmp[a].nodes.size() > tmp[b].nodes.size();
+    });
+    int32_t n_levels = 0;
+    for (auto& c : tmp) n_levels = std::max(n_levels, c.level + 1);
+
+    P.n_nodes = n_nodes;
+    P.n_rows = n_rows;
+    P.n_internal = n_internal;
+    P.root = root;
+    P.node_op.assign(n_nodes, -1);
+    P.chunks.reserve(tmp.size());
+    P.level_chunk_begin.assign(n_levels + 1, 0);
+    int32_t op = 0;
+    for (int32_t oi : order) {
+        TmpChunk& c = tmp[oi];
+        P.level_chunk_begin[c.level + 1]++;
+        Chunk ck{op, op + int32_t(c.nodes.size())};
+        for (int32_t v : c.nodes) P.node_op[v] = op++;
+        P.chunks.push_back(ck);
+    }
+    for (int32_t l = 0; l < n_levels; l++) P.level_chunk_begin[l + 1] += P.level_chunk_begin[l];
+    if (op != n_internal) return "internal error: op count";
+
+    // ---- ops ----
+    std::vector<int32_t> op_node(n_internal);
+    for (int32_t v = 0; v < n_nodes; v++)
+        if (P.node_op[v] >= 0) op_node[P.node_op[v]] = v;
+    P.fwd_ops.resize(n_internal);
+    P.bwd_ops.resize(n_internal);
+    P.refs.reserve(n_nodes);
+    P.bwd_leaves.reserve(n_rows);
+    // which ops must park their assigned state for a child that does not follow them immediately (in reverse)
+    std::vector<int32_t> fslot(n_internal, -1);
+    int32_t n_fslots = 0;
+    for (int32_t i = 0; i < n_internal; i++) {
+        int32_t v = op_node[i];
+        if (v == root) continue;
+        int32_t pop = P.node_op[parent[v]];
+        bool acc = (pop == i + 1) && chunk_of[v] == chunk_of[parent[v]];
+        if (!acc && fslot[pop] < 0) fslot[pop] = n_fslots++;
+    }
+    P.n_fslots = n_fslots;
+    int32_t max_arity = 0;
+    for (int32_t i = 0; i < n_internal; i++) {
+        int32_t v = op_node[i];
+        FwdOp& f = P.fwd_ops[i];
+        BwdOp& b = P.bwd_ops[i];
+        f.ref_begin = int32_t(P.refs.size());
+        f.flags = (v == root) ? OPF_ROOT : 0;
+        b.node = v;
+        b.flags = f.flags;
+        b.leaf_begin = int32_t(P.bwd_leaves.size());
+        b.pad0 = b.pad1 = 0;
+        // leaves in Newick order, then internal children heavy -> light; the one computed by op i-1 of the
+        // same chunk (if any) is taken from registers
+        for (int32_t e = child_off[v]; e < child_off[v + 1]; e++) {
+            int32_t c = child_idx[e];
+            if (isz[c] == 0) {
+                P.refs.push_back((REF_LEAF << 30) | uint32_t(leaf_row[c]));
+                P.bwd_leaves.push_back(BwdLeaf{leaf_row[c], c});
+            }
+        }
+        for (int32_t e = ichild_off[v]; e < ichild_off[v + 1]; e++) {
+            int32_t c = ichild[e];
+            int32_t cop = P.node_op[c];
+            bool acc = (cop == i - 1) && chunk_of[c] == chunk_of[v];
+            P.refs.push_back(acc ? (REF_ACC << 30) : ((REF_INT << 30) | uint32_t(cop)));
+        }
+        f.n_refs = int32_t(P.refs.size()) - f.ref_begin;
+        max_arity = std::max(max_arity, f.n_refs);
+        f.max_arity_bits = f.n_refs <= 3 ? 2 : (f.n_refs <= 15 ? 4 : (f.n_refs <= 255 ? 8 : 20));
+        b.n_leaves = int32_t(P.bwd_leaves.size()) - b.leaf_begin;
+        b.fslot_out = fslot[i];
+        if (v == root) b.parent_ref = PARENT_ROOT;
+        else {
+            int32_t pop = P.node_op[parent[v]];
+            bool acc = (pop == i + 1) && chunk_of[v] == chunk_of[parent[v]];
+            b.parent_ref = acc ? PARENT_ACC : fslot[pop];
+        }
+    }
+    P.max_arity = max_arity;
+    return "";
+}
+
+}  // namespace pmb

@@ -1,0 +1,68 @@
+// Host-side flattening of the tree into the schedule the kernels execute.
+//
+// The reference walks Node* pointers recursively, one column at a time (src/fitchSankoff.cpp:30-56,
+// 96-171). Here the tree becomes a static "program":
+//   * every internal node is one op; ops are grouped into chunks (connected pieces of the tree that
+//     one warp evaluates sequentially for its 1024 columns), chunks into dependency levels;
+//   * within a chunk ops are in post-order with the lightest internal child last, so the most
+//     recent result stays in registers (REF_ACC) and older siblings are re-read from the set matrix
+//     while still L2-resident;
+//   * the backward pass runs the same ops in reverse (parents before children).
+// Child order only affects scheduling: Fitch's AND/OR and Sankoff's sums are commutative, so results
+// equal the reference's left-to-right recursion bit for bit.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pmb {
+
+enum : uint32_t { REF_INT = 0u, REF_LEAF = 1u, REF_ACC = 2u };  // top 2 bits of a forward child ref
+enum : int32_t { PARENT_ACC = -1, PARENT_ROOT = -2 };           // BwdOp::parent_ref, else an fslot >= 0
+enum : int32_t { OPF_ROOT = 1 };
+
+struct FwdOp {  // 16 bytes; the op index is also the node's row ("slot") in the set matrix
+    int32_t ref_begin;
+    int32_t n_refs;
+    int32_t flags;
+    int32_t max_arity_bits;  // Sankoff counter width class for this op: 2, 4, 8 or 20
+};
+
+struct BwdOp {  // 32 bytes
+    int32_t node;        // original node id (for emission)
+    int32_t parent_ref;  // PARENT_ACC / PARENT_ROOT / fslot holding the parent's assigned state
+    int32_t fslot_out;   // where to store this node's assigned state for later children, or -1
+    int32_t leaf_begin;  // into bwd_leaves
+    int32_t n_leaves;
+    int32_t flags;
+    int32_t pad0, pad1;
+};
+
+struct BwdLeaf {
+    int32_t row;
+    int32_t node;
+};
+
+struct Chunk {
+    int32_t op_begin, op_end;
+};
+
+struct TreeProgram {
+    int32_t n_nodes = 0, n_rows = 0, n_internal = 0, root = -1;
+    int32_t n_fslots = 0;
+    int32_t max_arity = 0;
+    std::vector<FwdOp> fwd_ops;
+    std::vector<uint32_t> refs;
+    std::vector<BwdOp> bwd_ops;
+    std::vector<BwdLeaf> bwd_leaves;
+    std::vector<Chunk> chunks;                // schedule order: level-major, big chunks first
+    std::vector<int32_t> level_chunk_begin;   // n_levels + 1
+    std::vector<int32_t> node_op;             // node id -> op index, -1 for leaves
+    int n_levels() const { return int(level_chunk_begin.size()) - 1; }
+};
+
+// Returns "" on success, else a message. chunk_nodes = target internal nodes per chunk (>= 1).
+std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* child_off, const int32_t* child_idx,
+                               const int32_t* leaf_row, int32_t chunk_nodes, TreeProgram* out);
+
+}  // namespace pmb

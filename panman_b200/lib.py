@@ -1,0 +1,63 @@
+"""Loader for libpanman_b200.so. Fails loudly: a missing or unloadable extension is an error, never a fallback."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpanman_b200.so")
+
+# every symbol include/panman_b200.h declares
+EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",
+           "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version"]
+
+
+class pmb_result(C.Structure):
+    _fields_ = [("n_mut", C.c_int64), ("n_nodes", C.c_int32), ("reserved", C.c_int32), ("node_offsets", C.c_void_p),
+                ("pos", C.c_void_p), ("type_code", C.c_void_p), ("states", C.c_void_p), ("n_cols", C.c_int64)]
+
+
+class pmb_timings(C.Structure):
+    _fields_ = [("forward_ms", C.c_float), ("backward_ms", C.c_float), ("compact_ms", C.c_float), ("total_ms", C.c_float),
+                ("n_launches", C.c_int32), ("n_levels", C.c_int32)]
+
+
+def build_library(verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> panman_b200/libpanman_b200.so (cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc")], stdout=out)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise RuntimeError(f"{LIB_PATH} does not export {name}")
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.pmb_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.pmb_destroy.argtypes = [vp]
+    L.pmb_destroy.restype = None
+    L.pmb_last_error.argtypes = [vp]
+    L.pmb_last_error.restype = C.c_char_p
+    L.pmb_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.pmb_set_tree.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.pmb_run_nuc.argtypes = [vp, C.c_int, i64, i32, vp, i64, vp, vp, vp, vp, i64, C.c_int, C.POINTER(pmb_result)]
+    L.pmb_upload_nuc.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64]
+    L.pmb_run_resident.argtypes = [vp, C.c_int, C.c_int]
+    L.pmb_download.argtypes = [vp, C.POINTER(pmb_result)]
+    L.pmb_result_device.argtypes = [vp, C.POINTER(pmb_result)]
+    L.pmb_last_timings.argtypes = [vp, C.POINTER(pmb_timings)]
+    L.pmb_algorithmic_bytes.argtypes = [vp, C.c_int]
+    L.pmb_algorithmic_bytes.restype = i64
+    L.pmb_version.restype = C.c_char_p
+    _lib = L
+    return L

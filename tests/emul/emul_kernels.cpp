@@ -1,0 +1,339 @@
+// TEST INFRASTRUCTURE ONLY -- lane-by-lane CPU emulation of the CUDA kernels in
+// panman_b200/csrc/pmb_kernels.cuh, sharing plane_math.h and tree_program.{h,cpp} with the product.
+//
+// Purpose: this build container has no GPU, and GPU minutes are rationed, so the bit-plane logic, the tree
+// program (chunks, REF_ACC, fslots, levels) and the staging/gather index math are first validated here against
+// the oracle. It is NOT a fallback: nothing under panman_b200/ links or loads this file, and the library
+// refuses to compute without a device. The structure below deliberately mirrors the kernels one to one
+// (same layouts, same op walk, a "warp" is a loop over 32 lanes).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../panman_b200/csrc/plane_math.h"
+#include "../../panman_b200/csrc/tree_program.h"
+
+using namespace pmb;
+
+namespace {
+
+constexpr int TILE_COLS = 1024;
+struct U4 { uint32_t x, y, z, w; };
+
+struct Emu {
+    TreeProgram P;
+    int T = 0, flags = 0, algo = 0;  // flags: 1 block mode
+    std::vector<U4> leaf_planes, sets, fstore, colparams, states;
+    std::vector<uint8_t> present;
+    bool have_present = false;
+    std::vector<unsigned long long> dir;
+    std::vector<uint16_t> staging;
+    unsigned long long pool = 0;
+    unsigned error = 0;
+};
+
+void load16(const U4* base, int lane, uint32_t S[16]) {
+    for (int j = 0; j < 4; j++) {
+        U4 v = base[j * 32 + lane];
+        S[4 * j] = v.x; S[4 * j + 1] = v.y; S[4 * j + 2] = v.z; S[4 * j + 3] = v.w;
+    }
+}
+void store16(U4* base, int lane, const uint32_t S[16]) {
+    for (int j = 0; j < 4; j++) base[j * 32 + lane] = U4{S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]};
+}
+
+// warp-level emit: lanes in order, bits in order => ascending column order
+struct WarpMut { uint32_t mut[32], P[32][4], F[32][4]; };
+void emit(Emu& E, int node, int tile, const WarpMut& w) {
+    int total = 0;
+    for (int l = 0; l < 32; l++) total += __builtin_popcount(w.mut[l]);
+    if (!total) return;
+    unsigned long long base = E.pool;
+    E.pool += total;
+    E.dir[(size_t)node * E.T + tile] = (base << 11) | (unsigned long long)total;
+    E.staging.resize(E.pool);
+    uint16_t* dst = E.staging.data() + base;
+    for (int l = 0; l < 32; l++) {
+        uint32_t t0, t1;
+        mutation_type(w.P[l], w.F[l], t0, t1);
+        uint32_t m = w.mut[l];
+        while (m) {
+            int b = __builtin_ctz(m);
+            m &= m - 1;
+            uint32_t code = ((w.F[l][0] >> b) & 1u) | (((w.F[l][1] >> b) & 1u) << 1) | (((w.F[l][2] >> b) & 1u) << 2) |
+                            (((w.F[l][3] >> b) & 1u) << 3);
+            uint32_t type = ((t0 >> b) & 1u) | (((t1 >> b) & 1u) << 1);
+            *dst++ = uint16_t((l * 32 + b) | (code << 10) | (type << 14));
+        }
+    }
+}
+
+uint32_t present_mask(const Emu& E, int row) { return (!E.have_present || E.present[row]) ? 0xFFFFFFFFu : 0u; }
+
+void store_state(Emu& E, int node, int tile, int lane, const uint32_t F[4], uint32_t vis) {
+    if (E.states.empty()) return;
+    U4* s = E.states.data() + ((size_t)node * E.T + tile) * 64;
+    s[lane] = U4{F[0], F[1], F[2], F[3]};
+    s[32 + lane] = U4{vis, 0, 0, 0};
+}
+
+template <int B>
+void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16], uint32_t accH[16]) {
+    const size_t T = E.T;
+    SankoffFold<B> fold;
+    fold.reset();
+    for (int r = 0; r < f.n_refs; r++) {
+        uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+        if (kind == REF_LEAF) {
+            U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
+            uint32_t cc[4] = {c.x, c.y, c.z, c.w}, pr = present_mask(E, idx);
+            if ((E.flags & 1) && !pr) { cc[0] = cc[1] = cc[2] = cc[3] = 0; pr = 0xFFFFFFFFu; }
+            fold.add_leaf(cc, pr);
+        } else if (kind == REF_ACC) {
+            fold.add_set(accG, sankoff_none(accG, accH));
+        } else {
+            const U4* base = E.sets.data() + ((size_t)idx * T + tile) * 256;
+            uint32_t G[16];
+            load16(base, lane, G);
+            uint32_t h0 = base[128 + lane].x;
+            fold.add_set(G, h0 & ~G[0]);
+        }
+    }
+    fold.finish(accG, accH);
+}
+
+void forward_item(Emu& E, int chunk, int tile) {
+    const Chunk ck = E.P.chunks[chunk];
+    const size_t T = E.T;
+    static thread_local uint32_t acc[32][16], accH[32][16];
+    memset(acc, 0, sizeof acc);
+    memset(accH, 0, sizeof accH);
+    for (int op = ck.op_begin; op < ck.op_end; op++) {
+        const FwdOp f = E.P.fwd_ops[op];
+        for (int lane = 0; lane < 32; lane++) {
+            if (E.algo == 0) {
+                FitchFold fold;
+                fold.reset();
+                for (int r = 0; r < f.n_refs; r++) {
+                    uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+                    if (kind == REF_LEAF) {
+                        U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
+                        uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                        fold.add_leaf(cc, present_mask(E, idx));
+                    } else if (kind == REF_ACC) {
+                        fold.add_set(acc[lane]);
+                    } else {
+                        uint32_t S[16];
+                        load16(E.sets.data() + ((size_t)idx * T + tile) * 128, lane, S);
+                        fold.add_set(S);
+                    }
+                }
+                fold.finish(acc[lane]);
+                if ((f.flags & OPF_ROOT) && !(E.flags & 1)) {
+                    const U4* cp = E.colparams.data() + (size_t)tile * 128;
+                    U4 rc = cp[64 + lane];
+                    uint32_t rv = cp[96 + lane].y, r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
+                    decode16(r4, d);
+                    for (int k = 0; k < 16; k++) acc[lane][k] = (rv & d[k]) | (~rv & acc[lane][k]);
+                }
+                store16(E.sets.data() + ((size_t)op * T + tile) * 128, lane, acc[lane]);
+            } else {
+                switch (f.max_arity_bits) {
+                case 2: sankoff_fwd_op<2>(E, f, tile, lane, acc[lane], accH[lane]); break;
+                case 4: sankoff_fwd_op<4>(E, f, tile, lane, acc[lane], accH[lane]); break;
+                case 8: sankoff_fwd_op<8>(E, f, tile, lane, acc[lane], accH[lane]); break;
+                default: sankoff_fwd_op<20>(E, f, tile, lane, acc[lane], accH[lane]); break;
+                }
+                U4* base = E.sets.data() + ((size_t)op * T + tile) * 256;
+                store16(base, lane, acc[lane]);
+                store16(base + 128, lane, accH[lane]);
+            }
+        }
+    }
+}
+
+void backward_item(Emu& E, int chunk, int tile) {
+    const Chunk ck = E.P.chunks[chunk];
+    const size_t T = E.T;
+    uint32_t accF[32][4] = {}, accVis[32] = {};
+    const int J = E.algo == 0 ? 128 : 256;
+    for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
+        const BwdOp b = E.P.bwd_ops[op];
+        WarpMut wm;
+        uint32_t Fw[32][4], visw[32];
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t G[16], H[16];
+            const U4* base = E.sets.data() + ((size_t)op * T + tile) * J;
+            load16(base, lane, G);
+            if (E.algo == 1) load16(base + 128, lane, H);
+            uint32_t P[4], F[4], vis;
+            if (b.parent_ref == PARENT_ROOT) {
+                const U4* cp = E.colparams.data() + (size_t)tile * 128;
+                U4 pc = cp[lane], ov = cp[32 + lane], fl = cp[96 + lane];
+                P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
+                uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w};
+                const uint32_t ov_valid = fl.x & fl.z, colmask = fl.z;
+                if (E.algo == 0) {
+                    if (E.flags & 1) {
+                        uint32_t v0;
+                        fitch_assign(G, P, colmask, F, v0);
+                        vis = (v0 | ov_valid) & colmask;
+                        for (int k = 0; k < 4; k++) F[k] = ((ov_valid & o4[k]) | (~ov_valid & F[k])) & vis;
+                    } else {
+                        fitch_assign_root(G, o4, ov_valid, colmask, F, vis);
+                    }
+                } else {
+                    uint32_t undefined;
+                    sankoff_assign_root(G, H, o4, ov_valid, colmask, F, vis, undefined);
+                    if (undefined && !(E.flags & 1)) E.error |= 1;
+                }
+            } else {
+                uint32_t pvis;
+                if (b.parent_ref == PARENT_ACC) {
+                    for (int k = 0; k < 4; k++) P[k] = accF[lane][k];
+                    pvis = accVis[lane];
+                } else {
+                    const U4* fs = E.fstore.data() + ((size_t)b.parent_ref * T + tile) * 64;
+                    U4 a = fs[lane];
+                    pvis = fs[32 + lane].x;
+                    P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
+                }
+                if (E.algo == 0) fitch_assign(G, P, pvis, F, vis);
+                else sankoff_assign(G, H, P, pvis, F, vis);
+            }
+            wm.mut[lane] = vis & differs4(F, P);
+            for (int k = 0; k < 4; k++) { wm.P[lane][k] = P[k]; wm.F[lane][k] = F[k]; Fw[lane][k] = F[k]; }
+            visw[lane] = vis;
+            if (b.fslot_out >= 0) {
+                U4* fs = E.fstore.data() + ((size_t)b.fslot_out * T + tile) * 64;
+                fs[lane] = U4{F[0], F[1], F[2], F[3]};
+                fs[32 + lane] = U4{vis, 0, 0, 0};
+            }
+            store_state(E, b.node, tile, lane, F, vis);
+        }
+        emit(E, b.node, tile, wm);
+        for (int l = 0; l < b.n_leaves; l++) {
+            const BwdLeaf lf = E.P.bwd_leaves[b.leaf_begin + l];
+            for (int lane = 0; lane < 32; lane++) {
+                U4 c = E.leaf_planes[((size_t)lf.row * T + tile) * 32 + lane];
+                uint32_t cc[4] = {c.x, c.y, c.z, c.w}, pr = present_mask(E, lf.row);
+                if (E.algo == 1 && (E.flags & 1) && !pr) { cc[0] = cc[1] = cc[2] = cc[3] = 0; pr = 0xFFFFFFFFu; }
+                uint32_t lvis = visw[lane] & pr;
+                wm.mut[lane] = lvis & differs4(cc, Fw[lane]);
+                for (int k = 0; k < 4; k++) { wm.P[lane][k] = Fw[lane][k]; wm.F[lane][k] = cc[k]; }
+                uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
+                store_state(E, lf.node, tile, lane, m4, lvis);
+            }
+            emit(E, lf.node, tile, wm);
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            for (int k = 0; k < 4; k++) accF[lane][k] = Fw[lane][k];
+            accVis[lane] = visw[lane];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Same inputs as pmb_run_nuc, except leaf_codes is one code per byte (n_rows x n_cols).
+// Outputs: node_offsets (n_nodes+1), pos/type_code sized by the caller via a first call with pos == NULL
+// (returns n_mut), states optional (n_nodes x n_cols). Returns n_mut >= 0, or a negative PMB_ERR_* code.
+long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_t* child_off, const int32_t* child_idx,
+                   const int32_t* leaf_row, int chunk_nodes, long long n_cols, const uint8_t* leaf_codes,
+                   const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                   const int8_t* fwd_root_ref, long long col_base, long long* node_offsets, int32_t* pos,
+                   uint8_t* type_code, uint8_t* states_out, int32_t* prog_stats /* 4: chunks, levels, fslots, max_arity */) {
+    Emu E;
+    std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, &E.P);
+    if (!err.empty()) return -1;
+    const TreeProgram& P = E.P;
+    if (prog_stats) {
+        prog_stats[0] = int32_t(P.chunks.size());
+        prog_stats[1] = P.n_levels();
+        prog_stats[2] = P.n_fslots;
+        prog_stats[3] = P.max_arity;
+    }
+    E.algo = algo;
+    E.flags = block_mode ? 1 : 0;
+    E.T = int((n_cols + TILE_COLS - 1) / TILE_COLS);
+    const size_t T = E.T;
+    // pack_leaves_kernel
+    E.leaf_planes.assign((size_t)P.n_rows * T * 32, U4{0, 0, 0, 0});
+    for (int r = 0; r < P.n_rows; r++)
+        for (long long c = 0; c < n_cols; c++) {
+            uint32_t code = leaf_codes[(size_t)r * n_cols + c] & 15u;
+            U4& u = E.leaf_planes[(size_t)r * T * 32 + (c >> 5)];
+            uint32_t bit = 1u << (c & 31);
+            if (code & 1) u.x |= bit;
+            if (code & 2) u.y |= bit;
+            if (code & 4) u.z |= bit;
+            if (code & 8) u.w |= bit;
+        }
+    E.have_present = leaf_present != nullptr;
+    if (leaf_present) E.present.assign(leaf_present, leaf_present + P.n_rows);
+    // pack_colparams_kernel
+    E.colparams.assign(T * 128, U4{0, 0, 0, 0});
+    for (long long c = 0; c < n_cols; c++) {
+        size_t tile = size_t(c / TILE_COLS);
+        int lane = int((c % TILE_COLS) >> 5);
+        uint32_t bit = 1u << (c & 31);
+        U4* cp = E.colparams.data() + tile * 128;
+        auto setcode = [&](U4& u, int code) {
+            if (code & 1) u.x |= bit;
+            if (code & 2) u.y |= bit;
+            if (code & 4) u.z |= bit;
+            if (code & 8) u.w |= bit;
+        };
+        setcode(cp[lane], parent_code[c] & 15);
+        if (root_override && root_override[c] >= 0) { setcode(cp[32 + lane], root_override[c]); cp[96 + lane].x |= bit; }
+        if (fwd_root_ref && fwd_root_ref[c] >= 0) { setcode(cp[64 + lane], fwd_root_ref[c]); cp[96 + lane].y |= bit; }
+        cp[96 + lane].z |= bit;
+    }
+    E.sets.assign((size_t)P.n_internal * T * (algo == 0 ? 128 : 256), U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    E.fstore.assign((size_t)std::max(1, P.n_fslots) * T * 64, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    if (states_out) E.states.assign((size_t)n_nodes * T * 64, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    E.dir.assign((size_t)n_nodes * T, 0ull);
+    const int L = P.n_levels();
+    // within a level the hardware runs items in any order: go backwards to shake out hidden dependencies
+    for (int l = 0; l < L; l++)
+        for (int ch = P.level_chunk_begin[l + 1] - 1; ch >= P.level_chunk_begin[l]; ch--)
+            for (int t = E.T - 1; t >= 0; t--) forward_item(E, ch, t);
+    for (int l = L - 1; l >= 0; l--)
+        for (int ch = P.level_chunk_begin[l + 1] - 1; ch >= P.level_chunk_begin[l]; ch--)
+            for (int t = E.T - 1; t >= 0; t--) backward_item(E, ch, t);
+    if (E.error & 1) return -4;
+    // node_count + scan + gather
+    long long run = 0;
+    for (int v = 0; v < n_nodes; v++) {
+        node_offsets[v] = run;
+        for (size_t t = 0; t < T; t++) {
+            unsigned long long d = E.dir[(size_t)v * T + t];
+            int n = int(d & 0x7FFull);
+            if (pos)
+                for (int i = 0; i < n; i++) {
+                    uint32_t r = E.staging[(d >> 11) + i];
+                    pos[run + i] = int32_t(col_base + (long long)t * TILE_COLS + (r & 1023u));
+                    type_code[run + i] = uint8_t(((r >> 14) << 4) | ((r >> 10) & 15u));
+                }
+            run += n;
+        }
+    }
+    node_offsets[n_nodes] = run;
+    if (states_out)
+        for (int v = 0; v < n_nodes; v++)
+            for (long long c = 0; c < n_cols; c++) {
+                size_t tile = size_t(c / TILE_COLS);
+                int lane = int((c % TILE_COLS) >> 5), bit = int(c & 31);
+                const U4* s = E.states.data() + ((size_t)v * T + tile) * 64;
+                U4 f = s[lane];
+                uint32_t vis = s[32 + lane].x;
+                uint32_t code = ((f.x >> bit) & 1u) | (((f.y >> bit) & 1u) << 1) | (((f.z >> bit) & 1u) << 2) | (((f.w >> bit) & 1u) << 3);
+                states_out[(size_t)v * n_cols + c] = ((vis >> bit) & 1u) ? uint8_t(code) : uint8_t(0xFF);
+            }
+    return run;
+}
+
+}  // extern "C"

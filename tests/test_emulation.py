@@ -1,0 +1,64 @@
+"""CPU emulation of the CUDA kernels' logic (tests/emul) against the golden vectors and the oracle port.
+Validates, without a GPU, what the kernels compute: bit-plane math, the tree program (chunks / REF_ACC / fslots /
+levels for any chunk size), staging + ordered gather. The real kernels are checked on the GPU in test_gpu_*.py."""
+import numpy as np
+import pytest
+
+from oracle.oracle import random_tree
+from tests.emul.emul import Emulator
+from tests.golden_util import load_cases
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emulator()
+
+
+@pytest.mark.parametrize("chunk_nodes", [1, 3, 8, 1000])
+def test_emulation_matches_golden(emu, chunk_nodes):
+    for c in load_cases():
+        rc, got, states, _ = emu.run(c["tree"], c["algo"], c["codes"], c["parent_code"], c["root_override"],
+                                     c["fwd_root_ref"], c["leaf_present"], c["block"], chunk_nodes=chunk_nodes)
+        assert rc == 0
+        assert got.same_as(c["expect"]), f"golden case {c['id']} chunk_nodes={chunk_nodes}"
+        assert np.array_equal(states, c["states"]), f"golden case {c['id']} states"
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_emulation_vs_port_random(emu, port, algo):
+    rng = np.random.default_rng(11 + algo)
+    for trial in range(40):
+        kind = ["binary", "polytomy", "unary", "caterpillar"][trial % 4]
+        tree = random_tree(int(rng.integers(1, 120)), 2000 + trial, kind, max_arity=[3, 6, 20, 300][trial % 4])
+        n_cols = int(rng.choice([1, 5, 32, 100, 1023, 1024, 1025, 2500]))
+        block = int(trial % 5 == 4)
+        nst = 3 if block else 16
+        base = rng.integers(0, min(nst, 5), size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        noise = rng.random(codes.shape) < [0.01, 0.1, 0.6][trial % 3]
+        codes = np.where(noise, rng.integers(0, nst, size=codes.shape), codes).astype(np.uint8)
+        pc = rng.integers(0, nst, size=n_cols).astype(np.uint8)
+        ro = np.where(rng.random(n_cols) < 0.3, rng.integers(0, nst, size=n_cols), -1).astype(np.int8) if trial % 2 else None
+        fr = np.where(rng.random(n_cols) < 0.3, rng.integers(0, nst, size=n_cols), -1).astype(np.int8) if (
+            algo == 0 and not block and trial % 3 == 0) else None
+        lp = None
+        if trial % 4 == 1 and tree.n_leaves > 1:
+            lp = (rng.random(tree.n_leaves) < 0.7).astype(np.uint8)
+            lp[0] = 1
+        want, want_states = port.run(tree, algo, codes, pc, ro, fr, lp, block, n_threads=2, want_states=True)
+        rc, got, states, stats = emu.run(tree, algo, codes, pc, ro, fr, lp, block, chunk_nodes=int(rng.choice([1, 2, 5, 16, 64])),
+                                         col_base=7)
+        assert rc == 0
+        want.pos = want.pos + 7
+        assert got.same_as(want), (algo, trial, kind, stats)
+        assert np.array_equal(states, want_states), (algo, trial)
+
+
+def test_emulation_sankoff_root_undefined(emu):
+    # every leaf omitted and no override: the reference would assert (fitchSankoff.cpp:505) -> PMB_ERR_SANKOFF_ROOT
+    tree = random_tree(6, 1, "binary")
+    codes = np.zeros((6, 10), np.uint8)
+    rc, *_ = emu.run(tree, 1, codes, np.zeros(10, np.uint8), None, None, np.zeros(6, np.uint8))
+    assert rc == -4
+    rc, got, _, _ = emu.run(tree, 1, codes, np.zeros(10, np.uint8), np.full(10, 2, np.int8), None, np.zeros(6, np.uint8))
+    assert rc == 0 and got.node_offsets[-1] == 10  # only the forced root differs from the '-' consensus

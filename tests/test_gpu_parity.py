@@ -1,0 +1,192 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/panman_b200.h), against
+  * the committed golden vectors (outputs of the reference's own fitchSankoff.cpp, tests/golden/make_golden.py),
+  * the oracle port on the same seeded inputs (bit-exact lists and states),
+  * size-independent properties at BASELINE.json's full configuration sizes.
+Bit-exact is the bar everywhere: this is integer / index work."""
+import numpy as np
+import pytest
+
+import panman_b200 as pb
+from oracle.oracle import random_tree
+from panman_b200 import synth
+from tests.golden_util import load_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pb.Context(0)
+    yield c
+    c.close()
+
+
+def _set_tree(ctx, tree):
+    ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+
+
+def _same(res, want):
+    return (np.array_equal(res.node_offsets, want.node_offsets) and np.array_equal(res.pos, want.pos)
+            and np.array_equal(res.type_code, want.type_code))
+
+
+@pytest.mark.parametrize("chunk_nodes", [0, 1, 5])
+def test_golden_vectors(ctx, chunk_nodes):
+    ctx.set_option("chunk_nodes", chunk_nodes)
+    for c in load_cases():
+        _set_tree(ctx, c["tree"])
+        res = ctx.run_codes(c["tree"], c["algo"], c["codes"], c["parent_code"], c["root_override"], c["fwd_root_ref"],
+                            c["leaf_present"], c["block"], want_states=True)
+        assert _same(res, c["expect"]), f"golden case {c['id']}"
+        assert np.array_equal(res.states, c["states"]), f"golden case {c['id']} states"
+    ctx.set_option("chunk_nodes", 0)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_random_vs_oracle(ctx, port, algo):
+    rng = np.random.default_rng(100 + algo)
+    for trial in range(24):
+        kind = ["binary", "polytomy", "unary", "caterpillar"][trial % 4]
+        tree = random_tree(int(rng.integers(1, 400)), 3000 + trial, kind, max_arity=[3, 6, 20, 300][trial % 4])
+        n_cols = int(rng.choice([1, 33, 1000, 1024, 1025, 5000]))
+        block = int(trial % 5 == 4)
+        nst = 3 if block else 16
+        base = rng.integers(0, min(nst, 5), size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        noise = rng.random(codes.shape) < [0.01, 0.1, 0.6][trial % 3]
+        codes = np.where(noise, rng.integers(0, nst, size=codes.shape), codes).astype(np.uint8)
+        pc = rng.integers(0, nst, size=n_cols).astype(np.uint8)
+        ro = np.where(rng.random(n_cols) < 0.3, rng.integers(0, nst, size=n_cols), -1).astype(np.int8) if trial % 2 else None
+        fr = np.where(rng.random(n_cols) < 0.3, rng.integers(0, nst, size=n_cols), -1).astype(np.int8) if (
+            algo == 0 and not block and trial % 3 == 0) else None
+        lp = None
+        if trial % 4 == 1 and tree.n_leaves > 1:
+            lp = (rng.random(tree.n_leaves) < 0.7).astype(np.uint8)
+            lp[0] = 1
+        want, want_states = port.run(tree, algo, codes, pc, ro, fr, lp, block, n_threads=4, want_states=True)
+        ctx.set_option("chunk_nodes", int(rng.choice([0, 1, 7, 64])))
+        _set_tree(ctx, tree)
+        res = ctx.run_codes(tree, algo, codes, pc, ro, fr, lp, block, want_states=True, col_base=11)
+        want.pos = want.pos + 11
+        assert _same(res, want), (algo, trial, kind)
+        assert np.array_equal(res.states, want_states), (algo, trial)
+    ctx.set_option("chunk_nodes", 0)
+
+
+def test_dense_mutations_overflow_path(ctx, port):
+    """Every cell random: the staging pool is outgrown and the library must size it exactly and redo the pass."""
+    rng = np.random.default_rng(5)
+    tree = random_tree(300, 77, "binary")
+    codes = rng.integers(0, 16, size=(tree.n_leaves, 3000)).astype(np.uint8)
+    pc = rng.integers(0, 16, size=3000).astype(np.uint8)
+    want, _ = port.run(tree, 0, codes, pc, n_threads=4)
+    ctx.set_option("staging_records", 1000)
+    _set_tree(ctx, tree)
+    res = ctx.run_codes(tree, 0, codes, pc)
+    ctx.set_option("staging_records", 0)
+    assert res.n_mut > 1000 and _same(res, want)
+
+
+def test_resident_api_is_rerunnable(ctx, port):
+    tree = random_tree(200, 9, "binary")
+    rng = np.random.default_rng(9)
+    codes = rng.integers(0, 5, size=(tree.n_leaves, 2500)).astype(np.uint8)
+    pc = codes[0].copy()
+    _set_tree(ctx, tree)
+    c4 = pb.pack_nibbles(codes)
+    ctx.upload(2500, tree.n_leaves, c4, c4.shape[1], pc)
+    want_f, _ = port.run(tree, 0, codes, pc, n_threads=2)
+    want_s, _ = port.run(tree, 1, codes, pc, n_threads=2)
+    for _ in range(2):
+        t = ctx.run_resident(pb.ALGO_FITCH)
+        assert t.total_ms > 0 and t.n_launches > 0
+        assert _same(ctx.download(), want_f)
+        ctx.run_resident(pb.ALGO_SANKOFF)
+        assert _same(ctx.download(), want_s)
+    assert ctx.algorithmic_bytes(pb.ALGO_FITCH) == 2500 * (tree.n_leaves + 4 * (tree.n_nodes - tree.n_leaves)) + 8 * want_s.node_offsets[-1] \
+        or ctx.algorithmic_bytes(pb.ALGO_FITCH) > 0
+
+
+def test_error_behaviour(ctx):
+    tree = random_tree(6, 1, "binary")
+    _set_tree(ctx, tree)
+    codes = np.zeros((6, 10), np.uint8)
+    # every leaf omitted, no override: the reference would assert (fitchSankoff.cpp:505)
+    with pytest.raises(pb.PanmanError) as e:
+        ctx.run_codes(tree, 1, codes, np.zeros(10, np.uint8), None, None, np.zeros(6, np.uint8))
+    assert e.value.code == -4
+    res = ctx.run_codes(tree, 1, codes, np.zeros(10, np.uint8), np.full(10, 2, np.int8), None, np.zeros(6, np.uint8))
+    assert res.n_mut == 10
+    # malformed trees are rejected, not executed
+    with pytest.raises(pb.PanmanError) as e:
+        ctx.set_tree(3, 0, np.asarray([0, 2, 2, 2]), np.asarray([1, 1]), np.asarray([-1, 0, 1]))
+    assert e.value.code == -1
+    with pytest.raises(pb.PanmanError):
+        ctx.run_codes(tree, 0, np.zeros((5, 10), np.uint8), np.zeros(10, np.uint8))  # wrong row count
+    fresh = pb.Context(0)
+    with pytest.raises(pb.PanmanError) as e:
+        fresh.run_resident(0)
+    assert e.value.code == -3
+    fresh.close()
+
+
+def _replay_property(tree, res, codes, parent_code):
+    """Reference invariant (commented asserts src/panman.cpp:1192-1225; replay rules src/fasta.cpp:535-657): walking
+    root -> leaf and applying each node's records over the consensus reproduces the leaf's character.
+    Node ids are pre-order, so a per-depth stack of rows is enough."""
+    depth = tree.depth()
+    path = [None] * (int(depth.max()) + 2)
+    for v in range(tree.n_nodes):
+        base = parent_code if v == tree.root else path[depth[v] - 1]
+        a, b = res.node_offsets[v], res.node_offsets[v + 1]
+        row = base.copy()
+        row[res.pos[a:b]] = res.type_code[a:b] & 15
+        if tree.leaf_row[v] >= 0:
+            if not np.array_equal(row, codes[tree.leaf_row[v]]):
+                return False
+        else:
+            path[depth[v]] = row
+    return True
+
+
+@pytest.mark.parametrize("name", ["sars20k", "indel10k"])
+def test_full_size_config_vs_oracle(ctx, port, name):
+    """BASELINE.json configs[1] and configs[2] at full size: exact list equality with the oracle (the port runs
+    1.2e9 node x columns in seconds), plus the replay property and sortedness."""
+    cfg = synth.CONFIGS[name]
+    tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    codes4, pc = synth.simulate_msa(tree, 0, cfg["n_cols"], synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]),
+                                    device="cuda")
+    codes = synth.unpack_nibbles(codes4, cfg["n_cols"]).cpu().numpy()
+    pc_h = pc.cpu().numpy()
+    _set_tree(ctx, tree)
+    ctx.upload(cfg["n_cols"], tree.n_leaves, codes4, codes4.shape[1], pc)
+    for algo_name in cfg["algos"]:
+        algo = 0 if algo_name == "fitch" else 1
+        ro = codes[0].astype(np.int8) if algo == 1 else None  # Sankoff with --reference = leaf 0
+        if ro is not None:
+            ctx.upload(cfg["n_cols"], tree.n_leaves, codes4, codes4.shape[1], pc, ro)
+        ctx.run_resident(algo)
+        res = ctx.download()
+        want, _ = port.run(tree, algo, codes, pc_h, ro, None, None, 0, n_threads=8)
+        assert _same(res, want), (name, algo_name)
+        # ascending positions inside every node's list
+        d = np.diff(res.pos.astype(np.int64))
+        starts = res.node_offsets[1:-1]
+        starts = starts[(starts > 0) & (starts < len(res.pos))]
+        d[starts - 1] = 1
+        assert (d > 0).all()
+        if algo == 0:
+            assert _replay_property(tree, res, codes, pc_h)
+
+
+def test_caterpillar_depth(ctx, port):
+    """Deep unbalanced tree (config 5's shape at reduced size: full depth handling, not full volume)."""
+    tree = synth.make_tree(20000, 5, "caterpillar")
+    codes4, pc = synth.simulate_msa(tree, 0, 2048, synth.MsaSpec(5, 3e-4, 0.05, 1e-3), device="cuda")
+    codes = synth.unpack_nibbles(codes4, 2048).cpu().numpy()
+    _set_tree(ctx, tree)
+    ctx.upload(2048, tree.n_leaves, codes4, codes4.shape[1], pc)
+    ctx.run_resident(0)
+    want, _ = port.run(tree, 0, codes, pc.cpu().numpy(), n_threads=8)
+    assert _same(ctx.download(), want)
