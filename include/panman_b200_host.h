@@ -1,0 +1,72 @@
+/* libpanman_b200_host -- host-side adaptor above libpanman_b200 (C++ inside, C ABI outside).
+ *
+ * It restates the parts of the reference's Tree constructor that surround the per-column passes, so that the
+ * -M / -N construction flow can be exercised end to end without the reference's TBB/Boost/capnp dependencies:
+ *   - Newick -> tree with the reference's node ids and child order   (reference src/panman.cpp:310-450)
+ *   - FASTA/MSA reader, consensus rule, all-gap column removal        (reference src/panman.cpp:1288-1362, 1479-1557)
+ *   - per-column inputs -> pmb_run_nuc                                 (replaces the loops at :1381-1435 and :1568-1613)
+ *   - per-node sort order + greedy <=6 run-merge into NucMut fields    (reference src/panman.cpp:1445-1466, 1625-1646;
+ *                                                                        NucMut ctor src/panman.hpp:109-151)
+ * The outputs are exactly the fields the reference stores in Node::nucMutation / Node::blockMutation, in the order
+ * it stores them; the capnp writer (src/panman.cpp:2854-2929) stays the reference's own.
+ */
+#ifndef PANMAN_B200_HOST_H
+#define PANMAN_B200_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "panman_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmh_tree pmh_tree;
+typedef struct pmh_build pmh_build;
+
+/* One NucMut as the reference holds it (src/panman.hpp:75-81). */
+typedef struct pmh_nucmut {
+    int32_t nucPosition;
+    int32_t nucGapPosition;   /* -1 for MSA builds */
+    int32_t primaryBlockId;   /* 0 for MSA builds */
+    int32_t secondaryBlockId; /* -1 */
+    uint8_t mutInfo;          /* (length << 4) + type */
+    uint32_t nucs;            /* code_k << (4 * (5 - k)) */
+} pmh_nucmut;
+
+/* ---- Newick ---- */
+pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len); /* NULL on malformed input */
+void pmh_tree_free(pmh_tree* t);
+int32_t pmh_tree_n_nodes(const pmh_tree* t);
+int32_t pmh_tree_n_leaves(const pmh_tree* t);
+int32_t pmh_tree_root(const pmh_tree* t);
+const char* pmh_tree_name(const pmh_tree* t, int32_t node);
+const int32_t* pmh_tree_parent(const pmh_tree* t);
+const int32_t* pmh_tree_child_offsets(const pmh_tree* t);
+const int32_t* pmh_tree_child_index(const pmh_tree* t);
+const int32_t* pmh_tree_leaf_row(const pmh_tree* t);
+int pmh_tree_has_polytomy(const pmh_tree* t); /* reference src/panman.cpp:621-631 */
+
+/* ---- MSA construction: panmanUtils -M msa.fa -N tree.nwk [--reference id] [--low-mem-mode] ----
+ * fasta / newick are the file contents. low_mem_mode = 0: Fitch (reference FILE_TYPE::MSA, src/panman.cpp:1274-1466);
+ * 1: Sankoff (FILE_TYPE::MSA_OPTIMIZE, :1467-1649). Returns NULL and fills err on failure. */
+pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len, const char* newick, const char* reference,
+                              int low_mem_mode, char* err, size_t err_len);
+void pmh_build_free(pmh_build* b);
+const pmh_tree* pmh_build_tree(const pmh_build* b);
+const char* pmh_build_consensus(const pmh_build* b, int64_t* len); /* blocks[0] consensus (src/panman.cpp:1439) */
+int64_t pmh_build_n_nucmut(const pmh_build* b, int32_t node);
+const pmh_nucmut* pmh_build_nucmut(const pmh_build* b, int32_t node); /* Node::nucMutation, in stored order */
+/* raw per-node tuples (pos, type, code) before the merge, node-major (debugging / parity) */
+int64_t pmh_build_n_tuples(const pmh_build* b);
+const int64_t* pmh_build_tuple_offsets(const pmh_build* b);
+const int32_t* pmh_build_tuple_pos(const pmh_build* b);
+const uint8_t* pmh_build_tuple_type_code(const pmh_build* b);
+/* seconds spent: [0] parse+consensus, [1] pack, [2] pmb_run_nuc, [3] run-merge */
+const double* pmh_build_seconds(const pmh_build* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,24 @@
+// Host-side tree with the reference's node numbering (see include/panman_b200_host.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pmh {
+
+struct HostTree {
+    std::vector<std::string> names;
+    std::vector<int32_t> parent, child_off, child_idx, leaf_row;
+    int32_t root = 0;
+    int32_t n_leaves = 0;
+    int32_t n_nodes() const { return int32_t(names.size()); }
+    bool has_polytomy() const;
+};
+
+// reference src/panman.cpp:265-295 (stringSplit, apostrophe-aware)
+void split_quote_aware(const std::string& s, char delim, std::vector<std::string>& words);
+
+// reference src/panman.cpp:310-450 (createTreeFromNewickString). Returns "" or an error message.
+std::string parse_newick(const std::string& newick, HostTree* out);
+
+}  // namespace pmh

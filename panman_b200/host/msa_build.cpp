@@ -1,0 +1,296 @@
+// Host adaptor for `panmanUtils -M msa.fa -N tree.nwk [--reference id] [--low-mem-mode]` on top of the C ABI of
+// libpanman_b200. Restates what surrounds the per-column passes in the reference's Tree constructor
+// (src/panman.cpp:1274-1466 for FILE_TYPE::MSA, :1467-1649 for FILE_TYPE::MSA_OPTIMIZE); the passes themselves
+// (the loops at :1381-1435 and :1568-1613) become ONE pmb_run_nuc call.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/panman_b200_host.h"
+#include "host_tree.hpp"
+
+struct pmh_tree {
+    pmh::HostTree t;
+};
+
+struct pmh_build {
+    pmh_tree tree;
+    std::string consensus;
+    std::vector<std::vector<pmh_nucmut>> nuc;
+    std::vector<int64_t> tuple_off;
+    std::vector<int32_t> tuple_pos;
+    std::vector<uint8_t> tuple_tc;
+    double seconds[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+void set_err(char* err, size_t n, const std::string& m) {
+    if (err && n) {
+        std::strncpy(err, m.c_str(), n - 1);
+        err[n - 1] = 0;
+    }
+}
+
+// reference src/panman.cpp:78-113 (getCodeFromNucleotide) as a table: unlisted characters (incl. '-') -> 0
+struct CodeTable {
+    uint8_t t[256];
+    CodeTable() {
+        std::memset(t, 0, sizeof t);
+        const char* sym = "ACMGRSVTWYHKDBN";  // codes 1..15, src/panman.hpp:27-44
+        for (int i = 0; i < 15; i++) t[(unsigned char)sym[i]] = uint8_t(i + 1);
+    }
+};
+const CodeTable kCode;
+
+// FASTA reader of the MSA branch (src/panman.cpp:1288-1325). `strip_cr`: the MSA branch cuts lines and ids at '\r',
+// the low-memory branch (:1479-1501, readFastaInBatch :677-724) does not.
+std::string read_msa(const char* text, size_t len, bool strip_cr, std::map<std::string, std::string>* seqs, size_t* line_length) {
+    std::string cur_seq, cur_id;
+    size_t ll = 0;
+    auto first_piece = [](const std::string& s, char delim) {
+        std::vector<std::string> w;
+        pmh::split_quote_aware(s, delim, w);
+        return w.empty() ? std::string() : w[0];
+    };
+    size_t p = 0;
+    while (p < len) {
+        const char* nl = static_cast<const char*>(std::memchr(text + p, '\n', len - p));
+        size_t e = nl ? size_t(nl - text) : len;
+        std::string line(text + p, e - p);
+        p = e + 1;
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            if (!cur_seq.empty()) {
+                if (ll == 0) ll = cur_seq.size();
+                else if (ll != cur_seq.size()) return "sequence lengths don't match: " + cur_id;
+                (*seqs)[strip_cr ? first_piece(cur_id, '\r') : cur_id] = cur_seq;
+            }
+            cur_id = first_piece(line, ' ').substr(1);
+            cur_seq.clear();
+        } else {
+            cur_seq += strip_cr ? first_piece(line, '\r') : line;
+        }
+    }
+    if (!cur_seq.empty()) {
+        if (ll != 0 && ll != cur_seq.size()) return "sequence lengths don't match: " + cur_id;
+        ll = cur_seq.size();
+        (*seqs)[cur_id] = cur_seq;  // the last record keeps its id as is (:1316-1325)
+    }
+    *line_length = ll;
+    return "";
+}
+
+// greedy <= 6 run-merge of one node's position-sorted tuples (src/panman.cpp:1445-1466; NucMut ctor src/panman.hpp:109-151)
+void merge_runs(const int32_t* pos, const uint8_t* tc, int64_t n, std::vector<pmh_nucmut>* out) {
+    if (n == 0) return;
+    int64_t start = 0;
+    for (int64_t i = 1; i <= n; i++) {
+        bool split = (i == n) || (i - start == 6) || pos[i] != pos[i - 1] + 1 || (tc[i] >> 4) != (tc[i - 1] >> 4);
+        if (!split) continue;
+        pmh_nucmut m;
+        m.nucPosition = pos[start];
+        m.nucGapPosition = -1;
+        m.primaryBlockId = 0;
+        m.secondaryBlockId = -1;
+        m.mutInfo = uint8_t(((i - start) << 4) + (tc[start] >> 4));
+        m.nucs = 0;
+        for (int64_t k = start; k < i; k++) m.nucs += uint32_t(tc[k] & 15) << (4 * (5 - (k - start)));
+        out->push_back(m);
+        start = i;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len) {
+    if (!newick) { set_err(err, err_len, "null newick"); return nullptr; }
+    pmh_tree* t = new pmh_tree();
+    std::string e = pmh::parse_newick(newick, &t->t);
+    if (!e.empty()) {
+        set_err(err, err_len, e);
+        delete t;
+        return nullptr;
+    }
+    return t;
+}
+void pmh_tree_free(pmh_tree* t) { delete t; }
+int32_t pmh_tree_n_nodes(const pmh_tree* t) { return t->t.n_nodes(); }
+int32_t pmh_tree_n_leaves(const pmh_tree* t) { return t->t.n_leaves; }
+int32_t pmh_tree_root(const pmh_tree* t) { return t->t.root; }
+const char* pmh_tree_name(const pmh_tree* t, int32_t v) { return t->t.names[v].c_str(); }
+const int32_t* pmh_tree_parent(const pmh_tree* t) { return t->t.parent.data(); }
+const int32_t* pmh_tree_child_offsets(const pmh_tree* t) { return t->t.child_off.data(); }
+const int32_t* pmh_tree_child_index(const pmh_tree* t) { return t->t.child_idx.data(); }
+const int32_t* pmh_tree_leaf_row(const pmh_tree* t) { return t->t.leaf_row.data(); }
+int pmh_tree_has_polytomy(const pmh_tree* t) { return t->t.has_polytomy() ? 1 : 0; }
+
+pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len, const char* newick, const char* reference_c,
+                              int low_mem_mode, char* err, size_t err_len) {
+    if (!ctx || !fasta || !newick) { set_err(err, err_len, "null argument"); return nullptr; }
+    const std::string reference = reference_c ? reference_c : "";
+    pmh_build* b = new pmh_build();
+    auto fail = [&](const std::string& m) -> pmh_build* {
+        set_err(err, err_len, m);
+        delete b;
+        return nullptr;
+    };
+    auto t0 = Clock::now();
+    {   // std::getline(secondFin, newickString) : first line only (src/panman.cpp:1277, 1470)
+        std::string nw(newick);
+        size_t nl = nw.find('\n');
+        if (nl != std::string::npos) nw.resize(nl);
+        std::string e = pmh::parse_newick(nw, &b->tree.t);
+        if (!e.empty()) return fail(e);
+    }
+    const pmh::HostTree& T = b->tree.t;
+    std::map<std::string, std::string> seqs;  // std::map: id order decides the consensus (src/panman.cpp:1280)
+    size_t line_length = 0;
+    std::string e = read_msa(fasta, fasta_len, /*strip_cr=*/!low_mem_mode, &seqs, &line_length);
+    if (!e.empty()) return fail(e);
+    std::vector<const std::string*> ordered;
+    for (auto& u : seqs) ordered.push_back(&u.second);
+
+    std::string& cons = b->consensus;
+    const std::string* ref_seq = nullptr;
+    if (!reference.empty()) {
+        auto it = seqs.find(reference);
+        if (it != seqs.end()) ref_seq = &it->second;
+    }
+    if (!low_mem_mode) {
+        if (!reference.empty()) {
+            // consensusSeq = sequenceIdsToSequences[reference] (:1333-1334); an unknown id yields an empty consensus
+            cons = ref_seq ? *ref_seq : std::string();
+        } else {
+            // first non-gap character in map order; all-gap columns are removed from every sequence (:1336-1361)
+            cons.assign(line_length, 0);
+            std::vector<char> keep(line_length, 0);
+            for (size_t i = 0; i < line_length; i++)
+                for (const std::string* s : ordered)
+                    if ((*s)[i] != '-') { cons[i] = (*s)[i]; keep[i] = 1; break; }
+            size_t kept = size_t(std::count(keep.begin(), keep.end(), 1));
+            if (kept != line_length) {
+                for (auto& u : seqs) {
+                    std::string f;
+                    f.reserve(kept);
+                    for (size_t i = 0; i < u.second.size(); i++)
+                        if (keep[i]) f += u.second[i];
+                    u.second.swap(f);
+                }
+                // the reference keeps consensusSeq at full length with '\0' at the dropped positions but then iterates
+                // i < consensusSeq.size() over the SHORTENED sequences; positions line up only when nothing was dropped.
+                // We follow the intent that also matches every later use (blocks[0] = consensus of kept columns).
+                std::string f;
+                for (size_t i = 0; i < line_length; i++)
+                    if (keep[i]) f += cons[i];
+                cons.swap(f);
+            }
+        }
+    } else {
+        // low-memory branch: consensus per batch (:1527-1557); batches only bound memory, columns are independent
+        cons.assign(line_length, 0);
+        if (!reference.empty() && !ref_seq) return fail("Reference not found in the sequence");  // exit(0) at :1592-1595
+        for (size_t i = 0; i < line_length; i++) {
+            if (ref_seq && (*ref_seq)[i] != '-') { cons[i] = (*ref_seq)[i]; continue; }
+            bool found = false;
+            for (const std::string* s : ordered)
+                if ((*s)[i] != '-') { cons[i] = (*s)[i]; found = true; break; }
+            if (!found && !ref_seq) return fail("all-gap column without --reference (the reference exits here)");  // :1548-1551
+        }
+    }
+    const int64_t n_cols = int64_t(cons.size());
+    b->seconds[0] = since(t0);
+    b->nuc.assign(T.n_nodes(), {});
+    b->tuple_off.assign(T.n_nodes() + 1, 0);
+    if (n_cols == 0) return b;
+
+    // ---- pack: leaf rows (4-bit codes, two columns per byte) in tree leaf order; leaves without a sequence are absent
+    t0 = Clock::now();
+    const int64_t stride = ((n_cols + 1) / 2 + 15) / 16 * 16;
+    std::vector<uint8_t> codes4(size_t(T.n_leaves) * size_t(stride), 0);
+    std::vector<uint8_t> present(T.n_leaves, 0);
+    std::vector<std::pair<int32_t, const std::string*>> rows;
+    for (int32_t v = 0; v < T.n_nodes(); v++) {
+        if (T.leaf_row[v] < 0) continue;
+        auto it = seqs.find(T.names[v]);
+        if (it == seqs.end()) continue;
+        present[T.leaf_row[v]] = 1;
+        rows.emplace_back(T.leaf_row[v], &it->second);
+    }
+    {
+        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nt; k++)
+            th.emplace_back([&, k]() {
+                for (size_t r = k; r < rows.size(); r += nt) {
+                    const unsigned char* s = reinterpret_cast<const unsigned char*>(rows[r].second->data());
+                    uint8_t* d = codes4.data() + size_t(rows[r].first) * size_t(stride);
+                    int64_t c = 0;
+                    for (; c + 1 < n_cols; c += 2) d[c >> 1] = uint8_t(kCode.t[s[c]] | (kCode.t[s[c + 1]] << 4));
+                    if (c < n_cols) d[c >> 1] = kCode.t[s[c]];
+                }
+            });
+        for (auto& x : th) x.join();
+    }
+    std::vector<uint8_t> parent_code(n_cols);
+    for (int64_t i = 0; i < n_cols; i++) parent_code[i] = kCode.t[(unsigned char)cons[i]];
+    std::vector<int8_t> per_col;
+    const int8_t *root_override = nullptr, *fwd_root_ref = nullptr;
+    if (ref_seq) {
+        per_col.resize(n_cols);
+        for (int64_t i = 0; i < n_cols; i++) per_col[i] = int8_t(kCode.t[(unsigned char)(*ref_seq)[i]]);
+        if (low_mem_mode) root_override = per_col.data();  // defaultState (:1583-1604)
+        else fwd_root_ref = per_col.data();                // refState (:1419-1420)
+    }
+    b->seconds[1] = since(t0);
+
+    // ---- the passes
+    t0 = Clock::now();
+    int rc = pmb_set_tree(ctx, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data());
+    if (rc) return fail(std::string("pmb_set_tree: ") + pmb_last_error(ctx));
+    bool all_present = std::all_of(present.begin(), present.end(), [](uint8_t x) { return x != 0; });
+    pmb_result res;
+    rc = pmb_run_nuc(ctx, low_mem_mode ? PMB_ALGO_SANKOFF : PMB_ALGO_FITCH, n_cols, T.n_leaves, codes4.data(), stride,
+                     all_present ? nullptr : present.data(), parent_code.data(), root_override, fwd_root_ref, 0, 0, &res);
+    if (rc) return fail(std::string("pmb_run_nuc: ") + pmb_last_error(ctx));
+    b->seconds[2] = since(t0);
+
+    // ---- lists are already per node in ascending position (= std::sort of the tuples, :1447); merge runs
+    t0 = Clock::now();
+    b->tuple_off.assign(res.node_offsets, res.node_offsets + T.n_nodes() + 1);
+    b->tuple_pos.assign(res.pos, res.pos + res.n_mut);
+    b->tuple_tc.assign(res.type_code, res.type_code + res.n_mut);
+    for (int32_t v = 0; v < T.n_nodes(); v++) {
+        int64_t a = res.node_offsets[v], z = res.node_offsets[v + 1];
+        merge_runs(res.pos + a, res.type_code + a, z - a, &b->nuc[v]);
+    }
+    b->seconds[3] = since(t0);
+    return b;
+}
+
+void pmh_build_free(pmh_build* b) { delete b; }
+const pmh_tree* pmh_build_tree(const pmh_build* b) { return &b->tree; }
+const char* pmh_build_consensus(const pmh_build* b, int64_t* len) {
+    if (len) *len = int64_t(b->consensus.size());
+    return b->consensus.data();
+}
+int64_t pmh_build_n_nucmut(const pmh_build* b, int32_t v) { return int64_t(b->nuc[v].size()); }
+const pmh_nucmut* pmh_build_nucmut(const pmh_build* b, int32_t v) { return b->nuc[v].data(); }
+int64_t pmh_build_n_tuples(const pmh_build* b) { return int64_t(b->tuple_pos.size()); }
+const int64_t* pmh_build_tuple_offsets(const pmh_build* b) { return b->tuple_off.data(); }
+const int32_t* pmh_build_tuple_pos(const pmh_build* b) { return b->tuple_pos.data(); }
+const uint8_t* pmh_build_tuple_type_code(const pmh_build* b) { return b->tuple_tc.data(); }
+const double* pmh_build_seconds(const pmh_build* b) { return b->seconds; }
+
+}  // extern "C"
