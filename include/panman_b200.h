@@ -89,8 +89,10 @@ typedef struct pmb_timings {
 int pmb_create(pmb_ctx** ctx, int device);
 void pmb_destroy(pmb_ctx* ctx);
 const char* pmb_last_error(const pmb_ctx* ctx);
-/* Tuning knobs (all optional): "chunk_nodes" (internal nodes per sequential chunk), "staging_records"
- * (initial capacity of the mutation staging pool), "use_graph" (1 = replay the level schedule as a CUDA graph). */
+/* Tuning knobs (all optional): "chunk_nodes" (largest bottom subtree evaluated by one warp; 0 = chosen from the
+ * column count), "inline_nodes" (light subtrees up to this size stay in their parent's chunk), "schedule"
+ * (1 = persistent kernels with dependency flags [default], 0 = one launch per dependency level),
+ * "staging_records" (initial capacity of the mutation staging pool; 0 = chosen from the problem size). */
 int pmb_set_option(pmb_ctx* ctx, const char* key, int64_t value);
 
 /* ---- tree: replaces the Node* tree walked by every reference call ----

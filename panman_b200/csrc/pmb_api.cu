@@ -68,14 +68,17 @@ struct pmb_ctx {
     // options
     int64_t opt_chunk_nodes = 0;      // 0 = choose from the tile count
     int64_t opt_staging_records = 0;  // 0 = choose from the problem size
-    int64_t opt_use_graph = 0;
+    int64_t opt_inline_nodes = 3;     // light subtrees up to this size are evaluated inside the parent's chunk
+    int64_t opt_schedule = 1;         // 1 = persistent kernels with dependency flags, 0 = one launch per level
+    int n_sms = 0;
+    unsigned int epoch = 0;
 
     // tree
     bool have_tree = false;
     int32_t n_nodes = 0, root = -1;
     std::vector<int32_t> child_off, child_idx, leaf_row;
     TreeProgram prog;
-    int32_t prog_chunk_nodes = -1;
+    int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1;
     DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks;
 
     // resident input
@@ -86,6 +89,7 @@ struct pmb_ctx {
     DevBuf d_leaf_planes, d_present, d_colparams, d_tmp_codes, d_tmp_cols;
 
     // work + result
+    DevBuf d_done, d_fdone, d_ticket;
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_node_counts, d_offsets, d_pos, d_tc,
         d_states_u8;
     unsigned long long staging_cap = 0;
@@ -137,9 +141,10 @@ int32_t pick_chunk_nodes(const pmb_ctx* c) {
 
 int ensure_program(pmb_ctx* c) {
     int32_t k = pick_chunk_nodes(c);
-    if (k == c->prog_chunk_nodes) return PMB_OK;
+    int32_t inl = int32_t(std::max<int64_t>(0, std::min<int64_t>(c->opt_inline_nodes, 1 << 20)));
+    if (k == c->prog_chunk_nodes && inl == c->prog_inline_nodes) return PMB_OK;
     std::string e = build_tree_program(c->n_nodes, c->root, c->child_off.data(), c->child_idx.data(), c->leaf_row.data(), k,
-                                       &c->prog);
+                                       inl, &c->prog);
     if (!e.empty()) return fail(c, PMB_ERR_INVALID, e);
     int rc;
     if ((rc = upload_vec(c, c->d_fwd_ops, c->prog.fwd_ops))) return rc;
@@ -149,33 +154,74 @@ int ensure_program(pmb_ctx* c) {
     if ((rc = upload_vec(c, c->d_chunks, c->prog.chunks))) return rc;
     PMB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above may be rebuilt before the copies ran
     c->prog_chunk_nodes = k;
+    c->prog_inline_nodes = inl;
     return PMB_OK;
 }
 
-int launch_levels(pmb_ctx* c, const RunParams& rp, int algo, bool forward, int* n_launches) {
+// zero-filled on growth: flag words hold the epoch of the run that published them, epochs start at 1
+int ensure_flags(pmb_ctx* c, DevBuf& buf, size_t words) {
+    size_t bytes = std::max<size_t>(16, words * sizeof(unsigned int));
+    if (bytes <= buf.cap) return PMB_OK;
+    PMB_CUDA(buf.ensure(bytes));
+    PMB_CUDA(cudaMemsetAsync(buf.p, 0, buf.cap, c->stream));
+    return PMB_OK;
+}
+
+template <class K>
+int launch_kernel(pmb_ctx* c, K kernel, size_t smem, const RunParams& rp_in, int chunk_begin, int n_chunks, int* n_launches) {
+    RunParams rp = rp_in;
+    dim3 block(WARPS_PER_BLOCK * 32);
+    long long warps = (long long)n_chunks * c->T;
+    if (warps <= 0) return PMB_OK;
+    unsigned blocks;
+    if (rp.ticket) {
+        int per_sm = 0;
+        PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, smem));
+        long long resident = (long long)std::max(1, per_sm) * c->n_sms;
+        blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
+        PMB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(unsigned long long), c->stream));
+    } else {
+        blocks = unsigned((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    }
+    kernel<<<blocks, block, smem, c->stream>>>(rp, chunk_begin, n_chunks);
+    (*n_launches)++;
+    return PMB_OK;
+}
+
+template <class K>
+int launch_schedule(pmb_ctx* c, K kernel, size_t smem, RunParams rp, bool forward, int* n_launches) {
     const TreeProgram& P = c->prog;
-    const int L = P.n_levels();
-    for (int i = 0; i < L; i++) {
-        int l = forward ? i : L - 1 - i;
-        int cb = P.level_chunk_begin[l], nc = P.level_chunk_begin[l + 1] - cb;
-        if (nc <= 0) continue;
-        long long warps = (long long)nc * c->T;
-        unsigned blocks = unsigned((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-        dim3 block(WARPS_PER_BLOCK * 32);
-        if (algo == PMB_ALGO_FITCH) {
-            if (forward) fitch_forward_kernel<<<blocks, block, 0, c->stream>>>(rp, cb, nc);
-            else fitch_backward_kernel<<<blocks, block, 0, c->stream>>>(rp, cb, nc);
-        } else {
-            if (!forward) sankoff_backward_kernel<<<blocks, block, 0, c->stream>>>(rp, cb, nc);
-            else if (P.max_arity <= 3) sankoff_forward_kernel<2><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
-            else if (P.max_arity <= 15) sankoff_forward_kernel<4><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
-            else if (P.max_arity <= 255) sankoff_forward_kernel<8><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
-            else sankoff_forward_kernel<20><<<blocks, block, 0, c->stream>>>(rp, cb, nc);
+    int rc;
+    if (smem > 48 * 1024) PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (c->opt_schedule == 1) {
+        rp.ticket = c->d_ticket.as<unsigned long long>();
+        if ((rc = launch_kernel(c, kernel, smem, rp, 0, int(P.chunks.size()), n_launches))) return rc;
+    } else {
+        rp.ticket = nullptr;
+        const int L = P.n_levels();
+        for (int i = 0; i < L; i++) {
+            int l = forward ? i : L - 1 - i;
+            int cb = P.level_chunk_begin[l], nc = P.level_chunk_begin[l + 1] - cb;
+            if ((rc = launch_kernel(c, kernel, smem, rp, cb, nc, n_launches))) return rc;
         }
-        (*n_launches)++;
     }
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
+}
+
+int launch_pass(pmb_ctx* c, const RunParams& rp, int algo, bool forward, int* n_launches) {
+    const TreeProgram& P = c->prog;
+    const size_t fwd_smem = size_t(WARPS_PER_BLOCK) * FWD_DEPTH * FWD_STAGE_U4 * sizeof(uint4);
+    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * BWD_DEPTH * (4 + 2) * 32 * sizeof(uint4);
+    const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * BWD_DEPTH * (8 + 2) * 32 * sizeof(uint4);
+    if (algo == PMB_ALGO_FITCH)
+        return forward ? launch_schedule(c, fitch_forward_kernel, fwd_smem, rp, true, n_launches)
+                       : launch_schedule(c, fitch_backward_kernel, bwd_smem_f, rp, false, n_launches);
+    if (!forward) return launch_schedule(c, sankoff_backward_kernel, bwd_smem_s, rp, false, n_launches);
+    if (P.max_arity <= 3) return launch_schedule(c, sankoff_forward_kernel<2>, fwd_smem, rp, true, n_launches);
+    if (P.max_arity <= 15) return launch_schedule(c, sankoff_forward_kernel<4>, fwd_smem, rp, true, n_launches);
+    if (P.max_arity <= 255) return launch_schedule(c, sankoff_forward_kernel<8>, fwd_smem, rp, true, n_launches);
+    return launch_schedule(c, sankoff_forward_kernel<20>, fwd_smem, rp, true, n_launches);
 }
 
 }  // namespace
@@ -200,6 +246,8 @@ int pmb_create(pmb_ctx** out, int device) {
         *out = c;
         return PMB_ERR_CUDA;
     }
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (c->n_sms <= 0) c->n_sms = 148;
     *out = c;
     return PMB_OK;
 }
@@ -212,7 +260,7 @@ void pmb_destroy(pmb_ctx* c) {
         for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_leaf_planes,
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
-                          &c->d_pos, &c->d_tc, &c->d_states_u8})
+                          &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters}) b->release();
         for (int i = 0; i < 4; i++)
@@ -229,7 +277,8 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "chunk_nodes") c->opt_chunk_nodes = value;
     else if (k == "staging_records") c->opt_staging_records = value;
-    else if (k == "use_graph") c->opt_use_graph = value;
+    else if (k == "inline_nodes") c->opt_inline_nodes = value;
+    else if (k == "schedule") c->opt_schedule = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
 }
@@ -241,7 +290,7 @@ int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child
     if (n_nodes < 2 || !child_offsets || !child_index || !leaf_row) return fail(c, PMB_ERR_INVALID, "bad tree arguments");
     // validate with a throw-away build (chunk size does not matter for validity)
     TreeProgram probe;
-    std::string e = build_tree_program(n_nodes, root, child_offsets, child_index, leaf_row, 64, &probe);
+    std::string e = build_tree_program(n_nodes, root, child_offsets, child_index, leaf_row, 64, 3, &probe);
     if (!e.empty()) return fail(c, PMB_ERR_INVALID, e);
     c->n_nodes = n_nodes;
     c->root = root;
@@ -333,6 +382,12 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     PMB_CUDA(c->d_dir.ensure(size_t(P.n_nodes) * T * sizeof(unsigned long long)));
     PMB_CUDA(c->d_counters.ensure(64));
     PMB_CUDA(c->h_counters.ensure(64));
+    PMB_CUDA(c->d_ticket.ensure(64));
+    {
+        int rcf;
+        if ((rcf = ensure_flags(c, c->d_done, size_t(P.n_internal) * T))) return rcf;
+        if ((rcf = ensure_flags(c, c->d_fdone, size_t(std::max(1, P.n_fslots)) * T))) return rcf;
+    }
     PMB_CUDA(c->d_node_counts.ensure(size_t(P.n_nodes) * sizeof(unsigned long long)));
     PMB_CUDA(c->d_offsets.ensure(size_t(P.n_nodes + 1) * sizeof(long long)));
     if (c->staging_cap == 0) {
@@ -357,12 +412,16 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     rp.dir = c->d_dir.as<unsigned long long>();
     rp.pool_count = c->d_counters.as<unsigned long long>();
     rp.error = reinterpret_cast<unsigned int*>(c->d_counters.as<unsigned long long>() + 1);
+    rp.done = c->d_done.as<unsigned int>();
+    rp.fdone = c->d_fdone.as<unsigned int>();
+    rp.ticket = nullptr;
     rp.T = c->T;
     rp.flags = ((flags & PMB_FLAG_BLOCK_MODE) ? RUN_BLOCK_MODE : 0) | (want_states ? RUN_WANT_STATES : 0);
 
     int n_launches = 0;
     PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    int rc = launch_levels(c, rp, algo, true, &n_launches);
+    rp.epoch = ++c->epoch;
+    int rc = launch_pass(c, rp, algo, true, &n_launches);
     if (rc) return rc;
     PMB_CUDA(cudaEventRecord(c->ev[1], c->stream));
     for (int attempt = 0;; attempt++) {
@@ -374,7 +433,8 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, size_t(P.n_nodes) * T * sizeof(unsigned long long), c->stream));
         unsigned int init[4] = {0, 0, 0, 0xFFFFFFFFu};  // pool_count (64 bit), error flags, first bad column
         PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-        if ((rc = launch_levels(c, rp, algo, false, &n_launches))) return rc;
+        rp.epoch = ++c->epoch;
+        if ((rc = launch_pass(c, rp, algo, false, &n_launches))) return rc;
         PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
         {
             unsigned blocks = unsigned(((long long)P.n_nodes * 32 + 255) / 256);
@@ -390,6 +450,7 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         PMB_CUDA(cudaStreamSynchronize(c->stream));
         unsigned long long total = *c->h_counters.as<unsigned long long>();
         unsigned int eflags = c->h_counters.as<unsigned int>()[2], ecol = c->h_counters.as<unsigned int>()[3];
+        if (eflags & 2u) return fail(c, PMB_ERR_INTERNAL, "scheduler watchdog fired: a dependency flag never arrived");
         if (eflags & 1u) {
             char buf[160];
             snprintf(buf, sizeof buf, "Sankoff root has no finite cost at column %lld and no root override was given",

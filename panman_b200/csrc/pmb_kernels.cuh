@@ -40,10 +40,13 @@ struct RunParams {
     uint16_t* staging;
     unsigned long long* pool_count;
     unsigned long long staging_cap;
-    unsigned int* error;          // [0] flags, [1] first offending column
+    unsigned int* error;          // [0] flags (1 Sankoff root undefined, 2 scheduler watchdog), [1] first offending column
+    unsigned int* done;           // [op][tile]   forward: set matrix row published (value = epoch)
+    unsigned int* fdone;          // [fslot][tile] backward: assigned-state slot published
+    unsigned long long* ticket;   // persistent launch: work-item counter; nullptr = one static item per warp
+    unsigned int epoch;
     int T;
     int flags;
-    long long col_base_tile0;     // unused by kernels that emit tile-local columns; kept for diagnostics
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
@@ -60,14 +63,82 @@ __device__ __forceinline__ void store_planes16(uint4* base, int lane, const uint
 #pragma unroll
     for (int j = 0; j < 4; j++) base[j * 32 + lane] = make_uint4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
 }
+__device__ __forceinline__ void unpack16(const uint4 v[4], uint32_t S[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) { S[4 * j] = v[j].x; S[4 * j + 1] = v[j].y; S[4 * j + 2] = v[j].z; S[4 * j + 3] = v[j].w; }
+}
 
-__device__ __forceinline__ bool warp_item(const RunParams& p, int chunk_begin, int n_chunks, int& chunk, int& tile, int& lane) {
-    long long warp = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    lane = threadIdx.x & 31;
-    if (warp >= (long long)n_chunks * p.T) return false;
-    chunk = chunk_begin + int(warp / p.T);
-    tile = int(warp % p.T);
+// ------------------------------------------------------------------ work items and dependencies
+// A work item is (chunk, tile). Level launches give every warp one static item; the persistent launch hands
+// items out through an atomic ticket in the program's topological chunk order (reverse for the backward pass).
+// An item may only wait for data of items with SMALLER tickets, and every ticket holder is a resident, running
+// warp, so the lowest unfinished ticket always makes progress: no deadlock, no co-residency requirement.
+struct ItemIter {
+    bool taken = false;
+};
+__device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int chunk_begin, int n_chunks, bool reverse,
+                                          int& chunk, int& tile, int lane) {
+    unsigned long long w;
+    if (p.ticket) {
+        if (lane == 0) w = atomicAdd(p.ticket, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+    } else {
+        if (it.taken) return false;
+        it.taken = true;
+        w = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    }
+    if (w >= (unsigned long long)n_chunks * (unsigned long long)p.T) return false;
+    int c = int(w / (unsigned)p.T);
+    chunk = chunk_begin + (reverse ? n_chunks - 1 - c : c);
+    tile = int(w % (unsigned)p.T);
     return true;
+}
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Warp-collective wait until *flag == epoch. Lane 0 polls with back-off; a watchdog (wall clock) turns a
+// scheduling bug into error bit 2 instead of a hung GPU. Returns false if the run must be abandoned.
+__device__ __noinline__ bool wait_flag_slow(const unsigned* flag, unsigned epoch, unsigned* error, int lane) {
+    unsigned ok = 1;
+    if (lane == 0) {
+        unsigned long long t0 = global_ns();
+        unsigned spins = 0;
+        while (ld_acquire(flag) != epoch) {
+            __nanosleep(64);
+            if ((++spins & 255u) == 0) {
+                if ((*reinterpret_cast<volatile unsigned*>(error) & 2u) || global_ns() - t0 > 20000000000ull) {
+                    atomicOr(error, 2u);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+    }
+    return __shfl_sync(FULL, ok, 0) != 0;
+}
+__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, unsigned* error, int lane) {
+    unsigned v = 0;
+    if (lane == 0) v = ld_acquire(flag);
+    v = __shfl_sync(FULL, v, 0);
+    if (v == epoch) return true;
+    return wait_flag_slow(flag, epoch, error, lane);
+}
+// Publish: every lane's earlier stores happen-before the release store of lane 0 (warp barrier + release).
+__device__ __forceinline__ void signal_flag(unsigned* flag, unsigned epoch, int lane) {
+    __syncwarp();
+    if (lane == 0) st_release(flag, epoch);
 }
 
 __device__ __forceinline__ uint32_t leaf_present_mask(const RunParams& p, int row) {
@@ -116,127 +187,261 @@ __device__ __forceinline__ void store_state(const RunParams& p, int node, int ti
     s[32 + lane] = make_uint4(vis, 0, 0, 0);
 }
 
+// ------------------------------------------------------------------ asynchronous input ring (cp.async)
+// Every warp keeps a ring of DEPTH "stages" in shared memory, one stage per upcoming op, filled with LDGSTS
+// (cp.async.cg, 16 B per lane = 512 B per warp instruction) DEPTH ops ahead of use. Only IMMUTABLE inputs go
+// through the ring -- leaf rows, and in the backward pass the set rows written by the finished forward pass --
+// so no ordering against this kernel's own stores is ever needed. Each lane copies and later reads its own
+// 16 bytes: completion is tracked per thread with cp.async.wait_group, no barrier involved.
+__device__ __forceinline__ void cp_async16(uint4* smem_dst, const uint4* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n groups still in flight
+    switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+
+constexpr int FWD_DEPTH = 6;       // forward: stage = 2 leaf rows            (1 KB per warp and stage)
+constexpr int FWD_STAGE_U4 = 2 * 32;
+constexpr int BWD_DEPTH = 3;       // backward: stage = set row + 2 leaf rows (3 KB Fitch / 5 KB Sankoff)
+
+// forward: queue the (first two) leaf rows of `op` into its stage; always commits one group
+__device__ __forceinline__ void fwd_issue(const RunParams& p, uint4* ring, int op, int op_begin, int tile, int lane) {
+    const size_t T = p.T;
+    const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+    uint4* st = ring + ((op - op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
+    int nl = 0;
+    for (int r = 0; r < f.y && nl < 2; r++) {
+        const uint32_t ref = __ldg(p.refs + f.x + r);
+        if ((ref >> 30) == REF_LEAF) {
+            cp_async16(st + nl * 32 + lane, p.leaf_planes + ((size_t)(ref & REF_IDX_MASK) * T + tile) * 32 + lane);
+            nl++;
+        }
+    }
+    cp_async_commit();
+}
+
 // ------------------------------------------------------------------ Fitch forward
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
-    int chunk, tile, lane;
-    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
-    const Chunk ck = p.chunks[chunk];
+    extern __shared__ uint4 smem[];
+    const int lane = threadIdx.x & 31;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FWD_DEPTH * FWD_STAGE_U4;
     const size_t T = p.T;
-    uint32_t acc[16];
+    ItemIter it;
+    int chunk, tile;
+    while (next_item(p, it, chunk_begin, n_chunks, false, chunk, tile, lane)) {
+        const Chunk ck = p.chunks[chunk];
+        uint32_t acc[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = 0;
-    for (int op = ck.op_begin; op < ck.op_end; op++) {
-        const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));  // ref_begin, n_refs, flags, bits
-        FitchFold fold;
-        fold.reset();
-        for (int r = 0; r < f.y; r++) {
-            const uint32_t ref = __ldg(p.refs + f.x + r);
-            const uint32_t kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
-            if (kind == REF_LEAF) {
-                uint4 c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
-                uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-                fold.add_leaf(cc, leaf_present_mask(p, idx));
-            } else if (kind == REF_ACC) {
-                fold.add_set(acc);
-            } else {
-                uint32_t S[16];
-                load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
-                fold.add_set(S);
+        for (int k = 0; k < 16; k++) acc[k] = 0;
+        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) fwd_issue(p, ring, ck.op_begin + i, ck.op_begin, tile, lane);
+        for (int op = ck.op_begin; op < ck.op_end; op++) {
+            const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));  // ref_begin, n_refs, flags, bits
+            cp_async_wait_pending(min(FWD_DEPTH - 1, ck.op_end - 1 - op));
+            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
+            const uint4 l0 = st[lane], l1 = st[32 + lane];
+            if (op + FWD_DEPTH < ck.op_end) fwd_issue(p, ring, op + FWD_DEPTH, ck.op_begin, tile, lane);  // refill this stage
+            FitchFold fold;
+            fold.reset();
+            int nl = 0;
+            for (int r = 0; r < f.y; r++) {
+                const uint32_t ref = __ldg(p.refs + f.x + r);
+                const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
+                if (kind == REF_LEAF) {
+                    uint4 c;
+                    if (nl == 0) c = l0;
+                    else if (nl == 1) c = l1;
+                    else c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+                    nl++;
+                    uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                    fold.add_leaf(cc, leaf_present_mask(p, idx));
+                } else if (kind == REF_ACC) {
+                    fold.add_set(acc);
+                } else {
+                    if (ref & REF_EXT) {
+                        if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return;
+                    }
+                    uint32_t S[16];
+                    load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
+                    fold.add_set(S);
+                }
             }
-        }
-        fold.finish(acc);
-        if ((f.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
-            // refState: the root's forward value is replaced (fitchSankoff.cpp:45-47)
-            const uint4* cp = p.colparams + (size_t)tile * 128;
-            uint4 rc = __ldg(cp + 64 + lane);
-            uint32_t rv = __ldg(cp + 96 + lane).y;
-            uint32_t r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
-            decode16(r4, d);
+            fold.finish(acc);
+            if ((f.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
+                // refState: the root's forward value is replaced (fitchSankoff.cpp:45-47)
+                const uint4* cp = p.colparams + (size_t)tile * 128;
+                uint4 rc = __ldg(cp + 64 + lane);
+                uint32_t rv = __ldg(cp + 96 + lane).y;
+                uint32_t r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
+                decode16(r4, d);
 #pragma unroll
-            for (int k = 0; k < 16; k++) acc[k] = (rv & d[k]) | (~rv & acc[k]);
+                for (int k = 0; k < 16; k++) acc[k] = (rv & d[k]) | (~rv & acc[k]);
+            }
+            store_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, acc);
+            if (f.z & OPF_SIGNAL) signal_flag(p.done + (size_t)op * T + tile, p.epoch, lane);
         }
-        store_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, acc);
+    }
+}
+
+// ------------------------------------------------------------------ backward: shared pieces
+// stage layout: [J set-row vectors][2 leaf rows], each 32 lanes wide; J = 4 (Fitch) or 8 (Sankoff)
+template <int J>
+__device__ __forceinline__ void bwd_issue(const RunParams& p, uint4* ring, int op, int op_last, int tile, int lane) {
+    const size_t T = p.T;
+    uint4* st = ring + ((op_last - op) % BWD_DEPTH) * ((J + 2) * 32);
+    const uint4* srow = p.sets + ((size_t)op * T + tile) * (J * 32);
+#pragma unroll
+    for (int j = 0; j < J; j++) cp_async16(st + j * 32 + lane, srow + j * 32 + lane);
+    const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
+    const int nl = __ldg(reinterpret_cast<const int*>(p.bwd_ops + op) + 4);
+    for (int l = 0; l < nl && l < 2; l++) {
+        const int row = __ldg(&p.bwd_leaves[b0.w + l].row);
+        cp_async16(st + (J + l) * 32 + lane, p.leaf_planes + ((size_t)row * T + tile) * 32 + lane);
+    }
+    cp_async_commit();
+}
+
+struct BwdHead {
+    int4 b0;  // node, parent_ref, fslot_out, leaf_begin
+    int4 b1;  // n_leaves, flags
+};
+
+// parent's assigned state from registers (ACC) or from its parked slot (possibly written by another chunk)
+__device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h, int tile, int lane, const uint32_t accF[4],
+                                           uint32_t accVis, uint32_t P[4], uint32_t& pvis) {
+    if (h.b0.y == PARENT_ACC) {
+        P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
+        pvis = accVis;
+        return true;
+    }
+    const size_t T = p.T;
+    if (h.b1.y & OPF_PARENT_EXT) {
+        if (!wait_flag(p.fdone + (size_t)h.b0.y * T + tile, p.epoch, p.error, lane)) return false;
+    }
+    const uint4* fs = p.fstore + ((size_t)h.b0.y * T + tile) * 64;
+    uint4 a = ld_l2(fs + lane);
+    pvis = ld_l2(fs + 32 + lane).x;
+    P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
+    return true;
+}
+
+// what follows the assignment of an internal node, shared by Fitch and Sankoff: its own record, the parked
+// state for later children, and its leaf children (a present leaf is always assigned its own code)
+__device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdHead& h, const uint4* leaf_stage, int tile, int lane,
+                                              const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block) {
+    const size_t T = p.T;
+    emit(p, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
+    if (h.b0.z >= 0) {
+        uint4* fs = p.fstore + ((size_t)h.b0.z * T + tile) * 64;
+        fs[lane] = make_uint4(F[0], F[1], F[2], F[3]);
+        fs[32 + lane] = make_uint4(vis, 0, 0, 0);
+        if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + (size_t)h.b0.z * T + tile, p.epoch, lane);
+    }
+    if (p.states) store_state(p, h.b0.x, tile, lane, F, vis);
+    for (int l = 0; l < h.b1.x; l++) {
+        const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + h.b0.w + l));  // row, node
+        uint4 c;
+        if (l < 2) c = leaf_stage[l * 32 + lane];
+        else c = ld_stream(p.leaf_planes + ((size_t)lf.x * T + tile) * 32 + lane);
+        uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+        uint32_t present = leaf_present_mask(p, lf.x);
+        if (sankoff_block && !present) {  // omitted block leaf = "absent" state (fitchSankoff.cpp:711-714)
+            cc[0] = cc[1] = cc[2] = cc[3] = 0;
+            present = FULL;
+        }
+        const uint32_t lvis = vis & present;
+        emit(p, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
+        if (p.states) {
+            uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
+            store_state(p, lf.y, tile, lane, m4, lvis);
+        }
     }
 }
 
 // ------------------------------------------------------------------ Fitch backward + mutation detection
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
-    int chunk, tile, lane;
-    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
-    const Chunk ck = p.chunks[chunk];
-    const size_t T = p.T;
-    uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
-    for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
-        const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));      // node, parent_ref, fslot_out, leaf_begin
-        const int4 b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);  // n_leaves, flags
-        uint32_t S[16];
-        load_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, S);
-        uint32_t P[4], F[4], vis;
-        if (b0.y == PARENT_ROOT) {
-            const uint4* cp = p.colparams + (size_t)tile * 128;
-            uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
-            P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
-            uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w};
-            const uint32_t ov_valid = fl.x & fl.z, colmask = fl.z;
-            if (p.flags & RUN_BLOCK_MODE) {
-                // blockFitchBackwardPassNew: the root is treated like any node with parentState (:249-263)
-                uint32_t v0;
-                fitch_assign(S, P, colmask, F, v0);
-                vis = (v0 | ov_valid) & colmask;
+    extern __shared__ uint4 smem[];
+    constexpr int J = 4, STAGE = (J + 2) * 32;
+    const int lane = threadIdx.x & 31;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
+    ItemIter it;
+    int chunk, tile;
+    while (next_item(p, it, chunk_begin, n_chunks, true, chunk, tile, lane)) {
+        const Chunk ck = p.chunks[chunk];
+        const int last = ck.op_end - 1;
+        uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
+        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, ring, last - i, last, tile, lane);
+        for (int op = last; op >= ck.op_begin; op--) {
+            BwdHead h;
+            h.b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
+            h.b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
+            uint32_t P[4], pvis = 0, F[4], vis;
+            if (h.b0.y != PARENT_ROOT) {
+                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis)) return;
+            }
+            cp_async_wait_pending(min(BWD_DEPTH - 1, op - ck.op_begin));
+            const uint4* st = ring + ((last - op) % BWD_DEPTH) * STAGE;
+            uint32_t S[16];
 #pragma unroll
-                for (int k = 0; k < 4; k++) F[k] = ((ov_valid & o4[k]) | (~ov_valid & F[k])) & vis;
+            for (int j = 0; j < 4; j++) {
+                uint4 v = st[j * 32 + lane];
+                S[4 * j] = v.x; S[4 * j + 1] = v.y; S[4 * j + 2] = v.z; S[4 * j + 3] = v.w;
+            }
+            if (h.b0.y == PARENT_ROOT) {
+                const uint4* cp = p.colparams + (size_t)tile * 128;
+                uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
+                P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
+                uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w};
+                const uint32_t ov_valid = fl.x & fl.z, colmask = fl.z;
+                if (p.flags & RUN_BLOCK_MODE) {
+                    // blockFitchBackwardPassNew: the root is treated like any node with parentState (:249-263)
+                    uint32_t v0;
+                    fitch_assign(S, P, colmask, F, v0);
+                    vis = (v0 | ov_valid) & colmask;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) F[k] = ((ov_valid & o4[k]) | (~ov_valid & F[k])) & vis;
+                } else {
+                    fitch_assign_root(S, o4, ov_valid, colmask, F, vis);
+                }
             } else {
-                fitch_assign_root(S, o4, ov_valid, colmask, F, vis);
+                fitch_assign(S, P, pvis, F, vis);
             }
-        } else {
-            uint32_t pvis;
-            if (b0.y == PARENT_ACC) {
-                P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
-                pvis = accVis;
-            } else {
-                const uint4* fs = p.fstore + ((size_t)b0.y * T + tile) * 64;
-                uint4 a = ld_l2(fs + lane);
-                pvis = ld_l2(fs + 32 + lane).x;
-                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
-            }
-            fitch_assign(S, P, pvis, F, vis);
+            bwd_finish_op(p, h, st + J * 32, tile, lane, P, F, vis, false);
+            // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
+            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, ring, op - BWD_DEPTH, last, tile, lane);
+            accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
+            accVis = vis;
         }
-        emit(p, b0.x, tile, lane, vis & differs4(F, P), P, F);
-        if (b0.z >= 0) {
-            uint4* fs = p.fstore + ((size_t)b0.z * T + tile) * 64;
-            fs[lane] = make_uint4(F[0], F[1], F[2], F[3]);
-            fs[32 + lane] = make_uint4(vis, 0, 0, 0);
-        }
-        if (p.states) store_state(p, b0.x, tile, lane, F, vis);
-        for (int l = 0; l < b1.x; l++) {
-            const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + b0.w + l));  // row, node
-            uint4 c = ld_stream(p.leaf_planes + ((size_t)lf.x * T + tile) * 32 + lane);
-            uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-            // a present leaf's set is one-hot: assigned state = its own code wherever the parent was assigned
-            const uint32_t lvis = vis & leaf_present_mask(p, lf.x);
-            emit(p, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
-            if (p.states) {
-                uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
-                store_state(p, lf.y, tile, lane, m4, lvis);
-            }
-        }
-        accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
-        accVis = vis;
     }
 }
 
 // ------------------------------------------------------------------ Sankoff forward
 template <int B>
-__device__ __forceinline__ void sankoff_forward_op(const RunParams& p, const int4 f, int tile, int lane, uint32_t accG[16],
-                                                   uint32_t accH[16]) {
+__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int4 f, const uint4 l0, const uint4 l1, int tile,
+                                                   int lane, uint32_t accG[16], uint32_t accH[16]) {
     const size_t T = p.T;
     SankoffFold<B> fold;
     fold.reset();
+    int nl = 0;
     for (int r = 0; r < f.y; r++) {
         const uint32_t ref = __ldg(p.refs + f.x + r);
-        const uint32_t kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+        const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
         if (kind == REF_LEAF) {
-            uint4 c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+            uint4 c;
+            if (nl == 0) c = l0;
+            else if (nl == 1) c = l1;
+            else c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+            nl++;
             uint32_t present = leaf_present_mask(p, idx);
             uint32_t cc[4] = {c.x, c.y, c.z, c.w};
             if ((p.flags & RUN_BLOCK_MODE) && !present) {  // omitted block leaf = "absent" state (:711-714)
@@ -247,6 +452,9 @@ __device__ __forceinline__ void sankoff_forward_op(const RunParams& p, const int
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
+            if (ref & REF_EXT) {
+                if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return false;
+            }
             const uint4* base = p.sets + ((size_t)idx * T + tile) * 256;
             uint32_t G[16];
             load_planes16(base, lane, G);
@@ -255,97 +463,96 @@ __device__ __forceinline__ void sankoff_forward_op(const RunParams& p, const int
         }
     }
     fold.finish(accG, accH);
+    return true;
 }
 
 // MAXB = widest child counter any op of this tree needs (2: up to 3 children, 4: 15, 8: 255, 20: more), so
 // that binary trees do not pay registers for polytomy paths.
 template <int MAXB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
-    int chunk, tile, lane;
-    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
-    const Chunk ck = p.chunks[chunk];
+    extern __shared__ uint4 smem[];
+    const int lane = threadIdx.x & 31;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FWD_DEPTH * FWD_STAGE_U4;
     const size_t T = p.T;
-    uint32_t accG[16], accH[16];
+    ItemIter it;
+    int chunk, tile;
+    while (next_item(p, it, chunk_begin, n_chunks, false, chunk, tile, lane)) {
+        const Chunk ck = p.chunks[chunk];
+        uint32_t accG[16], accH[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
-    for (int op = ck.op_begin; op < ck.op_end; op++) {
-        const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
-        if (MAXB == 2 || f.w == 2) sankoff_forward_op<2>(p, f, tile, lane, accG, accH);
-        else if (MAXB == 4 || f.w == 4) sankoff_forward_op<4>(p, f, tile, lane, accG, accH);
-        else if (MAXB == 8 || f.w == 8) sankoff_forward_op<8>(p, f, tile, lane, accG, accH);
-        else sankoff_forward_op<20>(p, f, tile, lane, accG, accH);
-        uint4* base = p.sets + ((size_t)op * T + tile) * 256;
-        store_planes16(base, lane, accG);
-        store_planes16(base + 128, lane, accH);
+        for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
+        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) fwd_issue(p, ring, ck.op_begin + i, ck.op_begin, tile, lane);
+        for (int op = ck.op_begin; op < ck.op_end; op++) {
+            const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+            cp_async_wait_pending(min(FWD_DEPTH - 1, ck.op_end - 1 - op));
+            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
+            const uint4 l0 = st[lane], l1 = st[32 + lane];
+            if (op + FWD_DEPTH < ck.op_end) fwd_issue(p, ring, op + FWD_DEPTH, ck.op_begin, tile, lane);
+            bool ok;
+            if (MAXB == 2 || f.w == 2) ok = sankoff_forward_op<2>(p, f, l0, l1, tile, lane, accG, accH);
+            else if (MAXB == 4 || f.w == 4) ok = sankoff_forward_op<4>(p, f, l0, l1, tile, lane, accG, accH);
+            else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, f, l0, l1, tile, lane, accG, accH);
+            else ok = sankoff_forward_op<20>(p, f, l0, l1, tile, lane, accG, accH);
+            if (!ok) return;
+            uint4* base = p.sets + ((size_t)op * T + tile) * 256;
+            store_planes16(base, lane, accG);
+            store_planes16(base + 128, lane, accH);
+            if (f.z & OPF_SIGNAL) signal_flag(p.done + (size_t)op * T + tile, p.epoch, lane);
+        }
     }
 }
 
 // ------------------------------------------------------------------ Sankoff backward + mutation detection
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
-    int chunk, tile, lane;
-    if (!warp_item(p, chunk_begin, n_chunks, chunk, tile, lane)) return;
-    const Chunk ck = p.chunks[chunk];
-    const size_t T = p.T;
-    uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
-    for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
-        const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
-        const int4 b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
-        uint32_t G[16], H[16];
-        const uint4* base = p.sets + ((size_t)op * T + tile) * 256;
-        load_planes16(base, lane, G);
-        load_planes16(base + 128, lane, H);
-        uint32_t P[4], F[4], vis;
-        if (b0.y == PARENT_ROOT) {
-            const uint4* cp = p.colparams + (size_t)tile * 128;
-            uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
-            P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
-            uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w}, undefined;
-            sankoff_assign_root(G, H, o4, fl.x & fl.z, fl.z, F, vis, undefined);
-            if (undefined) {  // reference: assert(minPtr != -1), fitchSankoff.cpp:505 (block variant returns, :754-757)
-                if (!(p.flags & RUN_BLOCK_MODE)) {
-                    atomicOr(p.error, 1u);
-                    atomicMin(p.error + 1, (unsigned)(tile * TILE_COLS + lane * 32 + (__ffs(undefined) - 1)));
+    extern __shared__ uint4 smem[];
+    constexpr int J = 8, STAGE = (J + 2) * 32;
+    const int lane = threadIdx.x & 31;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
+    ItemIter it;
+    int chunk, tile;
+    while (next_item(p, it, chunk_begin, n_chunks, true, chunk, tile, lane)) {
+        const Chunk ck = p.chunks[chunk];
+        const int last = ck.op_end - 1;
+        uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
+        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, ring, last - i, last, tile, lane);
+        for (int op = last; op >= ck.op_begin; op--) {
+            BwdHead h;
+            h.b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
+            h.b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
+            uint32_t P[4], pvis = 0, F[4], vis;
+            if (h.b0.y != PARENT_ROOT) {
+                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis)) return;
+            }
+            cp_async_wait_pending(min(BWD_DEPTH - 1, op - ck.op_begin));
+            const uint4* st = ring + ((last - op) % BWD_DEPTH) * STAGE;
+            uint32_t G[16], H[16];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint4 v = st[j * 32 + lane], w = st[(4 + j) * 32 + lane];
+                G[4 * j] = v.x; G[4 * j + 1] = v.y; G[4 * j + 2] = v.z; G[4 * j + 3] = v.w;
+                H[4 * j] = w.x; H[4 * j + 1] = w.y; H[4 * j + 2] = w.z; H[4 * j + 3] = w.w;
+            }
+            if (h.b0.y == PARENT_ROOT) {
+                const uint4* cp = p.colparams + (size_t)tile * 128;
+                uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
+                P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
+                uint32_t o4[4] = {ov.x, ov.y, ov.z, ov.w}, undefined;
+                sankoff_assign_root(G, H, o4, fl.x & fl.z, fl.z, F, vis, undefined);
+                if (undefined) {  // reference: assert(minPtr != -1), fitchSankoff.cpp:505 (block variant returns, :754-757)
+                    if (!(p.flags & RUN_BLOCK_MODE)) {
+                        atomicOr(p.error, 1u);
+                        atomicMin(p.error + 1, (unsigned)(tile * TILE_COLS + lane * 32 + (__ffs(undefined) - 1)));
+                    }
                 }
-            }
-        } else {
-            uint32_t pvis;
-            if (b0.y == PARENT_ACC) {
-                P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
-                pvis = accVis;
             } else {
-                const uint4* fs = p.fstore + ((size_t)b0.y * T + tile) * 64;
-                uint4 a = ld_l2(fs + lane);
-                pvis = ld_l2(fs + 32 + lane).x;
-                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
-            }
-            sankoff_assign(G, H, P, pvis, F, vis);
-        }
-        emit(p, b0.x, tile, lane, vis & differs4(F, P), P, F);
-        if (b0.z >= 0) {
-            uint4* fs = p.fstore + ((size_t)b0.z * T + tile) * 64;
-            fs[lane] = make_uint4(F[0], F[1], F[2], F[3]);
-            fs[32 + lane] = make_uint4(vis, 0, 0, 0);
-        }
-        if (p.states) store_state(p, b0.x, tile, lane, F, vis);
-        for (int l = 0; l < b1.x; l++) {
-            const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + b0.w + l));
-            uint4 c = ld_stream(p.leaf_planes + ((size_t)lf.x * T + tile) * 32 + lane);
-            uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-            uint32_t present = leaf_present_mask(p, lf.x);
-            if ((p.flags & RUN_BLOCK_MODE) && !present) {
-                cc[0] = cc[1] = cc[2] = cc[3] = 0;
-                present = FULL;
+                sankoff_assign(G, H, P, pvis, F, vis);
             }
             // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
-            const uint32_t lvis = vis & present;
-            emit(p, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
-            if (p.states) {
-                uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
-                store_state(p, lf.y, tile, lane, m4, lvis);
-            }
+            bwd_finish_op(p, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
+            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, ring, op - BWD_DEPTH, last, tile, lane);
+            accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
+            accVis = vis;
         }
-        accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
-        accVis = vis;
     }
 }
 

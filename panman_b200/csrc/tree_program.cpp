@@ -6,13 +6,14 @@
 namespace pmb {
 
 std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* child_off, const int32_t* child_idx,
-                               const int32_t* leaf_row, int32_t chunk_nodes, TreeProgram* out) {
+                               const int32_t* leaf_row, int32_t chunk_nodes, int32_t inline_nodes, TreeProgram* out) {
     TreeProgram& P = *out;
     P = TreeProgram();
     if (n_nodes < 2) return "tree needs at least one internal node and one leaf";
     if (root < 0 || root >= n_nodes) return "root out of range";
     if (child_off[0] != 0) return "child_offsets[0] must be 0";
     if (chunk_nodes < 1) chunk_nodes = 1;
+    if (n_nodes > int32_t(REF_IDX_MASK)) return "tree too large";
     const int32_t n_edges = child_off[n_nodes];
     if (n_edges != n_nodes - 1) return "child_index must hold exactly n_nodes - 1 entries (a tree)";
 
@@ -81,17 +82,19 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         ichild_off[v + 1] = int32_t(ichild.size());
     }
 
-    // ---- bottom-up cut into chunks ----
-    std::vector<int32_t> pend(n_nodes, 0);
+    // ---- cut into chunks: bottom subtrees (<= chunk_nodes) and heavy-path segments of the top tree ----
+    if (inline_nodes < 0) inline_nodes = 0;
+    if (inline_nodes >= chunk_nodes) inline_nodes = chunk_nodes - 1;
     std::vector<char> cut(n_nodes, 0);
-    for (int32_t i = n_nodes - 1; i >= 0; i--) {
+    for (int32_t i = 0; i < n_nodes; i++) {
         int32_t v = pre[i];
         if (isz[v] == 0) continue;
-        int32_t p = 1;
-        for (int32_t e = ichild_off[v]; e < ichild_off[v + 1]; e++)
-            if (!cut[ichild[e]]) p += pend[ichild[e]];
-        pend[v] = p;
-        if (p >= chunk_nodes || v == root) cut[v] = 1;
+        if (v == root) { cut[v] = 1; continue; }
+        int32_t p = parent[v];
+        bool p_top = isz[p] > chunk_nodes;
+        if (!p_top) continue;                         // inside a bottom subtree
+        if (isz[v] > chunk_nodes) cut[v] = (ichild[ichild_off[p]] != v);  // top node: stays iff heaviest child
+        else cut[v] = isz[v] > inline_nodes;          // bottom subtree hanging off the top tree
     }
 
     // ---- per-chunk op lists (post-order over uncut internal children), chunk levels ----
@@ -168,6 +171,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     P.bwd_leaves.reserve(n_rows);
     // which ops must park their assigned state for a child that does not follow them immediately (in reverse)
     std::vector<int32_t> fslot(n_internal, -1);
+    std::vector<char> ext_child(n_internal, 0);  // some child of this op lives in another chunk
     int32_t n_fslots = 0;
     for (int32_t i = 0; i < n_internal; i++) {
         int32_t v = op_node[i];
@@ -175,6 +179,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         int32_t pop = P.node_op[parent[v]];
         bool acc = (pop == i + 1) && chunk_of[v] == chunk_of[parent[v]];
         if (!acc && fslot[pop] < 0) fslot[pop] = n_fslots++;
+        if (chunk_of[v] != chunk_of[parent[v]]) ext_child[pop] = 1;
     }
     P.n_fslots = n_fslots;
     int32_t max_arity = 0;
@@ -183,9 +188,9 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         FwdOp& f = P.fwd_ops[i];
         BwdOp& b = P.bwd_ops[i];
         f.ref_begin = int32_t(P.refs.size());
-        f.flags = (v == root) ? OPF_ROOT : 0;
+        f.flags = ((v == root) ? OPF_ROOT : 0) | (cut[v] ? OPF_SIGNAL : 0);
         b.node = v;
-        b.flags = f.flags;
+        b.flags = ((v == root) ? OPF_ROOT : 0) | (ext_child[i] ? OPF_SIGNAL_F : 0);
         b.leaf_begin = int32_t(P.bwd_leaves.size());
         b.pad0 = b.pad1 = 0;
         // leaves in Newick order, then internal children heavy -> light; the one computed by op i-1 of the
@@ -201,7 +206,8 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
             int32_t c = ichild[e];
             int32_t cop = P.node_op[c];
             bool acc = (cop == i - 1) && chunk_of[c] == chunk_of[v];
-            P.refs.push_back(acc ? (REF_ACC << 30) : ((REF_INT << 30) | uint32_t(cop)));
+            bool ext = chunk_of[c] != chunk_of[v];
+            P.refs.push_back(acc ? (REF_ACC << 30) : ((REF_INT << 30) | (ext ? REF_EXT : 0u) | uint32_t(cop)));
         }
         f.n_refs = int32_t(P.refs.size()) - f.ref_begin;
         max_arity = std::max(max_arity, f.n_refs);
@@ -213,6 +219,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
             int32_t pop = P.node_op[parent[v]];
             bool acc = (pop == i + 1) && chunk_of[v] == chunk_of[parent[v]];
             b.parent_ref = acc ? PARENT_ACC : fslot[pop];
+            if (chunk_of[v] != chunk_of[parent[v]]) b.flags |= OPF_PARENT_EXT;
         }
     }
     P.max_arity = max_arity;

@@ -3,7 +3,15 @@
 // The reference walks Node* pointers recursively, one column at a time (src/fitchSankoff.cpp:30-56,
 // 96-171). Here the tree becomes a static "program":
 //   * every internal node is one op; ops are grouped into chunks (connected pieces of the tree that
-//     one warp evaluates sequentially for its 1024 columns), chunks into dependency levels;
+//     one warp evaluates sequentially for its 1024 columns);
+//   * chunks are (a) whole bottom subtrees of at most chunk_nodes internal nodes and (b) heavy-path
+//     segments of the remaining "top" tree (a top node stays in its parent's chunk iff it is the
+//     parent's heaviest child), with tiny light subtrees inlined. This keeps the dependency chain
+//     through the top of the tree inside as few warps as possible;
+//   * a chunk may start before the chunks below it are finished: every cross-chunk read carries a
+//     dependency (REF_EXT / OPF_PARENT_EXT) that the kernels resolve with per-(op, tile) done flags.
+//     Chunks are listed in topological order (level-major), which is also the ticket order of the
+//     persistent kernels: an item only ever waits for items with smaller tickets, so it cannot deadlock;
 //   * within a chunk ops are in post-order with the lightest internal child last, so the most
 //     recent result stays in registers (REF_ACC) and older siblings are re-read from the set matrix
 //     while still L2-resident;
@@ -18,8 +26,15 @@
 namespace pmb {
 
 enum : uint32_t { REF_INT = 0u, REF_LEAF = 1u, REF_ACC = 2u };  // top 2 bits of a forward child ref
+constexpr uint32_t REF_EXT = 1u << 29;                          // REF_INT written by another chunk: wait for its flag
+constexpr uint32_t REF_IDX_MASK = (1u << 29) - 1u;
 enum : int32_t { PARENT_ACC = -1, PARENT_ROOT = -2 };           // BwdOp::parent_ref, else an fslot >= 0
-enum : int32_t { OPF_ROOT = 1 };
+enum : int32_t {
+    OPF_ROOT = 1,
+    OPF_SIGNAL = 2,      // forward: this op is a chunk root, publish its done flag after the store
+    OPF_PARENT_EXT = 4,  // backward: the parent's state slot is written by another chunk, wait for it
+    OPF_SIGNAL_F = 8     // backward: another chunk reads this op's state slot, publish after the store
+};
 
 struct FwdOp {  // 16 bytes; the op index is also the node's row ("slot") in the set matrix
     int32_t ref_begin;
@@ -61,8 +76,9 @@ struct TreeProgram {
     int n_levels() const { return int(level_chunk_begin.size()) - 1; }
 };
 
-// Returns "" on success, else a message. chunk_nodes = target internal nodes per chunk (>= 1).
+// Returns "" on success, else a message. chunk_nodes = largest bottom subtree kept in one chunk (>= 1);
+// inline_nodes = light subtrees up to this size are evaluated inside their parent's chunk (0 = never).
 std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* child_off, const int32_t* child_idx,
-                               const int32_t* leaf_row, int32_t chunk_nodes, TreeProgram* out);
+                               const int32_t* leaf_row, int32_t chunk_nodes, int32_t inline_nodes, TreeProgram* out);
 
 }  // namespace pmb

@@ -27,6 +27,8 @@ struct Emu {
     std::vector<U4> leaf_planes, sets, fstore, colparams, states;
     std::vector<uint8_t> present;
     bool have_present = false;
+    std::vector<unsigned> done, fdone;   // dependency flags, as in the kernels (value 1 = published this run)
+    bool order_violation = false;        // an item read data of an item that had not run yet (would be a wait/deadlock)
     std::vector<unsigned long long> dir;
     std::vector<uint16_t> staging;
     unsigned long long pool = 0;
@@ -84,7 +86,7 @@ void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16
     SankoffFold<B> fold;
     fold.reset();
     for (int r = 0; r < f.n_refs; r++) {
-        uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+        uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
         if (kind == REF_LEAF) {
             U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
             uint32_t cc[4] = {c.x, c.y, c.z, c.w}, pr = present_mask(E, idx);
@@ -93,6 +95,7 @@ void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
+            if ((ref & REF_EXT) && E.done[(size_t)idx * T + tile] != 1) E.order_violation = true;
             const U4* base = E.sets.data() + ((size_t)idx * T + tile) * 256;
             uint32_t G[16];
             load16(base, lane, G);
@@ -116,7 +119,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                 FitchFold fold;
                 fold.reset();
                 for (int r = 0; r < f.n_refs; r++) {
-                    uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & 0x3FFFFFFFu;
+                    uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
                     if (kind == REF_LEAF) {
                         U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
                         uint32_t cc[4] = {c.x, c.y, c.z, c.w};
@@ -124,6 +127,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc[lane]);
                     } else {
+                        if ((ref & REF_EXT) && E.done[(size_t)idx * T + tile] != 1) E.order_violation = true;
                         uint32_t S[16];
                         load16(E.sets.data() + ((size_t)idx * T + tile) * 128, lane, S);
                         fold.add_set(S);
@@ -150,6 +154,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                 store16(base + 128, lane, accH[lane]);
             }
         }
+        if (f.flags & OPF_SIGNAL) E.done[(size_t)op * T + tile] = 1;
     }
 }
 
@@ -194,6 +199,7 @@ void backward_item(Emu& E, int chunk, int tile) {
                     for (int k = 0; k < 4; k++) P[k] = accF[lane][k];
                     pvis = accVis[lane];
                 } else {
+                    if ((b.flags & OPF_PARENT_EXT) && E.fdone[(size_t)b.parent_ref * T + tile] != 1) E.order_violation = true;
                     const U4* fs = E.fstore.data() + ((size_t)b.parent_ref * T + tile) * 64;
                     U4 a = fs[lane];
                     pvis = fs[32 + lane].x;
@@ -213,6 +219,7 @@ void backward_item(Emu& E, int chunk, int tile) {
             store_state(E, b.node, tile, lane, F, vis);
         }
         emit(E, b.node, tile, wm);
+        if (b.fslot_out >= 0 && (b.flags & OPF_SIGNAL_F)) E.fdone[(size_t)b.fslot_out * T + tile] = 1;
         for (int l = 0; l < b.n_leaves; l++) {
             const BwdLeaf lf = E.P.bwd_leaves[b.leaf_begin + l];
             for (int lane = 0; lane < 32; lane++) {
@@ -245,9 +252,10 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
                    const int32_t* leaf_row, int chunk_nodes, long long n_cols, const uint8_t* leaf_codes,
                    const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
                    const int8_t* fwd_root_ref, long long col_base, long long* node_offsets, int32_t* pos,
-                   uint8_t* type_code, uint8_t* states_out, int32_t* prog_stats /* 4: chunks, levels, fslots, max_arity */) {
+                   uint8_t* type_code, uint8_t* states_out, int32_t* prog_stats /* 4: chunks, levels, fslots, max_arity */,
+                   int inline_nodes) {
     Emu E;
-    std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, &E.P);
+    std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, inline_nodes, &E.P);
     if (!err.empty()) return -1;
     const TreeProgram& P = E.P;
     if (prog_stats) {
@@ -296,14 +304,16 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
     E.fstore.assign((size_t)std::max(1, P.n_fslots) * T * 64, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     if (states_out) E.states.assign((size_t)n_nodes * T * 64, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     E.dir.assign((size_t)n_nodes * T, 0ull);
-    const int L = P.n_levels();
-    // within a level the hardware runs items in any order: go backwards to shake out hidden dependencies
-    for (int l = 0; l < L; l++)
-        for (int ch = P.level_chunk_begin[l + 1] - 1; ch >= P.level_chunk_begin[l]; ch--)
-            for (int t = E.T - 1; t >= 0; t--) forward_item(E, ch, t);
-    for (int l = L - 1; l >= 0; l--)
-        for (int ch = P.level_chunk_begin[l + 1] - 1; ch >= P.level_chunk_begin[l]; ch--)
-            for (int t = E.T - 1; t >= 0; t--) backward_item(E, ch, t);
+    E.done.assign((size_t)P.n_internal * T, 0u);
+    E.fdone.assign((size_t)std::max(1, P.n_fslots) * T, 0u);
+    // persistent-kernel ticket order: chunks in schedule order, tiles fastest (backward: chunks reversed). An item
+    // that finds a dependency flag unset here would have to wait for a LARGER ticket on the GPU: a scheduling bug.
+    const int NC = int(P.chunks.size());
+    for (int ch = 0; ch < NC; ch++)
+        for (int t = 0; t < E.T; t++) forward_item(E, ch, t);
+    for (int ch = NC - 1; ch >= 0; ch--)
+        for (int t = 0; t < E.T; t++) backward_item(E, ch, t);
+    if (E.order_violation) return -7;
     if (E.error & 1) return -4;
     // node_count + scan + gather
     long long run = 0;
@@ -337,3 +347,38 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
 }
 
 }  // extern "C"
+
+// schedule statistics of the tree program (no data involved): out[0] chunks, [1] levels, [2] fslots, [3] max arity,
+// [4] largest chunk (ops), [5] ops in the root's chunk, [6] critical path in ops (longest dependency chain of
+// chunks, counting every op of each chunk on it), [7] number of chunks with <= 2 ops
+extern "C" int emul_prog_stats(int n_nodes, int root, const int32_t* child_off, const int32_t* child_idx, const int32_t* leaf_row,
+                               int chunk_nodes, int inline_nodes, long long* out) {
+    TreeProgram P;
+    std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, inline_nodes, &P);
+    if (!err.empty()) return -1;
+    const int NC = int(P.chunks.size());
+    std::vector<int> chunk_of_op(P.n_internal);
+    for (int c = 0; c < NC; c++)
+        for (int op = P.chunks[c].op_begin; op < P.chunks[c].op_end; op++) chunk_of_op[op] = c;
+    std::vector<long long> cp(NC, 0);
+    long long best = 0, largest = 0, tiny = 0;
+    for (int c = 0; c < NC; c++) {  // schedule order is topological
+        long long dep = 0;
+        for (int op = P.chunks[c].op_begin; op < P.chunks[c].op_end; op++) {
+            const FwdOp& f = P.fwd_ops[op];
+            for (int r = 0; r < f.n_refs; r++) {
+                uint32_t ref = P.refs[f.ref_begin + r];
+                if ((ref >> 30) == REF_INT && (ref & REF_EXT)) dep = std::max(dep, cp[chunk_of_op[ref & REF_IDX_MASK]]);
+            }
+        }
+        long long n = P.chunks[c].op_end - P.chunks[c].op_begin;
+        cp[c] = dep + n;
+        best = std::max(best, cp[c]);
+        largest = std::max(largest, n);
+        tiny += n <= 2;
+    }
+    out[0] = NC; out[1] = P.n_levels(); out[2] = P.n_fslots; out[3] = P.max_arity; out[4] = largest;
+    out[5] = P.chunks[chunk_of_op[P.node_op[root]]].op_end - P.chunks[chunk_of_op[P.node_op[root]]].op_begin;
+    out[6] = best; out[7] = tiny;
+    return 0;
+}

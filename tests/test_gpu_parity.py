@@ -30,9 +30,12 @@ def _same(res, want):
             and np.array_equal(res.type_code, want.type_code))
 
 
-@pytest.mark.parametrize("chunk_nodes", [0, 1, 5])
-def test_golden_vectors(ctx, chunk_nodes):
+@pytest.mark.parametrize("chunk_nodes,inline_nodes,schedule", [(0, 3, 1), (1, 0, 1), (5, 1, 1), (5, 3, 0)])
+def test_golden_vectors(ctx, chunk_nodes, inline_nodes, schedule):
+    """schedule 1 = persistent kernels with dependency flags, 0 = one launch per dependency level"""
     ctx.set_option("chunk_nodes", chunk_nodes)
+    ctx.set_option("inline_nodes", inline_nodes)
+    ctx.set_option("schedule", schedule)
     for c in load_cases():
         _set_tree(ctx, c["tree"])
         res = ctx.run_codes(c["tree"], c["algo"], c["codes"], c["parent_code"], c["root_override"], c["fwd_root_ref"],
@@ -40,6 +43,8 @@ def test_golden_vectors(ctx, chunk_nodes):
         assert _same(res, c["expect"]), f"golden case {c['id']}"
         assert np.array_equal(res.states, c["states"]), f"golden case {c['id']} states"
     ctx.set_option("chunk_nodes", 0)
+    ctx.set_option("inline_nodes", 3)
+    ctx.set_option("schedule", 1)
 
 
 @pytest.mark.parametrize("algo", [0, 1])
@@ -65,12 +70,16 @@ def test_random_vs_oracle(ctx, port, algo):
             lp[0] = 1
         want, want_states = port.run(tree, algo, codes, pc, ro, fr, lp, block, n_threads=4, want_states=True)
         ctx.set_option("chunk_nodes", int(rng.choice([0, 1, 7, 64])))
+        ctx.set_option("inline_nodes", int(rng.choice([0, 2, 3, 9])))
+        ctx.set_option("schedule", int(trial % 3 != 0))
         _set_tree(ctx, tree)
         res = ctx.run_codes(tree, algo, codes, pc, ro, fr, lp, block, want_states=True, col_base=11)
         want.pos = want.pos + 11
         assert _same(res, want), (algo, trial, kind)
         assert np.array_equal(res.states, want_states), (algo, trial)
     ctx.set_option("chunk_nodes", 0)
+    ctx.set_option("inline_nodes", 3)
+    ctx.set_option("schedule", 1)
 
 
 def test_dense_mutations_overflow_path(ctx, port):
