@@ -441,7 +441,8 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
             node_count_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, P.n_nodes, c->T, c->d_node_counts.as<unsigned long long>());
             scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_node_counts.as<unsigned long long>(), P.n_nodes, c->d_offsets.as<long long>());
             gather_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, rp.staging, c->d_offsets.as<long long>(), P.n_nodes, c->T,
-                                                         c->col_base, c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>());
+                                                         c->col_base, c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(),
+                                                         rp.pool_count, rp.staging_cap);
             n_launches += 3;
         }
         PMB_CUDA(cudaGetLastError());

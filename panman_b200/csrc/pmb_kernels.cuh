@@ -594,8 +594,12 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned long long* co
 }
 
 // 3) gather: a warp walks one node's tiles in order and copies each staged segment to its final place.
+// If the staging pool overflowed (the host will grow it and redo the backward pass) the segments beyond the
+// capacity were never written and the final arrays are too small: do nothing.
 __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* staging, const long long* offsets, int n_nodes,
-                              int T, long long col_base, int32_t* pos, uint8_t* type_code) {
+                              int T, long long col_base, int32_t* pos, uint8_t* type_code,
+                              const unsigned long long* pool_count, unsigned long long staging_cap) {
+    if (*pool_count > staging_cap) return;
     int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (node >= n_nodes) return;
     long long run = offsets[node];
