@@ -121,6 +121,34 @@ struct FitchFold {
     }
 };
 
+// Fast paths for the three binary shapes that make up almost every op of a bifurcating tree. They are algebraic
+// specialisations of FitchFold for PRESENT leaves (one-hot sets), a third of the instructions:
+//   leaf,leaf : equal codes -> that code, else both                      S = d1 | (d2 & ~eq)
+//   leaf,set  : the leaf's state in X -> only it, else X plus it         S = d | (X & ~X[code])
+//   set,set   : intersection if anywhere non-empty, else union           S = (X&Y) | ((X|Y) & ~any(X&Y))
+PMB_HD void fitch_leaf_leaf(const uint32_t c1[4], const uint32_t c2[4], uint32_t S[16]) {
+    uint32_t d1[16], d2[16];
+    decode16(c1, d1);
+    decode16(c2, d2);
+    const uint32_t ne = differs4(c1, c2);
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[k] = d1[k] | (d2[k] & ne);
+}
+PMB_HD void fitch_leaf_set(const uint32_t c[4], const uint32_t X[16], uint32_t S[16]) {
+    uint32_t d[16];
+    decode16(c, d);
+    const uint32_t hit = mux16(X, c);
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[k] = d[k] | (X[k] & ~hit);
+}
+PMB_HD void fitch_set_set(const uint32_t X[16], const uint32_t Y[16], uint32_t S[16]) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) nz |= X[k] & Y[k];
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[k] = (X[k] & Y[k]) | ((X[k] | Y[k]) & ~nz);
+}
+
 // Assigned state of a non-root node (or a block-mode root): parent state P (code planes) where visited pvis.
 // F = P if P in S else lowest(S); vis = pvis & (S != 0)          (fitchSankoff.cpp:101-103, 115-123)
 PMB_HD void fitch_assign(const uint32_t S[16], const uint32_t P[4], uint32_t pvis, uint32_t F[4], uint32_t& vis) {

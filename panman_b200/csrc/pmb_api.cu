@@ -79,7 +79,7 @@ struct pmb_ctx {
     std::vector<int32_t> child_off, child_idx, leaf_row;
     TreeProgram prog;
     int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1;
-    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks;
+    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order;
 
     // resident input
     bool have_input = false;
@@ -89,7 +89,7 @@ struct pmb_ctx {
     DevBuf d_leaf_planes, d_present, d_colparams, d_tmp_codes, d_tmp_cols;
 
     // work + result
-    DevBuf d_done, d_fdone, d_ticket;
+    DevBuf d_done, d_fdone, d_ticket, d_block_sums;
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_node_counts, d_offsets, d_pos, d_tc,
         d_states_u8;
     unsigned long long staging_cap = 0;
@@ -152,6 +152,8 @@ int ensure_program(pmb_ctx* c) {
     if ((rc = upload_vec(c, c->d_bwd_ops, c->prog.bwd_ops))) return rc;
     if ((rc = upload_vec(c, c->d_bwd_leaves, c->prog.bwd_leaves))) return rc;
     if ((rc = upload_vec(c, c->d_chunks, c->prog.chunks))) return rc;
+    if ((rc = upload_vec(c, c->d_bwd_order, c->prog.bwd_order))) return rc;
+    if ((rc = upload_vec(c, c->d_level_order, c->prog.level_order))) return rc;
     PMB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above may be rebuilt before the copies ran
     c->prog_chunk_nodes = k;
     c->prog_inline_nodes = inl;
@@ -194,10 +196,15 @@ int launch_schedule(pmb_ctx* c, K kernel, size_t smem, RunParams rp, bool forwar
     int rc;
     if (smem > 48 * 1024) PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     if (c->opt_schedule == 1) {
+        // persistent: tickets follow chunks[] (forward) or bwd_order (backward), both topological for their pass
         rp.ticket = c->d_ticket.as<unsigned long long>();
+        rp.order = forward ? nullptr : c->d_bwd_order.as<int>();
+        rp.stage_block = 512;
         if ((rc = launch_kernel(c, kernel, smem, rp, 0, int(P.chunks.size()), n_launches))) return rc;
     } else {
         rp.ticket = nullptr;
+        rp.order = c->d_level_order.as<int>();
+        rp.stage_block = 32;
         const int L = P.n_levels();
         for (int i = 0; i < L; i++) {
             int l = forward ? i : L - 1 - i;
@@ -257,7 +264,8 @@ void pmb_destroy(pmb_ctx* c) {
     if (c->stream) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
-        for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_leaf_planes,
+        for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_bwd_order,
+                          &c->d_level_order, &c->d_block_sums, &c->d_leaf_planes,
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket})
@@ -376,7 +384,7 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     const size_t T = size_t(c->T);
     const size_t set_bytes_per = (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
     PMB_CUDA(c->d_sets.ensure(size_t(P.n_internal) * T * set_bytes_per));
-    PMB_CUDA(c->d_fstore.ensure(std::max<size_t>(16, size_t(P.n_fslots) * T * 64 * sizeof(uint4))));
+    PMB_CUDA(c->d_fstore.ensure(std::max<size_t>(16, size_t(P.n_fslots) * T * FSLOT_WORDS * sizeof(uint32_t))));
     const bool want_states = flags & PMB_FLAG_WANT_STATES;
     if (want_states) PMB_CUDA(c->d_states_planes.ensure(size_t(P.n_nodes) * T * 64 * sizeof(uint4)));
     PMB_CUDA(c->d_dir.ensure(size_t(P.n_nodes) * T * sizeof(unsigned long long)));
@@ -388,7 +396,9 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         if ((rcf = ensure_flags(c, c->d_done, size_t(P.n_internal) * T))) return rcf;
         if ((rcf = ensure_flags(c, c->d_fdone, size_t(std::max(1, P.n_fslots)) * T))) return rcf;
     }
-    PMB_CUDA(c->d_node_counts.ensure(size_t(P.n_nodes) * sizeof(unsigned long long)));
+    PMB_CUDA(c->d_node_counts.ensure(size_t(P.n_nodes) * sizeof(unsigned int)));
+    const int scan_blocks = (P.n_nodes + SCAN_TILE - 1) / SCAN_TILE;
+    PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
     PMB_CUDA(c->d_offsets.ensure(size_t(P.n_nodes + 1) * sizeof(long long)));
     if (c->staging_cap == 0) {
         unsigned long long cells = (unsigned long long)P.n_nodes * (unsigned long long)c->n_cols;
@@ -406,7 +416,10 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     rp.leaf_planes = c->d_leaf_planes.as<uint4>();
     rp.leaf_present = c->have_present ? c->d_present.as<uint8_t>() : nullptr;
     rp.sets = c->d_sets.as<uint4>();
-    rp.fstore = c->d_fstore.as<uint4>();
+    rp.fstore = c->d_fstore.as<uint32_t>();
+    rp.node_count = c->d_node_counts.as<unsigned int>();
+    rp.order = nullptr;
+    rp.stage_block = 512;
     rp.colparams = c->d_colparams.as<uint4>();
     rp.states = want_states ? c->d_states_planes.as<uint4>() : nullptr;
     rp.dir = c->d_dir.as<unsigned long long>();
@@ -431,15 +444,17 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         rp.staging = c->d_staging.as<uint16_t>();
         rp.staging_cap = c->staging_cap;
         PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, size_t(P.n_nodes) * T * sizeof(unsigned long long), c->stream));
+        PMB_CUDA(cudaMemsetAsync(c->d_node_counts.p, 0, size_t(P.n_nodes) * sizeof(unsigned int), c->stream));
         unsigned int init[4] = {0, 0, 0, 0xFFFFFFFFu};  // pool_count (64 bit), error flags, first bad column
         PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
         rp.epoch = ++c->epoch;
         if ((rc = launch_pass(c, rp, algo, false, &n_launches))) return rc;
         PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
         {
+            scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(rp.node_count, P.n_nodes, c->d_block_sums.as<unsigned long long>());
+            scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(rp.node_count, P.n_nodes, c->d_block_sums.as<unsigned long long>(),
+                                                                         c->d_offsets.as<long long>());
             unsigned blocks = unsigned(((long long)P.n_nodes * 32 + 255) / 256);
-            node_count_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, P.n_nodes, c->T, c->d_node_counts.as<unsigned long long>());
-            scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_node_counts.as<unsigned long long>(), P.n_nodes, c->d_offsets.as<long long>());
             gather_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, rp.staging, c->d_offsets.as<long long>(), P.n_nodes, c->T,
                                                          c->col_base, c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(),
                                                          rp.pool_count, rp.staging_cap);
@@ -448,6 +463,8 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         PMB_CUDA(cudaGetLastError());
         PMB_CUDA(cudaEventRecord(c->ev[3], c->stream));
         PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_offsets.as<long long>() + P.n_nodes, 8, cudaMemcpyDeviceToHost,
+                                 c->stream));
         PMB_CUDA(cudaStreamSynchronize(c->stream));
         unsigned long long total = *c->h_counters.as<unsigned long long>();
         unsigned int eflags = c->h_counters.as<unsigned int>()[2], ecol = c->h_counters.as<unsigned int>()[3];
@@ -463,7 +480,7 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
             c->staging_cap = total;
             continue;
         }
-        c->n_mut = int64_t(total);
+        c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 16);  // offsets[n_nodes]; the pool also holds slack
         break;
     }
     PMB_CUDA(cudaEventElapsedTime(&c->timings.forward_ms, c->ev[0], c->ev[1]));

@@ -21,6 +21,7 @@ namespace pmb {
 constexpr int TILE_COLS = 1024;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int FSLOT_WORDS = 160;   // parked assigned state of one (node, tile): 4 code planes + visited plane per lane
 
 enum : int { RUN_BLOCK_MODE = 1, RUN_WANT_STATES = 2 };
 
@@ -33,7 +34,7 @@ struct RunParams {
     const uint4* leaf_planes;
     const uint8_t* leaf_present;  // device, n_rows bytes, or nullptr = all present
     uint4* sets;
-    uint4* fstore;                // [fslot][tile][2][lane]
+    uint32_t* fstore;             // [fslot][tile][FSLOT_WORDS]: 32 x uint4 code planes, then 32 visited words
     const uint4* colparams;       // [tile][4][lane]: parent code, override code, fwd ref code, {ov_valid, ref_valid, col_valid, 0}
     uint4* states;                // [node][tile][2][lane] or nullptr
     unsigned long long* dir;      // [node][tile]: (staging base << 11) | count
@@ -44,9 +45,12 @@ struct RunParams {
     unsigned int* done;           // [op][tile]   forward: set matrix row published (value = epoch)
     unsigned int* fdone;          // [fslot][tile] backward: assigned-state slot published
     unsigned long long* ticket;   // persistent launch: work-item counter; nullptr = one static item per warp
+    const int* order;             // item i works on chunk order[i / T]; nullptr = identity
+    unsigned int* node_count;     // [node] records emitted for the node in this run
     unsigned int epoch;
     int T;
     int flags;
+    int stage_block;              // staging records a warp reserves per atomic
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
@@ -76,8 +80,8 @@ __device__ __forceinline__ void unpack16(const uint4 v[4], uint32_t S[16]) {
 struct ItemIter {
     bool taken = false;
 };
-__device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int chunk_begin, int n_chunks, bool reverse,
-                                          int& chunk, int& tile, int lane) {
+__device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int chunk_begin, int n_chunks, int& chunk,
+                                          int& tile, int lane) {
     unsigned long long w;
     if (p.ticket) {
         if (lane == 0) w = atomicAdd(p.ticket, 1ull);
@@ -88,8 +92,8 @@ __device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int 
         w = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     }
     if (w >= (unsigned long long)n_chunks * (unsigned long long)p.T) return false;
-    int c = int(w / (unsigned)p.T);
-    chunk = chunk_begin + (reverse ? n_chunks - 1 - c : c);
+    int c = chunk_begin + int(w / (unsigned)p.T);
+    chunk = p.order ? __ldg(p.order + c) : c;
     tile = int(w % (unsigned)p.T);
     return true;
 }
@@ -148,10 +152,17 @@ __device__ __forceinline__ uint32_t leaf_present_mask(const RunParams& p, int ro
 
 // ------------------------------------------------------------------ mutation staging
 // Appends the records of one (node, tile) in ascending column order: warp ballot to skip the common empty
-// case, shuffle prefix sum over per-lane popcounts, one atomic reservation per warp.
+// case, shuffle prefix sum over per-lane popcounts. Staging space is reserved per warp in blocks of
+// p.stage_block records (one atomic per block, not per append: the round trip of a per-append atomic was 46 % of
+// the backward pass' stall samples in profiles/r01_v2). The (node, tile) directory remembers where each
+// segment went; gather_kernel later lays the segments out node-major in column order.
 // Record: column-in-tile (10 bits) | code << 10 | type << 14.
-__device__ __forceinline__ void emit(const RunParams& p, int node, int tile, int lane, uint32_t mut, const uint32_t P[4],
-                                     const uint32_t F[4]) {
+struct StageCursor {
+    unsigned long long base = 0;
+    int left = 0;
+};
+__device__ __forceinline__ void emit(const RunParams& p, StageCursor& sc, int node, int tile, int lane, uint32_t mut,
+                                     const uint32_t P[4], const uint32_t F[4]) {
     if (__ballot_sync(FULL, mut != 0) == 0) return;
     int cnt = __popc(mut);
     int incl = cnt;
@@ -160,13 +171,21 @@ __device__ __forceinline__ void emit(const RunParams& p, int node, int tile, int
         int t = __shfl_up_sync(FULL, incl, d);
         if (lane >= d) incl += t;
     }
-    int total = __shfl_sync(FULL, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 0) {
-        base = atomicAdd(p.pool_count, (unsigned long long)total);
-        p.dir[(size_t)node * p.T + tile] = (base << 11) | (unsigned long long)total;
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total > sc.left) {
+        const int take = max(total, p.stage_block);
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.pool_count, (unsigned long long)take);
+        sc.base = __shfl_sync(FULL, b, 0);
+        sc.left = take;
     }
-    base = __shfl_sync(FULL, base, 0);
+    const unsigned long long base = sc.base;
+    sc.base += total;
+    sc.left -= total;
+    if (lane == 0) {
+        p.dir[(size_t)node * p.T + tile] = (base << 11) | (unsigned long long)total;
+        atomicAdd(p.node_count + node, (unsigned)total);
+    }
     if (base + (unsigned long long)total > p.staging_cap) return;  // host grows the pool and reruns the pass
     uint32_t t0, t1;
     mutation_type(P, F, t0, t1);
@@ -239,7 +258,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
     const size_t T = p.T;
     ItemIter it;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, false, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
         const Chunk ck = p.chunks[chunk];
         uint32_t acc[16];
 #pragma unroll
@@ -251,32 +270,61 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
             const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
             const uint4 l0 = st[lane], l1 = st[32 + lane];
             if (op + FWD_DEPTH < ck.op_end) fwd_issue(p, ring, op + FWD_DEPTH, ck.op_begin, tile, lane);  // refill this stage
-            FitchFold fold;
-            fold.reset();
-            int nl = 0;
-            for (int r = 0; r < f.y; r++) {
-                const uint32_t ref = __ldg(p.refs + f.x + r);
-                const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
-                if (kind == REF_LEAF) {
-                    uint4 c;
-                    if (nl == 0) c = l0;
-                    else if (nl == 1) c = l1;
-                    else c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
-                    nl++;
-                    uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-                    fold.add_leaf(cc, leaf_present_mask(p, idx));
-                } else if (kind == REF_ACC) {
-                    fold.add_set(acc);
-                } else {
-                    if (ref & REF_EXT) {
-                        if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return;
-                    }
-                    uint32_t S[16];
-                    load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
-                    fold.add_set(S);
+            const int type = p.leaf_present ? FT_GENERIC : ((f.z >> OPF_TYPE_SHIFT) & 15);
+            if (type == FT_LEAF_LEAF) {
+                const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w}, c1[4] = {l1.x, l1.y, l1.z, l1.w};
+                fitch_leaf_leaf(c0, c1, acc);
+            } else if (type == FT_LEAF_ACC) {
+                const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w};
+                uint32_t X[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) X[k] = acc[k];
+                fitch_leaf_set(c0, X, acc);
+            } else if (type == FT_LEAF_INT || type == FT_INT_ACC) {
+                const uint32_t ref = __ldg(p.refs + f.x + (type == FT_LEAF_INT ? 1 : 0));
+                const uint32_t idx = ref & REF_IDX_MASK;
+                if (ref & REF_EXT) {
+                    if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return;
                 }
+                uint32_t X[16];
+                load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, X);
+                if (type == FT_LEAF_INT) {
+                    const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w};
+                    fitch_leaf_set(c0, X, acc);
+                } else {
+                    uint32_t Y[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) Y[k] = acc[k];
+                    fitch_set_set(X, Y, acc);
+                }
+            } else {
+                FitchFold fold;
+                fold.reset();
+                int nl = 0;
+                for (int r = 0; r < f.y; r++) {
+                    const uint32_t ref = __ldg(p.refs + f.x + r);
+                    const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
+                    if (kind == REF_LEAF) {
+                        uint4 c;
+                        if (nl == 0) c = l0;
+                        else if (nl == 1) c = l1;
+                        else c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+                        nl++;
+                        uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                        fold.add_leaf(cc, leaf_present_mask(p, idx));
+                    } else if (kind == REF_ACC) {
+                        fold.add_set(acc);
+                    } else {
+                        if (ref & REF_EXT) {
+                            if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return;
+                        }
+                        uint32_t S[16];
+                        load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
+                        fold.add_set(S);
+                    }
+                }
+                fold.finish(acc);
             }
-            fold.finish(acc);
             if ((f.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
                 // refState: the root's forward value is replaced (fitchSankoff.cpp:45-47)
                 const uint4* cp = p.colparams + (size_t)tile * 128;
@@ -328,23 +376,24 @@ __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h,
     if (h.b1.y & OPF_PARENT_EXT) {
         if (!wait_flag(p.fdone + (size_t)h.b0.y * T + tile, p.epoch, p.error, lane)) return false;
     }
-    const uint4* fs = p.fstore + ((size_t)h.b0.y * T + tile) * 64;
-    uint4 a = ld_l2(fs + lane);
-    pvis = ld_l2(fs + 32 + lane).x;
+    const uint32_t* fs = p.fstore + ((size_t)h.b0.y * T + tile) * FSLOT_WORDS;
+    uint4 a = ld_l2(reinterpret_cast<const uint4*>(fs) + lane);
+    pvis = __ldcg(fs + 128 + lane);
     P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
     return true;
 }
 
 // what follows the assignment of an internal node, shared by Fitch and Sankoff: its own record, the parked
 // state for later children, and its leaf children (a present leaf is always assigned its own code)
-__device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdHead& h, const uint4* leaf_stage, int tile, int lane,
-                                              const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block) {
+__device__ __forceinline__ void bwd_finish_op(const RunParams& p, StageCursor& sc, const BwdHead& h, const uint4* leaf_stage,
+                                              int tile, int lane, const uint32_t P[4], const uint32_t F[4], uint32_t vis,
+                                              bool sankoff_block) {
     const size_t T = p.T;
-    emit(p, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
+    emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
     if (h.b0.z >= 0) {
-        uint4* fs = p.fstore + ((size_t)h.b0.z * T + tile) * 64;
-        fs[lane] = make_uint4(F[0], F[1], F[2], F[3]);
-        fs[32 + lane] = make_uint4(vis, 0, 0, 0);
+        uint32_t* fs = p.fstore + ((size_t)h.b0.z * T + tile) * FSLOT_WORDS;
+        reinterpret_cast<uint4*>(fs)[lane] = make_uint4(F[0], F[1], F[2], F[3]);
+        fs[128 + lane] = vis;
         if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + (size_t)h.b0.z * T + tile, p.epoch, lane);
     }
     if (p.states) store_state(p, h.b0.x, tile, lane, F, vis);
@@ -360,7 +409,7 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdHead&
             present = FULL;
         }
         const uint32_t lvis = vis & present;
-        emit(p, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
+        emit(p, sc, lf.y, tile, lane, lvis & differs4(cc, F), F, cc);
         if (p.states) {
             uint32_t m4[4] = {cc[0] & lvis, cc[1] & lvis, cc[2] & lvis, cc[3] & lvis};
             store_state(p, lf.y, tile, lane, m4, lvis);
@@ -375,8 +424,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
     ItemIter it;
+    StageCursor sc;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, true, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
         const Chunk ck = p.chunks[chunk];
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
@@ -416,7 +466,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             } else {
                 fitch_assign(S, P, pvis, F, vis);
             }
-            bwd_finish_op(p, h, st + J * 32, tile, lane, P, F, vis, false);
+            bwd_finish_op(p, sc, h, st + J * 32, tile, lane, P, F, vis, false);
             // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
             if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, ring, op - BWD_DEPTH, last, tile, lane);
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
@@ -476,7 +526,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
     const size_t T = p.T;
     ItemIter it;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, false, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
         const Chunk ck = p.chunks[chunk];
         uint32_t accG[16], accH[16];
 #pragma unroll
@@ -509,8 +559,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
     ItemIter it;
+    StageCursor sc;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, true, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
         const Chunk ck = p.chunks[chunk];
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
@@ -548,7 +599,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
                 sankoff_assign(G, H, P, pvis, F, vis);
             }
             // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
-            bwd_finish_op(p, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
+            bwd_finish_op(p, sc, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
             if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, ring, op - BWD_DEPTH, last, tile, lane);
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
@@ -557,45 +608,85 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
 }
 
 // ------------------------------------------------------------------ ordered compaction
-// 1) per-node totals from the (node, tile) directory
-__global__ void node_count_kernel(const unsigned long long* dir, int n_nodes, int T, unsigned long long* counts) {
-    int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (node >= n_nodes) return;
-    unsigned long long s = 0;
-    for (int t = lane; t < T; t += 32) s += dir[(size_t)node * T + t] & 0x7FFull;
+// Per-node record counts were accumulated by emit(). Exclusive scan over nodes in two fully parallel kernels
+// (block sums, then block-local scan + prefix of the block sums), then the gather.
+constexpr int SCAN_BLOCK = 1024, SCAN_ITEMS = 4, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long block_reduce_sum(unsigned long long v, unsigned long long* sh) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(FULL, s, d);
-    if (lane == 0) counts[node] = s;
-}
-
-// 2) exclusive scan of n values by ONE block (n_nodes is at most a few hundred thousand): each thread owns a
-//    contiguous segment; block-wide scan of the segment sums through shared memory.
-__global__ void __launch_bounds__(1024) scan_kernel(const unsigned long long* counts, int n, long long* offsets) {
-    __shared__ unsigned long long part[1024];
-    const int tid = threadIdx.x;
-    const int seg = (n + 1023) / 1024;
-    const int b = min(n, tid * seg), e = min(n, b + seg);
-    unsigned long long s = 0;
-    for (int i = b; i < e; i++) s += counts[i];
-    part[tid] = s;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(FULL, v, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        unsigned long long t = tid >= d ? part[tid - d] : 0;
-        __syncthreads();
-        part[tid] += t;
-        __syncthreads();
+    unsigned long long t = (threadIdx.x < 32) ? sh[threadIdx.x] : 0ull;  // SCAN_BLOCK / 32 == 32 warps
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(FULL, t, d);
+        if (threadIdx.x == 0) sh[32] = t;
     }
-    unsigned long long run = part[tid] - s;
-    for (int i = b; i < e; i++) {
-        offsets[i] = (long long)run;
-        run += counts[i];
-    }
-    if (tid == 1023) offsets[n] = (long long)part[1023];
+    __syncthreads();
+    unsigned long long r = sh[32];
+    __syncthreads();
+    return r;
 }
 
-// 3) gather: a warp walks one node's tiles in order and copies each staged segment to its final place.
-// If the staging pool overflowed (the host will grow it and redo the backward pass) the segments beyond the
-// capacity were never written and the final arrays are too small: do nothing.
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(const unsigned int* counts, int n, unsigned long long* block_sums) {
+    __shared__ unsigned long long sh[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) s += counts[base + k];
+    s = block_reduce_sum(s, sh);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(const unsigned int* counts, int n, const unsigned long long* block_sums,
+                                                                long long* offsets) {
+    __shared__ unsigned long long sh[33];
+    __shared__ unsigned long long warp_tot[32];
+    // prefix of the sums of the blocks before this one
+    unsigned long long before = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_BLOCK) before += block_sums[b];
+    before = block_reduce_sum(before, sh);
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? counts[base + k] : 0u;
+        s += v[k];
+    }
+    // inclusive scan of the per-thread sums: warp shuffle scan, then the warp totals
+    unsigned long long incl = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(FULL, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_tot[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    unsigned long long run = before + warp_tot[warp] + (incl - s);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) offsets[base + k] = (long long)run;
+        run += v[k];
+        if (base + k == n - 1) offsets[n] = (long long)run;
+    }
+}
+
+// gather: a warp takes one node; each lane owns one tile's segment and copies it to its final place (segments are
+// short, a few records; the 32 copies of a node proceed in parallel). Nothing is done after a pool overflow: the
+// host grows the pool and reruns the backward pass.
 __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* staging, const long long* offsets, int n_nodes,
                               int T, long long col_base, int32_t* pos, uint8_t* type_code,
                               const unsigned long long* pool_count, unsigned long long staging_cap) {
@@ -605,24 +696,24 @@ __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* sta
     long long run = offsets[node];
     if (offsets[node + 1] == run) return;
     for (int t0 = 0; t0 < T; t0 += 32) {
-        int t = t0 + lane;
-        unsigned long long d = t < T ? dir[(size_t)node * T + t] : 0ull;
-        int cnt = int(d & 0x7FFull);
-        unsigned has = __ballot_sync(FULL, cnt != 0);
-        while (has) {
-            int src = __ffs(has) - 1;
-            has &= has - 1;
-            unsigned long long sd = __shfl_sync(FULL, d, src);
-            int n = int(sd & 0x7FFull);
-            const uint16_t* s = staging + (sd >> 11);
-            long long cb = col_base + (long long)(t0 + src) * TILE_COLS;
-            for (int i = lane; i < n; i += 32) {
-                uint32_t r = s[i];
-                pos[run + i] = int32_t(cb + (r & 1023u));
-                type_code[run + i] = uint8_t(((r >> 14) << 4) | ((r >> 10) & 15u));
-            }
-            run += n;
+        const int t = t0 + lane;
+        const unsigned long long d = t < T ? dir[(size_t)node * T + t] : 0ull;
+        const int cnt = int(d & 0x7FFull);
+        int incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, s);
+            if (lane >= s) incl += v;
         }
+        const long long at = run + (incl - cnt);
+        const uint16_t* src = staging + (d >> 11);
+        const long long cb = col_base + (long long)t * TILE_COLS;
+        for (int i = 0; i < cnt; i++) {
+            const uint32_t r = src[i];
+            pos[at + i] = int32_t(cb + (r & 1023u));
+            type_code[at + i] = uint8_t(((r >> 14) << 4) | ((r >> 10) & 15u));
+        }
+        run += __shfl_sync(FULL, incl, 31);
     }
 }
 

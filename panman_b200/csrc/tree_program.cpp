@@ -133,13 +133,56 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         tmp.push_back(std::move(ch));
     }
 
-    // ---- schedule order: level ascending, larger chunks first inside a level ----
-    std::vector<int32_t> order(tmp.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-        if (tmp[a].level != tmp[b].level) return tmp[a].level < tmp[b].level;
-        return tmp[a].nodes.size() > tmp[b].nodes.size();
-    });
+    // ---- ticket orders ----
+    const int32_t NC = int32_t(tmp.size());
+    std::vector<int32_t> par_chunk(NC, -1), par_pos(NC, 0), n_kids(NC, 0);
+    {
+        std::vector<int32_t> pos_in_chunk(n_nodes, 0);
+        for (auto& c : tmp)
+            for (size_t k = 0; k < c.nodes.size(); k++) pos_in_chunk[c.nodes[k]] = int32_t(k);
+        for (int32_t c = 0; c < NC; c++) {
+            int32_t r = tmp[c].root_node;
+            if (r == root) continue;
+            par_chunk[c] = chunk_of[parent[r]];
+            par_pos[c] = pos_in_chunk[parent[r]];
+            n_kids[par_chunk[c]]++;
+        }
+    }
+    // chunks were created children-first, so walking ids downwards visits parents before children
+    std::vector<int64_t> t_end(NC, 0), est(NC, 0);  // ops left after the chunk ends (forward) / before it can start (backward)
+    for (int32_t c = NC - 1; c >= 0; c--) {
+        if (par_chunk[c] < 0) continue;
+        int32_t q = par_chunk[c];
+        int64_t after = int64_t(tmp[q].nodes.size()) - par_pos[c];  // parent's ops from the consuming op to its end
+        t_end[c] = after + t_end[q];
+        est[c] = est[q] + after;  // backward runs the parent chunk's ops in reverse: same count
+    }
+    std::vector<int32_t> fwd_order;
+    fwd_order.reserve(NC);
+    {
+        // Kahn's algorithm with a max-heap on the remaining chain (own ops + t_end)
+        auto key = [&](int32_t c) { return int64_t(tmp[c].nodes.size()) + t_end[c]; };
+        auto cmp = [&](int32_t a, int32_t b) { return key(a) != key(b) ? key(a) < key(b) : a > b; };
+        std::vector<int32_t> heap;
+        std::vector<int32_t> pending = n_kids;
+        for (int32_t c = 0; c < NC; c++)
+            if (pending[c] == 0) heap.push_back(c);
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            int32_t c = heap.back();
+            heap.pop_back();
+            fwd_order.push_back(c);
+            int32_t q = par_chunk[c];
+            if (q >= 0 && --pending[q] == 0) {
+                heap.push_back(q);
+                std::push_heap(heap.begin(), heap.end(), cmp);
+            }
+        }
+        if (int32_t(fwd_order.size()) != NC) return "internal error: chunk order";
+    }
+    std::vector<int32_t> new_id(NC);
+    for (int32_t k = 0; k < NC; k++) new_id[fwd_order[k]] = k;
     int32_t n_levels = 0;
     for (auto& c : tmp) n_levels = std::max(n_levels, c.level + 1);
 
@@ -148,18 +191,32 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     P.n_internal = n_internal;
     P.root = root;
     P.node_op.assign(n_nodes, -1);
-    P.chunks.reserve(tmp.size());
-    P.level_chunk_begin.assign(n_levels + 1, 0);
+    P.chunks.reserve(NC);
     int32_t op = 0;
-    for (int32_t oi : order) {
+    for (int32_t oi : fwd_order) {
         TmpChunk& c = tmp[oi];
-        P.level_chunk_begin[c.level + 1]++;
         Chunk ck{op, op + int32_t(c.nodes.size())};
         for (int32_t v : c.nodes) P.node_op[v] = op++;
         P.chunks.push_back(ck);
     }
-    for (int32_t l = 0; l < n_levels; l++) P.level_chunk_begin[l + 1] += P.level_chunk_begin[l];
     if (op != n_internal) return "internal error: op count";
+    P.bwd_order.resize(NC);
+    std::iota(P.bwd_order.begin(), P.bwd_order.end(), 0);
+    std::stable_sort(P.bwd_order.begin(), P.bwd_order.end(), [&](int32_t a, int32_t b) {
+        int32_t oa = fwd_order[a], ob = fwd_order[b];
+        if (est[oa] != est[ob]) return est[oa] < est[ob];
+        return tmp[oa].nodes.size() > tmp[ob].nodes.size();
+    });
+    P.level_order.resize(NC);
+    std::iota(P.level_order.begin(), P.level_order.end(), 0);
+    std::stable_sort(P.level_order.begin(), P.level_order.end(), [&](int32_t a, int32_t b) {
+        int32_t oa = fwd_order[a], ob = fwd_order[b];
+        if (tmp[oa].level != tmp[ob].level) return tmp[oa].level < tmp[ob].level;
+        return tmp[oa].nodes.size() > tmp[ob].nodes.size();
+    });
+    P.level_chunk_begin.assign(n_levels + 1, 0);
+    for (auto& c : tmp) P.level_chunk_begin[c.level + 1]++;
+    for (int32_t l = 0; l < n_levels; l++) P.level_chunk_begin[l + 1] += P.level_chunk_begin[l];
 
     // ---- ops ----
     std::vector<int32_t> op_node(n_internal);
@@ -211,6 +268,15 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         }
         f.n_refs = int32_t(P.refs.size()) - f.ref_begin;
         max_arity = std::max(max_arity, f.n_refs);
+        if (f.n_refs == 2) {
+            const uint32_t k0 = P.refs[f.ref_begin] >> 30, k1 = P.refs[f.ref_begin + 1] >> 30;
+            int32_t type = FT_GENERIC;
+            if (k0 == REF_LEAF && k1 == REF_LEAF) type = FT_LEAF_LEAF;
+            else if (k0 == REF_LEAF && k1 == REF_ACC) type = FT_LEAF_ACC;
+            else if (k0 == REF_LEAF && k1 == REF_INT) type = FT_LEAF_INT;
+            else if (k0 == REF_INT && k1 == REF_ACC) type = FT_INT_ACC;
+            f.flags |= type << OPF_TYPE_SHIFT;
+        }
         f.max_arity_bits = f.n_refs <= 3 ? 2 : (f.n_refs <= 15 ? 4 : (f.n_refs <= 255 ? 8 : 20));
         b.n_leaves = int32_t(P.bwd_leaves.size()) - b.leaf_begin;
         b.fslot_out = fslot[i];

@@ -33,8 +33,11 @@ enum : int32_t {
     OPF_ROOT = 1,
     OPF_SIGNAL = 2,      // forward: this op is a chunk root, publish its done flag after the store
     OPF_PARENT_EXT = 4,  // backward: the parent's state slot is written by another chunk, wait for it
-    OPF_SIGNAL_F = 8     // backward: another chunk reads this op's state slot, publish after the store
+    OPF_SIGNAL_F = 8,    // backward: another chunk reads this op's state slot, publish after the store
+    OPF_TYPE_SHIFT = 8   // forward: bits 8..11 hold the op's shape (FwdType) for the fast paths
 };
+// shape of a forward op; refs are stored in the order named (leaves first, then internal children heavy -> light)
+enum FwdType : int32_t { FT_GENERIC = 0, FT_LEAF_LEAF = 1, FT_LEAF_ACC = 2, FT_LEAF_INT = 3, FT_INT_ACC = 4 };
 
 struct FwdOp {  // 16 bytes; the op index is also the node's row ("slot") in the set matrix
     int32_t ref_begin;
@@ -70,8 +73,14 @@ struct TreeProgram {
     std::vector<uint32_t> refs;
     std::vector<BwdOp> bwd_ops;
     std::vector<BwdLeaf> bwd_leaves;
-    std::vector<Chunk> chunks;                // schedule order: level-major, big chunks first
-    std::vector<int32_t> level_chunk_begin;   // n_levels + 1
+    std::vector<Chunk> chunks;                // in forward ticket order (see below)
+    // Ticket orders of the persistent kernels. Both are topological for their pass, so an item only waits for
+    // smaller tickets. Forward = chunks[] order itself: critical-path list scheduling, among the chunks whose inputs
+    // are all scheduled take the one with the longest remaining chain of ops up to the root. Backward = bwd_order:
+    // ascending earliest start (ops executed on the way down from the root before the chunk's parent state exists).
+    std::vector<int32_t> bwd_order;           // chunk indices
+    std::vector<int32_t> level_order;         // chunk indices, level-major (for schedule = one launch per level)
+    std::vector<int32_t> level_chunk_begin;   // n_levels + 1, into level_order
     std::vector<int32_t> node_op;             // node id -> op index, -1 for leaves
     int n_levels() const { return int(level_chunk_begin.size()) - 1; }
 };

@@ -32,7 +32,7 @@ class Emulator:
         self.L.emul_run.restype = C.c_longlong
 
     def run(self, tree, algo, leaf_codes, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None,
-            block_mode=0, chunk_nodes=8, col_base=0, want_states=True, inline_nodes=3):
+            block_mode=0, chunk_nodes=8, col_base=0, want_states=True, inline_nodes=3, level_mode=0):
         codes = np.ascontiguousarray(leaf_codes, np.uint8)
         n_rows, n_cols = codes.shape
         pc = np.ascontiguousarray(parent_code, np.uint8)
@@ -48,7 +48,7 @@ class Emulator:
                 _p(tree.child_idx, C.c_int32), _p(tree.leaf_row, C.c_int32), C.c_int(chunk_nodes), C.c_longlong(n_cols),
                 _p(codes, C.c_uint8), _p(lp, C.c_uint8), _p(pc, C.c_uint8), _p(ro, C.c_int8), _p(fr, C.c_int8),
                 C.c_longlong(col_base), _p(off, C.c_longlong), _p(pos, C.c_int32), _p(tc, C.c_uint8), _p(states, C.c_uint8),
-                _p(stats, C.c_int32), C.c_int(inline_nodes))
+                _p(stats, C.c_int32), C.c_int(inline_nodes), C.c_int(level_mode))
 
         n = call(None, None, None)
         if n < 0:

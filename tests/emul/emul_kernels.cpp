@@ -24,7 +24,8 @@ struct U4 { uint32_t x, y, z, w; };
 struct Emu {
     TreeProgram P;
     int T = 0, flags = 0, algo = 0;  // flags: 1 block mode
-    std::vector<U4> leaf_planes, sets, fstore, colparams, states;
+    std::vector<U4> leaf_planes, sets, colparams, states;
+    std::vector<uint32_t> fstore;  // [fslot][tile][160 words]
     std::vector<uint8_t> present;
     bool have_present = false;
     std::vector<unsigned> done, fdone;   // dependency flags, as in the kernels (value 1 = published this run)
@@ -116,6 +117,36 @@ void forward_item(Emu& E, int chunk, int tile) {
         const FwdOp f = E.P.fwd_ops[op];
         for (int lane = 0; lane < 32; lane++) {
             if (E.algo == 0) {
+                const int type = E.have_present ? FT_GENERIC : ((f.flags >> OPF_TYPE_SHIFT) & 15);
+                auto leafc = [&](int r, uint32_t cc[4]) {
+                    uint32_t idx = E.P.refs[f.ref_begin + r] & REF_IDX_MASK;
+                    U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
+                    cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
+                };
+                auto intset = [&](int r, uint32_t X[16]) {
+                    uint32_t ref = E.P.refs[f.ref_begin + r], idx = ref & REF_IDX_MASK;
+                    if ((ref & REF_EXT) && E.done[(size_t)idx * T + tile] != 1) E.order_violation = true;
+                    load16(E.sets.data() + ((size_t)idx * T + tile) * 128, lane, X);
+                };
+                if (type == FT_LEAF_LEAF) {
+                    uint32_t c0[4], c1[4];
+                    leafc(0, c0); leafc(1, c1);
+                    fitch_leaf_leaf(c0, c1, acc[lane]);
+                } else if (type == FT_LEAF_ACC) {
+                    uint32_t c0[4], X[16];
+                    leafc(0, c0);
+                    for (int k = 0; k < 16; k++) X[k] = acc[lane][k];
+                    fitch_leaf_set(c0, X, acc[lane]);
+                } else if (type == FT_LEAF_INT) {
+                    uint32_t c0[4], X[16];
+                    leafc(0, c0); intset(1, X);
+                    fitch_leaf_set(c0, X, acc[lane]);
+                } else if (type == FT_INT_ACC) {
+                    uint32_t X[16], Y[16];
+                    intset(0, X);
+                    for (int k = 0; k < 16; k++) Y[k] = acc[lane][k];
+                    fitch_set_set(X, Y, acc[lane]);
+                } else {
                 FitchFold fold;
                 fold.reset();
                 for (int r = 0; r < f.n_refs; r++) {
@@ -134,6 +165,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                     }
                 }
                 fold.finish(acc[lane]);
+                }
                 if ((f.flags & OPF_ROOT) && !(E.flags & 1)) {
                     const U4* cp = E.colparams.data() + (size_t)tile * 128;
                     U4 rc = cp[64 + lane];
@@ -200,9 +232,9 @@ void backward_item(Emu& E, int chunk, int tile) {
                     pvis = accVis[lane];
                 } else {
                     if ((b.flags & OPF_PARENT_EXT) && E.fdone[(size_t)b.parent_ref * T + tile] != 1) E.order_violation = true;
-                    const U4* fs = E.fstore.data() + ((size_t)b.parent_ref * T + tile) * 64;
-                    U4 a = fs[lane];
-                    pvis = fs[32 + lane].x;
+                    const uint32_t* fs = E.fstore.data() + ((size_t)b.parent_ref * T + tile) * 160;
+                    U4 a = reinterpret_cast<const U4*>(fs)[lane];
+                    pvis = fs[128 + lane];
                     P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
                 }
                 if (E.algo == 0) fitch_assign(G, P, pvis, F, vis);
@@ -212,9 +244,9 @@ void backward_item(Emu& E, int chunk, int tile) {
             for (int k = 0; k < 4; k++) { wm.P[lane][k] = P[k]; wm.F[lane][k] = F[k]; Fw[lane][k] = F[k]; }
             visw[lane] = vis;
             if (b.fslot_out >= 0) {
-                U4* fs = E.fstore.data() + ((size_t)b.fslot_out * T + tile) * 64;
-                fs[lane] = U4{F[0], F[1], F[2], F[3]};
-                fs[32 + lane] = U4{vis, 0, 0, 0};
+                uint32_t* fs = E.fstore.data() + ((size_t)b.fslot_out * T + tile) * 160;
+                reinterpret_cast<U4*>(fs)[lane] = U4{F[0], F[1], F[2], F[3]};
+                fs[128 + lane] = vis;
             }
             store_state(E, b.node, tile, lane, F, vis);
         }
@@ -253,7 +285,7 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
                    const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
                    const int8_t* fwd_root_ref, long long col_base, long long* node_offsets, int32_t* pos,
                    uint8_t* type_code, uint8_t* states_out, int32_t* prog_stats /* 4: chunks, levels, fslots, max_arity */,
-                   int inline_nodes) {
+                   int inline_nodes, int level_mode) {
     Emu E;
     std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, inline_nodes, &E.P);
     if (!err.empty()) return -1;
@@ -301,7 +333,7 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
         cp[96 + lane].z |= bit;
     }
     E.sets.assign((size_t)P.n_internal * T * (algo == 0 ? 128 : 256), U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
-    E.fstore.assign((size_t)std::max(1, P.n_fslots) * T * 64, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    E.fstore.assign((size_t)std::max(1, P.n_fslots) * T * 160, 0xDEADBEEFu);
     if (states_out) E.states.assign((size_t)n_nodes * T * 64, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
     E.dir.assign((size_t)n_nodes * T, 0ull);
     E.done.assign((size_t)P.n_internal * T, 0u);
@@ -311,8 +343,22 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
     const int NC = int(P.chunks.size());
     for (int ch = 0; ch < NC; ch++)
         for (int t = 0; t < E.T; t++) forward_item(E, ch, t);
-    for (int ch = NC - 1; ch >= 0; ch--)
-        for (int t = 0; t < E.T; t++) backward_item(E, ch, t);
+    for (int k = 0; k < NC; k++)
+        for (int t = 0; t < E.T; t++) backward_item(E, P.bwd_order[k], t);
+    if (level_mode) {  // the level-major order must be a valid schedule too (one launch per level)
+        std::fill(E.done.begin(), E.done.end(), 0u);
+        std::fill(E.fdone.begin(), E.fdone.end(), 0u);
+        E.pool = 0;
+        E.staging.clear();
+        std::fill(E.dir.begin(), E.dir.end(), 0ull);
+        const int L = P.n_levels();
+        for (int l = 0; l < L; l++)
+            for (int k = P.level_chunk_begin[l + 1] - 1; k >= P.level_chunk_begin[l]; k--)
+                for (int t = E.T - 1; t >= 0; t--) forward_item(E, P.level_order[k], t);
+        for (int l = L - 1; l >= 0; l--)
+            for (int k = P.level_chunk_begin[l + 1] - 1; k >= P.level_chunk_begin[l]; k--)
+                for (int t = E.T - 1; t >= 0; t--) backward_item(E, P.level_order[k], t);
+    }
     if (E.order_violation) return -7;
     if (E.error & 1) return -4;
     // node_count + scan + gather

@@ -19,7 +19,7 @@ def test_emulation_matches_golden(emu, chunk_nodes, inline_nodes):
     for c in load_cases():
         rc, got, states, _ = emu.run(c["tree"], c["algo"], c["codes"], c["parent_code"], c["root_override"],
                                      c["fwd_root_ref"], c["leaf_present"], c["block"], chunk_nodes=chunk_nodes,
-                                     inline_nodes=inline_nodes)
+                                     inline_nodes=inline_nodes, level_mode=chunk_nodes % 2)
         assert rc == 0
         assert got.same_as(c["expect"]), f"golden case {c['id']} chunk_nodes={chunk_nodes}"
         assert np.array_equal(states, c["states"]), f"golden case {c['id']} states"
@@ -48,7 +48,7 @@ def test_emulation_vs_port_random(emu, port, algo):
             lp[0] = 1
         want, want_states = port.run(tree, algo, codes, pc, ro, fr, lp, block, n_threads=2, want_states=True)
         rc, got, states, stats = emu.run(tree, algo, codes, pc, ro, fr, lp, block, chunk_nodes=int(rng.choice([1, 2, 5, 16, 64])),
-                                         col_base=7, inline_nodes=int(rng.choice([0, 1, 3, 10])))
+                                         col_base=7, inline_nodes=int(rng.choice([0, 1, 3, 10])), level_mode=trial % 2)
         assert rc == 0
         want.pos = want.pos + 7
         assert got.same_as(want), (algo, trial, kind, stats)
