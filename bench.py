@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--cols", type=int, default=0, help="override the column count (debug)")
     ap.add_argument("--leaves", type=int, default=0, help="override the leaf count (debug)")
     ap.add_argument("--chunk-nodes", type=int, default=0)
+    ap.add_argument("--col-groups", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -213,6 +214,8 @@ def run_b200_arm(args):
     ctx = pb.Context(local)
     if args.chunk_nodes:
         ctx.set_option("chunk_nodes", args.chunk_nodes)
+    if args.col_groups:
+        ctx.set_option("col_groups", args.col_groups)
     ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
     ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro, None, None, c0)
 

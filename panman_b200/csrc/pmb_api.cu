@@ -70,6 +70,10 @@ struct pmb_ctx {
     int64_t opt_staging_records = 0;  // 0 = choose from the problem size
     int64_t opt_inline_nodes = 3;     // light subtrees up to this size are evaluated inside the parent's chunk
     int64_t opt_schedule = 1;         // 1 = persistent kernels with dependency flags, 0 = one launch per level
+    int64_t opt_col_groups = 0;       // column-tile groups run on separate streams (0 = chosen from the tile count)
+    static constexpr int MAX_GROUPS = 16;
+    cudaStream_t gstream[MAX_GROUPS] = {};
+    cudaEvent_t gev_fwd[MAX_GROUPS] = {}, gev_done[MAX_GROUPS] = {}, ev_fork = nullptr;
     int n_sms = 0;
     unsigned int epoch = 0;
 
@@ -170,10 +174,11 @@ int ensure_flags(pmb_ctx* c, DevBuf& buf, size_t words) {
 }
 
 template <class K>
-int launch_kernel(pmb_ctx* c, K kernel, size_t smem, const RunParams& rp_in, int chunk_begin, int n_chunks, int* n_launches) {
+int launch_kernel(pmb_ctx* c, cudaStream_t stream, K kernel, size_t smem, const RunParams& rp_in, int chunk_begin, int n_chunks,
+                  int* n_launches) {
     RunParams rp = rp_in;
     dim3 block(WARPS_PER_BLOCK * 32);
-    long long warps = (long long)n_chunks * c->T;
+    long long warps = (long long)n_chunks * rp.tile_count;
     if (warps <= 0) return PMB_OK;
     unsigned blocks;
     if (rp.ticket) {
@@ -181,26 +186,27 @@ int launch_kernel(pmb_ctx* c, K kernel, size_t smem, const RunParams& rp_in, int
         PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, smem));
         long long resident = (long long)std::max(1, per_sm) * c->n_sms;
         blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
-        PMB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(unsigned long long), c->stream));
+        PMB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(unsigned long long), stream));
     } else {
         blocks = unsigned((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     }
-    kernel<<<blocks, block, smem, c->stream>>>(rp, chunk_begin, n_chunks);
+    kernel<<<blocks, block, smem, stream>>>(rp, chunk_begin, n_chunks);
     (*n_launches)++;
     return PMB_OK;
 }
 
 template <class K>
-int launch_schedule(pmb_ctx* c, K kernel, size_t smem, RunParams rp, bool forward, int* n_launches) {
+int launch_schedule(pmb_ctx* c, cudaStream_t stream, int ticket_slot, K kernel, size_t smem, RunParams rp, bool forward,
+                    int* n_launches) {
     const TreeProgram& P = c->prog;
     int rc;
     if (smem > 48 * 1024) PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     if (c->opt_schedule == 1) {
         // persistent: tickets follow chunks[] (forward) or bwd_order (backward), both topological for their pass
-        rp.ticket = c->d_ticket.as<unsigned long long>();
+        rp.ticket = c->d_ticket.as<unsigned long long>() + ticket_slot;
         rp.order = forward ? nullptr : c->d_bwd_order.as<int>();
         rp.stage_block = 512;
-        if ((rc = launch_kernel(c, kernel, smem, rp, 0, int(P.chunks.size()), n_launches))) return rc;
+        if ((rc = launch_kernel(c, stream, kernel, smem, rp, 0, int(P.chunks.size()), n_launches))) return rc;
     } else {
         rp.ticket = nullptr;
         rp.order = c->d_level_order.as<int>();
@@ -209,26 +215,36 @@ int launch_schedule(pmb_ctx* c, K kernel, size_t smem, RunParams rp, bool forwar
         for (int i = 0; i < L; i++) {
             int l = forward ? i : L - 1 - i;
             int cb = P.level_chunk_begin[l], nc = P.level_chunk_begin[l + 1] - cb;
-            if ((rc = launch_kernel(c, kernel, smem, rp, cb, nc, n_launches))) return rc;
+            if ((rc = launch_kernel(c, stream, kernel, smem, rp, cb, nc, n_launches))) return rc;
         }
     }
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
 
-int launch_pass(pmb_ctx* c, const RunParams& rp, int algo, bool forward, int* n_launches) {
+int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParams& rp, int algo, bool forward, int* n_launches) {
     const TreeProgram& P = c->prog;
     const size_t fwd_smem = size_t(WARPS_PER_BLOCK) * FWD_DEPTH * FWD_STAGE_U4 * sizeof(uint4);
     const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * BWD_DEPTH * (4 + 2) * 32 * sizeof(uint4);
     const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * BWD_DEPTH * (8 + 2) * 32 * sizeof(uint4);
     if (algo == PMB_ALGO_FITCH)
-        return forward ? launch_schedule(c, fitch_forward_kernel, fwd_smem, rp, true, n_launches)
-                       : launch_schedule(c, fitch_backward_kernel, bwd_smem_f, rp, false, n_launches);
-    if (!forward) return launch_schedule(c, sankoff_backward_kernel, bwd_smem_s, rp, false, n_launches);
-    if (P.max_arity <= 3) return launch_schedule(c, sankoff_forward_kernel<2>, fwd_smem, rp, true, n_launches);
-    if (P.max_arity <= 15) return launch_schedule(c, sankoff_forward_kernel<4>, fwd_smem, rp, true, n_launches);
-    if (P.max_arity <= 255) return launch_schedule(c, sankoff_forward_kernel<8>, fwd_smem, rp, true, n_launches);
-    return launch_schedule(c, sankoff_forward_kernel<20>, fwd_smem, rp, true, n_launches);
+        return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel, fwd_smem, rp, true, n_launches)
+                       : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel, bwd_smem_f, rp, false, n_launches);
+    if (!forward) return launch_schedule(c, stream, ticket_slot, sankoff_backward_kernel, bwd_smem_s, rp, false, n_launches);
+    if (P.max_arity <= 3) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<2>, fwd_smem, rp, true, n_launches);
+    if (P.max_arity <= 15) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<4>, fwd_smem, rp, true, n_launches);
+    if (P.max_arity <= 255) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<8>, fwd_smem, rp, true, n_launches);
+    return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<20>, fwd_smem, rp, true, n_launches);
+}
+
+// Column tiles are split into groups that run forward -> backward on their own streams: a group's low-parallelism
+// phases (the top of the tree at the end of its forward pass and at the start of its backward pass) overlap another
+// group's bulk work, and a group's set rows are re-read by its backward pass soon after they were written.
+int pick_groups(const pmb_ctx* c) {
+    int64_t g = c->opt_col_groups;
+    if (g <= 0) g = c->T >= 12 ? 3 : (c->T >= 4 ? 2 : 1);
+    g = std::min<int64_t>(g, std::min<int64_t>(c->T, pmb_ctx::MAX_GROUPS));
+    return int(std::max<int64_t>(1, g));
 }
 
 }  // namespace
@@ -248,6 +264,19 @@ int pmb_create(pmb_ctx** out, int device) {
     if (e != cudaSuccess) {
         // keep the context so that pmb_last_error can say why; every compute call will refuse to run
         c->err = std::string("no usable CUDA device: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        c->stream = nullptr;
+        *out = c;
+        return PMB_ERR_CUDA;
+    }
+    for (int g = 0; g < pmb_ctx::MAX_GROUPS && e == cudaSuccess; g++) {
+        e = cudaStreamCreateWithFlags(&c->gstream[g], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->gev_fwd[g], cudaEventDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->gev_done[g], cudaEventDefault);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        c->err = std::string("stream/event creation failed: ") + cudaGetErrorString(e);
         cudaGetLastError();
         c->stream = nullptr;
         *out = c;
@@ -273,6 +302,12 @@ void pmb_destroy(pmb_ctx* c) {
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters}) b->release();
         for (int i = 0; i < 4; i++)
             if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        for (int g = 0; g < pmb_ctx::MAX_GROUPS; g++) {
+            if (c->gev_fwd[g]) cudaEventDestroy(c->gev_fwd[g]);
+            if (c->gev_done[g]) cudaEventDestroy(c->gev_done[g]);
+            if (c->gstream[g]) cudaStreamDestroy(c->gstream[g]);
+        }
+        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -287,6 +322,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "staging_records") c->opt_staging_records = value;
     else if (k == "inline_nodes") c->opt_inline_nodes = value;
     else if (k == "schedule") c->opt_schedule = value;
+    else if (k == "col_groups") c->opt_col_groups = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
 }
@@ -390,7 +426,7 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     PMB_CUDA(c->d_dir.ensure(size_t(P.n_nodes) * T * sizeof(unsigned long long)));
     PMB_CUDA(c->d_counters.ensure(64));
     PMB_CUDA(c->h_counters.ensure(64));
-    PMB_CUDA(c->d_ticket.ensure(64));
+    PMB_CUDA(c->d_ticket.ensure(64 * sizeof(unsigned long long)));
     {
         int rcf;
         if ((rcf = ensure_flags(c, c->d_done, size_t(P.n_internal) * T))) return rcf;
@@ -432,11 +468,16 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     rp.flags = ((flags & PMB_FLAG_BLOCK_MODE) ? RUN_BLOCK_MODE : 0) | (want_states ? RUN_WANT_STATES : 0);
 
     int n_launches = 0;
+    int rc = 0;
+    const int G = pick_groups(c);
+    auto group_range = [&](int g, int* tb, int* tc) {
+        *tb = int((long long)c->T * g / G);
+        *tc = int((long long)c->T * (g + 1) / G) - *tb;
+    };
+    PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 64 * sizeof(unsigned long long), c->stream));
     PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     rp.epoch = ++c->epoch;
-    int rc = launch_pass(c, rp, algo, true, &n_launches);
-    if (rc) return rc;
-    PMB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    const unsigned int fwd_epoch = rp.epoch;
     for (int attempt = 0;; attempt++) {
         PMB_CUDA(c->d_staging.ensure(size_t(c->staging_cap) * sizeof(uint16_t)));
         PMB_CUDA(c->d_pos.ensure(size_t(c->staging_cap) * sizeof(int32_t)));
@@ -447,8 +488,22 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         PMB_CUDA(cudaMemsetAsync(c->d_node_counts.p, 0, size_t(P.n_nodes) * sizeof(unsigned int), c->stream));
         unsigned int init[4] = {0, 0, 0, 0xFFFFFFFFu};  // pool_count (64 bit), error flags, first bad column
         PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-        rp.epoch = ++c->epoch;
-        if ((rc = launch_pass(c, rp, algo, false, &n_launches))) return rc;
+        const unsigned int bwd_epoch = ++c->epoch;
+        PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        for (int g = 0; g < G; g++) {
+            cudaStream_t st = G == 1 ? c->stream : c->gstream[g];
+            if (G > 1) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_fork, 0));
+            group_range(g, &rp.tile_begin, &rp.tile_count);
+            if (attempt == 0) {  // the forward result stays valid across a staging-pool retry
+                rp.epoch = fwd_epoch;
+                if ((rc = launch_pass(c, st, 2 * g, rp, algo, true, &n_launches))) return rc;
+            }
+            PMB_CUDA(cudaEventRecord(c->gev_fwd[g], st));
+            rp.epoch = bwd_epoch;
+            if ((rc = launch_pass(c, st, 2 * g + 1 + 32 * (attempt & 1), rp, algo, false, &n_launches))) return rc;
+            PMB_CUDA(cudaEventRecord(c->gev_done[g], st));
+            if (G > 1) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->gev_done[g], 0));
+        }
         PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
         {
             scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(rp.node_count, P.n_nodes, c->d_block_sums.as<unsigned long long>());
@@ -483,8 +538,16 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 16);  // offsets[n_nodes]; the pool also holds slack
         break;
     }
-    PMB_CUDA(cudaEventElapsedTime(&c->timings.forward_ms, c->ev[0], c->ev[1]));
-    PMB_CUDA(cudaEventElapsedTime(&c->timings.backward_ms, c->ev[1], c->ev[2]));
+    // groups overlap: "forward" = until the last group's forward pass ended, "backward" = the rest up to compaction
+    float to_bwd_end = 0.f;
+    c->timings.forward_ms = 0.f;
+    for (int g = 0; g < G; g++) {
+        float f = 0.f;
+        PMB_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->gev_fwd[g]));
+        c->timings.forward_ms = std::max(c->timings.forward_ms, f);
+    }
+    PMB_CUDA(cudaEventElapsedTime(&to_bwd_end, c->ev[0], c->ev[2]));
+    c->timings.backward_ms = to_bwd_end - c->timings.forward_ms;
     PMB_CUDA(cudaEventElapsedTime(&c->timings.compact_ms, c->ev[2], c->ev[3]));
     PMB_CUDA(cudaEventElapsedTime(&c->timings.total_ms, c->ev[0], c->ev[3]));
     c->timings.n_launches = n_launches;

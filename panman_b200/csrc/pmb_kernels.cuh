@@ -51,6 +51,7 @@ struct RunParams {
     int T;
     int flags;
     int stage_block;              // staging records a warp reserves per atomic
+    int tile_begin, tile_count;   // this launch covers tiles [tile_begin, tile_begin + tile_count) (column group)
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
@@ -91,10 +92,10 @@ __device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int 
         it.taken = true;
         w = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     }
-    if (w >= (unsigned long long)n_chunks * (unsigned long long)p.T) return false;
-    int c = chunk_begin + int(w / (unsigned)p.T);
+    if (w >= (unsigned long long)n_chunks * (unsigned long long)p.tile_count) return false;
+    int c = chunk_begin + int(w / (unsigned)p.tile_count);
     chunk = p.order ? __ldg(p.order + c) : c;
-    tile = int(w % (unsigned)p.T);
+    tile = p.tile_begin + int(w % (unsigned)p.tile_count);
     return true;
 }
 

@@ -45,6 +45,7 @@ def test_golden_vectors(ctx, chunk_nodes, inline_nodes, schedule):
     ctx.set_option("chunk_nodes", 0)
     ctx.set_option("inline_nodes", 3)
     ctx.set_option("schedule", 1)
+    ctx.set_option("col_groups", 0)
 
 
 @pytest.mark.parametrize("algo", [0, 1])
@@ -72,6 +73,7 @@ def test_random_vs_oracle(ctx, port, algo):
         ctx.set_option("chunk_nodes", int(rng.choice([0, 1, 7, 64])))
         ctx.set_option("inline_nodes", int(rng.choice([0, 2, 3, 9])))
         ctx.set_option("schedule", int(trial % 3 != 0))
+        ctx.set_option("col_groups", int(rng.choice([0, 1, 2, 5])))
         _set_tree(ctx, tree)
         res = ctx.run_codes(tree, algo, codes, pc, ro, fr, lp, block, want_states=True, col_base=11)
         want.pos = want.pos + 11
@@ -80,6 +82,7 @@ def test_random_vs_oracle(ctx, port, algo):
     ctx.set_option("chunk_nodes", 0)
     ctx.set_option("inline_nodes", 3)
     ctx.set_option("schedule", 1)
+    ctx.set_option("col_groups", 0)
 
 
 def test_dense_mutations_overflow_path(ctx, port):
