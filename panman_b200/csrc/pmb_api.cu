@@ -70,6 +70,9 @@ struct pmb_ctx {
     int64_t opt_staging_records = 0;  // 0 = choose from the problem size
     int64_t opt_inline_nodes = 3;     // light subtrees up to this size are evaluated inside the parent's chunk
     int64_t opt_schedule = 1;         // 1 = persistent kernels with dependency flags, 0 = one launch per level
+    int64_t opt_trace = 0;            // debug: record a per-item timeline (pmb_debug_trace)
+    DevBuf d_trace;
+    std::vector<unsigned long long> h_trace;
     int64_t opt_col_groups = 0;       // column-tile groups run on separate streams (0 = chosen from the tile count)
     static constexpr int MAX_GROUPS = 16;
     cudaStream_t gstream[MAX_GROUPS] = {};
@@ -323,6 +326,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "inline_nodes") c->opt_inline_nodes = value;
     else if (k == "schedule") c->opt_schedule = value;
     else if (k == "col_groups") c->opt_col_groups = value;
+    else if (k == "trace") c->opt_trace = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
 }
@@ -469,6 +473,13 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
 
     int n_launches = 0;
     int rc = 0;
+    const size_t trace_items = size_t(P.chunks.size()) * T;
+    rp.trace = nullptr;
+    if (c->opt_trace) {
+        PMB_CUDA(c->d_trace.ensure(trace_items * 2 * 4 * sizeof(unsigned long long)));
+        PMB_CUDA(cudaMemsetAsync(c->d_trace.p, 0, trace_items * 2 * 4 * sizeof(unsigned long long), c->stream));
+        rp.trace = c->d_trace.as<unsigned long long>();
+    }
     const int G = pick_groups(c);
     auto group_range = [&](int g, int* tb, int* tc) {
         *tb = int((long long)c->T * g / G);
@@ -494,12 +505,15 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
             cudaStream_t st = G == 1 ? c->stream : c->gstream[g];
             if (G > 1) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_fork, 0));
             group_range(g, &rp.tile_begin, &rp.tile_count);
+            // debug trace slots: forward items of the group, then (second half) its backward items
+            rp.trace_base = (unsigned long long)P.chunks.size() * rp.tile_begin;
             if (attempt == 0) {  // the forward result stays valid across a staging-pool retry
                 rp.epoch = fwd_epoch;
                 if ((rc = launch_pass(c, st, 2 * g, rp, algo, true, &n_launches))) return rc;
             }
             PMB_CUDA(cudaEventRecord(c->gev_fwd[g], st));
             rp.epoch = bwd_epoch;
+            rp.trace_base = trace_items + (unsigned long long)P.chunks.size() * rp.tile_begin;
             if ((rc = launch_pass(c, st, 2 * g + 1 + 32 * (attempt & 1), rp, algo, false, &n_launches))) return rc;
             PMB_CUDA(cudaEventRecord(c->gev_done[g], st));
             if (G > 1) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->gev_done[g], 0));
@@ -550,6 +564,10 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     c->timings.backward_ms = to_bwd_end - c->timings.forward_ms;
     PMB_CUDA(cudaEventElapsedTime(&c->timings.compact_ms, c->ev[2], c->ev[3]));
     PMB_CUDA(cudaEventElapsedTime(&c->timings.total_ms, c->ev[0], c->ev[3]));
+    if (c->opt_trace) {
+        c->h_trace.resize(trace_items * 2 * 4);
+        PMB_CUDA(cudaMemcpy(c->h_trace.data(), c->d_trace.p, c->h_trace.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
     c->timings.n_launches = n_launches;
     c->timings.n_levels = P.n_levels();
     c->last_algo = algo;
@@ -617,6 +635,16 @@ int pmb_run_nuc(pmb_ctx* c, int algo, int64_t n_cols, int32_t n_rows, const uint
     if (rc) return rc;
     if ((rc = pmb_run_resident(c, algo, flags))) return rc;
     return pmb_download(c, out);
+}
+
+// Debug only (not part of include/panman_b200.h): the per-item timeline of the last run made with option "trace".
+// Layout: 2 * n_items records of 4 x uint64 {start ns, end ns, (chunk << 32) | tile, (sm << 32) | ns spent waiting};
+// the first n_items are forward items, the rest backward items. Returns the number of uint64 copied.
+long long pmb_debug_trace(const pmb_ctx* c, unsigned long long* out, long long max_words) {
+    if (!c || !out) return 0;
+    long long n = std::min<long long>(max_words, (long long)c->h_trace.size());
+    std::memcpy(out, c->h_trace.data(), size_t(n) * sizeof(unsigned long long));
+    return n;
 }
 
 int pmb_last_timings(const pmb_ctx* c, pmb_timings* out) {

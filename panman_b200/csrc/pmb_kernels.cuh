@@ -52,7 +52,19 @@ struct RunParams {
     int flags;
     int stage_block;              // staging records a warp reserves per atomic
     int tile_begin, tile_count;   // this launch covers tiles [tile_begin, tile_begin + tile_count) (column group)
+    unsigned long long* trace;    // debug: per item {start ns, end ns, (chunk << 32) | tile, (sm << 32) | waited ns}; or nullptr
+    unsigned long long trace_base;
 };
+
+struct TraceItem {  // debug timeline of one work item (option "trace")
+    unsigned long long t0 = 0, w = 0;
+    unsigned waited = 0;
+};
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ uint4 ld_l2(const uint4* p) { return __ldcg(p); }
@@ -78,11 +90,12 @@ __device__ __forceinline__ void unpack16(const uint4 v[4], uint32_t S[16]) {
 // items out through an atomic ticket in the program's topological chunk order (reverse for the backward pass).
 // An item may only wait for data of items with SMALLER tickets, and every ticket holder is a resident, running
 // warp, so the lowest unfinished ticket always makes progress: no deadlock, no co-residency requirement.
+__device__ __forceinline__ unsigned long long global_ns();
 struct ItemIter {
     bool taken = false;
 };
 __device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int chunk_begin, int n_chunks, int& chunk,
-                                          int& tile, int lane) {
+                                          int& tile, int lane, TraceItem& tr) {
     unsigned long long w;
     if (p.ticket) {
         if (lane == 0) w = atomicAdd(p.ticket, 1ull);
@@ -96,7 +109,21 @@ __device__ __forceinline__ bool next_item(const RunParams& p, ItemIter& it, int 
     int c = chunk_begin + int(w / (unsigned)p.tile_count);
     chunk = p.order ? __ldg(p.order + c) : c;
     tile = p.tile_begin + int(w % (unsigned)p.tile_count);
+    if (p.trace) {
+        tr.t0 = global_ns();
+        tr.w = w;
+        tr.waited = 0;
+    }
     return true;
+}
+__device__ __forceinline__ void trace_end(const RunParams& p, const TraceItem& tr, int chunk, int tile, int lane) {
+    if (p.trace && lane == 0) {
+        unsigned long long* q = p.trace + (p.trace_base + tr.w) * 4;
+        q[0] = tr.t0;
+        q[1] = global_ns();
+        q[2] = ((unsigned long long)(unsigned)chunk << 32) | (unsigned)tile;
+        q[3] = ((unsigned long long)smid() << 32) | tr.waited;
+    }
 }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -115,7 +142,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 // Warp-collective wait until *flag == epoch. Lane 0 polls with back-off; a watchdog (wall clock) turns a
 // scheduling bug into error bit 2 instead of a hung GPU. Returns false if the run must be abandoned.
-__device__ __noinline__ bool wait_flag_slow(const unsigned* flag, unsigned epoch, unsigned* error, int lane) {
+__device__ __noinline__ bool wait_flag_slow(const unsigned* flag, unsigned epoch, unsigned* error, int lane, unsigned* waited) {
     unsigned ok = 1;
     if (lane == 0) {
         unsigned long long t0 = global_ns();
@@ -130,15 +157,16 @@ __device__ __noinline__ bool wait_flag_slow(const unsigned* flag, unsigned epoch
                 }
             }
         }
+        *waited += unsigned(global_ns() - t0);
     }
     return __shfl_sync(FULL, ok, 0) != 0;
 }
-__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, unsigned* error, int lane) {
+__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, unsigned* error, int lane, TraceItem& tr) {
     unsigned v = 0;
     if (lane == 0) v = ld_acquire(flag);
     v = __shfl_sync(FULL, v, 0);
     if (v == epoch) return true;
-    return wait_flag_slow(flag, epoch, error, lane);
+    return wait_flag_slow(flag, epoch, error, lane, &tr.waited);
 }
 // Publish: every lane's earlier stores happen-before the release store of lane 0 (warp barrier + release).
 __device__ __forceinline__ void signal_flag(unsigned* flag, unsigned epoch, int lane) {
@@ -258,8 +286,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FWD_DEPTH * FWD_STAGE_U4;
     const size_t T = p.T;
     ItemIter it;
+    TraceItem tr;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         uint32_t acc[16];
 #pragma unroll
@@ -285,7 +314,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 const uint32_t ref = __ldg(p.refs + f.x + (type == FT_LEAF_INT ? 1 : 0));
                 const uint32_t idx = ref & REF_IDX_MASK;
                 if (ref & REF_EXT) {
-                    if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return;
+                    if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane, tr)) return;
                 }
                 uint32_t X[16];
                 load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, X);
@@ -317,7 +346,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         fold.add_set(acc);
                     } else {
                         if (ref & REF_EXT) {
-                            if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return;
+                            if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane, tr)) return;
                         }
                         uint32_t S[16];
                         load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
@@ -339,6 +368,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
             store_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, acc);
             if (f.z & OPF_SIGNAL) signal_flag(p.done + (size_t)op * T + tile, p.epoch, lane);
         }
+        trace_end(p, tr, chunk, tile, lane);
     }
 }
 
@@ -367,7 +397,7 @@ struct BwdHead {
 
 // parent's assigned state from registers (ACC) or from its parked slot (possibly written by another chunk)
 __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h, int tile, int lane, const uint32_t accF[4],
-                                           uint32_t accVis, uint32_t P[4], uint32_t& pvis) {
+                                           uint32_t accVis, uint32_t P[4], uint32_t& pvis, TraceItem& tr) {
     if (h.b0.y == PARENT_ACC) {
         P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
         pvis = accVis;
@@ -375,7 +405,7 @@ __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h,
     }
     const size_t T = p.T;
     if (h.b1.y & OPF_PARENT_EXT) {
-        if (!wait_flag(p.fdone + (size_t)h.b0.y * T + tile, p.epoch, p.error, lane)) return false;
+        if (!wait_flag(p.fdone + (size_t)h.b0.y * T + tile, p.epoch, p.error, lane, tr)) return false;
     }
     const uint32_t* fs = p.fstore + ((size_t)h.b0.y * T + tile) * FSLOT_WORDS;
     uint4 a = ld_l2(reinterpret_cast<const uint4*>(fs) + lane);
@@ -425,9 +455,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
     ItemIter it;
+    TraceItem tr;
     StageCursor sc;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
@@ -438,7 +469,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             h.b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
             uint32_t P[4], pvis = 0, F[4], vis;
             if (h.b0.y != PARENT_ROOT) {
-                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis)) return;
+                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis, tr)) return;
             }
             cp_async_wait_pending(min(BWD_DEPTH - 1, op - ck.op_begin));
             const uint4* st = ring + ((last - op) % BWD_DEPTH) * STAGE;
@@ -473,13 +504,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
         }
+        trace_end(p, tr, chunk, tile, lane);
     }
 }
 
 // ------------------------------------------------------------------ Sankoff forward
 template <int B>
 __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int4 f, const uint4 l0, const uint4 l1, int tile,
-                                                   int lane, uint32_t accG[16], uint32_t accH[16]) {
+                                                   int lane, uint32_t accG[16], uint32_t accH[16], TraceItem& tr) {
     const size_t T = p.T;
     SankoffFold<B> fold;
     fold.reset();
@@ -504,7 +536,7 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
             if (ref & REF_EXT) {
-                if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane)) return false;
+                if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane, tr)) return false;
             }
             const uint4* base = p.sets + ((size_t)idx * T + tile) * 256;
             uint32_t G[16];
@@ -526,8 +558,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FWD_DEPTH * FWD_STAGE_U4;
     const size_t T = p.T;
     ItemIter it;
+    TraceItem tr;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         uint32_t accG[16], accH[16];
 #pragma unroll
@@ -540,16 +573,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
             const uint4 l0 = st[lane], l1 = st[32 + lane];
             if (op + FWD_DEPTH < ck.op_end) fwd_issue(p, ring, op + FWD_DEPTH, ck.op_begin, tile, lane);
             bool ok;
-            if (MAXB == 2 || f.w == 2) ok = sankoff_forward_op<2>(p, f, l0, l1, tile, lane, accG, accH);
-            else if (MAXB == 4 || f.w == 4) ok = sankoff_forward_op<4>(p, f, l0, l1, tile, lane, accG, accH);
-            else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, f, l0, l1, tile, lane, accG, accH);
-            else ok = sankoff_forward_op<20>(p, f, l0, l1, tile, lane, accG, accH);
+            if (MAXB == 2 || f.w == 2) ok = sankoff_forward_op<2>(p, f, l0, l1, tile, lane, accG, accH, tr);
+            else if (MAXB == 4 || f.w == 4) ok = sankoff_forward_op<4>(p, f, l0, l1, tile, lane, accG, accH, tr);
+            else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, f, l0, l1, tile, lane, accG, accH, tr);
+            else ok = sankoff_forward_op<20>(p, f, l0, l1, tile, lane, accG, accH, tr);
             if (!ok) return;
             uint4* base = p.sets + ((size_t)op * T + tile) * 256;
             store_planes16(base, lane, accG);
             store_planes16(base + 128, lane, accH);
             if (f.z & OPF_SIGNAL) signal_flag(p.done + (size_t)op * T + tile, p.epoch, lane);
         }
+        trace_end(p, tr, chunk, tile, lane);
     }
 }
 
@@ -560,9 +594,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
     ItemIter it;
+    TraceItem tr;
     StageCursor sc;
     int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane)) {
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
@@ -573,7 +608,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
             h.b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
             uint32_t P[4], pvis = 0, F[4], vis;
             if (h.b0.y != PARENT_ROOT) {
-                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis)) return;
+                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis, tr)) return;
             }
             cp_async_wait_pending(min(BWD_DEPTH - 1, op - ck.op_begin));
             const uint4* st = ring + ((last - op) % BWD_DEPTH) * STAGE;
@@ -605,6 +640,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
         }
+        trace_end(p, tr, chunk, tile, lane);
     }
 }
 
