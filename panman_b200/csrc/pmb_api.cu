@@ -86,7 +86,7 @@ struct pmb_ctx {
     std::vector<int32_t> child_off, child_idx, leaf_row;
     TreeProgram prog;
     int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1;
-    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order;
+    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order, d_row_slot;
 
     // resident input
     bool have_input = false;
@@ -161,6 +161,7 @@ int ensure_program(pmb_ctx* c) {
     if ((rc = upload_vec(c, c->d_chunks, c->prog.chunks))) return rc;
     if ((rc = upload_vec(c, c->d_bwd_order, c->prog.bwd_order))) return rc;
     if ((rc = upload_vec(c, c->d_level_order, c->prog.level_order))) return rc;
+    if ((rc = upload_vec(c, c->d_row_slot, c->prog.row_slot))) return rc;
     PMB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above may be rebuilt before the copies ran
     c->prog_chunk_nodes = k;
     c->prog_inline_nodes = inl;
@@ -297,7 +298,7 @@ void pmb_destroy(pmb_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_bwd_order,
-                          &c->d_level_order, &c->d_block_sums, &c->d_leaf_planes,
+                          &c->d_level_order, &c->d_row_slot, &c->d_block_sums, &c->d_leaf_planes,
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket})
@@ -384,14 +385,17 @@ int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* le
                                  size_t(nr) * size_t(row_stride_bytes), cudaMemcpyDefault, c->stream));
         long long total = (long long)nr * c->T * 32;
         unsigned blocks = unsigned((total + 255) / 256);
-        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tmp_codes.as<uint8_t>(), row_stride_bytes, nr, n_cols, c->T,
-                                                          c->d_leaf_planes.as<uint4>() + size_t(r0) * c->T * 32);
+        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tmp_codes.as<uint8_t>(), row_stride_bytes, r0, nr, n_rows, n_cols, c->T,
+                                                          c->d_row_slot.as<int>(), c->d_leaf_planes.as<uint4>());
     }
     PMB_CUDA(cudaGetLastError());
     c->have_present = leaf_present != nullptr;
-    if (leaf_present) {
+    if (leaf_present) {  // kernels index presence by leaf slot
+        std::vector<uint8_t> tmp(static_cast<size_t>(n_rows)), by_slot(static_cast<size_t>(n_rows));
+        PMB_CUDA(cudaMemcpy(tmp.data(), leaf_present, size_t(n_rows), cudaMemcpyDefault));
+        for (int32_t r = 0; r < n_rows; r++) by_slot[c->prog.row_slot[r]] = tmp[r];
         PMB_CUDA(c->d_present.ensure(size_t(n_rows)));
-        PMB_CUDA(cudaMemcpyAsync(c->d_present.p, leaf_present, size_t(n_rows), cudaMemcpyDefault, c->stream));
+        PMB_CUDA(cudaMemcpy(c->d_present.p, by_slot.data(), size_t(n_rows), cudaMemcpyHostToDevice));
     }
     PMB_CUDA(c->d_tmp_cols.ensure(size_t(n_cols) * 3));
     uint8_t* t = c->d_tmp_cols.as<uint8_t>();
@@ -469,6 +473,9 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     rp.fdone = c->d_fdone.as<unsigned int>();
     rp.ticket = nullptr;
     rp.T = c->T;
+    rp.n_ops = P.n_internal;
+    rp.n_rows = P.n_rows;
+    rp.n_fslots = std::max(1, P.n_fslots);
     rp.flags = ((flags & PMB_FLAG_BLOCK_MODE) ? RUN_BLOCK_MODE : 0) | (want_states ? RUN_WANT_STATES : 0);
 
     int n_launches = 0;

@@ -49,6 +49,7 @@ struct RunParams {
     unsigned int* node_count;     // [node] records emitted for the node in this run
     unsigned int epoch;
     int T;
+    int n_ops, n_rows, n_fslots;  // matrices are TILE-major: [tile][op], [tile][leaf slot], [tile][fslot]
     int flags;
     int stage_block;              // staging records a warp reserves per atomic
     int tile_begin, tile_count;   // this launch covers tiles [tile_begin, tile_begin + tile_count) (column group)
@@ -65,6 +66,12 @@ __device__ __forceinline__ unsigned smid() {
     asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
     return r;
 }
+
+// Tile-major addressing: for one tile the rows of consecutive ops (and the leaf rows in the order the program
+// consumes them) are contiguous, so a warp streams through memory instead of hopping between far-apart rows.
+__device__ __forceinline__ size_t set_index(const RunParams& p, unsigned op, int tile) { return (size_t)tile * p.n_ops + op; }
+__device__ __forceinline__ size_t leaf_index(const RunParams& p, unsigned slot, int tile) { return (size_t)tile * p.n_rows + slot; }
+__device__ __forceinline__ size_t fslot_index(const RunParams& p, unsigned f, int tile) { return (size_t)tile * p.n_fslots + f; }
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ uint4 ld_l2(const uint4* p) { return __ldcg(p); }
@@ -272,7 +279,7 @@ __device__ __forceinline__ void fwd_issue(const RunParams& p, uint4* ring, int o
     for (int r = 0; r < f.y && nl < 2; r++) {
         const uint32_t ref = __ldg(p.refs + f.x + r);
         if ((ref >> 30) == REF_LEAF) {
-            cp_async16(st + nl * 32 + lane, p.leaf_planes + ((size_t)(ref & REF_IDX_MASK) * T + tile) * 32 + lane);
+            cp_async16(st + nl * 32 + lane, p.leaf_planes + leaf_index(p, ref & REF_IDX_MASK, tile) * 32 + lane);
             nl++;
         }
     }
@@ -314,10 +321,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 const uint32_t ref = __ldg(p.refs + f.x + (type == FT_LEAF_INT ? 1 : 0));
                 const uint32_t idx = ref & REF_IDX_MASK;
                 if (ref & REF_EXT) {
-                    if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane, tr)) return;
+                    if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return;
                 }
                 uint32_t X[16];
-                load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, X);
+                load_planes16(p.sets + set_index(p, idx, tile) * 128, lane, X);
                 if (type == FT_LEAF_INT) {
                     const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w};
                     fitch_leaf_set(c0, X, acc);
@@ -338,7 +345,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         uint4 c;
                         if (nl == 0) c = l0;
                         else if (nl == 1) c = l1;
-                        else c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+                        else c = ld_stream(p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
                         nl++;
                         uint32_t cc[4] = {c.x, c.y, c.z, c.w};
                         fold.add_leaf(cc, leaf_present_mask(p, idx));
@@ -346,10 +353,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         fold.add_set(acc);
                     } else {
                         if (ref & REF_EXT) {
-                            if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane, tr)) return;
+                            if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return;
                         }
                         uint32_t S[16];
-                        load_planes16(p.sets + ((size_t)idx * T + tile) * 128, lane, S);
+                        load_planes16(p.sets + set_index(p, idx, tile) * 128, lane, S);
                         fold.add_set(S);
                     }
                 }
@@ -365,8 +372,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
 #pragma unroll
                 for (int k = 0; k < 16; k++) acc[k] = (rv & d[k]) | (~rv & acc[k]);
             }
-            store_planes16(p.sets + ((size_t)op * T + tile) * 128, lane, acc);
-            if (f.z & OPF_SIGNAL) signal_flag(p.done + (size_t)op * T + tile, p.epoch, lane);
+            store_planes16(p.sets + set_index(p, op, tile) * 128, lane, acc);
+            if (f.z & OPF_SIGNAL) signal_flag(p.done + set_index(p, op, tile), p.epoch, lane);
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -378,14 +385,14 @@ template <int J>
 __device__ __forceinline__ void bwd_issue(const RunParams& p, uint4* ring, int op, int op_last, int tile, int lane) {
     const size_t T = p.T;
     uint4* st = ring + ((op_last - op) % BWD_DEPTH) * ((J + 2) * 32);
-    const uint4* srow = p.sets + ((size_t)op * T + tile) * (J * 32);
+    const uint4* srow = p.sets + set_index(p, op, tile) * (J * 32);
 #pragma unroll
     for (int j = 0; j < J; j++) cp_async16(st + j * 32 + lane, srow + j * 32 + lane);
     const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
     const int nl = __ldg(reinterpret_cast<const int*>(p.bwd_ops + op) + 4);
     for (int l = 0; l < nl && l < 2; l++) {
         const int row = __ldg(&p.bwd_leaves[b0.w + l].row);
-        cp_async16(st + (J + l) * 32 + lane, p.leaf_planes + ((size_t)row * T + tile) * 32 + lane);
+        cp_async16(st + (J + l) * 32 + lane, p.leaf_planes + leaf_index(p, row, tile) * 32 + lane);
     }
     cp_async_commit();
 }
@@ -405,9 +412,9 @@ __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h,
     }
     const size_t T = p.T;
     if (h.b1.y & OPF_PARENT_EXT) {
-        if (!wait_flag(p.fdone + (size_t)h.b0.y * T + tile, p.epoch, p.error, lane, tr)) return false;
+        if (!wait_flag(p.fdone + fslot_index(p, h.b0.y, tile), p.epoch, p.error, lane, tr)) return false;
     }
-    const uint32_t* fs = p.fstore + ((size_t)h.b0.y * T + tile) * FSLOT_WORDS;
+    const uint32_t* fs = p.fstore + fslot_index(p, h.b0.y, tile) * FSLOT_WORDS;
     uint4 a = ld_l2(reinterpret_cast<const uint4*>(fs) + lane);
     pvis = __ldcg(fs + 128 + lane);
     P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
@@ -422,17 +429,17 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, StageCursor& s
     const size_t T = p.T;
     emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
     if (h.b0.z >= 0) {
-        uint32_t* fs = p.fstore + ((size_t)h.b0.z * T + tile) * FSLOT_WORDS;
+        uint32_t* fs = p.fstore + fslot_index(p, h.b0.z, tile) * FSLOT_WORDS;
         reinterpret_cast<uint4*>(fs)[lane] = make_uint4(F[0], F[1], F[2], F[3]);
         fs[128 + lane] = vis;
-        if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + (size_t)h.b0.z * T + tile, p.epoch, lane);
+        if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + fslot_index(p, h.b0.z, tile), p.epoch, lane);
     }
     if (p.states) store_state(p, h.b0.x, tile, lane, F, vis);
     for (int l = 0; l < h.b1.x; l++) {
         const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + h.b0.w + l));  // row, node
         uint4 c;
         if (l < 2) c = leaf_stage[l * 32 + lane];
-        else c = ld_stream(p.leaf_planes + ((size_t)lf.x * T + tile) * 32 + lane);
+        else c = ld_stream(p.leaf_planes + leaf_index(p, lf.x, tile) * 32 + lane);
         uint32_t cc[4] = {c.x, c.y, c.z, c.w};
         uint32_t present = leaf_present_mask(p, lf.x);
         if (sankoff_block && !present) {  // omitted block leaf = "absent" state (fitchSankoff.cpp:711-714)
@@ -523,7 +530,7 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int
             uint4 c;
             if (nl == 0) c = l0;
             else if (nl == 1) c = l1;
-            else c = ld_stream(p.leaf_planes + ((size_t)idx * T + tile) * 32 + lane);
+            else c = ld_stream(p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
             nl++;
             uint32_t present = leaf_present_mask(p, idx);
             uint32_t cc[4] = {c.x, c.y, c.z, c.w};
@@ -536,9 +543,9 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
             if (ref & REF_EXT) {
-                if (!wait_flag(p.done + (size_t)idx * T + tile, p.epoch, p.error, lane, tr)) return false;
+                if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return false;
             }
-            const uint4* base = p.sets + ((size_t)idx * T + tile) * 256;
+            const uint4* base = p.sets + set_index(p, idx, tile) * 256;
             uint32_t G[16];
             load_planes16(base, lane, G);
             uint32_t h0 = ld_l2(base + 128 + lane).x;
@@ -578,10 +585,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
             else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, f, l0, l1, tile, lane, accG, accH, tr);
             else ok = sankoff_forward_op<20>(p, f, l0, l1, tile, lane, accG, accH, tr);
             if (!ok) return;
-            uint4* base = p.sets + ((size_t)op * T + tile) * 256;
+            uint4* base = p.sets + set_index(p, op, tile) * 256;
             store_planes16(base, lane, accG);
             store_planes16(base + 128, lane, accH);
-            if (f.z & OPF_SIGNAL) signal_flag(p.done + (size_t)op * T + tile, p.epoch, lane);
+            if (f.z & OPF_SIGNAL) signal_flag(p.done + set_index(p, op, tile), p.epoch, lane);
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -756,10 +763,11 @@ __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* sta
 
 // ------------------------------------------------------------------ ingest
 // nibble-packed rows -> code planes. One thread per (row, 32-column group).
-__global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, int n_rows, long long n_cols, int T, uint4* planes) {
+__global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, int row_begin, int n_rows_slab, int n_rows_total,
+                                   long long n_cols, int T, const int* row_slot, uint4* planes) {
     const long long groups = (long long)T * 32;  // 32-column groups per row, padded to whole tiles
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= groups * n_rows) return;
+    if (idx >= groups * n_rows_slab) return;
     const long long row = idx / groups, g = idx % groups;
     uint32_t pl[4] = {0, 0, 0, 0};
     const uint8_t* src = codes + (size_t)row * row_stride;
@@ -783,7 +791,10 @@ __global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, i
             pl[b] |= y << (8 * w);
         }
     }
-    planes[idx] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    // tile-major, rows in the order the forward program consumes them
+    const int slot = row_slot[row_begin + row];
+    const long long tile = g >> 5, lane = g & 31;
+    planes[((size_t)tile * n_rows_total + slot) * 32 + lane] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
 // per-column parameters -> planes; one warp per 32-column group (ballot builds the planes)

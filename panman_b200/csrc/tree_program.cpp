@@ -226,6 +226,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     P.bwd_ops.resize(n_internal);
     P.refs.reserve(n_nodes);
     P.bwd_leaves.reserve(n_rows);
+    P.row_slot.assign(n_rows, -1);
     // which ops must park their assigned state for a child that does not follow them immediately (in reverse)
     std::vector<int32_t> fslot(n_internal, -1);
     std::vector<char> ext_child(n_internal, 0);  // some child of this op lives in another chunk
@@ -255,8 +256,10 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         for (int32_t e = child_off[v]; e < child_off[v + 1]; e++) {
             int32_t c = child_idx[e];
             if (isz[c] == 0) {
-                P.refs.push_back((REF_LEAF << 30) | uint32_t(leaf_row[c]));
-                P.bwd_leaves.push_back(BwdLeaf{leaf_row[c], c});
+                const int32_t slot = int32_t(P.bwd_leaves.size());  // consumption order of the forward program
+                P.row_slot[leaf_row[c]] = slot;
+                P.refs.push_back((REF_LEAF << 30) | uint32_t(slot));
+                P.bwd_leaves.push_back(BwdLeaf{slot, c});
             }
         }
         for (int32_t e = ichild_off[v]; e < ichild_off[v + 1]; e++) {

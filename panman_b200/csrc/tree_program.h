@@ -57,7 +57,7 @@ struct BwdOp {  // 32 bytes
 };
 
 struct BwdLeaf {
-    int32_t row;
+    int32_t row;  // leaf SLOT (see TreeProgram::row_slot)
     int32_t node;
 };
 
@@ -82,6 +82,8 @@ struct TreeProgram {
     std::vector<int32_t> level_order;         // chunk indices, level-major (for schedule = one launch per level)
     std::vector<int32_t> level_chunk_begin;   // n_levels + 1, into level_order
     std::vector<int32_t> node_op;             // node id -> op index, -1 for leaves
+    std::vector<int32_t> row_slot;            // caller's leaf row -> slot in the packed leaf matrix: slots number the
+                                              // leaves in the order the forward program reads them
     int n_levels() const { return int(level_chunk_begin.size()) - 1; }
 };
 

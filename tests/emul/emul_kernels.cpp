@@ -89,15 +89,15 @@ void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16
     for (int r = 0; r < f.n_refs; r++) {
         uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
         if (kind == REF_LEAF) {
-            U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
+            U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
             uint32_t cc[4] = {c.x, c.y, c.z, c.w}, pr = present_mask(E, idx);
             if ((E.flags & 1) && !pr) { cc[0] = cc[1] = cc[2] = cc[3] = 0; pr = 0xFFFFFFFFu; }
             fold.add_leaf(cc, pr);
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
-            if ((ref & REF_EXT) && E.done[(size_t)idx * T + tile] != 1) E.order_violation = true;
-            const U4* base = E.sets.data() + ((size_t)idx * T + tile) * 256;
+            if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+            const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256;
             uint32_t G[16];
             load16(base, lane, G);
             uint32_t h0 = base[128 + lane].x;
@@ -120,13 +120,13 @@ void forward_item(Emu& E, int chunk, int tile) {
                 const int type = E.have_present ? FT_GENERIC : ((f.flags >> OPF_TYPE_SHIFT) & 15);
                 auto leafc = [&](int r, uint32_t cc[4]) {
                     uint32_t idx = E.P.refs[f.ref_begin + r] & REF_IDX_MASK;
-                    U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
+                    U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
                     cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
                 };
                 auto intset = [&](int r, uint32_t X[16]) {
                     uint32_t ref = E.P.refs[f.ref_begin + r], idx = ref & REF_IDX_MASK;
-                    if ((ref & REF_EXT) && E.done[(size_t)idx * T + tile] != 1) E.order_violation = true;
-                    load16(E.sets.data() + ((size_t)idx * T + tile) * 128, lane, X);
+                    if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                    load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 128, lane, X);
                 };
                 if (type == FT_LEAF_LEAF) {
                     uint32_t c0[4], c1[4];
@@ -152,15 +152,15 @@ void forward_item(Emu& E, int chunk, int tile) {
                 for (int r = 0; r < f.n_refs; r++) {
                     uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
                     if (kind == REF_LEAF) {
-                        U4 c = E.leaf_planes[((size_t)idx * T + tile) * 32 + lane];
+                        U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
                         uint32_t cc[4] = {c.x, c.y, c.z, c.w};
                         fold.add_leaf(cc, present_mask(E, idx));
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc[lane]);
                     } else {
-                        if ((ref & REF_EXT) && E.done[(size_t)idx * T + tile] != 1) E.order_violation = true;
+                        if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
                         uint32_t S[16];
-                        load16(E.sets.data() + ((size_t)idx * T + tile) * 128, lane, S);
+                        load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 128, lane, S);
                         fold.add_set(S);
                     }
                 }
@@ -173,7 +173,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                     decode16(r4, d);
                     for (int k = 0; k < 16; k++) acc[lane][k] = (rv & d[k]) | (~rv & acc[lane][k]);
                 }
-                store16(E.sets.data() + ((size_t)op * T + tile) * 128, lane, acc[lane]);
+                store16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, acc[lane]);
             } else {
                 switch (f.max_arity_bits) {
                 case 2: sankoff_fwd_op<2>(E, f, tile, lane, acc[lane], accH[lane]); break;
@@ -181,12 +181,12 @@ void forward_item(Emu& E, int chunk, int tile) {
                 case 8: sankoff_fwd_op<8>(E, f, tile, lane, acc[lane], accH[lane]); break;
                 default: sankoff_fwd_op<20>(E, f, tile, lane, acc[lane], accH[lane]); break;
                 }
-                U4* base = E.sets.data() + ((size_t)op * T + tile) * 256;
+                U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 256;
                 store16(base, lane, acc[lane]);
                 store16(base + 128, lane, accH[lane]);
             }
         }
-        if (f.flags & OPF_SIGNAL) E.done[(size_t)op * T + tile] = 1;
+        if (f.flags & OPF_SIGNAL) E.done[(size_t)tile * E.P.n_internal + op] = 1;
     }
 }
 
@@ -201,7 +201,7 @@ void backward_item(Emu& E, int chunk, int tile) {
         uint32_t Fw[32][4], visw[32];
         for (int lane = 0; lane < 32; lane++) {
             uint32_t G[16], H[16];
-            const U4* base = E.sets.data() + ((size_t)op * T + tile) * J;
+            const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * J;
             load16(base, lane, G);
             if (E.algo == 1) load16(base + 128, lane, H);
             uint32_t P[4], F[4], vis;
@@ -231,8 +231,8 @@ void backward_item(Emu& E, int chunk, int tile) {
                     for (int k = 0; k < 4; k++) P[k] = accF[lane][k];
                     pvis = accVis[lane];
                 } else {
-                    if ((b.flags & OPF_PARENT_EXT) && E.fdone[(size_t)b.parent_ref * T + tile] != 1) E.order_violation = true;
-                    const uint32_t* fs = E.fstore.data() + ((size_t)b.parent_ref * T + tile) * 160;
+                    if ((b.flags & OPF_PARENT_EXT) && E.fdone[(size_t)tile * std::max(1, E.P.n_fslots) + b.parent_ref] != 1) E.order_violation = true;
+                    const uint32_t* fs = E.fstore.data() + ((size_t)tile * std::max(1, E.P.n_fslots) + b.parent_ref) * 160;
                     U4 a = reinterpret_cast<const U4*>(fs)[lane];
                     pvis = fs[128 + lane];
                     P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
@@ -244,18 +244,18 @@ void backward_item(Emu& E, int chunk, int tile) {
             for (int k = 0; k < 4; k++) { wm.P[lane][k] = P[k]; wm.F[lane][k] = F[k]; Fw[lane][k] = F[k]; }
             visw[lane] = vis;
             if (b.fslot_out >= 0) {
-                uint32_t* fs = E.fstore.data() + ((size_t)b.fslot_out * T + tile) * 160;
+                uint32_t* fs = E.fstore.data() + ((size_t)tile * std::max(1, E.P.n_fslots) + b.fslot_out) * 160;
                 reinterpret_cast<U4*>(fs)[lane] = U4{F[0], F[1], F[2], F[3]};
                 fs[128 + lane] = vis;
             }
             store_state(E, b.node, tile, lane, F, vis);
         }
         emit(E, b.node, tile, wm);
-        if (b.fslot_out >= 0 && (b.flags & OPF_SIGNAL_F)) E.fdone[(size_t)b.fslot_out * T + tile] = 1;
+        if (b.fslot_out >= 0 && (b.flags & OPF_SIGNAL_F)) E.fdone[(size_t)tile * std::max(1, E.P.n_fslots) + b.fslot_out] = 1;
         for (int l = 0; l < b.n_leaves; l++) {
             const BwdLeaf lf = E.P.bwd_leaves[b.leaf_begin + l];
             for (int lane = 0; lane < 32; lane++) {
-                U4 c = E.leaf_planes[((size_t)lf.row * T + tile) * 32 + lane];
+                U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + lf.row) * 32 + lane];
                 uint32_t cc[4] = {c.x, c.y, c.z, c.w}, pr = present_mask(E, lf.row);
                 if (E.algo == 1 && (E.flags & 1) && !pr) { cc[0] = cc[1] = cc[2] = cc[3] = 0; pr = 0xFFFFFFFFu; }
                 uint32_t lvis = visw[lane] & pr;
@@ -305,7 +305,7 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
     for (int r = 0; r < P.n_rows; r++)
         for (long long c = 0; c < n_cols; c++) {
             uint32_t code = leaf_codes[(size_t)r * n_cols + c] & 15u;
-            U4& u = E.leaf_planes[(size_t)r * T * 32 + (c >> 5)];
+            U4& u = E.leaf_planes[((size_t)(c / TILE_COLS) * P.n_rows + P.row_slot[r]) * 32 + ((c % TILE_COLS) >> 5)];
             uint32_t bit = 1u << (c & 31);
             if (code & 1) u.x |= bit;
             if (code & 2) u.y |= bit;
@@ -313,7 +313,10 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
             if (code & 8) u.w |= bit;
         }
     E.have_present = leaf_present != nullptr;
-    if (leaf_present) E.present.assign(leaf_present, leaf_present + P.n_rows);
+    if (leaf_present) {  // indexed by leaf slot, like the kernels
+        E.present.assign(P.n_rows, 0);
+        for (int r = 0; r < P.n_rows; r++) E.present[P.row_slot[r]] = leaf_present[r];
+    }
     // pack_colparams_kernel
     E.colparams.assign(T * 128, U4{0, 0, 0, 0});
     for (long long c = 0; c < n_cols; c++) {
