@@ -228,17 +228,18 @@ int launch_schedule(pmb_ctx* c, cudaStream_t stream, int ticket_slot, K kernel, 
 
 int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParams& rp, int algo, bool forward, int* n_launches) {
     const TreeProgram& P = c->prog;
-    const size_t fwd_smem = size_t(WARPS_PER_BLOCK) * FWD_DEPTH * FWD_STAGE_U4 * sizeof(uint4);
-    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * BWD_DEPTH * (4 + 2) * 32 * sizeof(uint4);
-    const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * BWD_DEPTH * (8 + 2) * 32 * sizeof(uint4);
+    const size_t fwd_smem = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 4) * 32 + FWD_META_U4) * sizeof(uint4);
+    const size_t fwd_smem_s = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 5) * 32 + FWD_META_U4) * sizeof(uint4);
+    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (4 + 2) * 32 + BWD_META_U4) * sizeof(uint4);
+    const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (8 + 2) * 32 + BWD_META_U4) * sizeof(uint4);
     if (algo == PMB_ALGO_FITCH)
         return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel, fwd_smem, rp, true, n_launches)
                        : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel, bwd_smem_f, rp, false, n_launches);
     if (!forward) return launch_schedule(c, stream, ticket_slot, sankoff_backward_kernel, bwd_smem_s, rp, false, n_launches);
-    if (P.max_arity <= 3) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<2>, fwd_smem, rp, true, n_launches);
-    if (P.max_arity <= 15) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<4>, fwd_smem, rp, true, n_launches);
-    if (P.max_arity <= 255) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<8>, fwd_smem, rp, true, n_launches);
-    return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<20>, fwd_smem, rp, true, n_launches);
+    if (P.max_arity <= 3) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<2>, fwd_smem_s, rp, true, n_launches);
+    if (P.max_arity <= 15) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<4>, fwd_smem_s, rp, true, n_launches);
+    if (P.max_arity <= 255) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<8>, fwd_smem_s, rp, true, n_launches);
+    return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<20>, fwd_smem_s, rp, true, n_launches);
 }
 
 // Column tiles are split into groups that run forward -> backward on their own streams: a group's low-parallelism
@@ -476,6 +477,7 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     rp.n_ops = P.n_internal;
     rp.n_rows = P.n_rows;
     rp.n_fslots = std::max(1, P.n_fslots);
+    rp.n_refs_total = int(P.refs.size());
     rp.flags = ((flags & PMB_FLAG_BLOCK_MODE) ? RUN_BLOCK_MODE : 0) | (want_states ? RUN_WANT_STATES : 0);
 
     int n_launches = 0;

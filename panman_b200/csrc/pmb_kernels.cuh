@@ -50,6 +50,7 @@ struct RunParams {
     unsigned int epoch;
     int T;
     int n_ops, n_rows, n_fslots;  // matrices are TILE-major: [tile][op], [tile][leaf slot], [tile][fslot]
+    int n_refs_total;
     int flags;
     int stage_block;              // staging records a warp reserves per atomic
     int tile_begin, tile_count;   // this launch covers tiles [tile_begin, tile_begin + tile_count) (column group)
@@ -266,32 +267,125 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n gro
     }
 }
 
-constexpr int FWD_DEPTH = 6;       // forward: stage = 2 leaf rows            (1 KB per warp and stage)
-constexpr int FWD_STAGE_U4 = 2 * 32;
-constexpr int BWD_DEPTH = 3;       // backward: stage = set row + 2 leaf rows (3 KB Fitch / 5 KB Sankoff)
+constexpr int FWD_DEPTH = 4;       // forward: stage = 2 leaf rows + one child set row (3 KB Fitch / 3.5 KB Sankoff)
+constexpr int BWD_DEPTH = 3;       // backward: stage = set row + 2 leaf rows           (3 KB Fitch / 5 KB Sankoff)
 
-// forward: queue the (first two) leaf rows of `op` into its stage; always commits one group
-__device__ __forceinline__ void fwd_issue(const RunParams& p, uint4* ring, int op, int op_begin, int tile, int lane) {
-    const size_t T = p.T;
-    const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
-    uint4* st = ring + ((op - op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
-    int nl = 0;
-    for (int r = 0; r < f.y && nl < 2; r++) {
-        const uint32_t ref = __ldg(p.refs + f.x + r);
-        if ((ref >> 30) == REF_LEAF) {
-            cp_async16(st + nl * 32 + lane, p.leaf_planes + leaf_index(p, ref & REF_IDX_MASK, tile) * 32 + lane);
+// ------------------------------------------------------------------ program metadata windows
+// Op headers and child references are tiny but sat on the critical path of every op as dependent L2 loads
+// (profiles/r01_v3: the top stall in both passes). Each warp therefore keeps a window of its chunk's metadata in
+// shared memory, refilled with a few coalesced loads every META_OPS - depth ops.
+constexpr int META_OPS = 32, META_REFS = 96, META_LEAVES = 64;
+constexpr int FWD_META_U4 = META_OPS + META_REFS / 4;            // FwdOp is 16 B
+constexpr int BWD_META_U4 = 2 * META_OPS + META_LEAVES / 2;      // BwdOp is 32 B, BwdLeaf 8 B
+
+struct FwdMeta {
+    int4* ops;
+    uint32_t* refs;
+    int wb;       // first op of the window
+    unsigned rb;  // first ref of the window
+};
+__device__ __forceinline__ void fwd_meta_load(const RunParams& p, FwdMeta& m, int wb, int op_end, int lane) {
+    __syncwarp();  // all lanes are done with the previous window
+    m.wb = wb;
+    int4 h = make_int4(0, 0, 0, 0);
+    if (wb + lane < op_end) h = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + wb + lane));
+    m.ops[lane] = h;
+    m.rb = (unsigned)__shfl_sync(FULL, h.x, 0);
+#pragma unroll
+    for (int k = 0; k < META_REFS / 32; k++) {
+        const unsigned i = m.rb + lane + 32 * k;
+        m.refs[lane + 32 * k] = i < (unsigned)p.n_refs_total ? __ldg(p.refs + i) : 0u;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int4 fwd_head(const FwdMeta& m, int op) { return m.ops[op - m.wb]; }
+__device__ __forceinline__ uint32_t fwd_ref(const RunParams& p, const FwdMeta& m, unsigned i) {
+    const unsigned d = i - m.rb;
+    return d < (unsigned)META_REFS ? m.refs[d] : __ldg(p.refs + i);
+}
+
+struct BwdMeta {
+    int4* ops;
+    int2* leaves;
+    int lo;       // lowest op of the window (ops run downwards)
+    unsigned lb;  // first leaf entry of the window
+};
+__device__ __forceinline__ void bwd_meta_load(const RunParams& p, BwdMeta& m, int top, int op_begin, int lane) {
+    __syncwarp();
+    m.lo = max(op_begin, top - (META_OPS - 1));
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = h0;
+    if (m.lo + lane <= top) {
+        h0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + m.lo + lane));
+        h1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + m.lo + lane) + 1);
+    }
+    m.ops[2 * lane] = h0;
+    m.ops[2 * lane + 1] = h1;
+    m.lb = (unsigned)__shfl_sync(FULL, h0.w, 0);
+#pragma unroll
+    for (int k = 0; k < META_LEAVES / 32; k++) {
+        const unsigned i = m.lb + lane + 32 * k;
+        m.leaves[lane + 32 * k] = i < (unsigned)p.n_rows ? __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + i)) : make_int2(0, 0);
+    }
+    __syncwarp();
+}
+struct BwdHead {
+    int4 b0;  // node, parent_ref, fslot_out, leaf_begin
+    int4 b1;  // n_leaves, flags, parent op
+};
+__device__ __forceinline__ BwdHead bwd_head(const BwdMeta& m, int op) {
+    BwdHead h;
+    h.b0 = m.ops[2 * (op - m.lo)];
+    h.b1 = m.ops[2 * (op - m.lo) + 1];
+    return h;
+}
+__device__ __forceinline__ int2 bwd_leaf(const RunParams& p, const BwdMeta& m, unsigned i) {
+    const unsigned d = i - m.lb;
+    return d < (unsigned)META_LEAVES ? m.leaves[d] : __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + i));
+}
+
+// forward: queue the inputs of `op` into its stage and commit one group: the first two leaf rows, and the first
+// set row that is not the register accumulator when it is already final -- written by another chunk (after its
+// done flag) or by this warp at least FWD_DEPTH ops ago. JS = vectors of a set row the consumer needs.
+template <int JS>
+__device__ __forceinline__ bool fwd_set_prefetched(uint32_t ref, int op) {
+    return (ref & REF_EXT) || int(ref & REF_IDX_MASK) + FWD_DEPTH <= op;
+}
+template <int JS, int JROW>
+__device__ __forceinline__ bool fwd_issue(const RunParams& p, const FwdMeta& m, uint4* ring, int op, int op_begin, int tile,
+                                          int lane, TraceItem& tr) {
+    const int4 f = fwd_head(m, op);
+    uint4* st = ring + ((op - op_begin) % FWD_DEPTH) * ((2 + JS) * 32);
+    int nl = 0, ni = 0;
+    bool ok = true;
+    for (int r = 0; r < f.y && (nl < 2 || ni < 1); r++) {
+        const uint32_t ref = fwd_ref(p, m, f.x + r);
+        const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
+        if (kind == REF_LEAF) {
+            if (nl < 2) cp_async16(st + nl * 32 + lane, p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
             nl++;
+        } else if (kind == REF_INT) {
+            if (ni == 0 && fwd_set_prefetched<JS>(ref, op)) {
+                if (ref & REF_EXT) ok = wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr);
+                const uint4* row = p.sets + set_index(p, idx, tile) * (JROW * 32);
+#pragma unroll
+                for (int j = 0; j < JS; j++) cp_async16(st + (2 + j) * 32 + lane, row + j * 32 + lane);
+            }
+            ni++;
         }
     }
     cp_async_commit();
+    return ok;
 }
 
 // ------------------------------------------------------------------ Fitch forward
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
+    constexpr int JS = 4, STAGE = (2 + JS) * 32, PER_WARP = FWD_DEPTH * STAGE + FWD_META_U4;
     const int lane = threadIdx.x & 31;
-    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FWD_DEPTH * FWD_STAGE_U4;
-    const size_t T = p.T;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
+    FwdMeta m;
+    m.ops = reinterpret_cast<int4*>(ring + FWD_DEPTH * STAGE);
+    m.refs = reinterpret_cast<uint32_t*>(m.ops + META_OPS);
     ItemIter it;
     TraceItem tr;
     int chunk, tile;
@@ -300,13 +394,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
         uint32_t acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0;
-        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) fwd_issue(p, ring, ck.op_begin + i, ck.op_begin, tile, lane);
+        fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
+        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
+            if (!fwd_issue<JS, 4>(p, m, ring, ck.op_begin + i, ck.op_begin, tile, lane, tr)) return;
+        }
         for (int op = ck.op_begin; op < ck.op_end; op++) {
-            const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));  // ref_begin, n_refs, flags, bits
+            if (op + FWD_DEPTH >= m.wb + META_OPS && m.wb + META_OPS < ck.op_end) fwd_meta_load(p, m, op, ck.op_end, lane);
+            const int4 f = fwd_head(m, op);  // ref_begin, n_refs, flags, bits
             cp_async_wait_pending(min(FWD_DEPTH - 1, ck.op_end - 1 - op));
-            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
+            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * STAGE;
             const uint4 l0 = st[lane], l1 = st[32 + lane];
-            if (op + FWD_DEPTH < ck.op_end) fwd_issue(p, ring, op + FWD_DEPTH, ck.op_begin, tile, lane);  // refill this stage
             const int type = p.leaf_present ? FT_GENERIC : ((f.z >> OPF_TYPE_SHIFT) & 15);
             if (type == FT_LEAF_LEAF) {
                 const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w}, c1[4] = {l1.x, l1.y, l1.z, l1.w};
@@ -318,13 +415,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 for (int k = 0; k < 16; k++) X[k] = acc[k];
                 fitch_leaf_set(c0, X, acc);
             } else if (type == FT_LEAF_INT || type == FT_INT_ACC) {
-                const uint32_t ref = __ldg(p.refs + f.x + (type == FT_LEAF_INT ? 1 : 0));
-                const uint32_t idx = ref & REF_IDX_MASK;
-                if (ref & REF_EXT) {
-                    if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return;
-                }
+                const uint32_t ref = fwd_ref(p, m, f.x + (type == FT_LEAF_INT ? 1 : 0));
                 uint32_t X[16];
-                load_planes16(p.sets + set_index(p, idx, tile) * 128, lane, X);
+                if (fwd_set_prefetched<JS>(ref, op)) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = st[(2 + j) * 32 + lane];
+                    unpack16(v, X);
+                } else {
+                    load_planes16(p.sets + set_index(p, ref & REF_IDX_MASK, tile) * 128, lane, X);
+                }
                 if (type == FT_LEAF_INT) {
                     const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w};
                     fitch_leaf_set(c0, X, acc);
@@ -337,9 +437,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
             } else {
                 FitchFold fold;
                 fold.reset();
-                int nl = 0;
+                int nl = 0, ni = 0;
                 for (int r = 0; r < f.y; r++) {
-                    const uint32_t ref = __ldg(p.refs + f.x + r);
+                    const uint32_t ref = fwd_ref(p, m, f.x + r);
                     const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
                     if (kind == REF_LEAF) {
                         uint4 c;
@@ -352,11 +452,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc);
                     } else {
-                        if (ref & REF_EXT) {
-                            if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return;
-                        }
                         uint32_t S[16];
-                        load_planes16(p.sets + set_index(p, idx, tile) * 128, lane, S);
+                        if (ni == 0 && fwd_set_prefetched<JS>(ref, op)) {
+                            uint4 v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) v[j] = st[(2 + j) * 32 + lane];
+                            unpack16(v, S);
+                        } else {
+                            if (ref & REF_EXT) {
+                                if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return;
+                            }
+                            load_planes16(p.sets + set_index(p, idx, tile) * 128, lane, S);
+                        }
+                        ni++;
                         fold.add_set(S);
                     }
                 }
@@ -374,6 +482,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
             }
             store_planes16(p.sets + set_index(p, op, tile) * 128, lane, acc);
             if (f.z & OPF_SIGNAL) signal_flag(p.done + set_index(p, op, tile), p.epoch, lane);
+            // the stage of this op is consumed and its result stored: refill the stage for the op FWD_DEPTH ahead
+            if (op + FWD_DEPTH < ck.op_end) {
+                if (!fwd_issue<JS, 4>(p, m, ring, op + FWD_DEPTH, ck.op_begin, tile, lane, tr)) return;
+            }
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -382,25 +494,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
 // ------------------------------------------------------------------ backward: shared pieces
 // stage layout: [J set-row vectors][2 leaf rows], each 32 lanes wide; J = 4 (Fitch) or 8 (Sankoff)
 template <int J>
-__device__ __forceinline__ void bwd_issue(const RunParams& p, uint4* ring, int op, int op_last, int tile, int lane) {
-    const size_t T = p.T;
+__device__ __forceinline__ void bwd_issue(const RunParams& p, const BwdMeta& m, uint4* ring, int op, int op_last, int tile, int lane) {
     uint4* st = ring + ((op_last - op) % BWD_DEPTH) * ((J + 2) * 32);
     const uint4* srow = p.sets + set_index(p, op, tile) * (J * 32);
 #pragma unroll
     for (int j = 0; j < J; j++) cp_async16(st + j * 32 + lane, srow + j * 32 + lane);
-    const int4 b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
-    const int nl = __ldg(reinterpret_cast<const int*>(p.bwd_ops + op) + 4);
-    for (int l = 0; l < nl && l < 2; l++) {
-        const int row = __ldg(&p.bwd_leaves[b0.w + l].row);
+    const BwdHead h = bwd_head(m, op);
+    for (int l = 0; l < h.b1.x && l < 2; l++) {
+        const int row = bwd_leaf(p, m, h.b0.w + l).x;
         cp_async16(st + (J + l) * 32 + lane, p.leaf_planes + leaf_index(p, row, tile) * 32 + lane);
     }
     cp_async_commit();
 }
-
-struct BwdHead {
-    int4 b0;  // node, parent_ref, fslot_out, leaf_begin
-    int4 b1;  // n_leaves, flags
-};
 
 // parent's assigned state from registers (ACC) or from its parked slot (possibly written by another chunk)
 __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h, int tile, int lane, const uint32_t accF[4],
@@ -410,7 +515,6 @@ __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h,
         pvis = accVis;
         return true;
     }
-    const size_t T = p.T;
     if (h.b1.y & OPF_PARENT_EXT) {
         if (!wait_flag(p.fdone + fslot_index(p, h.b0.y, tile), p.epoch, p.error, lane, tr)) return false;
     }
@@ -423,10 +527,9 @@ __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h,
 
 // what follows the assignment of an internal node, shared by Fitch and Sankoff: its own record, the parked
 // state for later children, and its leaf children (a present leaf is always assigned its own code)
-__device__ __forceinline__ void bwd_finish_op(const RunParams& p, StageCursor& sc, const BwdHead& h, const uint4* leaf_stage,
-                                              int tile, int lane, const uint32_t P[4], const uint32_t F[4], uint32_t vis,
-                                              bool sankoff_block) {
-    const size_t T = p.T;
+__device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta& m, StageCursor& sc, const BwdHead& h,
+                                              const uint4* leaf_stage, int tile, int lane, const uint32_t P[4],
+                                              const uint32_t F[4], uint32_t vis, bool sankoff_block) {
     emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
     if (h.b0.z >= 0) {
         uint32_t* fs = p.fstore + fslot_index(p, h.b0.z, tile) * FSLOT_WORDS;
@@ -436,7 +539,7 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, StageCursor& s
     }
     if (p.states) store_state(p, h.b0.x, tile, lane, F, vis);
     for (int l = 0; l < h.b1.x; l++) {
-        const int2 lf = __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + h.b0.w + l));  // row, node
+        const int2 lf = bwd_leaf(p, m, h.b0.w + l);  // slot, node
         uint4 c;
         if (l < 2) c = leaf_stage[l * 32 + lane];
         else c = ld_stream(p.leaf_planes + leaf_index(p, lf.x, tile) * 32 + lane);
@@ -458,9 +561,12 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, StageCursor& s
 // ------------------------------------------------------------------ Fitch backward + mutation detection
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
-    constexpr int J = 4, STAGE = (J + 2) * 32;
+    constexpr int J = 4, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4;
     const int lane = threadIdx.x & 31;
-    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
+    BwdMeta m;
+    m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
+    m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
     ItemIter it;
     TraceItem tr;
     StageCursor sc;
@@ -469,11 +575,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
         const Chunk ck = p.chunks[chunk];
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
-        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, ring, last - i, last, tile, lane);
+        bwd_meta_load(p, m, last, ck.op_begin, lane);
+        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, m, ring, last - i, last, tile, lane);
         for (int op = last; op >= ck.op_begin; op--) {
-            BwdHead h;
-            h.b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
-            h.b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
+            if (op - BWD_DEPTH < m.lo && m.lo > ck.op_begin) bwd_meta_load(p, m, op, ck.op_begin, lane);
+            const BwdHead h = bwd_head(m, op);
             uint32_t P[4], pvis = 0, F[4], vis;
             if (h.b0.y != PARENT_ROOT) {
                 if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis, tr)) return;
@@ -505,9 +611,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             } else {
                 fitch_assign(S, P, pvis, F, vis);
             }
-            bwd_finish_op(p, sc, h, st + J * 32, tile, lane, P, F, vis, false);
+            bwd_finish_op(p, m, sc, h, st + J * 32, tile, lane, P, F, vis, false);
             // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
-            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, ring, op - BWD_DEPTH, last, tile, lane);
+            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, m, ring, op - BWD_DEPTH, last, tile, lane);
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
         }
@@ -516,20 +622,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
 }
 
 // ------------------------------------------------------------------ Sankoff forward
+// first non-accumulator set row either comes prefetched from the stage (G planes + first H vector) or is loaded here
 template <int B>
-__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int4 f, const uint4 l0, const uint4 l1, int tile,
-                                                   int lane, uint32_t accG[16], uint32_t accH[16], TraceItem& tr) {
-    const size_t T = p.T;
+__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const FwdMeta& m, const int4 f, int op, const uint4* st,
+                                                   int tile, int lane, uint32_t accG[16], uint32_t accH[16], TraceItem& tr) {
     SankoffFold<B> fold;
     fold.reset();
-    int nl = 0;
+    int nl = 0, ni = 0;
     for (int r = 0; r < f.y; r++) {
-        const uint32_t ref = __ldg(p.refs + f.x + r);
+        const uint32_t ref = fwd_ref(p, m, f.x + r);
         const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
         if (kind == REF_LEAF) {
             uint4 c;
-            if (nl == 0) c = l0;
-            else if (nl == 1) c = l1;
+            if (nl < 2) c = st[nl * 32 + lane];
             else c = ld_stream(p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
             nl++;
             uint32_t present = leaf_present_mask(p, idx);
@@ -542,13 +647,22 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
-            if (ref & REF_EXT) {
-                if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return false;
+            uint32_t G[16], h0;
+            if (ni == 0 && fwd_set_prefetched<5>(ref, op)) {
+                uint4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = st[(2 + j) * 32 + lane];
+                unpack16(v, G);
+                h0 = st[(2 + 4) * 32 + lane].x;
+            } else {
+                if (ref & REF_EXT) {
+                    if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return false;
+                }
+                const uint4* base = p.sets + set_index(p, idx, tile) * 256;
+                load_planes16(base, lane, G);
+                h0 = ld_l2(base + 128 + lane).x;
             }
-            const uint4* base = p.sets + set_index(p, idx, tile) * 256;
-            uint32_t G[16];
-            load_planes16(base, lane, G);
-            uint32_t h0 = ld_l2(base + 128 + lane).x;
+            ni++;
             fold.add_set(G, h0 & ~G[0]);
         }
     }
@@ -556,14 +670,19 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const int
     return true;
 }
 
+// Sankoff rows are [G: 4 vectors][H: 4 vectors]; the forward pass only needs G and the first H vector (NONE marker)
+// of a child, which are contiguous: JS = 5 of JROW = 8.
 // MAXB = widest child counter any op of this tree needs (2: up to 3 children, 4: 15, 8: 255, 20: more), so
 // that binary trees do not pay registers for polytomy paths.
 template <int MAXB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
+    constexpr int JS = 5, STAGE = (2 + JS) * 32, PER_WARP = FWD_DEPTH * STAGE + FWD_META_U4;
     const int lane = threadIdx.x & 31;
-    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FWD_DEPTH * FWD_STAGE_U4;
-    const size_t T = p.T;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
+    FwdMeta m;
+    m.ops = reinterpret_cast<int4*>(ring + FWD_DEPTH * STAGE);
+    m.refs = reinterpret_cast<uint32_t*>(m.ops + META_OPS);
     ItemIter it;
     TraceItem tr;
     int chunk, tile;
@@ -572,23 +691,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
         uint32_t accG[16], accH[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
-        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) fwd_issue(p, ring, ck.op_begin + i, ck.op_begin, tile, lane);
+        fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
+        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
+            if (!fwd_issue<JS, 8>(p, m, ring, ck.op_begin + i, ck.op_begin, tile, lane, tr)) return;
+        }
         for (int op = ck.op_begin; op < ck.op_end; op++) {
-            const int4 f = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+            if (op + FWD_DEPTH >= m.wb + META_OPS && m.wb + META_OPS < ck.op_end) fwd_meta_load(p, m, op, ck.op_end, lane);
+            const int4 f = fwd_head(m, op);
             cp_async_wait_pending(min(FWD_DEPTH - 1, ck.op_end - 1 - op));
-            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * FWD_STAGE_U4;
-            const uint4 l0 = st[lane], l1 = st[32 + lane];
-            if (op + FWD_DEPTH < ck.op_end) fwd_issue(p, ring, op + FWD_DEPTH, ck.op_begin, tile, lane);
+            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * STAGE;
             bool ok;
-            if (MAXB == 2 || f.w == 2) ok = sankoff_forward_op<2>(p, f, l0, l1, tile, lane, accG, accH, tr);
-            else if (MAXB == 4 || f.w == 4) ok = sankoff_forward_op<4>(p, f, l0, l1, tile, lane, accG, accH, tr);
-            else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, f, l0, l1, tile, lane, accG, accH, tr);
-            else ok = sankoff_forward_op<20>(p, f, l0, l1, tile, lane, accG, accH, tr);
+            if (MAXB == 2 || f.w == 2) ok = sankoff_forward_op<2>(p, m, f, op, st, tile, lane, accG, accH, tr);
+            else if (MAXB == 4 || f.w == 4) ok = sankoff_forward_op<4>(p, m, f, op, st, tile, lane, accG, accH, tr);
+            else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, m, f, op, st, tile, lane, accG, accH, tr);
+            else ok = sankoff_forward_op<20>(p, m, f, op, st, tile, lane, accG, accH, tr);
             if (!ok) return;
             uint4* base = p.sets + set_index(p, op, tile) * 256;
             store_planes16(base, lane, accG);
             store_planes16(base + 128, lane, accH);
             if (f.z & OPF_SIGNAL) signal_flag(p.done + set_index(p, op, tile), p.epoch, lane);
+            if (op + FWD_DEPTH < ck.op_end) {
+                if (!fwd_issue<JS, 8>(p, m, ring, op + FWD_DEPTH, ck.op_begin, tile, lane, tr)) return;
+            }
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -597,9 +721,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
 // ------------------------------------------------------------------ Sankoff backward + mutation detection
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
-    constexpr int J = 8, STAGE = (J + 2) * 32;
+    constexpr int J = 8, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4;
     const int lane = threadIdx.x & 31;
-    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * BWD_DEPTH * STAGE;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
+    BwdMeta m;
+    m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
+    m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
     ItemIter it;
     TraceItem tr;
     StageCursor sc;
@@ -608,11 +735,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
         const Chunk ck = p.chunks[chunk];
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
-        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, ring, last - i, last, tile, lane);
+        bwd_meta_load(p, m, last, ck.op_begin, lane);
+        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, m, ring, last - i, last, tile, lane);
         for (int op = last; op >= ck.op_begin; op--) {
-            BwdHead h;
-            h.b0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op));
-            h.b1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + op) + 1);
+            if (op - BWD_DEPTH < m.lo && m.lo > ck.op_begin) bwd_meta_load(p, m, op, ck.op_begin, lane);
+            const BwdHead h = bwd_head(m, op);
             uint32_t P[4], pvis = 0, F[4], vis;
             if (h.b0.y != PARENT_ROOT) {
                 if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis, tr)) return;
@@ -642,8 +769,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
                 sankoff_assign(G, H, P, pvis, F, vis);
             }
             // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
-            bwd_finish_op(p, sc, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
-            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, ring, op - BWD_DEPTH, last, tile, lane);
+            bwd_finish_op(p, m, sc, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
+            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, m, ring, op - BWD_DEPTH, last, tile, lane);
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
         }

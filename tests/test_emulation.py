@@ -30,7 +30,7 @@ def test_emulation_vs_port_random(emu, port, algo):
     rng = np.random.default_rng(11 + algo)
     for trial in range(40):
         kind = ["binary", "polytomy", "unary", "caterpillar"][trial % 4]
-        tree = random_tree(int(rng.integers(1, 120)), 2000 + trial, kind, max_arity=[3, 6, 20, 300][trial % 4])
+        tree = random_tree(int(rng.integers(1, 120)), 2000 + trial, kind, max_arity=[3, 6, 20, 300][(trial // 4) % 4])
         n_cols = int(rng.choice([1, 5, 32, 100, 1023, 1024, 1025, 2500]))
         block = int(trial % 5 == 4)
         nst = 3 if block else 16

@@ -16,7 +16,7 @@ rng = np.random.default_rng(100 + algo)
 port = PortOracle()
 for trial in range(24):
     kind = ["binary", "polytomy", "unary", "caterpillar"][trial % 4]
-    tree = random_tree(int(rng.integers(1, 400)), 3000 + trial, kind, max_arity=[3, 6, 20, 300][trial % 4])
+    tree = random_tree(int(rng.integers(1, 400)), 3000 + trial, kind, max_arity=[3, 6, 20, 300][(trial // 4) % 4])
     n_cols = int(rng.choice([1, 33, 1000, 1024, 1025, 5000]))
     block = int(trial % 5 == 4)
     nst = 3 if block else 16
