@@ -270,13 +270,23 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n gro
 constexpr int FWD_DEPTH = 4;       // forward: stage = 2 leaf rows + one child set row (3 KB Fitch / 3.5 KB Sankoff)
 constexpr int BWD_DEPTH = 3;       // backward: stage = set row + 2 leaf rows           (3 KB Fitch / 5 KB Sankoff)
 
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// steady state: DEPTH - 1 younger groups may stay in flight; near the end of a chunk simply drain
+template <int DEPTH>
+__device__ __forceinline__ void cp_async_wait_stage(int ops_left_after) {
+    if (ops_left_after >= DEPTH - 1) cp_async_wait<DEPTH - 1>();
+    else cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------ program metadata windows
-// Op headers and child references are tiny but sat on the critical path of every op as dependent L2 loads
+// Op records and child references are tiny but sat on the critical path of every op as dependent L2 loads
 // (profiles/r01_v3: the top stall in both passes). Each warp therefore keeps a window of its chunk's metadata in
-// shared memory, refilled with a few coalesced loads every META_OPS - depth ops.
+// shared memory, refilled with a few coalesced loads every META_OPS - depth ops. Records are 32 bytes and carry
+// their first two references inline, so the bifurcating common case is straight-line code.
 constexpr int META_OPS = 32, META_REFS = 96, META_LEAVES = 64;
-constexpr int FWD_META_U4 = META_OPS + META_REFS / 4;            // FwdOp is 16 B
-constexpr int BWD_META_U4 = 2 * META_OPS + META_LEAVES / 2;      // BwdOp is 32 B, BwdLeaf 8 B
+constexpr int FWD_META_U4 = 2 * META_OPS + META_REFS / 4;
+constexpr int BWD_META_U4 = 2 * META_OPS + META_LEAVES / 2;
 
 struct FwdMeta {
     int4* ops;
@@ -287,10 +297,14 @@ struct FwdMeta {
 __device__ __forceinline__ void fwd_meta_load(const RunParams& p, FwdMeta& m, int wb, int op_end, int lane) {
     __syncwarp();  // all lanes are done with the previous window
     m.wb = wb;
-    int4 h = make_int4(0, 0, 0, 0);
-    if (wb + lane < op_end) h = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + wb + lane));
-    m.ops[lane] = h;
-    m.rb = (unsigned)__shfl_sync(FULL, h.x, 0);
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = h0;
+    if (wb + lane < op_end) {
+        h0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + wb + lane));
+        h1 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + wb + lane) + 1);
+    }
+    m.ops[2 * lane] = h0;
+    m.ops[2 * lane + 1] = h1;
+    m.rb = (unsigned)__shfl_sync(FULL, h0.x, 0);
 #pragma unroll
     for (int k = 0; k < META_REFS / 32; k++) {
         const unsigned i = m.rb + lane + 32 * k;
@@ -298,7 +312,6 @@ __device__ __forceinline__ void fwd_meta_load(const RunParams& p, FwdMeta& m, in
     }
     __syncwarp();
 }
-__device__ __forceinline__ int4 fwd_head(const FwdMeta& m, int op) { return m.ops[op - m.wb]; }
 __device__ __forceinline__ uint32_t fwd_ref(const RunParams& p, const FwdMeta& m, unsigned i) {
     const unsigned d = i - m.rb;
     return d < (unsigned)META_REFS ? m.refs[d] : __ldg(p.refs + i);
@@ -330,51 +343,99 @@ __device__ __forceinline__ void bwd_meta_load(const RunParams& p, BwdMeta& m, in
 }
 struct BwdHead {
     int4 b0;  // node, parent_ref, fslot_out, leaf_begin
-    int4 b1;  // n_leaves, flags, parent op
+    int4 b1;  // n_leaves, flags, leaf0 slot, leaf1 slot
 };
-__device__ __forceinline__ BwdHead bwd_head(const BwdMeta& m, int op) {
-    BwdHead h;
-    h.b0 = m.ops[2 * (op - m.lo)];
-    h.b1 = m.ops[2 * (op - m.lo) + 1];
-    return h;
-}
 __device__ __forceinline__ int2 bwd_leaf(const RunParams& p, const BwdMeta& m, unsigned i) {
     const unsigned d = i - m.lb;
     return d < (unsigned)META_LEAVES ? m.leaves[d] : __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + i));
 }
 
-// forward: queue the inputs of `op` into its stage and commit one group: the first two leaf rows, and the first
-// set row that is not the register accumulator when it is already final -- written by another chunk (after its
-// done flag) or by this warp at least FWD_DEPTH ops ago. JS = vectors of a set row the consumer needs.
-template <int JS>
+// per-item base pointers (tile-major layouts), already offset by the lane
+struct TileCtx {
+    const uint4* leaf;  // + slot * 32
+    uint4* sets;        // + op * JROW * 32
+    unsigned* done;     // + op
+};
+template <int JROW>
+__device__ __forceinline__ TileCtx tile_ctx(const RunParams& p, int tile, int lane) {
+    TileCtx t;
+    t.leaf = p.leaf_planes + (size_t)tile * p.n_rows * 32 + lane;
+    t.sets = p.sets + (size_t)tile * p.n_ops * (JROW * 32) + lane;
+    t.done = p.done + (size_t)tile * p.n_ops;
+    return t;
+}
+
+// A set row other than the register accumulator can be prefetched when it is already final at issue time:
+// written by another chunk (after its done flag) or by this warp at least FWD_DEPTH ops before the consumer.
 __device__ __forceinline__ bool fwd_set_prefetched(uint32_t ref, int op) {
     return (ref & REF_EXT) || int(ref & REF_IDX_MASK) + FWD_DEPTH <= op;
 }
 template <int JS, int JROW>
-__device__ __forceinline__ bool fwd_issue(const RunParams& p, const FwdMeta& m, uint4* ring, int op, int op_begin, int tile,
-                                          int lane, TraceItem& tr) {
-    const int4 f = fwd_head(m, op);
-    uint4* st = ring + ((op - op_begin) % FWD_DEPTH) * ((2 + JS) * 32);
-    int nl = 0, ni = 0;
+__device__ __forceinline__ bool fwd_issue_set(const RunParams& p, const TileCtx& tc, uint4* st, uint32_t ref, int op, int lane,
+                                              TraceItem& tr) {
+    if (!fwd_set_prefetched(ref, op)) return true;
+    const uint32_t idx = ref & REF_IDX_MASK;
     bool ok = true;
-    for (int r = 0; r < f.y && (nl < 2 || ni < 1); r++) {
-        const uint32_t ref = fwd_ref(p, m, f.x + r);
-        const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
-        if (kind == REF_LEAF) {
-            if (nl < 2) cp_async16(st + nl * 32 + lane, p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
-            nl++;
-        } else if (kind == REF_INT) {
-            if (ni == 0 && fwd_set_prefetched<JS>(ref, op)) {
-                if (ref & REF_EXT) ok = wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr);
-                const uint4* row = p.sets + set_index(p, idx, tile) * (JROW * 32);
+    if (ref & REF_EXT) ok = wait_flag(tc.done + idx, p.epoch, p.error, lane, tr);
+    const uint4* row = tc.sets + (size_t)idx * (JROW * 32);
 #pragma unroll
-                for (int j = 0; j < JS; j++) cp_async16(st + (2 + j) * 32 + lane, row + j * 32 + lane);
+    for (int j = 0; j < JS; j++) cp_async16(st + (2 + j) * 32, row + j * 32);
+    return ok;
+}
+// forward: queue the inputs of `op` into stage `st` (lane-offset pointer) and commit one group: the first two leaf
+// rows and, when prefetchable, the first set row. JS = vectors of a set row the consumer needs, JROW = row length.
+template <int JS, int JROW>
+__device__ __forceinline__ bool fwd_issue(const RunParams& p, const FwdMeta& m, const TileCtx& tc, uint4* st, int op, int lane,
+                                          TraceItem& tr) {
+    const int4 w0 = m.ops[2 * (op - m.wb)], w1 = m.ops[2 * (op - m.wb) + 1];
+    const uint32_t r0 = (uint32_t)w1.x, r1 = (uint32_t)w1.y;
+    bool ok = true;
+    switch ((w0.z >> OPF_TYPE_SHIFT) & 15) {
+    case FT_LEAF_LEAF:
+        cp_async16(st, tc.leaf + (size_t)(r0 & REF_IDX_MASK) * 32);
+        cp_async16(st + 32, tc.leaf + (size_t)(r1 & REF_IDX_MASK) * 32);
+        break;
+    case FT_LEAF_ACC:
+        cp_async16(st, tc.leaf + (size_t)(r0 & REF_IDX_MASK) * 32);
+        break;
+    case FT_LEAF_INT:
+        cp_async16(st, tc.leaf + (size_t)(r0 & REF_IDX_MASK) * 32);
+        ok = fwd_issue_set<JS, JROW>(p, tc, st, r1, op, lane, tr);
+        break;
+    case FT_INT_ACC:
+        ok = fwd_issue_set<JS, JROW>(p, tc, st, r0, op, lane, tr);
+        break;
+    default: {
+        int nl = 0, ni = 0;
+        for (int r = 0; r < w0.y && (nl < 2 || ni < 1); r++) {
+            const uint32_t ref = fwd_ref(p, m, w0.x + r);
+            const uint32_t kind = ref >> 30;
+            if (kind == REF_LEAF) {
+                if (nl < 2) cp_async16(st + nl * 32, tc.leaf + (size_t)(ref & REF_IDX_MASK) * 32);
+                nl++;
+            } else if (kind == REF_INT) {
+                if (ni == 0) ok = fwd_issue_set<JS, JROW>(p, tc, st, ref, op, lane, tr) && ok;
+                ni++;
             }
-            ni++;
         }
+    }
     }
     cp_async_commit();
     return ok;
+}
+__device__ __forceinline__ void stage_set16(const uint4* st, uint32_t X[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 v = st[(2 + j) * 32];
+        X[4 * j] = v.x; X[4 * j + 1] = v.y; X[4 * j + 2] = v.z; X[4 * j + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void row_set16(const uint4* row, uint32_t X[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 v = ld_l2(row + j * 32);
+        X[4 * j] = v.x; X[4 * j + 1] = v.y; X[4 * j + 2] = v.z; X[4 * j + 3] = v.w;
+    }
 }
 
 // ------------------------------------------------------------------ Fitch forward
@@ -385,47 +446,46 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
     FwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + FWD_DEPTH * STAGE);
-    m.refs = reinterpret_cast<uint32_t*>(m.ops + META_OPS);
+    m.refs = reinterpret_cast<uint32_t*>(m.ops + 2 * META_OPS);
+    uint4* const ring_l = ring + lane;
     ItemIter it;
     TraceItem tr;
     int chunk, tile;
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
+        const TileCtx tc = tile_ctx<4>(p, tile, lane);
         uint32_t acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0;
         fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
         for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 4>(p, m, ring, ck.op_begin + i, ck.op_begin, tile, lane, tr)) return;
+            if (!fwd_issue<JS, 4>(p, m, tc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
         }
+        int stage = 0;
         for (int op = ck.op_begin; op < ck.op_end; op++) {
             if (op + FWD_DEPTH >= m.wb + META_OPS && m.wb + META_OPS < ck.op_end) fwd_meta_load(p, m, op, ck.op_end, lane);
-            const int4 f = fwd_head(m, op);  // ref_begin, n_refs, flags, bits
-            cp_async_wait_pending(min(FWD_DEPTH - 1, ck.op_end - 1 - op));
-            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * STAGE;
-            const uint4 l0 = st[lane], l1 = st[32 + lane];
-            const int type = p.leaf_present ? FT_GENERIC : ((f.z >> OPF_TYPE_SHIFT) & 15);
+            const int4 w0 = m.ops[2 * (op - m.wb)], w1 = m.ops[2 * (op - m.wb) + 1];  // {ref_begin, n_refs, flags, bits}, {ref0, ref1}
+            cp_async_wait_stage<FWD_DEPTH>(ck.op_end - 1 - op);
+            uint4* st = ring_l + stage * STAGE;
+            const int type = p.leaf_present ? FT_GENERIC : ((w0.z >> OPF_TYPE_SHIFT) & 15);
             if (type == FT_LEAF_LEAF) {
+                const uint4 l0 = st[0], l1 = st[32];
                 const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w}, c1[4] = {l1.x, l1.y, l1.z, l1.w};
                 fitch_leaf_leaf(c0, c1, acc);
             } else if (type == FT_LEAF_ACC) {
+                const uint4 l0 = st[0];
                 const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w};
                 uint32_t X[16];
 #pragma unroll
                 for (int k = 0; k < 16; k++) X[k] = acc[k];
                 fitch_leaf_set(c0, X, acc);
             } else if (type == FT_LEAF_INT || type == FT_INT_ACC) {
-                const uint32_t ref = fwd_ref(p, m, f.x + (type == FT_LEAF_INT ? 1 : 0));
+                const uint32_t ref = (uint32_t)(type == FT_LEAF_INT ? w1.y : w1.x);
                 uint32_t X[16];
-                if (fwd_set_prefetched<JS>(ref, op)) {
-                    uint4 v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = st[(2 + j) * 32 + lane];
-                    unpack16(v, X);
-                } else {
-                    load_planes16(p.sets + set_index(p, ref & REF_IDX_MASK, tile) * 128, lane, X);
-                }
+                if (fwd_set_prefetched(ref, op)) stage_set16(st, X);
+                else row_set16(tc.sets + (size_t)(ref & REF_IDX_MASK) * 128, X);
                 if (type == FT_LEAF_INT) {
+                    const uint4 l0 = st[0];
                     const uint32_t c0[4] = {l0.x, l0.y, l0.z, l0.w};
                     fitch_leaf_set(c0, X, acc);
                 } else {
@@ -438,14 +498,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 FitchFold fold;
                 fold.reset();
                 int nl = 0, ni = 0;
-                for (int r = 0; r < f.y; r++) {
-                    const uint32_t ref = fwd_ref(p, m, f.x + r);
+                for (int r = 0; r < w0.y; r++) {
+                    const uint32_t ref = fwd_ref(p, m, w0.x + r);
                     const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
                     if (kind == REF_LEAF) {
                         uint4 c;
-                        if (nl == 0) c = l0;
-                        else if (nl == 1) c = l1;
-                        else c = ld_stream(p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
+                        if (nl < 2) c = st[nl * 32];
+                        else c = ld_stream(tc.leaf + (size_t)idx * 32);
                         nl++;
                         uint32_t cc[4] = {c.x, c.y, c.z, c.w};
                         fold.add_leaf(cc, leaf_present_mask(p, idx));
@@ -453,16 +512,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         fold.add_set(acc);
                     } else {
                         uint32_t S[16];
-                        if (ni == 0 && fwd_set_prefetched<JS>(ref, op)) {
-                            uint4 v[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) v[j] = st[(2 + j) * 32 + lane];
-                            unpack16(v, S);
+                        if (ni == 0 && fwd_set_prefetched(ref, op)) {
+                            stage_set16(st, S);
                         } else {
                             if (ref & REF_EXT) {
-                                if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return;
+                                if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return;
                             }
-                            load_planes16(p.sets + set_index(p, idx, tile) * 128, lane, S);
+                            row_set16(tc.sets + (size_t)idx * 128, S);
                         }
                         ni++;
                         fold.add_set(S);
@@ -470,7 +526,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 }
                 fold.finish(acc);
             }
-            if ((f.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
+            if ((w0.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
                 // refState: the root's forward value is replaced (fitchSankoff.cpp:45-47)
                 const uint4* cp = p.colparams + (size_t)tile * 128;
                 uint4 rc = __ldg(cp + 64 + lane);
@@ -480,12 +536,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
 #pragma unroll
                 for (int k = 0; k < 16; k++) acc[k] = (rv & d[k]) | (~rv & acc[k]);
             }
-            store_planes16(p.sets + set_index(p, op, tile) * 128, lane, acc);
-            if (f.z & OPF_SIGNAL) signal_flag(p.done + set_index(p, op, tile), p.epoch, lane);
+            uint4* out = tc.sets + (size_t)op * 128;
+#pragma unroll
+            for (int j = 0; j < 4; j++) out[j * 32] = make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
             // the stage of this op is consumed and its result stored: refill the stage for the op FWD_DEPTH ahead
             if (op + FWD_DEPTH < ck.op_end) {
-                if (!fwd_issue<JS, 4>(p, m, ring, op + FWD_DEPTH, ck.op_begin, tile, lane, tr)) return;
+                if (!fwd_issue<JS, 4>(p, m, tc, st, op + FWD_DEPTH, lane, tr)) return;
             }
+            stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -494,31 +553,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
 // ------------------------------------------------------------------ backward: shared pieces
 // stage layout: [J set-row vectors][2 leaf rows], each 32 lanes wide; J = 4 (Fitch) or 8 (Sankoff)
 template <int J>
-__device__ __forceinline__ void bwd_issue(const RunParams& p, const BwdMeta& m, uint4* ring, int op, int op_last, int tile, int lane) {
-    uint4* st = ring + ((op_last - op) % BWD_DEPTH) * ((J + 2) * 32);
-    const uint4* srow = p.sets + set_index(p, op, tile) * (J * 32);
+__device__ __forceinline__ void bwd_issue(const BwdMeta& m, const TileCtx& tc, uint4* st, int op) {
+    const uint4* srow = tc.sets + (size_t)op * (J * 32);
 #pragma unroll
-    for (int j = 0; j < J; j++) cp_async16(st + j * 32 + lane, srow + j * 32 + lane);
-    const BwdHead h = bwd_head(m, op);
-    for (int l = 0; l < h.b1.x && l < 2; l++) {
-        const int row = bwd_leaf(p, m, h.b0.w + l).x;
-        cp_async16(st + (J + l) * 32 + lane, p.leaf_planes + leaf_index(p, row, tile) * 32 + lane);
-    }
+    for (int j = 0; j < J; j++) cp_async16(st + j * 32, srow + j * 32);
+    const int4 b1 = m.ops[2 * (op - m.lo) + 1];  // n_leaves, flags, leaf0 slot, leaf1 slot
+    if (b1.x > 0) cp_async16(st + J * 32, tc.leaf + (size_t)b1.z * 32);
+    if (b1.x > 1) cp_async16(st + (J + 1) * 32, tc.leaf + (size_t)b1.w * 32);
     cp_async_commit();
 }
 
-// parent's assigned state from registers (ACC) or from its parked slot (possibly written by another chunk)
-__device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h, int tile, int lane, const uint32_t accF[4],
-                                           uint32_t accVis, uint32_t P[4], uint32_t& pvis, TraceItem& tr) {
-    if (h.b0.y == PARENT_ACC) {
-        P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
-        pvis = accVis;
-        return true;
-    }
+// parent's assigned state from its parked slot (possibly written by another chunk)
+__device__ __forceinline__ bool bwd_parent_slot(const RunParams& p, const BwdHead& h, int tile, int lane, uint32_t P[4],
+                                                uint32_t& pvis, TraceItem& tr) {
+    const size_t fi = fslot_index(p, h.b0.y, tile);
     if (h.b1.y & OPF_PARENT_EXT) {
-        if (!wait_flag(p.fdone + fslot_index(p, h.b0.y, tile), p.epoch, p.error, lane, tr)) return false;
+        if (!wait_flag(p.fdone + fi, p.epoch, p.error, lane, tr)) return false;
     }
-    const uint32_t* fs = p.fstore + fslot_index(p, h.b0.y, tile) * FSLOT_WORDS;
+    const uint32_t* fs = p.fstore + fi * FSLOT_WORDS;
     uint4 a = ld_l2(reinterpret_cast<const uint4*>(fs) + lane);
     pvis = __ldcg(fs + 128 + lane);
     P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
@@ -527,22 +579,23 @@ __device__ __forceinline__ bool bwd_parent(const RunParams& p, const BwdHead& h,
 
 // what follows the assignment of an internal node, shared by Fitch and Sankoff: its own record, the parked
 // state for later children, and its leaf children (a present leaf is always assigned its own code)
-__device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta& m, StageCursor& sc, const BwdHead& h,
-                                              const uint4* leaf_stage, int tile, int lane, const uint32_t P[4],
-                                              const uint32_t F[4], uint32_t vis, bool sankoff_block) {
+__device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta& m, const TileCtx& tc, StageCursor& sc,
+                                              const BwdHead& h, const uint4* leaf_stage, int tile, int lane,
+                                              const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block) {
     emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
     if (h.b0.z >= 0) {
-        uint32_t* fs = p.fstore + fslot_index(p, h.b0.z, tile) * FSLOT_WORDS;
+        const size_t fi = fslot_index(p, h.b0.z, tile);
+        uint32_t* fs = p.fstore + fi * FSLOT_WORDS;
         reinterpret_cast<uint4*>(fs)[lane] = make_uint4(F[0], F[1], F[2], F[3]);
         fs[128 + lane] = vis;
-        if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + fslot_index(p, h.b0.z, tile), p.epoch, lane);
+        if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + fi, p.epoch, lane);
     }
     if (p.states) store_state(p, h.b0.x, tile, lane, F, vis);
     for (int l = 0; l < h.b1.x; l++) {
         const int2 lf = bwd_leaf(p, m, h.b0.w + l);  // slot, node
         uint4 c;
-        if (l < 2) c = leaf_stage[l * 32 + lane];
-        else c = ld_stream(p.leaf_planes + leaf_index(p, lf.x, tile) * 32 + lane);
+        if (l < 2) c = leaf_stage[l * 32];
+        else c = ld_stream(tc.leaf + (size_t)lf.x * 32);
         uint32_t cc[4] = {c.x, c.y, c.z, c.w};
         uint32_t present = leaf_present_mask(p, lf.x);
         if (sankoff_block && !present) {  // omitted block leaf = "absent" state (fitchSankoff.cpp:711-714)
@@ -567,29 +620,37 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
     BwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
     m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
+    uint4* const ring_l = ring + lane;
     ItemIter it;
     TraceItem tr;
     StageCursor sc;
     int chunk, tile;
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
+        const TileCtx tc = tile_ctx<J>(p, tile, lane);
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
         bwd_meta_load(p, m, last, ck.op_begin, lane);
-        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, m, ring, last - i, last, tile, lane);
+        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, last - i);
+        int stage = 0;
         for (int op = last; op >= ck.op_begin; op--) {
             if (op - BWD_DEPTH < m.lo && m.lo > ck.op_begin) bwd_meta_load(p, m, op, ck.op_begin, lane);
-            const BwdHead h = bwd_head(m, op);
-            uint32_t P[4], pvis = 0, F[4], vis;
-            if (h.b0.y != PARENT_ROOT) {
-                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis, tr)) return;
+            BwdHead h;
+            h.b0 = m.ops[2 * (op - m.lo)];
+            h.b1 = m.ops[2 * (op - m.lo) + 1];
+            uint32_t P[4], pvis, F[4], vis;
+            if (h.b0.y == PARENT_ACC) {
+                P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
+                pvis = accVis;
+            } else if (h.b0.y >= 0) {
+                if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
             }
-            cp_async_wait_pending(min(BWD_DEPTH - 1, op - ck.op_begin));
-            const uint4* st = ring + ((last - op) % BWD_DEPTH) * STAGE;
+            cp_async_wait_stage<BWD_DEPTH>(op - ck.op_begin);
+            uint4* st = ring_l + stage * STAGE;
             uint32_t S[16];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint4 v = st[j * 32 + lane];
+                const uint4 v = st[j * 32];
                 S[4 * j] = v.x; S[4 * j + 1] = v.y; S[4 * j + 2] = v.z; S[4 * j + 3] = v.w;
             }
             if (h.b0.y == PARENT_ROOT) {
@@ -611,9 +672,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             } else {
                 fitch_assign(S, P, pvis, F, vis);
             }
-            bwd_finish_op(p, m, sc, h, st + J * 32, tile, lane, P, F, vis, false);
+            bwd_finish_op(p, m, tc, sc, h, st + J * 32, tile, lane, P, F, vis, false);
             // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
-            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, m, ring, op - BWD_DEPTH, last, tile, lane);
+            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
+            stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
         }
@@ -624,18 +686,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
 // ------------------------------------------------------------------ Sankoff forward
 // first non-accumulator set row either comes prefetched from the stage (G planes + first H vector) or is loaded here
 template <int B>
-__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const FwdMeta& m, const int4 f, int op, const uint4* st,
-                                                   int tile, int lane, uint32_t accG[16], uint32_t accH[16], TraceItem& tr) {
+__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const FwdMeta& m, const TileCtx& tc, const int4 w0, int op,
+                                                   const uint4* st, int lane, uint32_t accG[16], uint32_t accH[16],
+                                                   TraceItem& tr) {
     SankoffFold<B> fold;
     fold.reset();
     int nl = 0, ni = 0;
-    for (int r = 0; r < f.y; r++) {
-        const uint32_t ref = fwd_ref(p, m, f.x + r);
+    for (int r = 0; r < w0.y; r++) {
+        const uint32_t ref = fwd_ref(p, m, w0.x + r);
         const uint32_t kind = ref >> 30, idx = ref & REF_IDX_MASK;
         if (kind == REF_LEAF) {
             uint4 c;
-            if (nl < 2) c = st[nl * 32 + lane];
-            else c = ld_stream(p.leaf_planes + leaf_index(p, idx, tile) * 32 + lane);
+            if (nl < 2) c = st[nl * 32];
+            else c = ld_stream(tc.leaf + (size_t)idx * 32);
             nl++;
             uint32_t present = leaf_present_mask(p, idx);
             uint32_t cc[4] = {c.x, c.y, c.z, c.w};
@@ -648,19 +711,16 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Fwd
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
             uint32_t G[16], h0;
-            if (ni == 0 && fwd_set_prefetched<5>(ref, op)) {
-                uint4 v[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = st[(2 + j) * 32 + lane];
-                unpack16(v, G);
-                h0 = st[(2 + 4) * 32 + lane].x;
+            if (ni == 0 && fwd_set_prefetched(ref, op)) {
+                stage_set16(st, G);
+                h0 = st[(2 + 4) * 32].x;
             } else {
                 if (ref & REF_EXT) {
-                    if (!wait_flag(p.done + set_index(p, idx, tile), p.epoch, p.error, lane, tr)) return false;
+                    if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return false;
                 }
-                const uint4* base = p.sets + set_index(p, idx, tile) * 256;
-                load_planes16(base, lane, G);
-                h0 = ld_l2(base + 128 + lane).x;
+                const uint4* row = tc.sets + (size_t)idx * 256;
+                row_set16(row, G);
+                h0 = ld_l2(row + 128).x;
             }
             ni++;
             fold.add_set(G, h0 & ~G[0]);
@@ -682,37 +742,44 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
     FwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + FWD_DEPTH * STAGE);
-    m.refs = reinterpret_cast<uint32_t*>(m.ops + META_OPS);
+    m.refs = reinterpret_cast<uint32_t*>(m.ops + 2 * META_OPS);
+    uint4* const ring_l = ring + lane;
     ItemIter it;
     TraceItem tr;
     int chunk, tile;
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
+        const TileCtx tc = tile_ctx<8>(p, tile, lane);
         uint32_t accG[16], accH[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
         fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
         for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 8>(p, m, ring, ck.op_begin + i, ck.op_begin, tile, lane, tr)) return;
+            if (!fwd_issue<JS, 8>(p, m, tc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
         }
+        int stage = 0;
         for (int op = ck.op_begin; op < ck.op_end; op++) {
             if (op + FWD_DEPTH >= m.wb + META_OPS && m.wb + META_OPS < ck.op_end) fwd_meta_load(p, m, op, ck.op_end, lane);
-            const int4 f = fwd_head(m, op);
-            cp_async_wait_pending(min(FWD_DEPTH - 1, ck.op_end - 1 - op));
-            const uint4* st = ring + ((op - ck.op_begin) % FWD_DEPTH) * STAGE;
+            const int4 w0 = m.ops[2 * (op - m.wb)];
+            cp_async_wait_stage<FWD_DEPTH>(ck.op_end - 1 - op);
+            uint4* st = ring_l + stage * STAGE;
             bool ok;
-            if (MAXB == 2 || f.w == 2) ok = sankoff_forward_op<2>(p, m, f, op, st, tile, lane, accG, accH, tr);
-            else if (MAXB == 4 || f.w == 4) ok = sankoff_forward_op<4>(p, m, f, op, st, tile, lane, accG, accH, tr);
-            else if (MAXB == 8 || f.w == 8) ok = sankoff_forward_op<8>(p, m, f, op, st, tile, lane, accG, accH, tr);
-            else ok = sankoff_forward_op<20>(p, m, f, op, st, tile, lane, accG, accH, tr);
+            if (MAXB == 2 || w0.w == 2) ok = sankoff_forward_op<2>(p, m, tc, w0, op, st, lane, accG, accH, tr);
+            else if (MAXB == 4 || w0.w == 4) ok = sankoff_forward_op<4>(p, m, tc, w0, op, st, lane, accG, accH, tr);
+            else if (MAXB == 8 || w0.w == 8) ok = sankoff_forward_op<8>(p, m, tc, w0, op, st, lane, accG, accH, tr);
+            else ok = sankoff_forward_op<20>(p, m, tc, w0, op, st, lane, accG, accH, tr);
             if (!ok) return;
-            uint4* base = p.sets + set_index(p, op, tile) * 256;
-            store_planes16(base, lane, accG);
-            store_planes16(base + 128, lane, accH);
-            if (f.z & OPF_SIGNAL) signal_flag(p.done + set_index(p, op, tile), p.epoch, lane);
-            if (op + FWD_DEPTH < ck.op_end) {
-                if (!fwd_issue<JS, 8>(p, m, ring, op + FWD_DEPTH, ck.op_begin, tile, lane, tr)) return;
+            uint4* out = tc.sets + (size_t)op * 256;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                out[j * 32] = make_uint4(accG[4 * j], accG[4 * j + 1], accG[4 * j + 2], accG[4 * j + 3]);
+                out[(4 + j) * 32] = make_uint4(accH[4 * j], accH[4 * j + 1], accH[4 * j + 2], accH[4 * j + 3]);
             }
+            if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
+            if (op + FWD_DEPTH < ck.op_end) {
+                if (!fwd_issue<JS, 8>(p, m, tc, st, op + FWD_DEPTH, lane, tr)) return;
+            }
+            stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -727,29 +794,37 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
     BwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
     m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
+    uint4* const ring_l = ring + lane;
     ItemIter it;
     TraceItem tr;
     StageCursor sc;
     int chunk, tile;
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
+        const TileCtx tc = tile_ctx<J>(p, tile, lane);
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
         bwd_meta_load(p, m, last, ck.op_begin, lane);
-        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(p, m, ring, last - i, last, tile, lane);
+        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, last - i);
+        int stage = 0;
         for (int op = last; op >= ck.op_begin; op--) {
             if (op - BWD_DEPTH < m.lo && m.lo > ck.op_begin) bwd_meta_load(p, m, op, ck.op_begin, lane);
-            const BwdHead h = bwd_head(m, op);
-            uint32_t P[4], pvis = 0, F[4], vis;
-            if (h.b0.y != PARENT_ROOT) {
-                if (!bwd_parent(p, h, tile, lane, accF, accVis, P, pvis, tr)) return;
+            BwdHead h;
+            h.b0 = m.ops[2 * (op - m.lo)];
+            h.b1 = m.ops[2 * (op - m.lo) + 1];
+            uint32_t P[4], pvis, F[4], vis;
+            if (h.b0.y == PARENT_ACC) {
+                P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
+                pvis = accVis;
+            } else if (h.b0.y >= 0) {
+                if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
             }
-            cp_async_wait_pending(min(BWD_DEPTH - 1, op - ck.op_begin));
-            const uint4* st = ring + ((last - op) % BWD_DEPTH) * STAGE;
+            cp_async_wait_stage<BWD_DEPTH>(op - ck.op_begin);
+            uint4* st = ring_l + stage * STAGE;
             uint32_t G[16], H[16];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint4 v = st[j * 32 + lane], w = st[(4 + j) * 32 + lane];
+                const uint4 v = st[j * 32], w = st[(4 + j) * 32];
                 G[4 * j] = v.x; G[4 * j + 1] = v.y; G[4 * j + 2] = v.z; G[4 * j + 3] = v.w;
                 H[4 * j] = w.x; H[4 * j + 1] = w.y; H[4 * j + 2] = w.z; H[4 * j + 3] = w.w;
             }
@@ -769,8 +844,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
                 sankoff_assign(G, H, P, pvis, F, vis);
             }
             // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
-            bwd_finish_op(p, m, sc, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
-            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(p, m, ring, op - BWD_DEPTH, last, tile, lane);
+            bwd_finish_op(p, m, tc, sc, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
+            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
+            stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
         }

@@ -250,7 +250,9 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         b.node = v;
         b.flags = ((v == root) ? OPF_ROOT : 0) | (ext_child[i] ? OPF_SIGNAL_F : 0);
         b.leaf_begin = int32_t(P.bwd_leaves.size());
-        b.pad0 = b.pad1 = 0;
+        b.leaf0_slot = b.leaf1_slot = 0;
+        f.ref0 = f.ref1 = 0;
+        f.pad0 = f.pad1 = 0;
         // leaves in Newick order, then internal children heavy -> light; the one computed by op i-1 of the
         // same chunk (if any) is taken from registers
         for (int32_t e = child_off[v]; e < child_off[v + 1]; e++) {
@@ -270,6 +272,8 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
             P.refs.push_back(acc ? (REF_ACC << 30) : ((REF_INT << 30) | (ext ? REF_EXT : 0u) | uint32_t(cop)));
         }
         f.n_refs = int32_t(P.refs.size()) - f.ref_begin;
+        if (f.n_refs > 0) f.ref0 = P.refs[f.ref_begin];
+        if (f.n_refs > 1) f.ref1 = P.refs[f.ref_begin + 1];
         max_arity = std::max(max_arity, f.n_refs);
         if (f.n_refs == 2) {
             const uint32_t k0 = P.refs[f.ref_begin] >> 30, k1 = P.refs[f.ref_begin + 1] >> 30;
@@ -282,6 +286,8 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         }
         f.max_arity_bits = f.n_refs <= 3 ? 2 : (f.n_refs <= 15 ? 4 : (f.n_refs <= 255 ? 8 : 20));
         b.n_leaves = int32_t(P.bwd_leaves.size()) - b.leaf_begin;
+        if (b.n_leaves > 0) b.leaf0_slot = P.bwd_leaves[b.leaf_begin].row;
+        if (b.n_leaves > 1) b.leaf1_slot = P.bwd_leaves[b.leaf_begin + 1].row;
         b.fslot_out = fslot[i];
         if (v == root) b.parent_ref = PARENT_ROOT;
         else {

@@ -39,11 +39,13 @@ enum : int32_t {
 // shape of a forward op; refs are stored in the order named (leaves first, then internal children heavy -> light)
 enum FwdType : int32_t { FT_GENERIC = 0, FT_LEAF_LEAF = 1, FT_LEAF_ACC = 2, FT_LEAF_INT = 3, FT_INT_ACC = 4 };
 
-struct FwdOp {  // 16 bytes; the op index is also the node's row ("slot") in the set matrix
+struct FwdOp {  // 32 bytes; the op index is also the node's row ("slot") in the set matrix
     int32_t ref_begin;
     int32_t n_refs;
     int32_t flags;
     int32_t max_arity_bits;  // Sankoff counter width class for this op: 2, 4, 8 or 20
+    uint32_t ref0, ref1;     // copies of the first two refs, so that binary ops never touch refs[]
+    int32_t pad0, pad1;
 };
 
 struct BwdOp {  // 32 bytes
@@ -53,7 +55,7 @@ struct BwdOp {  // 32 bytes
     int32_t leaf_begin;  // into bwd_leaves
     int32_t n_leaves;
     int32_t flags;
-    int32_t pad0, pad1;
+    int32_t leaf0_slot, leaf1_slot;  // slots of the first two leaf children (their node ids: bwd_leaves[leaf_begin + k].node)
 };
 
 struct BwdLeaf {
