@@ -247,7 +247,7 @@ int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParam
 // group's bulk work, and a group's set rows are re-read by its backward pass soon after they were written.
 int pick_groups(const pmb_ctx* c) {
     int64_t g = c->opt_col_groups;
-    if (g <= 0) g = c->T >= 12 ? 3 : (c->T >= 4 ? 2 : 1);
+    if (g <= 0) g = 1;  // measured (tools/sweep.py): with the critical-path ticket orders one group is as good or better
     g = std::min<int64_t>(g, std::min<int64_t>(c->T, pmb_ctx::MAX_GROUPS));
     return int(std::max<int64_t>(1, g));
 }

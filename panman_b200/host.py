@@ -1,0 +1,121 @@
+"""ctypes mirror of include/panman_b200_host.h: the host-side adaptor (Newick, MSA flow, run-merge into NucMut)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .lib import HERE, load_library
+
+HOST_LIB_PATH = os.path.join(HERE, "libpanman_b200_host.so")
+
+
+class pmh_nucmut(C.Structure):
+    _fields_ = [("nucPosition", C.c_int32), ("nucGapPosition", C.c_int32), ("primaryBlockId", C.c_int32),
+                ("secondaryBlockId", C.c_int32), ("mutInfo", C.c_uint8), ("nucs", C.c_uint32)]
+
+
+_hlib = None
+
+
+def load_host_library():
+    global _hlib
+    if _hlib is not None:
+        return _hlib
+    load_library()  # the device library first (rpath $ORIGIN also finds it)
+    if not os.path.exists(HOST_LIB_PATH):
+        raise RuntimeError(f"{HOST_LIB_PATH} is missing: run __graft_entry__.build()")
+    L = C.CDLL(HOST_LIB_PATH)
+    vp = C.c_void_p
+    L.pmh_tree_from_newick.restype = vp
+    L.pmh_tree_from_newick.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    L.pmh_tree_free.argtypes = [vp]
+    for f in ("pmh_tree_n_nodes", "pmh_tree_n_leaves", "pmh_tree_root", "pmh_tree_has_polytomy"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_int32
+    L.pmh_tree_name.argtypes = [vp, C.c_int32]
+    L.pmh_tree_name.restype = C.c_char_p
+    for f in ("pmh_tree_parent", "pmh_tree_child_offsets", "pmh_tree_child_index", "pmh_tree_leaf_row"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.POINTER(C.c_int32)
+    L.pmh_build_from_msa.restype = vp
+    L.pmh_build_from_msa.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+    L.pmh_build_free.argtypes = [vp]
+    L.pmh_build_tree.argtypes = [vp]
+    L.pmh_build_tree.restype = vp
+    L.pmh_build_consensus.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.pmh_build_consensus.restype = C.POINTER(C.c_char)
+    L.pmh_build_n_nucmut.argtypes = [vp, C.c_int32]
+    L.pmh_build_n_nucmut.restype = C.c_int64
+    L.pmh_build_nucmut.argtypes = [vp, C.c_int32]
+    L.pmh_build_nucmut.restype = C.POINTER(pmh_nucmut)
+    L.pmh_build_n_tuples.argtypes = [vp]
+    L.pmh_build_n_tuples.restype = C.c_int64
+    L.pmh_build_tuple_offsets.argtypes = [vp]
+    L.pmh_build_tuple_offsets.restype = C.POINTER(C.c_int64)
+    L.pmh_build_tuple_pos.argtypes = [vp]
+    L.pmh_build_tuple_pos.restype = C.POINTER(C.c_int32)
+    L.pmh_build_tuple_type_code.argtypes = [vp]
+    L.pmh_build_tuple_type_code.restype = C.POINTER(C.c_uint8)
+    L.pmh_build_seconds.argtypes = [vp]
+    L.pmh_build_seconds.restype = C.POINTER(C.c_double)
+    _hlib = L
+    return L
+
+
+class HostTree:
+    """Result of the C++ Newick parser (reference src/panman.cpp:310-450 conventions)."""
+
+    def __init__(self, handle, owned=True):
+        self.L = load_host_library()
+        self.h = handle
+        self.owned = owned
+        n = self.L.pmh_tree_n_nodes(handle)
+        self.names = [self.L.pmh_tree_name(handle, v).decode() for v in range(n)]
+        self.parent = np.ctypeslib.as_array(self.L.pmh_tree_parent(handle), (n,)).copy()
+        self.child_off = np.ctypeslib.as_array(self.L.pmh_tree_child_offsets(handle), (n + 1,)).copy()
+        self.child_idx = np.ctypeslib.as_array(self.L.pmh_tree_child_index(handle), (max(n - 1, 1),))[:n - 1].copy()
+        self.leaf_row = np.ctypeslib.as_array(self.L.pmh_tree_leaf_row(handle), (n,)).copy()
+        self.root = int(self.L.pmh_tree_root(handle))
+        self.n_nodes = n
+        self.n_leaves = int(self.L.pmh_tree_n_leaves(handle))
+        self.polytomy = bool(self.L.pmh_tree_has_polytomy(handle))
+        if owned:
+            self.L.pmh_tree_free(handle)
+            self.h = None
+
+
+def parse_newick(newick: str) -> HostTree:
+    L = load_host_library()
+    err = C.create_string_buffer(256)
+    h = L.pmh_tree_from_newick(newick.encode(), err, 256)
+    if not h:
+        raise ValueError(err.value.decode())
+    return HostTree(h)
+
+
+class MsaBuild:
+    """panmanUtils -M msa.fa -N tree.nwk [--reference id] [--low-mem-mode] through libpanman_b200."""
+
+    def __init__(self, ctx, fasta: bytes, newick: str, reference: str = "", low_mem_mode: bool = False):
+        L = load_host_library()
+        err = C.create_string_buffer(512)
+        h = L.pmh_build_from_msa(ctx.h, fasta, len(fasta), newick.encode(), reference.encode(), int(low_mem_mode), err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode())
+        self.tree = HostTree(L.pmh_build_tree(h), owned=False)
+        n = C.c_int64()
+        p = L.pmh_build_consensus(h, C.byref(n))
+        self.consensus = C.string_at(p, n.value)
+        self.nucmut = []
+        for v in range(self.tree.n_nodes):
+            k = L.pmh_build_n_nucmut(h, v)
+            arr = L.pmh_build_nucmut(h, v)
+            self.nucmut.append([(arr[i].nucPosition, arr[i].nucGapPosition, arr[i].primaryBlockId, arr[i].secondaryBlockId,
+                                 arr[i].mutInfo, arr[i].nucs) for i in range(k)])
+        nt = L.pmh_build_n_tuples(h)
+        N = self.tree.n_nodes
+        self.tuple_offsets = np.ctypeslib.as_array(L.pmh_build_tuple_offsets(h), (N + 1,)).copy()
+        self.tuple_pos = np.ctypeslib.as_array(L.pmh_build_tuple_pos(h), (max(nt, 1),))[:nt].copy()
+        self.tuple_type_code = np.ctypeslib.as_array(L.pmh_build_tuple_type_code(h), (max(nt, 1),))[:nt].copy()
+        self.seconds = list(np.ctypeslib.as_array(L.pmh_build_seconds(h), (4,)))
+        L.pmh_build_free(h)
