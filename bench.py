@@ -223,45 +223,14 @@ def run_b200_arm(args):
 
     def gather_lists():
         """Column-range gather of the per-rank lists to rank 0 (NCCL), then concatenation per node in rank order."""
+        from panman_b200.distributed import gather_lists as _gather
+
         r = ctx.result_device()
         n = int(r.n_mut)
         off = torch.as_tensor(_DevArray(r.node_offsets, N + 1, "<i8"), device=dev)
         pos = torch.as_tensor(_DevArray(r.pos, max(n, 1), "<i4"), device=dev)[:n]
         tc = torch.as_tensor(_DevArray(r.type_code, max(n, 1), "|u1"), device=dev)[:n]
-        counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=dev))
-        cl = counts.tolist()
-        offs = [torch.empty(N + 1, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(off, offs, dst=0)
-        if rank == 0:
-            poss = [pos] + [torch.empty(cl[k], dtype=torch.int32, device=dev) for k in range(1, world)]
-            tcs = [tc] + [torch.empty(cl[k], dtype=torch.uint8, device=dev) for k in range(1, world)]
-            ops = []
-            for k in range(1, world):
-                if cl[k]:
-                    ops += [dist.P2POp(dist.irecv, poss[k], k), dist.P2POp(dist.irecv, tcs[k], k)]
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            cnt = torch.stack([o[1:] - o[:-1] for o in offs])  # world x N
-            before = torch.cumsum(cnt, 0) - cnt
-            merged_off = torch.zeros(N + 1, dtype=torch.int64, device=dev)
-            merged_off[1:] = torch.cumsum(cnt.sum(0), 0)
-            total = int(merged_off[-1])
-            mpos = torch.empty(total, dtype=torch.int32, device=dev)
-            mtc = torch.empty(total, dtype=torch.uint8, device=dev)
-            for k in range(world):
-                if cl[k] == 0:
-                    continue
-                shift = merged_off[:-1] + before[k] - offs[k][:-1]
-                idx = torch.repeat_interleave(shift, cnt[k]) + torch.arange(cl[k], device=dev)
-                mpos[idx] = poss[k]
-                mtc[idx] = tcs[k]
-            return merged_off, mpos, mtc
-        if n:
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, pos, 0), dist.P2POp(dist.isend, tc, 0)]):
-                w.wait()
-        return None
+        return _gather(dist, rank, world, off, pos, tc)
 
     def step():
         t = ctx.run_resident(algo_i)
@@ -363,7 +332,8 @@ def run_b200_arm(args):
                 "steps": e2e_steps, "api": "pmb_run_nuc with pinned host buffers"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "forward + backward level launches + compaction of one pass (CUDA events on the library stream)",
+                     "kernel": "one pass = persistent forward kernel + persistent backward kernel + compaction "
+                               "(CUDA events on the library's stream, averaged over the timed steps)",
                      "algorithmic_bytes_per_pass": int(alg_bytes)},
     }
     if not args.no_cpu_baseline:
