@@ -221,16 +221,35 @@ def run_b200_arm(args):
 
     N = tree.n_nodes
 
-    def gather_lists():
-        """Column-range gather of the per-rank lists to rank 0 (NCCL), then concatenation per node in rank order."""
-        from panman_b200.distributed import gather_lists as _gather
+    # ---- N > 1: every step ends with the column-range gather of the per-rank lists to rank 0 and their merge there.
+    # A rank packs its result into one device buffer (pmb_pack_result) -> ONE NCCL gather -> pmb_merge_packed on rank 0.
+    # The gather/merge of step i runs on a side stream and overlaps the passes of step i+1 (double-buffered); the
+    # timed region ends only after the last merge has finished.
+    shard = None
+    if world > 1:
+        ctx.run_resident(algo_i)
+        nmax = torch.tensor([ctx.result_device().n_mut], dtype=torch.int64, device=dev)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+        cap = int(nmax.item() * 5 // 4) + 4096  # same on every rank; identical steps => stable
+        pbytes = ctx.packed_bytes(cap)
+        shard = dict(cap=cap, bytes=pbytes, send=[torch.empty(pbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
+                     recv=[torch.empty(world * pbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if rank == 0 else None,
+                     comm=torch.cuda.Stream(device=dev), lib=torch.cuda.ExternalStream(ctx.stream_handle(), device=dev), i=0,
+                     merged=None)
 
-        r = ctx.result_device()
-        n = int(r.n_mut)
-        off = torch.as_tensor(_DevArray(r.node_offsets, N + 1, "<i8"), device=dev)
-        pos = torch.as_tensor(_DevArray(r.pos, max(n, 1), "<i4"), device=dev)[:n]
-        tc = torch.as_tensor(_DevArray(r.type_code, max(n, 1), "|u1"), device=dev)[:n]
-        return _gather(dist, rank, world, off, pos, tc)
+    def gather_lists():
+        k = shard["i"] & 1
+        shard["i"] += 1
+        comm, lib = shard["comm"], shard["lib"]
+        lib.wait_stream(comm)                      # the gather that last used this send buffer is done
+        ctx.pack_result(shard["send"][k], shard["cap"])     # on the library's stream, right behind the pass
+        comm.wait_stream(lib)
+        with torch.cuda.stream(comm):
+            dst = [shard["recv"][k][r * shard["bytes"]:(r + 1) * shard["bytes"]] for r in range(world)] if rank == 0 else None
+            work = dist.gather(shard["send"][k], dst, dst=0, async_op=True)
+            work.wait()                            # orders the comm stream after the collective; the host does not block
+            if rank == 0:
+                shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=comm.cuda_stream)
 
     def step():
         t = ctx.run_resident(algo_i)
@@ -240,6 +259,7 @@ def run_b200_arm(args):
 
     def barrier():
         if world > 1:
+            shard["comm"].synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 

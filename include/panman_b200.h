@@ -132,6 +132,19 @@ int pmb_download(pmb_ctx* ctx, pmb_result* out);
 /* Device-side view of the last result (for an NCCL gather straight from HBM). Pointers are device memory. */
 int pmb_result_device(pmb_ctx* ctx, pmb_result* out);
 
+/* ---- column-range shards (one context / GPU / rank per contiguous column range) ----
+ * A rank packs its last result into ONE device buffer (header, node offsets, positions, type|code bytes) so that a
+ * single collective (e.g. an NCCL gather issued by the host program) moves it; the receiving rank merges the packed
+ * shards, given in ascending column-range order, into node-major lists: per node the shard lists are concatenated in
+ * shard order (each is already in ascending position), nothing is sorted. The reference's <=6 run-merge
+ * (src/panman.cpp:1445-1466) must run on the merged lists, never per shard. `capacity` = records the buffer can hold
+ * (>= n_mut of every shard); `stream` = CUDA stream (cudaStream_t) to enqueue on, NULL = the context's stream. */
+void* pmb_stream(pmb_ctx* ctx); /* the cudaStream_t the context enqueues on, to order caller work after it */
+int64_t pmb_packed_bytes(int32_t n_nodes, int64_t capacity);
+int pmb_pack_result(pmb_ctx* ctx, void* d_packed, int64_t capacity, void* stream);
+int pmb_merge_packed(pmb_ctx* ctx, int32_t n_shards, const void* d_packed_shards, int64_t capacity, void* stream,
+                     pmb_result* out_device);
+
 /* ---- introspection ---- */
 int pmb_last_timings(const pmb_ctx* ctx, pmb_timings* out);
 /* Bytes the roofline is computed on, for the resident input and `algo`:

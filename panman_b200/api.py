@@ -144,6 +144,21 @@ class Context:
         self._check(self.L.pmb_result_device(self.h, C.byref(r)))
         return r
 
+    # column-range shards (multi-GPU): pack -> one collective by the caller -> merge on the receiving rank
+    def stream_handle(self) -> int:
+        return int(self.L.pmb_stream(self.h) or 0)
+
+    def packed_bytes(self, capacity: int) -> int:
+        return int(self.L.pmb_packed_bytes(self.n_nodes, int(capacity)))
+
+    def pack_result(self, d_packed, capacity: int, stream=None):
+        self._check(self.L.pmb_pack_result(self.h, _ptr(d_packed), int(capacity), stream))
+
+    def merge_packed(self, n_shards: int, d_packed, capacity: int, stream=None) -> pmb_result:
+        r = pmb_result()
+        self._check(self.L.pmb_merge_packed(self.h, int(n_shards), _ptr(d_packed), int(capacity), stream, C.byref(r)))
+        return r
+
     def run_nuc(self, algo, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
                 leaf_present=None, col_base=0, flags=0, copy=True) -> Result:
         r = pmb_result()

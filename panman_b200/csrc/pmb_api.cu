@@ -79,6 +79,7 @@ struct pmb_ctx {
     cudaEvent_t gev_fwd[MAX_GROUPS] = {}, gev_done[MAX_GROUPS] = {}, ev_fork = nullptr;
     int n_sms = 0;
     unsigned int epoch = 0;
+    unsigned int pack_seq = 0;
 
     // tree
     bool have_tree = false;
@@ -97,6 +98,8 @@ struct pmb_ctx {
 
     // work + result
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
+    DevBuf d_mcounts, d_moff, d_mpos, d_mtc;  // merged shards
+    HostBuf h_pack_header;
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_node_counts, d_offsets, d_pos, d_tc,
         d_states_u8;
     unsigned long long staging_cap = 0;
@@ -302,9 +305,10 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_level_order, &c->d_row_slot, &c->d_block_sums, &c->d_leaf_planes,
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
-                          &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket})
+                          &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
+                          &c->d_mpos, &c->d_mtc})
             b->release();
-        for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters}) b->release();
+        for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header}) b->release();
         for (int i = 0; i < 4; i++)
             if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         for (int g = 0; g < pmb_ctx::MAX_GROUPS; g++) {
@@ -654,6 +658,70 @@ long long pmb_debug_trace(const pmb_ctx* c, unsigned long long* out, long long m
     long long n = std::min<long long>(max_words, (long long)c->h_trace.size());
     std::memcpy(out, c->h_trace.data(), size_t(n) * sizeof(unsigned long long));
     return n;
+}
+
+void* pmb_stream(pmb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+
+int64_t pmb_packed_bytes(int32_t n_nodes, int64_t capacity) { return int64_t(packed_bytes(n_nodes, capacity)); }
+
+int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v) {
+    if (!c || !d_packed) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
+    if (capacity < c->n_mut) return fail(c, PMB_ERR_INVALID, "pmb_pack_result: capacity below the record count");
+    PMB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
+    const long long N = c->prog.n_nodes;
+    unsigned char* out = static_cast<unsigned char*>(d_packed);
+    PMB_CUDA(c->h_pack_header.ensure(4 * 16));
+    // a small ring of pinned headers: several packs may be in flight before the host touches the slot again
+    static_assert(sizeof(long long) == 8, "");
+    long long* hdr = c->h_pack_header.as<long long>() + 2 * (c->pack_seq++ & 3);
+    hdr[0] = c->n_mut;
+    hdr[1] = N;
+    PMB_CUDA(cudaMemcpyAsync(out, hdr, 16, cudaMemcpyHostToDevice, st));
+    PMB_CUDA(cudaMemcpyAsync(out + 16, c->d_offsets.p, size_t(N + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    if (c->n_mut) {
+        PMB_CUDA(cudaMemcpyAsync(out + packed_pos_offset(N), c->d_pos.p, size_t(c->n_mut) * 4, cudaMemcpyDeviceToDevice, st));
+        PMB_CUDA(cudaMemcpyAsync(out + packed_tc_offset(N, capacity), c->d_tc.p, size_t(c->n_mut), cudaMemcpyDeviceToDevice, st));
+    }
+    return PMB_OK;
+}
+
+int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, int64_t capacity, void* stream_v,
+                     pmb_result* out) {
+    if (!c || !d_packed_shards || !out || n_shards < 1) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
+    PMB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
+    const int N = c->prog.n_nodes;
+    const size_t shard_bytes = packed_bytes(N, capacity);
+    const size_t total_cap = size_t(n_shards) * size_t(capacity);
+    PMB_CUDA(c->d_mcounts.ensure(size_t(N) * sizeof(unsigned int)));
+    PMB_CUDA(c->d_moff.ensure(size_t(N + 1) * sizeof(long long)));
+    PMB_CUDA(c->d_mpos.ensure(std::max<size_t>(1, total_cap) * sizeof(int32_t)));
+    PMB_CUDA(c->d_mtc.ensure(std::max<size_t>(1, total_cap)));
+    const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
+    PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
+    const unsigned char* packed = static_cast<const unsigned char*>(d_packed_shards);
+    merge_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(packed, shard_bytes, n_shards, N, c->d_mcounts.as<unsigned int>());
+    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>());
+    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>(),
+                                                           c->d_moff.as<long long>());
+    merge_copy_kernel<<<unsigned(((long long)N * 32 + 255) / 256), 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity,
+                                                                                  c->d_moff.as<long long>(), c->d_mpos.as<int32_t>(),
+                                                                                  c->d_mtc.as<uint8_t>());
+    PMB_CUDA(cudaGetLastError());
+    out->n_mut = -1;  // on the device: node_offsets[n_nodes]; the call does not synchronise
+    out->n_nodes = N;
+    out->reserved = 0;
+    out->node_offsets = reinterpret_cast<const int64_t*>(c->d_moff.p);
+    out->pos = c->d_mpos.as<int32_t>();
+    out->type_code = c->d_mtc.as<uint8_t>();
+    out->states = nullptr;
+    out->n_cols = 0;
+    return PMB_OK;
 }
 
 int pmb_last_timings(const pmb_ctx* c, pmb_timings* out) {

@@ -964,6 +964,50 @@ __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* sta
     }
 }
 
+// ------------------------------------------------------------------ merging column-range shards (multi-GPU)
+// A packed shard = {int64 n_mut, int64 n_nodes | int64 offsets[N+1] | int32 pos[cap] | uint8 type_code[cap]} (16-byte
+// aligned sections). Shards are column ranges in ascending order, so a node's merged list is the concatenation of its
+// per-shard lists in shard order.
+__host__ __device__ inline size_t packed_pos_offset(long long n_nodes) { return (16 + size_t(n_nodes + 1) * 8 + 15) / 16 * 16; }
+__host__ __device__ inline size_t packed_tc_offset(long long n_nodes, long long cap) {
+    return (packed_pos_offset(n_nodes) + size_t(cap) * 4 + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t packed_bytes(long long n_nodes, long long cap) {
+    return (packed_tc_offset(n_nodes, cap) + size_t(cap) + 15) / 16 * 16;
+}
+
+__global__ void merge_count_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, unsigned int* counts) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    unsigned int c = 0;
+    for (int k = 0; k < n_shards; k++) {
+        const long long* off = reinterpret_cast<const long long*>(packed + k * shard_bytes + 16);
+        c += (unsigned int)(off[v + 1] - off[v]);
+    }
+    counts[v] = c;
+}
+
+__global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, long long cap,
+                                  const long long* merged_off, int32_t* pos, uint8_t* type_code) {
+    int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= n_nodes) return;
+    long long run = merged_off[v];
+    if (merged_off[v + 1] == run) return;
+    const size_t po = packed_pos_offset(n_nodes), to = packed_tc_offset(n_nodes, cap);
+    for (int k = 0; k < n_shards; k++) {
+        const unsigned char* sh = packed + k * shard_bytes;
+        const long long* off = reinterpret_cast<const long long*>(sh + 16);
+        const long long a = off[v], b = off[v + 1];
+        const int32_t* sp = reinterpret_cast<const int32_t*>(sh + po);
+        const uint8_t* st = sh + to;
+        for (long long i = a + lane; i < b; i += 32) {
+            pos[run + (i - a)] = sp[i];
+            type_code[run + (i - a)] = st[i];
+        }
+        run += b - a;
+    }
+}
+
 // ------------------------------------------------------------------ ingest
 // nibble-packed rows -> code planes. One thread per (row, 32-column group).
 __global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, int row_begin, int n_rows_slab, int n_rows_total,

@@ -8,7 +8,8 @@ LIB_PATH = os.path.join(HERE, "libpanman_b200.so")
 
 # every symbol include/panman_b200.h declares
 EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",
-           "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version"]
+           "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version",
+           "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream"]
 
 
 class pmb_result(C.Structure):
@@ -59,5 +60,11 @@ def load_library():
     L.pmb_algorithmic_bytes.argtypes = [vp, C.c_int]
     L.pmb_algorithmic_bytes.restype = i64
     L.pmb_version.restype = C.c_char_p
+    L.pmb_stream.argtypes = [vp]
+    L.pmb_stream.restype = vp
+    L.pmb_packed_bytes.argtypes = [i32, i64]
+    L.pmb_packed_bytes.restype = i64
+    L.pmb_pack_result.argtypes = [vp, vp, i64, vp]
+    L.pmb_merge_packed.argtypes = [vp, i32, vp, i64, vp, C.POINTER(pmb_result)]
     _lib = L
     return L
