@@ -127,6 +127,12 @@ int pmb_upload_nuc(pmb_ctx* ctx, int64_t n_cols, int32_t n_rows, const uint8_t* 
                    int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* parent_code,
                    const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base);
 int pmb_run_resident(pmb_ctx* ctx, int algo, int flags);
+/* Asynchronous form: enqueues the pass on the context's stream and returns; several passes (and the caller's own
+ * stream work ordered with pmb_stream) can be in flight. pmb_wait blocks until the stream drains and reports the
+ * status of everything since the last wait (the first error wins). The mutation staging pool is not regrown on
+ * the fly in this mode: an overflow is reported by pmb_wait (and the pool grown for the next attempt). */
+int pmb_run_resident_async(pmb_ctx* ctx, int algo, int flags);
+int pmb_wait(pmb_ctx* ctx);
 int pmb_download(pmb_ctx* ctx, pmb_result* out);
 
 /* Device-side view of the last result (for an NCCL gather straight from HBM). Pointers are device memory. */

@@ -109,6 +109,13 @@ class Context:
         self._check(self.L.pmb_run_resident(self.h, int(algo), int(flags)))
         return self.timings()
 
+    def run_resident_async(self, algo=ALGO_FITCH, flags=0):
+        self._check(self.L.pmb_run_resident_async(self.h, int(algo), int(flags)))
+
+    def wait(self) -> Timings:
+        self._check(self.L.pmb_wait(self.h))
+        return self.timings()
+
     def timings(self) -> Timings:
         t = pmb_timings()
         self._check(self.L.pmb_last_timings(self.h, C.byref(t)))

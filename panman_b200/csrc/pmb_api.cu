@@ -80,6 +80,8 @@ struct pmb_ctx {
     int n_sms = 0;
     unsigned int epoch = 0;
     unsigned int pack_seq = 0;
+    bool async_pending = false;
+    int async_groups = 1;
 
     // tree
     bool have_tree = false;
@@ -421,7 +423,7 @@ int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* le
     return PMB_OK;
 }
 
-int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
+static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     if (!c) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
@@ -437,8 +439,17 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     const bool want_states = flags & PMB_FLAG_WANT_STATES;
     if (want_states) PMB_CUDA(c->d_states_planes.ensure(size_t(P.n_nodes) * T * 64 * sizeof(uint4)));
     PMB_CUDA(c->d_dir.ensure(size_t(P.n_nodes) * T * sizeof(unsigned long long)));
-    PMB_CUDA(c->d_counters.ensure(64));
-    PMB_CUDA(c->h_counters.ensure(64));
+    if (!c->d_counters.p) {
+        PMB_CUDA(c->d_counters.ensure(64));
+        PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
+        unsigned int sticky_init[2] = {0u, 0xFFFFFFFFu};
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 16, sticky_init, 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    PMB_CUDA(c->h_counters.ensure(128));
+    {   // pinned constants for the per-run counter reset (a pageable source could serialise the host with the stream)
+        unsigned int* init = c->h_counters.as<unsigned int>() + 16;
+        init[0] = 0; init[1] = 0; init[2] = 0; init[3] = 0xFFFFFFFFu;
+    }
     PMB_CUDA(c->d_ticket.ensure(64 * sizeof(unsigned long long)));
     {
         int rcf;
@@ -510,8 +521,8 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
         rp.staging_cap = c->staging_cap;
         PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, size_t(P.n_nodes) * T * sizeof(unsigned long long), c->stream));
         PMB_CUDA(cudaMemsetAsync(c->d_node_counts.p, 0, size_t(P.n_nodes) * sizeof(unsigned int), c->stream));
-        unsigned int init[4] = {0, 0, 0, 0xFFFFFFFFu};  // pool_count (64 bit), error flags, first bad column
-        PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+        // pool_count (64 bit), error flags, first bad column
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, c->h_counters.as<unsigned int>() + 16, 16, cudaMemcpyHostToDevice, c->stream));
         const unsigned int bwd_epoch = ++c->epoch;
         PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         for (int g = 0; g < G; g++) {
@@ -542,8 +553,21 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
                                                          rp.pool_count, rp.staging_cap);
             n_launches += 3;
         }
+        sticky_status_kernel<<<1, 1, 0, c->stream>>>(rp.pool_count, rp.staging_cap, rp.error,
+                                                     reinterpret_cast<unsigned int*>(c->d_counters.as<char>() + 16));
         PMB_CUDA(cudaGetLastError());
         PMB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        if (async) {  // status, overflow handling and timings wait for pmb_wait
+            c->async_pending = true;
+            c->async_groups = G;
+            c->timings.n_launches = n_launches + 1;
+            c->timings.n_levels = P.n_levels();
+            c->last_algo = algo;
+            c->last_flags = flags;
+            c->n_mut = -1;
+            c->have_result = true;
+            return PMB_OK;
+        }
         PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
         PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_offsets.as<long long>() + P.n_nodes, 8, cudaMemcpyDeviceToHost,
                                  c->stream));
@@ -589,6 +613,57 @@ int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
     return PMB_OK;
 }
 
+int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
+    if (c && c->async_pending) {
+        int rc = pmb_wait(c);
+        if (rc) return rc;
+    }
+    return run_impl(c, algo, flags, false);
+}
+
+int pmb_run_resident_async(pmb_ctx* c, int algo, int flags) { return run_impl(c, algo, flags, true); }
+
+int pmb_wait(pmb_ctx* c) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->async_pending) return PMB_OK;
+    PMB_CUDA(cudaSetDevice(c->device));
+    const int N = c->prog.n_nodes;
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 32, c->d_offsets.as<long long>() + N, 8, cudaMemcpyDeviceToHost, c->stream));
+    PMB_CUDA(cudaStreamSynchronize(c->stream));
+    c->async_pending = false;
+    const unsigned int sticky = c->h_counters.as<unsigned int>()[4], scol = c->h_counters.as<unsigned int>()[5];
+    unsigned int sticky_init[2] = {0u, 0xFFFFFFFFu};
+    PMB_CUDA(cudaMemcpy(c->d_counters.as<char>() + 16, sticky_init, 8, cudaMemcpyHostToDevice));
+    if (sticky & 2u) { c->have_result = false; return fail(c, PMB_ERR_INTERNAL, "scheduler watchdog fired: a dependency flag never arrived"); }
+    if (sticky & 1u) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "Sankoff root has no finite cost at column %lld and no root override was given",
+                 (long long)scol + (long long)c->col_base);
+        c->have_result = false;
+        return fail(c, PMB_ERR_SANKOFF_ROOT, buf);
+    }
+    if (sticky & 4u) {
+        c->have_result = false;
+        c->staging_cap = std::max<unsigned long long>(c->staging_cap * 4, *c->h_counters.as<unsigned long long>());
+        return fail(c, PMB_ERR_INTERNAL, "the mutation staging pool overflowed during an asynchronous run; rerun (the pool was grown)");
+    }
+    c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 32);
+    PMB_CUDA(cudaEventElapsedTime(&c->timings.total_ms, c->ev[0], c->ev[3]));
+    PMB_CUDA(cudaEventElapsedTime(&c->timings.compact_ms, c->ev[2], c->ev[3]));
+    float to_bwd_end = 0.f;
+    c->timings.forward_ms = 0.f;
+    for (int g = 0; g < c->async_groups; g++) {
+        float f = 0.f;
+        PMB_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->gev_fwd[g]));
+        c->timings.forward_ms = std::max(c->timings.forward_ms, f);
+    }
+    PMB_CUDA(cudaEventElapsedTime(&to_bwd_end, c->ev[0], c->ev[2]));
+    c->timings.backward_ms = to_bwd_end - c->timings.forward_ms;
+    return PMB_OK;
+}
+
 int pmb_result_device(pmb_ctx* c, pmb_result* out) {
     if (!c || !out) return PMB_ERR_INVALID;
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
@@ -607,6 +682,10 @@ int pmb_download(pmb_ctx* c, pmb_result* out) {
     if (!c || !out) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
+    if (c->async_pending) {
+        int rcw = pmb_wait(c);
+        if (rcw) return rcw;
+    }
     PMB_CUDA(cudaSetDevice(c->device));
     const size_t n = size_t(c->n_mut), N = size_t(c->prog.n_nodes);
     PMB_CUDA(c->h_offsets.ensure((N + 1) * sizeof(int64_t)));
@@ -668,22 +747,22 @@ int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v
     if (!c || !d_packed) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
-    if (capacity < c->n_mut) return fail(c, PMB_ERR_INVALID, "pmb_pack_result: capacity below the record count");
+    if (c->n_mut >= 0 && capacity < c->n_mut) return fail(c, PMB_ERR_INVALID, "pmb_pack_result: capacity below the record count");
     PMB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
     const long long N = c->prog.n_nodes;
     unsigned char* out = static_cast<unsigned char*>(d_packed);
-    PMB_CUDA(c->h_pack_header.ensure(4 * 16));
-    // a small ring of pinned headers: several packs may be in flight before the host touches the slot again
-    static_assert(sizeof(long long) == 8, "");
-    long long* hdr = c->h_pack_header.as<long long>() + 2 * (c->pack_seq++ & 3);
-    hdr[0] = c->n_mut;
-    hdr[1] = N;
-    PMB_CUDA(cudaMemcpyAsync(out, hdr, 16, cudaMemcpyHostToDevice, st));
+    // header {n_mut, n_nodes}: n_mut straight from the device (offsets[N]) so that nothing here needs the host to
+    // know the result of a still running asynchronous pass; n_nodes from a pinned constant
+    PMB_CUDA(c->h_pack_header.ensure(16));
+    c->h_pack_header.as<long long>()[0] = N;
+    PMB_CUDA(cudaMemcpyAsync(out, c->d_offsets.as<long long>() + N, 8, cudaMemcpyDeviceToDevice, st));
+    PMB_CUDA(cudaMemcpyAsync(out + 8, c->h_pack_header.p, 8, cudaMemcpyHostToDevice, st));
     PMB_CUDA(cudaMemcpyAsync(out + 16, c->d_offsets.p, size_t(N + 1) * 8, cudaMemcpyDeviceToDevice, st));
-    if (c->n_mut) {
-        PMB_CUDA(cudaMemcpyAsync(out + packed_pos_offset(N), c->d_pos.p, size_t(c->n_mut) * 4, cudaMemcpyDeviceToDevice, st));
-        PMB_CUDA(cudaMemcpyAsync(out + packed_tc_offset(N, capacity), c->d_tc.p, size_t(c->n_mut), cudaMemcpyDeviceToDevice, st));
+    const size_t n_copy = c->n_mut >= 0 ? size_t(c->n_mut) : size_t(std::min<unsigned long long>(capacity, c->staging_cap));
+    if (n_copy) {
+        PMB_CUDA(cudaMemcpyAsync(out + packed_pos_offset(N), c->d_pos.p, n_copy * 4, cudaMemcpyDeviceToDevice, st));
+        PMB_CUDA(cudaMemcpyAsync(out + packed_tc_offset(N, capacity), c->d_tc.p, n_copy, cudaMemcpyDeviceToDevice, st));
     }
     return PMB_OK;
 }

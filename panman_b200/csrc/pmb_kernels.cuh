@@ -964,6 +964,14 @@ __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* sta
     }
 }
 
+// folds the per-run status into a word that survives until pmb_wait (asynchronous runs reset the per-run counters)
+__global__ void sticky_status_kernel(const unsigned long long* pool_count, unsigned long long staging_cap, const unsigned int* error,
+                                     unsigned int* sticky) {
+    unsigned int s = error[0] | (*pool_count > staging_cap ? 4u : 0u);
+    if (s) atomicOr(sticky, s);
+    if (error[0] & 1u) atomicMin(sticky + 1, error[1]);
+}
+
 // ------------------------------------------------------------------ merging column-range shards (multi-GPU)
 // A packed shard = {int64 n_mut, int64 n_nodes | int64 offsets[N+1] | int32 pos[cap] | uint8 type_code[cap]} (16-byte
 // aligned sections). Shards are column ranges in ascending order, so a node's merged list is the concatenation of its

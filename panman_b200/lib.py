@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libpanman_b200.so")
 # every symbol include/panman_b200.h declares
 EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",
            "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version",
-           "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream"]
+           "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream", "pmb_run_resident_async", "pmb_wait"]
 
 
 class pmb_result(C.Structure):
@@ -54,6 +54,8 @@ def load_library():
     L.pmb_run_nuc.argtypes = [vp, C.c_int, i64, i32, vp, i64, vp, vp, vp, vp, i64, C.c_int, C.POINTER(pmb_result)]
     L.pmb_upload_nuc.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64]
     L.pmb_run_resident.argtypes = [vp, C.c_int, C.c_int]
+    L.pmb_run_resident_async.argtypes = [vp, C.c_int, C.c_int]
+    L.pmb_wait.argtypes = [vp]
     L.pmb_download.argtypes = [vp, C.POINTER(pmb_result)]
     L.pmb_result_device.argtypes = [vp, C.POINTER(pmb_result)]
     L.pmb_last_timings.argtypes = [vp, C.POINTER(pmb_timings)]

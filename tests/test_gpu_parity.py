@@ -202,3 +202,75 @@ def test_caterpillar_depth(ctx, port):
     ctx.run_resident(0)
     want, _ = port.run(tree, 0, codes, pc.cpu().numpy(), n_threads=8)
     assert _same(ctx.download(), want)
+
+
+def test_async_runs_and_shard_merge(ctx, port):
+    """Two column-range shards (two contexts on this GPU, as two ranks would hold them) run asynchronously, are packed
+    (pmb_pack_result) and merged (pmb_merge_packed): the merged lists equal the single-range result."""
+    import torch
+
+    from panman_b200.distributed import column_ranges
+
+    rng = np.random.default_rng(31)
+    tree = random_tree(300, 55, "binary")
+    n_cols = 5000
+    base = rng.integers(0, 5, size=n_cols)
+    codes = np.repeat(base[None, :], tree.n_leaves, 0)
+    codes = np.where(rng.random(codes.shape) < 0.03, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+    pc = codes[0].copy()
+    want, _ = port.run(tree, 0, codes, pc, n_threads=4)
+    ranges = column_ranges(n_cols, 2)
+    shards = []
+    for a, b in ranges:
+        c = pb.Context(0)
+        c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+        c4 = pb.pack_nibbles(codes[:, a:b])
+        c.upload(b - a, tree.n_leaves, c4, c4.shape[1], np.ascontiguousarray(pc[a:b]), col_base=a)
+        for _ in range(3):  # several passes in flight, one wait
+            c.run_resident_async(pb.ALGO_FITCH)
+        shards.append(c)
+    cap = 0
+    for c in shards:
+        t = c.wait()
+        assert t.total_ms > 0
+        cap = max(cap, int(c.result_device().n_mut))
+    cap += 100
+    nbytes = shards[0].packed_bytes(cap)
+    buf = torch.empty(2 * nbytes, dtype=torch.uint8, device="cuda")
+    for k, c in enumerate(shards):
+        c.pack_result(buf[k * nbytes:(k + 1) * nbytes], cap)
+        c.wait()
+        torch.cuda.synchronize()
+    r = shards[0].merge_packed(2, buf, cap)
+    torch.cuda.synchronize()
+    N = tree.n_nodes
+
+    class _Arr:
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    off = torch.as_tensor(_Arr(r.node_offsets, N + 1, "<i8"), device="cuda").cpu().numpy()
+    n = int(off[-1])
+    pos = torch.as_tensor(_Arr(r.pos, max(n, 1), "<i4"), device="cuda")[:n].cpu().numpy()
+    tc = torch.as_tensor(_Arr(r.type_code, max(n, 1), "|u1"), device="cuda")[:n].cpu().numpy()
+    assert np.array_equal(off, want.node_offsets) and np.array_equal(pos, want.pos) and np.array_equal(tc, want.type_code)
+    for c in shards:
+        c.close()
+
+
+def test_async_overflow_is_reported(ctx):
+    rng = np.random.default_rng(5)
+    tree = random_tree(100, 7, "binary")
+    codes = rng.integers(0, 16, size=(tree.n_leaves, 2000)).astype(np.uint8)
+    c = pb.Context(0)
+    c.set_option("staging_records", 100)
+    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    c4 = pb.pack_nibbles(codes)
+    c.upload(2000, tree.n_leaves, c4, c4.shape[1], codes[0].copy())
+    c.run_resident_async(pb.ALGO_FITCH)
+    with pytest.raises(pb.PanmanError) as e:
+        c.wait()
+    assert e.value.code == -7 and "overflow" in str(e.value)
+    t = c.run_resident(pb.ALGO_FITCH)  # the synchronous entry sizes the pool and succeeds
+    assert c.download().n_mut > 100 and t.total_ms > 0
+    c.close()
