@@ -241,15 +241,20 @@ def run_b200_arm(args):
         k = shard["i"] & 1
         shard["i"] += 1
         comm, lib = shard["comm"], shard["lib"]
-        lib.wait_stream(comm)                      # the gather that last used this send buffer is done
         ctx.pack_result(shard["send"][k], shard["cap"])     # on the library's stream, right behind the pass
         comm.wait_stream(lib)
         with torch.cuda.stream(comm):
             dst = [shard["recv"][k][r * shard["bytes"]:(r + 1) * shard["bytes"]] for r in range(world)] if rank == 0 else None
             work = dist.gather(shard["send"][k], dst, dst=0, async_op=True)
             work.wait()                            # orders the comm stream after the collective; the host does not block
+            done = torch.cuda.Event()
+            done.record(comm)
             if rank == 0:
                 shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=comm.cuda_stream)
+        # The next pass starts only after the collective: the persistent pass kernels fill every SM, and an NCCL
+        # kernel that has to squeeze in beside them (on both ranks at once) stalls far longer than it runs.
+        # Rank 0's merge kernels are small and do overlap the next pass.
+        lib.wait_event(done)
 
     lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
 
