@@ -255,6 +255,38 @@ struct SankoffFold {
     }
 };
 
+// Two children (the bifurcating common case), closed form of SankoffFold<2>: with a_k, b_k = "child has excess > 0
+// at state k" (0 for a NONE child), r_k = a_k + b_k in {0,1,2} and m = min_k r_k:
+//   m = 0 (some state free in both):  e = r        -> G = a|b, H = a&b
+//   m = 1:                            e = r - 1    -> G = a&b, H = 0
+//   m = 2 (only if a&b everywhere):   e = 0        -> G = H = 0
+PMB_HD void sankoff_pair(const uint32_t g1[16], uint32_t none1, const uint32_t g2[16], uint32_t none2, uint32_t G[16],
+                         uint32_t H[16]) {
+    uint32_t any0 = 0, all2 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t a = g1[k] & ~none1, b = g2[k] & ~none2;
+        any0 |= ~(a | b);
+        all2 &= a & b;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t a = g1[k] & ~none1, b = g2[k] & ~none2;
+        G[k] = (any0 & (a | b)) | (~any0 & a & b & ~all2);
+        H[k] = any0 & a & b;
+    }
+    const uint32_t both_none = none1 & none2;
+    H[0] |= both_none;
+    G[0] &= ~both_none;
+}
+// excess>0 planes of a leaf: every state but its own code (nothing, and NONE, when the leaf is omitted)
+PMB_HD void sankoff_leaf_g(const uint32_t c[4], uint32_t present, uint32_t g[16]) {
+    uint32_t d[16];
+    decode16(c, d);
+#pragma unroll
+    for (int k = 0; k < 16; k++) g[k] = ~d[k] & present;
+}
+
 // Child pointer chosen by a parent in state P (fitchSankoff.cpp:518-529 in excess form):
 // e[s]==0 -> s ; e[s]==1 -> min(s, z) ; e[s]==2 -> z, with z the lowest zero-excess state.
 PMB_HD void sankoff_assign(const uint32_t G[16], const uint32_t H[16], const uint32_t P[4], uint32_t pvis,

@@ -578,7 +578,9 @@ __device__ __forceinline__ bool bwd_parent_slot(const RunParams& p, const BwdHea
 }
 
 // what follows the assignment of an internal node, shared by Fitch and Sankoff: its own record, the parked
-// state for later children, and its leaf children (a present leaf is always assigned its own code)
+// state for later children, and its leaf children (a present leaf is always assigned its own code).
+// The common case (every leaf present, no state dump) is straight-line for the first two leaves: one ballot each,
+// and the leaf's node id is only fetched when it really has a record.
 __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta& m, const TileCtx& tc, StageCursor& sc,
                                               const BwdHead& h, const uint4* leaf_stage, int tile, int lane,
                                               const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block) {
@@ -590,8 +592,19 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta&
         fs[128 + lane] = vis;
         if (h.b1.y & OPF_SIGNAL_F) signal_flag(p.fdone + fi, p.epoch, lane);
     }
+    const bool plain = p.states == nullptr && p.leaf_present == nullptr;
     if (p.states) store_state(p, h.b0.x, tile, lane, F, vis);
-    for (int l = 0; l < h.b1.x; l++) {
+    int l0 = 0;
+    if (plain) {
+        const int nfast = min(h.b1.x, 2);
+        for (; l0 < nfast; l0++) {
+            const uint4 c = leaf_stage[l0 * 32];
+            const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            const uint32_t mut = vis & differs4(cc, F);
+            if (__ballot_sync(FULL, mut != 0)) emit(p, sc, bwd_leaf(p, m, h.b0.w + l0).y, tile, lane, mut, F, cc);
+        }
+    }
+    for (int l = l0; l < h.b1.x; l++) {
         const int2 lf = bwd_leaf(p, m, h.b0.w + l);  // slot, node
         uint4 c;
         if (l < 2) c = leaf_stage[l * 32];
@@ -763,8 +776,55 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
             const int4 w0 = m.ops[2 * (op - m.wb)];
             cp_async_wait_stage<FWD_DEPTH>(ck.op_end - 1 - op);
             uint4* st = ring_l + stage * STAGE;
-            bool ok;
-            if (MAXB == 2 || w0.w == 2) ok = sankoff_forward_op<2>(p, m, tc, w0, op, st, lane, accG, accH, tr);
+            bool ok = true;
+            const int type = (w0.z >> OPF_TYPE_SHIFT) & 15;
+            if (type != FT_GENERIC) {
+                // two children: closed form (plane_math.h sankoff_pair)
+                const int4 w1 = m.ops[2 * (op - m.wb) + 1];
+                uint32_t g1[16], g2[16], n1, n2;
+                auto leaf_child = [&](int slot_k, uint32_t ref, uint32_t g[16], uint32_t& none) {
+                    const uint4 c = st[slot_k * 32];
+                    uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                    uint32_t present = leaf_present_mask(p, ref & REF_IDX_MASK);
+                    if ((p.flags & RUN_BLOCK_MODE) && !present) {  // omitted block leaf = "absent" state (:711-714)
+                        cc[0] = cc[1] = cc[2] = cc[3] = 0;
+                        present = FULL;
+                    }
+                    sankoff_leaf_g(cc, present, g);
+                    none = ~present;
+                };
+                auto set_child = [&](uint32_t ref, uint32_t g[16], uint32_t& none) {
+                    uint32_t h0;
+                    if (fwd_set_prefetched(ref, op)) {
+                        stage_set16(st, g);
+                        h0 = st[(2 + 4) * 32].x;
+                    } else {
+                        const uint4* row = tc.sets + (size_t)(ref & REF_IDX_MASK) * 256;
+                        row_set16(row, g);
+                        h0 = ld_l2(row + 128).x;
+                    }
+                    none = h0 & ~g[0];
+                };
+                auto acc_child = [&](uint32_t g[16], uint32_t& none) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) g[k] = accG[k];
+                    none = sankoff_none(accG, accH);
+                };
+                if (type == FT_LEAF_LEAF) {
+                    leaf_child(0, (uint32_t)w1.x, g1, n1);
+                    leaf_child(1, (uint32_t)w1.y, g2, n2);
+                } else if (type == FT_LEAF_ACC) {
+                    leaf_child(0, (uint32_t)w1.x, g1, n1);
+                    acc_child(g2, n2);
+                } else if (type == FT_LEAF_INT) {
+                    leaf_child(0, (uint32_t)w1.x, g1, n1);
+                    set_child((uint32_t)w1.y, g2, n2);
+                } else {
+                    set_child((uint32_t)w1.x, g1, n1);
+                    acc_child(g2, n2);
+                }
+                sankoff_pair(g1, n1, g2, n2, accG, accH);
+            } else if (MAXB == 2 || w0.w == 2) ok = sankoff_forward_op<2>(p, m, tc, w0, op, st, lane, accG, accH, tr);
             else if (MAXB == 4 || w0.w == 4) ok = sankoff_forward_op<4>(p, m, tc, w0, op, st, lane, accG, accH, tr);
             else if (MAXB == 8 || w0.w == 8) ok = sankoff_forward_op<8>(p, m, tc, w0, op, st, lane, accG, accH, tr);
             else ok = sankoff_forward_op<20>(p, m, tc, w0, op, st, lane, accG, accH, tr);

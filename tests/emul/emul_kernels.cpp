@@ -175,6 +175,34 @@ void forward_item(Emu& E, int chunk, int tile) {
                 }
                 store16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, acc[lane]);
             } else {
+                const int stype = (f.flags >> OPF_TYPE_SHIFT) & 15;
+                if (stype != FT_GENERIC) {
+                    uint32_t g1[16], g2[16], n1, n2;
+                    auto leaf_child = [&](int r, uint32_t g[16], uint32_t& none) {
+                        uint32_t idx = E.P.refs[f.ref_begin + r] & REF_IDX_MASK;
+                        U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
+                        uint32_t cc[4] = {c.x, c.y, c.z, c.w}, pr = present_mask(E, idx);
+                        if ((E.flags & 1) && !pr) { cc[0] = cc[1] = cc[2] = cc[3] = 0; pr = 0xFFFFFFFFu; }
+                        sankoff_leaf_g(cc, pr, g);
+                        none = ~pr;
+                    };
+                    auto set_child = [&](int r, uint32_t g[16], uint32_t& none) {
+                        uint32_t ref = E.P.refs[f.ref_begin + r], idx = ref & REF_IDX_MASK;
+                        if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                        const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256;
+                        load16(base, lane, g);
+                        none = base[128 + lane].x & ~g[0];
+                    };
+                    auto acc_child = [&](uint32_t g[16], uint32_t& none) {
+                        for (int k = 0; k < 16; k++) g[k] = acc[lane][k];
+                        none = sankoff_none(acc[lane], accH[lane]);
+                    };
+                    if (stype == FT_LEAF_LEAF) { leaf_child(0, g1, n1); leaf_child(1, g2, n2); }
+                    else if (stype == FT_LEAF_ACC) { leaf_child(0, g1, n1); acc_child(g2, n2); }
+                    else if (stype == FT_LEAF_INT) { leaf_child(0, g1, n1); set_child(1, g2, n2); }
+                    else { set_child(0, g1, n1); acc_child(g2, n2); }
+                    sankoff_pair(g1, n1, g2, n2, acc[lane], accH[lane]);
+                } else
                 switch (f.max_arity_bits) {
                 case 2: sankoff_fwd_op<2>(E, f, tile, lane, acc[lane], accH[lane]); break;
                 case 4: sankoff_fwd_op<4>(E, f, tile, lane, acc[lane], accH[lane]); break;
