@@ -89,7 +89,7 @@ struct pmb_ctx {
     std::vector<int32_t> child_off, child_idx, leaf_row;
     TreeProgram prog;
     int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1;
-    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order, d_row_slot;
+    DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order, d_row_slot, d_deps;
 
     // resident input
     bool have_input = false;
@@ -167,6 +167,7 @@ int ensure_program(pmb_ctx* c) {
     if ((rc = upload_vec(c, c->d_bwd_order, c->prog.bwd_order))) return rc;
     if ((rc = upload_vec(c, c->d_level_order, c->prog.level_order))) return rc;
     if ((rc = upload_vec(c, c->d_row_slot, c->prog.row_slot))) return rc;
+    if ((rc = upload_vec(c, c->d_deps, c->prog.deps))) return rc;
     PMB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above may be rebuilt before the copies ran
     c->prog_chunk_nodes = k;
     c->prog_inline_nodes = inl;
@@ -235,8 +236,8 @@ int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParam
     const TreeProgram& P = c->prog;
     const size_t fwd_smem = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 4) * 32 + FWD_META_U4) * sizeof(uint4);
     const size_t fwd_smem_s = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 5) * 32 + FWD_META_U4) * sizeof(uint4);
-    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (4 + 2) * 32 + BWD_META_U4) * sizeof(uint4);
-    const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (8 + 2) * 32 + BWD_META_U4) * sizeof(uint4);
+    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (4 + 2) * 32 + BWD_META_U4 + BWD_STACK_U4) * sizeof(uint4);
+    const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (8 + 2) * 32 + BWD_META_U4 + BWD_STACK_U4) * sizeof(uint4);
     if (algo == PMB_ALGO_FITCH)
         return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel, fwd_smem, rp, true, n_launches)
                        : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel, bwd_smem_f, rp, false, n_launches);
@@ -304,7 +305,7 @@ void pmb_destroy(pmb_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_bwd_order,
-                          &c->d_level_order, &c->d_row_slot, &c->d_block_sums, &c->d_leaf_planes,
+                          &c->d_level_order, &c->d_row_slot, &c->d_deps, &c->d_block_sums, &c->d_leaf_planes,
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
@@ -473,6 +474,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     rp.bwd_ops = c->d_bwd_ops.as<BwdOp>();
     rp.bwd_leaves = c->d_bwd_leaves.as<BwdLeaf>();
     rp.chunks = c->d_chunks.as<Chunk>();
+    rp.deps = c->d_deps.as<int>();
     rp.leaf_planes = c->d_leaf_planes.as<uint4>();
     rp.leaf_present = c->have_present ? c->d_present.as<uint8_t>() : nullptr;
     rp.sets = c->d_sets.as<uint4>();

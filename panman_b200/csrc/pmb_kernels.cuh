@@ -31,6 +31,7 @@ struct RunParams {
     const BwdOp* bwd_ops;
     const BwdLeaf* bwd_leaves;
     const Chunk* chunks;
+    const int* deps;              // forward dependency lists of the chunks
     const uint4* leaf_planes;
     const uint8_t* leaf_present;  // device, n_rows bytes, or nullptr = all present
     uint4* sets;
@@ -176,6 +177,40 @@ __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, 
     if (v == epoch) return true;
     return wait_flag_slow(flag, epoch, error, lane, &tr.waited);
 }
+// Forward items wait ONCE, when they start, for every row of other chunks they will read (each lane polls one
+// flag per round), so the op loop itself contains no acquire at all.
+__device__ __noinline__ bool wait_deps_slow(const unsigned* flag, unsigned epoch, unsigned* error, unsigned* waited) {
+    unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    bool mine = flag == nullptr || ld_acquire(flag) == epoch;
+    bool ok = true;
+    while (!__all_sync(FULL, mine)) {
+        __nanosleep(64);
+        if (!mine) mine = ld_acquire(flag) == epoch;
+        if ((++spins & 255u) == 0) {
+            bool dead = (*reinterpret_cast<volatile unsigned*>(error) & 2u) || global_ns() - t0 > 20000000000ull;
+            if (__any_sync(FULL, dead)) {
+                atomicOr(error, 2u);
+                ok = false;
+                break;
+            }
+        }
+    }
+    *waited += unsigned(global_ns() - t0);
+    return ok;
+}
+__device__ __forceinline__ bool wait_chunk_deps(const RunParams& p, const Chunk& ck, const unsigned* done_tile, int lane, TraceItem& tr) {
+    for (int base = 0; base < ck.dep_count; base += 32) {
+        const int i = base + lane;
+        const unsigned* flag = i < ck.dep_count ? done_tile + __ldg(p.deps + ck.dep_begin + i) : nullptr;
+        const bool mine = flag == nullptr || ld_acquire(flag) == p.epoch;
+        if (!__all_sync(FULL, mine)) {
+            if (!wait_deps_slow(flag, p.epoch, p.error, &tr.waited)) return false;
+        }
+    }
+    return true;
+}
+
 // Publish: every lane's earlier stores happen-before the release store of lane 0 (warp barrier + release).
 __device__ __forceinline__ void signal_flag(unsigned* flag, unsigned epoch, int lane) {
     __syncwarp();
@@ -287,6 +322,7 @@ __device__ __forceinline__ void cp_async_wait_stage(int ops_left_after) {
 constexpr int META_OPS = 32, META_REFS = 96, META_LEAVES = 64;
 constexpr int FWD_META_U4 = 2 * META_OPS + META_REFS / 4;
 constexpr int BWD_META_U4 = 2 * META_OPS + META_LEAVES / 2;
+constexpr int BWD_STACK_U4 = BWD_STACK_DEPTH * FSLOT_WORDS / 4;  // per-warp stack of parked assigned states
 
 struct FwdMeta {
     int4* ops;
@@ -374,13 +410,10 @@ template <int JS, int JROW>
 __device__ __forceinline__ bool fwd_issue_set(const RunParams& p, const TileCtx& tc, uint4* st, uint32_t ref, int op, int lane,
                                               TraceItem& tr) {
     if (!fwd_set_prefetched(ref, op)) return true;
-    const uint32_t idx = ref & REF_IDX_MASK;
-    bool ok = true;
-    if (ref & REF_EXT) ok = wait_flag(tc.done + idx, p.epoch, p.error, lane, tr);
-    const uint4* row = tc.sets + (size_t)idx * (JROW * 32);
+    const uint4* row = tc.sets + (size_t)(ref & REF_IDX_MASK) * (JROW * 32);  // external rows: verified at item start
 #pragma unroll
     for (int j = 0; j < JS; j++) cp_async16(st + (2 + j) * 32, row + j * 32);
-    return ok;
+    return true;
 }
 // forward: queue the inputs of `op` into stage `st` (lane-offset pointer) and commit one group: the first two leaf
 // rows and, when prefetchable, the first set row. JS = vectors of a set row the consumer needs, JROW = row length.
@@ -454,6 +487,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<4>(p, tile, lane);
+        if (!wait_chunk_deps(p, ck, tc.done, lane, tr)) return;
         uint32_t acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0;
@@ -515,9 +549,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         if (ni == 0 && fwd_set_prefetched(ref, op)) {
                             stage_set16(st, S);
                         } else {
-                            if (ref & REF_EXT) {
-                                if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return;
-                            }
                             row_set16(tc.sets + (size_t)idx * 128, S);
                         }
                         ni++;
@@ -582,9 +613,14 @@ __device__ __forceinline__ bool bwd_parent_slot(const RunParams& p, const BwdHea
 // The common case (every leaf present, no state dump) is straight-line for the first two leaves: one ballot each,
 // and the leaf's node id is only fetched when it really has a record.
 __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta& m, const TileCtx& tc, StageCursor& sc,
-                                              const BwdHead& h, const uint4* leaf_stage, int tile, int lane,
+                                              const BwdHead& h, const uint4* leaf_stage, uint32_t* stack, int tile, int lane,
                                               const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block) {
     emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
+    if (h.b1.y & OPF_PUSH) {  // a later op of this chunk needs this state: park it in the warp's shared-memory stack
+        uint32_t* e = stack + ((h.b1.y >> OPF_PUSH_SHIFT) & 15) * FSLOT_WORDS;
+        reinterpret_cast<uint4*>(e)[lane] = make_uint4(F[0], F[1], F[2], F[3]);
+        e[128 + lane] = vis;
+    }
     if (h.b0.z >= 0) {
         const size_t fi = fslot_index(p, h.b0.z, tile);
         uint32_t* fs = p.fstore + fi * FSLOT_WORDS;
@@ -627,12 +663,13 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta&
 // ------------------------------------------------------------------ Fitch backward + mutation detection
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
-    constexpr int J = 4, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4;
+    constexpr int J = 4, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4 + BWD_STACK_U4;
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
     BwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
     m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
+    uint32_t* stack = reinterpret_cast<uint32_t*>(ring + BWD_DEPTH * STAGE + BWD_META_U4);
     uint4* const ring_l = ring + lane;
     ItemIter it;
     TraceItem tr;
@@ -655,6 +692,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             if (h.b0.y == PARENT_ACC) {
                 P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
                 pvis = accVis;
+            } else if (h.b0.y <= PARENT_STACK0) {
+                const uint32_t* e = stack + (PARENT_STACK0 - h.b0.y) * FSLOT_WORDS;
+                const uint4 a = reinterpret_cast<const uint4*>(e)[lane];
+                pvis = e[128 + lane];
+                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
             } else if (h.b0.y >= 0) {
                 if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
             }
@@ -685,7 +727,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             } else {
                 fitch_assign(S, P, pvis, F, vis);
             }
-            bwd_finish_op(p, m, tc, sc, h, st + J * 32, tile, lane, P, F, vis, false);
+            bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, false);
             // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
             if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
             stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
@@ -728,9 +770,6 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Fwd
                 stage_set16(st, G);
                 h0 = st[(2 + 4) * 32].x;
             } else {
-                if (ref & REF_EXT) {
-                    if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return false;
-                }
                 const uint4* row = tc.sets + (size_t)idx * 256;
                 row_set16(row, G);
                 h0 = ld_l2(row + 128).x;
@@ -763,6 +802,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<8>(p, tile, lane);
+        if (!wait_chunk_deps(p, ck, tc.done, lane, tr)) return;
         uint32_t accG[16], accH[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
@@ -848,12 +888,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
 // ------------------------------------------------------------------ Sankoff backward + mutation detection
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
-    constexpr int J = 8, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4;
+    constexpr int J = 8, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4 + BWD_STACK_U4;
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
     BwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
     m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
+    uint32_t* stack = reinterpret_cast<uint32_t*>(ring + BWD_DEPTH * STAGE + BWD_META_U4);
     uint4* const ring_l = ring + lane;
     ItemIter it;
     TraceItem tr;
@@ -876,6 +917,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
             if (h.b0.y == PARENT_ACC) {
                 P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
                 pvis = accVis;
+            } else if (h.b0.y <= PARENT_STACK0) {
+                const uint32_t* e = stack + (PARENT_STACK0 - h.b0.y) * FSLOT_WORDS;
+                const uint4 a = reinterpret_cast<const uint4*>(e)[lane];
+                pvis = e[128 + lane];
+                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
             } else if (h.b0.y >= 0) {
                 if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
             }
@@ -904,7 +950,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
                 sankoff_assign(G, H, P, pvis, F, vis);
             }
             // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
-            bwd_finish_op(p, m, tc, sc, h, st + J * 32, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
+            bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
             if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
             stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];

@@ -195,7 +195,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     int32_t op = 0;
     for (int32_t oi : fwd_order) {
         TmpChunk& c = tmp[oi];
-        Chunk ck{op, op + int32_t(c.nodes.size())};
+        Chunk ck{op, op + int32_t(c.nodes.size()), 0, 0};
         for (int32_t v : c.nodes) P.node_op[v] = op++;
         P.chunks.push_back(ck);
     }
@@ -298,6 +298,56 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         }
     }
     P.max_arity = max_arity;
+
+    // ---- forward dependencies per chunk (external rows it reads) ----
+    for (Chunk& ck : P.chunks) {
+        ck.dep_begin = int32_t(P.deps.size());
+        for (int32_t i = ck.op_begin; i < ck.op_end; i++) {
+            const FwdOp& f = P.fwd_ops[i];
+            for (int32_t r = 0; r < f.n_refs; r++) {
+                const uint32_t ref = P.refs[f.ref_begin + r];
+                if ((ref >> 30) == REF_INT && (ref & REF_EXT)) P.deps.push_back(int32_t(ref & REF_IDX_MASK));
+            }
+        }
+        ck.dep_count = int32_t(P.deps.size()) - ck.dep_begin;
+    }
+
+    // ---- backward: parents inside the chunk are served from a per-warp shared-memory stack ----
+    // Ops run in reverse; an op whose state is needed by a same-chunk child other than the very next op parks it in
+    // stack entry d = number of such states currently parked (they are consumed strictly last-in-first-out because
+    // the children's subtrees nest). Deeper than BWD_STACK_DEPTH (or needed by another chunk): the global slot.
+    {
+        std::vector<int32_t> pending(n_internal, 0);   // same-chunk non-ACC children still to come (reverse order)
+        std::vector<int32_t> entry(n_internal, -1);
+        for (const Chunk& ck : P.chunks) {
+            for (int32_t i = ck.op_begin; i < ck.op_end; i++) {
+                int32_t v = op_node[i];
+                if (v == root) continue;
+                int32_t pop = P.node_op[parent[v]];
+                if (pop >= ck.op_begin && pop < ck.op_end && pop != i + 1) pending[pop]++;
+            }
+            int32_t depth = 0;
+            for (int32_t i = ck.op_end - 1; i >= ck.op_begin; i--) {
+                BwdOp& b = P.bwd_ops[i];
+                int32_t v = op_node[i];
+                if (v != root) {
+                    int32_t pop = P.node_op[parent[v]];
+                    bool same = pop >= ck.op_begin && pop < ck.op_end;
+                    if (same && pop != i + 1 && entry[pop] >= 0) {
+                        b.parent_ref = PARENT_STACK0 - entry[pop];
+                        if (--pending[pop] == 0) depth--;   // last reader: the entry is free again
+                    } else if (same && pop != i + 1) {
+                        --pending[pop];
+                    }
+                }
+                if (pending[i] > 0 && depth < BWD_STACK_DEPTH) {
+                    entry[i] = depth++;
+                    b.flags |= OPF_PUSH | (entry[i] << OPF_PUSH_SHIFT);
+                    if (!ext_child[i]) b.fslot_out = -1;    // nobody reads the global slot
+                }
+            }
+        }
+    }
     return "";
 }
 

@@ -28,13 +28,18 @@ namespace pmb {
 enum : uint32_t { REF_INT = 0u, REF_LEAF = 1u, REF_ACC = 2u };  // top 2 bits of a forward child ref
 constexpr uint32_t REF_EXT = 1u << 29;                          // REF_INT written by another chunk: wait for its flag
 constexpr uint32_t REF_IDX_MASK = (1u << 29) - 1u;
-enum : int32_t { PARENT_ACC = -1, PARENT_ROOT = -2 };           // BwdOp::parent_ref, else an fslot >= 0
+// BwdOp::parent_ref: >= 0 a global state slot (fslot); PARENT_ACC the previous op's registers; PARENT_ROOT the
+// per-column parameters; <= PARENT_STACK0 entry (PARENT_STACK0 - parent_ref) of the warp's shared-memory state stack
+enum : int32_t { PARENT_ACC = -1, PARENT_ROOT = -2, PARENT_STACK0 = -16 };
+constexpr int32_t BWD_STACK_DEPTH = 5;   // entries of the per-warp state stack (640 B each)
 enum : int32_t {
     OPF_ROOT = 1,
     OPF_SIGNAL = 2,      // forward: this op is a chunk root, publish its done flag after the store
     OPF_PARENT_EXT = 4,  // backward: the parent's state slot is written by another chunk, wait for it
     OPF_SIGNAL_F = 8,    // backward: another chunk reads this op's state slot, publish after the store
-    OPF_TYPE_SHIFT = 8   // forward: bits 8..11 hold the op's shape (FwdType) for the fast paths
+    OPF_TYPE_SHIFT = 8,  // forward: bits 8..11 hold the op's shape (FwdType) for the fast paths
+    OPF_PUSH = 16,       // backward: park this op's assigned state in the warp's stack entry (flags >> OPF_PUSH_SHIFT) & 15
+    OPF_PUSH_SHIFT = 12
 };
 // shape of a forward op; refs are stored in the order named (leaves first, then internal children heavy -> light)
 enum FwdType : int32_t { FT_GENERIC = 0, FT_LEAF_LEAF = 1, FT_LEAF_ACC = 2, FT_LEAF_INT = 3, FT_INT_ACC = 4 };
@@ -65,6 +70,7 @@ struct BwdLeaf {
 
 struct Chunk {
     int32_t op_begin, op_end;
+    int32_t dep_begin, dep_count;  // forward: ops of other chunks whose rows this chunk reads (TreeProgram::deps)
 };
 
 struct TreeProgram {
@@ -76,6 +82,7 @@ struct TreeProgram {
     std::vector<BwdOp> bwd_ops;
     std::vector<BwdLeaf> bwd_leaves;
     std::vector<Chunk> chunks;                // in forward ticket order (see below)
+    std::vector<int32_t> deps;                // per chunk: external child ops, waited for once when the item starts
     // Ticket orders of the persistent kernels. Both are topological for their pass, so an item only waits for
     // smaller tickets. Forward = chunks[] order itself: critical-path list scheduling, among the chunks whose inputs
     // are all scheduled take the one with the longest remaining chain of ops up to the root. Backward = bwd_order:

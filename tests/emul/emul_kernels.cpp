@@ -110,6 +110,9 @@ void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16
 void forward_item(Emu& E, int chunk, int tile) {
     const Chunk ck = E.P.chunks[chunk];
     const size_t T = E.T;
+    // the kernels wait for every external row once, when the item starts
+    for (int i = 0; i < ck.dep_count; i++)
+        if (E.done[(size_t)tile * E.P.n_internal + E.P.deps[ck.dep_begin + i]] != 1) E.order_violation = true;
     static thread_local uint32_t acc[32][16], accH[32][16];
     memset(acc, 0, sizeof acc);
     memset(accH, 0, sizeof accH);
@@ -222,6 +225,8 @@ void backward_item(Emu& E, int chunk, int tile) {
     const Chunk ck = E.P.chunks[chunk];
     const size_t T = E.T;
     uint32_t accF[32][4] = {}, accVis[32] = {};
+    static thread_local uint32_t stack[BWD_STACK_DEPTH][160];
+    for (auto& e : stack) for (auto& w : e) w = 0xDEADBEEFu;
     const int J = E.algo == 0 ? 128 : 256;
     for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
         const BwdOp b = E.P.bwd_ops[op];
@@ -258,6 +263,10 @@ void backward_item(Emu& E, int chunk, int tile) {
                 if (b.parent_ref == PARENT_ACC) {
                     for (int k = 0; k < 4; k++) P[k] = accF[lane][k];
                     pvis = accVis[lane];
+                } else if (b.parent_ref <= PARENT_STACK0) {
+                    const uint32_t* e = stack[PARENT_STACK0 - b.parent_ref];
+                    for (int k = 0; k < 4; k++) P[k] = e[4 * lane + k];
+                    pvis = e[128 + lane];
                 } else {
                     if ((b.flags & OPF_PARENT_EXT) && E.fdone[(size_t)tile * std::max(1, E.P.n_fslots) + b.parent_ref] != 1) E.order_violation = true;
                     const uint32_t* fs = E.fstore.data() + ((size_t)tile * std::max(1, E.P.n_fslots) + b.parent_ref) * 160;
@@ -271,6 +280,11 @@ void backward_item(Emu& E, int chunk, int tile) {
             wm.mut[lane] = vis & differs4(F, P);
             for (int k = 0; k < 4; k++) { wm.P[lane][k] = P[k]; wm.F[lane][k] = F[k]; Fw[lane][k] = F[k]; }
             visw[lane] = vis;
+            if (b.flags & OPF_PUSH) {
+                uint32_t* e = stack[(b.flags >> OPF_PUSH_SHIFT) & 15];
+                for (int k = 0; k < 4; k++) e[4 * lane + k] = F[k];
+                e[128 + lane] = vis;
+            }
             if (b.fslot_out >= 0) {
                 uint32_t* fs = E.fstore.data() + ((size_t)tile * std::max(1, E.P.n_fslots) + b.fslot_out) * 160;
                 reinterpret_cast<U4*>(fs)[lane] = U4{F[0], F[1], F[2], F[3]};

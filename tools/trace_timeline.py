@@ -22,6 +22,9 @@ def main():
     ap.add_argument("--chunk-nodes", type=int, default=0)
     ap.add_argument("--col-groups", type=int, default=1)
     ap.add_argument("--bins", type=int, default=24)
+    ap.add_argument("--last", type=int, default=12)
+    ap.add_argument("--window", type=float, default=30.0)
+    ap.add_argument("--dump", default="")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.config]
     tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
@@ -45,6 +48,8 @@ def main():
     ctx.L.pmb_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
     n = ctx.L.pmb_debug_trace(ctx.h, buf.ctypes.data, len(buf))
     rec = buf[:n].reshape(-1, 4)
+    if args.dump:
+        np.save(args.dump, rec)
     half = len(rec) // 2
     origin = rec[rec[:, 0] > 0, 0].min()
     for name, r in (("forward", rec[:half]), ("backward", rec[half:])):
@@ -69,6 +74,17 @@ def main():
         print("   time(us)  " + " ".join(f"{e:6.0f}" for e in edges[:-1]))
         print("   warps     " + " ".join(f"{x:6.0f}" for x in line_a))
         print("   ~waiting  " + " ".join(f"{x:6.0f}" for x in line_w))
+        # the items that finish last: which chunks are they, how long did they run and wait
+        chunk = (r[:, 2] >> np.uint64(32)).astype(np.int64)
+        tile = (r[:, 2] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        order = np.argsort(-t1)[:args.last]
+        print(f"   last {args.last} items to finish (end us, start us, waited us, chunk, tile):")
+        print("   " + "  ".join(f"({t1[i]:.0f},{t0[i]:.0f},{waited[i]:.0f},c{chunk[i]},t{tile[i]})" for i in order))
+        # per-chunk summary of the late finishers
+        late = t1 > (t1.max() - args.window)
+        cs, counts = np.unique(chunk[late], return_counts=True)
+        print(f"   chunks with items finishing in the last {args.window:.0f} us: {len(cs)}; "
+              + ", ".join(f"c{c}x{n}" for c, n in list(zip(cs, counts))[:40]))
     ctx.close()
 
 
