@@ -177,38 +177,44 @@ __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, 
     if (v == epoch) return true;
     return wait_flag_slow(flag, epoch, error, lane, &tr.waited);
 }
-// Forward items wait ONCE, when they start, for every row of other chunks they will read (each lane polls one
-// flag per round), so the op loop itself contains no acquire at all.
-__device__ __noinline__ bool wait_deps_slow(const unsigned* flag, unsigned epoch, unsigned* error, unsigned* waited) {
-    unsigned long long t0 = global_ns();
+// Forward dependencies: a chunk lists the external rows it reads in consumption order (Chunk::dep_*), and an
+// external ref names its ordinal k in that list. The warp keeps `upto` = number of leading dependencies known to be
+// published; when ref k is not covered yet, all 32 lanes poll the next 32 flags at once, so one L2 round trip (one
+// acquire) usually verifies the dependencies of many upcoming ops -- the per-op acquire of the earlier version was
+// what made the top-of-tree chain slow (profiles/r01_v5). Consumption stays progressive: an item starts working
+// before its later inputs exist.
+struct DepCursor {
+    int upto = 0;
+};
+__device__ __forceinline__ bool wait_dep(const RunParams& p, const Chunk& ck, const unsigned* done_tile, DepCursor& dc, int k,
+                                         int lane, TraceItem& tr) {
+    if (k < dc.upto) return true;
+    unsigned long long t0 = 0;
     unsigned spins = 0;
-    bool mine = flag == nullptr || ld_acquire(flag) == epoch;
-    bool ok = true;
-    while (!__all_sync(FULL, mine)) {
+    for (;;) {
+        const int i = dc.upto + lane;
+        bool ok = false;
+        if (i < ck.dep_count) ok = ld_acquire(done_tile + __ldg(p.deps + ck.dep_begin + i)) == p.epoch;
+        const unsigned b = __ballot_sync(FULL, ok);
+        dc.upto += (b == FULL) ? 32 : (__ffs(~b) - 1);
+        if (k < dc.upto) break;
+        if (spins == 0) t0 = global_ns();
         __nanosleep(64);
-        if (!mine) mine = ld_acquire(flag) == epoch;
         if ((++spins & 255u) == 0) {
-            bool dead = (*reinterpret_cast<volatile unsigned*>(error) & 2u) || global_ns() - t0 > 20000000000ull;
+            bool dead = (*reinterpret_cast<volatile unsigned*>(p.error) & 2u) || global_ns() - t0 > 20000000000ull;
             if (__any_sync(FULL, dead)) {
-                atomicOr(error, 2u);
-                ok = false;
-                break;
+                atomicOr(p.error, 2u);
+                return false;
             }
         }
     }
-    *waited += unsigned(global_ns() - t0);
-    return ok;
-}
-__device__ __forceinline__ bool wait_chunk_deps(const RunParams& p, const Chunk& ck, const unsigned* done_tile, int lane, TraceItem& tr) {
-    for (int base = 0; base < ck.dep_count; base += 32) {
-        const int i = base + lane;
-        const unsigned* flag = i < ck.dep_count ? done_tile + __ldg(p.deps + ck.dep_begin + i) : nullptr;
-        const bool mine = flag == nullptr || ld_acquire(flag) == p.epoch;
-        if (!__all_sync(FULL, mine)) {
-            if (!wait_deps_slow(flag, p.epoch, p.error, &tr.waited)) return false;
-        }
-    }
+    if (spins) tr.waited += unsigned(global_ns() - t0);
     return true;
+}
+// row of a set reference: direct, or through the dependency list for an external ref
+__device__ __forceinline__ uint32_t ref_row(const RunParams& p, const Chunk& ck, uint32_t ref) {
+    const uint32_t v = ref & REF_IDX_MASK;
+    return (ref & REF_EXT) ? (uint32_t)__ldg(p.deps + ck.dep_begin + v) : v;
 }
 
 // Publish: every lane's earlier stores happen-before the release store of lane 0 (warp barrier + release).
@@ -302,8 +308,17 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n gro
     }
 }
 
-constexpr int FWD_DEPTH = 4;       // forward: stage = 2 leaf rows + one child set row (3 KB Fitch / 3.5 KB Sankoff)
-constexpr int BWD_DEPTH = 3;       // backward: stage = set row + 2 leaf rows           (3 KB Fitch / 5 KB Sankoff)
+#ifndef PMB_BWD_DEPTH
+#define PMB_BWD_DEPTH 3
+#endif
+#ifndef PMB_FWD_DEPTH
+#define PMB_FWD_DEPTH 4
+#endif
+#ifndef PMB_META_OPS
+#define PMB_META_OPS 32
+#endif
+constexpr int FWD_DEPTH = PMB_FWD_DEPTH;  // forward: stage = 2 leaf rows + one child set row (3 KB Fitch / 3.5 KB Sankoff)
+constexpr int BWD_DEPTH = PMB_BWD_DEPTH;  // backward: stage = set row + 2 leaf rows           (3 KB Fitch / 5 KB Sankoff)
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -319,7 +334,7 @@ __device__ __forceinline__ void cp_async_wait_stage(int ops_left_after) {
 // (profiles/r01_v3: the top stall in both passes). Each warp therefore keeps a window of its chunk's metadata in
 // shared memory, refilled with a few coalesced loads every META_OPS - depth ops. Records are 32 bytes and carry
 // their first two references inline, so the bifurcating common case is straight-line code.
-constexpr int META_OPS = 32, META_REFS = 96, META_LEAVES = 64;
+constexpr int META_OPS = PMB_META_OPS, META_REFS = 3 * PMB_META_OPS, META_LEAVES = 2 * PMB_META_OPS;
 constexpr int FWD_META_U4 = 2 * META_OPS + META_REFS / 4;
 constexpr int BWD_META_U4 = 2 * META_OPS + META_LEAVES / 2;
 constexpr int BWD_STACK_U4 = BWD_STACK_DEPTH * FSLOT_WORDS / 4;  // per-warp stack of parked assigned states
@@ -334,17 +349,19 @@ __device__ __forceinline__ void fwd_meta_load(const RunParams& p, FwdMeta& m, in
     __syncwarp();  // all lanes are done with the previous window
     m.wb = wb;
     int4 h0 = make_int4(0, 0, 0, 0), h1 = h0;
-    if (wb + lane < op_end) {
+    if (lane < META_OPS && wb + lane < op_end) {
         h0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + wb + lane));
         h1 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + wb + lane) + 1);
     }
-    m.ops[2 * lane] = h0;
-    m.ops[2 * lane + 1] = h1;
+    if (lane < META_OPS) {
+        m.ops[2 * lane] = h0;
+        m.ops[2 * lane + 1] = h1;
+    }
     m.rb = (unsigned)__shfl_sync(FULL, h0.x, 0);
 #pragma unroll
-    for (int k = 0; k < META_REFS / 32; k++) {
-        const unsigned i = m.rb + lane + 32 * k;
-        m.refs[lane + 32 * k] = i < (unsigned)p.n_refs_total ? __ldg(p.refs + i) : 0u;
+    for (int d = lane; d < META_REFS; d += 32) {
+        const unsigned i = m.rb + d;
+        m.refs[d] = i < (unsigned)p.n_refs_total ? __ldg(p.refs + i) : 0u;
     }
     __syncwarp();
 }
@@ -363,17 +380,19 @@ __device__ __forceinline__ void bwd_meta_load(const RunParams& p, BwdMeta& m, in
     __syncwarp();
     m.lo = max(op_begin, top - (META_OPS - 1));
     int4 h0 = make_int4(0, 0, 0, 0), h1 = h0;
-    if (m.lo + lane <= top) {
+    if (lane < META_OPS && m.lo + lane <= top) {
         h0 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + m.lo + lane));
         h1 = __ldg(reinterpret_cast<const int4*>(p.bwd_ops + m.lo + lane) + 1);
     }
-    m.ops[2 * lane] = h0;
-    m.ops[2 * lane + 1] = h1;
+    if (lane < META_OPS) {
+        m.ops[2 * lane] = h0;
+        m.ops[2 * lane + 1] = h1;
+    }
     m.lb = (unsigned)__shfl_sync(FULL, h0.w, 0);
 #pragma unroll
-    for (int k = 0; k < META_LEAVES / 32; k++) {
-        const unsigned i = m.lb + lane + 32 * k;
-        m.leaves[lane + 32 * k] = i < (unsigned)p.n_rows ? __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + i)) : make_int2(0, 0);
+    for (int d = lane; d < META_LEAVES; d += 32) {
+        const unsigned i = m.lb + d;
+        m.leaves[d] = i < (unsigned)p.n_rows ? __ldg(reinterpret_cast<const int2*>(p.bwd_leaves + i)) : make_int2(0, 0);
     }
     __syncwarp();
 }
@@ -407,10 +426,13 @@ __device__ __forceinline__ bool fwd_set_prefetched(uint32_t ref, int op) {
     return (ref & REF_EXT) || int(ref & REF_IDX_MASK) + FWD_DEPTH <= op;
 }
 template <int JS, int JROW>
-__device__ __forceinline__ bool fwd_issue_set(const RunParams& p, const TileCtx& tc, uint4* st, uint32_t ref, int op, int lane,
-                                              TraceItem& tr) {
+__device__ __forceinline__ bool fwd_issue_set(const RunParams& p, const Chunk& ck, const TileCtx& tc, DepCursor& dc, uint4* st,
+                                              uint32_t ref, int op, int lane, TraceItem& tr) {
     if (!fwd_set_prefetched(ref, op)) return true;
-    const uint4* row = tc.sets + (size_t)(ref & REF_IDX_MASK) * (JROW * 32);  // external rows: verified at item start
+    if (ref & REF_EXT) {
+        if (!wait_dep(p, ck, tc.done, dc, int(ref & REF_IDX_MASK), lane, tr)) return false;
+    }
+    const uint4* row = tc.sets + (size_t)ref_row(p, ck, ref) * (JROW * 32);
 #pragma unroll
     for (int j = 0; j < JS; j++) cp_async16(st + (2 + j) * 32, row + j * 32);
     return true;
@@ -418,8 +440,8 @@ __device__ __forceinline__ bool fwd_issue_set(const RunParams& p, const TileCtx&
 // forward: queue the inputs of `op` into stage `st` (lane-offset pointer) and commit one group: the first two leaf
 // rows and, when prefetchable, the first set row. JS = vectors of a set row the consumer needs, JROW = row length.
 template <int JS, int JROW>
-__device__ __forceinline__ bool fwd_issue(const RunParams& p, const FwdMeta& m, const TileCtx& tc, uint4* st, int op, int lane,
-                                          TraceItem& tr) {
+__device__ __forceinline__ bool fwd_issue(const RunParams& p, const Chunk& ck, const FwdMeta& m, const TileCtx& tc, DepCursor& dc,
+                                          uint4* st, int op, int lane, TraceItem& tr) {
     const int4 w0 = m.ops[2 * (op - m.wb)], w1 = m.ops[2 * (op - m.wb) + 1];
     const uint32_t r0 = (uint32_t)w1.x, r1 = (uint32_t)w1.y;
     bool ok = true;
@@ -433,10 +455,10 @@ __device__ __forceinline__ bool fwd_issue(const RunParams& p, const FwdMeta& m, 
         break;
     case FT_LEAF_INT:
         cp_async16(st, tc.leaf + (size_t)(r0 & REF_IDX_MASK) * 32);
-        ok = fwd_issue_set<JS, JROW>(p, tc, st, r1, op, lane, tr);
+        ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, r1, op, lane, tr);
         break;
     case FT_INT_ACC:
-        ok = fwd_issue_set<JS, JROW>(p, tc, st, r0, op, lane, tr);
+        ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, r0, op, lane, tr);
         break;
     default: {
         int nl = 0, ni = 0;
@@ -447,7 +469,7 @@ __device__ __forceinline__ bool fwd_issue(const RunParams& p, const FwdMeta& m, 
                 if (nl < 2) cp_async16(st + nl * 32, tc.leaf + (size_t)(ref & REF_IDX_MASK) * 32);
                 nl++;
             } else if (kind == REF_INT) {
-                if (ni == 0) ok = fwd_issue_set<JS, JROW>(p, tc, st, ref, op, lane, tr) && ok;
+                if (ni == 0) ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, ref, op, lane, tr) && ok;
                 ni++;
             }
         }
@@ -487,13 +509,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<4>(p, tile, lane);
-        if (!wait_chunk_deps(p, ck, tc.done, lane, tr)) return;
+        DepCursor dc;
         uint32_t acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0;
         fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
         for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 4>(p, m, tc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
+            if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
         }
         int stage = 0;
         for (int op = ck.op_begin; op < ck.op_end; op++) {
@@ -549,7 +571,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         if (ni == 0 && fwd_set_prefetched(ref, op)) {
                             stage_set16(st, S);
                         } else {
-                            row_set16(tc.sets + (size_t)idx * 128, S);
+                            if (ref & REF_EXT) {
+                                if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return;
+                            }
+                            row_set16(tc.sets + (size_t)ref_row(p, ck, ref) * 128, S);
                         }
                         ni++;
                         fold.add_set(S);
@@ -573,7 +598,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
             if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
             // the stage of this op is consumed and its result stored: refill the stage for the op FWD_DEPTH ahead
             if (op + FWD_DEPTH < ck.op_end) {
-                if (!fwd_issue<JS, 4>(p, m, tc, st, op + FWD_DEPTH, lane, tr)) return;
+                if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, st, op + FWD_DEPTH, lane, tr)) return;
             }
             stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
         }
@@ -741,9 +766,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
 // ------------------------------------------------------------------ Sankoff forward
 // first non-accumulator set row either comes prefetched from the stage (G planes + first H vector) or is loaded here
 template <int B>
-__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const FwdMeta& m, const TileCtx& tc, const int4 w0, int op,
-                                                   const uint4* st, int lane, uint32_t accG[16], uint32_t accH[16],
-                                                   TraceItem& tr) {
+__device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Chunk& ck, DepCursor& dc, const FwdMeta& m,
+                                                   const TileCtx& tc, const int4 w0, int op, const uint4* st, int lane,
+                                                   uint32_t accG[16], uint32_t accH[16], TraceItem& tr) {
     SankoffFold<B> fold;
     fold.reset();
     int nl = 0, ni = 0;
@@ -770,7 +795,10 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Fwd
                 stage_set16(st, G);
                 h0 = st[(2 + 4) * 32].x;
             } else {
-                const uint4* row = tc.sets + (size_t)idx * 256;
+                if (ref & REF_EXT) {
+                    if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return false;
+                }
+                const uint4* row = tc.sets + (size_t)ref_row(p, ck, ref) * 256;
                 row_set16(row, G);
                 h0 = ld_l2(row + 128).x;
             }
@@ -802,13 +830,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<8>(p, tile, lane);
-        if (!wait_chunk_deps(p, ck, tc.done, lane, tr)) return;
+        DepCursor dc;
         uint32_t accG[16], accH[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
         fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
         for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 8>(p, m, tc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
+            if (!fwd_issue<JS, 8>(p, ck, m, tc, dc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
         }
         int stage = 0;
         for (int op = ck.op_begin; op < ck.op_end; op++) {
@@ -864,10 +892,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
                     acc_child(g2, n2);
                 }
                 sankoff_pair(g1, n1, g2, n2, accG, accH);
-            } else if (MAXB == 2 || w0.w == 2) ok = sankoff_forward_op<2>(p, m, tc, w0, op, st, lane, accG, accH, tr);
-            else if (MAXB == 4 || w0.w == 4) ok = sankoff_forward_op<4>(p, m, tc, w0, op, st, lane, accG, accH, tr);
-            else if (MAXB == 8 || w0.w == 8) ok = sankoff_forward_op<8>(p, m, tc, w0, op, st, lane, accG, accH, tr);
-            else ok = sankoff_forward_op<20>(p, m, tc, w0, op, st, lane, accG, accH, tr);
+            } else if (MAXB == 2 || w0.w == 2) ok = sankoff_forward_op<2>(p, ck, dc, m, tc, w0, op, st, lane, accG, accH, tr);
+            else if (MAXB == 4 || w0.w == 4) ok = sankoff_forward_op<4>(p, ck, dc, m, tc, w0, op, st, lane, accG, accH, tr);
+            else if (MAXB == 8 || w0.w == 8) ok = sankoff_forward_op<8>(p, ck, dc, m, tc, w0, op, st, lane, accG, accH, tr);
+            else ok = sankoff_forward_op<20>(p, ck, dc, m, tc, w0, op, st, lane, accG, accH, tr);
             if (!ok) return;
             uint4* out = tc.sets + (size_t)op * 256;
 #pragma unroll
@@ -877,7 +905,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
             }
             if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
             if (op + FWD_DEPTH < ck.op_end) {
-                if (!fwd_issue<JS, 8>(p, m, tc, st, op + FWD_DEPTH, lane, tr)) return;
+                if (!fwd_issue<JS, 8>(p, ck, m, tc, dc, st, op + FWD_DEPTH, lane, tr)) return;
             }
             stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
         }

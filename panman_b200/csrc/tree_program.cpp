@@ -299,15 +299,22 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     }
     P.max_arity = max_arity;
 
-    // ---- forward dependencies per chunk (external rows it reads) ----
+    // ---- forward dependencies per chunk (external rows it reads), in consumption order; an external ref then
+    //      carries its ordinal in that list instead of the row ----
     for (Chunk& ck : P.chunks) {
         ck.dep_begin = int32_t(P.deps.size());
         for (int32_t i = ck.op_begin; i < ck.op_end; i++) {
-            const FwdOp& f = P.fwd_ops[i];
+            FwdOp& f = P.fwd_ops[i];
             for (int32_t r = 0; r < f.n_refs; r++) {
-                const uint32_t ref = P.refs[f.ref_begin + r];
-                if ((ref >> 30) == REF_INT && (ref & REF_EXT)) P.deps.push_back(int32_t(ref & REF_IDX_MASK));
+                uint32_t& ref = P.refs[f.ref_begin + r];
+                if ((ref >> 30) == REF_INT && (ref & REF_EXT)) {
+                    const uint32_t k = uint32_t(P.deps.size()) - uint32_t(ck.dep_begin);
+                    P.deps.push_back(int32_t(ref & REF_IDX_MASK));
+                    ref = (REF_INT << 30) | REF_EXT | k;
+                }
             }
+            if (f.n_refs > 0) f.ref0 = P.refs[f.ref_begin];
+            if (f.n_refs > 1) f.ref1 = P.refs[f.ref_begin + 1];
         }
         ck.dep_count = int32_t(P.deps.size()) - ck.dep_begin;
     }

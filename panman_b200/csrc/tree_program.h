@@ -26,12 +26,16 @@
 namespace pmb {
 
 enum : uint32_t { REF_INT = 0u, REF_LEAF = 1u, REF_ACC = 2u };  // top 2 bits of a forward child ref
-constexpr uint32_t REF_EXT = 1u << 29;                          // REF_INT written by another chunk: wait for its flag
+constexpr uint32_t REF_EXT = 1u << 29;                          // REF_INT of another chunk: the index field holds the ORDINAL k of
+                                                                // the dependency in the chunk's list; the row is deps[dep_begin + k]
 constexpr uint32_t REF_IDX_MASK = (1u << 29) - 1u;
 // BwdOp::parent_ref: >= 0 a global state slot (fslot); PARENT_ACC the previous op's registers; PARENT_ROOT the
 // per-column parameters; <= PARENT_STACK0 entry (PARENT_STACK0 - parent_ref) of the warp's shared-memory state stack
 enum : int32_t { PARENT_ACC = -1, PARENT_ROOT = -2, PARENT_STACK0 = -16 };
-constexpr int32_t BWD_STACK_DEPTH = 5;   // entries of the per-warp state stack (640 B each)
+#ifndef PMB_BWD_STACK_DEPTH
+#define PMB_BWD_STACK_DEPTH 5
+#endif
+constexpr int32_t BWD_STACK_DEPTH = PMB_BWD_STACK_DEPTH;   // entries of the per-warp state stack (640 B each)
 enum : int32_t {
     OPF_ROOT = 1,
     OPF_SIGNAL = 2,      // forward: this op is a chunk root, publish its done flag after the store

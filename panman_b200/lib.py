@@ -4,7 +4,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpanman_b200.so")
+LIB_PATH = os.environ.get("PANMAN_B200_LIB", os.path.join(HERE, "libpanman_b200.so"))  # override: tuning variants only
 
 # every symbol include/panman_b200.h declares
 EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",

@@ -82,7 +82,7 @@ void store_state(Emu& E, int node, int tile, int lane, const uint32_t F[4], uint
 }
 
 template <int B>
-void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16], uint32_t accH[16]) {
+void sankoff_fwd_op(Emu& E, const Chunk& ck, const FwdOp& f, int tile, int lane, uint32_t accG[16], uint32_t accH[16]) {
     const size_t T = E.T;
     SankoffFold<B> fold;
     fold.reset();
@@ -96,6 +96,7 @@ void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
+            if (ref & REF_EXT) idx = uint32_t(E.P.deps[ck.dep_begin + idx]);
             if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
             const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256;
             uint32_t G[16];
@@ -110,9 +111,10 @@ void sankoff_fwd_op(Emu& E, const FwdOp& f, int tile, int lane, uint32_t accG[16
 void forward_item(Emu& E, int chunk, int tile) {
     const Chunk ck = E.P.chunks[chunk];
     const size_t T = E.T;
-    // the kernels wait for every external row once, when the item starts
-    for (int i = 0; i < ck.dep_count; i++)
-        if (E.done[(size_t)tile * E.P.n_internal + E.P.deps[ck.dep_begin + i]] != 1) E.order_violation = true;
+    auto row_of = [&](uint32_t ref) -> uint32_t {  // external refs name their ordinal in the chunk's dependency list
+        uint32_t v = ref & REF_IDX_MASK;
+        return (ref & REF_EXT) ? uint32_t(E.P.deps[ck.dep_begin + v]) : v;
+    };
     static thread_local uint32_t acc[32][16], accH[32][16];
     memset(acc, 0, sizeof acc);
     memset(accH, 0, sizeof accH);
@@ -127,7 +129,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                     cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
                 };
                 auto intset = [&](int r, uint32_t X[16]) {
-                    uint32_t ref = E.P.refs[f.ref_begin + r], idx = ref & REF_IDX_MASK;
+                    uint32_t ref = E.P.refs[f.ref_begin + r], idx = row_of(ref);
                     if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
                     load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 128, lane, X);
                 };
@@ -161,6 +163,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc[lane]);
                     } else {
+                        idx = row_of(ref);
                         if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
                         uint32_t S[16];
                         load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 128, lane, S);
@@ -190,7 +193,7 @@ void forward_item(Emu& E, int chunk, int tile) {
                         none = ~pr;
                     };
                     auto set_child = [&](int r, uint32_t g[16], uint32_t& none) {
-                        uint32_t ref = E.P.refs[f.ref_begin + r], idx = ref & REF_IDX_MASK;
+                        uint32_t ref = E.P.refs[f.ref_begin + r], idx = row_of(ref);
                         if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
                         const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256;
                         load16(base, lane, g);
@@ -207,10 +210,10 @@ void forward_item(Emu& E, int chunk, int tile) {
                     sankoff_pair(g1, n1, g2, n2, acc[lane], accH[lane]);
                 } else
                 switch (f.max_arity_bits) {
-                case 2: sankoff_fwd_op<2>(E, f, tile, lane, acc[lane], accH[lane]); break;
-                case 4: sankoff_fwd_op<4>(E, f, tile, lane, acc[lane], accH[lane]); break;
-                case 8: sankoff_fwd_op<8>(E, f, tile, lane, acc[lane], accH[lane]); break;
-                default: sankoff_fwd_op<20>(E, f, tile, lane, acc[lane], accH[lane]); break;
+                case 2: sankoff_fwd_op<2>(E, ck, f, tile, lane, acc[lane], accH[lane]); break;
+                case 4: sankoff_fwd_op<4>(E, ck, f, tile, lane, acc[lane], accH[lane]); break;
+                case 8: sankoff_fwd_op<8>(E, ck, f, tile, lane, acc[lane], accH[lane]); break;
+                default: sankoff_fwd_op<20>(E, ck, f, tile, lane, acc[lane], accH[lane]); break;
                 }
                 U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 256;
                 store16(base, lane, acc[lane]);
@@ -459,7 +462,8 @@ extern "C" int emul_prog_stats(int n_nodes, int root, const int32_t* child_off, 
             const FwdOp& f = P.fwd_ops[op];
             for (int r = 0; r < f.n_refs; r++) {
                 uint32_t ref = P.refs[f.ref_begin + r];
-                if ((ref >> 30) == REF_INT && (ref & REF_EXT)) dep = std::max(dep, cp[chunk_of_op[ref & REF_IDX_MASK]]);
+                if ((ref >> 30) == REF_INT && (ref & REF_EXT))
+                    dep = std::max(dep, cp[chunk_of_op[P.deps[P.chunks[c].dep_begin + (ref & REF_IDX_MASK)]]]);
             }
         }
         long long n = P.chunks[c].op_end - P.chunks[c].op_begin;
