@@ -149,6 +149,83 @@ PMB_HD void fitch_set_set(const uint32_t X[16], const uint32_t Y[16], uint32_t S
     for (int k = 0; k < 16; k++) S[k] = (X[k] & Y[k]) | ((X[k] | Y[k]) & ~nz);
 }
 
+// ---- speculative evaluation of chain segments (tree_program.h "chain segments") ----
+// Forward: the set S entering a segment from the segment below is unknown; lo <= S <= hi (as sets, per column)
+// bounds it. One op on the path combines S with its other, known, children: A = their intersection, O = their
+// union (FitchFold before finish()). Per column, with every known child non-empty:
+//   lo&A != 0 : certainly intersects                 -> [lo&A, hi&A]
+//   hi&A == 0 : certainly disjoint (A may be empty)  -> [lo|O, hi|O]
+//   else      : either                               -> [one & (lo|O), hi|O], one = hi&A if that is a single state
+// (if it does intersect, the result is a non-empty subset of hi&A, hence exactly hi&A when that is one state). The
+// value is known exactly where lo == hi: for one-hot leaves that happens as soon as two consecutive leaves agree.
+struct FitchInterval {
+    uint32_t lo[16], hi[16];
+    PMB_HD void reset() {
+#pragma unroll
+        for (int k = 0; k < 16; k++) { lo[k] = 0; hi[k] = 0xFFFFFFFFu; }
+    }
+    PMB_HD void step(const uint32_t A[16], const uint32_t O[16]) {
+        uint32_t sure = 0, maybe = 0, one = 0, two = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t h = hi[k] & A[k];
+            sure |= lo[k] & A[k];
+            maybe |= h;
+            two |= one & h;
+            one |= h;
+        }
+        const uint32_t single = one & ~two, uni = ~maybe, either = maybe & ~sure;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t l = lo[k], h = hi[k];
+            lo[k] = (sure & l & A[k]) | (uni & (l | O[k])) | (either & single & h & A[k] & (l | O[k]));
+            hi[k] = (sure & h & A[k]) | (~sure & (h | O[k]));
+        }
+    }
+    // columns where the value is not known exactly yet
+    PMB_HD uint32_t open() const {
+        uint32_t d = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) d |= lo[k] ^ hi[k];
+        return d;
+    }
+};
+
+// Backward: the state a segment's top node receives from above is unknown; Q = the states it may be (one-hot planes).
+// A node with set S != 0 keeps the parent's state if S has it, else takes lowest(S)  (fitch_assign below), so its own
+// candidates are (Q & S) plus lowest(S) if some candidate is outside S. Known exactly where one candidate is left.
+PMB_HD void fitch_candidates_step(uint32_t Q[16], const uint32_t S[16]) {
+    uint32_t outside = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) outside |= Q[k] & ~S[k];
+    uint32_t seen = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t lowest = S[k] & ~seen;
+        seen |= S[k];
+        Q[k] = (Q[k] & S[k]) | (outside & lowest);
+    }
+}
+PMB_HD uint32_t candidates_open(const uint32_t Q[16]) {  // columns with more (or fewer) than one candidate
+    uint32_t one = 0, two = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        two |= one & Q[k];
+        one |= Q[k];
+    }
+    return ~one | two;
+}
+PMB_HD void encode16(const uint32_t d[16], uint32_t c[4]) {  // one-hot planes -> code planes
+    c[0] = c[1] = c[2] = c[3] = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k & 1) c[0] |= d[k];
+        if (k & 2) c[1] |= d[k];
+        if (k & 4) c[2] |= d[k];
+        if (k & 8) c[3] |= d[k];
+    }
+}
+
 // Assigned state of a non-root node (or a block-mode root): parent state P (code planes) where visited pvis.
 // F = P if P in S else lowest(S); vis = pvis & (S != 0)          (fitchSankoff.cpp:101-103, 115-123)
 PMB_HD void fitch_assign(const uint32_t S[16], const uint32_t P[4], uint32_t pvis, uint32_t F[4], uint32_t& vis) {

@@ -427,12 +427,12 @@ __device__ __forceinline__ bool fwd_set_prefetched(uint32_t ref, int op) {
 }
 template <int JS, int JROW>
 __device__ __forceinline__ bool fwd_issue_set(const RunParams& p, const Chunk& ck, const TileCtx& tc, DepCursor& dc, uint4* st,
-                                              uint32_t ref, int op, int lane, TraceItem& tr) {
+                                              uint32_t ref, uint32_t row_idx, int op, int lane, TraceItem& tr) {
     if (!fwd_set_prefetched(ref, op)) return true;
     if (ref & REF_EXT) {
         if (!wait_dep(p, ck, tc.done, dc, int(ref & REF_IDX_MASK), lane, tr)) return false;
     }
-    const uint4* row = tc.sets + (size_t)ref_row(p, ck, ref) * (JROW * 32);
+    const uint4* row = tc.sets + (size_t)row_idx * (JROW * 32);
 #pragma unroll
     for (int j = 0; j < JS; j++) cp_async16(st + (2 + j) * 32, row + j * 32);
     return true;
@@ -455,10 +455,10 @@ __device__ __forceinline__ bool fwd_issue(const RunParams& p, const Chunk& ck, c
         break;
     case FT_LEAF_INT:
         cp_async16(st, tc.leaf + (size_t)(r0 & REF_IDX_MASK) * 32);
-        ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, r1, op, lane, tr);
+        ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, r1, (uint32_t)w1.w, op, lane, tr);
         break;
     case FT_INT_ACC:
-        ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, r0, op, lane, tr);
+        ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, r0, (uint32_t)w1.z, op, lane, tr);
         break;
     default: {
         int nl = 0, ni = 0;
@@ -469,7 +469,7 @@ __device__ __forceinline__ bool fwd_issue(const RunParams& p, const Chunk& ck, c
                 if (nl < 2) cp_async16(st + nl * 32, tc.leaf + (size_t)(ref & REF_IDX_MASK) * 32);
                 nl++;
             } else if (kind == REF_INT) {
-                if (ni == 0) ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, ref, op, lane, tr) && ok;
+                if (ni == 0) ok = fwd_issue_set<JS, JROW>(p, ck, tc, dc, st, ref, ref_row(p, ck, ref), op, lane, tr) && ok;
                 ni++;
             }
         }
@@ -493,6 +493,68 @@ __device__ __forceinline__ void row_set16(const uint4* row, uint32_t X[16]) {
     }
 }
 
+// ------------------------------------------------------------------ chain segments (speculative evaluation)
+// See tree_program.h. `head` is the latest op seen on the segment's heavy path (-1 before the first one): an op is on
+// the path iff it holds the REF_CHAIN child or consumes `head`.
+__device__ __forceinline__ bool fwd_on_path(const RunParams& p, const int4 w0, int op, int head) {
+    for (int r = 0; r < w0.y; r++) {
+        const uint32_t ref = __ldg(p.refs + w0.x + r), kind = ref >> 30;
+        if (kind == REF_CHAIN) return true;
+        if (head < 0) continue;
+        if (kind == REF_ACC && head == op - 1) return true;
+        if (kind == REF_INT && !(ref & REF_EXT) && int(ref & REF_IDX_MASK) == head) return true;
+    }
+    return false;
+}
+// Folds the KNOWN children of `op` (all but the one on the path) into fold.A / fold.O. Every leaf is present here
+// (speculation is only used without a presence mask). ACC_REGS: the previous op's result is still in `acc`.
+template <bool ACC_REGS>
+__device__ __forceinline__ bool fitch_fold_known(const RunParams& p, const Chunk& ck, const TileCtx& tc, DepCursor& dc, const int4 w0,
+                                                 int op, int head, const uint32_t acc[16], int lane, FitchFold& fold, TraceItem& tr) {
+    fold.reset();
+    for (int r = 0; r < w0.y; r++) {
+        const uint32_t ref = __ldg(p.refs + w0.x + r), kind = ref >> 30, idx = ref & REF_IDX_MASK;
+        if (kind == REF_CHAIN) continue;
+        if (kind == REF_LEAF) {
+            const uint4 c = ld_stream(tc.leaf + (size_t)idx * 32);
+            const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            fold.add_leaf(cc, FULL);
+        } else if (kind == REF_ACC) {
+            if (head >= 0 && head == op - 1) continue;
+            if (ACC_REGS) {
+                fold.add_set(acc);
+            } else {
+                uint32_t S[16];
+                row_set16(tc.sets + (size_t)(op - 1) * 128, S);
+                fold.add_set(S);
+            }
+        } else {
+            if (!(ref & REF_EXT) && head >= 0 && int(idx) == head) continue;
+            if (ref & REF_EXT) {
+                if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return false;
+            }
+            uint32_t S[16];
+            row_set16(tc.sets + (size_t)ref_row(p, ck, ref) * 128, S);
+            fold.add_set(S);
+        }
+    }
+    return true;
+}
+// refState: the root's forward value is replaced where a reference state is given (fitchSankoff.cpp:45-47)
+__device__ __forceinline__ void fitch_root_ref(const RunParams& p, int tile, int lane, uint32_t S[16]) {
+    const uint4* cp = p.colparams + (size_t)tile * 128;
+    uint4 rc = __ldg(cp + 64 + lane);
+    uint32_t rv = __ldg(cp + 96 + lane).y;
+    uint32_t r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
+    decode16(r4, d);
+#pragma unroll
+    for (int k = 0; k < 16; k++) S[k] = (rv & d[k]) | (~rv & S[k]);
+}
+__device__ __forceinline__ void store_set16(uint4* out, const uint32_t S[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j * 32] = make_uint4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
+}
+
 // ------------------------------------------------------------------ Fitch forward
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
@@ -513,12 +575,49 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
         uint32_t acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0;
-        fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
-        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
+        // Chain segment: the value entering from the segment below is not waited for. Bounds on it are carried up the
+        // path until no column depends on it any more (op `resolved`); the plain loop continues from there and the
+        // few ops before it are redone at the end, once the segment below has published.
+        const bool spec = ck.chain_op >= 0 && p.leaf_present == nullptr;
+        int first = ck.op_begin, resolved = -1;
+        if (spec) {
+            FitchInterval iv;
+            iv.reset();
+            int head = -1;
+            first = ck.op_end;
+            for (int op = ck.op_begin; op < ck.op_end; op++) {
+                const int4 w0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+                const bool on_path = fwd_on_path(p, w0, op, head);
+                FitchFold fold;
+                if (!fitch_fold_known<true>(p, ck, tc, dc, w0, op, head, acc, lane, fold, tr)) return;
+                if (!on_path) {  // a light subtree evaluated inside the segment: exact
+                    fold.finish(acc);
+                    store_set16(tc.sets + (size_t)op * 128, acc);
+                    continue;
+                }
+                iv.step(fold.A, fold.O);
+                if ((w0.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
+                    fitch_root_ref(p, tile, lane, iv.lo);
+                    fitch_root_ref(p, tile, lane, iv.hi);
+                }
+                head = op;
+                if (!__any_sync(FULL, iv.open() != 0)) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) acc[k] = iv.lo[k];
+                    store_set16(tc.sets + (size_t)op * 128, acc);
+                    if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
+                    resolved = op;
+                    first = op + 1;
+                    break;
+                }
+            }
+        }
+        if (first < ck.op_end) fwd_meta_load(p, m, first, ck.op_end, lane);
+        for (int i = 0; i < FWD_DEPTH && first + i < ck.op_end; i++) {
+            if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, ring_l + i * STAGE, first + i, lane, tr)) return;
         }
         int stage = 0;
-        for (int op = ck.op_begin; op < ck.op_end; op++) {
+        for (int op = first; op < ck.op_end; op++) {
             if (op + FWD_DEPTH >= m.wb + META_OPS && m.wb + META_OPS < ck.op_end) fwd_meta_load(p, m, op, ck.op_end, lane);
             const int4 w0 = m.ops[2 * (op - m.wb)], w1 = m.ops[2 * (op - m.wb) + 1];  // {ref_begin, n_refs, flags, bits}, {ref0, ref1}
             cp_async_wait_stage<FWD_DEPTH>(ck.op_end - 1 - op);
@@ -566,6 +665,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         fold.add_leaf(cc, leaf_present_mask(p, idx));
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc);
+                    } else if (kind == REF_CHAIN) {  // not speculating (presence mask): wait for the segment below
+                        if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return;
+                        uint32_t S[16];
+                        row_set16(tc.sets + (size_t)idx * 128, S);
+                        fold.add_set(S);
                     } else {
                         uint32_t S[16];
                         if (ni == 0 && fwd_set_prefetched(ref, op)) {
@@ -582,25 +686,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 }
                 fold.finish(acc);
             }
-            if ((w0.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) {
-                // refState: the root's forward value is replaced (fitchSankoff.cpp:45-47)
-                const uint4* cp = p.colparams + (size_t)tile * 128;
-                uint4 rc = __ldg(cp + 64 + lane);
-                uint32_t rv = __ldg(cp + 96 + lane).y;
-                uint32_t r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
-                decode16(r4, d);
-#pragma unroll
-                for (int k = 0; k < 16; k++) acc[k] = (rv & d[k]) | (~rv & acc[k]);
-            }
-            uint4* out = tc.sets + (size_t)op * 128;
-#pragma unroll
-            for (int j = 0; j < 4; j++) out[j * 32] = make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            if ((w0.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) fitch_root_ref(p, tile, lane, acc);
+            store_set16(tc.sets + (size_t)op * 128, acc);
             if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
             // the stage of this op is consumed and its result stored: refill the stage for the op FWD_DEPTH ahead
             if (op + FWD_DEPTH < ck.op_end) {
                 if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, st, op + FWD_DEPTH, lane, tr)) return;
             }
             stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
+        }
+        if (spec) {  // the value from below is needed now: redo the path ops that depended on it
+            if (!wait_flag(tc.done + ck.chain_row, p.epoch, p.error, lane, tr)) return;
+            uint32_t S[16];
+            row_set16(tc.sets + (size_t)ck.chain_row * 128, S);
+            const int end = resolved >= 0 ? resolved : ck.op_end;
+            int head = -1;
+            for (int op = ck.chain_op; op < end; op++) {
+                const int4 w0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+                if (!fwd_on_path(p, w0, op, head)) continue;
+                FitchFold fold;
+                if (!fitch_fold_known<false>(p, ck, tc, dc, w0, op, head, acc, lane, fold, tr)) return;
+                fold.add_set(S);
+                fold.finish(S);
+                if ((w0.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) fitch_root_ref(p, tile, lane, S);
+                store_set16(tc.sets + (size_t)op * 128, S);
+                if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
+                head = op;
+            }
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -639,8 +751,9 @@ __device__ __forceinline__ bool bwd_parent_slot(const RunParams& p, const BwdHea
 // and the leaf's node id is only fetched when it really has a record.
 __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta& m, const TileCtx& tc, StageCursor& sc,
                                               const BwdHead& h, const uint4* leaf_stage, uint32_t* stack, int tile, int lane,
-                                              const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block) {
-    emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
+                                              const uint32_t P[4], const uint32_t F[4], uint32_t vis, bool sankoff_block,
+                                              bool own_record = true) {
+    if (own_record) emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
     if (h.b1.y & OPF_PUSH) {  // a later op of this chunk needs this state: park it in the warp's shared-memory stack
         uint32_t* e = stack + ((h.b1.y >> OPF_PUSH_SHIFT) & 15) * FSLOT_WORDS;
         reinterpret_cast<uint4*>(e)[lane] = make_uint4(F[0], F[1], F[2], F[3]);
@@ -705,16 +818,47 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
         const TileCtx tc = tile_ctx<J>(p, tile, lane);
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
-        bwd_meta_load(p, m, last, ck.op_begin, lane);
-        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, last - i);
+        // Chain segment: the state handed down by the segment above is not waited for. The states it may be are
+        // narrowed down the segment's heavy path until one is left in every column (op `resolved`); that op's subtree
+        // is processed first, then -- once the segment above has published -- the ops above it, and its own record.
+        int resolved = -1;
+        uint32_t specF[4] = {0, 0, 0, 0}, specVis = 0;
+        if (p.leaf_present == nullptr && (__ldg(&p.bwd_ops[last].flags) & OPF_CHAIN_TOP)) {
+            uint32_t Q[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) Q[k] = FULL;
+            for (int op = last; op >= ck.op_begin; op--) {
+                if (op != last && !(__ldg(&p.bwd_ops[op].flags) & OPF_HEAVY)) continue;
+                uint32_t S[16];
+                row_set16(tc.sets + (size_t)op * 128, S);
+                fitch_candidates_step(Q, S);
+                if (!__any_sync(FULL, candidates_open(Q) != 0)) {
+                    resolved = op;
+                    encode16(Q, specF);
+                    specVis = __ldg(p.colparams + (size_t)tile * 128 + 96 + lane).z;  // every set is non-empty: visited = valid column
+#pragma unroll
+                    for (int k = 0; k < 4; k++) specF[k] &= specVis;
+                    break;
+                }
+            }
+        }
+        for (int range = (resolved >= 0 ? 0 : 1); range < 2; range++) {
+        // range 0: the resolved op (state known, own record postponed) and everything below it;
+        // range 1: the ops above it in full, then the resolved op's own record -- or, without speculation, the whole chunk
+        const int hi = range == 0 ? resolved : last;
+        const int lo = (range == 1 && resolved >= 0) ? resolved : ck.op_begin;
+        bwd_meta_load(p, m, hi, lo, lane);
+        for (int i = 0; i < BWD_DEPTH && hi - i >= lo; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, hi - i);
         int stage = 0;
-        for (int op = last; op >= ck.op_begin; op--) {
-            if (op - BWD_DEPTH < m.lo && m.lo > ck.op_begin) bwd_meta_load(p, m, op, ck.op_begin, lane);
+        for (int op = hi; op >= lo; op--) {
+            if (op - BWD_DEPTH < m.lo && m.lo > lo) bwd_meta_load(p, m, op, lo, lane);
             BwdHead h;
             h.b0 = m.ops[2 * (op - m.lo)];
             h.b1 = m.ops[2 * (op - m.lo) + 1];
-            uint32_t P[4], pvis, F[4], vis;
-            if (h.b0.y == PARENT_ACC) {
+            const bool given = range == 0 && op == resolved, own_only = range == 1 && op == resolved;
+            uint32_t P[4] = {0, 0, 0, 0}, pvis = 0, F[4], vis;
+            if (given) {
+            } else if (h.b0.y == PARENT_ACC) {
                 P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
                 pvis = accVis;
             } else if (h.b0.y <= PARENT_STACK0) {
@@ -725,7 +869,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             } else if (h.b0.y >= 0) {
                 if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
             }
-            cp_async_wait_stage<BWD_DEPTH>(op - ck.op_begin);
+            cp_async_wait_stage<BWD_DEPTH>(op - lo);
             uint4* st = ring_l + stage * STAGE;
             uint32_t S[16];
 #pragma unroll
@@ -733,7 +877,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
                 const uint4 v = st[j * 32];
                 S[4 * j] = v.x; S[4 * j + 1] = v.y; S[4 * j + 2] = v.z; S[4 * j + 3] = v.w;
             }
-            if (h.b0.y == PARENT_ROOT) {
+            if (given) {
+                F[0] = specF[0]; F[1] = specF[1]; F[2] = specF[2]; F[3] = specF[3];
+                vis = specVis;
+            } else if (h.b0.y == PARENT_ROOT) {
                 const uint4* cp = p.colparams + (size_t)tile * 128;
                 uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
                 P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
@@ -752,12 +899,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
             } else {
                 fitch_assign(S, P, pvis, F, vis);
             }
-            bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, false);
+            if (own_only) emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
+            else bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, false, !given);
             // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
-            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
+            if (op - BWD_DEPTH >= lo) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
             stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
+        }
         }
         trace_end(p, tr, chunk, tile, lane);
     }
@@ -789,6 +938,13 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Chu
             fold.add_leaf(cc, present);
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
+        } else if (kind == REF_CHAIN) {  // chain segments of the Sankoff pass wait for the segment below
+            if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return false;
+            const uint4* row = tc.sets + (size_t)idx * 256;
+            uint32_t G[16];
+            row_set16(row, G);
+            const uint32_t h0 = ld_l2(row + 128).x;
+            fold.add_set(G, h0 & ~G[0]);
         } else {
             uint32_t G[16], h0;
             if (ni == 0 && fwd_set_prefetched(ref, op)) {

@@ -85,16 +85,27 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     // ---- cut into chunks: bottom subtrees (<= chunk_nodes) and heavy-path segments of the top tree ----
     if (inline_nodes < 0) inline_nodes = 0;
     if (inline_nodes >= chunk_nodes) inline_nodes = chunk_nodes - 1;
-    std::vector<char> cut(n_nodes, 0);
+    std::vector<char> cut(n_nodes, 0), chain_cut(n_nodes, 0);
+    std::vector<int32_t> run(n_nodes, 0);  // top nodes: ops of the node's chunk from the chunk's root down to this node
     for (int32_t i = 0; i < n_nodes; i++) {
         int32_t v = pre[i];
         if (isz[v] == 0) continue;
-        if (v == root) { cut[v] = 1; continue; }
+        const bool v_top = isz[v] > chunk_nodes;
+        int32_t own = 1;  // this op plus the light subtrees evaluated inside the chunk
+        if (v_top)
+            for (int32_t e = ichild_off[v]; e < ichild_off[v + 1]; e++)
+                if (isz[ichild[e]] <= inline_nodes) own += isz[ichild[e]];
+        if (v == root) { cut[v] = 1; run[v] = own; continue; }
         int32_t p = parent[v];
         bool p_top = isz[p] > chunk_nodes;
         if (!p_top) continue;                         // inside a bottom subtree
-        if (isz[v] > chunk_nodes) cut[v] = (ichild[ichild_off[p]] != v);  // top node: stays iff heaviest child
-        else cut[v] = isz[v] > inline_nodes;          // bottom subtree hanging off the top tree
+        if (v_top) {
+            cut[v] = (ichild[ichild_off[p]] != v);    // top node: stays iff heaviest child ...
+            if (!cut[v] && run[p] >= chunk_nodes) cut[v] = chain_cut[v] = 1;  // ... and the path segment is not full yet
+            run[v] = cut[v] ? own : run[p] + own;
+        } else {
+            cut[v] = isz[v] > inline_nodes;           // bottom subtree hanging off the top tree
+        }
     }
 
     // ---- per-chunk op lists (post-order over uncut internal children), chunk levels ----
@@ -154,6 +165,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         if (par_chunk[c] < 0) continue;
         int32_t q = par_chunk[c];
         int64_t after = int64_t(tmp[q].nodes.size()) - par_pos[c];  // parent's ops from the consuming op to its end
+        if (chain_cut[tmp[c].root_node]) after = 1;  // chain segments do not wait for each other (speculative evaluation)
         t_end[c] = after + t_end[q];
         est[c] = est[q] + after;  // backward runs the parent chunk's ops in reverse: same count
     }
@@ -195,7 +207,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
     int32_t op = 0;
     for (int32_t oi : fwd_order) {
         TmpChunk& c = tmp[oi];
-        Chunk ck{op, op + int32_t(c.nodes.size()), 0, 0};
+        Chunk ck{op, op + int32_t(c.nodes.size()), 0, 0, -1, -1, 0, 0};
         for (int32_t v : c.nodes) P.node_op[v] = op++;
         P.chunks.push_back(ck);
     }
@@ -252,7 +264,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         b.leaf_begin = int32_t(P.bwd_leaves.size());
         b.leaf0_slot = b.leaf1_slot = 0;
         f.ref0 = f.ref1 = 0;
-        f.pad0 = f.pad1 = 0;
+        f.row0 = f.row1 = 0;
         // leaves in Newick order, then internal children heavy -> light; the one computed by op i-1 of the
         // same chunk (if any) is taken from registers
         for (int32_t e = child_off[v]; e < child_off[v + 1]; e++) {
@@ -269,7 +281,14 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
             int32_t cop = P.node_op[c];
             bool acc = (cop == i - 1) && chunk_of[c] == chunk_of[v];
             bool ext = chunk_of[c] != chunk_of[v];
-            P.refs.push_back(acc ? (REF_ACC << 30) : ((REF_INT << 30) | (ext ? REF_EXT : 0u) | uint32_t(cop)));
+            if (chain_cut[c]) {
+                P.refs.push_back((REF_CHAIN << 30) | uint32_t(cop));
+                Chunk& ck = P.chunks[new_id[chunk_of[v]]];
+                ck.chain_op = i;
+                ck.chain_row = cop;
+            } else {
+                P.refs.push_back(acc ? (REF_ACC << 30) : ((REF_INT << 30) | (ext ? REF_EXT : 0u) | uint32_t(cop)));
+            }
         }
         f.n_refs = int32_t(P.refs.size()) - f.ref_begin;
         if (f.n_refs > 0) f.ref0 = P.refs[f.ref_begin];
@@ -295,9 +314,19 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
             bool acc = (pop == i + 1) && chunk_of[v] == chunk_of[parent[v]];
             b.parent_ref = acc ? PARENT_ACC : fslot[pop];
             if (chunk_of[v] != chunk_of[parent[v]]) b.flags |= OPF_PARENT_EXT;
+            if (chain_cut[v]) b.flags |= OPF_CHAIN_TOP;
         }
     }
     P.max_arity = max_arity;
+    // the heavy path that starts at each chunk's root, as far as it stays inside the chunk
+    for (const TmpChunk& c : tmp)
+        for (int32_t v = c.root_node;;) {
+            P.bwd_ops[P.node_op[v]].flags |= OPF_HEAVY;
+            if (ichild_off[v] == ichild_off[v + 1]) break;
+            const int32_t h = ichild[ichild_off[v]];
+            if (cut[h]) break;
+            v = h;
+        }
 
     // ---- forward dependencies per chunk (external rows it reads), in consumption order; an external ref then
     //      carries its ordinal in that list instead of the row ----
@@ -313,8 +342,12 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
                     ref = (REF_INT << 30) | REF_EXT | k;
                 }
             }
-            if (f.n_refs > 0) f.ref0 = P.refs[f.ref_begin];
-            if (f.n_refs > 1) f.ref1 = P.refs[f.ref_begin + 1];
+            auto row_of = [&](uint32_t ref) {
+                const uint32_t v = ref & REF_IDX_MASK;
+                return int32_t(((ref >> 30) == REF_INT && (ref & REF_EXT)) ? uint32_t(P.deps[ck.dep_begin + v]) : v);
+            };
+            if (f.n_refs > 0) { f.ref0 = P.refs[f.ref_begin]; f.row0 = row_of(f.ref0); }
+            if (f.n_refs > 1) { f.ref1 = P.refs[f.ref_begin + 1]; f.row1 = row_of(f.ref1); }
         }
         ck.dep_count = int32_t(P.deps.size()) - ck.dep_begin;
     }

@@ -15,7 +15,15 @@
 //   * within a chunk ops are in post-order with the lightest internal child last, so the most
 //     recent result stays in registers (REF_ACC) and older siblings are re-read from the set matrix
 //     while still L2-resident;
-//   * the backward pass runs the same ops in reverse (parents before children).
+//   * the backward pass runs the same ops in reverse (parents before children);
+//   * chain segments: a heavy path of the top tree longer than chunk_nodes ops (a caterpillar's spine, the backbone of
+//     an unbalanced phylogeny) is cut into segments of about chunk_nodes ops. Taken literally each segment would wait
+//     for the one below (forward) / above (backward) and a deep tree would run one segment at a time. The Fitch
+//     kernels therefore evaluate a segment SPECULATIVELY: they track bounds on the unknown value entering the
+//     segment (plane_math.h, FitchInterval / fitch_candidates_step) until, a few ops in, the value no longer depends
+//     on it in any column -- in real alignments neighbouring leaves agree in almost every column -- continue exactly
+//     from there, publish the segment's result, and only then wait for the neighbour to redo the few ops before
+//     that point. Segments of one path thus run in parallel; results are exact, never approximate.
 // Child order only affects scheduling: Fitch's AND/OR and Sankoff's sums are commutative, so results
 // equal the reference's left-to-right recursion bit for bit.
 #pragma once
@@ -25,7 +33,10 @@
 
 namespace pmb {
 
-enum : uint32_t { REF_INT = 0u, REF_LEAF = 1u, REF_ACC = 2u };  // top 2 bits of a forward child ref
+enum : uint32_t { REF_INT = 0u, REF_LEAF = 1u, REF_ACC = 2u, REF_CHAIN = 3u };  // top 2 bits of a forward child ref
+// REF_CHAIN: the heavy child of a node where a long heavy path was cut into segments; the index field holds the row
+// (op) of that child, the top op of the segment below. Not listed in deps[]: the kernels either wait for it explicitly
+// or evaluate the segment speculatively (see "chain segments" below).
 constexpr uint32_t REF_EXT = 1u << 29;                          // REF_INT of another chunk: the index field holds the ORDINAL k of
                                                                 // the dependency in the chunk's list; the row is deps[dep_begin + k]
 constexpr uint32_t REF_IDX_MASK = (1u << 29) - 1u;
@@ -43,7 +54,9 @@ enum : int32_t {
     OPF_SIGNAL_F = 8,    // backward: another chunk reads this op's state slot, publish after the store
     OPF_TYPE_SHIFT = 8,  // forward: bits 8..11 hold the op's shape (FwdType) for the fast paths
     OPF_PUSH = 16,       // backward: park this op's assigned state in the warp's stack entry (flags >> OPF_PUSH_SHIFT) & 15
-    OPF_PUSH_SHIFT = 12
+    OPF_PUSH_SHIFT = 12,
+    OPF_CHAIN_TOP = 32,  // backward: top op of a chain segment, its parent is the bottom heavy op of the segment above
+    OPF_HEAVY = 64       // backward: on the heavy path that starts at the chunk's root (inside the chunk)
 };
 // shape of a forward op; refs are stored in the order named (leaves first, then internal children heavy -> light)
 enum FwdType : int32_t { FT_GENERIC = 0, FT_LEAF_LEAF = 1, FT_LEAF_ACC = 2, FT_LEAF_INT = 3, FT_INT_ACC = 4 };
@@ -54,7 +67,7 @@ struct FwdOp {  // 32 bytes; the op index is also the node's row ("slot") in the
     int32_t flags;
     int32_t max_arity_bits;  // Sankoff counter width class for this op: 2, 4, 8 or 20
     uint32_t ref0, ref1;     // copies of the first two refs, so that binary ops never touch refs[]
-    int32_t pad0, pad1;
+    int32_t row0, row1;      // their rows (leaf slot / set-matrix op), resolved through deps[] for external refs
 };
 
 struct BwdOp {  // 32 bytes
@@ -72,9 +85,12 @@ struct BwdLeaf {
     int32_t node;
 };
 
-struct Chunk {
+struct Chunk {  // 32 bytes
     int32_t op_begin, op_end;
     int32_t dep_begin, dep_count;  // forward: ops of other chunks whose rows this chunk reads (TreeProgram::deps)
+    int32_t chain_op;              // op of this chunk holding the REF_CHAIN child (the deepest op of its heavy path), or -1
+    int32_t chain_row;             // that child's row: the top op of the chain segment below
+    int32_t pad0, pad1;
 };
 
 struct TreeProgram {

@@ -40,7 +40,7 @@ class Emulator:
         fr = None if fwd_root_ref is None else np.ascontiguousarray(fwd_root_ref, np.int8)
         lp = None if leaf_present is None else np.ascontiguousarray(leaf_present, np.uint8)
         off = np.zeros(tree.n_nodes + 1, np.int64)
-        stats = np.zeros(4, np.int32)
+        stats = np.zeros(8, np.int32)
 
         def call(pos, tc, states):
             return self.L.emul_run(

@@ -30,6 +30,8 @@ struct Emu {
     bool have_present = false;
     std::vector<unsigned> done, fdone;   // dependency flags, as in the kernels (value 1 = published this run)
     bool order_violation = false;        // an item read data of an item that had not run yet (would be a wait/deadlock)
+    bool spec_mismatch = false;          // a speculatively resolved value differed from the exact one
+    long long spec_items = 0, spec_resolved = 0;
     std::vector<unsigned long long> dir;
     std::vector<uint16_t> staging;
     unsigned long long pool = 0;
@@ -96,8 +98,12 @@ void sankoff_fwd_op(Emu& E, const Chunk& ck, const FwdOp& f, int tile, int lane,
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
         } else {
-            if (ref & REF_EXT) idx = uint32_t(E.P.deps[ck.dep_begin + idx]);
-            if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+            if (kind == REF_CHAIN) {
+                if (E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+            } else {
+                if (ref & REF_EXT) idx = uint32_t(E.P.deps[ck.dep_begin + idx]);
+                if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+            }
             const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256;
             uint32_t G[16];
             load16(base, lane, G);
@@ -118,7 +124,89 @@ void forward_item(Emu& E, int chunk, int tile) {
     static thread_local uint32_t acc[32][16], accH[32][16];
     memset(acc, 0, sizeof acc);
     memset(accH, 0, sizeof accH);
-    for (int op = ck.op_begin; op < ck.op_end; op++) {
+    // ---- chain segment, as in fitch_forward_kernel: bounds on the unknown input until every column is resolved
+    const bool spec = E.algo == 0 && ck.chain_op >= 0 && !E.have_present;
+    int first = ck.op_begin, resolved = -1;
+    auto on_path = [&](const FwdOp& f, int op, int head) {
+        for (int r = 0; r < f.n_refs; r++) {
+            uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30;
+            if (kind == REF_CHAIN) return true;
+            if (head < 0) continue;
+            if (kind == REF_ACC && head == op - 1) return true;
+            if (kind == REF_INT && !(ref & REF_EXT) && int(ref & REF_IDX_MASK) == head) return true;
+        }
+        return false;
+    };
+    auto fold_known = [&](const FwdOp& f, int op, int head, int lane, bool acc_regs, FitchFold& fold) {
+        fold.reset();
+        for (int r = 0; r < f.n_refs; r++) {
+            uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
+            if (kind == REF_CHAIN) continue;
+            if (kind == REF_LEAF) {
+                U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
+                uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                fold.add_leaf(cc, 0xFFFFFFFFu);
+            } else if (kind == REF_ACC) {
+                if (head >= 0 && head == op - 1) continue;
+                if (acc_regs) fold.add_set(acc[lane]);
+                else {
+                    uint32_t S[16];
+                    load16(E.sets.data() + ((size_t)tile * E.P.n_internal + (op - 1)) * 128, lane, S);
+                    fold.add_set(S);
+                }
+            } else {
+                if (!(ref & REF_EXT) && head >= 0 && int(idx) == head) continue;
+                idx = row_of(ref);
+                if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                uint32_t S[16];
+                load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 128, lane, S);
+                fold.add_set(S);
+            }
+        }
+    };
+    auto root_ref = [&](int lane, uint32_t S[16]) {
+        const U4* cp = E.colparams.data() + (size_t)tile * 128;
+        U4 rc = cp[64 + lane];
+        uint32_t rv = cp[96 + lane].y, r4[4] = {rc.x, rc.y, rc.z, rc.w}, d[16];
+        decode16(r4, d);
+        for (int k = 0; k < 16; k++) S[k] = (rv & d[k]) | (~rv & S[k]);
+    };
+    if (spec) {
+        static thread_local FitchInterval iv[32];
+        for (auto& x : iv) x.reset();
+        int head = -1;
+        first = ck.op_end;
+        for (int op = ck.op_begin; op < ck.op_end; op++) {
+            const FwdOp f = E.P.fwd_ops[op];
+            const bool path = on_path(f, op, head);
+            uint32_t open = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                FitchFold fold;
+                fold_known(f, op, head, lane, true, fold);
+                if (!path) {
+                    fold.finish(acc[lane]);
+                    store16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, acc[lane]);
+                    continue;
+                }
+                iv[lane].step(fold.A, fold.O);
+                if ((f.flags & OPF_ROOT) && !(E.flags & 1)) { root_ref(lane, iv[lane].lo); root_ref(lane, iv[lane].hi); }
+                open |= iv[lane].open();
+            }
+            if (!path) continue;
+            head = op;
+            if (!open) {
+                for (int lane = 0; lane < 32; lane++) {
+                    for (int k = 0; k < 16; k++) acc[lane][k] = iv[lane].lo[k];
+                    store16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, acc[lane]);
+                }
+                if (f.flags & OPF_SIGNAL) E.done[(size_t)tile * E.P.n_internal + op] = 1;
+                resolved = op;
+                first = op + 1;
+                break;
+            }
+        }
+    }
+    for (int op = first; op < ck.op_end; op++) {
         const FwdOp f = E.P.fwd_ops[op];
         for (int lane = 0; lane < 32; lane++) {
             if (E.algo == 0) {
@@ -163,8 +251,12 @@ void forward_item(Emu& E, int chunk, int tile) {
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc[lane]);
                     } else {
-                        idx = row_of(ref);
-                        if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                        if (kind == REF_CHAIN) {
+                            if (E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                        } else {
+                            idx = row_of(ref);
+                            if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                        }
                         uint32_t S[16];
                         load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 128, lane, S);
                         fold.add_set(S);
@@ -222,6 +314,41 @@ void forward_item(Emu& E, int chunk, int tile) {
         }
         if (f.flags & OPF_SIGNAL) E.done[(size_t)tile * E.P.n_internal + op] = 1;
     }
+    if (spec) {  // redo the path ops before the resolved one with the real input
+        if (E.done[(size_t)tile * E.P.n_internal + ck.chain_row] != 1) E.order_violation = true;
+        static thread_local uint32_t S[32][16];
+        for (int lane = 0; lane < 32; lane++) load16(E.sets.data() + ((size_t)tile * E.P.n_internal + ck.chain_row) * 128, lane, S[lane]);
+        const int end = resolved >= 0 ? resolved : ck.op_end;
+        int head = -1;
+        for (int op = ck.chain_op; op < end; op++) {
+            const FwdOp f = E.P.fwd_ops[op];
+            if (!on_path(f, op, head)) continue;
+            for (int lane = 0; lane < 32; lane++) {
+                FitchFold fold;
+                fold_known(f, op, head, lane, false, fold);
+                fold.add_set(S[lane]);
+                fold.finish(S[lane]);
+                if ((f.flags & OPF_ROOT) && !(E.flags & 1)) root_ref(lane, S[lane]);
+                store16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, S[lane]);
+            }
+            if (f.flags & OPF_SIGNAL) E.done[(size_t)tile * E.P.n_internal + op] = 1;
+            head = op;
+        }
+        if (resolved >= 0) {  // the speculation must have produced what the exact evaluation gives
+            const FwdOp f = E.P.fwd_ops[resolved];
+            for (int lane = 0; lane < 32; lane++) {
+                FitchFold fold;
+                fold_known(f, resolved, head, lane, false, fold);
+                fold.add_set(S[lane]);
+                uint32_t X[16], Y[16];
+                fold.finish(X);
+                if ((f.flags & OPF_ROOT) && !(E.flags & 1)) root_ref(lane, X);
+                load16(E.sets.data() + ((size_t)tile * E.P.n_internal + resolved) * 128, lane, Y);
+                for (int k = 0; k < 16; k++)
+                    if (X[k] != Y[k]) E.spec_mismatch = true;
+            }
+        }
+    }
 }
 
 void backward_item(Emu& E, int chunk, int tile) {
@@ -231,8 +358,40 @@ void backward_item(Emu& E, int chunk, int tile) {
     static thread_local uint32_t stack[BWD_STACK_DEPTH][160];
     for (auto& e : stack) for (auto& w : e) w = 0xDEADBEEFu;
     const int J = E.algo == 0 ? 128 : 256;
-    for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
+    const int last = ck.op_end - 1;
+    int resolved = -1;
+    uint32_t specF[32][4] = {}, specVis[32] = {};
+    if (E.algo == 0 && !E.have_present && (E.P.bwd_ops[last].flags & OPF_CHAIN_TOP)) {
+        E.spec_items++;
+        static thread_local uint32_t Q[32][16];
+        for (auto& q : Q) for (auto& w : q) w = 0xFFFFFFFFu;
+        for (int op = last; op >= ck.op_begin; op--) {
+            if (op != last && !(E.P.bwd_ops[op].flags & OPF_HEAVY)) continue;
+            uint32_t open = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                uint32_t S[16];
+                load16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, S);
+                fitch_candidates_step(Q[lane], S);
+                open |= candidates_open(Q[lane]);
+            }
+            if (!open) {
+                resolved = op;
+                E.spec_resolved++;
+                for (int lane = 0; lane < 32; lane++) {
+                    encode16(Q[lane], specF[lane]);
+                    specVis[lane] = E.colparams[(size_t)tile * 128 + 96 + lane].z;
+                    for (int k = 0; k < 4; k++) specF[lane][k] &= specVis[lane];
+                }
+                break;
+            }
+        }
+    }
+    for (int range = (resolved >= 0 ? 0 : 1); range < 2; range++) {
+    const int hi = range == 0 ? resolved : last;
+    const int lo = (range == 1 && resolved >= 0) ? resolved : ck.op_begin;
+    for (int op = hi; op >= lo; op--) {
         const BwdOp b = E.P.bwd_ops[op];
+        const bool given = range == 0 && op == resolved, own_only = range == 1 && op == resolved;
         WarpMut wm;
         uint32_t Fw[32][4], visw[32];
         for (int lane = 0; lane < 32; lane++) {
@@ -240,8 +399,11 @@ void backward_item(Emu& E, int chunk, int tile) {
             const U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * J;
             load16(base, lane, G);
             if (E.algo == 1) load16(base + 128, lane, H);
-            uint32_t P[4], F[4], vis;
-            if (b.parent_ref == PARENT_ROOT) {
+            uint32_t P[4] = {0, 0, 0, 0}, F[4], vis;
+            if (given) {
+                for (int k = 0; k < 4; k++) F[k] = specF[lane][k];
+                vis = specVis[lane];
+            } else if (b.parent_ref == PARENT_ROOT) {
                 const U4* cp = E.colparams.data() + (size_t)tile * 128;
                 U4 pc = cp[lane], ov = cp[32 + lane], fl = cp[96 + lane];
                 P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
@@ -283,6 +445,12 @@ void backward_item(Emu& E, int chunk, int tile) {
             wm.mut[lane] = vis & differs4(F, P);
             for (int k = 0; k < 4; k++) { wm.P[lane][k] = P[k]; wm.F[lane][k] = F[k]; Fw[lane][k] = F[k]; }
             visw[lane] = vis;
+            if (own_only) {
+                if (F[0] != specF[lane][0] || F[1] != specF[lane][1] || F[2] != specF[lane][2] || F[3] != specF[lane][3] ||
+                    vis != specVis[lane])
+                    E.spec_mismatch = true;
+                continue;
+            }
             if (b.flags & OPF_PUSH) {
                 uint32_t* e = stack[(b.flags >> OPF_PUSH_SHIFT) & 15];
                 for (int k = 0; k < 4; k++) e[4 * lane + k] = F[k];
@@ -295,7 +463,8 @@ void backward_item(Emu& E, int chunk, int tile) {
             }
             store_state(E, b.node, tile, lane, F, vis);
         }
-        emit(E, b.node, tile, wm);
+        if (!given) emit(E, b.node, tile, wm);
+        if (own_only) continue;
         if (b.fslot_out >= 0 && (b.flags & OPF_SIGNAL_F)) E.fdone[(size_t)tile * std::max(1, E.P.n_fslots) + b.fslot_out] = 1;
         for (int l = 0; l < b.n_leaves; l++) {
             const BwdLeaf lf = E.P.bwd_leaves[b.leaf_begin + l];
@@ -316,6 +485,7 @@ void backward_item(Emu& E, int chunk, int tile) {
             accVis[lane] = visw[lane];
         }
     }
+    }
 }
 
 }  // namespace
@@ -329,7 +499,8 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
                    const int32_t* leaf_row, int chunk_nodes, long long n_cols, const uint8_t* leaf_codes,
                    const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
                    const int8_t* fwd_root_ref, long long col_base, long long* node_offsets, int32_t* pos,
-                   uint8_t* type_code, uint8_t* states_out, int32_t* prog_stats /* 4: chunks, levels, fslots, max_arity */,
+                   uint8_t* type_code, uint8_t* states_out,
+                   int32_t* prog_stats /* 8: chunks, levels, fslots, max_arity, chain segments, speculated backward items, of which resolved, 0 */,
                    int inline_nodes, int level_mode) {
     Emu E;
     std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, inline_nodes, &E.P);
@@ -407,7 +578,15 @@ long long emul_run(int algo, int block_mode, int n_nodes, int root, const int32_
             for (int k = P.level_chunk_begin[l + 1] - 1; k >= P.level_chunk_begin[l]; k--)
                 for (int t = E.T - 1; t >= 0; t--) backward_item(E, P.level_order[k], t);
     }
+    if (prog_stats) {
+        prog_stats[4] = 0;
+        for (const Chunk& ck : P.chunks) prog_stats[4] += ck.chain_op >= 0;
+        prog_stats[5] = int32_t(E.spec_items);
+        prog_stats[6] = int32_t(E.spec_resolved);
+        prog_stats[7] = 0;
+    }
     if (E.order_violation) return -7;
+    if (E.spec_mismatch) return -8;
     if (E.error & 1) return -4;
     // node_count + scan + gather
     long long run = 0;
@@ -475,5 +654,91 @@ extern "C" int emul_prog_stats(int n_nodes, int root, const int32_t* child_off, 
     out[0] = NC; out[1] = P.n_levels(); out[2] = P.n_fslots; out[3] = P.max_arity; out[4] = largest;
     out[5] = P.chunks[chunk_of_op[P.node_op[root]]].op_end - P.chunks[chunk_of_op[P.node_op[root]]].op_begin;
     out[6] = best; out[7] = tiny;
+    return 0;
+}
+
+// Soundness of the speculation bounds (plane_math.h FitchInterval / fitch_candidates_step), column by column against
+// plain integer arithmetic on random inputs: the true value always lies within the bounds, and wherever the bounds
+// say "known" they are the true value. Returns 0, or the 1-based number of the first failing trial.
+extern "C" int emul_speculation_selftest(unsigned long long seed, int trials) {
+    auto rnd = [&]() {
+        seed += 0x9E3779B97F4A7C15ull;
+        unsigned long long z = seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto rand_set = [&](int style) -> unsigned {  // non-empty 16-bit set
+        unsigned s;
+        if (style == 0) s = 1u << (rnd() % 4);                       // one of four one-hot states (alignment-like)
+        else if (style == 1) s = 1u << (rnd() % 16);
+        else if (style == 2) s = unsigned(rnd() & rnd() & 0xFFFFu);  // sparse
+        else s = unsigned(rnd() & 0xFFFFu);
+        return s ? s : 1u;
+    };
+    for (int t = 0; t < trials; t++) {
+        const int steps = 1 + int(rnd() % 12);
+        // ---- forward: 32 independent columns per trial
+        unsigned S[32];
+        FitchInterval iv;
+        iv.reset();
+        const int style = int(rnd() % 4);
+        for (int j = 0; j < 32; j++) S[j] = rand_set(int(rnd() % 4));
+        for (int s = 0; s < steps; s++) {
+            unsigned A[32], O[32];
+            uint32_t Ap[16] = {}, Op[16] = {};
+            for (int j = 0; j < 32; j++) {
+                const int nk = int(rnd() % 3);  // 0 known children: a unary node
+                A[j] = 0xFFFFu;
+                O[j] = 0;
+                for (int c = 0; c < nk; c++) {
+                    unsigned x = rand_set(style);
+                    A[j] &= x;
+                    O[j] |= x;
+                }
+                for (int k = 0; k < 16; k++) {
+                    if ((A[j] >> k) & 1) Ap[k] |= 1u << j;
+                    if ((O[j] >> k) & 1) Op[k] |= 1u << j;
+                }
+                S[j] = (S[j] & A[j]) ? (S[j] & A[j]) : (S[j] | O[j]);
+            }
+            iv.step(Ap, Op);
+            const uint32_t open = iv.open();
+            for (int j = 0; j < 32; j++) {
+                unsigned lo = 0, hi = 0;
+                for (int k = 0; k < 16; k++) {
+                    lo |= ((iv.lo[k] >> j) & 1u) << k;
+                    hi |= ((iv.hi[k] >> j) & 1u) << k;
+                }
+                if ((lo & ~S[j]) || (S[j] & ~hi)) return t + 1;
+                if (!((open >> j) & 1u) && lo != S[j]) return t + 1;
+            }
+        }
+        // ---- backward
+        unsigned P[32];
+        uint32_t Q[16];
+        for (int k = 0; k < 16; k++) Q[k] = 0xFFFFFFFFu;
+        for (int j = 0; j < 32; j++) P[j] = unsigned(rnd() % 16);
+        for (int s = 0; s < steps; s++) {
+            uint32_t Sp[16] = {};
+            for (int j = 0; j < 32; j++) {
+                unsigned x = rand_set(style);
+                for (int k = 0; k < 16; k++)
+                    if ((x >> k) & 1) Sp[k] |= 1u << j;
+                if (!((x >> P[j]) & 1u)) P[j] = unsigned(__builtin_ctz(x));
+            }
+            fitch_candidates_step(Q, Sp);
+            const uint32_t open = candidates_open(Q);
+            uint32_t code[4];
+            encode16(Q, code);
+            for (int j = 0; j < 32; j++) {
+                if (!((Q[P[j]] >> j) & 1u)) return t + 1;
+                if (!((open >> j) & 1u)) {
+                    unsigned c = ((code[0] >> j) & 1u) | (((code[1] >> j) & 1u) << 1) | (((code[2] >> j) & 1u) << 2) | (((code[3] >> j) & 1u) << 3);
+                    if (c != P[j]) return t + 1;
+                }
+            }
+        }
+    }
     return 0;
 }

@@ -63,3 +63,39 @@ def test_emulation_sankoff_root_undefined(emu):
     assert rc == -4
     rc, got, _, _ = emu.run(tree, 1, codes, np.zeros(10, np.uint8), np.full(10, 2, np.int8), None, np.zeros(6, np.uint8))
     assert rc == 0 and got.node_offsets[-1] == 10  # only the forced root differs from the '-' consensus
+
+
+def test_speculation_bounds_selftest(emu):
+    """plane_math.h FitchInterval / fitch_candidates_step against plain integer arithmetic, column by column."""
+    import ctypes as C
+
+    emu.L.emul_speculation_selftest.argtypes = [C.c_ulonglong, C.c_int]
+    assert emu.L.emul_speculation_selftest(2024, 50000) == 0
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.02, 0.7])
+def test_emulation_chain_segments(emu, port, noise):
+    """Deep trees cut into chain segments that are evaluated speculatively (tree_program.h): conserved columns resolve
+    after a couple of ops, noisy ones never do and fall back to waiting -- both must equal the oracle."""
+    rng = np.random.default_rng(int(noise * 100) + 3)
+    for trial in range(12):
+        kind = ["caterpillar", "unary", "polytomy"][trial % 3]
+        tree = random_tree(int(rng.integers(40, 260)), 4000 + trial, kind, max_arity=3)
+        n_cols = int(rng.choice([40, 1024, 1500]))
+        base = rng.integers(0, 5, size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        codes = np.where(rng.random(codes.shape) < noise, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+        pc = rng.integers(0, 16, size=n_cols).astype(np.uint8)
+        ro = np.where(rng.random(n_cols) < 0.3, rng.integers(0, 16, size=n_cols), -1).astype(np.int8) if trial % 2 else None
+        fr = np.where(rng.random(n_cols) < 0.3, rng.integers(0, 16, size=n_cols), -1).astype(np.int8) if trial % 4 == 0 else None
+        for algo in (0, 1):
+            want, want_states = port.run(tree, algo, codes, pc, ro, fr if algo == 0 else None, None, 0, n_threads=2, want_states=True)
+            rc, got, states, stats = emu.run(tree, algo, codes, pc, ro, fr if algo == 0 else None, None, 0,
+                                             chunk_nodes=int(rng.choice([1, 2, 4, 9])), inline_nodes=int(rng.choice([0, 1, 3])),
+                                             level_mode=trial % 2)
+            assert rc == 0, (rc, trial, algo)
+            assert got.same_as(want) and np.array_equal(states, want_states), (trial, algo, kind)
+            if kind == "caterpillar":
+                assert stats[4] > 0, "the tree was expected to be cut into chain segments"
+                if algo == 0 and noise == 0.0:
+                    assert stats[5] > 0 and stats[6] == stats[5]

@@ -204,6 +204,35 @@ def test_caterpillar_depth(ctx, port):
     assert _same(ctx.download(), want)
 
 
+@pytest.mark.parametrize("noise", [0.0, 0.02, 0.7])
+def test_chain_segments(ctx, port, noise):
+    """Deep trees are cut into chain segments that run concurrently and speculatively (tree_program.h): conserved
+    columns resolve after a couple of ops, noisy ones never do and fall back to waiting for the neighbour segment."""
+    rng = np.random.default_rng(int(noise * 100) + 3)
+    for trial in range(8):
+        kind = ["caterpillar", "unary"][trial % 2]
+        tree = random_tree(int(rng.integers(200, 3000)), 4100 + trial, kind, max_arity=3)
+        n_cols = int(rng.choice([700, 2048, 4100]))
+        base = rng.integers(0, 5, size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        codes = np.where(rng.random(codes.shape) < noise, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+        pc = rng.integers(0, 16, size=n_cols).astype(np.uint8)
+        ro = np.where(rng.random(n_cols) < 0.3, rng.integers(0, 16, size=n_cols), -1).astype(np.int8) if trial % 2 else None
+        fr = np.where(rng.random(n_cols) < 0.3, rng.integers(0, 16, size=n_cols), -1).astype(np.int8) if trial % 4 == 0 else None
+        ctx.set_option("chunk_nodes", int(rng.choice([2, 5, 16, 64])))
+        ctx.set_option("inline_nodes", int(rng.choice([0, 1, 3])))
+        ctx.set_option("schedule", int(trial % 4 != 3))
+        _set_tree(ctx, tree)
+        for algo in (0, 1):
+            want, want_states = port.run(tree, algo, codes, pc, ro, fr if algo == 0 else None, None, 0, n_threads=4, want_states=True)
+            res = ctx.run_codes(tree, algo, codes, pc, ro, fr if algo == 0 else None, None, 0, want_states=True)
+            assert _same(res, want), (noise, trial, algo, kind)
+            assert np.array_equal(res.states, want_states), (noise, trial, algo)
+    ctx.set_option("chunk_nodes", 0)
+    ctx.set_option("inline_nodes", 3)
+    ctx.set_option("schedule", 1)
+
+
 def test_async_runs_and_shard_merge(ctx, port):
     """Two column-range shards (two contexts on this GPU, as two ranks would hold them) run asynchronously, are packed
     (pmb_pack_result) and merged (pmb_merge_packed): the merged lists equal the single-range result."""
