@@ -73,6 +73,7 @@ struct pmb_ctx {
     int64_t opt_trace = 0;            // debug: record a per-item timeline (pmb_debug_trace)
     DevBuf d_trace;
     std::vector<unsigned long long> h_trace;
+    int64_t opt_bwd_tail = 20;        // tenths of a machine-full of warps whose items form the backward pass' sorted tail
     int64_t opt_col_groups = 0;       // column-tile groups run on separate streams (0 = chosen from the tile count)
     static constexpr int MAX_GROUPS = 16;
     cudaStream_t gstream[MAX_GROUPS] = {};
@@ -88,7 +89,7 @@ struct pmb_ctx {
     int32_t n_nodes = 0, root = -1;
     std::vector<int32_t> child_off, child_idx, leaf_row;
     TreeProgram prog;
-    int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1;
+    int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1, prog_tail = -1;
     DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order, d_row_slot, d_deps;
 
     // resident input
@@ -154,9 +155,12 @@ int32_t pick_chunk_nodes(const pmb_ctx* c) {
 int ensure_program(pmb_ctx* c) {
     int32_t k = pick_chunk_nodes(c);
     int32_t inl = int32_t(std::max<int64_t>(0, std::min<int64_t>(c->opt_inline_nodes, 1 << 20)));
-    if (k == c->prog_chunk_nodes && inl == c->prog_inline_nodes) return PMB_OK;
+    // backward tail: enough short items to cover opt_bwd_tail / 10 times the warps the GPU holds at once
+    const int64_t resident_warps = int64_t(c->n_sms) * 5 * WARPS_PER_BLOCK;
+    const int32_t tail = int32_t(std::min<int64_t>(1 << 30, std::max<int64_t>(0, c->opt_bwd_tail) * resident_warps / 10 / std::max(1, c->T)));
+    if (k == c->prog_chunk_nodes && inl == c->prog_inline_nodes && tail == c->prog_tail) return PMB_OK;
     std::string e = build_tree_program(c->n_nodes, c->root, c->child_off.data(), c->child_idx.data(), c->leaf_row.data(), k,
-                                       inl, &c->prog);
+                                       inl, &c->prog, tail);
     if (!e.empty()) return fail(c, PMB_ERR_INVALID, e);
     int rc;
     if ((rc = upload_vec(c, c->d_fwd_ops, c->prog.fwd_ops))) return rc;
@@ -171,6 +175,7 @@ int ensure_program(pmb_ctx* c) {
     PMB_CUDA(cudaStreamSynchronize(c->stream));  // the vectors above may be rebuilt before the copies ran
     c->prog_chunk_nodes = k;
     c->prog_inline_nodes = inl;
+    c->prog_tail = tail;
     return PMB_OK;
 }
 
@@ -335,6 +340,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "inline_nodes") c->opt_inline_nodes = value;
     else if (k == "schedule") c->opt_schedule = value;
     else if (k == "col_groups") c->opt_col_groups = value;
+    else if (k == "bwd_tail") c->opt_bwd_tail = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
@@ -463,8 +469,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     PMB_CUDA(c->d_offsets.ensure(size_t(P.n_nodes + 1) * sizeof(long long)));
     if (c->staging_cap == 0) {
         unsigned long long cells = (unsigned long long)P.n_nodes * (unsigned long long)c->n_cols;
+        // default: one record per 32 cells, plus the part of a reserved block every resident warp may leave unused
         unsigned long long cap = c->opt_staging_records > 0 ? (unsigned long long)c->opt_staging_records
-                                                            : std::max<unsigned long long>(1ull << 20, cells / 32);
+                                                            : std::max<unsigned long long>(1ull << 20, cells / 32) +
+                                                                  (unsigned long long)c->n_sms * 8 * WARPS_PER_BLOCK * 512ull;
         c->staging_cap = cap;
     }
 
@@ -583,9 +591,11 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
                      (long long)ecol + (long long)c->col_base);
             return fail(c, PMB_ERR_SANKOFF_ROOT, buf);
         }
-        if (total > c->staging_cap) {  // denser than provisioned: size exactly and redo the backward pass
-            if (attempt >= 2) return fail(c, PMB_ERR_INTERNAL, "staging pool overflow persisted");
-            c->staging_cap = total;
+        if (total > c->staging_cap) {  // denser than provisioned: resize and redo the backward pass
+            if (attempt >= 4) return fail(c, PMB_ERR_INTERNAL, "staging pool overflow persisted");
+            // `total` includes the unused part of the blocks the warps reserved, and which warp reserves how much differs
+            // from run to run: leave room for one more block per resident warp
+            c->staging_cap = total + total / 8 + (unsigned long long)c->n_sms * 8 * WARPS_PER_BLOCK * 512ull;
             continue;
         }
         c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 16);  // offsets[n_nodes]; the pool also holds slack

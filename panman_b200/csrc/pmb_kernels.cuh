@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
         // is processed first, then -- once the segment above has published -- the ops above it, and its own record.
         int resolved = -1;
         uint32_t specF[4] = {0, 0, 0, 0}, specVis = 0;
-        if (p.leaf_present == nullptr && (__ldg(&p.bwd_ops[last].flags) & OPF_CHAIN_TOP)) {
+        if (p.leaf_present == nullptr && (ck.flags & CHUNK_CHAIN_TOP)) {
             uint32_t Q[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) Q[k] = FULL;

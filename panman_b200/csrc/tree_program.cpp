@@ -6,7 +6,8 @@
 namespace pmb {
 
 std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* child_off, const int32_t* child_idx,
-                               const int32_t* leaf_row, int32_t chunk_nodes, int32_t inline_nodes, TreeProgram* out) {
+                               const int32_t* leaf_row, int32_t chunk_nodes, int32_t inline_nodes, TreeProgram* out,
+                               int32_t bwd_tail_chunks) {
     TreeProgram& P = *out;
     P = TreeProgram();
     if (n_nodes < 2) return "tree needs at least one internal node and one leaf";
@@ -219,6 +220,24 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         if (est[oa] != est[ob]) return est[oa] < est[ob];
         return tmp[oa].nodes.size() > tmp[ob].nodes.size();
     });
+    if (bwd_tail_chunks > 0) {
+        // A chunk without child chunks can take any later ticket. The smallest of them go last, largest first: the
+        // kernel then drains through short items instead of whatever happened to sit deepest in the tree.
+        std::vector<int32_t> term;
+        for (int32_t k = 0; k < NC; k++)
+            if (n_kids[fwd_order[k]] == 0) term.push_back(k);
+        std::stable_sort(term.begin(), term.end(),
+                         [&](int32_t a, int32_t b) { return tmp[fwd_order[a]].nodes.size() < tmp[fwd_order[b]].nodes.size(); });
+        if (int32_t(term.size()) > bwd_tail_chunks) term.resize(bwd_tail_chunks);
+        std::vector<char> in_tail(NC, 0);
+        for (int32_t k : term) in_tail[k] = 1;
+        std::vector<int32_t> order;
+        order.reserve(NC);
+        for (int32_t k : P.bwd_order)
+            if (!in_tail[k]) order.push_back(k);
+        for (auto it = term.rbegin(); it != term.rend(); ++it) order.push_back(*it);
+        P.bwd_order.swap(order);
+    }
     P.level_order.resize(NC);
     std::iota(P.level_order.begin(), P.level_order.end(), 0);
     std::stable_sort(P.level_order.begin(), P.level_order.end(), [&](int32_t a, int32_t b) {
@@ -314,7 +333,10 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
             bool acc = (pop == i + 1) && chunk_of[v] == chunk_of[parent[v]];
             b.parent_ref = acc ? PARENT_ACC : fslot[pop];
             if (chunk_of[v] != chunk_of[parent[v]]) b.flags |= OPF_PARENT_EXT;
-            if (chain_cut[v]) b.flags |= OPF_CHAIN_TOP;
+            if (chain_cut[v]) {
+                b.flags |= OPF_CHAIN_TOP;
+                P.chunks[new_id[chunk_of[v]]].flags |= CHUNK_CHAIN_TOP;
+            }
         }
     }
     P.max_arity = max_arity;

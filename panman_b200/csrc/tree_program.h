@@ -85,12 +85,14 @@ struct BwdLeaf {
     int32_t node;
 };
 
+enum : int32_t { CHUNK_CHAIN_TOP = 1 };
 struct Chunk {  // 32 bytes
     int32_t op_begin, op_end;
     int32_t dep_begin, dep_count;  // forward: ops of other chunks whose rows this chunk reads (TreeProgram::deps)
     int32_t chain_op;              // op of this chunk holding the REF_CHAIN child (the deepest op of its heavy path), or -1
     int32_t chain_row;             // that child's row: the top op of the chain segment below
-    int32_t pad0, pad1;
+    int32_t flags;                 // CHUNK_CHAIN_TOP: the chunk is a chain segment with another segment above it
+    int32_t pad1;
 };
 
 struct TreeProgram {
@@ -118,7 +120,10 @@ struct TreeProgram {
 
 // Returns "" on success, else a message. chunk_nodes = largest bottom subtree kept in one chunk (>= 1);
 // inline_nodes = light subtrees up to this size are evaluated inside their parent's chunk (0 = never).
+// bwd_tail_chunks = that many of the smallest chunks without child chunks get the LAST backward tickets, largest first,
+// so that the persistent kernel drains through short items (0 = plain earliest-start order).
 std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* child_off, const int32_t* child_idx,
-                               const int32_t* leaf_row, int32_t chunk_nodes, int32_t inline_nodes, TreeProgram* out);
+                               const int32_t* leaf_row, int32_t chunk_nodes, int32_t inline_nodes, TreeProgram* out,
+                               int32_t bwd_tail_chunks = 0);
 
 }  // namespace pmb

@@ -361,7 +361,7 @@ void backward_item(Emu& E, int chunk, int tile) {
     const int last = ck.op_end - 1;
     int resolved = -1;
     uint32_t specF[32][4] = {}, specVis[32] = {};
-    if (E.algo == 0 && !E.have_present && (E.P.bwd_ops[last].flags & OPF_CHAIN_TOP)) {
+    if (E.algo == 0 && !E.have_present && (ck.flags & CHUNK_CHAIN_TOP)) {
         E.spec_items++;
         static thread_local uint32_t Q[32][16];
         for (auto& q : Q) for (auto& w : q) w = 0xFFFFFFFFu;

@@ -23,3 +23,25 @@ def load_cases():
             leaf_present=z[p + "leaf_present"] if p + "leaf_present" in z else None,
             expect=MutLists(z[p + "node_offsets"], z[p + "pos"], z[p + "type_code"]), states=z[p + "states"]))
     return cases
+
+
+SARS20_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sars20_pangraph.npz")
+
+
+def load_sars20():
+    """BASELINE.json configs[0] as column batches (tests/golden/make_sars20_golden.py): returns (tree, batches); a batch is
+    a dict in the pmb_run_nuc convention with expect[algo] = (MutLists, states) from the verbatim reference. The first
+    batch is the block-level pass (3-state, block mode), the others are the nucleotide columns of one block each."""
+    z = np.load(SARS20_PATH)
+    tree = parse_newick(bytes(z["newick"]).decode())
+    nb = int(z["n_blocks"][0])
+    batches = [dict(id="blocks", block=1, codes=z["blk_codes"], present=None, parent_code=np.zeros(nb, np.uint8),
+                    root_override={0: None, 1: None},
+                    expect={a: (MutLists(z[f"blk_a{a}_off"], z[f"blk_a{a}_pos"], z[f"blk_a{a}_tc"]), z[f"blk_a{a}_states"]) for a in (0, 1)})]
+    for i in range(nb):
+        p = f"b{i}_"
+        batches.append(dict(id=f"block{i}", block=0, codes=z[p + "codes"], present=z[p + "present"], parent_code=z[p + "parent_code"],
+                            root_override={0: z[p + "root_override"], 1: None}, col_j=z[p + "col_j"], col_k=z[p + "col_k"],
+                            expect={a: (MutLists(z[p + f"a{a}_off"], z[p + f"a{a}_pos"], z[p + f"a{a}_tc"]), z[p + f"a{a}_states"])
+                                    for a in (0, 1)}))
+    return tree, batches
