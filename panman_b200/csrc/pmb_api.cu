@@ -80,6 +80,8 @@ struct pmb_ctx {
     cudaEvent_t gev_fwd[MAX_GROUPS] = {}, gev_done[MAX_GROUPS] = {}, ev_fork = nullptr;
     int n_sms = 0;
     unsigned int epoch = 0;
+    unsigned int dir_clean_epoch = 0;  // epoch at which the staging directory was last cleared (0 = never)
+    bool state_dirty = true;           // per-run device state (counters, tickets, node counts, directory) must be re-initialised
     unsigned int pack_seq = 0;
     bool async_pending = false;
     int async_groups = 1;
@@ -161,6 +163,12 @@ int ensure_program(pmb_ctx* c) {
     if (k == c->prog_chunk_nodes && inl == c->prog_inline_nodes && tail == c->prog_tail) return PMB_OK;
     std::string e = build_tree_program(c->n_nodes, c->root, c->child_off.data(), c->child_idx.data(), c->leaf_row.data(), k,
                                        inl, &c->prog, tail);
+    if (e.empty() && c->opt_chunk_nodes <= 0 && c->prog.n_chain_segments > 0 && k > 128) {
+        // a deep tree: its chain segments run independently of each other (speculative evaluation), so shorter
+        // segments cost nothing in dependencies and balance better (measured: caterpillar 100k x 30k)
+        e = build_tree_program(c->n_nodes, c->root, c->child_off.data(), c->child_idx.data(), c->leaf_row.data(), 128, inl, &c->prog,
+                               tail);
+    }
     if (!e.empty()) return fail(c, PMB_ERR_INVALID, e);
     int rc;
     if ((rc = upload_vec(c, c->d_fwd_ops, c->prog.fwd_ops))) return rc;
@@ -201,7 +209,7 @@ int launch_kernel(pmb_ctx* c, cudaStream_t stream, K kernel, size_t smem, const 
         PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, smem));
         long long resident = (long long)std::max(1, per_sm) * c->n_sms;
         blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
-        PMB_CUDA(cudaMemsetAsync(rp.ticket, 0, sizeof(unsigned long long), stream));
+        // the ticket is zero: finish_run_kernel of the previous run (or the initial clearing) left it so
     } else {
         blocks = unsigned((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     }
@@ -243,9 +251,13 @@ int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParam
     const size_t fwd_smem_s = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 5) * 32 + FWD_META_U4) * sizeof(uint4);
     const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (4 + 2) * 32 + BWD_META_U4 + BWD_STACK_U4) * sizeof(uint4);
     const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (8 + 2) * 32 + BWD_META_U4 + BWD_STACK_U4) * sizeof(uint4);
-    if (algo == PMB_ALGO_FITCH)
-        return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel, fwd_smem, rp, true, n_launches)
-                       : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel, bwd_smem_f, rp, false, n_launches);
+    if (algo == PMB_ALGO_FITCH) {
+        if (P.n_chain_segments > 0)
+            return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel<true>, fwd_smem, rp, true, n_launches)
+                           : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel<true>, bwd_smem_f, rp, false, n_launches);
+        return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel<false>, fwd_smem, rp, true, n_launches)
+                       : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel<false>, bwd_smem_f, rp, false, n_launches);
+    }
     if (!forward) return launch_schedule(c, stream, ticket_slot, sankoff_backward_kernel, bwd_smem_s, rp, false, n_launches);
     if (P.max_arity <= 3) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<2>, fwd_smem_s, rp, true, n_launches);
     if (P.max_arity <= 15) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<4>, fwd_smem_s, rp, true, n_launches);
@@ -445,24 +457,22 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     PMB_CUDA(c->d_fstore.ensure(std::max<size_t>(16, size_t(P.n_fslots) * T * FSLOT_WORDS * sizeof(uint32_t))));
     const bool want_states = flags & PMB_FLAG_WANT_STATES;
     if (want_states) PMB_CUDA(c->d_states_planes.ensure(size_t(P.n_nodes) * T * 64 * sizeof(uint4)));
-    PMB_CUDA(c->d_dir.ensure(size_t(P.n_nodes) * T * sizeof(unsigned long long)));
+    const size_t dir_bytes = size_t(P.n_nodes) * T * sizeof(unsigned long long);
+    if (dir_bytes > c->d_dir.cap) c->dir_clean_epoch = 0;
+    PMB_CUDA(c->d_dir.ensure(dir_bytes));
     if (!c->d_counters.p) {
         PMB_CUDA(c->d_counters.ensure(64));
-        PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
-        unsigned int sticky_init[2] = {0u, 0xFFFFFFFFu};
-        PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 16, sticky_init, 8, cudaMemcpyHostToDevice, c->stream));
+        c->state_dirty = true;
     }
     PMB_CUDA(c->h_counters.ensure(128));
-    {   // pinned constants for the per-run counter reset (a pageable source could serialise the host with the stream)
-        unsigned int* init = c->h_counters.as<unsigned int>() + 16;
-        init[0] = 0; init[1] = 0; init[2] = 0; init[3] = 0xFFFFFFFFu;
-    }
+    if (!c->d_ticket.p) c->state_dirty = true;
     PMB_CUDA(c->d_ticket.ensure(64 * sizeof(unsigned long long)));
     {
         int rcf;
         if ((rcf = ensure_flags(c, c->d_done, size_t(P.n_internal) * T))) return rcf;
         if ((rcf = ensure_flags(c, c->d_fdone, size_t(std::max(1, P.n_fslots)) * T))) return rcf;
     }
+    if (size_t(P.n_nodes) * sizeof(unsigned int) > c->d_node_counts.cap) c->state_dirty = true;
     PMB_CUDA(c->d_node_counts.ensure(size_t(P.n_nodes) * sizeof(unsigned int)));
     const int scan_blocks = (P.n_nodes + SCAN_TILE - 1) / SCAN_TILE;
     PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
@@ -519,7 +529,19 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         *tb = int((long long)c->T * g / G);
         *tc = int((long long)c->T * (g + 1) / G) - *tb;
     };
-    PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 64 * sizeof(unsigned long long), c->stream));
+    // Per-run device state is left clean by the run before (scan_apply_kernel zeroes the node counts, finish_run_kernel
+    // the counters and tickets; directory entries carry a run tag): nothing is cleared on the stream in steady state.
+    if (c->state_dirty) {
+        PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 64 * sizeof(unsigned long long), c->stream));
+        PMB_CUDA(cudaMemsetAsync(c->d_node_counts.p, 0, c->d_node_counts.cap, c->stream));
+        PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
+        unsigned int* init = c->h_counters.as<unsigned int>() + 16;  // pinned
+        init[0] = 0xFFFFFFFFu;
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 12, init, 4, cudaMemcpyHostToDevice, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 20, init, 4, cudaMemcpyHostToDevice, c->stream));
+        c->dir_clean_epoch = 0;
+    }
+    c->state_dirty = true;  // until everything below has been enqueued
     PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     rp.epoch = ++c->epoch;
     const unsigned int fwd_epoch = rp.epoch;
@@ -529,11 +551,12 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         PMB_CUDA(c->d_tc.ensure(size_t(c->staging_cap)));
         rp.staging = c->d_staging.as<uint16_t>();
         rp.staging_cap = c->staging_cap;
-        PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, size_t(P.n_nodes) * T * sizeof(unsigned long long), c->stream));
-        PMB_CUDA(cudaMemsetAsync(c->d_node_counts.p, 0, size_t(P.n_nodes) * sizeof(unsigned int), c->stream));
-        // pool_count (64 bit), error flags, first bad column
-        PMB_CUDA(cudaMemcpyAsync(c->d_counters.p, c->h_counters.as<unsigned int>() + 16, 16, cudaMemcpyHostToDevice, c->stream));
         const unsigned int bwd_epoch = ++c->epoch;
+        if (c->dir_clean_epoch == 0 || bwd_epoch - c->dir_clean_epoch >= DIR_TAG_MASK - 8u) {  // new buffer, or the tag would wrap
+            PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, c->d_dir.cap, c->stream));
+            c->dir_clean_epoch = bwd_epoch;
+        }
+        rp.dir_tag = bwd_epoch & DIR_TAG_MASK;
         PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         for (int g = 0; g < G; g++) {
             cudaStream_t st = G == 1 ? c->stream : c->gstream[g];
@@ -558,15 +581,16 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(rp.node_count, P.n_nodes, c->d_block_sums.as<unsigned long long>(),
                                                                          c->d_offsets.as<long long>());
             unsigned blocks = unsigned(((long long)P.n_nodes * 32 + 255) / 256);
-            gather_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, rp.staging, c->d_offsets.as<long long>(), P.n_nodes, c->T,
+            gather_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, rp.dir_tag, rp.staging, c->d_offsets.as<long long>(), P.n_nodes, c->T,
                                                          c->col_base, c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(),
                                                          rp.pool_count, rp.staging_cap);
             n_launches += 3;
         }
-        sticky_status_kernel<<<1, 1, 0, c->stream>>>(rp.pool_count, rp.staging_cap, rp.error,
-                                                     reinterpret_cast<unsigned int*>(c->d_counters.as<char>() + 16));
+        finish_run_kernel<<<1, 64, 0, c->stream>>>(c->d_counters.as<unsigned long long>(), rp.staging_cap,
+                                                   c->d_ticket.as<unsigned long long>(), 64);
         PMB_CUDA(cudaGetLastError());
         PMB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        c->state_dirty = false;
         if (async) {  // status, overflow handling and timings wait for pmb_wait
             c->async_pending = true;
             c->async_groups = G;
@@ -578,7 +602,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             c->have_result = true;
             return PMB_OK;
         }
-        PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 16, cudaMemcpyDeviceToHost, c->stream));  // snapshot
         PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_offsets.as<long long>() + P.n_nodes, 8, cudaMemcpyDeviceToHost,
                                  c->stream));
         PMB_CUDA(cudaStreamSynchronize(c->stream));
@@ -641,7 +665,9 @@ int pmb_wait(pmb_ctx* c) {
     if (!c->async_pending) return PMB_OK;
     PMB_CUDA(cudaSetDevice(c->device));
     const int N = c->prog.n_nodes;
-    PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    // [0,8) snapshot of the last run's staging reservation, [16,24) sticky status of all runs since the last wait
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 8, cudaMemcpyDeviceToHost, c->stream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_counters.as<char>() + 16, 8, cudaMemcpyDeviceToHost, c->stream));
     PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 32, c->d_offsets.as<long long>() + N, 8, cudaMemcpyDeviceToHost, c->stream));
     PMB_CUDA(cudaStreamSynchronize(c->stream));
     c->async_pending = false;

@@ -49,6 +49,7 @@ struct RunParams {
     const int* order;             // item i works on chunk order[i / T]; nullptr = identity
     unsigned int* node_count;     // [node] records emitted for the node in this run
     unsigned int epoch;
+    unsigned int dir_tag;         // backward: tag of this run's directory entries (entries with another tag are stale = empty)
     int T;
     int n_ops, n_rows, n_fslots;  // matrices are TILE-major: [tile][op], [tile][leaf slot], [tile][fslot]
     int n_refs_total;
@@ -235,6 +236,10 @@ __device__ __forceinline__ uint32_t leaf_present_mask(const RunParams& p, int ro
 // the backward pass' stall samples in profiles/r01_v2). The (node, tile) directory remembers where each
 // segment went; gather_kernel later lays the segments out node-major in column order.
 // Record: column-in-tile (10 bits) | code << 10 | type << 14.
+// Directory entry: tag (13 bits) | staging base (40 bits) | count (11 bits). The tag names the run that wrote the entry,
+// so the directory needs no clearing between runs (the host clears it when the tag is about to wrap).
+constexpr int DIR_TAG_SHIFT = 51;
+constexpr unsigned DIR_TAG_MASK = 0x1FFFu;
 struct StageCursor {
     unsigned long long base = 0;
     int left = 0;
@@ -261,7 +266,7 @@ __device__ __forceinline__ void emit(const RunParams& p, StageCursor& sc, int no
     sc.base += total;
     sc.left -= total;
     if (lane == 0) {
-        p.dir[(size_t)node * p.T + tile] = (base << 11) | (unsigned long long)total;
+        p.dir[(size_t)node * p.T + tile] = ((unsigned long long)p.dir_tag << DIR_TAG_SHIFT) | (base << 11) | (unsigned long long)total;
         atomicAdd(p.node_count + node, (unsigned)total);
     }
     if (base + (unsigned long long)total > p.staging_cap) return;  // host grows the pool and reruns the pass
@@ -308,14 +313,17 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n gro
     }
 }
 
+// Measured on B200 (tools/sweep.py, profiles/r01_v8_summary.md): shallower rings and smaller windows win because shared
+// memory is what limits residency (forward 4 -> 5 blocks per SM, backward 4 -> 6), and more resident warps hide latency
+// better than a deeper per-warp ring does.
 #ifndef PMB_BWD_DEPTH
-#define PMB_BWD_DEPTH 3
+#define PMB_BWD_DEPTH 2
 #endif
 #ifndef PMB_FWD_DEPTH
-#define PMB_FWD_DEPTH 4
+#define PMB_FWD_DEPTH 3
 #endif
 #ifndef PMB_META_OPS
-#define PMB_META_OPS 32
+#define PMB_META_OPS 16
 #endif
 constexpr int FWD_DEPTH = PMB_FWD_DEPTH;  // forward: stage = 2 leaf rows + one child set row (3 KB Fitch / 3.5 KB Sankoff)
 constexpr int BWD_DEPTH = PMB_BWD_DEPTH;  // backward: stage = set row + 2 leaf rows           (3 KB Fitch / 5 KB Sankoff)
@@ -556,6 +564,8 @@ __device__ __forceinline__ void store_set16(uint4* out, const uint32_t S[16]) {
 }
 
 // ------------------------------------------------------------------ Fitch forward
+// SPEC = the program has chain segments (tree_program.h); trees without them run the leaner instantiation
+template <bool SPEC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
     constexpr int JS = 4, STAGE = (2 + JS) * 32, PER_WARP = FWD_DEPTH * STAGE + FWD_META_U4;
@@ -578,7 +588,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
         // Chain segment: the value entering from the segment below is not waited for. Bounds on it are carried up the
         // path until no column depends on it any more (op `resolved`); the plain loop continues from there and the
         // few ops before it are redone at the end, once the segment below has published.
-        const bool spec = ck.chain_op >= 0 && p.leaf_present == nullptr;
+        const bool spec = SPEC && ck.chain_op >= 0 && p.leaf_present == nullptr;
         int first = ck.op_begin, resolved = -1;
         if (spec) {
             FitchInterval iv;
@@ -665,7 +675,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                         fold.add_leaf(cc, leaf_present_mask(p, idx));
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc);
-                    } else if (kind == REF_CHAIN) {  // not speculating (presence mask): wait for the segment below
+                    } else if (SPEC && kind == REF_CHAIN) {  // not speculating (presence mask): wait for the segment below
                         if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return;
                         uint32_t S[16];
                         row_set16(tc.sets + (size_t)idx * 128, S);
@@ -799,6 +809,7 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta&
 }
 
 // ------------------------------------------------------------------ Fitch backward + mutation detection
+template <bool SPEC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
     constexpr int J = 4, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4 + BWD_STACK_U4;
@@ -823,7 +834,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
         // is processed first, then -- once the segment above has published -- the ops above it, and its own record.
         int resolved = -1;
         uint32_t specF[4] = {0, 0, 0, 0}, specVis = 0;
-        if (p.leaf_present == nullptr && (ck.flags & CHUNK_CHAIN_TOP)) {
+        if (SPEC && p.leaf_present == nullptr && (ck.flags & CHUNK_CHAIN_TOP)) {
             uint32_t Q[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) Q[k] = FULL;
@@ -1177,7 +1188,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(const unsigned in
     if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(const unsigned int* counts, int n, const unsigned long long* block_sums,
+// The counts are consumed: they are left zeroed for the next run's atomic accumulation.
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(unsigned int* counts, int n, const unsigned long long* block_sums,
                                                                 long long* offsets) {
     __shared__ unsigned long long sh[33];
     __shared__ unsigned long long warp_tot[32];
@@ -1190,6 +1202,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(const unsigned i
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         v[k] = (base + k < n) ? counts[base + k] : 0u;
+        if (base + k < n) counts[base + k] = 0u;
         s += v[k];
     }
     // inclusive scan of the per-thread sums: warp shuffle scan, then the warp totals
@@ -1224,8 +1237,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(const unsigned i
 // gather: a warp takes one node; each lane owns one tile's segment and copies it to its final place (segments are
 // short, a few records; the 32 copies of a node proceed in parallel). Nothing is done after a pool overflow: the
 // host grows the pool and reruns the backward pass.
-__global__ void gather_kernel(const unsigned long long* dir, const uint16_t* staging, const long long* offsets, int n_nodes,
-                              int T, long long col_base, int32_t* pos, uint8_t* type_code,
+__global__ void gather_kernel(const unsigned long long* dir, unsigned dir_tag, const uint16_t* staging, const long long* offsets,
+                              int n_nodes, int T, long long col_base, int32_t* pos, uint8_t* type_code,
                               const unsigned long long* pool_count, unsigned long long staging_cap) {
     if (*pool_count > staging_cap) return;
     int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1234,7 +1247,9 @@ __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* sta
     if (offsets[node + 1] == run) return;
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
-        const unsigned long long d = t < T ? dir[(size_t)node * T + t] : 0ull;
+        unsigned long long d = t < T ? dir[(size_t)node * T + t] : 0ull;
+        if (unsigned(d >> DIR_TAG_SHIFT) != dir_tag) d = 0ull;  // written by an earlier run
+        d &= (1ull << DIR_TAG_SHIFT) - 1ull;
         const int cnt = int(d & 0x7FFull);
         int incl = cnt;
 #pragma unroll
@@ -1254,12 +1269,28 @@ __global__ void gather_kernel(const unsigned long long* dir, const uint16_t* sta
     }
 }
 
-// folds the per-run status into a word that survives until pmb_wait (asynchronous runs reset the per-run counters)
-__global__ void sticky_status_kernel(const unsigned long long* pool_count, unsigned long long staging_cap, const unsigned int* error,
-                                     unsigned int* sticky) {
-    unsigned int s = error[0] | (*pool_count > staging_cap ? 4u : 0u);
-    if (s) atomicOr(sticky, s);
-    if (error[0] & 1u) atomicMin(sticky + 1, error[1]);
+// Last kernel of a run. counters: [0,8) staging records reserved, [8,12) error flags, [12,16) first bad column,
+// [16,20) sticky status, [20,24) sticky first bad column, [32,48) snapshot of [0,16) for the host.
+// Folds the status into the sticky words (they survive until pmb_wait), snapshots the per-run counters and resets
+// them and the work tickets, so that the next run starts without any clearing on the stream.
+__global__ void finish_run_kernel(unsigned long long* counters, unsigned long long staging_cap, unsigned long long* tickets,
+                                  int n_tickets) {
+    if (threadIdx.x == 0) {
+        unsigned int* error = reinterpret_cast<unsigned int*>(counters + 1);
+        unsigned int* sticky = reinterpret_cast<unsigned int*>(counters + 2);
+        const unsigned long long pool = counters[0];
+        const unsigned int e0 = error[0], e1 = error[1];
+        const unsigned int s = e0 | (pool > staging_cap ? 4u : 0u);
+        if (s) sticky[0] |= s;
+        if ((e0 & 1u) && e1 < sticky[1]) sticky[1] = e1;
+        counters[4] = pool;
+        reinterpret_cast<unsigned int*>(counters + 5)[0] = e0;
+        reinterpret_cast<unsigned int*>(counters + 5)[1] = e1;
+        counters[0] = 0ull;
+        error[0] = 0u;
+        error[1] = 0xFFFFFFFFu;
+    }
+    for (int i = threadIdx.x; i < n_tickets; i += blockDim.x) tickets[i] = 0ull;
 }
 
 // ------------------------------------------------------------------ merging column-range shards (multi-GPU)

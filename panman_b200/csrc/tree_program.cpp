@@ -340,6 +340,7 @@ std::string build_tree_program(int32_t n_nodes, int32_t root, const int32_t* chi
         }
     }
     P.max_arity = max_arity;
+    for (const Chunk& ck : P.chunks) P.n_chain_segments += ck.chain_op >= 0;
     // the heavy path that starts at each chunk's root, as far as it stays inside the chunk
     for (const TmpChunk& c : tmp)
         for (int32_t v = c.root_node;;) {

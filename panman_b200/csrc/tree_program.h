@@ -44,7 +44,7 @@ constexpr uint32_t REF_IDX_MASK = (1u << 29) - 1u;
 // per-column parameters; <= PARENT_STACK0 entry (PARENT_STACK0 - parent_ref) of the warp's shared-memory state stack
 enum : int32_t { PARENT_ACC = -1, PARENT_ROOT = -2, PARENT_STACK0 = -16 };
 #ifndef PMB_BWD_STACK_DEPTH
-#define PMB_BWD_STACK_DEPTH 5
+#define PMB_BWD_STACK_DEPTH 3
 #endif
 constexpr int32_t BWD_STACK_DEPTH = PMB_BWD_STACK_DEPTH;   // entries of the per-warp state stack (640 B each)
 enum : int32_t {
@@ -99,6 +99,7 @@ struct TreeProgram {
     int32_t n_nodes = 0, n_rows = 0, n_internal = 0, root = -1;
     int32_t n_fslots = 0;
     int32_t max_arity = 0;
+    int32_t n_chain_segments = 0;             // chunks that receive a REF_CHAIN child
     std::vector<FwdOp> fwd_ops;
     std::vector<uint32_t> refs;
     std::vector<BwdOp> bwd_ops;
