@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--leaves", type=int, default=0, help="override the leaf count (debug)")
     ap.add_argument("--chunk-nodes", type=int, default=0)
     ap.add_argument("--col-groups", type=int, default=0)
+    ap.add_argument("--reserve-sms", type=int, default=8,
+                    help="N > 1: SMs the pass kernels leave free so that the NCCL gather of step i can overlap pass i+1 (0 = serialise)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -197,6 +199,7 @@ def run_b200_arm(args):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "4")  # the gather moves a few MB: few channels = few SMs
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, algo = workload(args)
     algo_i = pb.ALGO_FITCH if algo == "fitch" else pb.ALGO_SANKOFF
@@ -216,6 +219,9 @@ def run_b200_arm(args):
         ctx.set_option("chunk_nodes", args.chunk_nodes)
     if args.col_groups:
         ctx.set_option("col_groups", args.col_groups)
+    overlap_gather = world > 1 and args.reserve_sms > 0
+    if overlap_gather:
+        ctx.set_option("reserve_sms", args.reserve_sms)
     ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
     ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro, None, None, c0)
 
@@ -235,12 +241,14 @@ def run_b200_arm(args):
         shard = dict(cap=cap, bytes=pbytes, send=[torch.empty(pbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
                      recv=[torch.empty(world * pbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if rank == 0 else None,
                      comm=torch.cuda.Stream(device=dev), lib=torch.cuda.ExternalStream(ctx.stream_handle(), device=dev), i=0,
-                     merged=None)
+                     merged=None, done=[None, None])
 
     def gather_lists():
         k = shard["i"] & 1
         shard["i"] += 1
         comm, lib = shard["comm"], shard["lib"]
+        if shard["done"][k] is not None:
+            lib.wait_event(shard["done"][k])                # the gather that last used this buffer pair has finished
         ctx.pack_result(shard["send"][k], shard["cap"])     # on the library's stream, right behind the pass
         comm.wait_stream(lib)
         with torch.cuda.stream(comm):
@@ -251,10 +259,13 @@ def run_b200_arm(args):
             done.record(comm)
             if rank == 0:
                 shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=comm.cuda_stream)
-        # The next pass starts only after the collective: the persistent pass kernels fill every SM, and an NCCL
-        # kernel that has to squeeze in beside them (on both ranks at once) stalls far longer than it runs.
-        # Rank 0's merge kernels are small and do overlap the next pass.
-        lib.wait_event(done)
+        shard["done"][k] = done
+        # The persistent pass kernels fill every SM they are given, and an NCCL kernel that has to squeeze in beside them
+        # (on both ranks at once) stalls far longer than it runs. Either the pass kernels leave a few SMs free
+        # (--reserve-sms) and the gather of step i overlaps pass i+1, or the next pass waits for the collective.
+        # Rank 0's merge kernels are small and overlap the next pass in both cases.
+        if not overlap_gather:
+            lib.wait_event(done)
 
     lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
 
@@ -357,7 +368,8 @@ def run_b200_arm(args):
                                f"{algo}, seed {cfg['seed']}; rank r owns columns [r*{C},(r+1)*{C})",
                    "l2": "inputs larger than L2: leaf planes + set matrix = "
                          f"{(tree.n_leaves * 0.5 + (N - tree.n_leaves) * (2 if algo == 'fitch' else 4)) * C / 1e6:.0f} MB per pass",
-                   "parallelism": f"column ranges x{world}, tree replicated, NCCL gather of mutation lists" if world > 1 else "single GPU",
+                   "parallelism": (f"column ranges x{world}, tree replicated, NCCL gather of mutation lists"
+                                   + (f" overlapping the next pass ({args.reserve_sms} SMs left free)" if overlap_gather else "")) if world > 1 else "single GPU",
                    "n_mut_rank0": int(n_mut)},
         "device_ms_per_step": 1e3 * dev_total / K,
         "phases_ms": {"forward": fwd, "backward": bwd, "compact": cmp_, "note": "3 synchronous passes after the timed region"},

@@ -73,6 +73,7 @@ struct pmb_ctx {
     int64_t opt_trace = 0;            // debug: record a per-item timeline (pmb_debug_trace)
     DevBuf d_trace;
     std::vector<unsigned long long> h_trace;
+    int64_t opt_reserve_sms = 0;      // SMs the persistent kernels leave free (room for a concurrent NCCL kernel)
     int64_t opt_bwd_tail = 20;        // tenths of a machine-full of warps whose items form the backward pass' sorted tail
     int64_t opt_col_groups = 0;       // column-tile groups run on separate streams (0 = chosen from the tile count)
     static constexpr int MAX_GROUPS = 16;
@@ -207,7 +208,8 @@ int launch_kernel(pmb_ctx* c, cudaStream_t stream, K kernel, size_t smem, const 
     if (rp.ticket) {
         int per_sm = 0;
         PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, smem));
-        long long resident = (long long)std::max(1, per_sm) * c->n_sms;
+        const long long sms = std::max<long long>(1, c->n_sms - std::max<int64_t>(0, std::min<int64_t>(c->opt_reserve_sms, c->n_sms - 1)));
+        long long resident = (long long)std::max(1, per_sm) * sms;
         blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
         // the ticket is zero: finish_run_kernel of the previous run (or the initial clearing) left it so
     } else {
@@ -353,6 +355,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "schedule") c->opt_schedule = value;
     else if (k == "col_groups") c->opt_col_groups = value;
     else if (k == "bwd_tail") c->opt_bwd_tail = value;
+    else if (k == "reserve_sms") c->opt_reserve_sms = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
