@@ -153,7 +153,7 @@ def run_reference_arm(args):
 
     cfg, algo = workload(args)
     tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
-    sample_cols = min(cfg["n_cols"], 2048)
+    sample_cols = int(min(cfg["n_cols"], 8192, max(512, 300_000_000 // cfg["n_leaves"])))
     codes4, pc = synth.simulate_msa(tree, 0, sample_cols, synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]))
     codes = synth.unpack_nibbles(codes4, sample_cols).numpy()
     threads = host_threads()
@@ -384,7 +384,7 @@ def run_b200_arm(args):
                      "algorithmic_bytes_per_pass": int(alg_bytes)},
     }
     if not args.no_cpu_baseline:
-        sample_cols = min(C, 512)
+        sample_cols = int(min(C, 16384, max(512, 300_000_000 // tree.n_leaves)))  # bounded by host memory; ~cpu_seconds of work
         codes = synth.unpack_nibbles(codes4[:, :(sample_cols + 1) // 2], sample_cols).cpu().numpy()
         line["cpu_baseline"] = cpu_reference_run(tree, codes, pc[:sample_cols].cpu().numpy(), algo, args.cpu_seconds, host_threads())
     print(json.dumps(line))

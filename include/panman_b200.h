@@ -92,7 +92,10 @@ const char* pmb_last_error(const pmb_ctx* ctx);
 /* Tuning knobs (all optional): "chunk_nodes" (largest bottom subtree evaluated by one warp; 0 = chosen from the
  * column count), "inline_nodes" (light subtrees up to this size stay in their parent's chunk), "schedule"
  * (1 = persistent kernels with dependency flags [default], 0 = one launch per dependency level),
- * "staging_records" (initial capacity of the mutation staging pool; 0 = chosen from the problem size). */
+ * "staging_records" (initial capacity of the mutation staging pool; 0 = chosen from the problem size),
+ * "bwd_tail" (tenths of a machine-full of warps whose items form the sorted tail of the backward tickets; default 20),
+ * "reserve_sms" (SMs the persistent kernels leave free, e.g. for an NCCL kernel running beside them; default 0),
+ * "col_groups" (column-tile groups run on separate streams; default 1), "trace" (debug timeline). */
 int pmb_set_option(pmb_ctx* ctx, const char* key, int64_t value);
 
 /* ---- tree: replaces the Node* tree walked by every reference call ----

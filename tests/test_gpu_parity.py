@@ -192,6 +192,59 @@ def test_full_size_config_vs_oracle(ctx, port, name):
             assert _replay_property(tree, res, codes, pc_h)
 
 
+def _slice_lists(res, n_nodes, a, b):
+    """Per-node records of `res` with a <= position < b, as (offsets, pos, type_code)."""
+    node = np.repeat(np.arange(n_nodes), np.diff(res.node_offsets))
+    keep = (res.pos >= a) & (res.pos < b)
+    off = np.zeros(n_nodes + 1, np.int64)
+    off[1:] = np.cumsum(np.bincount(node[keep], minlength=n_nodes))
+    return off, res.pos[keep], res.type_code[keep]
+
+
+def _sorted_within_nodes(res):
+    d = np.diff(res.pos.astype(np.int64))
+    starts = res.node_offsets[1:-1]
+    starts = starts[(starts > 0) & (starts < len(res.pos))]
+    d[starts - 1] = 1
+    return bool((d > 0).all())
+
+
+@pytest.mark.parametrize("name,slice_cols", [("caterpillar100k", 2048), ("ecoli4k", 16384)])
+def test_full_size_deep_and_wide_configs(port, name, slice_cols):
+    """BASELINE.json configs[4] (100k-leaf caterpillar-heavy tree x 30k columns: depth, chain segments) and configs[3]
+    (4k leaves x 5M columns: volume, 4883 column tiles) at FULL size on one GPU. The oracle checks a column slice taken
+    from the middle -- the generator is stateless per cell, so the slice is reproduced in isolation -- and the whole
+    result must be position-sorted per node and consistent in its counts."""
+    import torch
+
+    cfg = synth.CONFIGS[name]
+    tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    spec = synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"])
+    C = cfg["n_cols"]
+    codes4, pc = synth.simulate_msa(tree, 0, C, spec, device="cuda")
+    c = pb.Context(0)
+    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    c.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc)
+    del codes4
+    torch.cuda.empty_cache()
+    t = c.run_resident(0)
+    res = c.download()
+    assert res.n_mut == res.node_offsets[-1] == len(res.pos) and t.total_ms > 0
+    assert res.pos.min() >= 0 and res.pos.max() < C
+    assert _sorted_within_nodes(res)
+    a = (C // 2 // 1024) * 1024 + 96          # not tile aligned on purpose
+    b = a + slice_cols
+    s4, spc = synth.simulate_msa(tree, a, b, spec, device="cuda")
+    codes = synth.unpack_nibbles(s4, b - a).cpu().numpy()
+    # the slice's parent codes are those of the full run (consensus = first non-gap leaf, a per-column rule)
+    assert np.array_equal(spc.cpu().numpy(), pc[a:b].cpu().numpy())
+    want, _ = port.run(tree, 0, codes, spc.cpu().numpy(), n_threads=16)
+    off, pos, tc = _slice_lists(res, tree.n_nodes, a, b)
+    assert np.array_equal(off, want.node_offsets)
+    assert np.array_equal(pos, want.pos + a) and np.array_equal(tc, want.type_code)
+    c.close()
+
+
 def test_caterpillar_depth(ctx, port):
     """Deep unbalanced tree (config 5's shape at reduced size: full depth handling, not full volume)."""
     tree = synth.make_tree(20000, 5, "caterpillar")
