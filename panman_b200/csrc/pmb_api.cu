@@ -79,6 +79,7 @@ struct pmb_ctx {
     static constexpr int MAX_GROUPS = 16;
     cudaStream_t gstream[MAX_GROUPS] = {};
     cudaEvent_t gev_fwd[MAX_GROUPS] = {}, gev_done[MAX_GROUPS] = {}, ev_fork = nullptr;
+    cudaEvent_t ev_slab_copied[2] = {nullptr, nullptr}, ev_slab_packed[2] = {nullptr, nullptr};
     int n_sms = 0;
     unsigned int epoch = 0;
     unsigned int dir_clean_epoch = 0;  // epoch at which the staging directory was last cleared (0 = never)
@@ -339,6 +340,10 @@ void pmb_destroy(pmb_ctx* c) {
             if (c->gstream[g]) cudaStreamDestroy(c->gstream[g]);
         }
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        for (int k = 0; k < 2; k++) {
+            if (c->ev_slab_copied[k]) cudaEventDestroy(c->ev_slab_copied[k]);
+            if (c->ev_slab_packed[k]) cudaEventDestroy(c->ev_slab_packed[k]);
+        }
         cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -404,18 +409,54 @@ int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* le
     if (rc) return rc;
     const size_t plane_bytes = size_t(n_rows) * c->T * 32 * sizeof(uint4);
     PMB_CUDA(c->d_leaf_planes.ensure(plane_bytes));
-    // rows in slabs so the temporary nibble buffer stays bounded
-    const size_t slab_budget = size_t(1) << 30;
-    int32_t slab_rows = int32_t(std::max<size_t>(1, std::min<size_t>(size_t(n_rows), slab_budget / size_t(row_stride_bytes))));
-    PMB_CUDA(c->d_tmp_codes.ensure(size_t(slab_rows) * size_t(row_stride_bytes)));
-    for (int32_t r0 = 0; r0 < n_rows; r0 += slab_rows) {
-        int32_t nr = std::min(slab_rows, n_rows - r0);
-        PMB_CUDA(cudaMemcpyAsync(c->d_tmp_codes.p, leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes),
-                                 size_t(nr) * size_t(row_stride_bytes), cudaMemcpyDefault, c->stream));
+    // Where does the nibble matrix live? Device memory and pinned (or registered) host memory are read by the packing
+    // kernel in place -- for pinned memory that fuses the host-to-device transfer with the transposition, one pass at
+    // PCIe speed and no staging buffer. Pageable host memory is staged through a bounded device buffer.
+    // Device memory is read by the packing kernel in place. Host memory is staged through two slabs of device memory:
+    // the copy engine fills one (on a side stream) while the kernel transposes the other, so the upload runs at the
+    // speed of the PCIe copy alone (measured on B200: the kernel reading pinned memory in place reaches 47 GB/s, the copy
+    // engine 54 GB/s; tools/e2e_breakdown.py). Pageable memory takes the same path at the driver's staging speed.
+    bool on_device = false;
+    {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, leaf_codes_4bit) == cudaSuccess)
+            on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+        else
+            cudaGetLastError();
+    }
+    auto pack = [&](const uint8_t* src, int32_t r0, int32_t nr) {
         long long total = (long long)nr * c->T * 32;
         unsigned blocks = unsigned((total + 255) / 256);
-        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tmp_codes.as<uint8_t>(), row_stride_bytes, r0, nr, n_rows, n_cols, c->T,
+        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(src, row_stride_bytes, r0, nr, n_rows, n_cols, c->T,
                                                           c->d_row_slot.as<int>(), c->d_leaf_planes.as<uint4>());
+    };
+    if (on_device) {
+        pack(leaf_codes_4bit, 0, n_rows);
+    } else {
+        const size_t slab_budget = size_t(32) << 20;
+        const int32_t slab_rows = int32_t(std::max<size_t>(1, std::min<size_t>(size_t(n_rows), slab_budget / size_t(row_stride_bytes))));
+        const size_t slab_bytes = size_t(slab_rows) * size_t(row_stride_bytes);
+        PMB_CUDA(c->d_tmp_codes.ensure(2 * slab_bytes));
+        cudaStream_t copy = c->gstream[0];
+        for (int k = 0; k < 2; k++) {
+            if (!c->ev_slab_copied[k]) PMB_CUDA(cudaEventCreateWithFlags(&c->ev_slab_copied[k], cudaEventDisableTiming));
+            if (!c->ev_slab_packed[k]) PMB_CUDA(cudaEventCreateWithFlags(&c->ev_slab_packed[k], cudaEventDisableTiming));
+        }
+        PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // the staging buffer may still be in use by earlier work
+        PMB_CUDA(cudaStreamWaitEvent(copy, c->ev_fork, 0));
+        int slab = 0;
+        for (int32_t r0 = 0; r0 < n_rows; r0 += slab_rows, slab++) {
+            const int k = slab & 1;
+            const int32_t nr = std::min(slab_rows, n_rows - r0);
+            uint8_t* buf = c->d_tmp_codes.as<uint8_t>() + size_t(k) * slab_bytes;
+            if (slab >= 2) PMB_CUDA(cudaStreamWaitEvent(copy, c->ev_slab_packed[k], 0));
+            PMB_CUDA(cudaMemcpyAsync(buf, leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes), size_t(nr) * size_t(row_stride_bytes),
+                                     cudaMemcpyHostToDevice, copy));
+            PMB_CUDA(cudaEventRecord(c->ev_slab_copied[k], copy));
+            PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_slab_copied[k], 0));
+            pack(buf, r0, nr);
+            PMB_CUDA(cudaEventRecord(c->ev_slab_packed[k], c->stream));
+        }
     }
     PMB_CUDA(cudaGetLastError());
     c->have_present = leaf_present != nullptr;

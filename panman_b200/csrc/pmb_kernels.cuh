@@ -1348,10 +1348,32 @@ __global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, i
     uint32_t pl[4] = {0, 0, 0, 0};
     const uint8_t* src = codes + (size_t)row * row_stride;
     long long c0 = g * 32;
+    // whole groups are fetched with the widest load the address allows (the source may be pinned HOST memory read
+    // across PCIe, where byte loads would waste the link); the ragged last group of a row goes byte by byte
+    uint32_t xw[4] = {0, 0, 0, 0};
+    const bool whole = c0 + 32 <= n_cols;
+    if (whole) {
+        const uint8_t* a = src + (c0 >> 1);
+        const unsigned long long addr = (unsigned long long)a;
+        if ((addr & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(a);
+            xw[0] = v.x; xw[1] = v.y; xw[2] = v.z; xw[3] = v.w;
+        } else if ((addr & 7) == 0) {
+            const uint2 v0 = *reinterpret_cast<const uint2*>(a), v1 = *reinterpret_cast<const uint2*>(a + 8);
+            xw[0] = v0.x; xw[1] = v0.y; xw[2] = v1.x; xw[3] = v1.y;
+        } else if ((addr & 3) == 0) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) xw[w] = *reinterpret_cast<const uint32_t*>(a + 4 * w);
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                xw[w] = uint32_t(a[4 * w]) | (uint32_t(a[4 * w + 1]) << 8) | (uint32_t(a[4 * w + 2]) << 16) | (uint32_t(a[4 * w + 3]) << 24);
+        }
+    }
     for (int w = 0; w < 4; w++) {  // 8 columns = 4 bytes per step
-        uint32_t x = 0;
+        uint32_t x = xw[w];
         long long cb = c0 + w * 8;
-        if (cb < n_cols) {
+        if (!whole && cb < n_cols) {
             long long byte = cb >> 1;
             long long ncol = min(n_cols, cb + 8) - cb;
             long long nbytes = (ncol + 1) >> 1;
