@@ -73,6 +73,8 @@ struct pmb_ctx {
     int64_t opt_trace = 0;            // debug: record a per-item timeline (pmb_debug_trace)
     DevBuf d_trace;
     std::vector<unsigned long long> h_trace;
+    DevBuf d_scan_state;              // compaction: group prefixes (u64) followed by group totals (u32)
+    int64_t opt_target_items = 0;     // (chunk, tile) work items aimed for when the chunk size is chosen (0 = default)
     int64_t opt_reserve_sms = 0;      // SMs the persistent kernels leave free (room for a concurrent NCCL kernel)
     int64_t opt_bwd_tail = 20;        // tenths of a machine-full of warps whose items form the backward pass' sorted tail
     int64_t opt_col_groups = 0;       // column-tile groups run on separate streams (0 = chosen from the tile count)
@@ -107,7 +109,7 @@ struct pmb_ctx {
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
     DevBuf d_mcounts, d_moff, d_mpos, d_mtc;  // merged shards
     HostBuf h_pack_header;
-    DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_node_counts, d_offsets, d_pos, d_tc,
+    DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_offsets, d_pos, d_tc,
         d_states_u8;
     unsigned long long staging_cap = 0;
     bool have_result = false;
@@ -148,7 +150,7 @@ int upload_vec(pmb_ctx* c, DevBuf& buf, const std::vector<T>& v) {
 // (chunk x tile) warps to fill 148 SMs several times over at the widest level.
 int32_t pick_chunk_nodes(const pmb_ctx* c) {
     if (c->opt_chunk_nodes > 0) return int32_t(std::min<int64_t>(c->opt_chunk_nodes, 1 << 30));
-    const int64_t target_warps = 148LL * 64;
+    const int64_t target_warps = c->opt_target_items > 0 ? c->opt_target_items : 148LL * 32;  // measured: tools/sweep.py
     int64_t want_chunks = std::max<int64_t>(1, (target_warps + c->T - 1) / std::max(1, c->T));
     int64_t n_internal = 0;
     for (int32_t v = 0; v < c->n_nodes; v++) n_internal += c->child_off[v + 1] > c->child_off[v];
@@ -212,7 +214,7 @@ int launch_kernel(pmb_ctx* c, cudaStream_t stream, K kernel, size_t smem, const 
         const long long sms = std::max<long long>(1, c->n_sms - std::max<int64_t>(0, std::min<int64_t>(c->opt_reserve_sms, c->n_sms - 1)));
         long long resident = (long long)std::max(1, per_sm) * sms;
         blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
-        // the ticket is zero: finish_run_kernel of the previous run (or the initial clearing) left it so
+        // the ticket is zero: compact_copy_kernel of the previous run (or the initial clearing) left it so
     } else {
         blocks = unsigned((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     }
@@ -327,9 +329,9 @@ void pmb_destroy(pmb_ctx* c) {
         for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_bwd_order,
                           &c->d_level_order, &c->d_row_slot, &c->d_deps, &c->d_block_sums, &c->d_leaf_planes,
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
-                          &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_node_counts, &c->d_offsets,
+                          &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
-                          &c->d_mpos, &c->d_mtc})
+                          &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header}) b->release();
         for (int i = 0; i < 4; i++)
@@ -361,6 +363,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "col_groups") c->opt_col_groups = value;
     else if (k == "bwd_tail") c->opt_bwd_tail = value;
     else if (k == "reserve_sms") c->opt_reserve_sms = value;
+    else if (k == "target_items") c->opt_target_items = value;
     else if (k == "trace") c->opt_trace = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
@@ -516,10 +519,6 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         if ((rcf = ensure_flags(c, c->d_done, size_t(P.n_internal) * T))) return rcf;
         if ((rcf = ensure_flags(c, c->d_fdone, size_t(std::max(1, P.n_fslots)) * T))) return rcf;
     }
-    if (size_t(P.n_nodes) * sizeof(unsigned int) > c->d_node_counts.cap) c->state_dirty = true;
-    PMB_CUDA(c->d_node_counts.ensure(size_t(P.n_nodes) * sizeof(unsigned int)));
-    const int scan_blocks = (P.n_nodes + SCAN_TILE - 1) / SCAN_TILE;
-    PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
     PMB_CUDA(c->d_offsets.ensure(size_t(P.n_nodes + 1) * sizeof(long long)));
     if (c->staging_cap == 0) {
         unsigned long long cells = (unsigned long long)P.n_nodes * (unsigned long long)c->n_cols;
@@ -541,7 +540,6 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     rp.leaf_present = c->have_present ? c->d_present.as<uint8_t>() : nullptr;
     rp.sets = c->d_sets.as<uint4>();
     rp.fstore = c->d_fstore.as<uint32_t>();
-    rp.node_count = c->d_node_counts.as<unsigned int>();
     rp.order = nullptr;
     rp.stage_block = 512;
     rp.colparams = c->d_colparams.as<uint4>();
@@ -573,11 +571,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         *tb = int((long long)c->T * g / G);
         *tc = int((long long)c->T * (g + 1) / G) - *tb;
     };
-    // Per-run device state is left clean by the run before (scan_apply_kernel zeroes the node counts, finish_run_kernel
-    // the counters and tickets; directory entries carry a run tag): nothing is cleared on the stream in steady state.
+    // Per-run device state is left clean by the run before (compact_copy_kernel's last block resets the counters and
+    // tickets; directory entries carry a run tag): nothing is cleared on the stream in steady state.
     if (c->state_dirty) {
         PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 64 * sizeof(unsigned long long), c->stream));
-        PMB_CUDA(cudaMemsetAsync(c->d_node_counts.p, 0, c->d_node_counts.cap, c->stream));
         PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
         unsigned int* init = c->h_counters.as<unsigned int>() + 16;  // pinned
         init[0] = 0xFFFFFFFFu;
@@ -621,24 +618,27 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         }
         PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
         {
-            scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(rp.node_count, P.n_nodes, c->d_block_sums.as<unsigned long long>());
-            scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(rp.node_count, P.n_nodes, c->d_block_sums.as<unsigned long long>(),
-                                                                         c->d_offsets.as<long long>());
-            unsigned blocks = unsigned(((long long)P.n_nodes * 32 + 255) / 256);
-            gather_kernel<<<blocks, 256, 0, c->stream>>>(rp.dir, rp.dir_tag, rp.staging, c->d_offsets.as<long long>(), P.n_nodes, c->T,
-                                                         c->col_base, c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(),
-                                                         rp.pool_count, rp.staging_cap);
-            n_launches += 3;
+            const unsigned long long n_entries = (unsigned long long)P.n_nodes * (unsigned long long)c->T;
+            const unsigned groups = unsigned((n_entries + CPT_GROUP - 1) / CPT_GROUP);
+            PMB_CUDA(c->d_scan_state.ensure(size_t(groups) * 12 + 16));
+            unsigned long long* gprefix = c->d_scan_state.as<unsigned long long>();
+            unsigned int* gtotals = reinterpret_cast<unsigned int*>(gprefix + groups);
+            compact_count_kernel<<<(groups + 7) / 8, 256, 0, c->stream>>>(n_entries, rp.dir, rp.dir_tag, gtotals, groups);
+            compact_scan_kernel<<<1, 1024, 0, c->stream>>>(gtotals, int(groups), gprefix, c->d_offsets.as<long long>() + P.n_nodes);
+            compact_copy_kernel<<<groups, CPT_GROUP, 0, c->stream>>>(
+                P.n_nodes, c->T, gprefix, c->d_offsets.as<long long>(), rp.dir, rp.dir_tag, rp.staging, c->col_base,
+                c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), c->d_counters.as<unsigned long long>(), rp.staging_cap,
+                c->d_ticket.as<unsigned long long>(), 64);
+            n_launches += 2;
+            n_launches += 1;
         }
-        finish_run_kernel<<<1, 64, 0, c->stream>>>(c->d_counters.as<unsigned long long>(), rp.staging_cap,
-                                                   c->d_ticket.as<unsigned long long>(), 64);
         PMB_CUDA(cudaGetLastError());
         PMB_CUDA(cudaEventRecord(c->ev[3], c->stream));
         c->state_dirty = false;
         if (async) {  // status, overflow handling and timings wait for pmb_wait
             c->async_pending = true;
             c->async_groups = G;
-            c->timings.n_launches = n_launches + 1;
+            c->timings.n_launches = n_launches;
             c->timings.n_levels = P.n_levels();
             c->last_algo = algo;
             c->last_flags = flags;

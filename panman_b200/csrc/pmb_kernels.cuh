@@ -47,7 +47,6 @@ struct RunParams {
     unsigned int* fdone;          // [fslot][tile] backward: assigned-state slot published
     unsigned long long* ticket;   // persistent launch: work-item counter; nullptr = one static item per warp
     const int* order;             // item i works on chunk order[i / T]; nullptr = identity
-    unsigned int* node_count;     // [node] records emitted for the node in this run
     unsigned int epoch;
     unsigned int dir_tag;         // backward: tag of this run's directory entries (entries with another tag are stale = empty)
     int T;
@@ -234,7 +233,7 @@ __device__ __forceinline__ uint32_t leaf_present_mask(const RunParams& p, int ro
 // case, shuffle prefix sum over per-lane popcounts. Staging space is reserved per warp in blocks of
 // p.stage_block records (one atomic per block, not per append: the round trip of a per-append atomic was 46 % of
 // the backward pass' stall samples in profiles/r01_v2). The (node, tile) directory remembers where each
-// segment went; gather_kernel later lays the segments out node-major in column order.
+// segment went; compact_copy_kernel later lays the segments out node-major in column order.
 // Record: column-in-tile (10 bits) | code << 10 | type << 14.
 // Directory entry: tag (13 bits) | staging base (40 bits) | count (11 bits). The tag names the run that wrote the entry,
 // so the directory needs no clearing between runs (the host clears it when the tag is about to wrap).
@@ -265,10 +264,8 @@ __device__ __forceinline__ void emit(const RunParams& p, StageCursor& sc, int no
     const unsigned long long base = sc.base;
     sc.base += total;
     sc.left -= total;
-    if (lane == 0) {
+    if (lane == 0)
         p.dir[(size_t)node * p.T + tile] = ((unsigned long long)p.dir_tag << DIR_TAG_SHIFT) | (base << 11) | (unsigned long long)total;
-        atomicAdd(p.node_count + node, (unsigned)total);
-    }
     if (base + (unsigned long long)total > p.staging_cap) return;  // host grows the pool and reruns the pass
     uint32_t t0, t1;
     mutation_type(P, F, t0, t1);
@@ -1155,9 +1152,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
     }
 }
 
-// ------------------------------------------------------------------ ordered compaction
-// Per-node record counts were accumulated by emit(). Exclusive scan over nodes in two fully parallel kernels
-// (block sums, then block-local scan + prefix of the block sums), then the gather.
+// ------------------------------------------------------------------ scan over per-node counts (shard merging)
+// Exclusive scan over per-node counts in two fully parallel kernels (block sums, then block-local scan + prefix of the
+// block sums): used when column-range shards are merged. A pass itself compacts with the kernels below.
 constexpr int SCAN_BLOCK = 1024, SCAN_ITEMS = 4, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
 
 __device__ __forceinline__ unsigned long long block_reduce_sum(unsigned long long v, unsigned long long* sh) {
@@ -1188,8 +1185,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(const unsigned in
     if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
 }
 
-// The counts are consumed: they are left zeroed for the next run's atomic accumulation.
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(unsigned int* counts, int n, const unsigned long long* block_sums,
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(const unsigned int* counts, int n, const unsigned long long* block_sums,
                                                                 long long* offsets) {
     __shared__ unsigned long long sh[33];
     __shared__ unsigned long long warp_tot[32];
@@ -1202,7 +1198,6 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(unsigned int* co
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         v[k] = (base + k < n) ? counts[base + k] : 0u;
-        if (base + k < n) counts[base + k] = 0u;
         s += v[k];
     }
     // inclusive scan of the per-thread sums: warp shuffle scan, then the warp totals
@@ -1234,64 +1229,167 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(unsigned int* co
     }
 }
 
-// gather: a warp takes one node; each lane owns one tile's segment and copies it to its final place (segments are
-// short, a few records; the 32 copies of a node proceed in parallel). Nothing is done after a pool overflow: the
-// host grows the pool and reruns the backward pass.
-__global__ void gather_kernel(const unsigned long long* dir, unsigned dir_tag, const uint16_t* staging, const long long* offsets,
-                              int n_nodes, int T, long long col_base, int32_t* pos, uint8_t* type_code,
-                              const unsigned long long* pool_count, unsigned long long staging_cap) {
-    if (*pool_count > staging_cap) return;
-    int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (node >= n_nodes) return;
-    long long run = offsets[node];
-    if (offsets[node + 1] == run) return;
-    for (int t0 = 0; t0 < T; t0 += 32) {
-        const int t = t0 + lane;
-        unsigned long long d = t < T ? dir[(size_t)node * T + t] : 0ull;
-        if (unsigned(d >> DIR_TAG_SHIFT) != dir_tag) d = 0ull;  // written by an earlier run
-        d &= (1ull << DIR_TAG_SHIFT) - 1ull;
-        const int cnt = int(d & 0x7FFull);
-        int incl = cnt;
+// ------------------------------------------------------------------ ordered compaction
+// An exclusive scan over the record counts of ALL directory entries, in (node, tile) order, is the final position of
+// every staged segment, and the value at (node, 0) is the node's offset. Three small launches without any spinning:
+// totals per group of CPT_GROUP entries, scan of the group totals (one block), then one thread per entry: rescan inside
+// the group, copy the entry's (short) segment, and the end-of-run bookkeeping. Work is spread over all entries instead
+// of one warp walking a node's tiles: the earlier per-node gather was latency-bound at 13 us (config 2) to 1 ms
+// (config 4) per pass, and a thread copying several entries' records in a row is no better (61 us on config 3).
+constexpr int CPT_GROUP = 256;  // entries per group = threads per block of compact_copy_kernel
+
+__device__ __forceinline__ unsigned long long dir_valid(unsigned long long d, unsigned dir_tag) {
+    if (unsigned(d >> DIR_TAG_SHIFT) != dir_tag) return 0ull;  // written by an earlier run: empty
+    return d & ((1ull << DIR_TAG_SHIFT) - 1ull);
+}
+
+// one warp per group: lane l sums entries [8 l, 8 l + 8) of the group (dir is 16-byte aligned, groups are 2 KB)
+__global__ void __launch_bounds__(256) compact_count_kernel(unsigned long long n_entries, const unsigned long long* dir, unsigned dir_tag,
+                                                           unsigned int* group_totals, unsigned n_groups) {
+    const unsigned g = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_groups) return;
+    const unsigned long long e0 = (unsigned long long)g * CPT_GROUP + lane * 8u;
+    unsigned sum = 0;
+    if (e0 + 8 <= n_entries) {
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(dir + e0 + k));
+            sum += unsigned(dir_valid((unsigned long long)v.x | ((unsigned long long)v.y << 32), dir_tag) & 0x7FFull);
+            sum += unsigned(dir_valid((unsigned long long)v.z | ((unsigned long long)v.w << 32), dir_tag) & 0x7FFull);
+        }
+    } else {
+        for (int k = 0; k < 8; k++)
+            if (e0 + k < n_entries) sum += unsigned(dir_valid(__ldcg(dir + e0 + k), dir_tag) & 0x7FFull);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_down_sync(FULL, sum, s);
+    if (lane == 0) group_totals[g] = sum;
+}
+
+// exclusive scan of the group totals by ONE block (a few thousand to a few hundred thousand groups)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned int* block_totals, int n_blocks, unsigned long long* block_prefix,
+                                                            long long* offsets_end) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int b = b0 + tid;
+        const unsigned long long v = b < n_blocks ? block_totals[b] : 0u;
+        unsigned long long incl = v;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
-            int v = __shfl_up_sync(FULL, incl, s);
-            if (lane >= s) incl += v;
+            unsigned long long t = __shfl_up_sync(FULL, incl, s);
+            if (lane >= s) incl += t;
         }
-        const long long at = run + (incl - cnt);
-        const uint16_t* src = staging + (d >> 11);
-        const long long cb = col_base + (long long)t * TILE_COLS;
-        for (int i = 0; i < cnt; i++) {
-            const uint32_t r = src[i];
-            pos[at + i] = int32_t(cb + (r & 1023u));
-            type_code[at + i] = uint8_t(((r >> 14) << 4) | ((r >> 10) & 15u));
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_w[lane], wi = w;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                unsigned long long t = __shfl_up_sync(FULL, wi, s);
+                if (lane >= s) wi += t;
+            }
+            s_w[lane] = wi - w;  // exclusive
         }
-        run += __shfl_sync(FULL, incl, 31);
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (b < n_blocks) block_prefix[b] = carry + s_w[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_w[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *offsets_end = (long long)s_carry;
+}
+
+// counters (64 bytes): layout below; [24,28) finished-block count of this kernel
+__global__ void __launch_bounds__(CPT_GROUP) compact_copy_kernel(int n_nodes, int T, const unsigned long long* group_prefix,
+                                                                long long* offsets, const unsigned long long* dir, unsigned dir_tag,
+                                                                const uint16_t* staging, long long col_base, int32_t* pos,
+                                                                uint8_t* type_code, unsigned long long* counters,
+                                                                unsigned long long staging_cap, unsigned long long* tickets, int n_tickets) {
+    __shared__ unsigned s_w[CPT_GROUP / 32];
+    __shared__ unsigned s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long n_entries = (unsigned long long)n_nodes * (unsigned long long)T;
+    const unsigned long long e = (unsigned long long)blockIdx.x * CPT_GROUP + tid;
+    const unsigned long long d = e < n_entries ? dir_valid(__ldcg(dir + e), dir_tag) : 0ull;
+    const unsigned cnt = unsigned(d & 0x7FFull);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        unsigned t = __shfl_up_sync(FULL, incl, s);
+        if (lane >= s) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned before = 0;
+#pragma unroll
+    for (int w = 0; w < CPT_GROUP / 32; w++)
+        if (w < warp) before += s_w[w];
+    if (e < n_entries) {
+        const unsigned long long at = group_prefix[blockIdx.x] + before + (incl - cnt);
+        unsigned long long node, tile;
+        if (n_entries <= 0xFFFFFFFFull) {
+            node = unsigned(e) / unsigned(T);
+            tile = unsigned(e) - unsigned(node) * unsigned(T);
+        } else {
+            node = e / (unsigned long long)T;
+            tile = e - node * (unsigned long long)T;
+        }
+        if (tile == 0) offsets[node] = (long long)at;
+        // after a pool overflow nothing is copied: the host grows the pool and reruns the backward pass
+        if (cnt && counters[0] <= staging_cap) {
+            const uint16_t* src = staging + (d >> 11);
+            const long long cb = col_base + (long long)tile * TILE_COLS;
+            for (unsigned q0 = 0; q0 < cnt; q0 += 4) {  // four independent loads in flight
+                uint32_t r[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) r[i] = q0 + i < cnt ? src[q0 + i] : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (q0 + i < cnt) {
+                        pos[at + q0 + i] = int32_t(cb + (r[i] & 1023u));
+                        type_code[at + q0 + i] = uint8_t(((r[i] >> 14) << 4) | ((r[i] >> 10) & 15u));
+                    }
+            }
+        }
+    }
+    // ---- the last block to finish does the end-of-run bookkeeping
+    __syncthreads();
+    unsigned int* done_blocks = reinterpret_cast<unsigned int*>(counters + 3);
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        if (tid == 0) {
+            unsigned int* error = reinterpret_cast<unsigned int*>(counters + 1);
+            unsigned int* sticky = reinterpret_cast<unsigned int*>(counters + 2);
+            const unsigned long long pool = counters[0];
+            const unsigned int er0 = error[0], er1 = error[1];
+            const unsigned int st = er0 | (pool > staging_cap ? 4u : 0u);
+            if (st) sticky[0] |= st;
+            if ((er0 & 1u) && er1 < sticky[1]) sticky[1] = er1;
+            counters[4] = pool;
+            reinterpret_cast<unsigned int*>(counters + 5)[0] = er0;
+            reinterpret_cast<unsigned int*>(counters + 5)[1] = er1;
+            counters[0] = 0ull;
+            error[0] = 0u;
+            error[1] = 0xFFFFFFFFu;
+            done_blocks[0] = 0u;
+        }
+        for (int i = tid; i < n_tickets; i += CPT_GROUP) tickets[i] = 0ull;
     }
 }
 
-// Last kernel of a run. counters: [0,8) staging records reserved, [8,12) error flags, [12,16) first bad column,
-// [16,20) sticky status, [20,24) sticky first bad column, [32,48) snapshot of [0,16) for the host.
-// Folds the status into the sticky words (they survive until pmb_wait), snapshots the per-run counters and resets
-// them and the work tickets, so that the next run starts without any clearing on the stream.
-__global__ void finish_run_kernel(unsigned long long* counters, unsigned long long staging_cap, unsigned long long* tickets,
-                                  int n_tickets) {
-    if (threadIdx.x == 0) {
-        unsigned int* error = reinterpret_cast<unsigned int*>(counters + 1);
-        unsigned int* sticky = reinterpret_cast<unsigned int*>(counters + 2);
-        const unsigned long long pool = counters[0];
-        const unsigned int e0 = error[0], e1 = error[1];
-        const unsigned int s = e0 | (pool > staging_cap ? 4u : 0u);
-        if (s) sticky[0] |= s;
-        if ((e0 & 1u) && e1 < sticky[1]) sticky[1] = e1;
-        counters[4] = pool;
-        reinterpret_cast<unsigned int*>(counters + 5)[0] = e0;
-        reinterpret_cast<unsigned int*>(counters + 5)[1] = e1;
-        counters[0] = 0ull;
-        error[0] = 0u;
-        error[1] = 0xFFFFFFFFu;
-    }
-    for (int i = threadIdx.x; i < n_tickets; i += blockDim.x) tickets[i] = 0ull;
-}
+// counters (64 bytes): [0,8) staging records reserved, [8,12) error flags, [12,16) first bad column, [16,20) sticky
+// status, [20,24) sticky first bad column, [24,28) compact_copy_kernel's finished-block count, [32,48) snapshot of
+// [0,16) for the host. compact_copy_kernel's last block folds the status into the sticky words (they survive until
+// pmb_wait), snapshots the per-run counters and resets them and the work tickets.
 
 // ------------------------------------------------------------------ merging column-range shards (multi-GPU)
 // A packed shard = {int64 n_mut, int64 n_nodes | int64 offsets[N+1] | int32 pos[cap] | uint8 type_code[cap]} (16-byte
