@@ -379,6 +379,30 @@ PMB_HD void sankoff_assign(const uint32_t G[16], const uint32_t H[16], const uin
     for (int b = 0; b < 4; b++) F[b] = ((keep & P[b]) | (~keep & z[b])) & vis;
 }
 
+// ---- speculative evaluation of chain segments, Sankoff (tree_program.h "chain segments") ----
+// Forward: a parent's vector depends on a child only through the child's zero-excess set Z = {k : e_k = 0} (every
+// child adds 0 to the parent's count r_k where k is in Z and 1 elsewhere). For a node with exactly two
+// children, Z(parent) = Z1 & Z2 if that is non-empty, else Z1 | Z2 -- the Fitch rule -- so FitchInterval bounds the
+// unknown Z entering a segment, with A = O = Z(known child). Where the bounds meet, G = ~Z is exact from there on;
+// H of that node still depends on the unknown below it and is redone with the ops before it.
+// Backward: the state a segment's top node receives is unknown; Q = the states it may be (one-hot planes). A node in
+// parent state s takes s if e_s = 0, min(s, z) if e_s = 1, z if e_s = 2, z = lowest zero-excess state (sankoff_assign).
+PMB_HD void sankoff_candidates_step(uint32_t Q[16], const uint32_t G[16], const uint32_t H[16]) {
+    uint32_t to_z = 0, seen = 0;
+    uint32_t keep[16], zhot[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t zero = ~G[k];
+        zhot[k] = zero & ~seen;     // k is the lowest zero-excess state
+        seen |= zero;               // some zero-excess state <= k, i.e. NOT (k < z)
+        const uint32_t one = G[k] & ~H[k];
+        keep[k] = Q[k] & (zero | (one & ~seen));             // e = 0, or e = 1 and k < z: stays k
+        to_z |= Q[k] & (H[k] | (one & seen));                // e = 2, or e = 1 and k > z: becomes z
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) Q[k] = keep[k] | (to_z & zhot[k]);
+}
+
 // Root: override if given, else the first minimum (fitchSankoff.cpp:492-507). undefined = columns where
 // the reference would trip assert(minPtr != -1).
 PMB_HD void sankoff_assign_root(const uint32_t G[16], const uint32_t H[16], const uint32_t ov[4], uint32_t ov_valid,

@@ -263,11 +263,18 @@ int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParam
         return forward ? launch_schedule(c, stream, ticket_slot, fitch_forward_kernel<false>, fwd_smem, rp, true, n_launches)
                        : launch_schedule(c, stream, ticket_slot, fitch_backward_kernel<false>, bwd_smem_f, rp, false, n_launches);
     }
-    if (!forward) return launch_schedule(c, stream, ticket_slot, sankoff_backward_kernel, bwd_smem_s, rp, false, n_launches);
-    if (P.max_arity <= 3) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<2>, fwd_smem_s, rp, true, n_launches);
-    if (P.max_arity <= 15) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<4>, fwd_smem_s, rp, true, n_launches);
-    if (P.max_arity <= 255) return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<8>, fwd_smem_s, rp, true, n_launches);
-    return launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<20>, fwd_smem_s, rp, true, n_launches);
+    const bool chains = P.n_chain_segments > 0;
+    if (!forward)
+        return chains ? launch_schedule(c, stream, ticket_slot, sankoff_backward_kernel<true>, bwd_smem_s, rp, false, n_launches)
+                      : launch_schedule(c, stream, ticket_slot, sankoff_backward_kernel<false>, bwd_smem_s, rp, false, n_launches);
+#define PMB_SANKOFF_FWD(B)                                                                                                    \
+    return chains ? launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<B, true>, fwd_smem_s, rp, true, n_launches) \
+                  : launch_schedule(c, stream, ticket_slot, sankoff_forward_kernel<B, false>, fwd_smem_s, rp, true, n_launches)
+    if (P.max_arity <= 3) PMB_SANKOFF_FWD(2);
+    if (P.max_arity <= 15) PMB_SANKOFF_FWD(4);
+    if (P.max_arity <= 255) PMB_SANKOFF_FWD(8);
+    PMB_SANKOFF_FWD(20);
+#undef PMB_SANKOFF_FWD
 }
 
 // Column tiles are split into groups that run forward -> backward on their own streams: a group's low-parallelism

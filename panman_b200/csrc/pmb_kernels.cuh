@@ -946,7 +946,7 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Chu
             fold.add_leaf(cc, present);
         } else if (kind == REF_ACC) {
             fold.add_set(accG, sankoff_none(accG, accH));
-        } else if (kind == REF_CHAIN) {  // chain segments of the Sankoff pass wait for the segment below
+        } else if (kind == REF_CHAIN) {  // a chain segment that is not evaluated speculatively waits for the segment below
             if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return false;
             const uint4* row = tc.sets + (size_t)idx * 256;
             uint32_t G[16];
@@ -974,11 +974,76 @@ __device__ __forceinline__ bool sankoff_forward_op(const RunParams& p, const Chu
     return true;
 }
 
+// ---- chain segments, Sankoff (plane_math.h): helpers with direct loads, only used without a presence mask, so no
+// vector is ever NONE. Speculation covers segments whose path ops are binary and whose inlined light subtrees have at
+// most three children per node (everything a bifurcating tree produces); any other segment simply waits.
+__device__ __forceinline__ void store_gh(uint4* out, const uint32_t G[16], const uint32_t H[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        out[j * 32] = make_uint4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]);
+        out[(4 + j) * 32] = make_uint4(H[4 * j], H[4 * j + 1], H[4 * j + 2], H[4 * j + 3]);
+    }
+}
+// exact evaluation of an op with at most 3 children, all known; acc = previous op's result in, this op's result out
+__device__ __forceinline__ bool sankoff_eval_small(const RunParams& p, const Chunk& ck, const TileCtx& tc, DepCursor& dc, const int4 w0,
+                                                   uint32_t accG[16], uint32_t accH[16], int lane, TraceItem& tr) {
+    SankoffFold<2> fold;
+    fold.reset();
+    for (int r = 0; r < w0.y; r++) {
+        const uint32_t ref = __ldg(p.refs + w0.x + r), kind = ref >> 30, idx = ref & REF_IDX_MASK;
+        if (kind == REF_LEAF) {
+            const uint4 c = ld_stream(tc.leaf + (size_t)idx * 32);
+            const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            fold.add_leaf(cc, FULL);
+        } else if (kind == REF_ACC) {
+            fold.add_set(accG, 0u);
+        } else {
+            if (ref & REF_EXT) {
+                if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return false;
+            }
+            uint32_t G[16];
+            row_set16(tc.sets + (size_t)ref_row(p, ck, ref) * 256, G);
+            fold.add_set(G, 0u);
+        }
+    }
+    fold.finish(accG, accH);
+    return true;
+}
+// G planes of the KNOWN child of a binary op on the path (the ref that is not the path's)
+template <bool ACC_REGS>
+__device__ __forceinline__ bool sankoff_known_child(const RunParams& p, const Chunk& ck, const TileCtx& tc, DepCursor& dc, const int4 w0,
+                                                    int op, int head, const uint32_t accG[16], int lane, uint32_t g[16], TraceItem& tr) {
+    for (int r = 0; r < w0.y; r++) {
+        const uint32_t ref = __ldg(p.refs + w0.x + r), kind = ref >> 30, idx = ref & REF_IDX_MASK;
+        if (kind == REF_CHAIN) continue;
+        if (kind == REF_LEAF) {
+            const uint4 c = ld_stream(tc.leaf + (size_t)idx * 32);
+            const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+            sankoff_leaf_g(cc, FULL, g);
+        } else if (kind == REF_ACC) {
+            if (head >= 0 && head == op - 1) continue;
+            if (ACC_REGS) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) g[k] = accG[k];
+            } else {
+                row_set16(tc.sets + (size_t)(op - 1) * 256, g);
+            }
+        } else {
+            if (!(ref & REF_EXT) && head >= 0 && int(idx) == head) continue;
+            if (ref & REF_EXT) {
+                if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return false;
+            }
+            row_set16(tc.sets + (size_t)ref_row(p, ck, ref) * 256, g);
+        }
+    }
+    return true;
+}
+
 // Sankoff rows are [G: 4 vectors][H: 4 vectors]; the forward pass only needs G and the first H vector (NONE marker)
 // of a child, which are contiguous: JS = 5 of JROW = 8.
 // MAXB = widest child counter any op of this tree needs (2: up to 3 children, 4: 15, 8: 255, 20: more), so
-// that binary trees do not pay registers for polytomy paths.
-template <int MAXB>
+// that binary trees do not pay registers for polytomy paths. SPEC = the program has chain segments.
+template <int MAXB, bool SPEC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
     constexpr int JS = 5, STAGE = (2 + JS) * 32, PER_WARP = FWD_DEPTH * STAGE + FWD_META_U4;
@@ -998,12 +1063,55 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
         uint32_t accG[16], accH[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
-        fwd_meta_load(p, m, ck.op_begin, ck.op_end, lane);
-        for (int i = 0; i < FWD_DEPTH && ck.op_begin + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 8>(p, ck, m, tc, dc, ring_l + i * STAGE, ck.op_begin + i, lane, tr)) return;
+        // Chain segment (see fitch_forward_kernel): bounds on the zero-excess set entering from the segment below until
+        // no column depends on it; G of the op where they meet is exact, its H is redone at the end with the ops before.
+        bool spec = SPEC && ck.chain_op >= 0 && p.leaf_present == nullptr;
+        int first = ck.op_begin, resolved = -1;
+        if (spec) {
+            FitchInterval iv;
+            iv.reset();
+            int head = -1;
+            first = ck.op_end;
+            for (int op = ck.op_begin; op < ck.op_end; op++) {
+                const int4 w0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+                const bool on_path = fwd_on_path(p, w0, op, head);
+                if ((on_path && w0.y != 2) || (!on_path && w0.w != 2)) {  // not covered: fall back to waiting
+                    spec = false;
+                    break;
+                }
+                if (!on_path) {  // a light subtree evaluated inside the segment: exact
+                    if (!sankoff_eval_small(p, ck, tc, dc, w0, accG, accH, lane, tr)) return;
+                    store_gh(tc.sets + (size_t)op * 256, accG, accH);
+                    continue;
+                }
+                uint32_t g[16];
+                if (!sankoff_known_child<true>(p, ck, tc, dc, w0, op, head, accG, lane, g, tr)) return;
+#pragma unroll
+                for (int k = 0; k < 16; k++) g[k] = ~g[k];  // zero-excess set of the known child
+                iv.step(g, g);
+                head = op;
+                if (!__any_sync(FULL, iv.open() != 0)) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) { accG[k] = ~iv.lo[k]; accH[k] = 0; }
+                    store_gh(tc.sets + (size_t)op * 256, accG, accH);  // G exact, H provisional (readers ahead only use G)
+                    if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
+                    resolved = op;
+                    first = op + 1;
+                    break;
+                }
+            }
+            if (!spec) {
+                first = ck.op_begin;
+#pragma unroll
+                for (int k = 0; k < 16; k++) { accG[k] = 0; accH[k] = 0; }
+            }
+        }
+        if (first < ck.op_end) fwd_meta_load(p, m, first, ck.op_end, lane);
+        for (int i = 0; i < FWD_DEPTH && first + i < ck.op_end; i++) {
+            if (!fwd_issue<JS, 8>(p, ck, m, tc, dc, ring_l + i * STAGE, first + i, lane, tr)) return;
         }
         int stage = 0;
-        for (int op = ck.op_begin; op < ck.op_end; op++) {
+        for (int op = first; op < ck.op_end; op++) {
             if (op + FWD_DEPTH >= m.wb + META_OPS && m.wb + META_OPS < ck.op_end) fwd_meta_load(p, m, op, ck.op_end, lane);
             const int4 w0 = m.ops[2 * (op - m.wb)];
             cp_async_wait_stage<FWD_DEPTH>(ck.op_end - 1 - op);
@@ -1073,11 +1181,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_forward_kernel(R
             }
             stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
         }
+        if (spec) {  // the vector from below is needed now: redo the path ops up to and including the resolved one
+            if (!wait_flag(tc.done + ck.chain_row, p.epoch, p.error, lane, tr)) return;
+            uint32_t Gc[16];
+            row_set16(tc.sets + (size_t)ck.chain_row * 256, Gc);
+            const int end = resolved >= 0 ? resolved + 1 : ck.op_end;
+            int head = -1;
+            for (int op = ck.chain_op; op < end; op++) {
+                const int4 w0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
+                if (!fwd_on_path(p, w0, op, head)) continue;
+                uint32_t g[16], G[16], H[16];
+                if (!sankoff_known_child<false>(p, ck, tc, dc, w0, op, head, accG, lane, g, tr)) return;
+                sankoff_pair(g, 0u, Gc, 0u, G, H);
+                store_gh(tc.sets + (size_t)op * 256, G, H);
+                if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
+#pragma unroll
+                for (int k = 0; k < 16; k++) Gc[k] = G[k];
+                head = op;
+            }
+        }
         trace_end(p, tr, chunk, tile, lane);
     }
 }
 
 // ------------------------------------------------------------------ Sankoff backward + mutation detection
+template <bool SPEC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
     extern __shared__ uint4 smem[];
     constexpr int J = 8, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4 + BWD_STACK_U4;
@@ -1097,16 +1225,45 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
         const TileCtx tc = tile_ctx<J>(p, tile, lane);
         const int last = ck.op_end - 1;
         uint32_t accF[4] = {0, 0, 0, 0}, accVis = 0;
-        bwd_meta_load(p, m, last, ck.op_begin, lane);
-        for (int i = 0; i < BWD_DEPTH && last - i >= ck.op_begin; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, last - i);
+        // Chain segment (see fitch_backward_kernel): candidate states of the parent above are narrowed down the heavy
+        // path until one is left in every column.
+        int resolved = -1;
+        uint32_t specF[4] = {0, 0, 0, 0}, specVis = 0;
+        if (SPEC && p.leaf_present == nullptr && (ck.flags & CHUNK_CHAIN_TOP)) {
+            uint32_t Q[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) Q[k] = FULL;
+            for (int op = last; op >= ck.op_begin; op--) {
+                if (op != last && !(__ldg(&p.bwd_ops[op].flags) & OPF_HEAVY)) continue;
+                uint32_t G[16], H[16];
+                row_set16(tc.sets + (size_t)op * 256, G);
+                row_set16(tc.sets + (size_t)op * 256 + 128, H);
+                sankoff_candidates_step(Q, G, H);
+                if (!__any_sync(FULL, candidates_open(Q) != 0)) {
+                    resolved = op;
+                    encode16(Q, specF);
+                    specVis = __ldg(p.colparams + (size_t)tile * 128 + 96 + lane).z;  // no vector is NONE: visited = valid column
+#pragma unroll
+                    for (int k = 0; k < 4; k++) specF[k] &= specVis;
+                    break;
+                }
+            }
+        }
+        for (int range = (resolved >= 0 ? 0 : 1); range < 2; range++) {
+        const int hi = range == 0 ? resolved : last;
+        const int lo = (range == 1 && resolved >= 0) ? resolved : ck.op_begin;
+        bwd_meta_load(p, m, hi, lo, lane);
+        for (int i = 0; i < BWD_DEPTH && hi - i >= lo; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, hi - i);
         int stage = 0;
-        for (int op = last; op >= ck.op_begin; op--) {
-            if (op - BWD_DEPTH < m.lo && m.lo > ck.op_begin) bwd_meta_load(p, m, op, ck.op_begin, lane);
+        for (int op = hi; op >= lo; op--) {
+            if (op - BWD_DEPTH < m.lo && m.lo > lo) bwd_meta_load(p, m, op, lo, lane);
             BwdHead h;
             h.b0 = m.ops[2 * (op - m.lo)];
             h.b1 = m.ops[2 * (op - m.lo) + 1];
-            uint32_t P[4], pvis, F[4], vis;
-            if (h.b0.y == PARENT_ACC) {
+            const bool given = range == 0 && op == resolved, own_only = range == 1 && op == resolved;
+            uint32_t P[4] = {0, 0, 0, 0}, pvis = 0, F[4], vis;
+            if (given) {
+            } else if (h.b0.y == PARENT_ACC) {
                 P[0] = accF[0]; P[1] = accF[1]; P[2] = accF[2]; P[3] = accF[3];
                 pvis = accVis;
             } else if (h.b0.y <= PARENT_STACK0) {
@@ -1117,7 +1274,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
             } else if (h.b0.y >= 0) {
                 if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
             }
-            cp_async_wait_stage<BWD_DEPTH>(op - ck.op_begin);
+            cp_async_wait_stage<BWD_DEPTH>(op - lo);
             uint4* st = ring_l + stage * STAGE;
             uint32_t G[16], H[16];
 #pragma unroll
@@ -1126,7 +1283,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
                 G[4 * j] = v.x; G[4 * j + 1] = v.y; G[4 * j + 2] = v.z; G[4 * j + 3] = v.w;
                 H[4 * j] = w.x; H[4 * j + 1] = w.y; H[4 * j + 2] = w.z; H[4 * j + 3] = w.w;
             }
-            if (h.b0.y == PARENT_ROOT) {
+            if (given) {
+                F[0] = specF[0]; F[1] = specF[1]; F[2] = specF[2]; F[3] = specF[3];
+                vis = specVis;
+            } else if (h.b0.y == PARENT_ROOT) {
                 const uint4* cp = p.colparams + (size_t)tile * 128;
                 uint4 pc = __ldg(cp + lane), ov = __ldg(cp + 32 + lane), fl = __ldg(cp + 96 + lane);
                 P[0] = pc.x; P[1] = pc.y; P[2] = pc.z; P[3] = pc.w;
@@ -1142,11 +1302,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sankoff_backward_kernel(
                 sankoff_assign(G, H, P, pvis, F, vis);
             }
             // leaf vector is 0 at its code and INF elsewhere: the parent's argmin always lands on that code
-            bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0);
-            if (op - BWD_DEPTH >= ck.op_begin) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
+            if (own_only) emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
+            else bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, (p.flags & RUN_BLOCK_MODE) != 0, !given);
+            if (op - BWD_DEPTH >= lo) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
             stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
+        }
         }
         trace_end(p, tr, chunk, tile, lane);
     }

@@ -206,6 +206,92 @@ void forward_item(Emu& E, int chunk, int tile) {
             }
         }
     }
+    // ---- the same for Sankoff (sankoff_forward_kernel): bounds on the zero-excess set entering the segment
+    bool spec_s = E.algo == 1 && ck.chain_op >= 0 && !E.have_present;
+    auto known_g = [&](const FwdOp& f, int op, int head, int lane, bool acc_regs, uint32_t g[16]) {
+        for (int r = 0; r < f.n_refs; r++) {
+            uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
+            if (kind == REF_CHAIN) continue;
+            if (kind == REF_LEAF) {
+                U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
+                uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                sankoff_leaf_g(cc, 0xFFFFFFFFu, g);
+            } else if (kind == REF_ACC) {
+                if (head >= 0 && head == op - 1) continue;
+                if (acc_regs) for (int k = 0; k < 16; k++) g[k] = acc[lane][k];
+                else load16(E.sets.data() + ((size_t)tile * E.P.n_internal + (op - 1)) * 256, lane, g);
+            } else {
+                if (!(ref & REF_EXT) && head >= 0 && int(idx) == head) continue;
+                idx = row_of(ref);
+                if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256, lane, g);
+            }
+        }
+    };
+    if (spec_s) {
+        static thread_local FitchInterval iv[32];
+        for (auto& x : iv) x.reset();
+        int head = -1;
+        first = ck.op_end;
+        for (int op = ck.op_begin; op < ck.op_end; op++) {
+            const FwdOp f = E.P.fwd_ops[op];
+            const bool path = on_path(f, op, head);
+            if ((path && f.n_refs != 2) || (!path && f.max_arity_bits != 2)) { spec_s = false; break; }
+            if (!path) {
+                for (int lane = 0; lane < 32; lane++) {
+                    SankoffFold<2> fold;
+                    fold.reset();
+                    for (int r = 0; r < f.n_refs; r++) {
+                        uint32_t ref = E.P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
+                        if (kind == REF_LEAF) {
+                            U4 c = E.leaf_planes[((size_t)tile * E.P.n_rows + idx) * 32 + lane];
+                            uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+                            fold.add_leaf(cc, 0xFFFFFFFFu);
+                        } else if (kind == REF_ACC) {
+                            fold.add_set(acc[lane], 0u);
+                        } else {
+                            idx = row_of(ref);
+                            if ((ref & REF_EXT) && E.done[(size_t)tile * E.P.n_internal + idx] != 1) E.order_violation = true;
+                            uint32_t G[16];
+                            load16(E.sets.data() + ((size_t)tile * E.P.n_internal + idx) * 256, lane, G);
+                            fold.add_set(G, 0u);
+                        }
+                    }
+                    fold.finish(acc[lane], accH[lane]);
+                    U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 256;
+                    store16(base, lane, acc[lane]);
+                    store16(base + 128, lane, accH[lane]);
+                }
+                continue;
+            }
+            uint32_t open = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                uint32_t g[16];
+                known_g(f, op, head, lane, true, g);
+                for (int k = 0; k < 16; k++) g[k] = ~g[k];
+                iv[lane].step(g, g);
+                open |= iv[lane].open();
+            }
+            head = op;
+            if (!open) {
+                for (int lane = 0; lane < 32; lane++) {
+                    for (int k = 0; k < 16; k++) { acc[lane][k] = ~iv[lane].lo[k]; accH[lane][k] = 0; }
+                    U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 256;
+                    store16(base, lane, acc[lane]);
+                    store16(base + 128, lane, accH[lane]);
+                }
+                if (f.flags & OPF_SIGNAL) E.done[(size_t)tile * E.P.n_internal + op] = 1;
+                resolved = op;
+                first = op + 1;
+                break;
+            }
+        }
+        if (!spec_s) {
+            first = ck.op_begin;
+            memset(acc, 0, sizeof acc);
+            memset(accH, 0, sizeof accH);
+        }
+    }
     for (int op = first; op < ck.op_end; op++) {
         const FwdOp f = E.P.fwd_ops[op];
         for (int lane = 0; lane < 32; lane++) {
@@ -349,6 +435,34 @@ void forward_item(Emu& E, int chunk, int tile) {
             }
         }
     }
+    if (spec_s) {  // redo the path ops up to and including the resolved one with the real input
+        if (E.done[(size_t)tile * E.P.n_internal + ck.chain_row] != 1) E.order_violation = true;
+        static thread_local uint32_t Gc[32][16];
+        for (int lane = 0; lane < 32; lane++) load16(E.sets.data() + ((size_t)tile * E.P.n_internal + ck.chain_row) * 256, lane, Gc[lane]);
+        const int end = resolved >= 0 ? resolved + 1 : ck.op_end;
+        int head = -1;
+        for (int op = ck.chain_op; op < end; op++) {
+            const FwdOp f = E.P.fwd_ops[op];
+            if (!on_path(f, op, head)) continue;
+            for (int lane = 0; lane < 32; lane++) {
+                uint32_t g[16], G[16], H[16];
+                known_g(f, op, head, lane, false, g);
+                sankoff_pair(g, 0u, Gc[lane], 0u, G, H);
+                U4* base = E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 256;
+                if (op == resolved) {  // the speculated G must be what the exact evaluation gives
+                    uint32_t Y[16];
+                    load16(base, lane, Y);
+                    for (int k = 0; k < 16; k++)
+                        if (Y[k] != G[k]) E.spec_mismatch = true;
+                }
+                store16(base, lane, G);
+                store16(base + 128, lane, H);
+                for (int k = 0; k < 16; k++) Gc[lane][k] = G[k];
+            }
+            if (f.flags & OPF_SIGNAL) E.done[(size_t)tile * E.P.n_internal + op] = 1;
+            head = op;
+        }
+    }
 }
 
 void backward_item(Emu& E, int chunk, int tile) {
@@ -361,7 +475,7 @@ void backward_item(Emu& E, int chunk, int tile) {
     const int last = ck.op_end - 1;
     int resolved = -1;
     uint32_t specF[32][4] = {}, specVis[32] = {};
-    if (E.algo == 0 && !E.have_present && (ck.flags & CHUNK_CHAIN_TOP)) {
+    if (!E.have_present && (ck.flags & CHUNK_CHAIN_TOP)) {
         E.spec_items++;
         static thread_local uint32_t Q[32][16];
         for (auto& q : Q) for (auto& w : q) w = 0xFFFFFFFFu;
@@ -369,9 +483,14 @@ void backward_item(Emu& E, int chunk, int tile) {
             if (op != last && !(E.P.bwd_ops[op].flags & OPF_HEAVY)) continue;
             uint32_t open = 0;
             for (int lane = 0; lane < 32; lane++) {
-                uint32_t S[16];
-                load16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * 128, lane, S);
-                fitch_candidates_step(Q[lane], S);
+                uint32_t S[16], H[16];
+                load16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * J, lane, S);
+                if (E.algo == 0) {
+                    fitch_candidates_step(Q[lane], S);
+                } else {
+                    load16(E.sets.data() + ((size_t)tile * E.P.n_internal + op) * J + 128, lane, H);
+                    sankoff_candidates_step(Q[lane], S, H);
+                }
                 open |= candidates_open(Q[lane]);
             }
             if (!open) {
@@ -736,6 +855,40 @@ extern "C" int emul_speculation_selftest(unsigned long long seed, int trials) {
                 if (!((open >> j) & 1u)) {
                     unsigned c = ((code[0] >> j) & 1u) | (((code[1] >> j) & 1u) << 1) | (((code[2] >> j) & 1u) << 2) | (((code[3] >> j) & 1u) << 3);
                     if (c != P[j]) return t + 1;
+                }
+            }
+        }
+        // ---- backward, Sankoff: random excess vectors (at least one zero-excess state per column)
+        {
+            unsigned Ps[32];
+            uint32_t Qs[16];
+            for (int k = 0; k < 16; k++) Qs[k] = 0xFFFFFFFFu;
+            for (int j = 0; j < 32; j++) Ps[j] = unsigned(rnd() % 16);
+            for (int st = 0; st < steps; st++) {
+                uint32_t Gp[16] = {}, Hp[16] = {};
+                for (int j = 0; j < 32; j++) {
+                    int e[16], z = -1;
+                    const int zero_at = int(rnd() % 16);
+                    for (int k = 0; k < 16; k++) {
+                        e[k] = style == 0 ? 2 : int(rnd() % 3);
+                        if (k == zero_at) e[k] = 0;
+                        if (e[k] == 0 && z < 0) z = k;
+                        if (e[k] > 0) Gp[k] |= 1u << j;
+                        if (e[k] > 1) Hp[k] |= 1u << j;
+                    }
+                    const int sst = int(Ps[j]);
+                    Ps[j] = unsigned(e[sst] == 0 ? sst : (e[sst] == 1 ? (sst < z ? sst : z) : z));
+                }
+                sankoff_candidates_step(Qs, Gp, Hp);
+                const uint32_t open = candidates_open(Qs);
+                uint32_t code[4];
+                encode16(Qs, code);
+                for (int j = 0; j < 32; j++) {
+                    if (!((Qs[Ps[j]] >> j) & 1u)) return t + 1;
+                    if (!((open >> j) & 1u)) {
+                        unsigned c = ((code[0] >> j) & 1u) | (((code[1] >> j) & 1u) << 1) | (((code[2] >> j) & 1u) << 2) | (((code[3] >> j) & 1u) << 3);
+                        if (c != Ps[j]) return t + 1;
+                    }
                 }
             }
         }
