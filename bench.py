@@ -241,7 +241,9 @@ def run_b200_arm(args):
         shard = dict(cap=cap, bytes=pbytes, send=[torch.empty(pbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
                      recv=[torch.empty(world * pbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if rank == 0 else None,
                      comm=torch.cuda.Stream(device=dev), lib=torch.cuda.ExternalStream(ctx.stream_handle(), device=dev), i=0,
-                     merged=None, done=[None, None])
+                     merged=None, done=[None, None], events=[torch.cuda.Event(), torch.cuda.Event()])
+        # receive views built once: the step loop is host-bound at N > 1, every Python object per step counts
+        shard["dst"] = [[shard["recv"][k][r * pbytes:(r + 1) * pbytes] for r in range(world)] for k in range(2)] if rank == 0 else [None, None]
 
     def gather_lists():
         k = shard["i"] & 1
@@ -252,10 +254,8 @@ def run_b200_arm(args):
         ctx.pack_result(shard["send"][k], shard["cap"])     # on the library's stream, right behind the pass
         comm.wait_stream(lib)
         with torch.cuda.stream(comm):
-            dst = [shard["recv"][k][r * shard["bytes"]:(r + 1) * shard["bytes"]] for r in range(world)] if rank == 0 else None
-            work = dist.gather(shard["send"][k], dst, dst=0, async_op=True)
-            work.wait()                            # orders the comm stream after the collective; the host does not block
-            done = torch.cuda.Event()
+            dist.gather(shard["send"][k], shard["dst"][k], dst=0)  # enqueued on comm; the host does not block
+            done = shard["events"][k]
             done.record(comm)
             if rank == 0:
                 shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=comm.cuda_stream)

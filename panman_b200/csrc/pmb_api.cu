@@ -360,6 +360,19 @@ void pmb_destroy(pmb_ctx* c) {
 
 const char* pmb_last_error(const pmb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+void* pmb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void pmb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     if (!c || !key) return PMB_ERR_INVALID;
     std::string k(key);

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -218,7 +219,14 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
     // ---- pack: leaf rows (4-bit codes, two columns per byte) in tree leaf order; leaves without a sequence are absent
     t0 = Clock::now();
     const int64_t stride = ((n_cols + 1) / 2 + 15) / 16 * 16;
-    std::vector<uint8_t> codes4(size_t(T.n_leaves) * size_t(stride), 0);
+    // page-locked when the device library can provide it: the upload then runs at PCIe speed
+    const size_t codes_bytes = size_t(T.n_leaves) * size_t(stride);
+    std::unique_ptr<uint8_t, void (*)(uint8_t*)> pinned(static_cast<uint8_t*>(pmb_host_alloc(codes_bytes)),
+                                                        [](uint8_t* q) { pmb_host_free(q); });
+    std::vector<uint8_t> pageable;
+    if (!pinned) pageable.resize(codes_bytes);
+    uint8_t* const codes4 = pinned ? pinned.get() : pageable.data();
+    std::memset(codes4, 0, codes_bytes);
     std::vector<uint8_t> present(T.n_leaves, 0);
     std::vector<std::pair<int32_t, const std::string*>> rows;
     for (int32_t v = 0; v < T.n_nodes(); v++) {
@@ -235,7 +243,7 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
             th.emplace_back([&, k]() {
                 for (size_t r = k; r < rows.size(); r += nt) {
                     const unsigned char* s = reinterpret_cast<const unsigned char*>(rows[r].second->data());
-                    uint8_t* d = codes4.data() + size_t(rows[r].first) * size_t(stride);
+                    uint8_t* d = codes4 + size_t(rows[r].first) * size_t(stride);
                     int64_t c = 0;
                     for (; c + 1 < n_cols; c += 2) d[c >> 1] = uint8_t(kCode.t[s[c]] | (kCode.t[s[c + 1]] << 4));
                     if (c < n_cols) d[c >> 1] = kCode.t[s[c]];
@@ -261,7 +269,7 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
     if (rc) return fail(std::string("pmb_set_tree: ") + pmb_last_error(ctx));
     bool all_present = std::all_of(present.begin(), present.end(), [](uint8_t x) { return x != 0; });
     pmb_result res;
-    rc = pmb_run_nuc(ctx, low_mem_mode ? PMB_ALGO_SANKOFF : PMB_ALGO_FITCH, n_cols, T.n_leaves, codes4.data(), stride,
+    rc = pmb_run_nuc(ctx, low_mem_mode ? PMB_ALGO_SANKOFF : PMB_ALGO_FITCH, n_cols, T.n_leaves, codes4, stride,
                      all_present ? nullptr : present.data(), parent_code.data(), root_override, fwd_root_ref, 0, 0, &res);
     if (rc) return fail(std::string("pmb_run_nuc: ") + pmb_last_error(ctx));
     b->seconds[2] = since(t0);
