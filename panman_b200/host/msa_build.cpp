@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -63,29 +64,36 @@ std::string read_msa(const char* text, size_t len, bool strip_cr, std::map<std::
         pmh::split_quote_aware(s, delim, w);
         return w.empty() ? std::string() : w[0];
     };
+    // Same results as the reference's line-by-line reader, one copy per sequence byte: a sequence line without '\r' is
+    // appended straight from the input (splitting at an absent delimiter returns the whole line), finished sequences
+    // are moved into the map.
     size_t p = 0;
     while (p < len) {
         const char* nl = static_cast<const char*>(std::memchr(text + p, '\n', len - p));
         size_t e = nl ? size_t(nl - text) : len;
-        std::string line(text + p, e - p);
+        const char* lp = text + p;
+        const size_t ln = e - p;
         p = e + 1;
-        if (line.empty()) continue;
-        if (line[0] == '>') {
+        if (ln == 0) continue;
+        if (lp[0] == '>') {
             if (!cur_seq.empty()) {
                 if (ll == 0) ll = cur_seq.size();
                 else if (ll != cur_seq.size()) return "sequence lengths don't match: " + cur_id;
-                (*seqs)[strip_cr ? first_piece(cur_id, '\r') : cur_id] = cur_seq;
+                (*seqs)[strip_cr ? first_piece(cur_id, '\r') : cur_id] = std::move(cur_seq);
             }
-            cur_id = first_piece(line, ' ').substr(1);
+            cur_id = first_piece(std::string(lp, ln), ' ').substr(1);
             cur_seq.clear();
+            cur_seq.reserve(ll);
+        } else if (strip_cr && std::memchr(lp, '\r', ln)) {
+            cur_seq += first_piece(std::string(lp, ln), '\r');
         } else {
-            cur_seq += strip_cr ? first_piece(line, '\r') : line;
+            cur_seq.append(lp, ln);
         }
     }
     if (!cur_seq.empty()) {
         if (ll != 0 && ll != cur_seq.size()) return "sequence lengths don't match: " + cur_id;
         ll = cur_seq.size();
-        (*seqs)[cur_id] = cur_seq;  // the last record keeps its id as is (:1316-1325)
+        (*seqs)[cur_id] = std::move(cur_seq);  // the last record keeps its id as is (:1316-1325)
     }
     *line_length = ll;
     return "";
@@ -219,14 +227,23 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
     // ---- pack: leaf rows (4-bit codes, two columns per byte) in tree leaf order; leaves without a sequence are absent
     t0 = Clock::now();
     const int64_t stride = ((n_cols + 1) / 2 + 15) / 16 * 16;
-    // page-locked when the device library can provide it: the upload then runs at PCIe speed
+    // Page-locked when the device library can provide it (the upload then runs at PCIe speed). Page-locking costs about as
+    // much as one pageable upload of the same bytes, so the buffer is kept for the following builds of the process
+    // (PanGraph blocks, --low-mem-mode batches) instead of being pinned anew each time.
     const size_t codes_bytes = size_t(T.n_leaves) * size_t(stride);
-    std::unique_ptr<uint8_t, void (*)(uint8_t*)> pinned(static_cast<uint8_t*>(pmb_host_alloc(codes_bytes)),
-                                                        [](uint8_t* q) { pmb_host_free(q); });
+    static std::mutex pin_mutex;
+    static uint8_t* pin_buf = nullptr;
+    static size_t pin_cap = 0;
+    std::unique_lock<std::mutex> pin_lock(pin_mutex);  // one build at a time uses the cached buffer
+    if (codes_bytes > pin_cap) {
+        pmb_host_free(pin_buf);
+        pin_cap = 0;
+        pin_buf = static_cast<uint8_t*>(pmb_host_alloc(codes_bytes + codes_bytes / 4));
+        if (pin_buf) pin_cap = codes_bytes + codes_bytes / 4;
+    }
     std::vector<uint8_t> pageable;
-    if (!pinned) pageable.resize(codes_bytes);
-    uint8_t* const codes4 = pinned ? pinned.get() : pageable.data();
-    std::memset(codes4, 0, codes_bytes);
+    if (!pin_buf) pageable.resize(codes_bytes);
+    uint8_t* const codes4 = pin_buf ? pin_buf : pageable.data();  // rows of absent leaves are never read (presence mask)
     std::vector<uint8_t> present(T.n_leaves, 0);
     std::vector<std::pair<int32_t, const std::string*>> rows;
     for (int32_t v = 0; v < T.n_nodes(); v++) {
