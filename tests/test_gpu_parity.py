@@ -286,6 +286,27 @@ def test_chain_segments(ctx, port, noise):
     ctx.set_option("schedule", 1)
 
 
+def test_reroot_column_convention(ctx, port):
+    """Tree::reroot (reference src/reroot.cpp:170-224) re-infers every column on the re-rooted tree with the new root's
+    own character as defaultState: root override on EVERY column, 'x' read as a gap, assign-time parent state = '-'
+    for gap columns and the consensus character for main columns. Same kernels, same C ABI: root_override everywhere."""
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        tree = random_tree(int(rng.integers(5, 600)), 5100 + trial, ["binary", "caterpillar", "polytomy"][trial % 3], max_arity=4)
+        n_cols = int(rng.choice([300, 1024, 3000]))
+        base = rng.integers(0, 5, size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        codes = np.where(rng.random(codes.shape) < 0.05, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+        new_root_seq = codes[int(rng.integers(0, tree.n_leaves))].astype(np.int8)       # the new root's characters
+        pc = np.where(rng.random(n_cols) < 0.3, 0, base).astype(np.uint8)               # '-' for gap columns, consensus else
+        _set_tree(ctx, tree)
+        for algo in (0, 1):
+            want, want_states = port.run(tree, algo, codes, pc, new_root_seq, None, None, 0, n_threads=4, want_states=True)
+            res = ctx.run_codes(tree, algo, codes, pc, new_root_seq, None, None, 0, want_states=True)
+            assert _same(res, want) and np.array_equal(res.states, want_states), (trial, algo)
+            assert np.array_equal(res.states[tree.root], new_root_seq.astype(np.uint8))  # the root is what reroot forces it to be
+
+
 def test_async_runs_and_shard_merge(ctx, port):
     """Two column-range shards (two contexts on this GPU, as two ranks would hold them) run asynchronously, are packed
     (pmb_pack_result) and merged (pmb_merge_packed): the merged lists equal the single-range result."""
