@@ -83,6 +83,8 @@ struct pmb_ctx {
     cudaEvent_t gev_fwd[MAX_GROUPS] = {}, gev_done[MAX_GROUPS] = {}, ev_fork = nullptr;
     cudaEvent_t ev_slab_copied[2] = {nullptr, nullptr}, ev_slab_packed[2] = {nullptr, nullptr};
     int n_sms = 0;
+    struct Occupancy { const void* kernel; size_t smem; int per_sm; };
+    std::vector<Occupancy> occupancy;
     unsigned int epoch = 0;
     unsigned int dir_clean_epoch = 0;  // epoch at which the staging directory was last cleared (0 = never)
     bool state_dirty = true;           // per-run device state (counters, tickets, node counts, directory) must be re-initialised
@@ -209,8 +211,14 @@ int launch_kernel(pmb_ctx* c, cudaStream_t stream, K kernel, size_t smem, const 
     if (warps <= 0) return PMB_OK;
     unsigned blocks;
     if (rp.ticket) {
-        int per_sm = 0;
-        PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, smem));
+        int per_sm = -1;  // the occupancy query is a driver call: once per (kernel, shared memory size)
+        const void* key = reinterpret_cast<const void*>(kernel);
+        for (const auto& e : c->occupancy)
+            if (e.kernel == key && e.smem == smem) per_sm = e.per_sm;
+        if (per_sm < 0) {
+            PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, smem));
+            c->occupancy.push_back({key, smem, per_sm});
+        }
         const long long sms = std::max<long long>(1, c->n_sms - std::max<int64_t>(0, std::min<int64_t>(c->opt_reserve_sms, c->n_sms - 1)));
         long long resident = (long long)std::max(1, per_sm) * sms;
         blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
@@ -854,18 +862,11 @@ int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v
     cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
     const long long N = c->prog.n_nodes;
     unsigned char* out = static_cast<unsigned char*>(d_packed);
-    // header {n_mut, n_nodes}: n_mut straight from the device (offsets[N]) so that nothing here needs the host to
-    // know the result of a still running asynchronous pass; n_nodes from a pinned constant
-    PMB_CUDA(c->h_pack_header.ensure(16));
-    c->h_pack_header.as<long long>()[0] = N;
-    PMB_CUDA(cudaMemcpyAsync(out, c->d_offsets.as<long long>() + N, 8, cudaMemcpyDeviceToDevice, st));
-    PMB_CUDA(cudaMemcpyAsync(out + 8, c->h_pack_header.p, 8, cudaMemcpyHostToDevice, st));
-    PMB_CUDA(cudaMemcpyAsync(out + 16, c->d_offsets.p, size_t(N + 1) * 8, cudaMemcpyDeviceToDevice, st));
-    const size_t n_copy = c->n_mut >= 0 ? size_t(c->n_mut) : size_t(std::min<unsigned long long>(capacity, c->staging_cap));
-    if (n_copy) {
-        PMB_CUDA(cudaMemcpyAsync(out + packed_pos_offset(N), c->d_pos.p, n_copy * 4, cudaMemcpyDeviceToDevice, st));
-        PMB_CUDA(cudaMemcpyAsync(out + packed_tc_offset(N, capacity), c->d_tc.p, n_copy, cudaMemcpyDeviceToDevice, st));
-    }
+    // everything is read on the device (n_mut = offsets[N] included), so nothing here needs the host to know the result
+    // of a still running asynchronous pass
+    pack_result_kernel<<<c->n_sms * 2, 512, 0, st>>>(c->d_offsets.as<long long>(), c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), N,
+                                                    capacity, out);
+    PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
 

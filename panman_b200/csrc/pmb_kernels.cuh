@@ -1565,6 +1565,27 @@ __host__ __device__ inline size_t packed_bytes(long long n_nodes, long long cap)
     return (packed_tc_offset(n_nodes, cap) + size_t(cap) + 15) / 16 * 16;
 }
 
+// one launch instead of five copies: header, offsets, and the n = offsets[n_nodes] records actually present
+__global__ void pack_result_kernel(const long long* offsets, const int32_t* pos, const uint8_t* type_code, long long n_nodes,
+                                   long long cap, unsigned char* out) {
+    const long long n = min(offsets[n_nodes], cap);
+    long long* hdr = reinterpret_cast<long long*>(out);
+    long long* off_out = hdr + 2;
+    int32_t* pos_out = reinterpret_cast<int32_t*>(out + packed_pos_offset(n_nodes));
+    uint8_t* tc_out = out + packed_tc_offset(n_nodes, cap);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 == 0) {
+        hdr[0] = offsets[n_nodes];
+        hdr[1] = n_nodes;
+    }
+    for (long long i = i0; i <= n_nodes; i += stride) off_out[i] = offsets[i];
+    for (long long i = i0; i < n; i += stride) {
+        pos_out[i] = pos[i];
+        tc_out[i] = type_code[i];
+    }
+}
+
 __global__ void merge_count_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, unsigned int* counts) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
