@@ -562,20 +562,16 @@ __device__ __forceinline__ void store_set16(uint4* out, const uint32_t S[16]) {
 
 // ------------------------------------------------------------------ Fitch forward
 // SPEC = the program has chain segments (tree_program.h); trees without them run the leaner instantiation
+constexpr int FITCH_FWD_STAGE = (2 + 4) * 32, FITCH_FWD_PER_WARP = FWD_DEPTH * FITCH_FWD_STAGE + FWD_META_U4;
+// one work item: the chunk's ops for one column tile. `ring` = the warp's shared memory; false = abandon the run
 template <bool SPEC>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
-    extern __shared__ uint4 smem[];
-    constexpr int JS = 4, STAGE = (2 + JS) * 32, PER_WARP = FWD_DEPTH * STAGE + FWD_META_U4;
-    const int lane = threadIdx.x & 31;
-    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
+__device__ __forceinline__ bool fitch_forward_item(const RunParams& p, uint4* ring, int chunk, int tile, int lane, TraceItem& tr) {
+    constexpr int JS = 4, STAGE = FITCH_FWD_STAGE;
     FwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + FWD_DEPTH * STAGE);
     m.refs = reinterpret_cast<uint32_t*>(m.ops + 2 * META_OPS);
     uint4* const ring_l = ring + lane;
-    ItemIter it;
-    TraceItem tr;
-    int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
+    {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<4>(p, tile, lane);
         DepCursor dc;
@@ -596,7 +592,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 const int4 w0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
                 const bool on_path = fwd_on_path(p, w0, op, head);
                 FitchFold fold;
-                if (!fitch_fold_known<true>(p, ck, tc, dc, w0, op, head, acc, lane, fold, tr)) return;
+                if (!fitch_fold_known<true>(p, ck, tc, dc, w0, op, head, acc, lane, fold, tr)) return false;
                 if (!on_path) {  // a light subtree evaluated inside the segment: exact
                     fold.finish(acc);
                     store_set16(tc.sets + (size_t)op * 128, acc);
@@ -621,7 +617,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
         }
         if (first < ck.op_end) fwd_meta_load(p, m, first, ck.op_end, lane);
         for (int i = 0; i < FWD_DEPTH && first + i < ck.op_end; i++) {
-            if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, ring_l + i * STAGE, first + i, lane, tr)) return;
+            if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, ring_l + i * STAGE, first + i, lane, tr)) return false;
         }
         int stage = 0;
         for (int op = first; op < ck.op_end; op++) {
@@ -673,7 +669,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                     } else if (kind == REF_ACC) {
                         fold.add_set(acc);
                     } else if (SPEC && kind == REF_CHAIN) {  // not speculating (presence mask): wait for the segment below
-                        if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return;
+                        if (!wait_flag(tc.done + idx, p.epoch, p.error, lane, tr)) return false;
                         uint32_t S[16];
                         row_set16(tc.sets + (size_t)idx * 128, S);
                         fold.add_set(S);
@@ -683,7 +679,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                             stage_set16(st, S);
                         } else {
                             if (ref & REF_EXT) {
-                                if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return;
+                                if (!wait_dep(p, ck, tc.done, dc, int(idx), lane, tr)) return false;
                             }
                             row_set16(tc.sets + (size_t)ref_row(p, ck, ref) * 128, S);
                         }
@@ -698,12 +694,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
             if (w0.z & OPF_SIGNAL) signal_flag(tc.done + op, p.epoch, lane);
             // the stage of this op is consumed and its result stored: refill the stage for the op FWD_DEPTH ahead
             if (op + FWD_DEPTH < ck.op_end) {
-                if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, st, op + FWD_DEPTH, lane, tr)) return;
+                if (!fwd_issue<JS, 4>(p, ck, m, tc, dc, st, op + FWD_DEPTH, lane, tr)) return false;
             }
             stage = (stage + 1 == FWD_DEPTH) ? 0 : stage + 1;
         }
         if (spec) {  // the value from below is needed now: redo the path ops that depended on it
-            if (!wait_flag(tc.done + ck.chain_row, p.epoch, p.error, lane, tr)) return;
+            if (!wait_flag(tc.done + ck.chain_row, p.epoch, p.error, lane, tr)) return false;
             uint32_t S[16];
             row_set16(tc.sets + (size_t)ck.chain_row * 128, S);
             const int end = resolved >= 0 ? resolved : ck.op_end;
@@ -712,7 +708,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
                 const int4 w0 = __ldg(reinterpret_cast<const int4*>(p.fwd_ops + op));
                 if (!fwd_on_path(p, w0, op, head)) continue;
                 FitchFold fold;
-                if (!fitch_fold_known<false>(p, ck, tc, dc, w0, op, head, acc, lane, fold, tr)) return;
+                if (!fitch_fold_known<false>(p, ck, tc, dc, w0, op, head, acc, lane, fold, tr)) return false;
                 fold.add_set(S);
                 fold.finish(S);
                 if ((w0.z & OPF_ROOT) && !(p.flags & RUN_BLOCK_MODE)) fitch_root_ref(p, tile, lane, S);
@@ -723,6 +719,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_forward_kernel(Run
         }
         trace_end(p, tr, chunk, tile, lane);
     }
+    return true;
+}
+
+template <bool SPEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, SPEC ? 4 : 5) fitch_forward_kernel(RunParams p, int chunk_begin, int n_chunks) {
+    extern __shared__ uint4 smem[];
+    const int lane = threadIdx.x & 31;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FITCH_FWD_PER_WARP;
+    ItemIter it;
+    TraceItem tr;
+    int chunk, tile;
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr))
+        if (!fitch_forward_item<SPEC>(p, ring, chunk, tile, lane, tr)) return;
 }
 
 // ------------------------------------------------------------------ backward: shared pieces
@@ -806,22 +815,17 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta&
 }
 
 // ------------------------------------------------------------------ Fitch backward + mutation detection
+constexpr int FITCH_BWD_STAGE = (4 + 2) * 32, FITCH_BWD_PER_WARP = BWD_DEPTH * FITCH_BWD_STAGE + BWD_META_U4 + BWD_STACK_U4;
 template <bool SPEC>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
-    extern __shared__ uint4 smem[];
-    constexpr int J = 4, STAGE = (J + 2) * 32, PER_WARP = BWD_DEPTH * STAGE + BWD_META_U4 + BWD_STACK_U4;
-    const int lane = threadIdx.x & 31;
-    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * PER_WARP;
+__device__ __forceinline__ bool fitch_backward_item(const RunParams& p, uint4* ring, StageCursor& sc, int chunk, int tile, int lane,
+                                                    TraceItem& tr) {
+    constexpr int J = 4, STAGE = FITCH_BWD_STAGE;
     BwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
     m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
     uint32_t* stack = reinterpret_cast<uint32_t*>(ring + BWD_DEPTH * STAGE + BWD_META_U4);
     uint4* const ring_l = ring + lane;
-    ItemIter it;
-    TraceItem tr;
-    StageCursor sc;
-    int chunk, tile;
-    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr)) {
+    {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<J>(p, tile, lane);
         const int last = ck.op_end - 1;
@@ -875,7 +879,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
                 pvis = e[128 + lane];
                 P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
             } else if (h.b0.y >= 0) {
-                if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return;
+                if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return false;
             }
             cp_async_wait_stage<BWD_DEPTH>(op - lo);
             uint4* st = ring_l + stage * STAGE;
@@ -918,6 +922,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
         }
         trace_end(p, tr, chunk, tile, lane);
     }
+    return true;
+}
+
+template <bool SPEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(RunParams p, int chunk_begin, int n_chunks) {
+    extern __shared__ uint4 smem[];
+    const int lane = threadIdx.x & 31;
+    uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FITCH_BWD_PER_WARP;
+    ItemIter it;
+    TraceItem tr;
+    StageCursor sc;
+    int chunk, tile;
+    while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr))
+        if (!fitch_backward_item<SPEC>(p, ring, sc, chunk, tile, lane, tr)) return;
 }
 
 // ------------------------------------------------------------------ Sankoff forward
