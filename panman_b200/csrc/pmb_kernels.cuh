@@ -1446,7 +1446,9 @@ __global__ void __launch_bounds__(256) compact_count_kernel(unsigned long long n
     if (lane == 0) group_totals[g] = sum;
 }
 
-// exclusive scan of the group totals by ONE block (a few thousand to a few hundred thousand groups)
+// exclusive scan of the group totals by ONE block (a few thousand to a few hundred thousand groups): every thread owns
+// SCAN1_ITEMS consecutive totals per round
+constexpr int SCAN1_ITEMS = 8;
 __global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned int* block_totals, int n_blocks, unsigned long long* block_prefix,
                                                             long long* offsets_end) {
     __shared__ unsigned long long s_w[32];
@@ -1454,10 +1456,16 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned int* 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
-        const int b = b0 + tid;
-        const unsigned long long v = b < n_blocks ? block_totals[b] : 0u;
-        unsigned long long incl = v;
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024 * SCAN1_ITEMS) {
+        const int b = b0 + tid * SCAN1_ITEMS;
+        unsigned v[SCAN1_ITEMS];
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN1_ITEMS; k++) {
+            v[k] = b + k < n_blocks ? block_totals[b + k] : 0u;
+            sum += v[k];
+        }
+        unsigned long long incl = sum;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             unsigned long long t = __shfl_up_sync(FULL, incl, s);
@@ -1476,9 +1484,14 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned int* 
         }
         __syncthreads();
         const unsigned long long carry = s_carry;
-        if (b < n_blocks) block_prefix[b] = carry + s_w[warp] + incl - v;
+        unsigned long long run = carry + s_w[warp] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < SCAN1_ITEMS; k++) {
+            if (b + k < n_blocks) block_prefix[b + k] = run;
+            run += v[k];
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = carry + s_w[warp] + incl;
+        if (tid == 1023) s_carry = run;
         __syncthreads();
     }
     if (tid == 0) *offsets_end = (long long)s_carry;
