@@ -87,6 +87,7 @@ struct pmb_ctx {
     std::vector<Occupancy> occupancy;
     unsigned int epoch = 0;
     unsigned int dir_clean_epoch = 0;  // epoch at which the staging directory was last cleared (0 = never)
+    bool sticky_dirty = false;         // a synchronous run left a status bit in the sticky words that pmb_wait must not see
     bool state_dirty = true;           // per-run device state (counters, tickets, node counts, directory) must be re-initialised
     unsigned int pack_seq = 0;
     bool async_pending = false;
@@ -613,6 +614,13 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 20, init, 4, cudaMemcpyHostToDevice, c->stream));
         c->dir_clean_epoch = 0;
     }
+    if (c->sticky_dirty && !c->async_pending) {  // synchronous runs report their own status; only asynchronous ones use the sticky words
+        unsigned int* init = c->h_counters.as<unsigned int>() + 18;  // pinned
+        init[0] = 0u;
+        init[1] = 0xFFFFFFFFu;
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 16, init, 8, cudaMemcpyHostToDevice, c->stream));
+        c->sticky_dirty = false;
+    }
     c->state_dirty = true;  // until everything below has been enqueued
     PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     rp.epoch = ++c->epoch;
@@ -683,6 +691,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         PMB_CUDA(cudaStreamSynchronize(c->stream));
         unsigned long long total = *c->h_counters.as<unsigned long long>();
         unsigned int eflags = c->h_counters.as<unsigned int>()[2], ecol = c->h_counters.as<unsigned int>()[3];
+        if (eflags || total > c->staging_cap) c->sticky_dirty = true;
         if (eflags & 2u) return fail(c, PMB_ERR_INTERNAL, "scheduler watchdog fired: a dependency flag never arrived");
         if (eflags & 1u) {
             char buf[160];

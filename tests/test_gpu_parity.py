@@ -361,6 +361,25 @@ def test_async_runs_and_shard_merge(ctx, port):
         c.close()
 
 
+def test_sync_overflow_does_not_leak_into_async_status(port):
+    """A synchronous run that outgrew (and regrew) its staging pool must not leave a status bit for a later pmb_wait."""
+    rng = np.random.default_rng(6)
+    tree = random_tree(100, 5, "binary")
+    codes = rng.integers(0, 16, size=(tree.n_leaves, 1500)).astype(np.uint8)
+    want, _ = port.run(tree, 0, codes, codes[0].copy(), n_threads=2)
+    c = pb.Context(0)
+    c.set_option("staging_records", 500)
+    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    assert _same(c.run_codes(tree, 0, codes, codes[0].copy()), want)   # overflows once, resized, rerun
+    c.set_option("staging_records", 0)
+    c4 = pb.pack_nibbles(codes)
+    c.upload(1500, tree.n_leaves, c4, c4.shape[1], codes[0].copy())
+    c.run_resident_async(pb.ALGO_FITCH)
+    c.wait()
+    assert _same(c.download(), want)
+    c.close()
+
+
 def test_async_overflow_is_reported(ctx):
     rng = np.random.default_rng(5)
     tree = random_tree(100, 7, "binary")

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Small end-to-end cases for compute-sanitizer (memcheck): every kernel path once -- Fitch / Sankoff, plain / presence
+mask / block mode / states, chain segments (speculating and waiting), level schedule, overflow retry, shard merge."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import panman_b200 as pb  # noqa: E402
+from oracle.oracle import PortOracle, random_tree  # noqa: E402
+
+
+def main():
+    rng = np.random.default_rng(3)
+    port = PortOracle()
+    ctx = pb.Context(0)
+    n = 0
+    for kind, leaves, chunk, sched, noise in (("binary", 150, 0, 1, 0.05), ("caterpillar", 300, 8, 1, 0.0), ("caterpillar", 200, 5, 1, 0.7),
+                                              ("polytomy", 120, 3, 0, 0.1), ("unary", 90, 1, 1, 0.02)):
+        tree = random_tree(leaves, 900 + n, kind, max_arity=5)
+        n_cols = [1500, 1024, 33, 2100, 700][n % 5]
+        base = rng.integers(0, 5, size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        codes = np.where(rng.random(codes.shape) < noise, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+        pc = rng.integers(0, 16, size=n_cols).astype(np.uint8)
+        ro = np.where(rng.random(n_cols) < 0.3, rng.integers(0, 16, size=n_cols), -1).astype(np.int8)
+        lp = (rng.random(tree.n_leaves) < 0.8).astype(np.uint8)
+        lp[0] = 1
+        ctx.set_option("chunk_nodes", chunk)
+        ctx.set_option("schedule", sched)
+        ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+        for algo in (0, 1):
+            for present in (None, lp):
+                want, ws = port.run(tree, algo, codes, pc, ro, None, present, 0, n_threads=2, want_states=True)
+                res = ctx.run_codes(tree, algo, codes, pc, ro, None, present, 0, want_states=True)
+                assert np.array_equal(res.pos, want.pos) and np.array_equal(res.type_code, want.type_code)
+                assert np.array_equal(res.states, ws)
+        n += 1
+    # overflow retry + async + pack/merge
+    tree = random_tree(100, 5, "binary")
+    codes = rng.integers(0, 16, size=(tree.n_leaves, 1500)).astype(np.uint8)
+    ctx.set_option("chunk_nodes", 0)
+    ctx.set_option("schedule", 1)
+    ctx.set_option("staging_records", 500)
+    ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    want, _ = port.run(tree, 0, codes, codes[0].copy(), n_threads=2)
+    res = ctx.run_codes(tree, 0, codes, codes[0].copy())
+    assert np.array_equal(res.pos, want.pos)
+    ctx.set_option("staging_records", 0)
+    c4 = pb.pack_nibbles(codes)
+    ctx.upload(1500, tree.n_leaves, c4, c4.shape[1], codes[0].copy())
+    ctx.run_resident_async(0)
+    ctx.wait()
+    cap = int(ctx.result_device().n_mut) + 10
+    buf = torch.empty(2 * ctx.packed_bytes(cap), dtype=torch.uint8, device="cuda")
+    for k in range(2):
+        ctx.pack_result(buf[k * ctx.packed_bytes(cap):(k + 1) * ctx.packed_bytes(cap)], cap)
+    ctx.merge_packed(2, buf, cap)
+    torch.cuda.synchronize()
+    ctx.close()
+    print("sanitize_small ok")
+
+
+if __name__ == "__main__":
+    main()
