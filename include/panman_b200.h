@@ -144,6 +144,25 @@ int pmb_run_resident_async(pmb_ctx* ctx, int algo, int flags);
 int pmb_wait(pmb_ctx* ctx);
 int pmb_download(pmb_ctx* ctx, pmb_result* out);
 
+/* ---- post-processing: greedy <= 6 run-merge of the per-node lists into NucMut fields, on the device ----
+ * Replaces the sort + merge loop of the MSA branches (src/panman.cpp:1445-1466, 1625-1646; NucMut ctor
+ * src/panman.hpp:109-151): the lists are already position-sorted per node. source = 0: the lists of the last run;
+ * source = 1: the lists of the last pmb_merge_packed (column-range shards must be merged FIRST: a run may straddle a
+ * shard boundary). to_host != 0 copies the result to host memory owned by the context, else pointers are device memory
+ * and n is -1 (it is node_offsets[n_nodes], on the device). Entry k of node v = k-th NucMut the reference would append
+ * to Node::nucMutation: nucPosition, mutInfo = (length << 4) + type, nucs = code_j << (4 * (5 - j)); the other fields
+ * are constants for an MSA build (nucGapPosition -1, primaryBlockId 0, secondaryBlockId -1). */
+typedef struct pmb_nucmut_result {
+    int64_t n;
+    int32_t n_nodes;
+    int32_t reserved;
+    const int64_t* node_offsets; /* n_nodes + 1 */
+    const int32_t* nuc_position;
+    const uint8_t* mut_info;
+    const uint32_t* nucs;
+} pmb_nucmut_result;
+int pmb_merge_runs(pmb_ctx* ctx, int source, int to_host, pmb_nucmut_result* out);
+
 /* Device-side view of the last result (for an NCCL gather straight from HBM). Pointers are device memory. */
 int pmb_result_device(pmb_ctx* ctx, pmb_result* out);
 

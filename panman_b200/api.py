@@ -166,6 +166,23 @@ class Context:
         self._check(self.L.pmb_merge_packed(self.h, int(n_shards), _ptr(d_packed), int(capacity), stream, C.byref(r)))
         return r
 
+    def merge_runs(self, source: int = 0):
+        """Greedy <= 6 run-merge of the per-node lists into NucMut fields on the device (pmb_merge_runs); returns host arrays
+        (node_offsets int64[N+1], nuc_position int32, mut_info uint8, nucs uint32). source 1 = the last merge_packed."""
+        from .lib import pmb_nucmut_result
+
+        r = pmb_nucmut_result()
+        self._check(self.L.pmb_merge_runs(self.h, int(source), 1, C.byref(r)))
+        n, N = int(r.n), int(r.n_nodes)
+
+        def view(addr, ctype, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(addr, C.POINTER(ctype)), (count,)).astype(dtype, copy=True)
+
+        return (view(r.node_offsets, C.c_int64, N + 1, np.int64), view(r.nuc_position, C.c_int32, n, np.int32),
+                view(r.mut_info, C.c_uint8, n, np.uint8), view(r.nucs, C.c_uint32, n, np.uint32))
+
     def run_nuc(self, algo, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
                 leaf_present=None, col_base=0, flags=0, copy=True) -> Result:
         r = pmb_result()

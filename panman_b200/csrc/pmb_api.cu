@@ -111,6 +111,8 @@ struct pmb_ctx {
     // work + result
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
     DevBuf d_mcounts, d_moff, d_mpos, d_mtc;  // merged shards
+    DevBuf d_rm_counts, d_rm_off, d_rm_pos, d_rm_info, d_rm_nucs;  // run-merge (pmb_merge_runs)
+    HostBuf h_rm_off, h_rm_pos, h_rm_info, h_rm_nucs;
     HostBuf h_pack_header;
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_offsets, d_pos, d_tc,
         d_states_u8;
@@ -350,9 +352,11 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
-                          &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace})
+                          &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
+                          &c->d_rm_info, &c->d_rm_nucs})
             b->release();
-        for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header}) b->release();
+        for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
+                           &c->h_rm_info, &c->h_rm_nucs}) b->release();
         for (int i = 0; i < 4; i++)
             if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         for (int g = 0; g < pmb_ctx::MAX_GROUPS; g++) {
@@ -915,6 +919,69 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     out->type_code = c->d_mtc.as<uint8_t>();
     out->states = nullptr;
     out->n_cols = 0;
+    return PMB_OK;
+}
+
+int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) {
+    if (!c || !out || (source != 0 && source != 1)) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
+    if (source == 0 && !c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
+    if (source == 1 && !c->d_moff.p) return fail(c, PMB_ERR_NO_INPUT, "no merged shards: call pmb_merge_packed first");
+    PMB_CUDA(cudaSetDevice(c->device));
+    if (source == 0 && c->async_pending) {
+        int rcw = pmb_wait(c);
+        if (rcw) return rcw;
+    }
+    const int N = c->prog.n_nodes;
+    const long long* off = source == 0 ? c->d_offsets.as<long long>() : c->d_moff.as<long long>();
+    const int32_t* pos = source == 0 ? c->d_pos.as<int32_t>() : c->d_mpos.as<int32_t>();
+    const uint8_t* tc = source == 0 ? c->d_tc.as<uint8_t>() : c->d_mtc.as<uint8_t>();
+    // pieces <= records; the record count of merged shards is only known on the device, their capacity on the host
+    const size_t cap = std::max<size_t>(1, source == 0 ? size_t(c->n_mut) : c->d_mtc.cap);
+    PMB_CUDA(c->d_rm_counts.ensure(size_t(N) * sizeof(unsigned int)));
+    PMB_CUDA(c->d_rm_off.ensure(size_t(N + 1) * sizeof(long long)));
+    PMB_CUDA(c->d_rm_pos.ensure(cap * sizeof(int32_t)));
+    PMB_CUDA(c->d_rm_info.ensure(cap));
+    PMB_CUDA(c->d_rm_nucs.ensure(cap * sizeof(uint32_t)));
+    const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
+    PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
+    const unsigned blocks = unsigned(((long long)N * 32 + 255) / 256);
+    merge_runs_kernel<false><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr);
+    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->d_rm_counts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>());
+    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->d_rm_counts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>(),
+                                                                 c->d_rm_off.as<long long>());
+    merge_runs_kernel<true><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, nullptr, c->d_rm_off.as<long long>(), c->d_rm_pos.as<int32_t>(),
+                                                          c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>());
+    PMB_CUDA(cudaGetLastError());
+    out->n_nodes = N;
+    out->reserved = 0;
+    if (!to_host) {
+        out->n = -1;
+        out->node_offsets = reinterpret_cast<const int64_t*>(c->d_rm_off.p);
+        out->nuc_position = c->d_rm_pos.as<int32_t>();
+        out->mut_info = c->d_rm_info.as<uint8_t>();
+        out->nucs = c->d_rm_nucs.as<uint32_t>();
+        return PMB_OK;
+    }
+    PMB_CUDA(c->h_rm_off.ensure(size_t(N + 1) * sizeof(int64_t)));
+    PMB_CUDA(cudaMemcpyAsync(c->h_rm_off.p, c->d_rm_off.p, size_t(N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    PMB_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t m = size_t(c->h_rm_off.as<int64_t>()[N]);
+    PMB_CUDA(c->h_rm_pos.ensure(std::max<size_t>(m, 1) * sizeof(int32_t)));
+    PMB_CUDA(c->h_rm_info.ensure(std::max<size_t>(m, 1)));
+    PMB_CUDA(c->h_rm_nucs.ensure(std::max<size_t>(m, 1) * sizeof(uint32_t)));
+    if (m) {
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_pos.p, c->d_rm_pos.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_info.p, c->d_rm_info.p, m, cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_nucs.p, c->d_rm_nucs.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    out->n = int64_t(m);
+    out->node_offsets = c->h_rm_off.as<int64_t>();
+    out->nuc_position = c->h_rm_pos.as<int32_t>();
+    out->mut_info = c->h_rm_info.as<uint8_t>();
+    out->nucs = c->h_rm_nucs.as<uint32_t>();
     return PMB_OK;
 }
 

@@ -1649,6 +1649,62 @@ __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_byte
     }
 }
 
+// ------------------------------------------------------------------ run-merge into NucMut fields (MSA form)
+// reference src/panman.cpp:1445-1466 + NucMut ctor src/panman.hpp:109-151: a node's position-sorted records are cut where
+// the position is not the previous + 1 or the type changes, and every such maximal run greedily into pieces of at most
+// six; a piece becomes one NucMut {nucPosition = first position, mutInfo = (length << 4) + type, nucs = code_k <<
+// 4 (5 - k)}. A piece starts at record i iff (i - start of i's run) % 6 == 0. One warp per node, 32 records per step;
+// `carry` hands the run start across steps. FILL = false counts the pieces, true writes them at out_off[node].
+template <bool FILL>
+__global__ void merge_runs_kernel(const long long* off, const int32_t* pos, const uint8_t* tc, int n_nodes, unsigned int* counts,
+                                  const long long* out_off, int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= n_nodes) return;
+    const long long a = off[node], b = off[node + 1];
+    long long carry = a;
+    long long written = FILL ? out_off[node] : 0;
+    unsigned cnt = 0;
+    for (long long base = a; base < b; base += 32) {
+        const long long i = base + lane;
+        const bool valid = i < b;
+        const int32_t p = valid ? pos[i] : 0;
+        const uint32_t t = valid ? uint32_t(tc[i]) >> 4 : 0u;
+        int32_t pp = __shfl_up_sync(FULL, p, 1);
+        uint32_t pt = __shfl_up_sync(FULL, t, 1);
+        if (lane == 0 && valid && i > a) {
+            pp = pos[i - 1];
+            pt = uint32_t(tc[i - 1]) >> 4;
+        }
+        const bool brk = valid && (i == a || p != pp + 1 || t != pt);
+        long long rs = brk ? i : -1;  // start of the run this record belongs to: latest break at or before it
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(FULL, rs, d);
+            if (lane >= d) rs = max(rs, o);
+        }
+        rs = max(rs, carry);
+        const bool piece = valid && ((i - rs) % 6 == 0);
+        const unsigned m = __ballot_sync(FULL, piece);
+        if (FILL && piece) {
+            const long long o = written + __popc(m & ((1u << lane) - 1u));
+            uint32_t packed = (uint32_t(tc[i]) & 15u) << 20;
+            int len = 1;
+            for (; len < 6 && i + len < b; len++) {
+                const uint32_t q = tc[i + len];
+                if (pos[i + len] != p + len || (q >> 4) != t) break;
+                packed += (q & 15u) << (4 * (5 - len));
+            }
+            nuc_position[o] = p;
+            mut_info[o] = uint8_t((len << 4) + int(t));
+            nucs[o] = packed;
+        }
+        written += __popc(m);
+        cnt += __popc(m);
+        carry = __shfl_sync(FULL, rs, 31);
+    }
+    if (!FILL && lane == 0) counts[node] = cnt;
+}
+
 // ------------------------------------------------------------------ ingest
 // nibble-packed rows -> code planes. One thread per (row, 32-column group).
 __global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, int row_begin, int n_rows_slab, int n_rows_total,

@@ -99,26 +99,6 @@ std::string read_msa(const char* text, size_t len, bool strip_cr, std::map<std::
     return "";
 }
 
-// greedy <= 6 run-merge of one node's position-sorted tuples (src/panman.cpp:1445-1466; NucMut ctor src/panman.hpp:109-151)
-void merge_runs(const int32_t* pos, const uint8_t* tc, int64_t n, std::vector<pmh_nucmut>* out) {
-    if (n == 0) return;
-    int64_t start = 0;
-    for (int64_t i = 1; i <= n; i++) {
-        bool split = (i == n) || (i - start == 6) || pos[i] != pos[i - 1] + 1 || (tc[i] >> 4) != (tc[i - 1] >> 4);
-        if (!split) continue;
-        pmh_nucmut m;
-        m.nucPosition = pos[start];
-        m.nucGapPosition = -1;
-        m.primaryBlockId = 0;
-        m.secondaryBlockId = -1;
-        m.mutInfo = uint8_t(((i - start) << 4) + (tc[start] >> 4));
-        m.nucs = 0;
-        for (int64_t k = start; k < i; k++) m.nucs += uint32_t(tc[k] & 15) << (4 * (5 - (k - start)));
-        out->push_back(m);
-        start = i;
-    }
-}
-
 }  // namespace
 
 extern "C" {
@@ -296,9 +276,22 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
     b->tuple_off.assign(res.node_offsets, res.node_offsets + T.n_nodes() + 1);
     b->tuple_pos.assign(res.pos, res.pos + res.n_mut);
     b->tuple_tc.assign(res.type_code, res.type_code + res.n_mut);
+    // greedy <= 6 run-merge on the device (pmb_merge_runs; src/panman.cpp:1445-1466, NucMut ctor src/panman.hpp:109-151)
+    pmb_nucmut_result mr;
+    rc = pmb_merge_runs(ctx, /*source*/0, /*to_host*/1, &mr);
+    if (rc) return fail(std::string("pmb_merge_runs: ") + pmb_last_error(ctx));
     for (int32_t v = 0; v < T.n_nodes(); v++) {
-        int64_t a = res.node_offsets[v], z = res.node_offsets[v + 1];
-        merge_runs(res.pos + a, res.type_code + a, z - a, &b->nuc[v]);
+        const int64_t a = mr.node_offsets[v], z = mr.node_offsets[v + 1];
+        b->nuc[v].resize(size_t(z - a));
+        for (int64_t k = a; k < z; k++) {
+            pmh_nucmut& m = b->nuc[v][size_t(k - a)];
+            m.nucPosition = mr.nuc_position[k];
+            m.nucGapPosition = -1;
+            m.primaryBlockId = 0;
+            m.secondaryBlockId = -1;
+            m.mutInfo = mr.mut_info[k];
+            m.nucs = mr.nucs[k];
+        }
     }
     b->seconds[3] = since(t0);
     return b;

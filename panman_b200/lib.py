@@ -10,12 +10,17 @@ LIB_PATH = os.environ.get("PANMAN_B200_LIB", os.path.join(HERE, "libpanman_b200.
 EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",
            "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version",
            "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream", "pmb_run_resident_async", "pmb_wait",
-           "pmb_host_alloc", "pmb_host_free"]
+           "pmb_host_alloc", "pmb_host_free", "pmb_merge_runs"]
 
 
 class pmb_result(C.Structure):
     _fields_ = [("n_mut", C.c_int64), ("n_nodes", C.c_int32), ("reserved", C.c_int32), ("node_offsets", C.c_void_p),
                 ("pos", C.c_void_p), ("type_code", C.c_void_p), ("states", C.c_void_p), ("n_cols", C.c_int64)]
+
+
+class pmb_nucmut_result(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_nodes", C.c_int32), ("reserved", C.c_int32), ("node_offsets", C.c_void_p),
+                ("nuc_position", C.c_void_p), ("mut_info", C.c_void_p), ("nucs", C.c_void_p)]
 
 
 class pmb_timings(C.Structure):
@@ -71,6 +76,7 @@ def load_library():
     L.pmb_host_alloc.restype = vp
     L.pmb_host_free.argtypes = [vp]
     L.pmb_host_free.restype = None
+    L.pmb_merge_runs.argtypes = [vp, C.c_int, C.c_int, C.POINTER(pmb_nucmut_result)]
     L.pmb_pack_result.argtypes = [vp, vp, i64, vp]
     L.pmb_merge_packed.argtypes = [vp, i32, vp, i64, vp, C.POINTER(pmb_result)]
     _lib = L

@@ -357,8 +357,51 @@ def test_async_runs_and_shard_merge(ctx, port):
     pos = torch.as_tensor(_Arr(r.pos, max(n, 1), "<i4"), device="cuda")[:n].cpu().numpy()
     tc = torch.as_tensor(_Arr(r.type_code, max(n, 1), "|u1"), device="cuda")[:n].cpu().numpy()
     assert np.array_equal(off, want.node_offsets) and np.array_equal(pos, want.pos) and np.array_equal(tc, want.type_code)
+    # the run-merge comes after the shard merge: runs straddle the shard boundary
+    got = shards[0].merge_runs(source=1)
+    for g, w in zip(got, _oracle_merge(port, want, N)):
+        assert np.array_equal(g, w)
     for c in shards:
         c.close()
+
+
+def _oracle_merge(port, res, n_nodes):
+    off, P, M, U = [0], [], [], []
+    for v in range(n_nodes):
+        a, b = res.node_offsets[v], res.node_offsets[v + 1]
+        if b > a:
+            p, mi, nu = port.merge_msa(res.pos[a:b], res.type_code[a:b])
+            P.append(p); M.append(mi); U.append(nu)
+        off.append(off[-1] + (len(P[-1]) if b > a else 0))
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return np.asarray(off, np.int64), cat(P, np.int32), cat(M, np.uint8), cat(U, np.uint32)
+
+
+def test_run_merge_on_device(ctx, port):
+    """pmb_merge_runs (reference src/panman.cpp:1445-1466 + NucMut ctor src/panman.hpp:109-151) against the oracle's merge:
+    long runs (cut every six), type changes inside consecutive positions, nodes without records, several tiles."""
+    rng = np.random.default_rng(41)
+    for trial in range(6):
+        tree = random_tree(int(rng.integers(3, 300)), 6100 + trial, ["binary", "polytomy", "caterpillar"][trial % 3], max_arity=4)
+        n_cols = int(rng.choice([50, 1024, 2600]))
+        # block-wise columns: stretches where a clade differs from the consensus give long runs of consecutive positions
+        base = rng.integers(0, 5, size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        for _ in range(12):
+            a = int(rng.integers(0, n_cols))
+            b = min(n_cols, a + int(rng.integers(1, 40)))
+            rows = rng.random(tree.n_leaves) < 0.3
+            codes[np.ix_(rows, np.arange(a, b))] = rng.integers(0, 5, size=(int(rows.sum()), b - a))
+        codes = np.where(rng.random(codes.shape) < 0.01, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+        pc = base.astype(np.uint8)
+        _set_tree(ctx, tree)
+        for algo in (0, 1):
+            res = ctx.run_codes(tree, algo, codes, pc)
+            want = _oracle_merge(port, res, tree.n_nodes)
+            got = ctx.merge_runs()
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), (trial, algo)
+            assert (got[2] >> 4).max(initial=1) <= 6 and (got[2] >> 4).min(initial=1) >= 1
 
 
 def test_sync_overflow_does_not_leak_into_async_status(port):
