@@ -130,10 +130,12 @@ def cpu_reference_run(tree, codes_sample, parent_code_sample, algo, seconds, thr
             return time.perf_counter() - t0
 
         kind = "port"
-    probe = min(n_cols, max(threads, 8))
-    dt = run(probe)
-    nc = int(min(n_cols, max(probe, probe * seconds / max(dt, 1e-6))))
+    # grow the sample until one run takes about `seconds` (a short probe overweights the fixed costs and undershoots)
+    nc = min(n_cols, max(threads, 16))
     dt = run(nc)
+    while dt < 0.5 * seconds and nc < n_cols:
+        nc = int(min(n_cols, max(2 * nc, 0.9 * nc * seconds / max(dt, 1e-6))))
+        dt = run(nc)
     return dict(value=tree.n_nodes * nc / dt, unit="node*col/s", cores=threads, kind=kind,
                 sample=f"first {nc} columns of the workload ({tree.n_nodes} nodes), {dt:.1f} s, "
                        f"{'string-keyed reference drivers' if kind == 'reference' else 'array port'}, {threads} threads")
