@@ -66,6 +66,36 @@ const uint8_t* pmh_build_tuple_type_code(const pmh_build* b);
 /* seconds spent: [0] parse+consensus, [1] pack, [2] pmb_run_nuc, [3] run-merge */
 const double* pmh_build_seconds(const pmh_build* b);
 
+/* ---- PanGraph construction: panmanUtils -P pangraph.json -N tree.nwk [--reference id] ----
+ * pmh_pangraph_load parses the PanGraph JSON (reference src/panman.cpp:6200-6258) and builds, per block, the column batch
+ * the nucleotide passes run on: one column per consensus position 0..len ("main", the last one '-') and one per gap slot
+ * (pos, k); a sequence contributes its aligned character (consensus + substitutions / insertions / deletions,
+ * src/panman.cpp:1006-1045), sequences whose path lacks the block are omitted (leaf_present). Block order = JSON order;
+ * duplicated blocks and circular paths are rejected; the root override follows the rules stated in
+ * panman_b200/host/pangraph.cpp. pmh_pangraph_run runs the block-level pass (3 states, PMB_FLAG_BLOCK_MODE,
+ * src/panman.cpp:873-963) and one pmb_run_nuc per block (src/panman.cpp:1048-1232); algo = PMB_ALGO_FITCH for a bifurcating
+ * tree, PMB_ALGO_SANKOFF for the reference's polytomy branch. Results are the per-node (position-sorted) lists of every
+ * batch; column c of block b is (pmh_pangraph_col_pos[c], pmh_pangraph_col_gap[c]), gap = -1 for main columns. */
+typedef struct pmh_pangraph pmh_pangraph;
+pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* newick, const char* reference, char* err,
+                                size_t err_len);
+void pmh_pangraph_free(pmh_pangraph* g);
+const pmh_tree* pmh_pangraph_tree(const pmh_pangraph* g);
+int32_t pmh_pangraph_n_blocks(const pmh_pangraph* g);
+const char* pmh_pangraph_block_id(const pmh_pangraph* g, int32_t block);
+const uint8_t* pmh_pangraph_block_states(const pmh_pangraph* g); /* n_leaves x n_blocks: 0 absent, 1 forward, 2 reverse */
+int64_t pmh_pangraph_n_cols(const pmh_pangraph* g, int32_t block);
+const uint8_t* pmh_pangraph_codes4(const pmh_pangraph* g, int32_t block, int64_t* row_stride);
+const uint8_t* pmh_pangraph_present(const pmh_pangraph* g, int32_t block);
+const uint8_t* pmh_pangraph_parent_code(const pmh_pangraph* g, int32_t block);
+const int8_t* pmh_pangraph_root_override(const pmh_pangraph* g, int32_t block);
+const int32_t* pmh_pangraph_col_pos(const pmh_pangraph* g, int32_t block);
+const int32_t* pmh_pangraph_col_gap(const pmh_pangraph* g, int32_t block);
+int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t err_len);
+/* lists of one batch after pmh_pangraph_run; block = -1: the block-level pass. Returns the record count. */
+int64_t pmh_pangraph_result(const pmh_pangraph* g, int32_t block, const int64_t** node_offsets, const int32_t** pos,
+                            const uint8_t** type_code);
+
 #ifdef __cplusplus
 }
 #endif

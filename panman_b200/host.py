@@ -119,3 +119,88 @@ class MsaBuild:
         self.tuple_type_code = np.ctypeslib.as_array(L.pmh_build_tuple_type_code(h), (max(nt, 1),))[:nt].copy()
         self.seconds = list(np.ctypeslib.as_array(L.pmh_build_seconds(h), (4,)))
         L.pmh_build_free(h)
+
+
+class PanGraphBuild:
+    """panmanUtils -P pangraph.json -N tree.nwk [--reference id] through libpanman_b200 (include/panman_b200_host.h):
+    load() builds the per-block column batches on the host, run() executes the block-level pass and one pass per block."""
+
+    def __init__(self, json_text: bytes, newick: str, reference: str = ""):
+        L = load_host_library()
+        vp = C.c_void_p
+        L.pmh_pangraph_load.restype = vp
+        L.pmh_pangraph_load.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.pmh_pangraph_free.argtypes = [vp]
+        L.pmh_pangraph_tree.argtypes = [vp]
+        L.pmh_pangraph_tree.restype = vp
+        L.pmh_pangraph_n_blocks.argtypes = [vp]
+        L.pmh_pangraph_n_blocks.restype = C.c_int32
+        L.pmh_pangraph_block_id.argtypes = [vp, C.c_int32]
+        L.pmh_pangraph_block_id.restype = C.c_char_p
+        L.pmh_pangraph_block_states.argtypes = [vp]
+        L.pmh_pangraph_block_states.restype = C.POINTER(C.c_uint8)
+        L.pmh_pangraph_n_cols.argtypes = [vp, C.c_int32]
+        L.pmh_pangraph_n_cols.restype = C.c_int64
+        L.pmh_pangraph_codes4.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]
+        L.pmh_pangraph_codes4.restype = C.POINTER(C.c_uint8)
+        for f, t in (("present", C.c_uint8), ("parent_code", C.c_uint8), ("root_override", C.c_int8), ("col_pos", C.c_int32),
+                     ("col_gap", C.c_int32)):
+            getattr(L, "pmh_pangraph_" + f).argtypes = [vp, C.c_int32]
+            getattr(L, "pmh_pangraph_" + f).restype = C.POINTER(t)
+        L.pmh_pangraph_run.argtypes = [vp, vp, C.c_int, C.c_char_p, C.c_size_t]
+        L.pmh_pangraph_result.argtypes = [vp, C.c_int32, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32)),
+                                          C.POINTER(C.POINTER(C.c_uint8))]
+        L.pmh_pangraph_result.restype = C.c_int64
+        self.L = L
+        err = C.create_string_buffer(512)
+        self.h = L.pmh_pangraph_load(json_text, len(json_text), newick.encode(), reference.encode(), err, 512)
+        if not self.h:
+            raise ValueError(err.value.decode())
+        self.tree = HostTree(L.pmh_pangraph_tree(self.h), owned=False)
+        self.n_blocks = int(L.pmh_pangraph_n_blocks(self.h))
+        n_leaves = self.tree.n_leaves
+        self.block_ids = [L.pmh_pangraph_block_id(self.h, b).decode() for b in range(self.n_blocks)]
+        self.block_states = np.ctypeslib.as_array(L.pmh_pangraph_block_states(self.h), (n_leaves, max(self.n_blocks, 1)))[:, :self.n_blocks].copy()
+        self.batches = []
+        for b in range(self.n_blocks):
+            n = int(L.pmh_pangraph_n_cols(self.h, b))
+            stride = C.c_int64()
+            p = L.pmh_pangraph_codes4(self.h, b, C.byref(stride))
+            c4 = np.ctypeslib.as_array(p, (n_leaves, stride.value)).copy()
+            codes = np.empty((n_leaves, 2 * stride.value), np.uint8)
+            codes[:, 0::2] = c4 & 15
+            codes[:, 1::2] = c4 >> 4
+
+            def arr(name, count):
+                return np.ctypeslib.as_array(getattr(L, "pmh_pangraph_" + name)(self.h, b), (count,)).copy()
+
+            self.batches.append(dict(id=self.block_ids[b], codes=codes[:, :n], present=arr("present", n_leaves), parent_code=arr("parent_code", n),
+                                     root_override=arr("root_override", n), col_j=arr("col_pos", n), col_k=arr("col_gap", n)))
+
+    def run(self, ctx, algo: int):
+        """Returns [MutLists-like (node_offsets, pos, type_code)] for the block-level pass followed by every block."""
+        err = C.create_string_buffer(512)
+        rc = self.L.pmh_pangraph_run(ctx.h, self.h, int(algo), err, 512)
+        if rc:
+            raise RuntimeError(err.value.decode())
+        N = self.tree.n_nodes
+        out = []
+        for b in range(-1, self.n_blocks):
+            po, pp, pt = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)()
+            n = int(self.L.pmh_pangraph_result(self.h, b, C.byref(po), C.byref(pp), C.byref(pt)))
+            off = np.ctypeslib.as_array(po, (N + 1,)).copy()
+            pos = np.ctypeslib.as_array(pp, (max(n, 1),))[:n].copy()
+            tc = np.ctypeslib.as_array(pt, (max(n, 1),))[:n].copy()
+            out.append((off, pos, tc))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.pmh_pangraph_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -22,3 +22,8 @@ void split_quote_aware(const std::string& s, char delim, std::vector<std::string
 std::string parse_newick(const std::string& newick, HostTree* out);
 
 }  // namespace pmh
+
+// the opaque handle of include/panman_b200_host.h
+struct pmh_tree {
+    pmh::HostTree t;
+};

@@ -17,10 +17,6 @@
 #include "../../include/panman_b200_host.h"
 #include "host_tree.hpp"
 
-struct pmh_tree {
-    pmh::HostTree t;
-};
-
 struct pmh_build {
     pmh_tree tree;
     std::string consensus;

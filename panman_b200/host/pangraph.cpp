@@ -1,0 +1,409 @@
+// Host adaptor for the PanGraph construction flow (panmanUtils -P pangraph.json -N tree.nwk): JSON -> per-block column
+// batches in the pmb_run_nuc convention -> the block-level pass and one nucleotide pass per block on the device.
+//
+// Restated from the reference (nothing is copied; jsoncpp/TBB are not needed):
+//   * JSON fields and how they are read            src/panman.cpp:6200-6258 (Pangraph::Pangraph): paths[].name / blocks[]
+//     {id, strand}; blocks[]: sequence (upper-cased consensus), gaps {pos: length}, mutate [[{name, number}, [[pos(1-based),
+//     char]]]], insert [[{..}, [[[pos, offset], string]]]], delete [[{..}, [[pos(1-based), length]]]]
+//   * the aligned strings of a block                src/panman.cpp:1006-1045: consensus plus '-' filled gap slots (length+1
+//     main positions, the last one '-'), then substitutions, insertions into the gap slots, deletions
+//   * the column drivers                            src/panman.cpp:873-963 (blocks: 1 absent / 2 forward / 4 reverse) and
+//     :1048-1232 (one column per main position j and per gap slot (j, k); sequences whose path lacks the block are
+//     OMITTED from the state map; parent state = consensus character, '-' for gap slots)
+// Stand-ins for what the files do not determine (same as tests/golden/make_sars20_golden.py):
+//   * block order = order of "blocks" in the JSON (the reference orders them with chain_align, src/chaining.cpp; only the
+//     block id carried in the stored tuples depends on it, no per-column result);
+//   * duplicated blocks (number > 1) and circular paths (rotation) are rejected, not guessed;
+//   * root override: with --reference, the character of the LAST sequence in leaf-row order whose name contains the
+//     reference string (the reference iterates a tbb::concurrent_unordered_map); without it, gap columns and the Sankoff
+//     branch have none (guarded by reference.length()), while the Fitch main-column branch lacks that guard
+//     (src/panman.cpp:1132) and forces the root to whichever present sequence iterates last: here the highest leaf row.
+#include <cctype>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/panman_b200_host.h"
+#include "host_tree.hpp"
+
+namespace {
+
+// ---------------------------------------------------------------- a small JSON reader (objects, arrays, strings, numbers)
+struct JValue {
+    enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+    bool b = false;
+    double num = 0;
+    std::string str;
+    std::vector<JValue> arr;
+    std::vector<std::pair<std::string, JValue>> obj;  // insertion order kept
+    const JValue* get(const char* key) const {
+        for (auto& kv : obj)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+};
+
+struct JParser {
+    const char* p;
+    const char* end;
+    std::string err;
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++;
+    }
+    bool fail(const char* m) {
+        if (err.empty()) err = std::string("JSON: ") + m;
+        return false;
+    }
+    bool string(std::string& out) {
+        if (p >= end || *p != '"') return fail("string expected");
+        p++;
+        out.clear();
+        while (p < end && *p != '"') {
+            if (*p == '\\') {
+                if (++p >= end) return fail("bad escape");
+                switch (*p) {
+                case 'n': out += '\n'; break;
+                case 't': out += '\t'; break;
+                case 'r': out += '\r'; break;
+                case 'b': out += '\b'; break;
+                case 'f': out += '\f'; break;
+                case 'u': {  // names and sequences are ASCII; keep the low byte
+                    if (end - p < 5) return fail("bad \\u escape");
+                    out += char(std::strtol(std::string(p + 1, p + 5).c_str(), nullptr, 16) & 0xFF);
+                    p += 4;
+                    break;
+                }
+                default: out += *p;
+                }
+                p++;
+            } else {
+                out += *p++;
+            }
+        }
+        if (p >= end) return fail("unterminated string");
+        p++;
+        return true;
+    }
+    bool value(JValue& v) {
+        ws();
+        if (p >= end) return fail("unexpected end");
+        if (*p == '{') {
+            v.kind = JValue::Obj;
+            p++;
+            ws();
+            if (p < end && *p == '}') { p++; return true; }
+            for (;;) {
+                ws();
+                std::string k;
+                if (!string(k)) return false;
+                ws();
+                if (p >= end || *p != ':') return fail("':' expected");
+                p++;
+                v.obj.emplace_back(k, JValue());
+                if (!value(v.obj.back().second)) return false;
+                ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == '}') { p++; return true; }
+                return fail("',' or '}' expected");
+            }
+        }
+        if (*p == '[') {
+            v.kind = JValue::Arr;
+            p++;
+            ws();
+            if (p < end && *p == ']') { p++; return true; }
+            for (;;) {
+                v.arr.emplace_back();
+                if (!value(v.arr.back())) return false;
+                ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == ']') { p++; return true; }
+                return fail("',' or ']' expected");
+            }
+        }
+        if (*p == '"') {
+            v.kind = JValue::Str;
+            return string(v.str);
+        }
+        if (end - p >= 4 && !std::strncmp(p, "true", 4)) { v.kind = JValue::Bool; v.b = true; p += 4; return true; }
+        if (end - p >= 5 && !std::strncmp(p, "false", 5)) { v.kind = JValue::Bool; v.b = false; p += 5; return true; }
+        if (end - p >= 4 && !std::strncmp(p, "null", 4)) { v.kind = JValue::Null; p += 4; return true; }
+        char* q = nullptr;
+        v.num = std::strtod(p, &q);
+        if (q == p) return fail("value expected");
+        v.kind = JValue::Num;
+        p = q;
+        return true;
+    }
+};
+
+uint8_t code_of(unsigned char c) {  // getCodeFromNucleotide, src/panman.cpp:78-113: anything unlisted (incl. '-') -> 0
+    static const struct T {
+        uint8_t t[256];
+        T() {
+            std::memset(t, 0, sizeof t);
+            const char* sym = "ACMGRSVTWYHKDBN";
+            for (int i = 0; i < 15; i++) t[(unsigned char)sym[i]] = uint8_t(i + 1);
+        }
+    } tab;
+    return tab.t[c];
+}
+
+struct BlockBatch {
+    std::string id;
+    int64_t n_cols = 0, stride = 0;
+    std::vector<uint8_t> codes4, present, parent_code;
+    std::vector<int8_t> root_override_fitch;  // see the header comment; empty = none anywhere
+    bool any_override = false;
+    std::vector<int32_t> col_pos, col_gap;    // (j, k); k = -1 for main columns
+    // results of the last run
+    std::vector<int64_t> off;
+    std::vector<int32_t> pos;
+    std::vector<uint8_t> tc;
+};
+
+}  // namespace
+
+struct pmh_pangraph {
+    pmh_tree tree;
+    std::vector<BlockBatch> blocks;
+    std::vector<uint8_t> block_states;  // n_leaves x n_blocks, one 3-state code per byte
+    std::vector<int8_t> block_override; // n_blocks or empty
+    BlockBatch block_level;             // results of the block-level pass
+    bool has_reference = false;
+};
+
+namespace {
+
+void set_err(char* err, size_t n, const std::string& m) {
+    if (err && n) {
+        std::strncpy(err, m.c_str(), n - 1);
+        err[n - 1] = 0;
+    }
+}
+
+std::string upper(std::string s) {
+    for (char& c : s) c = char(std::toupper((unsigned char)c));
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* newick, const char* reference_c, char* err,
+                                size_t err_len) {
+    if (!json || !newick) { set_err(err, err_len, "null argument"); return nullptr; }
+    const std::string reference = reference_c ? reference_c : "";
+    std::unique_ptr<pmh_pangraph> g(new pmh_pangraph());
+    g->has_reference = !reference.empty();
+    {
+        std::string nw(newick);
+        size_t nl = nw.find('\n');
+        if (nl != std::string::npos) nw.resize(nl);
+        std::string e = pmh::parse_newick(nw, &g->tree.t);
+        if (!e.empty()) { set_err(err, err_len, e); return nullptr; }
+    }
+    const pmh::HostTree& T = g->tree.t;
+    JValue root;
+    {
+        JParser jp{json, json + json_len, ""};
+        if (!jp.value(root)) { set_err(err, err_len, jp.err); return nullptr; }
+    }
+    const JValue* paths = root.get("paths");
+    const JValue* blocks = root.get("blocks");
+    if (!paths || !blocks || paths->kind != JValue::Arr || blocks->kind != JValue::Arr) {
+        set_err(err, err_len, "PanGraph JSON needs \"paths\" and \"blocks\" arrays");
+        return nullptr;
+    }
+    std::unordered_map<std::string, int32_t> row_of;
+    for (int32_t v = 0; v < T.n_nodes(); v++)
+        if (T.leaf_row[v] >= 0) row_of[T.names[v]] = T.leaf_row[v];
+    // which sequences own which block, and on which strand (paths, src/panman.cpp:6203-6214)
+    std::unordered_map<std::string, std::map<int32_t, bool>> has_block;  // block id -> leaf row -> strand
+    for (const JValue& path : paths->arr) {
+        const JValue* name = path.get("name");
+        const JValue* pb = path.get("blocks");
+        const JValue* circ = path.get("circular");
+        if (!name || !pb) { set_err(err, err_len, "path without name / blocks"); return nullptr; }
+        if (circ && circ->kind == JValue::Bool && circ->b) { set_err(err, err_len, "circular paths (rotation) are not supported"); return nullptr; }
+        auto it = row_of.find(name->str);
+        if (it == row_of.end()) { set_err(err, err_len, "path " + name->str + " is not a leaf of the tree"); return nullptr; }
+        for (const JValue& b : pb->arr) {
+            const JValue *id = b.get("id"), *strand = b.get("strand"), *number = b.get("number");
+            if (!id) { set_err(err, err_len, "path block without id"); return nullptr; }
+            if ((number && number->num != 1) || has_block[id->str].count(it->second)) {
+                set_err(err, err_len, "duplicated block " + id->str + " in " + name->str + " is not supported");
+                return nullptr;
+            }
+            has_block[id->str][it->second] = !strand || strand->b;
+        }
+    }
+    auto matches_reference = [&](int32_t row) {
+        if (reference.empty()) return false;
+        for (int32_t v = 0; v < T.n_nodes(); v++)
+            if (T.leaf_row[v] == row) return T.names[v].find(reference) != std::string::npos;
+        return false;
+    };
+    const int32_t NB = int32_t(blocks->arr.size()), L = T.n_leaves;
+    g->blocks.resize(NB);
+    g->block_states.assign(size_t(L) * NB, 0);
+    if (!reference.empty()) g->block_override.assign(NB, -1);
+    for (int32_t i = 0; i < NB; i++) {
+        const JValue& blk = blocks->arr[i];
+        const JValue *id = blk.get("id"), *seq = blk.get("sequence"), *gaps = blk.get("gaps");
+        if (!id || !seq) { set_err(err, err_len, "block without id / sequence"); return nullptr; }
+        BlockBatch& B = g->blocks[i];
+        B.id = id->str;
+        const std::string cons = upper(seq->str);
+        const int64_t len = int64_t(cons.size());
+        std::map<int64_t, int64_t> gap_len;  // position -> slots, ascending
+        if (gaps)
+            for (auto& kv : gaps->obj) gap_len[std::stoll(kv.first)] = int64_t(kv.second.num);
+        // columns: main positions 0..len, then the gap slots in (position, slot) order
+        std::map<std::pair<int64_t, int64_t>, int64_t> gap_col;
+        for (int64_t j = 0; j <= len; j++) { B.col_pos.push_back(int32_t(j)); B.col_gap.push_back(-1); }
+        for (auto& kv : gap_len)
+            for (int64_t k = 0; k < kv.second; k++) {
+                gap_col[{kv.first, k}] = int64_t(B.col_pos.size());
+                B.col_pos.push_back(int32_t(kv.first));
+                B.col_gap.push_back(int32_t(k));
+            }
+        B.n_cols = int64_t(B.col_pos.size());
+        B.stride = ((B.n_cols + 1) / 2 + 15) / 16 * 16;
+        B.codes4.assign(size_t(L) * size_t(B.stride), 0);
+        B.present.assign(L, 0);
+        B.parent_code.assign(B.n_cols, 0);
+        for (int64_t j = 0; j < len; j++) B.parent_code[j] = code_of((unsigned char)cons[j]);
+        auto& owners = has_block[B.id];
+        std::vector<std::vector<uint8_t>> rows(L);
+        for (auto& ow : owners) {
+            const int32_t r = ow.first;
+            B.present[r] = 1;
+            g->block_states[size_t(r) * NB + i] = ow.second ? 1 : 2;
+            rows[r].assign(B.parent_code.begin(), B.parent_code.end());  // consensus, '-' in every gap slot
+        }
+        auto per_seq = [&](const char* field, auto&& fn) -> bool {
+            const JValue* arr = blk.get(field);
+            if (!arr) return true;
+            for (const JValue& e : arr->arr) {
+                if (e.arr.size() != 2) continue;
+                const JValue *name = e.arr[0].get("name"), *number = e.arr[0].get("number");
+                if (!name || (number && number->num != 1)) continue;
+                auto it = row_of.find(name->str);
+                if (it == row_of.end() || rows[it->second].empty()) continue;
+                for (const JValue& m : e.arr[1].arr)
+                    if (!fn(rows[it->second], m)) return false;
+            }
+            return true;
+        };
+        bool ok = per_seq("mutate", [&](std::vector<uint8_t>& row, const JValue& m) {
+            const int64_t pos = int64_t(m.arr[0].num);
+            if (pos < 1 || pos > len + 1) return false;
+            row[pos - 1] = code_of((unsigned char)std::toupper((unsigned char)m.arr[1].str[0]));
+            return true;
+        });
+        ok = ok && per_seq("insert", [&](std::vector<uint8_t>& row, const JValue& m) {
+            const int64_t pos = int64_t(m.arr[0].arr[0].num), off = int64_t(m.arr[0].arr[1].num);
+            const std::string s = upper(m.arr[1].str);
+            for (size_t t = 0; t < s.size(); t++) {
+                auto it = gap_col.find({pos, off + int64_t(t)});
+                if (it == gap_col.end()) return false;
+                row[it->second] = code_of((unsigned char)s[t]);
+            }
+            return true;
+        });
+        ok = ok && per_seq("delete", [&](std::vector<uint8_t>& row, const JValue& m) {
+            const int64_t pos = int64_t(m.arr[0].num), ln = int64_t(m.arr[1].num);
+            if (pos < 1 || pos + ln - 1 > len + 1) return false;
+            for (int64_t j = pos; j < pos + ln; j++) row[j - 1] = 0;
+            return true;
+        });
+        if (!ok) { set_err(err, err_len, "block " + B.id + ": a mutation lies outside the block"); return nullptr; }
+        int32_t last_present = -1, ref_row = -1;
+        for (int32_t r = 0; r < L; r++) {
+            if (rows[r].empty()) continue;
+            last_present = r;
+            if (matches_reference(r)) ref_row = r;
+            uint8_t* d = B.codes4.data() + size_t(r) * size_t(B.stride);
+            for (int64_t c = 0; c < B.n_cols; c++) d[c >> 1] |= uint8_t(rows[r][c] << (4 * (c & 1)));
+        }
+        // root override (see the header comment)
+        B.root_override_fitch.assign(B.n_cols, -1);
+        if (!reference.empty()) {
+            if (ref_row >= 0) {
+                for (int64_t c = 0; c < B.n_cols; c++) B.root_override_fitch[c] = int8_t(rows[ref_row][c]);
+                B.any_override = true;
+            }
+            for (int32_t r = 0; r < L; r++)
+                if (matches_reference(r)) g->block_override[i] = int8_t(g->block_states[size_t(r) * NB + i]);
+        } else if (last_present >= 0) {
+            for (int64_t c = 0; c <= len; c++) B.root_override_fitch[c] = int8_t(rows[last_present][c]);
+            B.any_override = true;
+        }
+    }
+    return g.release();
+}
+
+void pmh_pangraph_free(pmh_pangraph* g) { delete g; }
+const pmh_tree* pmh_pangraph_tree(const pmh_pangraph* g) { return &g->tree; }
+int32_t pmh_pangraph_n_blocks(const pmh_pangraph* g) { return int32_t(g->blocks.size()); }
+const char* pmh_pangraph_block_id(const pmh_pangraph* g, int32_t b) { return g->blocks[b].id.c_str(); }
+const uint8_t* pmh_pangraph_block_states(const pmh_pangraph* g) { return g->block_states.data(); }
+int64_t pmh_pangraph_n_cols(const pmh_pangraph* g, int32_t b) { return g->blocks[b].n_cols; }
+const uint8_t* pmh_pangraph_codes4(const pmh_pangraph* g, int32_t b, int64_t* row_stride) {
+    if (row_stride) *row_stride = g->blocks[b].stride;
+    return g->blocks[b].codes4.data();
+}
+const uint8_t* pmh_pangraph_present(const pmh_pangraph* g, int32_t b) { return g->blocks[b].present.data(); }
+const uint8_t* pmh_pangraph_parent_code(const pmh_pangraph* g, int32_t b) { return g->blocks[b].parent_code.data(); }
+const int8_t* pmh_pangraph_root_override(const pmh_pangraph* g, int32_t b) { return g->blocks[b].root_override_fitch.data(); }
+const int32_t* pmh_pangraph_col_pos(const pmh_pangraph* g, int32_t b) { return g->blocks[b].col_pos.data(); }
+const int32_t* pmh_pangraph_col_gap(const pmh_pangraph* g, int32_t b) { return g->blocks[b].col_gap.data(); }
+
+int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t err_len) {
+    if (!ctx || !g || (algo != PMB_ALGO_FITCH && algo != PMB_ALGO_SANKOFF)) { set_err(err, err_len, "bad argument"); return PMB_ERR_INVALID; }
+    const pmh::HostTree& T = g->tree.t;
+    int rc = pmb_set_tree(ctx, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data());
+    if (rc) { set_err(err, err_len, std::string("pmb_set_tree: ") + pmb_last_error(ctx)); return rc; }
+    const int32_t NB = int32_t(g->blocks.size()), L = T.n_leaves;
+    auto keep = [&](BlockBatch& B, const pmb_result& res) {
+        B.off.assign(res.node_offsets, res.node_offsets + T.n_nodes() + 1);
+        B.pos.assign(res.pos, res.pos + res.n_mut);
+        B.tc.assign(res.type_code, res.type_code + res.n_mut);
+    };
+    pmb_result res;
+    {   // block-level pass (src/panman.cpp:873-963): one 3-state column per block, parent state "absent"
+        const int64_t stride = (NB + 1) / 2;
+        std::vector<uint8_t> codes4(size_t(L) * size_t(stride), 0), parent(NB, 0);
+        for (int32_t r = 0; r < L; r++)
+            for (int32_t i = 0; i < NB; i++) codes4[size_t(r) * stride + (i >> 1)] |= uint8_t(g->block_states[size_t(r) * NB + i] << (4 * (i & 1)));
+        rc = pmb_run_nuc(ctx, algo, NB, L, codes4.data(), stride, nullptr, parent.data(),
+                         g->block_override.empty() ? nullptr : g->block_override.data(), nullptr, 0, PMB_FLAG_BLOCK_MODE, &res);
+        if (rc) { set_err(err, err_len, std::string("block pass: ") + pmb_last_error(ctx)); return rc; }
+        keep(g->block_level, res);
+    }
+    for (BlockBatch& B : g->blocks) {
+        // the Sankoff branch guards every override with reference.length(); the Fitch main-column branch does not
+        const bool use_override = B.any_override && (algo == PMB_ALGO_FITCH || g->has_reference);
+        rc = pmb_run_nuc(ctx, algo, B.n_cols, L, B.codes4.data(), B.stride, B.present.data(), B.parent_code.data(),
+                         use_override ? B.root_override_fitch.data() : nullptr, nullptr, 0, 0, &res);
+        if (rc) { set_err(err, err_len, "block " + B.id + ": " + pmb_last_error(ctx)); return rc; }
+        keep(B, res);
+    }
+    return PMB_OK;
+}
+
+int64_t pmh_pangraph_result(const pmh_pangraph* g, int32_t block, const int64_t** node_offsets, const int32_t** pos,
+                            const uint8_t** type_code) {
+    const BlockBatch& B = block < 0 ? g->block_level : g->blocks[block];
+    if (node_offsets) *node_offsets = B.off.data();
+    if (pos) *pos = B.pos.data();
+    if (type_code) *type_code = B.tc.data();
+    return int64_t(B.pos.size());
+}
+
+}  // extern "C"

@@ -30,14 +30,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle.oracle import CODE_OF, RefOracle, build, parse_newick, ref_run_columns  # noqa: E402
+from oracle.oracle import RefOracle, build, parse_newick, ref_run_columns  # noqa: E402
+from tests.pangraph_util import build_batches  # noqa: E402
 
 REF_TEST = "/root/reference/test"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sars20_pangraph.npz")
-
-
-def code_of(ch: str) -> int:
-    return int(CODE_OF[ord(ch)])  # anything but the 15 IUPAC letters (incl. '-') -> 0, as getCodeFromNucleotide
 
 
 def main():
@@ -46,20 +43,9 @@ def main():
     newick = open(os.path.join(REF_TEST, "sars_20.nwk")).readline().strip()
     tree = parse_newick(newick)
     pg = json.load(open(os.path.join(REF_TEST, "sars_20.json")))
-    row_of_name = {tree.names[v]: int(tree.leaf_row[v]) for v in tree.leaves}
-    n_leaves = tree.n_leaves
-    has_block = {}  # block id -> {sequence name: strand}
-    for path in pg["paths"]:
-        assert path["name"] in row_of_name and not path["circular"]
-        for b in path["blocks"]:
-            assert b["number"] == 1 and path["name"] not in has_block.setdefault(b["id"], {})
-            has_block[b["id"]][path["name"]] = bool(b["strand"])
+    bcodes, batches = build_batches(pg, tree)
     out = dict(newick=np.frombuffer(newick.encode(), np.uint8), n_blocks=np.asarray([len(pg["blocks"])], np.int32))
     # ---- block level: one 3-state column per block (0 absent, 1 forward, 2 reverse); parent state absent; no --reference
-    bcodes = np.zeros((n_leaves, len(pg["blocks"])), np.uint8)
-    for i, blk in enumerate(pg["blocks"]):
-        for name, strand in has_block[blk["id"]].items():
-            bcodes[row_of_name[name], i] = 1 if strand else 2
     out["blk_codes"] = bcodes
     for algo in (0, 1):
         want, states = ref_run_columns(ref, tree, algo, bcodes, np.zeros(bcodes.shape[1], np.uint8), None, None, None, 1)
@@ -67,51 +53,18 @@ def main():
         out[f"blk_a{algo}_states"] = states
     # ---- nucleotide level, block by block
     total_cols = 0
-    for i, blk in enumerate(pg["blocks"]):
-        cons = blk["sequence"].upper()
-        L = len(cons)
-        gaps = sorted((int(k), int(v)) for k, v in blk["gaps"].items())
-        main = [cons[j] if j < L else "-" for j in range(L + 1)]
-        col_j = list(range(L + 1)) + [j for j, g in gaps for _ in range(g)]
-        col_k = [-1] * (L + 1) + [k for _, g in gaps for k in range(g)]
-        gap_col = {}
-        for c in range(L + 1, len(col_j)):
-            gap_col[(col_j[c], col_k[c])] = c
-        n_cols = len(col_j)
-        codes = np.zeros((n_leaves, n_cols), np.uint8)
-        present = np.zeros(n_leaves, np.uint8)
-
-        def per_seq(field):
-            return {e[0]["name"]: e[1] for e in blk[field] if e[0]["number"] == 1}
-
-        subs, ins, dels = per_seq("mutate"), per_seq("insert"), per_seq("delete")
-        for name in has_block[blk["id"]]:
-            r = row_of_name[name]
-            present[r] = 1
-            row = [code_of(ch) for ch in main] + [0] * (n_cols - (L + 1))
-            for pos, ch in subs.get(name, []):
-                row[pos - 1] = code_of(ch.upper()[0])
-            for (pos, off), s in ins.get(name, []):
-                for t, ch in enumerate(s.upper()):
-                    row[gap_col[(pos, off + t)]] = code_of(ch)
-            for pos, ln in dels.get(name, []):
-                for j in range(pos, pos + ln):
-                    row[j - 1] = 0
-            codes[r] = row
-        parent_code = np.asarray([code_of(ch) for ch in main] + [0] * (n_cols - (L + 1)), np.uint8)
-        last_row = int(np.nonzero(present)[0].max())
-        root_override = np.full(n_cols, -1, np.int8)
-        root_override[:L + 1] = codes[last_row, :L + 1]
+    for i, bt in enumerate(batches):
         p = f"b{i}_"
+        codes, present, parent_code, root_override = bt["codes"], bt["present"], bt["parent_code"], bt["root_override"]
         out[p + "codes"], out[p + "present"], out[p + "parent_code"], out[p + "root_override"] = codes, present, parent_code, root_override
-        out[p + "col_j"], out[p + "col_k"] = np.asarray(col_j, np.int32), np.asarray(col_k, np.int32)
+        out[p + "col_j"], out[p + "col_k"] = bt["col_j"], bt["col_k"]
         for algo in (0, 1):
             ro = root_override if algo == 0 else None
             want, states = ref_run_columns(ref, tree, algo, codes, parent_code, ro, None, present, 0)
             out[p + f"a{algo}_off"], out[p + f"a{algo}_pos"], out[p + f"a{algo}_tc"] = want.node_offsets, want.pos, want.type_code
             out[p + f"a{algo}_states"] = states
-            print(f"block {i} {blk['id']}: {int(present.sum())} sequences x {n_cols} columns, algo {algo}: {len(want.pos)} records")
-        total_cols += n_cols
+            print(f"block {i} {bt['id']}: {int(present.sum())} sequences x {codes.shape[1]} columns, algo {algo}: {len(want.pos)} records")
+        total_cols += codes.shape[1]
     print("nucleotide columns in total:", total_cols)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

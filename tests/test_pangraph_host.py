@@ -1,0 +1,95 @@
+"""The C++ PanGraph adaptor (panman_b200/host/pangraph.cpp, include/panman_b200_host.h): its JSON reader and per-block
+column batches against the Python restatement used for the golden fixture (tests/pangraph_util.py) on random PanGraphs --
+and on the reference's own test/sars_20.json where /root/reference exists -- then, on a GPU, the whole -P flow against the
+oracle on the same batches."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import random_tree
+from tests.pangraph_util import build_batches, random_pangraph
+
+
+def _same_batches(got, want_states, want_batches):
+    assert np.array_equal(got.block_states, want_states)
+    assert len(got.batches) == len(want_batches)
+    for g, w in zip(got.batches, want_batches):
+        for k in ("codes", "present", "parent_code", "root_override", "col_j", "col_k"):
+            assert np.array_equal(g[k], w[k]), (g["id"], k)
+
+
+def test_adaptor_batches_match_restatement():
+    from panman_b200.host import PanGraphBuild
+
+    rng = np.random.default_rng(8)
+    for trial in range(10):
+        tree = random_tree(int(rng.integers(2, 40)), 8100 + trial, ["binary", "polytomy", "caterpillar"][trial % 3], max_arity=4)
+        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(1, 6)), max_len=int(rng.choice([8, 60, 300])))
+        want_states, want_batches = build_batches(json.loads(text), tree)
+        got = PanGraphBuild(text.encode(), tree.to_newick())
+        assert got.tree.names == tree.names
+        _same_batches(got, want_states, want_batches)
+        got.close()
+
+
+def test_adaptor_rejects_what_it_does_not_model():
+    from panman_b200.host import PanGraphBuild
+
+    tree = random_tree(3, 1, "binary")
+    pg = json.loads(random_pangraph(tree, np.random.default_rng(1), n_blocks=2))
+    bad = json.loads(json.dumps(pg))
+    bad["paths"][0]["circular"] = True
+    with pytest.raises(ValueError, match="circular"):
+        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
+    bad = json.loads(json.dumps(pg))
+    bad["paths"][0]["blocks"].append(dict(bad["paths"][0]["blocks"][0]))
+    with pytest.raises(ValueError, match="duplicated"):
+        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
+    with pytest.raises(ValueError, match="JSON"):
+        PanGraphBuild(b'{"paths": [', tree.to_newick())
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test/sars_20.json"), reason="the reference's test data is not on this machine")
+def test_adaptor_on_sars20_matches_fixture():
+    from panman_b200.host import PanGraphBuild
+    from tests.golden_util import load_sars20
+
+    tree, batches = load_sars20()
+    text = open("/root/reference/test/sars_20.json", "rb").read()
+    newick = open("/root/reference/test/sars_20.nwk").readline().strip()
+    got = PanGraphBuild(text, newick)
+    assert got.tree.names == tree.names
+    assert np.array_equal(got.block_states, batches[0]["codes"])
+    for g, w in zip(got.batches, batches[1:]):
+        assert np.array_equal(g["codes"], w["codes"]) and np.array_equal(g["present"], w["present"])
+        assert np.array_equal(g["parent_code"], w["parent_code"]) and np.array_equal(g["root_override"], w["root_override"][0])
+        assert np.array_equal(g["col_j"], w["col_j"]) and np.array_equal(g["col_k"], w["col_k"])
+    got.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", [0, 1])
+def test_pangraph_flow_matches_oracle(port, algo):
+    import panman_b200 as pb
+    from panman_b200.host import PanGraphBuild
+
+    rng = np.random.default_rng(80 + algo)
+    ctx = pb.Context(0)
+    for trial in range(5):
+        tree = random_tree(int(rng.integers(3, 60)), 8200 + trial, ["binary", "polytomy", "caterpillar"][trial % 3], max_arity=4)
+        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(1, 5)), max_len=int(rng.choice([40, 300, 1500])))
+        build = PanGraphBuild(text.encode(), tree.to_newick())
+        results = build.run(ctx, algo)
+        nb = build.n_blocks
+        want, _ = port.run(tree, algo, build.block_states, np.zeros(nb, np.uint8), None, None, None, 1, n_threads=2)
+        off, pos, tc = results[0]
+        assert np.array_equal(off, want.node_offsets) and np.array_equal(pos, want.pos) and np.array_equal(tc, want.type_code)
+        for bt, (off, pos, tc) in zip(build.batches, results[1:]):
+            ro = bt["root_override"] if algo == 0 else None
+            want, _ = port.run(tree, algo, bt["codes"], bt["parent_code"], ro, None, bt["present"], 0, n_threads=2)
+            assert np.array_equal(off, want.node_offsets), (trial, bt["id"])
+            assert np.array_equal(pos, want.pos) and np.array_equal(tc, want.type_code), (trial, bt["id"])
+        build.close()
+    ctx.close()
