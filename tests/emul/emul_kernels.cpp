@@ -895,3 +895,128 @@ extern "C" int emul_speculation_selftest(unsigned long long seed, int trials) {
     }
     return 0;
 }
+
+// Structural invariants of the tree program (no data involved). Returns 0, or a positive code naming the first violated
+// invariant (see the numbered comments). Used by hypothesis tests over random trees and parameters.
+extern "C" int emul_prog_check(int n_nodes, int root, const int32_t* child_off, const int32_t* child_idx, const int32_t* leaf_row,
+                               int chunk_nodes, int inline_nodes, int bwd_tail_chunks) {
+    TreeProgram P;
+    std::string err = build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, inline_nodes, &P, bwd_tail_chunks);
+    if (!err.empty()) return -1;
+    const int NC = int(P.chunks.size()), NI = P.n_internal;
+    std::vector<int> parent(n_nodes, -1);
+    for (int v = 0; v < n_nodes; v++)
+        for (int e = child_off[v]; e < child_off[v + 1]; e++) parent[child_idx[e]] = v;
+    // 1. the chunks partition the ops, in order
+    std::vector<int> chunk_of_op(NI, -1);
+    int expect = 0;
+    for (int c = 0; c < NC; c++) {
+        if (P.chunks[c].op_begin != expect || P.chunks[c].op_end <= P.chunks[c].op_begin) return 1;
+        for (int op = P.chunks[c].op_begin; op < P.chunks[c].op_end; op++) chunk_of_op[op] = c;
+        expect = P.chunks[c].op_end;
+    }
+    if (expect != NI) return 1;
+    // 2. node <-> op is a bijection on internal nodes; leaf rows <-> slots a permutation
+    std::vector<int> op_node(NI, -1);
+    for (int v = 0; v < n_nodes; v++) {
+        const bool internal = child_off[v] != child_off[v + 1];
+        if (internal != (P.node_op[v] >= 0)) return 2;
+        if (internal) {
+            if (op_node[P.node_op[v]] != -1) return 2;
+            op_node[P.node_op[v]] = v;
+        }
+    }
+    {
+        std::vector<char> seen(P.n_rows, 0);
+        for (int r = 0; r < P.n_rows; r++) {
+            if (P.row_slot[r] < 0 || P.row_slot[r] >= P.n_rows || seen[P.row_slot[r]]) return 2;
+            seen[P.row_slot[r]] = 1;
+        }
+    }
+    std::vector<int> level_of(NC, -1), bwd_pos(NC, -1);
+    for (int l = 0; l < P.n_levels(); l++)
+        for (int k = P.level_chunk_begin[l]; k < P.level_chunk_begin[l + 1]; k++) level_of[P.level_order[k]] = l;
+    for (int k = 0; k < NC; k++) {
+        if (P.bwd_order[k] < 0 || P.bwd_order[k] >= NC || bwd_pos[P.bwd_order[k]] != -1) return 3;
+        bwd_pos[P.bwd_order[k]] = k;
+    }
+    std::vector<char> has_child_chunk(NC, 0);
+    for (int op = 0; op < NI; op++) {
+        const FwdOp& f = P.fwd_ops[op];
+        const BwdOp& b = P.bwd_ops[op];
+        const int c = chunk_of_op[op], v = op_node[op];
+        if (b.node != v) return 4;
+        // 4. the refs name exactly the node's children
+        if (f.n_refs != child_off[v + 1] - child_off[v]) return 4;
+        int n_chain = 0;
+        for (int r = 0; r < f.n_refs; r++) {
+            const uint32_t ref = P.refs[f.ref_begin + r], kind = ref >> 30, idx = ref & REF_IDX_MASK;
+            int child_op = -1;
+            if (kind == REF_LEAF) continue;
+            if (kind == REF_ACC) {
+                if (op == P.chunks[c].op_begin) return 5;  // 5. the accumulator is the previous op of the same chunk
+                child_op = op - 1;
+            } else if (kind == REF_CHAIN) {
+                n_chain++;
+                child_op = int(idx);
+                // 8. a chain child is the top op of an earlier chunk flagged as a chain segment with a segment above
+                if (P.chunks[c].chain_op != op || P.chunks[c].chain_row != child_op) return 8;
+                const int cc = chunk_of_op[child_op];
+                if (cc >= c || child_op != P.chunks[cc].op_end - 1 || !(P.chunks[cc].flags & CHUNK_CHAIN_TOP)) return 8;
+                if (!(P.bwd_ops[child_op].flags & OPF_CHAIN_TOP) || !(P.bwd_ops[child_op].flags & OPF_PARENT_EXT)) return 8;
+                if (level_of[cc] >= level_of[c] || bwd_pos[cc] <= bwd_pos[c]) return 8;
+                has_child_chunk[c] = 1;
+            } else if (ref & REF_EXT) {
+                if (int(idx) >= P.chunks[c].dep_count) return 6;
+                child_op = P.deps[P.chunks[c].dep_begin + idx];
+                const int cc = chunk_of_op[child_op];
+                // 6. an external row comes from an earlier ticket, a lower level, and is published (chunk root)
+                if (cc >= c || level_of[cc] >= level_of[c] || bwd_pos[cc] <= bwd_pos[c]) return 6;
+                if (!(P.fwd_ops[child_op].flags & OPF_SIGNAL)) return 6;
+                has_child_chunk[c] = 1;
+            } else {
+                child_op = int(idx);
+                if (chunk_of_op[child_op] != c || child_op >= op) return 5;
+            }
+            if (parent[op_node[child_op]] != v) return 4;
+        }
+        if (n_chain > 1 || (n_chain == 1) != (P.chunks[c].chain_op == op)) return 8;
+        if (((f.flags & OPF_ROOT) != 0) != (v == root)) return 4;
+    }
+    // 7. backward: replay every chunk and check that each op receives ITS parent's state
+    for (int c = 0; c < NC; c++) {
+        const Chunk& ck = P.chunks[c];
+        int stack_owner[16];
+        for (int& s : stack_owner) s = -1;
+        for (int op = ck.op_end - 1; op >= ck.op_begin; op--) {
+            const BwdOp& b = P.bwd_ops[op];
+            const int v = b.node;
+            if (v == root) {
+                if (b.parent_ref != PARENT_ROOT) return 7;
+            } else {
+                const int pop = P.node_op[parent[v]];
+                if (b.parent_ref == PARENT_ACC) {
+                    if (pop != op + 1 || chunk_of_op[pop] != c) return 7;
+                } else if (b.parent_ref <= PARENT_STACK0) {
+                    const int e = PARENT_STACK0 - b.parent_ref;
+                    if (e >= BWD_STACK_DEPTH || stack_owner[e] != pop) return 7;
+                } else if (b.parent_ref >= 0) {
+                    if (P.bwd_ops[pop].fslot_out != b.parent_ref) return 7;
+                    const bool ext = chunk_of_op[pop] != c;
+                    if (ext != ((b.flags & OPF_PARENT_EXT) != 0)) return 7;
+                    if (ext && (!(P.bwd_ops[pop].flags & OPF_SIGNAL_F) || bwd_pos[chunk_of_op[pop]] >= bwd_pos[c])) return 7;
+                    if (!ext && pop <= op) return 7;
+                } else {
+                    return 7;
+                }
+            }
+            if (b.flags & OPF_PUSH) stack_owner[(b.flags >> OPF_PUSH_SHIFT) & 15] = op;
+        }
+        // 9. the heavy path flags: the chunk's last op is its root and carries OPF_HEAVY
+        if (!(P.bwd_ops[ck.op_end - 1].flags & OPF_HEAVY)) return 9;
+    }
+    // (the sorted backward tail needs no check of its own: invariants 6-8 already require every child chunk to come
+    //  later in the backward order than its parent, whatever moved where)
+    (void)has_child_chunk;
+    return 0;
+}
