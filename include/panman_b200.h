@@ -162,6 +162,11 @@ typedef struct pmb_nucmut_result {
     const uint32_t* nucs;
 } pmb_nucmut_result;
 int pmb_merge_runs(pmb_ctx* ctx, int source, int to_host, pmb_nucmut_result* out);
+/* Optional, for the batch uploaded last (cleared by the next upload): col_break[c] != 0 means column c never continues a
+ * run of column c - 1 even at a consecutive position. A PanGraph block batch lays its main positions first and the gap
+ * slots (pos, k) after them, so the first gap slot of every position is a break (src/panman.cpp:1242, 1261: non-gap
+ * records merge on pos + 1, gap records on equal pos and gapPos + 1). n_cols bytes, host or device; NULL clears. */
+int pmb_set_column_breaks(pmb_ctx* ctx, const uint8_t* col_break);
 
 /* Device-side view of the last result (for an NCCL gather straight from HBM). Pointers are device memory. */
 int pmb_result_device(pmb_ctx* ctx, pmb_result* out);

@@ -92,6 +92,10 @@ const int8_t* pmh_pangraph_root_override(const pmh_pangraph* g, int32_t block);
 const int32_t* pmh_pangraph_col_pos(const pmh_pangraph* g, int32_t block);
 const int32_t* pmh_pangraph_col_gap(const pmh_pangraph* g, int32_t block);
 int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t err_len);
+/* Node::nucMutation after pmh_pangraph_run (greedy <= 6 run-merge on the device, src/panman.cpp:1236-1272; 6-tuple NucMut
+ * ctor src/panman.hpp:154-189): the non-gap pieces of all blocks, then the gap pieces; primaryBlockId = block index. */
+int64_t pmh_pangraph_n_nucmut(const pmh_pangraph* g, int32_t node);
+const pmh_nucmut* pmh_pangraph_nucmut(const pmh_pangraph* g, int32_t node);
 /* lists of one batch after pmh_pangraph_run; block = -1: the block-level pass. Returns the record count. */
 int64_t pmh_pangraph_result(const pmh_pangraph* g, int32_t block, const int64_t** node_offsets, const int32_t** pos,
                             const uint8_t** type_code);

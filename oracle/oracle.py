@@ -346,6 +346,20 @@ class PortOracle:
         return op[:k].copy(), mi[:k].copy(), nu[:k].copy()
 
 
+    def merge_pangraph(self, gap: int, block: np.ndarray, pos: np.ndarray, gap_pos: np.ndarray, type_code: np.ndarray):
+        """reference src/panman.cpp:1236-1272 on one node's sorted 6-tuples; gap = 0 the non-gap list, 1 the gap list."""
+        n = len(pos)
+        a = lambda x, t: np.ascontiguousarray(x, t)
+        block, pos, gap_pos, tc = a(block, np.int32), a(pos, np.int32), a(gap_pos, np.int32), a(type_code, np.uint8)
+        ob, op, og = (np.empty(max(n, 1), np.int32) for _ in range(3))
+        mi = np.empty(max(n, 1), np.uint8)
+        nu = np.empty(max(n, 1), np.uint32)
+        k = self.L.orc_merge_pangraph(C.c_int(gap), C.c_int64(n), _p(block, C.c_int32), _p(pos, C.c_int32), _p(gap_pos, C.c_int32),
+                                      _p(tc, C.c_uint8), _p(ob, C.c_int32), _p(op, C.c_int32), _p(og, C.c_int32), _p(mi, C.c_uint8),
+                                      _p(nu, C.c_uint32))
+        return ob[:k].copy(), op[:k].copy(), og[:k].copy(), mi[:k].copy(), nu[:k].copy()
+
+
 # --------------------------------------------------------------------------- verbatim reference
 
 

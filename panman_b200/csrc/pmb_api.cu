@@ -112,6 +112,8 @@ struct pmb_ctx {
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
     DevBuf d_mcounts, d_moff, d_mpos, d_mtc;  // merged shards
     DevBuf d_rm_counts, d_rm_off, d_rm_pos, d_rm_info, d_rm_nucs;  // run-merge (pmb_merge_runs)
+    DevBuf d_col_break;
+    bool have_col_break = false;
     HostBuf h_rm_off, h_rm_pos, h_rm_info, h_rm_nucs;
     HostBuf h_pack_header;
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_offsets, d_pos, d_tc,
@@ -353,7 +355,7 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
-                          &c->d_rm_info, &c->d_rm_nucs})
+                          &c->d_rm_info, &c->d_rm_nucs, &c->d_col_break})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
                            &c->h_rm_info, &c->h_rm_nucs}) b->release();
@@ -440,6 +442,7 @@ int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* le
     PMB_CUDA(cudaSetDevice(c->device));
     c->have_input = false;
     c->have_result = false;
+    c->have_col_break = false;
     c->staging_cap = 0;
     c->n_cols = n_cols;
     c->col_base = col_base;
@@ -922,6 +925,20 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     return PMB_OK;
 }
 
+int pmb_set_column_breaks(pmb_ctx* c, const uint8_t* col_break) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->have_input) return fail(c, PMB_ERR_NO_INPUT, "pmb_upload_nuc has not been called");
+    PMB_CUDA(cudaSetDevice(c->device));
+    c->have_col_break = false;
+    if (!col_break) return PMB_OK;
+    PMB_CUDA(c->d_col_break.ensure(size_t(c->n_cols)));
+    PMB_CUDA(cudaMemcpyAsync(c->d_col_break.p, col_break, size_t(c->n_cols), cudaMemcpyDefault, c->stream));
+    PMB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is borrowed
+    c->have_col_break = true;
+    return PMB_OK;
+}
+
 int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) {
     if (!c || !out || (source != 0 && source != 1)) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
@@ -947,12 +964,14 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
     PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
     const unsigned blocks = unsigned(((long long)N * 32 + 255) / 256);
-    merge_runs_kernel<false><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr);
+    const uint8_t* brk = (source == 0 && c->have_col_break) ? c->d_col_break.as<uint8_t>() : nullptr;
+    merge_runs_kernel<false><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr,
+                                                           brk, c->col_base);
     scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->d_rm_counts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>());
     scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->d_rm_counts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>(),
                                                                  c->d_rm_off.as<long long>());
     merge_runs_kernel<true><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, nullptr, c->d_rm_off.as<long long>(), c->d_rm_pos.as<int32_t>(),
-                                                          c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>());
+                                                          c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(), brk, c->col_base);
     PMB_CUDA(cudaGetLastError());
     out->n_nodes = N;
     out->reserved = 0;

@@ -1655,9 +1655,12 @@ __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_byte
 // six; a piece becomes one NucMut {nucPosition = first position, mutInfo = (length << 4) + type, nucs = code_k <<
 // 4 (5 - k)}. A piece starts at record i iff (i - start of i's run) % 6 == 0. One warp per node, 32 records per step;
 // `carry` hands the run start across steps. FILL = false counts the pieces, true writes them at out_off[node].
+// col_break (optional, indexed by position - col_base): 1 = the column never continues the run of the column before it
+// (PanGraph batches: the first gap slot of every position, src/panman.cpp:1242, 1261).
 template <bool FILL>
 __global__ void merge_runs_kernel(const long long* off, const int32_t* pos, const uint8_t* tc, int n_nodes, unsigned int* counts,
-                                  const long long* out_off, int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs) {
+                                  const long long* out_off, int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs,
+                                  const uint8_t* col_break, long long col_base) {
     const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (node >= n_nodes) return;
     const long long a = off[node], b = off[node + 1];
@@ -1675,7 +1678,7 @@ __global__ void merge_runs_kernel(const long long* off, const int32_t* pos, cons
             pp = pos[i - 1];
             pt = uint32_t(tc[i - 1]) >> 4;
         }
-        const bool brk = valid && (i == a || p != pp + 1 || t != pt);
+        const bool brk = valid && (i == a || p != pp + 1 || t != pt || (col_break && col_break[p - col_base]));
         long long rs = brk ? i : -1;  // start of the run this record belongs to: latest break at or before it
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1691,7 +1694,7 @@ __global__ void merge_runs_kernel(const long long* off, const int32_t* pos, cons
             int len = 1;
             for (; len < 6 && i + len < b; len++) {
                 const uint32_t q = tc[i + len];
-                if (pos[i + len] != p + len || (q >> 4) != t) break;
+                if (pos[i + len] != p + len || (q >> 4) != t || (col_break && col_break[p + len - col_base])) break;
                 packed += (q & 15u) << (4 * (5 - len));
             }
             nuc_position[o] = p;

@@ -194,6 +194,21 @@ class PanGraphBuild:
             out.append((off, pos, tc))
         return out
 
+    def nucmut(self):
+        """Node::nucMutation per node after run(): lists of (nucPosition, nucGapPosition, primaryBlockId, secondaryBlockId,
+        mutInfo, nucs)."""
+        self.L.pmh_pangraph_n_nucmut.argtypes = [C.c_void_p, C.c_int32]
+        self.L.pmh_pangraph_n_nucmut.restype = C.c_int64
+        self.L.pmh_pangraph_nucmut.argtypes = [C.c_void_p, C.c_int32]
+        self.L.pmh_pangraph_nucmut.restype = C.POINTER(pmh_nucmut)
+        out = []
+        for v in range(self.tree.n_nodes):
+            k = self.L.pmh_pangraph_n_nucmut(self.h, v)
+            arr = self.L.pmh_pangraph_nucmut(self.h, v)
+            out.append([(arr[i].nucPosition, arr[i].nucGapPosition, arr[i].primaryBlockId, arr[i].secondaryBlockId, arr[i].mutInfo,
+                         arr[i].nucs) for i in range(k)])
+        return out
+
     def close(self):
         if self.h:
             self.L.pmh_pangraph_free(self.h)

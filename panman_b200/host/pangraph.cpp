@@ -159,10 +159,14 @@ struct BlockBatch {
     std::vector<int8_t> root_override_fitch;  // see the header comment; empty = none anywhere
     bool any_override = false;
     std::vector<int32_t> col_pos, col_gap;    // (j, k); k = -1 for main columns
-    // results of the last run
+    // results of the last run: per-node lists, and their run-merged pieces (start column, mutInfo, nucs)
     std::vector<int64_t> off;
     std::vector<int32_t> pos;
     std::vector<uint8_t> tc;
+    std::vector<int64_t> m_off;
+    std::vector<int32_t> m_col;
+    std::vector<uint8_t> m_info;
+    std::vector<uint32_t> m_nucs;
 };
 
 }  // namespace
@@ -174,6 +178,7 @@ struct pmh_pangraph {
     std::vector<int8_t> block_override; // n_blocks or empty
     BlockBatch block_level;             // results of the block-level pass
     bool has_reference = false;
+    std::vector<std::vector<pmh_nucmut>> nuc;  // Node::nucMutation after the run, in the reference's order
 };
 
 namespace {
@@ -393,9 +398,44 @@ int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t 
                          use_override ? B.root_override_fitch.data() : nullptr, nullptr, 0, 0, &res);
         if (rc) { set_err(err, err_len, "block " + B.id + ": " + pmb_last_error(ctx)); return rc; }
         keep(B, res);
+        // greedy <= 6 run-merge on the device (src/panman.cpp:1236-1272): main positions merge on pos + 1, gap slots on equal
+        // pos and gapPos + 1, so the first gap slot of every position never continues the column laid out before it
+        std::vector<uint8_t> brk(size_t(B.n_cols), 0);
+        for (int64_t c = 0; c < B.n_cols; c++) brk[c] = B.col_gap[c] == 0 ? 1 : 0;
+        pmb_nucmut_result mr;
+        rc = pmb_set_column_breaks(ctx, brk.data());
+        if (!rc) rc = pmb_merge_runs(ctx, 0, 1, &mr);
+        if (rc) { set_err(err, err_len, "block " + B.id + " run-merge: " + pmb_last_error(ctx)); return rc; }
+        B.m_off.assign(mr.node_offsets, mr.node_offsets + T.n_nodes() + 1);
+        B.m_col.assign(mr.nuc_position, mr.nuc_position + mr.n);
+        B.m_info.assign(mr.mut_info, mr.mut_info + mr.n);
+        B.m_nucs.assign(mr.nucs, mr.nucs + mr.n);
     }
+    // Node::nucMutation: the non-gap pieces of every block first, then the gap pieces (the reference appends the merged
+    // nonGapMutations map, then the merged gapMutations map; within a node both are sorted by block, position, gap slot)
+    g->nuc.assign(T.n_nodes(), {});
+    for (int pass = 0; pass < 2; pass++)
+        for (int32_t i = 0; i < NB; i++) {
+            const BlockBatch& B = g->blocks[i];
+            for (int32_t v = 0; v < T.n_nodes(); v++)
+                for (int64_t k = B.m_off[v]; k < B.m_off[v + 1]; k++) {
+                    const int32_t c = B.m_col[k];
+                    if ((B.col_gap[c] >= 0) != (pass == 1)) continue;
+                    pmh_nucmut m;
+                    m.nucPosition = B.col_pos[c];
+                    m.nucGapPosition = B.col_gap[c];
+                    m.primaryBlockId = i;
+                    m.secondaryBlockId = -1;
+                    m.mutInfo = B.m_info[k];
+                    m.nucs = B.m_nucs[k];
+                    g->nuc[v].push_back(m);
+                }
+        }
     return PMB_OK;
 }
+
+int64_t pmh_pangraph_n_nucmut(const pmh_pangraph* g, int32_t node) { return int64_t(g->nuc[node].size()); }
+const pmh_nucmut* pmh_pangraph_nucmut(const pmh_pangraph* g, int32_t node) { return g->nuc[node].data(); }
 
 int64_t pmh_pangraph_result(const pmh_pangraph* g, int32_t block, const int64_t** node_offsets, const int32_t** pos,
                             const uint8_t** type_code) {

@@ -91,5 +91,21 @@ def test_pangraph_flow_matches_oracle(port, algo):
             want, _ = port.run(tree, algo, bt["codes"], bt["parent_code"], ro, None, bt["present"], 0, n_threads=2)
             assert np.array_equal(off, want.node_offsets), (trial, bt["id"])
             assert np.array_equal(pos, want.pos) and np.array_equal(tc, want.type_code), (trial, bt["id"])
+        # Node::nucMutation: the oracle's run-merge of the 6-tuples (block, -1, pos, gapPos, type, code), non-gap list then gap list
+        got = build.nucmut()
+        for v in range(tree.n_nodes):
+            tup = []
+            for b, (bt, (off, pos, tc)) in enumerate(zip(build.batches, results[1:])):
+                for k in range(off[v], off[v + 1]):
+                    tup.append((b, int(bt["col_j"][pos[k]]), int(bt["col_k"][pos[k]]), int(tc[k])))
+            want_v = []
+            for gap in (0, 1):
+                sel = sorted(t for t in tup if (t[2] >= 0) == bool(gap))
+                if not sel:
+                    continue
+                ob, op_, og, mi, nu = port.merge_pangraph(gap, [t[0] for t in sel], [t[1] for t in sel], [t[2] for t in sel],
+                                                          np.asarray([t[3] for t in sel], np.uint8))
+                want_v += [(int(op_[i]), int(og[i]), int(ob[i]), -1, int(mi[i]), int(nu[i])) for i in range(len(ob))]
+            assert got[v] == want_v, (trial, v)
         build.close()
     ctx.close()
