@@ -9,7 +9,7 @@
  * PARITY PINNING: the reference ships no golden vectors (its test/ holds three data files,
  * SURVEY.md section 4). This port is pinned instead against the reference's own
  * fitchSankoff.cpp compiled verbatim (oracle/_ref/libpanman_ref.so, see oracle/Makefile):
- * tests/test_oracle_vs_reference.py compares them column by column, and
+ * tests/test_oracle.py compares them column by column, and
  * tests/golden/ holds vectors generated from that verbatim build
  * (tests/golden/make_golden.py).
  *

@@ -1628,6 +1628,9 @@ __global__ void merge_count_kernel(const unsigned char* packed, size_t shard_byt
     counts[v] = c;
 }
 
+// warp per node: the lanes first fetch the node's segment bounds in all shards at once (one round trip instead of one
+// per shard -- with 8 shards on the few SMs the pass kernels leave free this kernel was what limited rank 0), then the
+// segments are copied one after the other with the lanes across the records
 __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, long long cap,
                                   const long long* merged_off, int32_t* pos, uint8_t* type_code) {
     int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1635,17 +1638,26 @@ __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_byte
     long long run = merged_off[v];
     if (merged_off[v + 1] == run) return;
     const size_t po = packed_pos_offset(n_nodes), to = packed_tc_offset(n_nodes, cap);
-    for (int k = 0; k < n_shards; k++) {
-        const unsigned char* sh = packed + k * shard_bytes;
-        const long long* off = reinterpret_cast<const long long*>(sh + 16);
-        const long long a = off[v], b = off[v + 1];
-        const int32_t* sp = reinterpret_cast<const int32_t*>(sh + po);
-        const uint8_t* st = sh + to;
-        for (long long i = a + lane; i < b; i += 32) {
-            pos[run + (i - a)] = sp[i];
-            type_code[run + (i - a)] = st[i];
+    for (int k0 = 0; k0 < n_shards; k0 += 32) {
+        const int k = k0 + lane;
+        long long a = 0, len = 0;
+        if (k < n_shards) {
+            const long long* off = reinterpret_cast<const long long*>(packed + k * shard_bytes + 16);
+            a = off[v];
+            len = off[v + 1] - a;
         }
-        run += b - a;
+        const int nk = min(32, n_shards - k0);
+        for (int j = 0; j < nk; j++) {
+            const long long aj = __shfl_sync(FULL, a, j), lj = __shfl_sync(FULL, len, j);
+            const unsigned char* sh = packed + (size_t)(k0 + j) * shard_bytes;
+            const int32_t* sp = reinterpret_cast<const int32_t*>(sh + po) + aj;
+            const uint8_t* st = sh + to + aj;
+            for (long long i = lane; i < lj; i += 32) {
+                pos[run + i] = sp[i];
+                type_code[run + i] = st[i];
+            }
+            run += lj;
+        }
     }
 }
 
