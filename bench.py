@@ -39,6 +39,8 @@ def parse():
                     help="N > 1: SMs the pass kernels leave free so that the NCCL gather of step i can overlap pass i+1 (0 = serialise)")
     ap.add_argument("--e2e-contexts", type=int, default=1,
                     help="N = 1: contexts (host threads) the end-to-end measurement streams its batches through (1 = one call at a time)")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: split the configuration's columns over the ranks (strong scaling) instead of one configuration per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -209,6 +211,11 @@ def run_b200_arm(args):
     algo_i = pb.ALGO_FITCH if algo == "fitch" else pb.ALGO_SANKOFF
     C = cfg["n_cols"]
     c0 = rank * C  # weak scaling: rank r owns columns [r*C, (r+1)*C) of a world*C-column alignment
+    if args.strong and world > 1:
+        # strong scaling (BASELINE.json configs[3]: ONE alignment column-sharded over the GPUs): tile-aligned contiguous ranges
+        tiles = (cfg["n_cols"] + 1023) // 1024
+        a, b = tiles * rank // world, tiles * (rank + 1) // world
+        c0, C = a * 1024, min(cfg["n_cols"], b * 1024) - a * 1024
     tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
     spec = synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"])
     dev = torch.device("cuda", local)
@@ -319,7 +326,7 @@ def run_b200_arm(args):
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed, dev_total = float(el[0]), float(el[1])
     K = args.steps
-    units = N * C * world
+    units = N * (cfg["n_cols"] if (args.strong and world > 1) else C * world)
     value = units * K / elapsed
 
     # ---- end to end through the reference-facing C-ABI call with HOST buffers (H2D and D2H inside the timed region)
@@ -400,10 +407,10 @@ def run_b200_arm(args):
     line = {
         "metric": "fitch_sankoff_node_column_updates_per_sec", "value": value, "unit": "node*col/s", "n_gpus": world,
         "steps": K, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
         "dtype": "u16 Fitch sets as 16 bit-planes" if algo == "fitch" else "2-bit Sankoff excess as 32 bit-planes", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg['n_leaves']} leaves ({N} nodes) x {C} columns per GPU, {cfg['kind']} tree, "
-                               f"{algo}, seed {cfg['seed']}; rank r owns columns [r*{C},(r+1)*{C})",
+                               f"{algo}, seed {cfg['seed']}; " + (f"{cfg['n_cols']} columns split over the ranks" if (args.strong and world > 1) else f"rank r owns columns [r*{C},(r+1)*{C})"),
                    "l2": "inputs larger than L2: leaf planes + set matrix = "
                          f"{(tree.n_leaves * 0.5 + (N - tree.n_leaves) * (2 if algo == 'fitch' else 4)) * C / 1e6:.0f} MB per pass",
                    "parallelism": (f"column ranges x{world}, tree replicated, NCCL gather of mutation lists"
