@@ -30,6 +30,15 @@ def test_exports_match_header(lib):
     assert set(EXPORTS) == declared
 
 
+def test_host_library_exports_match_header(lib):
+    header = open(os.path.join(ROOT, "include", "panman_b200_host.h")).read()
+    declared = set(re.findall(r"\b(pmh_[a-z_0-9]+)\s*\(", header))
+    assert {"pmh_tree_from_newick", "pmh_build_from_msa", "pmh_pangraph_load", "pmh_pangraph_run"} <= declared
+    raw = C.CDLL(os.path.join(ROOT, "panman_b200", "libpanman_b200_host.so"))
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/panman_b200_host.h but not exported"
+
+
 def test_version_and_null_safety(lib):
     assert b"sm_100a" in lib.pmb_version()
     assert lib.pmb_last_error(None) == b"null context"
