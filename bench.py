@@ -252,7 +252,8 @@ def run_b200_arm(args):
         shard = dict(cap=cap, bytes=pbytes, send=[torch.empty(pbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
                      recv=[torch.empty(world * pbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if rank == 0 else None,
                      comm=torch.cuda.Stream(device=dev), lib=torch.cuda.ExternalStream(ctx.stream_handle(), device=dev), i=0,
-                     merged=None, done=[None, None], events=[torch.cuda.Event(), torch.cuda.Event()])
+                     merged=None, done=[None, None], events=[torch.cuda.Event(), torch.cuda.Event()],
+                     merge_stream=torch.cuda.Stream(device=dev), mdone=[None, None], mevents=[torch.cuda.Event(), torch.cuda.Event()])
         # receive views built once: the step loop is host-bound at N > 1, every Python object per step counts
         shard["dst"] = [[shard["recv"][k][r * pbytes:(r + 1) * pbytes] for r in range(world)] for k in range(2)] if rank == 0 else [None, None]
 
@@ -265,11 +266,19 @@ def run_b200_arm(args):
         ctx.pack_result(shard["send"][k], shard["cap"])     # on the library's stream, right behind the pass
         comm.wait_stream(lib)
         with torch.cuda.stream(comm):
+            if rank == 0 and shard["mdone"][k] is not None:
+                comm.wait_event(shard["mdone"][k])          # the merge that last read this receive buffer has finished
             dist.gather(shard["send"][k], shard["dst"][k], dst=0)  # enqueued on comm; the host does not block
             done = shard["events"][k]
             done.record(comm)
-            if rank == 0:
-                shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=comm.cuda_stream)
+        if rank == 0:
+            # the merge runs on its own stream: the gather of step i+1 overlaps the merge of step i (at 8 ranks the two in a
+            # row on one stream took longer than a pass and throttled the whole pipeline)
+            ms = shard["merge_stream"]
+            ms.wait_event(done)
+            shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=ms.cuda_stream)
+            shard["mevents"][k].record(ms)
+            shard["mdone"][k] = shard["mevents"][k]
         shard["done"][k] = done
         # The persistent pass kernels fill every SM they are given, and an NCCL kernel that has to squeeze in beside them
         # (on both ranks at once) stalls far longer than it runs. Either the pass kernels leave a few SMs free
@@ -292,6 +301,7 @@ def run_b200_arm(args):
         ctx.wait()
         if world > 1:
             shard["comm"].synchronize()
+            shard["merge_stream"].synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 
