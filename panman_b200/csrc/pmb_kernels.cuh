@@ -1,11 +1,13 @@
-// sm_100a kernels of libpanman_b200: level-synchronous Fitch / Sankoff passes over bit-plane matrices,
-// mutation staging with warp-ballot + prefix-sum compaction, ordered gather, and the ingest packers.
+// sm_100a kernels of libpanman_b200: persistent Fitch / Sankoff passes over bit-plane matrices (chain segments of deep
+// trees evaluated speculatively but exactly), mutation staging with warp-ballot + prefix-sum compaction, ordered
+// compaction by directory entry, the greedy run-merge into NucMut fields, shard merging, and the ingest packers.
 //
 // Work decomposition: one WARP owns (chunk of the tree) x (tile of 1024 columns). Lane l holds, for every
 // node it touches, one 32-bit word per bit-plane = columns [tile*1024 + l*32, +32). All HBM traffic is
-// 128-bit per lane, 512 contiguous bytes per warp instruction:
-//   leaf matrix   uint4 [row][tile][lane]            4 code planes            (0.5 B / column)
-//   set matrix    uint4 [op][tile][J][lane]          J=4 Fitch (16 planes),   (2 B / column)
+// 128-bit per lane, 512 contiguous bytes per warp instruction; every matrix is TILE-major, so a warp streams
+// through contiguous memory in program order:
+//   leaf matrix   uint4 [tile][leaf slot][lane]      4 code planes            (0.5 B / column)
+//   set matrix    uint4 [tile][op][J][lane]          J=4 Fitch (16 planes),   (2 B / column)
 //                                                    J=8 Sankoff (G,H planes) (4 B / column)
 // Reference semantics implemented here: src/fitchSankoff.cpp:30-171 (nuc Fitch), :224-308 (block Fitch),
 // :359-531 + :676-703 (nuc Sankoff), :707-818 (block Sankoff); see plane_math.h for the per-op logic.
