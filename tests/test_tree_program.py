@@ -70,3 +70,46 @@ def test_caterpillar_and_star_shapes():
         for i in range(1, n):
             spine.append(i - 1 if i % 2 else max(0, i - 2))
         assert _check(spine, 4, 0, 5) == 0
+
+
+# ---------------------------------------------------------------- emulation of the kernels' logic on the same random shapes
+def _flat_tree(parents):
+    from oracle.oracle import FlatTree
+
+    n = len(parents) + 1
+    kids = [[] for _ in range(n)]
+    for i, p in enumerate(parents):
+        kids[p].append(i + 1)
+    names, k = [], 0
+    for v in range(n):
+        if kids[v]:
+            k += 1
+            names.append(f"node_{k}")
+        else:
+            names.append(f"L{v}")
+    return FlatTree.from_children(names, kids, 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(trees(), st.sampled_from([1, 2, 4, 9, 40]), st.sampled_from([0, 1, 3]), st.integers(0, 1), st.sampled_from([0.0, 0.03, 0.5]),
+       st.integers(0, 2 ** 31 - 1))
+def test_emulation_matches_port_on_random_shapes(parents, chunk_nodes, inline_nodes, algo, noise, seed):
+    """Whatever the tree shape (unary chains, stars, deep backbones cut into chain segments) and however noisy the columns,
+    the emulated kernels -- speculation included, which asserts its own exactness -- produce the oracle's lists and states."""
+    from oracle.oracle import PortOracle
+
+    tree = _flat_tree(parents)
+    if tree.n_leaves < 1 or tree.n_nodes - tree.n_leaves < 1:
+        return
+    rng = np.random.default_rng(seed)
+    n_cols = int(rng.choice([7, 64, 1030]))
+    base = rng.integers(0, 5, size=n_cols)
+    codes = np.repeat(base[None, :], tree.n_leaves, 0)
+    codes = np.where(rng.random(codes.shape) < noise, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+    pc = rng.integers(0, 16, size=n_cols).astype(np.uint8)
+    ro = np.where(rng.random(n_cols) < 0.3, rng.integers(0, 16, size=n_cols), -1).astype(np.int8) if seed % 2 else None
+    want, want_states = PortOracle().run(tree, algo, codes, pc, ro, None, None, 0, n_threads=1, want_states=True)
+    rc, got, states, _ = _emu.run(tree, algo, codes, pc, ro, None, None, 0, chunk_nodes=chunk_nodes, inline_nodes=inline_nodes,
+                                  level_mode=seed % 3 == 0)
+    assert rc == 0
+    assert got.same_as(want) and np.array_equal(states, want_states)
