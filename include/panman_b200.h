@@ -128,6 +128,18 @@ int pmb_run_nuc(pmb_ctx* ctx, int algo, int64_t n_cols, int32_t n_rows, const ui
                 const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base, int flags,
                 pmb_result* out);
 
+/* ---- the block-level pass of a PanGraph build: one 3-state column per block ----
+ * Replaces blockFitchForwardPassNew / BackwardPassNew / AssignMutationsNew and blockSankoff* as driven by
+ * src/panman.cpp:873-963 (and src/reroot.cpp:54-122). leaf_block_state: n_rows x n_blocks bytes in HOST memory, row-major,
+ * 0 = the sequence lacks the block, 1 = forward strand, 2 = reverse strand (the reference's 1 / 2 / 4 and its 3-vector
+ * {absent, forward, reverse}); root_override: n_blocks or NULL, -1 none else the state the root is forced to
+ * (defaultState, :886-897). The parent state handed to the root is "absent", as in the reference. Records use the
+ * nucleotide form (see oracle.block_mut_from_nuc for the reference pair): type 2 = block insertion (code = strand state,
+ * 2 = inverted), type 1 = block deletion, type 0 = inversion of a present block. Same as pmb_run_nuc with
+ * PMB_FLAG_BLOCK_MODE on nibble-packed states. */
+int pmb_run_block(pmb_ctx* ctx, int algo, int64_t n_blocks, int32_t n_rows, const uint8_t* leaf_block_state,
+                  const int8_t* root_override, pmb_result* out);
+
 /* ---- the same, split so that the pass can be timed with inputs resident in HBM ----
  * pmb_upload_nuc copies + bit-plane-packs the inputs into device memory (the "packed leaf matrix resident in
  * HBM"); pmb_run_resident runs forward + backward + compaction on it, leaving the lists in device memory;

@@ -858,6 +858,21 @@ int pmb_run_nuc(pmb_ctx* c, int algo, int64_t n_cols, int32_t n_rows, const uint
     return pmb_download(c, out);
 }
 
+int pmb_run_block(pmb_ctx* c, int algo, int64_t n_blocks, int32_t n_rows, const uint8_t* leaf_block_state, const int8_t* root_override,
+                  pmb_result* out) {
+    if (!c || !leaf_block_state || !out || n_blocks <= 0 || n_rows <= 0) return c ? fail(c, PMB_ERR_INVALID, "bad block arguments") : PMB_ERR_INVALID;
+    const int64_t stride = (n_blocks + 1) / 2;
+    std::vector<uint8_t> codes4(size_t(n_rows) * size_t(stride), 0), parent(size_t(n_blocks), 0);  // parent state: absent
+    for (int32_t r = 0; r < n_rows; r++)
+        for (int64_t b = 0; b < n_blocks; b++) {
+            const uint8_t st = leaf_block_state[size_t(r) * size_t(n_blocks) + size_t(b)];
+            if (st > 2) return fail(c, PMB_ERR_INVALID, "block states are 0 (absent), 1 (forward) or 2 (reverse)");
+            codes4[size_t(r) * size_t(stride) + size_t(b >> 1)] |= uint8_t(st << (4 * (b & 1)));
+        }
+    return pmb_run_nuc(c, algo, n_blocks, n_rows, codes4.data(), stride, nullptr, parent.data(), root_override, nullptr, 0,
+                       PMB_FLAG_BLOCK_MODE, out);
+}
+
 // Debug only (not part of include/panman_b200.h): the per-item timeline of the last run made with option "trace".
 // Layout: 2 * n_items records of 4 x uint64 {start ns, end ns, (chunk << 32) | tile, (sm << 32) | ns spent waiting};
 // the first n_items are forward items, the rest backward items. Returns the number of uint64 copied.

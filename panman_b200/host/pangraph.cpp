@@ -382,12 +382,7 @@ int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t 
     };
     pmb_result res;
     {   // block-level pass (src/panman.cpp:873-963): one 3-state column per block, parent state "absent"
-        const int64_t stride = (NB + 1) / 2;
-        std::vector<uint8_t> codes4(size_t(L) * size_t(stride), 0), parent(NB, 0);
-        for (int32_t r = 0; r < L; r++)
-            for (int32_t i = 0; i < NB; i++) codes4[size_t(r) * stride + (i >> 1)] |= uint8_t(g->block_states[size_t(r) * NB + i] << (4 * (i & 1)));
-        rc = pmb_run_nuc(ctx, algo, NB, L, codes4.data(), stride, nullptr, parent.data(),
-                         g->block_override.empty() ? nullptr : g->block_override.data(), nullptr, 0, PMB_FLAG_BLOCK_MODE, &res);
+        rc = pmb_run_block(ctx, algo, NB, L, g->block_states.data(), g->block_override.empty() ? nullptr : g->block_override.data(), &res);
         if (rc) { set_err(err, err_len, std::string("block pass: ") + pmb_last_error(ctx)); return rc; }
         keep(g->block_level, res);
     }

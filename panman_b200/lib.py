@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("PANMAN_B200_LIB", os.path.join(HERE, "libpanman_b200.
 EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",
            "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version",
            "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream", "pmb_run_resident_async", "pmb_wait",
-           "pmb_host_alloc", "pmb_host_free", "pmb_merge_runs", "pmb_set_column_breaks"]
+           "pmb_host_alloc", "pmb_host_free", "pmb_merge_runs", "pmb_set_column_breaks", "pmb_run_block"]
 
 
 class pmb_result(C.Structure):
@@ -78,6 +78,7 @@ def load_library():
     L.pmb_host_free.restype = None
     L.pmb_merge_runs.argtypes = [vp, C.c_int, C.c_int, C.POINTER(pmb_nucmut_result)]
     L.pmb_set_column_breaks.argtypes = [vp, vp]
+    L.pmb_run_block.argtypes = [vp, C.c_int, i64, i32, vp, vp, C.POINTER(pmb_result)]
     L.pmb_pack_result.argtypes = [vp, vp, i64, vp]
     L.pmb_merge_packed.argtypes = [vp, i32, vp, i64, vp, C.POINTER(pmb_result)]
     _lib = L
