@@ -75,7 +75,8 @@ typedef struct pmb_result {
     int64_t n_cols;
 } pmb_result;
 
-/* Device-time breakdown of the last pmb_run_resident, CUDA events on the library's stream. */
+/* Device-time breakdown of the last pmb_run_resident, CUDA events on the library's stream. After an asynchronous pass
+ * (pmb_run_resident_async + pmb_wait) only total_ms is filled: the pass is timed as a whole. */
 typedef struct pmb_timings {
     float forward_ms;   /* post-order pass (all levels) */
     float backward_ms;  /* pre-order pass + mutation detection + staging append (all levels) */

@@ -91,6 +91,7 @@ struct pmb_ctx {
     bool state_dirty = true;           // per-run device state (counters, tickets, node counts, directory) must be re-initialised
     unsigned int pack_seq = 0;
     bool async_pending = false;
+    bool async_phase_events = true;
     int async_groups = 1;
 
     // tree
@@ -644,7 +645,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             c->dir_clean_epoch = bwd_epoch;
         }
         rp.dir_tag = bwd_epoch & DIR_TAG_MASK;
-        PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        // per-phase events only where somebody reads them: an asynchronous pass on one stream is timed as a whole, and
+        // every record between two kernels costs the stream a microsecond or two
+        const bool phase_events = !async || G > 1;
+        if (G > 1) PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         for (int g = 0; g < G; g++) {
             cudaStream_t st = G == 1 ? c->stream : c->gstream[g];
             if (G > 1) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_fork, 0));
@@ -655,14 +659,15 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
                 rp.epoch = fwd_epoch;
                 if ((rc = launch_pass(c, st, 2 * g, rp, algo, true, &n_launches))) return rc;
             }
-            PMB_CUDA(cudaEventRecord(c->gev_fwd[g], st));
+            if (phase_events) PMB_CUDA(cudaEventRecord(c->gev_fwd[g], st));
             rp.epoch = bwd_epoch;
             rp.trace_base = trace_items + (unsigned long long)P.chunks.size() * rp.tile_begin;
             if ((rc = launch_pass(c, st, 2 * g + 1 + 32 * (attempt & 1), rp, algo, false, &n_launches))) return rc;
-            PMB_CUDA(cudaEventRecord(c->gev_done[g], st));
+            if (phase_events) PMB_CUDA(cudaEventRecord(c->gev_done[g], st));
             if (G > 1) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->gev_done[g], 0));
         }
-        PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        if (phase_events) PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        c->async_phase_events = phase_events;
         {
             const unsigned long long n_entries = (unsigned long long)P.n_nodes * (unsigned long long)c->T;
             const unsigned groups = unsigned((n_entries + CPT_GROUP - 1) / CPT_GROUP);
@@ -780,9 +785,10 @@ int pmb_wait(pmb_ctx* c) {
     }
     c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 32);
     PMB_CUDA(cudaEventElapsedTime(&c->timings.total_ms, c->ev[0], c->ev[3]));
+    c->timings.forward_ms = c->timings.backward_ms = c->timings.compact_ms = 0.f;
+    if (!c->async_phase_events) return PMB_OK;  // timed as a whole
     PMB_CUDA(cudaEventElapsedTime(&c->timings.compact_ms, c->ev[2], c->ev[3]));
     float to_bwd_end = 0.f;
-    c->timings.forward_ms = 0.f;
     for (int g = 0; g < c->async_groups; g++) {
         float f = 0.f;
         PMB_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->gev_fwd[g]));
