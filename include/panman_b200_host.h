@@ -53,6 +53,17 @@ int pmh_tree_has_polytomy(const pmh_tree* t); /* reference src/panman.cpp:621-63
  * 1: Sankoff (FILE_TYPE::MSA_OPTIMIZE, :1467-1649). Returns NULL and fills err on failure. */
 pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len, const char* newick, const char* reference,
                               int low_mem_mode, char* err, size_t err_len);
+/* The same in two steps. pmh_msa_prepare is host-only (reader, consensus, all-gap column removal, packing: no device
+ * needed) and leaves the column batch in the build object; pmh_msa_run uploads it, runs the pass and the run-merge. */
+pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newick, const char* reference, int low_mem_mode,
+                           char* err, size_t err_len);
+int pmh_msa_run(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len);
+int64_t pmh_build_n_cols(const pmh_build* b);
+const uint8_t* pmh_build_codes4(const pmh_build* b, int64_t* row_stride); /* n_leaves rows; NULL once pmh_msa_run consumed it */
+const uint8_t* pmh_build_present(const pmh_build* b);                      /* n_leaves */
+const uint8_t* pmh_build_parent_code(const pmh_build* b);                  /* n_cols */
+const int8_t* pmh_build_root_override(const pmh_build* b);                 /* n_cols or NULL */
+const int8_t* pmh_build_fwd_root_ref(const pmh_build* b);                  /* n_cols or NULL */
 void pmh_build_free(pmh_build* b);
 const pmh_tree* pmh_build_tree(const pmh_build* b);
 const char* pmh_build_consensus(const pmh_build* b, int64_t* len); /* blocks[0] consensus (src/panman.cpp:1439) */

@@ -121,6 +121,53 @@ class MsaBuild:
         L.pmh_build_free(h)
 
 
+class MsaPrepared:
+    """pmh_msa_prepare: the host-only half of the -M flow (reader, consensus, all-gap column removal, packing)."""
+
+    def __init__(self, fasta: bytes, newick: str, reference: str = "", low_mem_mode: bool = False):
+        L = load_host_library()
+        vp = C.c_void_p
+        L.pmh_msa_prepare.restype = vp
+        L.pmh_msa_prepare.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        L.pmh_build_n_cols.argtypes = [vp]
+        L.pmh_build_n_cols.restype = C.c_int64
+        L.pmh_build_codes4.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.pmh_build_codes4.restype = C.POINTER(C.c_uint8)
+        for f, t in (("present", C.c_uint8), ("parent_code", C.c_uint8), ("root_override", C.c_int8), ("fwd_root_ref", C.c_int8)):
+            getattr(L, "pmh_build_" + f).argtypes = [vp]
+            getattr(L, "pmh_build_" + f).restype = C.POINTER(t)
+        err = C.create_string_buffer(512)
+        h = L.pmh_msa_prepare(fasta, len(fasta), newick.encode(), reference.encode(), int(low_mem_mode), err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode())
+        self.tree = HostTree(L.pmh_build_tree(h), owned=False)
+        n = C.c_int64()
+        p = L.pmh_build_consensus(h, C.byref(n))
+        self.consensus = C.string_at(p, n.value)
+        self.n_cols = int(L.pmh_build_n_cols(h))
+        nl, nc = self.tree.n_leaves, self.n_cols
+        stride = C.c_int64()
+        cp = L.pmh_build_codes4(h, C.byref(stride))
+        if nc and cp:
+            c4 = np.ctypeslib.as_array(cp, (nl, stride.value)).copy()
+            codes = np.empty((nl, 2 * stride.value), np.uint8)
+            codes[:, 0::2] = c4 & 15
+            codes[:, 1::2] = c4 >> 4
+            self.codes = codes[:, :nc]
+        else:
+            self.codes = np.zeros((nl, 0), np.uint8)
+
+        def arr(name, count):
+            q = getattr(L, "pmh_build_" + name)(h)
+            return np.ctypeslib.as_array(q, (count,)).copy() if q and count else None
+
+        self.present = arr("present", nl)
+        self.parent_code = arr("parent_code", nc)
+        self.root_override = arr("root_override", nc)
+        self.fwd_root_ref = arr("fwd_root_ref", nc)
+        L.pmh_build_free(h)
+
+
 class PanGraphBuild:
     """panmanUtils -P pangraph.json -N tree.nwk [--reference id] through libpanman_b200 (include/panman_b200_host.h):
     load() builds the per-block column batches on the host, run() executes the block-level pass and one pass per block."""

@@ -20,6 +20,14 @@
 struct pmh_build {
     pmh_tree tree;
     std::string consensus;
+    // the column batch (pmh_msa_prepare): nibble-packed leaf rows, presence, per-column parameters
+    int low_mem_mode = 0;
+    int64_t n_cols = 0, stride = 0;
+    uint8_t* codes4 = nullptr;  // page-locked where the device library can provide it
+    bool codes_cached = false;  // codes4 is the process-wide cached buffer (returned, not freed)
+    std::vector<uint8_t> codes_pageable, present, parent_code;
+    std::vector<int8_t> per_col;  // root_override (low-memory branch) or fwd_root_ref (MSA branch); empty = none
+    ~pmh_build();
     std::vector<std::vector<pmh_nucmut>> nuc;
     std::vector<int64_t> tuple_off;
     std::vector<int32_t> tuple_pos;
@@ -36,6 +44,44 @@ void set_err(char* err, size_t n, const std::string& m) {
     if (err && n) {
         std::strncpy(err, m.c_str(), n - 1);
         err[n - 1] = 0;
+    }
+}
+
+// Page-locking costs about as much as one pageable upload of the same bytes, so one buffer is kept for the following
+// builds of the process (PanGraph blocks, --low-mem-mode batches); a build that finds it taken pins its own.
+struct PinCache {
+    std::mutex m;
+    uint8_t* buf = nullptr;
+    size_t cap = 0;
+    bool in_use = false;
+} g_pin;
+
+uint8_t* pin_acquire(size_t bytes, bool* cached) {
+    std::lock_guard<std::mutex> lock(g_pin.m);
+    if (!g_pin.in_use) {
+        if (bytes > g_pin.cap) {
+            pmb_host_free(g_pin.buf);
+            g_pin.cap = 0;
+            g_pin.buf = static_cast<uint8_t*>(pmb_host_alloc(bytes + bytes / 4));
+            if (g_pin.buf) g_pin.cap = bytes + bytes / 4;
+        }
+        if (g_pin.buf) {
+            g_pin.in_use = true;
+            *cached = true;
+            return g_pin.buf;
+        }
+    }
+    *cached = false;
+    return static_cast<uint8_t*>(pmb_host_alloc(bytes));  // may be NULL (no device): the caller falls back to pageable memory
+}
+
+void pin_release(uint8_t* p, bool cached) {
+    if (!p) return;
+    if (cached) {
+        std::lock_guard<std::mutex> lock(g_pin.m);
+        g_pin.in_use = false;
+    } else {
+        pmb_host_free(p);
     }
 }
 
@@ -97,6 +143,8 @@ std::string read_msa(const char* text, size_t len, bool strip_cr, std::map<std::
 
 }  // namespace
 
+pmh_build::~pmh_build() { pin_release(codes4, codes_cached); }
+
 extern "C" {
 
 pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len) {
@@ -121,9 +169,9 @@ const int32_t* pmh_tree_child_index(const pmh_tree* t) { return t->t.child_idx.d
 const int32_t* pmh_tree_leaf_row(const pmh_tree* t) { return t->t.leaf_row.data(); }
 int pmh_tree_has_polytomy(const pmh_tree* t) { return t->t.has_polytomy() ? 1 : 0; }
 
-pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len, const char* newick, const char* reference_c,
-                              int low_mem_mode, char* err, size_t err_len) {
-    if (!ctx || !fasta || !newick) { set_err(err, err_len, "null argument"); return nullptr; }
+pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newick, const char* reference_c, int low_mem_mode,
+                           char* err, size_t err_len) {
+    if (!fasta || !newick) { set_err(err, err_len, "null argument"); return nullptr; }
     const std::string reference = reference_c ? reference_c : "";
     pmh_build* b = new pmh_build();
     auto fail = [&](const std::string& m) -> pmh_build* {
@@ -195,6 +243,8 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
         }
     }
     const int64_t n_cols = int64_t(cons.size());
+    b->low_mem_mode = low_mem_mode;
+    b->n_cols = n_cols;
     b->seconds[0] = since(t0);
     b->nuc.assign(T.n_nodes(), {});
     b->tuple_off.assign(T.n_nodes() + 1, 0);
@@ -203,24 +253,13 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
     // ---- pack: leaf rows (4-bit codes, two columns per byte) in tree leaf order; leaves without a sequence are absent
     t0 = Clock::now();
     const int64_t stride = ((n_cols + 1) / 2 + 15) / 16 * 16;
-    // Page-locked when the device library can provide it (the upload then runs at PCIe speed). Page-locking costs about as
-    // much as one pageable upload of the same bytes, so the buffer is kept for the following builds of the process
-    // (PanGraph blocks, --low-mem-mode batches) instead of being pinned anew each time.
     const size_t codes_bytes = size_t(T.n_leaves) * size_t(stride);
-    static std::mutex pin_mutex;
-    static uint8_t* pin_buf = nullptr;
-    static size_t pin_cap = 0;
-    std::unique_lock<std::mutex> pin_lock(pin_mutex);  // one build at a time uses the cached buffer
-    if (codes_bytes > pin_cap) {
-        pmb_host_free(pin_buf);
-        pin_cap = 0;
-        pin_buf = static_cast<uint8_t*>(pmb_host_alloc(codes_bytes + codes_bytes / 4));
-        if (pin_buf) pin_cap = codes_bytes + codes_bytes / 4;
-    }
-    std::vector<uint8_t> pageable;
-    if (!pin_buf) pageable.resize(codes_bytes);
-    uint8_t* const codes4 = pin_buf ? pin_buf : pageable.data();  // rows of absent leaves are never read (presence mask)
-    std::vector<uint8_t> present(T.n_leaves, 0);
+    b->stride = stride;
+    b->codes4 = pin_acquire(codes_bytes, &b->codes_cached);
+    if (!b->codes4) b->codes_pageable.resize(codes_bytes);
+    uint8_t* const codes4 = b->codes4 ? b->codes4 : b->codes_pageable.data();  // rows of absent leaves are never read (presence mask)
+    std::vector<uint8_t>& present = b->present;
+    present.assign(T.n_leaves, 0);
     std::vector<std::pair<int32_t, const std::string*>> rows;
     for (int32_t v = 0; v < T.n_nodes(); v++) {
         if (T.leaf_row[v] < 0) continue;
@@ -244,20 +283,36 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
             });
         for (auto& x : th) x.join();
     }
-    std::vector<uint8_t> parent_code(n_cols);
+    std::vector<uint8_t>& parent_code = b->parent_code;
+    parent_code.resize(n_cols);
     for (int64_t i = 0; i < n_cols; i++) parent_code[i] = kCode.t[(unsigned char)cons[i]];
-    std::vector<int8_t> per_col;
-    const int8_t *root_override = nullptr, *fwd_root_ref = nullptr;
-    if (ref_seq) {
-        per_col.resize(n_cols);
-        for (int64_t i = 0; i < n_cols; i++) per_col[i] = int8_t(kCode.t[(unsigned char)(*ref_seq)[i]]);
-        if (low_mem_mode) root_override = per_col.data();  // defaultState (:1583-1604)
-        else fwd_root_ref = per_col.data();                // refState (:1419-1420)
+    if (ref_seq) {  // defaultState of the low-memory branch (:1583-1604) / refState of the MSA branch (:1419-1420)
+        b->per_col.resize(n_cols);
+        for (int64_t i = 0; i < n_cols; i++) b->per_col[i] = int8_t(kCode.t[(unsigned char)(*ref_seq)[i]]);
     }
     b->seconds[1] = since(t0);
+    return b;
+}
+
+int pmh_msa_run(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
+    if (!ctx || !b) { set_err(err, err_len, "null argument"); return PMB_ERR_INVALID; }
+    auto fail = [&](const std::string& m) -> int {
+        set_err(err, err_len, m);
+        return PMB_ERR_INVALID;
+    };
+    const pmh::HostTree& T = b->tree.t;
+    const int64_t n_cols = b->n_cols, stride = b->stride;
+    if (n_cols == 0) return PMB_OK;
+    const uint8_t* codes4 = b->codes4 ? b->codes4 : b->codes_pageable.data();
+    if (!codes4 || b->present.empty()) return fail("the batch was already consumed by an earlier pmh_msa_run");
+    const std::vector<uint8_t>& present = b->present;
+    const std::vector<uint8_t>& parent_code = b->parent_code;
+    const int low_mem_mode = b->low_mem_mode;
+    const int8_t* root_override = (!b->per_col.empty() && low_mem_mode) ? b->per_col.data() : nullptr;
+    const int8_t* fwd_root_ref = (!b->per_col.empty() && !low_mem_mode) ? b->per_col.data() : nullptr;
 
     // ---- the passes
-    t0 = Clock::now();
+    auto t0 = Clock::now();
     int rc = pmb_set_tree(ctx, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data());
     if (rc) return fail(std::string("pmb_set_tree: ") + pmb_last_error(ctx));
     bool all_present = std::all_of(present.begin(), present.end(), [](uint8_t x) { return x != 0; });
@@ -266,6 +321,9 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
                      all_present ? nullptr : present.data(), parent_code.data(), root_override, fwd_root_ref, 0, 0, &res);
     if (rc) return fail(std::string("pmb_run_nuc: ") + pmb_last_error(ctx));
     b->seconds[2] = since(t0);
+    pin_release(b->codes4, b->codes_cached);  // uploaded: the page-locked buffer can serve the next build
+    b->codes4 = nullptr;
+    b->codes_pageable = std::vector<uint8_t>();
 
     // ---- lists are already per node in ascending position (= std::sort of the tuples, :1447); merge runs
     t0 = Clock::now();
@@ -290,10 +348,31 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
         }
     }
     b->seconds[3] = since(t0);
+    return PMB_OK;
+}
+
+pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len, const char* newick, const char* reference,
+                              int low_mem_mode, char* err, size_t err_len) {
+    if (!ctx) { set_err(err, err_len, "null argument"); return nullptr; }
+    pmh_build* b = pmh_msa_prepare(fasta, fasta_len, newick, reference, low_mem_mode, err, err_len);
+    if (!b) return nullptr;
+    if (pmh_msa_run(ctx, b, err, err_len) != PMB_OK) {
+        delete b;
+        return nullptr;
+    }
     return b;
 }
 
 void pmh_build_free(pmh_build* b) { delete b; }
+int64_t pmh_build_n_cols(const pmh_build* b) { return b->n_cols; }
+const uint8_t* pmh_build_codes4(const pmh_build* b, int64_t* row_stride) {
+    if (row_stride) *row_stride = b->stride;
+    return b->codes4 ? b->codes4 : (b->codes_pageable.empty() ? nullptr : b->codes_pageable.data());
+}
+const uint8_t* pmh_build_present(const pmh_build* b) { return b->present.data(); }
+const uint8_t* pmh_build_parent_code(const pmh_build* b) { return b->parent_code.data(); }
+const int8_t* pmh_build_root_override(const pmh_build* b) { return (!b->per_col.empty() && b->low_mem_mode) ? b->per_col.data() : nullptr; }
+const int8_t* pmh_build_fwd_root_ref(const pmh_build* b) { return (!b->per_col.empty() && !b->low_mem_mode) ? b->per_col.data() : nullptr; }
 const pmh_tree* pmh_build_tree(const pmh_build* b) { return &b->tree; }
 const char* pmh_build_consensus(const pmh_build* b, int64_t* len) {
     if (len) *len = int64_t(b->consensus.size());

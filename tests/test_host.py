@@ -39,6 +39,73 @@ def _fasta(names, rows, width=70):
     return b"\n".join(out) + b"\n"
 
 
+def _msa_case(rng, trial, low_mem):
+    """A random alignment + tree, and what the reference's -M branch makes of it: (tree, names, rows, reference id, consensus,
+    the rows the passes see)."""
+    alphabet = np.frombuffer(b"ACGTN-ACGTACGTRYKM", np.uint8)
+    kind = ["binary", "polytomy", "caterpillar"][trial % 3]
+    tree = random_tree(int(rng.integers(2, 80)), 700 + trial, kind, max_arity=4)
+    names = [tree.names[v] for v in tree.leaves]
+    n_cols = int(rng.integers(1, 2500))
+    base = rng.choice(alphabet[:4], size=n_cols)
+    rows = np.repeat(base[None, :], len(names), 0)
+    noise = rng.random(rows.shape) < 0.1
+    rows = np.where(noise, rng.choice(alphabet, size=rows.shape), rows).astype(np.uint8)
+    if not low_mem:
+        rows[:, rng.random(n_cols) < 0.03] = ord("-")  # all-gap columns: dropped by the -M branch
+    else:
+        rows = rows[:, (rows != ord("-")).any(0)]
+    reference = names[int(rng.integers(0, len(names)))] if trial % 2 else ""
+    order = sorted(range(len(names)), key=lambda i: names[i].encode())
+    srt = rows[order]
+    nongap = srt != ord("-")
+    first = srt[nongap.argmax(0), np.arange(rows.shape[1])]
+    if not low_mem:
+        if reference:
+            cons, use = rows[names.index(reference)].copy(), rows
+        else:
+            keep = nongap.any(0)
+            cons, use = first[keep], rows[:, keep]
+    else:
+        use = rows
+        if reference:
+            r = rows[names.index(reference)]
+            cons = np.where(r != ord("-"), r, np.where(nongap.any(0), first, 0)).astype(np.uint8)
+        else:
+            cons = first
+    return tree, names, rows, reference, cons, use
+
+
+@pytest.mark.parametrize("low_mem", [False, True])
+def test_msa_prepare_on_the_host(low_mem):
+    """The host-only half of the -M flow (pmh_msa_prepare: FASTA reader incl. wrapped lines and descriptions, consensus rule,
+    all-gap column removal, nibble packing, per-column parameters) against the restated rules -- no device involved."""
+    import panman_b200 as pb
+
+    pb.build_library()
+    from panman_b200.host import MsaPrepared
+
+    rng = np.random.default_rng(31 + int(low_mem))
+    for trial in range(10):
+        tree, names, rows, reference, cons, use = _msa_case(rng, trial, low_mem)
+        prep = MsaPrepared(_fasta(names, rows), tree.to_newick(), reference, low_mem)
+        assert prep.tree.names == tree.names
+        assert prep.consensus == bytes(cons), trial
+        assert prep.n_cols == len(cons)
+        row_of = {tree.names[v]: int(tree.leaf_row[v]) for v in tree.leaves}
+        want = np.zeros((tree.n_leaves, len(cons)), np.uint8)
+        for n, r in zip(names, use):
+            want[row_of[n]] = CODE_OF[r]
+        assert np.array_equal(prep.codes, want), trial
+        assert prep.present.all()
+        assert np.array_equal(prep.parent_code, CODE_OF[np.frombuffer(bytes(cons), np.uint8)])
+        refcodes = CODE_OF[use[names.index(reference)]].astype(np.int8) if reference else None
+        if low_mem:
+            assert prep.fwd_root_ref is None and (np.array_equal(prep.root_override, refcodes) if reference else prep.root_override is None)
+        else:
+            assert prep.root_override is None and (np.array_equal(prep.fwd_root_ref, refcodes) if reference else prep.fwd_root_ref is None)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("low_mem", [False, True])
 def test_msa_build_matches_reference_flow(port, ref, low_mem):
