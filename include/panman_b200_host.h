@@ -65,6 +65,9 @@ const uint8_t* pmh_build_parent_code(const pmh_build* b);                  /* n_
 const int8_t* pmh_build_root_override(const pmh_build* b);                 /* n_cols or NULL */
 const int8_t* pmh_build_fwd_root_ref(const pmh_build* b);                  /* n_cols or NULL */
 void pmh_build_free(pmh_build* b);
+/* Tuning: FASTA texts of at least this many bytes are cut at header lines and parsed by several threads (default 8 MiB;
+ * 0 = always). The records are stored in file order either way, so the result does not depend on it. */
+void pmh_set_reader_parallel_bytes(int64_t bytes);
 const pmh_tree* pmh_build_tree(const pmh_build* b);
 const char* pmh_build_consensus(const pmh_build* b, int64_t* len); /* blocks[0] consensus (src/panman.cpp:1439) */
 int64_t pmh_build_n_nucmut(const pmh_build* b, int32_t node);

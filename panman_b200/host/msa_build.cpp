@@ -98,45 +98,108 @@ const CodeTable kCode;
 
 // FASTA reader of the MSA branch (src/panman.cpp:1288-1325). `strip_cr`: the MSA branch cuts lines and ids at '\r',
 // the low-memory branch (:1479-1501, readFastaInBatch :677-724) does not.
-std::string read_msa(const char* text, size_t len, bool strip_cr, std::map<std::string, std::string>* seqs, size_t* line_length) {
-    std::string cur_seq, cur_id;
-    size_t ll = 0;
-    auto first_piece = [](const std::string& s, char delim) {
-        std::vector<std::string> w;
-        pmh::split_quote_aware(s, delim, w);
-        return w.empty() ? std::string() : w[0];
-    };
-    // Same results as the reference's line-by-line reader, one copy per sequence byte: a sequence line without '\r' is
-    // appended straight from the input (splitting at an absent delimiter returns the whole line), finished sequences
-    // are moved into the map.
-    size_t p = 0;
-    while (p < len) {
-        const char* nl = static_cast<const char*>(std::memchr(text + p, '\n', len - p));
-        size_t e = nl ? size_t(nl - text) : len;
+std::string first_piece(const std::string& s, char delim) {
+    std::vector<std::string> w;
+    pmh::split_quote_aware(s, delim, w);
+    return w.empty() ? std::string() : w[0];
+}
+
+struct FastaRecord {
+    std::string id;   // as the header gives it (text after '>' up to the first blank), before any '\r' cut
+    std::string seq;  // the record's sequence lines joined
+};
+
+// One contiguous piece of the file, line by line, exactly like the reference's reader. A piece either starts at a header
+// line or at the very beginning of the file (where sequence lines without a header belong to the id "").
+// One copy per sequence byte: a line without '\r' is appended straight from the input (splitting at an absent delimiter
+// returns the whole line).
+void parse_fasta_piece(const char* text, size_t begin, size_t end, bool strip_cr, size_t reserve_hint, std::vector<FastaRecord>* out) {
+    FastaRecord cur;
+    bool open = false;  // a record (or the headerless start of the file) is being collected
+    size_t p = begin;
+    while (p < end) {
+        const char* nl = static_cast<const char*>(std::memchr(text + p, '\n', end - p));
+        size_t e = nl ? size_t(nl - text) : end;
         const char* lp = text + p;
         const size_t ln = e - p;
         p = e + 1;
         if (ln == 0) continue;
         if (lp[0] == '>') {
-            if (!cur_seq.empty()) {
-                if (ll == 0) ll = cur_seq.size();
-                else if (ll != cur_seq.size()) return "sequence lengths don't match: " + cur_id;
-                (*seqs)[strip_cr ? first_piece(cur_id, '\r') : cur_id] = std::move(cur_seq);
-            }
-            cur_id = first_piece(std::string(lp, ln), ' ').substr(1);
-            cur_seq.clear();
-            cur_seq.reserve(ll);
-        } else if (strip_cr && std::memchr(lp, '\r', ln)) {
-            cur_seq += first_piece(std::string(lp, ln), '\r');
+            if (open) out->push_back(std::move(cur));
+            cur = FastaRecord();
+            cur.id = first_piece(std::string(lp, ln), ' ').substr(1);
+            cur.seq.reserve(reserve_hint);
+            open = true;
         } else {
-            cur_seq.append(lp, ln);
+            open = true;
+            if (strip_cr && std::memchr(lp, '\r', ln)) cur.seq += first_piece(std::string(lp, ln), '\r');
+            else cur.seq.append(lp, ln);
         }
     }
-    if (!cur_seq.empty()) {
-        if (ll != 0 && ll != cur_seq.size()) return "sequence lengths don't match: " + cur_id;
-        ll = cur_seq.size();
-        (*seqs)[cur_id] = std::move(cur_seq);  // the last record keeps its id as is (:1316-1325)
+    if (open) out->push_back(std::move(cur));
+}
+
+size_t g_reader_parallel_bytes = size_t(8) << 20;  // files at least this large are parsed by several threads
+
+// FASTA reader of the MSA branch (src/panman.cpp:1288-1325). `strip_cr`: the MSA branch cuts lines and ids at '\r',
+// the low-memory branch (:1479-1501, readFastaInBatch :677-724) does not. The reference's rules, kept record by record:
+// a record without sequence is dropped; the first stored record fixes the length every other one must have; every
+// record but the LAST is stored under its id cut at '\r' (MSA branch), the last keeps its id as is (:1316-1325); a
+// later record with the same id replaces the earlier one. Large files are cut at header lines and the pieces parsed in
+// parallel; the records are then stored in file order, so the result does not depend on the number of threads.
+std::string read_msa(const char* text, size_t len, bool strip_cr, std::map<std::string, std::string>* seqs, size_t* line_length) {
+    std::vector<std::vector<FastaRecord>> pieces;
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (len < g_reader_parallel_bytes || hw == 1) {
+        pieces.resize(1);
+        parse_fasta_piece(text, 0, len, strip_cr, 0, &pieces[0]);
+    } else {
+        // header lines: '>' at the start of the file or right after a newline
+        std::vector<std::vector<size_t>> found(hw);
+        {
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < hw; k++)
+                th.emplace_back([&, k]() {
+                    const size_t a = len * k / hw, b = len * (k + 1) / hw;
+                    for (size_t i = a; i < b;) {
+                        const char* q = static_cast<const char*>(std::memchr(text + i, '>', b - i));
+                        if (!q) break;
+                        const size_t at = size_t(q - text);
+                        if (at == 0 || text[at - 1] == '\n') found[k].push_back(at);
+                        i = at + 1;
+                    }
+                });
+            for (auto& t : th) t.join();
+        }
+        std::vector<size_t> headers;
+        for (auto& f : found) headers.insert(headers.end(), f.begin(), f.end());
+        // cut points: piece k starts at the first header at or after len * k / hw (piece 0 at the start of the file)
+        std::vector<size_t> cuts{0};
+        for (unsigned k = 1; k < hw; k++) {
+            auto it = std::lower_bound(headers.begin(), headers.end(), len * k / hw);
+            if (it != headers.end() && *it > cuts.back()) cuts.push_back(*it);
+        }
+        cuts.push_back(len);
+        const size_t hint = headers.size() > 1 ? (len / headers.size()) : 0;
+        pieces.resize(cuts.size() - 1);
+        std::vector<std::thread> th;
+        for (size_t k = 0; k + 1 < cuts.size(); k++)
+            th.emplace_back([&, k]() { parse_fasta_piece(text, cuts[k], cuts[k + 1], strip_cr, hint, &pieces[k]); });
+        for (auto& t : th) t.join();
     }
+    // the last record of the file, if it has a sequence, is the one the reference stores after its loop
+    FastaRecord* last = nullptr;
+    for (auto it = pieces.rbegin(); it != pieces.rend() && !last; ++it)
+        if (!it->empty()) last = &it->back();
+    size_t ll = 0;
+    for (auto& piece : pieces)
+        for (FastaRecord& r : piece) {
+            if (r.seq.empty()) continue;
+            if (ll == 0) ll = r.seq.size();
+            else if (ll != r.seq.size()) return "sequence lengths don't match: " + r.id;
+            const bool is_last = &r == last;
+            (*seqs)[(strip_cr && !is_last) ? first_piece(r.id, '\r') : r.id] = std::move(r.seq);
+        }
     *line_length = ll;
     return "";
 }
@@ -364,6 +427,7 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
 }
 
 void pmh_build_free(pmh_build* b) { delete b; }
+void pmh_set_reader_parallel_bytes(int64_t bytes) { g_reader_parallel_bytes = bytes < 0 ? 0 : size_t(bytes); }
 int64_t pmh_build_n_cols(const pmh_build* b) { return b->n_cols; }
 const uint8_t* pmh_build_codes4(const pmh_build* b, int64_t* row_stride) {
     if (row_stride) *row_stride = b->stride;

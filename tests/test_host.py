@@ -29,14 +29,14 @@ def test_cpp_newick_matches_restated_conventions():
             parse_newick(bad)
 
 
-def _fasta(names, rows, width=70):
+def _fasta(names, rows, width=70, eol=b"\n", final_eol=True):
     out = []
     for n, r in zip(names, rows):
         out.append(b">" + n.encode() + b" some description")
         s = bytes(r)
         for i in range(0, len(s), width):
             out.append(s[i:i + width])
-    return b"\n".join(out) + b"\n"
+    return eol.join(out) + (eol if final_eol else b"")
 
 
 def _msa_case(rng, trial, low_mem):
@@ -76,19 +76,27 @@ def _msa_case(rng, trial, low_mem):
     return tree, names, rows, reference, cons, use
 
 
+@pytest.mark.parametrize("parallel_bytes", [1 << 40, 0])
 @pytest.mark.parametrize("low_mem", [False, True])
-def test_msa_prepare_on_the_host(low_mem):
+def test_msa_prepare_on_the_host(low_mem, parallel_bytes):
     """The host-only half of the -M flow (pmh_msa_prepare: FASTA reader incl. wrapped lines and descriptions, consensus rule,
     all-gap column removal, nibble packing, per-column parameters) against the restated rules -- no device involved."""
     import panman_b200 as pb
 
     pb.build_library()
-    from panman_b200.host import MsaPrepared
+    from panman_b200.host import MsaPrepared, load_host_library
 
+    # the reader cuts large files at header lines and parses the pieces in parallel: both paths must give the same
+    import ctypes as C
+
+    load_host_library().pmh_set_reader_parallel_bytes(C.c_int64(parallel_bytes))
     rng = np.random.default_rng(31 + int(low_mem))
     for trial in range(10):
         tree, names, rows, reference, cons, use = _msa_case(rng, trial, low_mem)
-        prep = MsaPrepared(_fasta(names, rows), tree.to_newick(), reference, low_mem)
+        # the MSA branch cuts lines at '\r' (CRLF files), the low-memory branch does not; wrapped or single-line records
+        text = _fasta(names, rows, width=[70, 7, 10 ** 9][trial % 3], eol=b"\r\n" if (not low_mem and trial % 4 == 1) else b"\n",
+                      final_eol=trial % 5 != 2)
+        prep = MsaPrepared(text, tree.to_newick(), reference, low_mem)
         assert prep.tree.names == tree.names
         assert prep.consensus == bytes(cons), trial
         assert prep.n_cols == len(cons)
@@ -104,6 +112,7 @@ def test_msa_prepare_on_the_host(low_mem):
             assert prep.fwd_root_ref is None and (np.array_equal(prep.root_override, refcodes) if reference else prep.root_override is None)
         else:
             assert prep.root_override is None and (np.array_equal(prep.fwd_root_ref, refcodes) if reference else prep.fwd_root_ref is None)
+    load_host_library().pmh_set_reader_parallel_bytes(C.c_int64(8 << 20))
 
 
 @pytest.mark.gpu
