@@ -1020,3 +1020,54 @@ extern "C" int emul_prog_check(int n_nodes, int root, const int32_t* child_off, 
     (void)has_child_chunk;
     return 0;
 }
+
+// merge_runs_kernel, warp step by warp step (32 records per step, the run start handed across steps): the pieces of one
+// node's position-sorted records. Returns the number of pieces; outputs sized n by the caller.
+extern "C" long long emul_merge_runs(long long n, const int32_t* pos, const uint8_t* tc, const uint8_t* col_break, long long col_base,
+                                     int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs) {
+    const long long a = 0, b = n;
+    long long carry = a, written = 0;
+    for (long long base = a; base < b; base += 32) {
+        long long rs[32];
+        bool valid[32], piece[32];
+        for (int lane = 0; lane < 32; lane++) {
+            const long long i = base + lane;
+            valid[lane] = i < b;
+            bool brk = false;
+            if (valid[lane]) {
+                const int32_t p = pos[i];
+                const uint32_t t = uint32_t(tc[i]) >> 4;
+                brk = i == a || p != pos[i - 1] + 1 || t != (uint32_t(tc[i - 1]) >> 4) || (col_break && col_break[p - col_base]);
+            }
+            rs[lane] = brk ? i : -1;
+        }
+        for (int d = 1; d < 32; d <<= 1) {  // inclusive max-scan, as the shuffles do it
+            long long prev[32];
+            for (int lane = 0; lane < 32; lane++) prev[lane] = rs[lane];
+            for (int lane = d; lane < 32; lane++) rs[lane] = std::max(prev[lane], prev[lane - d]);
+        }
+        int rank = 0;
+        for (int lane = 0; lane < 32; lane++) {
+            rs[lane] = std::max(rs[lane], carry);
+            const long long i = base + lane;
+            piece[lane] = valid[lane] && ((i - rs[lane]) % 6 == 0);
+            if (!piece[lane]) continue;
+            const long long o = written + rank++;
+            const int32_t p = pos[i];
+            const uint32_t t = uint32_t(tc[i]) >> 4;
+            uint32_t packed = (uint32_t(tc[i]) & 15u) << 20;
+            int len = 1;
+            for (; len < 6 && i + len < b; len++) {
+                const uint32_t q = tc[i + len];
+                if (pos[i + len] != p + len || (q >> 4) != t || (col_break && col_break[p + len - col_base])) break;
+                packed += (q & 15u) << (4 * (5 - len));
+            }
+            nuc_position[o] = p;
+            mut_info[o] = uint8_t((len << 4) + int(t));
+            nucs[o] = packed;
+        }
+        written += rank;
+        carry = rs[31];
+    }
+    return written;
+}

@@ -99,3 +99,40 @@ def test_emulation_chain_segments(emu, port, noise):
                 assert stats[4] > 0, "the tree was expected to be cut into chain segments"
                 if noise == 0.0:  # both passes speculate (Fitch and Sankoff) and conserved columns always resolve
                     assert stats[5] > 0 and stats[6] == stats[5]
+
+
+def test_run_merge_logic_matches_oracle(emu, port):
+    """The warp-step logic of merge_runs_kernel (pieces start where (index - run start) % 6 == 0, the run start is carried
+    across 32-record steps) against the oracle's greedy merge (reference src/panman.cpp:1445-1466), incl. column breaks
+    checked against the oracle's PanGraph gap-list rule (:1261)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(17)
+    f = emu.L.emul_merge_runs
+    f.restype = C.c_longlong
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    for trial in range(300):
+        n = int(rng.integers(1, 200))
+        # positions: long consecutive stretches with occasional jumps; types change now and then
+        step = np.where(rng.random(n) < [0.05, 0.3, 0.8][trial % 3], rng.integers(2, 9, size=n), 1)
+        pos = np.cumsum(step).astype(np.int32) + int(rng.integers(0, 50))
+        ty = np.cumsum(rng.random(n) < 0.1) % 3
+        tc = ((ty << 4) | rng.integers(0, 16, size=n)).astype(np.uint8)
+        out_p, out_i, out_n = np.empty(n, np.int32), np.empty(n, np.uint8), np.empty(n, np.uint32)
+        k = f(C.c_longlong(n), P(pos, C.c_int32), P(tc, C.c_uint8), None, C.c_longlong(0), P(out_p, C.c_int32), P(out_i, C.c_uint8),
+              P(out_n, C.c_uint32))
+        wp, wi, wn = port.merge_msa(pos, tc)
+        assert k == len(wp) and np.array_equal(out_p[:k], wp) and np.array_equal(out_i[:k], wi) and np.array_equal(out_n[:k], wn), trial
+        # gap-slot columns: column c = (gap position j, slot k); consecutive columns merge only inside one position
+        widths = rng.integers(1, 12, size=40)
+        col_j = np.repeat(np.arange(len(widths)), widths)
+        col_k = np.concatenate([np.arange(w) for w in widths])
+        brk = (col_k == 0).astype(np.uint8)
+        cols = np.sort(rng.choice(len(col_j), size=min(n, len(col_j)), replace=False)).astype(np.int32)
+        tcc = tc[:len(cols)]
+        out_p, out_i, out_n = np.empty(len(cols), np.int32), np.empty(len(cols), np.uint8), np.empty(len(cols), np.uint32)
+        k = f(C.c_longlong(len(cols)), P(cols, C.c_int32), P(tcc, C.c_uint8), P(brk, C.c_uint8), C.c_longlong(0), P(out_p, C.c_int32),
+              P(out_i, C.c_uint8), P(out_n, C.c_uint32))
+        ob, op_, og, mi, nu = port.merge_pangraph(1, np.zeros(len(cols), np.int32), col_j[cols], col_k[cols], tcc)
+        assert k == len(op_) and np.array_equal(col_j[out_p[:k]], op_) and np.array_equal(col_k[out_p[:k]], og), trial
+        assert np.array_equal(out_i[:k], mi) and np.array_equal(out_n[:k], nu), trial
