@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""Benchmark of the Fitch/Sankoff construction pass (BASELINE.json metric: node x column updates / s).
+"""Benchmark of the Fitch/Sankoff construction pass (BASELINE.json metric: node x column updates / s at 1/2/4/8 B200).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME] [--algo fitch|sankoff] [--impl reference]
 
-A "step" is one pass of the hot path (forward + backward + ordered mutation compaction) over one batch of
-synthetic columns. N=1 runs BASELINE.json configs[1] (synthetic SARS-CoV-2-like MSA, 20k leaves x 30k columns,
-random binary tree, Fitch). For N>1 (launched by torch.distributed.run, one rank per GPU) every rank owns one such
-30k-column range of an N x 30k-column alignment on the replicated tree -- per-GPU work is fixed, scaling "weak" --
-and each step ends with the column-range gather of the per-rank mutation lists to rank 0 over NCCL.
-Prints ONE JSON line (rank 0).  --impl reference times the reference's own CPU implementation instead.
+A "step" is one pass of the hot path (forward + backward + ordered mutation compaction, and for N > 1 the column-range
+gather + merge of the per-rank lists on rank 0) over one batch of synthetic columns. The workload is BASELINE.json
+configs[3], the configuration the metric's scaling is quoted on: ONE synthetic bacterial-scale alignment, 4k leaves x 5M
+columns, whose columns are split into N contiguous ranges (strong scaling; N = 1 runs the same alignment on one GPU:
+50 GB of leaf planes + sets fit). Launched by torch.distributed.run for N > 1, one rank per GPU; every rank forms its
+part of ONE pmb_group (include/panman_b200.h): the library owns the ranges, the gather into rank 0's mailbox over
+NVLink (the packing kernel's stores into peer memory mapped through CUDA IPC), the hand-shakes (stream memory operations)
+and the merge; torch.distributed (NCCL) only all-gathers the 128-byte mailbox handles once and reduces the timings.
+Prints ONE JSON line (rank 0). At N = 1 the line also carries a `configs` table (every BASELINE.json configuration, both
+algorithms where the survey asks for both) measured the same way.  --impl reference times the reference's own CPU
+implementation instead.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -22,39 +29,39 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+METRIC = "fitch_sankoff_node_column_updates_per_sec"
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="sars20k")
+    ap.add_argument("--config", default="ecoli4k")
     ap.add_argument("--algo", default=None)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cols", type=int, default=0, help="override the column count (debug)")
     ap.add_argument("--leaves", type=int, default=0, help="override the leaf count (debug)")
     ap.add_argument("--chunk-nodes", type=int, default=0)
-    ap.add_argument("--col-groups", type=int, default=0)
-    ap.add_argument("--reserve-sms", type=int, default=8,
-                    help="N > 1: SMs the pass kernels leave free so that the NCCL gather of step i can overlap pass i+1 (0 = serialise)")
-    ap.add_argument("--e2e-contexts", type=int, default=1,
-                    help="N = 1: contexts (host threads) the end-to-end measurement streams its batches through (1 = one call at a time)")
-    ap.add_argument("--strong", action="store_true",
-                    help="N > 1: split the configuration's columns over the ranks (strong scaling) instead of one configuration per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the table of the other configurations")
+    ap.add_argument("--no-traffic", action="store_true", help="N = 1: do not measure DRAM traffic with an ncu child run")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
-def workload(args):
+def workload(args, name=None, algo=None):
     from panman_b200 import synth
 
-    cfg = dict(synth.CONFIGS[args.config])
-    if args.cols:
-        cfg["n_cols"] = args.cols
-    if args.leaves:
-        cfg["n_leaves"] = args.leaves
-    algo = args.algo or cfg["algos"][0]
+    cfg = dict(synth.CONFIGS[name or args.config])
+    if name is None:
+        if args.cols:
+            cfg["n_cols"] = args.cols
+        if args.leaves:
+            cfg["n_leaves"] = args.leaves
+    algo = algo or (args.algo if name is None else None) or cfg["algos"][0]
     return cfg, algo
 
 
@@ -95,52 +102,62 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-# ----------------------------------------------------------------------------- reference / oracle CPU timing
-def cpu_reference_run(tree, codes_sample, parent_code_sample, algo, seconds, threads):
-    """Times the reference's own CPU implementation of the path on a bounded column sample: oracle/_ref (the
-    verbatim fitchSankoff.cpp + restated string-keyed drivers) when it was built, else the oracle port."""
-    from oracle.oracle import CHAR_OF, PortOracle, RefOracle, have_ref
+# ----------------------------------------------------------------------------- reference / oracle on the host cores
+class CpuReference:
+    """The reference's own CPU implementation of the path on a column sample: oracle/_ref (the verbatim fitchSankoff.cpp +
+    restated string-keyed drivers) when it was built, else the oracle port. Used (a) as the timed CPU baseline and the
+    reference arm, (b) as the CHECKER of the GPU lists on the same columns -- never as part of the product path."""
 
-    n_cols = codes_sample.shape[1]
-    algo_i = 0 if algo == "fitch" else 1
-    names = tree.names()
-    if have_ref():
-        ref = RefOracle()
+    def __init__(self, tree):
+        from oracle.oracle import CHAR_OF, PortOracle, RefOracle, have_ref
 
-        class T:  # the fields RefOracle.tree needs
-            pass
+        self.tree, self.CHAR_OF = tree, CHAR_OF
+        self.port = PortOracle()
+        self.kind = "reference" if have_ref() else "port"
+        if self.kind == "reference":
+            self.ref = RefOracle()
 
-        t = T()
-        t.n_nodes, t.names, t.parent, t.child_off, t.child_idx = tree.n_nodes, names, tree.parent, tree.child_off, tree.child_idx
-        h = ref.tree(t)
-        leaf_names = [names[v] for v in tree.leaves]
-        rows = CHAR_OF[codes_sample]
-        cons = CHAR_OF[parent_code_sample]
+            class T:  # the fields RefOracle.tree needs
+                pass
 
-        def run(nc):
+            t = T()
+            names = tree.names()
+            t.n_nodes, t.names, t.parent, t.child_off, t.child_idx = tree.n_nodes, names, tree.parent, tree.child_off, tree.child_idx
+            self.t, self.h = t, self.ref.tree(t)
+            self.leaf_names = [names[v] for v in tree.leaves]
+
+    def timed(self, codes, parent_code, algo, n_cols, threads):
+        """Seconds for the first n_cols columns of the sample."""
+        algo_i = 0 if algo == "fitch" else 1
+        if self.kind == "reference":
+            rows = self.CHAR_OF[codes[:, :n_cols]]
+            cons = self.CHAR_OF[parent_code[:n_cols]]
+            seqs = [bytes(r) for r in rows]
             t0 = time.perf_counter()
-            ref.msa_run(h, t, algo_i, leaf_names, [bytes(r[:nc]) for r in rows], bytes(cons[:nc]), "", n_threads=threads)
+            self.ref.msa_run(self.h, self.t, algo_i, self.leaf_names, seqs, bytes(cons), "", n_threads=threads)
             return time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self.port.run(self.tree, algo_i, codes[:, :n_cols], parent_code[:n_cols], n_threads=threads)
+        return time.perf_counter() - t0
 
-        kind = "reference"
-    else:
-        port = PortOracle()
+    def sample(self, codes, parent_code, algo, seconds, threads):
+        """Grows the column sample until one run takes about `seconds` (a short probe overweights the fixed costs)."""
+        n_all = codes.shape[1]
+        nc = min(n_all, max(threads, 16))
+        dt = self.timed(codes, parent_code, algo, nc, threads)
+        while dt < 0.6 * seconds and nc < n_all:
+            nc = int(min(n_all, max(2 * nc, 0.95 * nc * seconds / max(dt, 1e-6))))
+            dt = self.timed(codes, parent_code, algo, nc, threads)
+        what = "string-keyed reference drivers (verbatim fitchSankoff.cpp)" if self.kind == "reference" else "array port"
+        return dict(value=self.tree.n_nodes * nc / dt, unit="node*col/s", cores=threads, kind=self.kind,
+                    sample=f"first {nc} columns of the workload ({self.tree.n_nodes} nodes), {dt:.1f} s, {what}, {threads} thread(s)",
+                    sample_cols=nc, sample_seconds=dt)
 
-        def run(nc):
-            t0 = time.perf_counter()
-            port.run(tree, algo_i, codes_sample[:, :nc], parent_code_sample[:nc], n_threads=threads)
-            return time.perf_counter() - t0
-
-        kind = "port"
-    # grow the sample until one run takes about `seconds` (a short probe overweights the fixed costs and undershoots)
-    nc = min(n_cols, max(threads, 16))
-    dt = run(nc)
-    while dt < 0.5 * seconds and nc < n_cols:
-        nc = int(min(n_cols, max(2 * nc, 0.9 * nc * seconds / max(dt, 1e-6))))
-        dt = run(nc)
-    return dict(value=tree.n_nodes * nc / dt, unit="node*col/s", cores=threads, kind=kind,
-                sample=f"first {nc} columns of the workload ({tree.n_nodes} nodes), {dt:.1f} s, "
-                       f"{'string-keyed reference drivers' if kind == 'reference' else 'array port'}, {threads} threads")
+    def lists(self, codes, parent_code, algo, root_override=None):
+        """The checker: per-node lists of the sample (array port; pinned to the verbatim build by tests/test_oracle.py)."""
+        want, _ = self.port.run(self.tree, 0 if algo == "fitch" else 1, codes, parent_code, root_override, None, None, 0,
+                                n_threads=host_threads())
+        return want
 
 
 def host_threads():
@@ -150,7 +167,11 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-# ----------------------------------------------------------------------------- main arms
+def sample_columns(n_leaves, n_cols):
+    return int(min(n_cols, 65536, max(512, 400_000_000 // n_leaves)))  # bounded by host memory
+
+
+# ----------------------------------------------------------------------------- reference arm
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -159,34 +180,158 @@ def run_reference_arm(args):
 
     cfg, algo = workload(args)
     tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
-    sample_cols = int(min(cfg["n_cols"], 8192, max(512, 300_000_000 // cfg["n_leaves"])))
-    codes4, pc = synth.simulate_msa(tree, 0, sample_cols, synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]))
-    codes = synth.unpack_nibbles(codes4, sample_cols).numpy()
+    n_s = sample_columns(cfg["n_leaves"], cfg["n_cols"])
+    codes4, pc = synth.simulate_msa(tree, 0, n_s, synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]))
+    codes = synth.unpack_nibbles(codes4, n_s).numpy()
+    pc = pc.numpy()
     threads = host_threads()
-    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    vals, last = [], None
+    cpu = CpuReference(tree)
+    # every step is one timed run of the reference over a column sample sized for >= 10 s
+    probe = cpu.sample(codes, pc, algo, 10.0, threads)
+    nc = probe["sample_cols"]
+    times = []
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_run(tree, codes, pc.numpy(), algo, per_step, threads)
+        dt = cpu.timed(codes, pc, algo, nc, threads)
         if i >= args.warmup:
-            vals.append(last["value"])
-    value = float(np.mean(vals))
-    last["value"] = value
+            times.append(dt)
+    step_s = float(np.mean(times))
+    value = tree.n_nodes * nc / step_s
+    base = dict(probe, value=value, sample_seconds=step_s,
+                sample=f"first {nc} columns of the workload ({tree.n_nodes} nodes), {step_s:.1f} s per step, "
+                       f"{'string-keyed reference drivers (verbatim fitchSankoff.cpp)' if cpu.kind == 'reference' else 'array port'}, {threads} thread(s)")
     line = {
-        "impl": "reference", "metric": "fitch_sankoff_node_column_updates_per_sec", "value": value, "unit": "node*col/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "node*col/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tree.n_nodes * cfg["n_cols"] / value, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u16 sets / int32 costs (CPU)", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg['n_leaves']} leaves x {cfg['n_cols']} columns, {cfg['kind']} tree, {algo}; "
-                               "each step = bounded column sample, rate extrapolated (columns are independent)"},
-        "cpu_baseline": last,
+                               f"each step = the first {nc} columns (columns are independent units: the rate is per node x column)"},
+        "extrapolated_ms_per_full_pass": 1e3 * tree.n_nodes * cfg["n_cols"] / value,
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": "node*col/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+# ----------------------------------------------------------------------------- B200 arm
+def peak_gbs():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth, burst)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def slice_lists(res, n_nodes, a, b):
+    node = np.repeat(np.arange(n_nodes), np.diff(res.node_offsets))
+    keep = (res.pos >= a) & (res.pos < b)
+    off = np.zeros(n_nodes + 1, np.int64)
+    off[1:] = np.cumsum(np.bincount(node[keep], minlength=n_nodes))
+    return off, res.pos[keep], res.type_code[keep]
+
+
+def measure_one(pb, synth, torch, name, algo, dev, local, steps, warmup):
+    """One configuration on one GPU, device-resident: ms per pass (CUDA events on the library's stream), roofline."""
+    cfg = synth.CONFIGS[name]
+    algo_i = pb.ALGO_FITCH if algo == "fitch" else pb.ALGO_SANKOFF
+    tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    C = cfg["n_cols"]
+    codes4, pc = synth.simulate_msa(tree, 0, C, synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]), device=dev)
+    ro = synth.unpack_nibbles(codes4[:1], C)[0].to(torch.int8).contiguous() if algo == "sankoff" else None
+    ctx = pb.Context(local)
+    ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro)
+    del codes4
+    lib = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    for _ in range(max(3, warmup)):
+        ctx.run_resident_async(algo_i)
+    ctx.wait()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lib)
+    for _ in range(steps):
+        ctx.run_resident_async(algo_i)
+    e1.record(lib)
+    ctx.wait()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    t = ctx.run_resident(algo_i)
+    n_mut = ctx.download(copy=False).n_mut
+    alg = ctx.algorithmic_bytes(algo_i)
+    peak, _ = peak_gbs()
+    out = {"config": name, "algo": algo, "leaves": cfg["n_leaves"], "nodes": tree.n_nodes, "cols": C, "ms": ms,
+           "value": tree.n_nodes * C / (ms * 1e-3), "algorithmic_bytes": int(alg), "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+           "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "n_mut": int(n_mut),
+           "phases_ms": {"forward": t.forward_ms, "backward": t.backward_ms, "compact": t.compact_ms}}
+    ctx.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def traffic_child(args):
+    """Run under ncu by measure_traffic(): the workload once, two passes."""
+    import torch
+
+    import panman_b200 as pb
+    from panman_b200 import synth
+
+    cfg, algo = workload(args)
+    algo_i = pb.ALGO_FITCH if algo == "fitch" else pb.ALGO_SANKOFF
+    dev = torch.device("cuda", 0)
+    tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    C = cfg["n_cols"]
+    codes4, pc = synth.simulate_msa(tree, 0, C, synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"]), device=dev)
+    ro = synth.unpack_nibbles(codes4[:1], C)[0].to(torch.int8).contiguous() if algo == "sankoff" else None
+    ctx = pb.Context(0)
+    ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro)
+    for _ in range(2):
+        ctx.run_resident(algo_i)
+    ctx.close()
+
+
+def measure_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pass kernels of ONE pass, from an ncu run of a child process on
+    the same workload (after the timed region; nothing timed runs under the profiler). None when ncu cannot profile here."""
+    import csv
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    with tempfile.TemporaryDirectory() as td:
+        log = os.path.join(td, "traffic.csv")
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv", "--log-file", log,
+               "--kernel-name", "regex:fitch_|sankoff_|compact_", sys.executable, os.path.abspath(__file__), "--traffic-child",
+               "--config", args.config] + (["--algo", args.algo] if args.algo else []) + (["--cols", str(args.cols)] if args.cols else []) \
+            + (["--leaves", str(args.leaves)] if args.leaves else [])
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=420, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]))
+        except Exception as e:  # noqa: BLE001
+            return None, f"ncu child failed: {e}"
+        if r.returncode != 0 or not os.path.exists(log):
+            return None, f"ncu child exited {r.returncode}"
+        rows = []
+        with open(log) as f:
+            lines = [ln for ln in f if not ln.startswith("==")]
+        for row in csv.DictReader(lines):
+            try:
+                v = float(row["Metric Value"].replace(",", ""))
+            except Exception:
+                continue
+            unit = row.get("Metric Unit", "byte").lower()
+            v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+            rows.append((int(row["ID"]), row["Kernel Name"], v))
+        if not rows:
+            return None, "ncu produced no metric rows (profiling counters not permitted?)"
+        per_launch = {}
+        for i, k, v in rows:
+            per_launch.setdefault(i, [k, 0.0])[1] += v
+        ids = sorted(per_launch)
+        half = ids[len(ids) // 2:]  # the second of the two passes
+        return int(sum(per_launch[i][1] for i in half)), f"ncu child run, launches {half[0]}..{half[-1]} = one pass ({len(half)} kernels)"
 
 
 def run_b200_arm(args):
@@ -194,6 +339,7 @@ def run_b200_arm(args):
 
     import panman_b200 as pb
     from panman_b200 import synth
+    from panman_b200.distributed import connect_group
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,112 +347,47 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libpanman_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "4")  # the gather moves a few MB: few channels = few SMs
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     cfg, algo = workload(args)
     algo_i = pb.ALGO_FITCH if algo == "fitch" else pb.ALGO_SANKOFF
     C = cfg["n_cols"]
-    c0 = rank * C  # weak scaling: rank r owns columns [r*C, (r+1)*C) of a world*C-column alignment
-    if args.strong and world > 1:
-        # strong scaling (BASELINE.json configs[3]: ONE alignment column-sharded over the GPUs): tile-aligned contiguous ranges
-        tiles = (cfg["n_cols"] + 1023) // 1024
-        a, b = tiles * rank // world, tiles * (rank + 1) // world
-        c0, C = a * 1024, min(cfg["n_cols"], b * 1024) - a * 1024
+    c0, c1 = pb.column_range(world, C, rank)  # strong scaling: ONE alignment, contiguous tile-aligned ranges
     tree = synth.make_tree(cfg["n_leaves"], cfg["seed"], cfg["kind"])
+    N = tree.n_nodes
     spec = synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"])
-    dev = torch.device("cuda", local)
-    codes4, pc = synth.simulate_msa(tree, c0, c0 + C, spec, device=dev)
+    codes4, pc = synth.simulate_msa(tree, c0, c1, spec, device=dev)  # this rank's range, generated on its device
     ro = None
     if algo == "sankoff":  # Sankoff runs with --reference = leaf 0
-        ro = (synth.unpack_nibbles(codes4[:1], C)[0]).to(torch.int8).contiguous()
+        ro = synth.unpack_nibbles(codes4[:1], c1 - c0)[0].to(torch.int8).contiguous()
     torch.cuda.synchronize()
 
-    ctx = pb.Context(local)
+    g = pb.Group([local], rank_base=rank, world=world)
+    ctx = g.ctx(0)
     if args.chunk_nodes:
         ctx.set_option("chunk_nodes", args.chunk_nodes)
-    if args.col_groups:
-        ctx.set_option("col_groups", args.col_groups)
-    overlap_gather = world > 1 and args.reserve_sms > 0
-    if overlap_gather:
-        ctx.set_option("reserve_sms", args.reserve_sms)
-    ctx.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
-    ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro, None, None, c0)
-
-    N = tree.n_nodes
-
-    # ---- N > 1: every step ends with the column-range gather of the per-rank lists to rank 0 and their merge there.
-    # A rank packs its result into one device buffer (pmb_pack_result) -> ONE NCCL gather -> pmb_merge_packed on rank 0.
-    # The gather/merge of step i runs on a side stream and overlaps the passes of step i+1 (double-buffered); the
-    # timed region ends only after the last merge has finished.
-    shard = None
+    g.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    g.upload_shard(0, C, tree.n_leaves, codes4, codes4.shape[1], pc, ro)
+    g.wait()
+    first = ctx.run_resident(algo_i)  # sizes the staging pool; its record count sizes the mailbox
+    n_mut_rank = int(ctx.result_device().n_mut)
     if world > 1:
-        ctx.run_resident(algo_i)
-        nmax = torch.tensor([ctx.result_device().n_mut], dtype=torch.int64, device=dev)
-        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
-        cap = int(nmax.item() * 5 // 4) + 4096  # same on every rank; identical steps => stable
-        pbytes = ctx.packed_bytes(cap)
-        shard = dict(cap=cap, bytes=pbytes, send=[torch.empty(pbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
-                     recv=[torch.empty(world * pbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if rank == 0 else None,
-                     comm=torch.cuda.Stream(device=dev), lib=torch.cuda.ExternalStream(ctx.stream_handle(), device=dev), i=0,
-                     merged=None, done=[None, None], events=[torch.cuda.Event(), torch.cuda.Event()],
-                     merge_stream=torch.cuda.Stream(device=dev), mdone=[None, None], mevents=[torch.cuda.Event(), torch.cuda.Event()])
-        # receive views built once: the step loop is host-bound at N > 1, every Python object per step counts
-        shard["dst"] = [[shard["recv"][k][r * pbytes:(r + 1) * pbytes] for r in range(world)] for k in range(2)] if rank == 0 else [None, None]
-
-    def gather_lists():
-        k = shard["i"] & 1
-        shard["i"] += 1
-        comm, lib = shard["comm"], shard["lib"]
-        if shard["done"][k] is not None:
-            lib.wait_event(shard["done"][k])                # the gather that last used this buffer pair has finished
-        ctx.pack_result(shard["send"][k], shard["cap"])     # on the library's stream, right behind the pass
-        comm.wait_stream(lib)
-        with torch.cuda.stream(comm):
-            if rank == 0 and shard["mdone"][k] is not None:
-                comm.wait_event(shard["mdone"][k])          # the merge that last read this receive buffer has finished
-            dist.gather(shard["send"][k], shard["dst"][k], dst=0)  # enqueued on comm; the host does not block
-            done = shard["events"][k]
-            done.record(comm)
-        if rank == 0:
-            # the merge runs on its own stream: the gather of step i+1 overlaps the merge of step i (at 8 ranks the two in a
-            # row on one stream took longer than a pass and throttled the whole pipeline)
-            ms = shard["merge_stream"]
-            ms.wait_event(done)
-            shard["merged"] = ctx.merge_packed(world, shard["recv"][k], shard["cap"], stream=ms.cuda_stream)
-            shard["mevents"][k].record(ms)
-            shard["mdone"][k] = shard["mevents"][k]
-        shard["done"][k] = done
-        # The persistent pass kernels fill every SM they are given, and an NCCL kernel that has to squeeze in beside them
-        # (on both ranks at once) stalls far longer than it runs. Either the pass kernels leave a few SMs free
-        # (--reserve-sms) and the gather of step i overlaps pass i+1, or the next pass waits for the collective.
-        # Rank 0's merge kernels are small and overlap the next pass in both cases.
-        if not overlap_gather:
-            lib.wait_event(done)
-
+        connect_group(g, dist, n_mut_rank + n_mut_rank // 4 + 4096, device=dev)
     lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
 
-    def step():
-        """One pass, enqueued asynchronously (pmb_run_resident_async): passes run back to back on the library's stream
-        and, for N > 1, the gather of a finished pass overlaps the next one. Nothing is skipped: pmb_wait at the end
-        checks the status of every pass."""
-        ctx.run_resident_async(algo_i)
-        if world > 1:
-            gather_lists()
-
     def barrier():
-        ctx.wait()
+        g.wait()
         if world > 1:
-            shard["comm"].synchronize()
-            shard["merge_stream"].synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
+    W = max(3, args.warmup)
+    for _ in range(W):
+        g.run_async(algo_i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -314,14 +395,27 @@ def run_b200_arm(args):
     t0 = time.perf_counter()
     ev0.record(lib_stream)
     for _ in range(args.steps):
-        step()
+        g.run_async(algo_i)  # one C call per step: pass -> pack into rank 0's mailbox -> signal (-> merge on rank 0)
     ev1.record(lib_stream)
-    barrier()
+    barrier()  # ends after the last merge on rank 0
     elapsed = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join()
-    tot = ev0.elapsed_time(ev1)  # device time of the K passes on the stream they were launched on
-    launches = ctx.timings().n_launches * args.steps
+    K = args.steps
+    dev_ms = ev0.elapsed_time(ev1) / K  # this rank's passes (+ packing) on the stream they were launched on
+    launches = ctx.timings().n_launches + (1 if world > 1 else 0) + (4 if world > 1 and rank == 0 else 0)
+    alg_bytes = ctx.algorithmic_bytes(algo_i)
+    el = torch.tensor([elapsed, dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed, dev_ms_max = float(el[0]), float(el[1])
+    value = N * C * K / elapsed
+
+    # ---- the result of the last step (outside the timed region): merged lists on rank 0, and the parity check
+    res = g.download(copy=True) if rank == 0 else None
+    parity = None
+    if rank == 0:
+        parity = parity_check(args, tree, cfg, algo, spec, res, world, synth, torch)
     # phase split of one pass: a few synchronous passes after the timed region (same kernels, same inputs)
     fwd = bwd = cmp_ = 0.0
     for _ in range(3):
@@ -329,127 +423,166 @@ def run_b200_arm(args):
         fwd += t.forward_ms / 3
         bwd += t.backward_ms / 3
         cmp_ += t.compact_ms / 3
-    n_mut = ctx.download(copy=False).n_mut
-    alg_bytes = ctx.algorithmic_bytes(algo_i)
-    el = torch.tensor([elapsed, tot / 1e3], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    elapsed, dev_total = float(el[0]), float(el[1])
-    K = args.steps
-    units = N * (cfg["n_cols"] if (args.strong and world > 1) else C * world)
-    value = units * K / elapsed
+        dist.barrier()
 
     # ---- end to end through the reference-facing C-ABI call with HOST buffers (H2D and D2H inside the timed region)
-    h_codes = torch.empty(codes4.shape, dtype=torch.uint8, pin_memory=True).copy_(codes4)
-    h_pc = torch.empty(pc.shape, dtype=torch.uint8, pin_memory=True).copy_(pc)
-    h_ro = None if ro is None else torch.empty(ro.shape, dtype=torch.int8, pin_memory=True).copy_(ro)
-    torch.cuda.synchronize()
-    e2e_steps = max(2, min(K, 6))
-    res = ctx.run_nuc(algo_i, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro, None, None, c0, 0, copy=False)
-    barrier()
-    e2e_api = "pmb_run_nuc with pinned host buffers"
-    if world == 1 and args.e2e_contexts > 1:
-        # Batches are independent, so a caller streams them through two contexts on two host threads (one context per
-        # thread is the library's threading model): the upload of one batch overlaps the pass and download of the other
-        # and the PCIe link, the bound of this path, stays busy. Every call still moves its own inputs and results.
-        ctxs = [ctx]
-        for _ in range(args.e2e_contexts - 1):
-            c2 = pb.Context(local)
-            c2.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
-            c2.run_nuc(algo_i, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro, None, None, c0, 0, copy=False)
-            ctxs.append(c2)
+    e2e = None
+    if not args.no_e2e:
+        h_codes = torch.empty(codes4.shape, dtype=torch.uint8, pin_memory=True).copy_(codes4)
+        h_pc = torch.empty(pc.shape, dtype=torch.uint8, pin_memory=True).copy_(pc)
+        h_ro = None if ro is None else torch.empty(ro.shape, dtype=torch.int8, pin_memory=True).copy_(ro)
         torch.cuda.synchronize()
-        per = max(2, e2e_steps // len(ctxs) + 1)
-        results = [None] * len(ctxs)
 
-        def worker(i):
-            torch.cuda.set_device(local)
-            for _ in range(per):
-                results[i] = ctxs[i].run_nuc(algo_i, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro, None, None, c0, 0, copy=False)
+        def e2e_step():
+            g.upload_shard(0, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro)  # host -> device, this rank's range
+            g.run_async(algo_i)
+            return g.download(copy=False)  # waits; on rank 0: merged lists device -> host
 
-        threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(ctxs))]
-        t0 = time.perf_counter()
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        torch.cuda.synchronize()
-        e2e_t = time.perf_counter() - t0
-        e2e_steps = per * len(ctxs)
-        res = results[0]
-        e2e_api = f"pmb_run_nuc with pinned host buffers, {len(ctxs)} contexts on {len(ctxs)} host threads (batches streamed)"
-        for c2 in ctxs[1:]:
-            c2.close()
-    else:
+        e2e_step()
+        barrier()
+        e2e_steps = max(2, min(K, 4))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            res = ctx.run_nuc(algo_i, C, tree.n_leaves, h_codes, h_codes.shape[1], h_pc, h_ro, None, None, c0, 0, copy=False)
-            if world > 1:
-                gather_lists()
+            r2 = e2e_step()
         barrier()
         e2e_t = time.perf_counter() - t0
-    e2 = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
-    e2e_value = units * e2e_steps / float(e2[0])
-    h2d = int(h_codes.numel() + h_pc.numel() + (0 if h_ro is None else h_ro.numel()))
-    d2h = int((N + 1) * 8 + res.n_mut * 5)
+        e2 = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+        h2d = int(h_codes.numel() + h_pc.numel() + (0 if h_ro is None else h_ro.numel()))
+        e2e = {"value": N * C * e2e_steps / float(e2[0]), "unit": "node*col/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
+               "d2h_bytes_per_step": int((N + 1) * 8 + (r2.n_mut if rank == 0 else 0) * 5), "steps": e2e_steps,
+               "ms_per_step": 1e3 * float(e2[0]) / e2e_steps,
+               "api": "pmb_group_upload_shard (pinned host buffers) + pmb_group_run_async + pmb_group_download on every rank"}
+        del h_codes, h_pc
 
     if rank != 0:
+        g.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    pass_ms = 1e3 * dev_total / K  # CUDA events around the K timed passes on the library's stream
-    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.config}:{algo}")
-    except Exception:
-        pass
+    peak, peak_src = peak_gbs()
+    achieved = alg_bytes / (dev_ms_max * 1e-3) / 1e9  # this rank's algorithmic bytes / the slowest rank's pass time
+    set_mb = (tree.n_leaves * 0.5 + (N - tree.n_leaves) * (2 if algo == "fitch" else 4)) * (c1 - c0) / 1e6
     line = {
-        "metric": "fitch_sankoff_node_column_updates_per_sec", "value": value, "unit": "node*col/s", "n_gpus": world,
-        "steps": K, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True,
-        "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": "node*col/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
         "dtype": "u16 Fitch sets as 16 bit-planes" if algo == "fitch" else "2-bit Sankoff excess as 32 bit-planes", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['n_leaves']} leaves ({N} nodes) x {C} columns per GPU, {cfg['kind']} tree, "
-                               f"{algo}, seed {cfg['seed']}; " + (f"{cfg['n_cols']} columns split over the ranks" if (args.strong and world > 1) else f"rank r owns columns [r*{C},(r+1)*{C})"),
-                   "l2": "inputs larger than L2: leaf planes + set matrix = "
-                         f"{(tree.n_leaves * 0.5 + (N - tree.n_leaves) * (2 if algo == 'fitch' else 4)) * C / 1e6:.0f} MB per pass",
-                   "parallelism": (f"column ranges x{world}, tree replicated, NCCL gather of mutation lists"
-                                   + (f" overlapping the next pass ({args.reserve_sms} SMs left free)" if overlap_gather else "")) if world > 1 else "single GPU",
-                   "n_mut_rank0": int(n_mut)},
-        "device_ms_per_step": 1e3 * dev_total / K,
-        "phases_ms": {"forward": fwd, "backward": bwd, "compact": cmp_, "note": "3 synchronous passes after the timed region"},
-        "gpu_launches": int(launches),
+        "config": {"workload": f"{args.config}: {cfg['n_leaves']} leaves ({N} nodes) x {C} columns, {cfg['kind']} tree, {algo}, seed {cfg['seed']}; "
+                               f"the columns are split into {world} contiguous 1024-aligned range(s), rank 0 owns [{c0},{c1})",
+                   "l2": f"inputs larger than L2: leaf planes + set matrix = {set_mb:.0f} MB per rank and pass",
+                   "parallelism": (f"column ranges x{world} (pmb_group), tree replicated; per-rank lists packed into rank 0's mailbox over NVLink "
+                                   "(peer stores of the packing kernel, CUDA IPC mapping), stream-memory-op hand-shake, merge on rank 0 "
+                                   "overlapping the next pass") if world > 1 else "single GPU",
+                   "n_mut": int(res.n_mut)},
+        "device_ms_per_step": dev_ms_max,
+        "phases_ms": {"forward": fwd, "backward": bwd, "compact": cmp_, "note": "rank 0, 3 synchronous passes after the timed region"},
+        "gpu_launches": int(launches * K),
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": "node*col/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": e2e_api},
+        "parity_check": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "one pass = persistent forward kernel + persistent backward kernel + compaction; "
-                               "duration = CUDA events around the timed passes on the library's stream / steps",
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "one pass on one rank = persistent forward kernel + persistent backward kernel + compaction"
+                               + (" + packing into the mailbox" if world > 1 else "")
+                               + "; duration = CUDA events around the timed passes on the library's stream / steps, max over ranks",
                      "algorithmic_bytes_per_pass": int(alg_bytes)},
     }
-    if not args.no_cpu_baseline:
-        sample_cols = int(min(C, 16384, max(512, 300_000_000 // tree.n_leaves)))  # bounded by host memory; ~cpu_seconds of work
-        codes = synth.unpack_nibbles(codes4[:, :(sample_cols + 1) // 2], sample_cols).cpu().numpy()
-        line["cpu_baseline"] = cpu_reference_run(tree, codes, pc[:sample_cols].cpu().numpy(), algo, args.cpu_seconds, host_threads())
+    if e2e:
+        line["e2e"] = e2e
+    g.close()
+    del g, codes4
+    torch.cuda.empty_cache()
+    if world == 1:
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, tree, cfg, algo, spec, synth)
+        if not args.no_configs:
+            table = []
+            for name, a in (("sars20k", "fitch"), ("indel10k", "fitch"), ("indel10k", "sankoff"), ("caterpillar100k", "fitch"),
+                            ("caterpillar100k", "sankoff")):
+                try:
+                    table.append(measure_one(pb, synth, torch, name, a, dev, local, 10, 3))
+                except Exception as e:  # noqa: BLE001
+                    table.append({"config": name, "algo": a, "error": str(e)})
+            table.append({"config": args.config, "algo": algo, "leaves": cfg["n_leaves"], "nodes": N, "cols": C, "ms": dev_ms_max,
+                          "value": N * C / (dev_ms_max * 1e-3), "algorithmic_bytes": int(alg_bytes), "achieved_gbs": achieved,
+                          "roofline_frac": achieved / peak, "n_mut": int(res.n_mut), "phases_ms": line["phases_ms"]})
+            line["configs"] = table
+        if not args.no_traffic:
+            traffic, how = measure_traffic(args)
+            if traffic is None:
+                try:
+                    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.config}:{algo}")
+                    how += "; value from profiles/traffic.json (earlier ncu capture)"
+                except Exception:
+                    pass
+            line["roofline"]["traffic"] = traffic
+            line["roofline"]["traffic_source"] = how
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def parity_check(args, tree, cfg, algo, spec, res, world, synth, torch):
+    """Outside the timed region, rank 0: the merged lists of the last timed step against the oracle on column slices --
+    one around every range boundary (shards meet there) and one in the middle -- plus the whole-result invariants."""
+    try:
+        cpu = CpuReference(tree)
+        C, N = cfg["n_cols"], tree.n_nodes
+        assert res.n_mut == int(res.node_offsets[-1]) == len(res.pos)
+        if len(res.pos):
+            assert int(res.pos.min()) >= 0 and int(res.pos.max()) < C
+            d = np.diff(res.pos.astype(np.int64))
+            starts = res.node_offsets[1:-1]
+            starts = starts[(starts > 0) & (starts < len(res.pos))]
+            d[starts - 1] = 1
+            assert bool((d > 0).all()), "positions not ascending inside a node's list"
+        width = int(max(256, min(2048, 40_000_000 // max(1, N))))
+        centres = sorted({pb_range(world, C, r)[0] for r in range(1, world)} | {C // 2})
+        checked = 0
+        for c in centres:
+            a, b = max(0, c - width // 2), min(C, c + width // 2)
+            if b <= a:
+                continue
+            s4, spc = synth.simulate_msa(tree, a, b, spec, device="cuda")
+            codes = synth.unpack_nibbles(s4, b - a).cpu().numpy()
+            ro = codes[0].astype(np.int8) if algo == "sankoff" else None
+            want = cpu.lists(codes, spc.cpu().numpy(), algo, ro)
+            off, pos, tc = slice_lists(res, N, a, b)
+            if not (np.array_equal(off, want.node_offsets) and np.array_equal(pos, want.pos + a) and np.array_equal(tc, want.type_code)):
+                return f"MISMATCH in columns [{a},{b})"
+            checked += b - a
+        return f"ok ({checked} columns in {len(centres)} slice(s) bit-exact vs the oracle incl. every range boundary; whole result sorted and consistent)"
+    except AssertionError as e:
+        return f"FAILED invariant: {e}"
+
+
+def pb_range(world, n_cols, rank):
+    import panman_b200 as pb
+
+    return pb.column_range(world, n_cols, rank)
+
+
+def cpu_baseline(args, tree, cfg, algo, spec, synth):
+    """N = 1, rank 0: the reference's CPU implementation on a bounded column sample, all host cores and -- the way the
+    reference ships its -M Fitch loop (src/panman.cpp:1381, serial) -- one thread."""
+    n_s = sample_columns(cfg["n_leaves"], cfg["n_cols"])
+    codes4, pc = synth.simulate_msa(tree, 0, n_s, spec)
+    codes = synth.unpack_nibbles(codes4, n_s).numpy()
+    cpu = CpuReference(tree)
+    out = cpu.sample(codes, pc.numpy(), algo, args.cpu_seconds, host_threads())
+    one = cpu.sample(codes, pc.numpy(), algo, max(3.0, args.cpu_seconds / 2), 1)
+    out["as_shipped_1_thread"] = {"value": one["value"], "unit": "node*col/s", "cores": 1, "sample": one["sample"]}
+    return out
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.traffic_child:
+        traffic_child(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200_arm(args)

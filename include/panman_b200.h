@@ -48,7 +48,11 @@ enum {
                                   would fail assert(minPtr != -1), src/fitchSankoff.cpp:505 */
     PMB_ERR_NO_INPUT = -5,     /* pmb_run_resident without pmb_upload_nuc */
     PMB_ERR_OOM = -6,          /* device memory */
-    PMB_ERR_INTERNAL = -7      /* scheduler watchdog fired; never expected */
+    PMB_ERR_INTERNAL = -7,     /* scheduler watchdog fired; never expected */
+    PMB_ERR_STAGING = -8,      /* an asynchronous pass emitted more records than the staging pool held: the pool has been
+                                  grown, run the pass again (a synchronous pass regrows and retries by itself) */
+    PMB_ERR_CAPACITY = -9      /* a packed column-range shard holds more records than the capacity it was packed /
+                                  merged with: reserve more and repeat the step */
 };
 
 enum { PMB_ALGO_FITCH = 0, PMB_ALGO_SANKOFF = 1 };
@@ -148,6 +152,11 @@ int pmb_run_block(pmb_ctx* ctx, int algo, int64_t n_blocks, int32_t n_rows, cons
 int pmb_upload_nuc(pmb_ctx* ctx, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit,
                    int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* parent_code,
                    const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base);
+/* The same without the final synchronisation: returns once the copies are enqueued; the input buffers must stay valid
+ * until the next pmb_wait / pmb_run_resident / pmb_download on the context (several devices can then upload at once). */
+int pmb_upload_nuc_async(pmb_ctx* ctx, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                         const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                         const int8_t* fwd_root_ref, int64_t col_base);
 int pmb_run_resident(pmb_ctx* ctx, int algo, int flags);
 /* Asynchronous form: enqueues the pass on the context's stream and returns; several passes (and the caller's own
  * stream work ordered with pmb_stream) can be in flight. pmb_wait blocks until the stream drains and reports the
@@ -193,9 +202,83 @@ int pmb_result_device(pmb_ctx* ctx, pmb_result* out);
  * (>= n_mut of every shard); `stream` = CUDA stream (cudaStream_t) to enqueue on, NULL = the context's stream. */
 void* pmb_stream(pmb_ctx* ctx); /* the cudaStream_t the context enqueues on, to order caller work after it */
 int64_t pmb_packed_bytes(int32_t n_nodes, int64_t capacity);
+/* Stream rules. pmb_pack_result on a stream other than the context's first makes that stream wait for the pass enqueued
+ * last (an event), so it may be called right behind pmb_run_resident_async. pmb_merge_packed remembers its stream:
+ * pmb_merge_runs(source = 1) and pmb_merge_status run on / wait for that stream. The destination of pmb_pack_result may be
+ * peer memory (another GPU's buffer mapped into this process): the shard is then written over NVLink by the packing
+ * kernel itself. A shard that holds more than `capacity` records is packed truncated and flagged in its header; merging
+ * skips such a shard and pmb_merge_status / pmb_merge_runs(source = 1) return PMB_ERR_CAPACITY. */
 int pmb_pack_result(pmb_ctx* ctx, void* d_packed, int64_t capacity, void* stream);
 int pmb_merge_packed(pmb_ctx* ctx, int32_t n_shards, const void* d_packed_shards, int64_t capacity, void* stream,
                      pmb_result* out_device);
+/* Blocks until the last pmb_merge_packed has finished; PMB_OK, or PMB_ERR_CAPACITY / PMB_ERR_INVALID when a shard was
+ * skipped (over capacity / packed for another tree). */
+int pmb_merge_status(pmb_ctx* ctx);
+
+/* ---- column-sharded passes over several GPUs (BASELINE.json north_star: "alignment column ranges are partitioned across
+ * the 8 GPUs of one box with the tree replicated on each; per-GPU mutation lists are merged by a column-range gather") ----
+ * The reference runs its column loop on the threads of one process (tbb::parallel_for over columns, src/panman.cpp:1568;
+ * per-node sort + merge AFTER all columns, :1445-1466 / :1625-1646). A pmb_group is the same loop over the GPUs of one
+ * box: rank r of `world` owns the r-th contiguous, 1024-column-aligned range of the alignment (pmb_group_column_range),
+ * every rank runs the whole pass on its range, packs its per-node lists straight into rank 0's mailbox over NVLink (the
+ * packing kernel's own stores into peer memory -- no copy through the host, no extra kernel), and rank 0 concatenates
+ * the shards per node in rank order (positions are already ascending: nothing is sorted). The <= 6 run-merge follows the
+ * gather, never a shard (a run may straddle a range boundary).
+ *
+ * Two ways to form a group, one implementation:
+ *   - ONE process driving several GPUs (what panmanUtils is: a single process): n_local == world, rank_base = 0.
+ *     Everything is set up by pmb_group_create.
+ *   - one process per GPU (torchrun / mpirun): n_local = 1, rank_base = the process' rank. Each process then calls
+ *     pmb_group_export, the caller all-gathers the PMB_GROUP_HANDLE_BYTES-byte handles of all ranks in rank order with
+ *     whatever transport it has (torch.distributed / MPI: the same role as ncclGetUniqueId + broadcast), and every
+ *     process calls pmb_group_connect with the `world` handles. Rank 0's mailbox is mapped into the other processes
+ *     with CUDA IPC.
+ * "shard arrived" / "mailbox slot free again" are 32-bit sequence numbers written and awaited by the streams themselves
+ * (stream memory operations): no SM is taken from the persistent pass kernels and no host thread waits in between, so
+ * the gather + merge of step i overlap the pass of step i + 1 (two mailbox slots per rank).
+ * A group is not thread-safe. All entries return PMB_OK or a negative code (text: pmb_group_last_error). */
+typedef struct pmb_group pmb_group;
+#define PMB_GROUP_HANDLE_BYTES 128
+int pmb_group_create(pmb_group** group, const int* devices, int n_local, int rank_base, int world);
+void pmb_group_destroy(pmb_group* group);
+const char* pmb_group_last_error(const pmb_group* group);
+int pmb_group_world(const pmb_group* group);
+pmb_ctx* pmb_group_ctx(pmb_group* group, int local_index); /* the context of a local rank: options, timings, stream */
+/* Column range [*col_begin, *col_end) of `rank` for an alignment of n_cols columns split over `world` ranks: contiguous,
+ * ascending with the rank, boundaries on multiples of 1024 columns; empty for the last ranks of a very short alignment. */
+int pmb_group_column_range(int world, int64_t n_cols, int rank, int64_t* col_begin, int64_t* col_end);
+int pmb_group_set_tree(pmb_group* group, int32_t n_nodes, int32_t root, const int32_t* child_offsets, const int32_t* child_index,
+                       const int32_t* leaf_row);
+/* Mailbox capacity, in records per shard (rank 0 holds 2 x world slots of pmb_packed_bytes(n_nodes, capacity)). Must be
+ * called after pmb_group_set_tree, with the same value on every rank, before export / connect; a single-process group
+ * (n_local == world) may call it again later to grow. */
+int pmb_group_reserve(pmb_group* group, int64_t shard_capacity_records);
+int pmb_group_export(pmb_group* group, void* handles_out /* n_local x PMB_GROUP_HANDLE_BYTES */);
+int pmb_group_connect(pmb_group* group, const void* all_handles /* world x PMB_GROUP_HANDLE_BYTES, rank order */);
+/* Inputs. pmb_group_upload_nuc takes the WHOLE alignment (arguments as pmb_upload_nuc, positions count from column 0):
+ * every local rank copies its own column range out of it. pmb_group_upload_shard takes one local rank's range only (the
+ * caller sliced or generated it): column col_begin of the range is the low nibble of byte 0 of every row, parent_code /
+ * root_override / fwd_root_ref start at col_begin too. Uploads of the local ranks run concurrently. */
+int pmb_group_upload_nuc(pmb_group* group, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                         const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                         const int8_t* fwd_root_ref);
+int pmb_group_upload_shard(pmb_group* group, int local_index, int64_t n_cols_total, int32_t n_rows, const uint8_t* shard_codes_4bit,
+                           int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* shard_parent_code,
+                           const int8_t* shard_root_override, const int8_t* shard_fwd_root_ref);
+/* One step, enqueued on every local rank and returning at once: pass -> pack into rank 0's mailbox -> signal; on the
+ * process holding rank 0 also: wait for all `world` signals -> merge -> release the slots. Steps may be issued back to
+ * back; pmb_group_wait drains everything and reports the first error of any local rank or of the merge. */
+int pmb_group_run_async(pmb_group* group, int algo, int flags);
+int pmb_group_wait(pmb_group* group);
+/* Results, on the process holding rank 0 (elsewhere: n_mut = 0, NULL pointers). Device view / host copy of the merged
+ * lists of the last step, and their run-merge (as pmb_merge_runs). */
+int pmb_group_result_device(pmb_group* group, pmb_result* out);
+int pmb_group_download(pmb_group* group, pmb_result* out);
+int pmb_group_merge_runs(pmb_group* group, int to_host, pmb_nucmut_result* out);
+/* Host buffers in, merged host lists out: upload + one step + wait + download (the end-to-end entry over several GPUs). */
+int pmb_group_run_nuc(pmb_group* group, int algo, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit,
+                      int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                      const int8_t* fwd_root_ref, int flags, pmb_result* out);
 
 /* ---- introspection ---- */
 int pmb_last_timings(const pmb_ctx* ctx, pmb_timings* out);

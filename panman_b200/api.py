@@ -4,7 +4,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import load_library, pmb_result, pmb_timings
+from .lib import GROUP_HANDLE_BYTES, load_library, pmb_nucmut_result, pmb_result, pmb_timings
 
 ALGO_FITCH, ALGO_SANKOFF = 0, 1
 FLAG_WANT_STATES, FLAG_BLOCK_MODE = 1, 2
@@ -25,7 +25,7 @@ class Result:
 
     @property
     def n_mut(self):
-        return int(self.node_offsets[-1])
+        return int(self.node_offsets[-1]) if len(self.node_offsets) else 0
 
 
 @dataclass
@@ -60,11 +60,37 @@ def _ptr(x):
     return x.data_ptr()  # torch tensor
 
 
+def _nucmut_arrays(r: pmb_nucmut_result):
+    n, N = int(r.n), int(r.n_nodes)
+
+    def view(addr, ctype, count, dtype):
+        if count == 0 or not addr:
+            return np.zeros(0, dtype)
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(ctype)), (count,)).astype(dtype, copy=True)
+
+    return (view(r.node_offsets, C.c_int64, N + 1, np.int64), view(r.nuc_position, C.c_int32, n, np.int32),
+            view(r.mut_info, C.c_uint8, n, np.uint8), view(r.nucs, C.c_uint32, n, np.uint32))
+
+
+def column_range(world: int, n_cols: int, rank: int):
+    """pmb_group_column_range: the contiguous, 1024-aligned column range of `rank` (needs no device)."""
+    a, b = C.c_int64(), C.c_int64()
+    rc = load_library().pmb_group_column_range(int(world), int(n_cols), int(rank), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise PanmanError(rc, "pmb_group_column_range: bad arguments")
+    return int(a.value), int(b.value)
+
+
 class Context:
     """One context per CUDA device / rank (pmb_ctx). Not thread-safe."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self.L = load_library()
+        self._keep = []
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a context owned by a Group
+            self.h = C.c_void_p(_borrowed)
+            return
         self.h = C.c_void_p()
         rc = self.L.pmb_create(C.byref(self.h), device)
         if rc != 0:
@@ -77,7 +103,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.pmb_destroy(self.h)
+            if self._owned:
+                self.L.pmb_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -166,22 +193,15 @@ class Context:
         self._check(self.L.pmb_merge_packed(self.h, int(n_shards), _ptr(d_packed), int(capacity), stream, C.byref(r)))
         return r
 
+    def merge_status(self):
+        self._check(self.L.pmb_merge_status(self.h))
+
     def merge_runs(self, source: int = 0):
         """Greedy <= 6 run-merge of the per-node lists into NucMut fields on the device (pmb_merge_runs); returns host arrays
         (node_offsets int64[N+1], nuc_position int32, mut_info uint8, nucs uint32). source 1 = the last merge_packed."""
-        from .lib import pmb_nucmut_result
-
         r = pmb_nucmut_result()
         self._check(self.L.pmb_merge_runs(self.h, int(source), 1, C.byref(r)))
-        n, N = int(r.n), int(r.n_nodes)
-
-        def view(addr, ctype, count, dtype):
-            if count == 0:
-                return np.zeros(0, dtype)
-            return np.ctypeslib.as_array(C.cast(addr, C.POINTER(ctype)), (count,)).astype(dtype, copy=True)
-
-        return (view(r.node_offsets, C.c_int64, N + 1, np.int64), view(r.nuc_position, C.c_int32, n, np.int32),
-                view(r.mut_info, C.c_uint8, n, np.uint8), view(r.nucs, C.c_uint32, n, np.uint32))
+        return _nucmut_arrays(r)
 
     def run_nuc(self, algo, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
                 leaf_present=None, col_base=0, flags=0, copy=True) -> Result:
@@ -202,3 +222,105 @@ class Context:
         lp = None if leaf_present is None else np.ascontiguousarray(leaf_present, np.uint8)
         flags = (FLAG_WANT_STATES if want_states else 0) | (FLAG_BLOCK_MODE if block_mode else 0)
         return self.run_nuc(algo, n_cols, n_rows, codes4, codes4.shape[1], pc, ro, fr, lp, col_base, flags)
+
+
+class Group:
+    """pmb_group: one column-sharded pass over several GPUs. Single process: Group([0, 1, ...]). One process per GPU
+    (torchrun): Group([local_device], rank_base=rank, world=world), then reserve(), export() -> all-gather -> connect()
+    (panman_b200.distributed.connect_group does the exchange over torch.distributed)."""
+
+    def __init__(self, devices, rank_base: int = 0, world: int = None):
+        self.L = load_library()
+        devices = [int(d) for d in devices]
+        self.n_local = len(devices)
+        self.rank_base = int(rank_base)
+        self.world = int(world) if world is not None else self.n_local
+        self.h = C.c_void_p()
+        arr = (C.c_int * self.n_local)(*devices)
+        rc = self.L.pmb_group_create(C.byref(self.h), arr, self.n_local, self.rank_base, self.world)
+        if rc != 0:
+            msg = self.L.pmb_group_last_error(self.h).decode() if self.h else "pmb_group_create: bad arguments"
+            if self.h:
+                self.L.pmb_group_destroy(self.h)
+                self.h = None
+            raise PanmanError(rc, msg)
+        self.n_nodes = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pmb_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PanmanError(rc, self.L.pmb_group_last_error(self.h).decode())
+
+    def ctx(self, local_index: int = 0) -> Context:
+        return Context(_borrowed=self.L.pmb_group_ctx(self.h, int(local_index)))
+
+    def column_range(self, n_cols: int, rank: int):
+        return column_range(self.world, n_cols, rank)
+
+    def set_tree(self, n_nodes, root, child_off, child_idx, leaf_row):
+        co = np.ascontiguousarray(child_off, np.int32)
+        ci = np.ascontiguousarray(child_idx, np.int32)
+        lr = np.ascontiguousarray(leaf_row, np.int32)
+        self.n_nodes = int(n_nodes)
+        self._check(self.L.pmb_group_set_tree(self.h, int(n_nodes), int(root), _ptr(co), _ptr(ci), _ptr(lr)))
+
+    def reserve(self, capacity: int):
+        self._check(self.L.pmb_group_reserve(self.h, int(capacity)))
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(self.n_local * GROUP_HANDLE_BYTES)
+        self._check(self.L.pmb_group_export(self.h, buf))
+        return buf.raw
+
+    def connect(self, all_handles: bytes):
+        assert len(all_handles) == self.world * GROUP_HANDLE_BYTES
+        self._check(self.L.pmb_group_connect(self.h, C.create_string_buffer(all_handles, len(all_handles))))
+
+    def upload(self, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None):
+        self._check(self.L.pmb_group_upload_nuc(self.h, int(n_cols), int(n_rows), _ptr(codes4), int(row_stride), _ptr(leaf_present),
+                                                _ptr(parent_code), _ptr(root_override), _ptr(fwd_root_ref)))
+
+    def upload_shard(self, local_index, n_cols_total, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
+                     leaf_present=None):
+        self._check(self.L.pmb_group_upload_shard(self.h, int(local_index), int(n_cols_total), int(n_rows), _ptr(codes4),
+                                                  int(row_stride), _ptr(leaf_present), _ptr(parent_code), _ptr(root_override),
+                                                  _ptr(fwd_root_ref)))
+
+    def run_async(self, algo=ALGO_FITCH, flags=0):
+        self._check(self.L.pmb_group_run_async(self.h, int(algo), int(flags)))
+
+    def wait(self):
+        self._check(self.L.pmb_group_wait(self.h))
+
+    def result_device(self) -> pmb_result:
+        r = pmb_result()
+        self._check(self.L.pmb_group_result_device(self.h, C.byref(r)))
+        return r
+
+    def download(self, copy=True) -> Result:
+        r = pmb_result()
+        self._check(self.L.pmb_group_download(self.h, C.byref(r)))
+        return Context._result(None, r, copy)
+
+    def merge_runs(self):
+        r = pmb_nucmut_result()
+        self._check(self.L.pmb_group_merge_runs(self.h, 1, C.byref(r)))
+        return _nucmut_arrays(r)
+
+    def run_nuc(self, algo, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
+                leaf_present=None, flags=0, copy=True) -> Result:
+        r = pmb_result()
+        self._check(self.L.pmb_group_run_nuc(self.h, int(algo), int(n_cols), int(n_rows), _ptr(codes4), int(row_stride),
+                                             _ptr(leaf_present), _ptr(parent_code), _ptr(root_override), _ptr(fwd_root_ref),
+                                             int(flags), C.byref(r)))
+        return Context._result(None, r, copy)

@@ -91,6 +91,11 @@ struct pmb_ctx {
     bool state_dirty = true;           // per-run device state (counters, tickets, node counts, directory) must be re-initialised
     unsigned int pack_seq = 0;
     bool async_pending = false;
+    bool upload_pending = false;       // pmb_upload_nuc_async: borrowed input buffers are still being read
+    cudaStream_t merge_stream = nullptr;  // stream of the last pmb_merge_packed (never owned)
+    cudaEvent_t ev_merge = nullptr, ev_rm = nullptr;
+    cudaStream_t rm_stream = nullptr;     // stream of the last pmb_merge_runs
+    DevBuf d_merge_err, d_mblock_sums;
     bool async_phase_events = true;
     int async_groups = 1;
 
@@ -332,6 +337,8 @@ int pmb_create(pmb_ctx** out, int device) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->gev_done[g], cudaEventDefault);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_merge, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rm, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         c->err = std::string("stream/event creation failed: ") + cudaGetErrorString(e);
         cudaGetLastError();
@@ -356,7 +363,7 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
-                          &c->d_rm_info, &c->d_rm_nucs, &c->d_col_break})
+                          &c->d_rm_info, &c->d_rm_nucs, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
                            &c->h_rm_info, &c->h_rm_nucs}) b->release();
@@ -368,6 +375,8 @@ void pmb_destroy(pmb_ctx* c) {
             if (c->gstream[g]) cudaStreamDestroy(c->gstream[g]);
         }
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->ev_merge) cudaEventDestroy(c->ev_merge);
+        if (c->ev_rm) cudaEventDestroy(c->ev_rm);
         for (int k = 0; k < 2; k++) {
             if (c->ev_slab_copied[k]) cudaEventDestroy(c->ev_slab_copied[k]);
             if (c->ev_slab_packed[k]) cudaEventDestroy(c->ev_slab_packed[k]);
@@ -430,9 +439,9 @@ int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child
     return PMB_OK;
 }
 
-int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
-                   const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
-                   const int8_t* fwd_root_ref, int64_t col_base) {
+static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                       const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                       const int8_t* fwd_root_ref, int64_t col_base, bool sync) {
     if (!c) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
@@ -524,9 +533,24 @@ int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* le
                                                              n_cols, c->T, c->d_colparams.as<uint4>());
     }
     PMB_CUDA(cudaGetLastError());
-    PMB_CUDA(cudaStreamSynchronize(c->stream));  // inputs were borrowed: they may be released on return
+    if (sync) PMB_CUDA(cudaStreamSynchronize(c->stream));  // inputs were borrowed: they may be released on return
+    c->upload_pending = !sync;
     c->have_input = true;
     return PMB_OK;
+}
+
+int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                   const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                   const int8_t* fwd_root_ref, int64_t col_base) {
+    return upload_impl(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override, fwd_root_ref,
+                       col_base, true);
+}
+
+int pmb_upload_nuc_async(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
+                         const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
+                         const int8_t* fwd_root_ref, int64_t col_base) {
+    return upload_impl(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override, fwd_root_ref,
+                       col_base, false);
 }
 
 static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
@@ -701,6 +725,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_offsets.as<long long>() + P.n_nodes, 8, cudaMemcpyDeviceToHost,
                                  c->stream));
         PMB_CUDA(cudaStreamSynchronize(c->stream));
+        c->upload_pending = false;
         unsigned long long total = *c->h_counters.as<unsigned long long>();
         unsigned int eflags = c->h_counters.as<unsigned int>()[2], ecol = c->h_counters.as<unsigned int>()[3];
         if (eflags || total > c->staging_cap) c->sticky_dirty = true;
@@ -758,8 +783,16 @@ int pmb_run_resident_async(pmb_ctx* c, int algo, int flags) { return run_impl(c,
 int pmb_wait(pmb_ctx* c) {
     if (!c) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
-    if (!c->async_pending) return PMB_OK;
+    if (!c->async_pending) {
+        if (c->upload_pending) {
+            PMB_CUDA(cudaSetDevice(c->device));
+            PMB_CUDA(cudaStreamSynchronize(c->stream));
+            c->upload_pending = false;
+        }
+        return PMB_OK;
+    }
     PMB_CUDA(cudaSetDevice(c->device));
+    c->upload_pending = false;
     const int N = c->prog.n_nodes;
     // [0,8) snapshot of the last run's staging reservation, [16,24) sticky status of all runs since the last wait
     PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -781,7 +814,7 @@ int pmb_wait(pmb_ctx* c) {
     if (sticky & 4u) {
         c->have_result = false;
         c->staging_cap = std::max<unsigned long long>(c->staging_cap * 4, *c->h_counters.as<unsigned long long>());
-        return fail(c, PMB_ERR_INTERNAL, "the mutation staging pool overflowed during an asynchronous run; rerun (the pool was grown)");
+        return fail(c, PMB_ERR_STAGING, "the mutation staging pool overflowed during an asynchronous run; rerun (the pool was grown)");
     }
     c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 32);
     PMB_CUDA(cudaEventElapsedTime(&c->timings.total_ms, c->ev[0], c->ev[3]));
@@ -897,22 +930,28 @@ int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v
     if (!c || !d_packed) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
-    if (c->n_mut >= 0 && capacity < c->n_mut) return fail(c, PMB_ERR_INVALID, "pmb_pack_result: capacity below the record count");
+    if (capacity < 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15u)) return fail(c, PMB_ERR_INVALID, "pmb_pack_result: buffer must be 16-byte aligned");
+    if (c->n_mut >= 0 && capacity < c->n_mut) return fail(c, PMB_ERR_CAPACITY, "pmb_pack_result: capacity below the record count");
     PMB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
+    if (st != c->stream) PMB_CUDA(cudaStreamWaitEvent(st, c->ev[3], 0));  // ev[3]: end of the pass enqueued last
     const long long N = c->prog.n_nodes;
     unsigned char* out = static_cast<unsigned char*>(d_packed);
-    // everything is read on the device (n_mut = offsets[N] included), so nothing here needs the host to know the result
-    // of a still running asynchronous pass
+    // everything is read on the device (n_mut = offsets[N] and the overflow status included), so nothing here needs the
+    // host to know the result of a still running asynchronous pass
     pack_result_kernel<<<c->n_sms * 2, 512, 0, st>>>(c->d_offsets.as<long long>(), c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), N,
-                                                    capacity, out);
+                                                    capacity, (long long)c->staging_cap, c->d_counters.as<unsigned long long>(), out);
     PMB_CUDA(cudaGetLastError());
+    if (st != c->stream) {  // the next pass overwrites the lists: it must wait for this copy
+        PMB_CUDA(cudaEventRecord(c->ev_fork, st));
+        PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+    }
     return PMB_OK;
 }
 
 int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, int64_t capacity, void* stream_v,
                      pmb_result* out) {
-    if (!c || !d_packed_shards || !out || n_shards < 1) return PMB_ERR_INVALID;
+    if (!c || !d_packed_shards || !out || n_shards < 1 || capacity < 0) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
     PMB_CUDA(cudaSetDevice(c->device));
@@ -920,21 +959,34 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     const int N = c->prog.n_nodes;
     const size_t shard_bytes = packed_bytes(N, capacity);
     const size_t total_cap = size_t(n_shards) * size_t(capacity);
+    // a pmb_merge_runs(source = 1) still reading the merged lists on another stream must finish first
+    if (c->rm_stream && c->rm_stream != st) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_rm, 0));
+    if (c->merge_stream && c->merge_stream != st) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_merge, 0));
+    const bool grow = size_t(N) * sizeof(unsigned int) > c->d_mcounts.cap || size_t(N + 1) * sizeof(long long) > c->d_moff.cap ||
+                      std::max<size_t>(1, total_cap) * sizeof(int32_t) > c->d_mpos.cap || std::max<size_t>(1, total_cap) > c->d_mtc.cap;
+    if (grow && c->merge_stream) PMB_CUDA(cudaStreamSynchronize(c->merge_stream));  // cudaFree of a buffer in use
     PMB_CUDA(c->d_mcounts.ensure(size_t(N) * sizeof(unsigned int)));
     PMB_CUDA(c->d_moff.ensure(size_t(N + 1) * sizeof(long long)));
     PMB_CUDA(c->d_mpos.ensure(std::max<size_t>(1, total_cap) * sizeof(int32_t)));
     PMB_CUDA(c->d_mtc.ensure(std::max<size_t>(1, total_cap)));
     const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
-    PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
+    PMB_CUDA(c->d_mblock_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
+    if (!c->d_merge_err.p) {
+        PMB_CUDA(c->d_merge_err.ensure(16));
+        PMB_CUDA(cudaMemsetAsync(c->d_merge_err.p, 0, 16, st));
+    }
     const unsigned char* packed = static_cast<const unsigned char*>(d_packed_shards);
-    merge_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(packed, shard_bytes, n_shards, N, c->d_mcounts.as<unsigned int>());
-    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>());
-    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>(),
+    merge_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity, c->d_mcounts.as<unsigned int>(),
+                                                        c->d_merge_err.as<unsigned int>());
+    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_mblock_sums.as<unsigned long long>());
+    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_mblock_sums.as<unsigned long long>(),
                                                            c->d_moff.as<long long>());
     merge_copy_kernel<<<unsigned(((long long)N * 32 + 255) / 256), 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity,
                                                                                   c->d_moff.as<long long>(), c->d_mpos.as<int32_t>(),
                                                                                   c->d_mtc.as<uint8_t>());
     PMB_CUDA(cudaGetLastError());
+    PMB_CUDA(cudaEventRecord(c->ev_merge, st));
+    c->merge_stream = st;
     out->n_mut = -1;  // on the device: node_offsets[n_nodes]; the call does not synchronise
     out->n_nodes = N;
     out->reserved = 0;
@@ -944,6 +996,21 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     out->states = nullptr;
     out->n_cols = 0;
     return PMB_OK;
+}
+
+int pmb_merge_status(pmb_ctx* c) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    if (!c->merge_stream || !c->d_merge_err.p) return PMB_OK;
+    PMB_CUDA(cudaSetDevice(c->device));
+    unsigned int flags = 0;
+    PMB_CUDA(cudaMemcpyAsync(&flags, c->d_merge_err.p, 4, cudaMemcpyDeviceToHost, c->merge_stream));
+    PMB_CUDA(cudaStreamSynchronize(c->merge_stream));
+    if (!flags) return PMB_OK;
+    PMB_CUDA(cudaMemsetAsync(c->d_merge_err.p, 0, 16, c->merge_stream));
+    if (flags & 2u) return fail(c, PMB_ERR_INVALID, "a merged shard was packed for a different tree (node count mismatch)");
+    return fail(c, PMB_ERR_CAPACITY, "a column-range shard held more records than the capacity it was packed with (or its pass "
+                                     "overflowed the staging pool): it was skipped; reserve more and repeat the step");
 }
 
 int pmb_set_column_breaks(pmb_ctx* c, const uint8_t* col_break) {
@@ -965,35 +1032,45 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
     if (source == 0 && !c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
-    if (source == 1 && !c->d_moff.p) return fail(c, PMB_ERR_NO_INPUT, "no merged shards: call pmb_merge_packed first");
+    if (source == 1 && (!c->d_moff.p || !c->merge_stream)) return fail(c, PMB_ERR_NO_INPUT, "no merged shards: call pmb_merge_packed first");
     PMB_CUDA(cudaSetDevice(c->device));
     if (source == 0 && c->async_pending) {
         int rcw = pmb_wait(c);
         if (rcw) return rcw;
     }
+    // source 0 runs on the context's stream, source 1 on the stream of the pmb_merge_packed that produced the lists; the
+    // output buffers are shared, so a call on the other stream waits for the one before it
+    cudaStream_t st = source == 0 ? c->stream : c->merge_stream;
+    if (c->rm_stream && c->rm_stream != st) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_rm, 0));
     const int N = c->prog.n_nodes;
     const long long* off = source == 0 ? c->d_offsets.as<long long>() : c->d_moff.as<long long>();
     const int32_t* pos = source == 0 ? c->d_pos.as<int32_t>() : c->d_mpos.as<int32_t>();
     const uint8_t* tc = source == 0 ? c->d_tc.as<uint8_t>() : c->d_mtc.as<uint8_t>();
     // pieces <= records; the record count of merged shards is only known on the device, their capacity on the host
     const size_t cap = std::max<size_t>(1, source == 0 ? size_t(c->n_mut) : c->d_mtc.cap);
+    const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
+    const bool grow = size_t(N) * sizeof(unsigned int) > c->d_rm_counts.cap || size_t(N + 1) * sizeof(long long) > c->d_rm_off.cap ||
+                      cap * sizeof(int32_t) > c->d_rm_pos.cap || cap > c->d_rm_info.cap || cap * sizeof(uint32_t) > c->d_rm_nucs.cap;
+    if (grow && c->rm_stream) PMB_CUDA(cudaStreamSynchronize(c->rm_stream));
     PMB_CUDA(c->d_rm_counts.ensure(size_t(N) * sizeof(unsigned int)));
     PMB_CUDA(c->d_rm_off.ensure(size_t(N + 1) * sizeof(long long)));
     PMB_CUDA(c->d_rm_pos.ensure(cap * sizeof(int32_t)));
     PMB_CUDA(c->d_rm_info.ensure(cap));
     PMB_CUDA(c->d_rm_nucs.ensure(cap * sizeof(uint32_t)));
-    const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
-    PMB_CUDA(c->d_block_sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
+    DevBuf& sums = source == 0 ? c->d_block_sums : c->d_mblock_sums;
+    PMB_CUDA(sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
     const unsigned blocks = unsigned(((long long)N * 32 + 255) / 256);
     const uint8_t* brk = (source == 0 && c->have_col_break) ? c->d_col_break.as<uint8_t>() : nullptr;
-    merge_runs_kernel<false><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr,
-                                                           brk, c->col_base);
-    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->d_rm_counts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>());
-    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->d_rm_counts.as<unsigned int>(), N, c->d_block_sums.as<unsigned long long>(),
-                                                                 c->d_rm_off.as<long long>());
-    merge_runs_kernel<true><<<blocks, 256, 0, c->stream>>>(off, pos, tc, N, nullptr, c->d_rm_off.as<long long>(), c->d_rm_pos.as<int32_t>(),
-                                                          c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(), brk, c->col_base);
+    merge_runs_kernel<false><<<blocks, 256, 0, st>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr,
+                                                    brk, c->col_base);
+    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_rm_counts.as<unsigned int>(), N, sums.as<unsigned long long>());
+    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_rm_counts.as<unsigned int>(), N, sums.as<unsigned long long>(),
+                                                          c->d_rm_off.as<long long>());
+    merge_runs_kernel<true><<<blocks, 256, 0, st>>>(off, pos, tc, N, nullptr, c->d_rm_off.as<long long>(), c->d_rm_pos.as<int32_t>(),
+                                                   c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(), brk, c->col_base);
     PMB_CUDA(cudaGetLastError());
+    PMB_CUDA(cudaEventRecord(c->ev_rm, st));
+    c->rm_stream = st;
     out->n_nodes = N;
     out->reserved = 0;
     if (!to_host) {
@@ -1004,18 +1081,22 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
         out->nucs = c->d_rm_nucs.as<uint32_t>();
         return PMB_OK;
     }
+    if (source == 1) {
+        int rcm = pmb_merge_status(c);
+        if (rcm) return rcm;
+    }
     PMB_CUDA(c->h_rm_off.ensure(size_t(N + 1) * sizeof(int64_t)));
-    PMB_CUDA(cudaMemcpyAsync(c->h_rm_off.p, c->d_rm_off.p, size_t(N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    PMB_CUDA(cudaStreamSynchronize(c->stream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_rm_off.p, c->d_rm_off.p, size_t(N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PMB_CUDA(cudaStreamSynchronize(st));
     const size_t m = size_t(c->h_rm_off.as<int64_t>()[N]);
     PMB_CUDA(c->h_rm_pos.ensure(std::max<size_t>(m, 1) * sizeof(int32_t)));
     PMB_CUDA(c->h_rm_info.ensure(std::max<size_t>(m, 1)));
     PMB_CUDA(c->h_rm_nucs.ensure(std::max<size_t>(m, 1) * sizeof(uint32_t)));
     if (m) {
-        PMB_CUDA(cudaMemcpyAsync(c->h_rm_pos.p, c->d_rm_pos.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        PMB_CUDA(cudaMemcpyAsync(c->h_rm_info.p, c->d_rm_info.p, m, cudaMemcpyDeviceToHost, c->stream));
-        PMB_CUDA(cudaMemcpyAsync(c->h_rm_nucs.p, c->d_rm_nucs.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        PMB_CUDA(cudaStreamSynchronize(c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_pos.p, c->d_rm_pos.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_info.p, c->d_rm_info.p, m, cudaMemcpyDeviceToHost, st));
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_nucs.p, c->d_rm_nucs.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PMB_CUDA(cudaStreamSynchronize(st));
     }
     out->n = int64_t(m);
     out->node_offsets = c->h_rm_off.as<int64_t>();

@@ -1598,10 +1598,17 @@ __host__ __device__ inline size_t packed_bytes(long long n_nodes, long long cap)
     return (packed_tc_offset(n_nodes, cap) + size_t(cap) + 15) / 16 * 16;
 }
 
-// one launch instead of five copies: header, offsets, and the n = offsets[n_nodes] records actually present
+// one launch instead of five copies: header, offsets, and the n = offsets[n_nodes] records actually present. `out` may be
+// peer memory (the gathering rank's mailbox mapped over NVLink): the column-range gather is then this kernel's stores.
+// A result that does not fit (`cap`), or whose offsets are not to be trusted because the pass overflowed its staging pool
+// (`src_cap` = records the source arrays hold), is flagged in the header and NO record is copied: the merge skips it.
+constexpr long long PACK_HDR_BAD = -1;
 __global__ void pack_result_kernel(const long long* offsets, const int32_t* pos, const uint8_t* type_code, long long n_nodes,
-                                   long long cap, unsigned char* out) {
-    const long long n = min(offsets[n_nodes], cap);
+                                   long long cap, long long src_cap, const unsigned long long* counters, unsigned char* out) {
+    const long long total = offsets[n_nodes];
+    // counters[4]: staging records the last pass reserved (snapshot by compact_copy_kernel); beyond src_cap nothing was copied
+    const bool ok = total >= 0 && total <= cap && total <= src_cap && counters[4] <= (unsigned long long)src_cap;
+    const long long n = ok ? total : 0;
     long long* hdr = reinterpret_cast<long long*>(out);
     long long* off_out = hdr + 2;
     int32_t* pos_out = reinterpret_cast<int32_t*>(out + packed_pos_offset(n_nodes));
@@ -1609,22 +1616,43 @@ __global__ void pack_result_kernel(const long long* offsets, const int32_t* pos,
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i0 == 0) {
-        hdr[0] = offsets[n_nodes];
+        hdr[0] = ok ? total : PACK_HDR_BAD;
         hdr[1] = n_nodes;
     }
+    if (!ok) return;
     for (long long i = i0; i <= n_nodes; i += stride) off_out[i] = offsets[i];
-    for (long long i = i0; i < n; i += stride) {
-        pos_out[i] = pos[i];
-        tc_out[i] = type_code[i];
-    }
+    // records: 16 bytes per thread and step while both arrays are aligned (they are: cudaMalloc + 16-byte sections)
+    const long long n4 = n / 4;
+    const int4* pos4 = reinterpret_cast<const int4*>(pos);
+    int4* pos_out4 = reinterpret_cast<int4*>(pos_out);
+    for (long long i = i0; i < n4; i += stride) pos_out4[i] = pos4[i];
+    const long long n16 = n / 16;
+    const uint4* tc16 = reinterpret_cast<const uint4*>(type_code);
+    uint4* tc_out16 = reinterpret_cast<uint4*>(tc_out);
+    for (long long i = i0; i < n16; i += stride) tc_out16[i] = tc16[i];
+    for (long long i = n4 * 4 + i0; i < n; i += stride) pos_out[i] = pos[i];
+    for (long long i = n16 * 16 + i0; i < n; i += stride) tc_out[i] = type_code[i];
 }
 
-__global__ void merge_count_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, unsigned int* counts) {
+// a shard is merged only if its header is sane: packed for this tree, not flagged, within the capacity
+__device__ __forceinline__ bool shard_ok(const unsigned char* shard, int n_nodes, long long cap) {
+    const long long* hdr = reinterpret_cast<const long long*>(shard);
+    return hdr[1] == n_nodes && hdr[0] >= 0 && hdr[0] <= cap;
+}
+
+// merge_err: bit 0 = a shard over capacity / flagged by its packer, bit 1 = a shard packed for another tree
+__global__ void merge_count_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, long long cap,
+                                   unsigned int* counts, unsigned int* merge_err) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
     unsigned int c = 0;
     for (int k = 0; k < n_shards; k++) {
-        const long long* off = reinterpret_cast<const long long*>(packed + k * shard_bytes + 16);
+        const unsigned char* sh = packed + k * shard_bytes;
+        if (!shard_ok(sh, n_nodes, cap)) {
+            if (v == 0) atomicOr(merge_err, reinterpret_cast<const long long*>(sh)[1] == n_nodes ? 1u : 2u);
+            continue;
+        }
+        const long long* off = reinterpret_cast<const long long*>(sh + 16);
         c += (unsigned int)(off[v + 1] - off[v]);
     }
     counts[v] = c;
@@ -1643,7 +1671,7 @@ __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_byte
     for (int k0 = 0; k0 < n_shards; k0 += 32) {
         const int k = k0 + lane;
         long long a = 0, len = 0;
-        if (k < n_shards) {
+        if (k < n_shards && shard_ok(packed + k * shard_bytes, n_nodes, cap)) {
             const long long* off = reinterpret_cast<const long long*>(packed + k * shard_bytes + 16);
             a = off[v];
             len = off[v + 1] - a;

@@ -10,7 +10,13 @@ LIB_PATH = os.environ.get("PANMAN_B200_LIB", os.path.join(HERE, "libpanman_b200.
 EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb_set_tree", "pmb_run_nuc", "pmb_upload_nuc",
            "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version",
            "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream", "pmb_run_resident_async", "pmb_wait",
-           "pmb_host_alloc", "pmb_host_free", "pmb_merge_runs", "pmb_set_column_breaks", "pmb_run_block"]
+           "pmb_host_alloc", "pmb_host_free", "pmb_merge_runs", "pmb_set_column_breaks", "pmb_run_block",
+           "pmb_upload_nuc_async", "pmb_merge_status",
+           "pmb_group_create", "pmb_group_destroy", "pmb_group_last_error", "pmb_group_world", "pmb_group_ctx",
+           "pmb_group_column_range", "pmb_group_set_tree", "pmb_group_reserve", "pmb_group_export", "pmb_group_connect",
+           "pmb_group_upload_nuc", "pmb_group_upload_shard", "pmb_group_run_async", "pmb_group_wait",
+           "pmb_group_result_device", "pmb_group_download", "pmb_group_merge_runs", "pmb_group_run_nuc"]
+GROUP_HANDLE_BYTES = 128
 
 
 class pmb_result(C.Structure):
@@ -81,5 +87,28 @@ def load_library():
     L.pmb_run_block.argtypes = [vp, C.c_int, i64, i32, vp, vp, C.POINTER(pmb_result)]
     L.pmb_pack_result.argtypes = [vp, vp, i64, vp]
     L.pmb_merge_packed.argtypes = [vp, i32, vp, i64, vp, C.POINTER(pmb_result)]
+    L.pmb_upload_nuc_async.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64]
+    L.pmb_merge_status.argtypes = [vp]
+    L.pmb_group_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]
+    L.pmb_group_destroy.argtypes = [vp]
+    L.pmb_group_destroy.restype = None
+    L.pmb_group_last_error.argtypes = [vp]
+    L.pmb_group_last_error.restype = C.c_char_p
+    L.pmb_group_world.argtypes = [vp]
+    L.pmb_group_ctx.argtypes = [vp, C.c_int]
+    L.pmb_group_ctx.restype = vp
+    L.pmb_group_column_range.argtypes = [C.c_int, i64, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+    L.pmb_group_set_tree.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.pmb_group_reserve.argtypes = [vp, i64]
+    L.pmb_group_export.argtypes = [vp, vp]
+    L.pmb_group_connect.argtypes = [vp, vp]
+    L.pmb_group_upload_nuc.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp]
+    L.pmb_group_upload_shard.argtypes = [vp, C.c_int, i64, i32, vp, i64, vp, vp, vp, vp]
+    L.pmb_group_run_async.argtypes = [vp, C.c_int, C.c_int]
+    L.pmb_group_wait.argtypes = [vp]
+    L.pmb_group_result_device.argtypes = [vp, C.POINTER(pmb_result)]
+    L.pmb_group_download.argtypes = [vp, C.POINTER(pmb_result)]
+    L.pmb_group_merge_runs.argtypes = [vp, C.c_int, C.POINTER(pmb_nucmut_result)]
+    L.pmb_group_run_nuc.argtypes = [vp, C.c_int, i64, i32, vp, i64, vp, vp, vp, vp, C.c_int, C.POINTER(pmb_result)]
     _lib = L
     return L

@@ -45,3 +45,42 @@ def load_sars20():
                             expect={a: (MutLists(z[p + f"a{a}_off"], z[p + f"a{a}_pos"], z[p + f"a{a}_tc"]), z[p + f"a{a}_states"])
                                     for a in (0, 1)}))
     return tree, batches
+
+
+def concat_shards(parts):
+    """Checker for the shard merge: parts = [(node_offsets, pos, type_code)] of contiguous column ranges in ascending order;
+    a node's merged list is the concatenation of its per-range lists in range order (nothing is sorted)."""
+    n_nodes = len(parts[0][0]) - 1
+    cnt = np.stack([np.diff(np.asarray(o, np.int64)) for o, _, _ in parts])  # ranges x N
+    off = np.zeros(n_nodes + 1, np.int64)
+    off[1:] = np.cumsum(cnt.sum(0))
+    pos = np.empty(int(off[-1]), np.int32)
+    tc = np.empty(int(off[-1]), np.uint8)
+    before = np.cumsum(cnt, 0) - cnt
+    for k, (o, p, t) in enumerate(parts):
+        if len(p) == 0:
+            continue
+        shift = off[:-1] + before[k] - np.asarray(o, np.int64)[:-1]
+        idx = np.repeat(shift, cnt[k]) + np.arange(len(p))
+        pos[idx] = p
+        tc[idx] = t
+    return off, pos, tc
+
+
+def merge_all_nodes(port, node_offsets, pos, type_code):
+    """The oracle's MSA run-merge (reference src/panman.cpp:1445-1466) applied to every node's list: returns
+    (offsets int64[N+1], nucPosition, mutInfo, nucs) in the layout of pmb_merge_runs."""
+    n_nodes = len(node_offsets) - 1
+    off = np.zeros(n_nodes + 1, np.int64)
+    ps, mis, nus = [], [], []
+    for v in range(n_nodes):
+        a, b = int(node_offsets[v]), int(node_offsets[v + 1])
+        if b > a:
+            p, mi, nu = port.merge_msa(pos[a:b], type_code[a:b])
+            ps.append(p)
+            mis.append(mi)
+            nus.append(nu)
+            off[v + 1] = len(p)
+    off = np.cumsum(off)
+    cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
+    return off, cat(ps, np.int32), cat(mis, np.uint8), cat(nus, np.uint32)

@@ -312,8 +312,6 @@ def test_async_runs_and_shard_merge(ctx, port):
     (pmb_pack_result) and merged (pmb_merge_packed): the merged lists equal the single-range result."""
     import torch
 
-    from panman_b200.distributed import column_ranges
-
     rng = np.random.default_rng(31)
     tree = random_tree(300, 55, "binary")
     n_cols = 5000
@@ -322,7 +320,7 @@ def test_async_runs_and_shard_merge(ctx, port):
     codes = np.where(rng.random(codes.shape) < 0.03, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
     pc = codes[0].copy()
     want, _ = port.run(tree, 0, codes, pc, n_threads=4)
-    ranges = column_ranges(n_cols, 2)
+    ranges = [pb.column_range(2, n_cols, k) for k in range(2)]
     shards = []
     for a, b in ranges:
         c = pb.Context(0)
@@ -435,7 +433,7 @@ def test_async_overflow_is_reported(ctx):
     c.run_resident_async(pb.ALGO_FITCH)
     with pytest.raises(pb.PanmanError) as e:
         c.wait()
-    assert e.value.code == -7 and "overflow" in str(e.value)
+    assert e.value.code == -8 and "overflow" in str(e.value)  # PMB_ERR_STAGING: its own code, not the watchdog's
     t = c.run_resident(pb.ALGO_FITCH)  # the synchronous entry sizes the pool and succeeds
     assert c.download().n_mut > 100 and t.total_ms > 0
     c.close()
