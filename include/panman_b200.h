@@ -182,6 +182,9 @@ typedef struct pmb_nucmut_result {
     const int32_t* nuc_position;
     const uint8_t* mut_info;
     const uint32_t* nucs;
+    const uint32_t* mut_info_wire; /* the same piece as the reference's capnp writer stores it (src/panman.cpp:2876):
+                                      ((nucs >> (24 - 4 * length)) << 8) + mutInfo; pieces of one node are already in the
+                                      writer's order (nucMutation order inside the single block group of an MSA build) */
 } pmb_nucmut_result;
 int pmb_merge_runs(pmb_ctx* ctx, int source, int to_host, pmb_nucmut_result* out);
 /* Optional, for the batch uploaded last (cleared by the next upload): col_break[c] != 0 means column c never continues a

@@ -37,6 +37,71 @@ def have_ref() -> bool:
     return os.path.exists(REF_SO)
 
 
+def wire_mut_info(mut_info, nucs):
+    """NucMut.mutInfo as the capnp writer stores it (reference src/panman.cpp:2876): the `length` nucleotide codes,
+    right-aligned, above the 8-bit mutInfo. Works on ints and numpy arrays."""
+    length = np.asarray(mut_info, np.uint32) >> 4
+    return ((np.asarray(nucs, np.uint32) >> (24 - 4 * length)) << 8) + np.asarray(mut_info, np.uint32)
+
+
+NUCMUT_SO = os.path.join(HERE, "_ref", "libpanman_nucmut.so")
+
+
+def have_ref_nucmut() -> bool:
+    return os.path.exists(NUCMUT_SO)
+
+
+class RefNucMut:
+    """oracle/_ref/libpanman_nucmut.so: the reference's own struct NucMut (src/panman.hpp:75-313, extracted verbatim at
+    build time) driven by restatements of the per-node merge loops (oracle/nucmut_driver.cpp). Each call takes ONE node's
+    tuples in any order and returns the fields of the NucMut objects the reference appends to Node::nucMutation."""
+    kind = "reference"
+
+    def __init__(self):
+        if not have_ref_nucmut():
+            raise FileNotFoundError(NUCMUT_SO)
+        L = C.CDLL(NUCMUT_SO)
+        L.refnm_merge_msa.restype = C.c_int64
+        L.refnm_merge_pangraph.restype = C.c_int64
+        L.refnm_wire.restype = C.c_uint32
+        self.L = L
+        assert L.refnm_sizeof() == 24  # the 24-byte struct of src/panman.hpp:75-81
+
+    @staticmethod
+    def _outs(n):
+        return (np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.uint8),
+                np.empty(n, np.uint32))
+
+    def merge_msa(self, pos, typ, code):
+        """-> (primaryBlockId, secondaryBlockId, nucPosition, nucGapPosition, mutInfo, nucs)"""
+        n = len(pos)
+        pos, typ, code = (np.ascontiguousarray(pos, np.int32), np.ascontiguousarray(typ, np.int8), np.ascontiguousarray(code, np.int8))
+        o = self._outs(max(n, 1))
+        k = self.L.refnm_merge_msa(C.c_int64(n), _p(pos, C.c_int32), _p(typ, C.c_int8), _p(code, C.c_int8), _p(o[0], C.c_int32),
+                                   _p(o[1], C.c_int32), _p(o[2], C.c_int32), _p(o[3], C.c_int32), _p(o[4], C.c_uint8), _p(o[5], C.c_uint32))
+        return tuple(x[:k].copy() for x in o)
+
+    def merge_pangraph(self, gap, block, pos, gap_pos, typ, code):
+        n = len(pos)
+        a = lambda x: np.ascontiguousarray(x, np.int32)
+        block, pos, gap_pos, typ, code = a(block), a(pos), a(gap_pos), a(typ), a(code)
+        o = self._outs(max(n, 1))
+        k = self.L.refnm_merge_pangraph(C.c_int(gap), C.c_int64(n), _p(block, C.c_int32), _p(pos, C.c_int32), _p(gap_pos, C.c_int32),
+                                        _p(typ, C.c_int32), _p(code, C.c_int32), _p(o[0], C.c_int32), _p(o[1], C.c_int32),
+                                        _p(o[2], C.c_int32), _p(o[3], C.c_int32), _p(o[4], C.c_uint8), _p(o[5], C.c_uint32))
+        return tuple(x[:k].copy() for x in o)
+
+    def wire(self, mut_info: int, nucs: int, nuc_position: int = 0):
+        """-> (mutInfo on the wire, src/panman.cpp:2876; and the (nucPosition, mutInfo, nucs, length, type, codes[6]) the
+        reader constructor src/panman.hpp:191-211 rebuilds from it)"""
+        bp, bl, bt = C.c_int32(), C.c_int32(), C.c_int32()
+        bi, bn = C.c_uint8(), C.c_uint32()
+        codes = (C.c_int32 * 6)()
+        w = self.L.refnm_wire(C.c_uint8(mut_info), C.c_uint32(nucs), C.c_int32(nuc_position), C.byref(bp), C.byref(bi), C.byref(bn),
+                              C.byref(bl), C.byref(bt), codes)
+        return int(w), (bp.value, bi.value, bn.value, bl.value, bt.value, list(codes))
+
+
 # --------------------------------------------------------------------------- trees
 
 

@@ -117,10 +117,10 @@ struct pmb_ctx {
     // work + result
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
     DevBuf d_mcounts, d_moff, d_mpos, d_mtc;  // merged shards
-    DevBuf d_rm_counts, d_rm_off, d_rm_pos, d_rm_info, d_rm_nucs;  // run-merge (pmb_merge_runs)
+    DevBuf d_rm_counts, d_rm_off, d_rm_pos, d_rm_info, d_rm_nucs, d_rm_wire;  // run-merge (pmb_merge_runs)
     DevBuf d_col_break;
     bool have_col_break = false;
-    HostBuf h_rm_off, h_rm_pos, h_rm_info, h_rm_nucs;
+    HostBuf h_rm_off, h_rm_pos, h_rm_info, h_rm_nucs, h_rm_wire;
     HostBuf h_pack_header;
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_offsets, d_pos, d_tc,
         d_states_u8;
@@ -363,10 +363,10 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
-                          &c->d_rm_info, &c->d_rm_nucs, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums})
+                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
-                           &c->h_rm_info, &c->h_rm_nucs}) b->release();
+                           &c->h_rm_info, &c->h_rm_nucs, &c->h_rm_wire}) b->release();
         for (int i = 0; i < 4; i++)
             if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         for (int g = 0; g < pmb_ctx::MAX_GROUPS; g++) {
@@ -1050,24 +1050,27 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     const size_t cap = std::max<size_t>(1, source == 0 ? size_t(c->n_mut) : c->d_mtc.cap);
     const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
     const bool grow = size_t(N) * sizeof(unsigned int) > c->d_rm_counts.cap || size_t(N + 1) * sizeof(long long) > c->d_rm_off.cap ||
-                      cap * sizeof(int32_t) > c->d_rm_pos.cap || cap > c->d_rm_info.cap || cap * sizeof(uint32_t) > c->d_rm_nucs.cap;
+                      cap * sizeof(int32_t) > c->d_rm_pos.cap || cap > c->d_rm_info.cap || cap * sizeof(uint32_t) > c->d_rm_nucs.cap ||
+                      cap * sizeof(uint32_t) > c->d_rm_wire.cap;
     if (grow && c->rm_stream) PMB_CUDA(cudaStreamSynchronize(c->rm_stream));
     PMB_CUDA(c->d_rm_counts.ensure(size_t(N) * sizeof(unsigned int)));
     PMB_CUDA(c->d_rm_off.ensure(size_t(N + 1) * sizeof(long long)));
     PMB_CUDA(c->d_rm_pos.ensure(cap * sizeof(int32_t)));
     PMB_CUDA(c->d_rm_info.ensure(cap));
     PMB_CUDA(c->d_rm_nucs.ensure(cap * sizeof(uint32_t)));
+    PMB_CUDA(c->d_rm_wire.ensure(cap * sizeof(uint32_t)));
     DevBuf& sums = source == 0 ? c->d_block_sums : c->d_mblock_sums;
     PMB_CUDA(sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
     const unsigned blocks = unsigned(((long long)N * 32 + 255) / 256);
     const uint8_t* brk = (source == 0 && c->have_col_break) ? c->d_col_break.as<uint8_t>() : nullptr;
     merge_runs_kernel<false><<<blocks, 256, 0, st>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr,
-                                                    brk, c->col_base);
+                                                    nullptr, brk, c->col_base);
     scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_rm_counts.as<unsigned int>(), N, sums.as<unsigned long long>());
     scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_rm_counts.as<unsigned int>(), N, sums.as<unsigned long long>(),
                                                           c->d_rm_off.as<long long>());
     merge_runs_kernel<true><<<blocks, 256, 0, st>>>(off, pos, tc, N, nullptr, c->d_rm_off.as<long long>(), c->d_rm_pos.as<int32_t>(),
-                                                   c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(), brk, c->col_base);
+                                                   c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(), c->d_rm_wire.as<uint32_t>(), brk,
+                                                   c->col_base);
     PMB_CUDA(cudaGetLastError());
     PMB_CUDA(cudaEventRecord(c->ev_rm, st));
     c->rm_stream = st;
@@ -1079,6 +1082,7 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
         out->nuc_position = c->d_rm_pos.as<int32_t>();
         out->mut_info = c->d_rm_info.as<uint8_t>();
         out->nucs = c->d_rm_nucs.as<uint32_t>();
+        out->mut_info_wire = c->d_rm_wire.as<uint32_t>();
         return PMB_OK;
     }
     if (source == 1) {
@@ -1092,10 +1096,12 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     PMB_CUDA(c->h_rm_pos.ensure(std::max<size_t>(m, 1) * sizeof(int32_t)));
     PMB_CUDA(c->h_rm_info.ensure(std::max<size_t>(m, 1)));
     PMB_CUDA(c->h_rm_nucs.ensure(std::max<size_t>(m, 1) * sizeof(uint32_t)));
+    PMB_CUDA(c->h_rm_wire.ensure(std::max<size_t>(m, 1) * sizeof(uint32_t)));
     if (m) {
         PMB_CUDA(cudaMemcpyAsync(c->h_rm_pos.p, c->d_rm_pos.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PMB_CUDA(cudaMemcpyAsync(c->h_rm_info.p, c->d_rm_info.p, m, cudaMemcpyDeviceToHost, st));
         PMB_CUDA(cudaMemcpyAsync(c->h_rm_nucs.p, c->d_rm_nucs.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PMB_CUDA(cudaMemcpyAsync(c->h_rm_wire.p, c->d_rm_wire.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PMB_CUDA(cudaStreamSynchronize(st));
     }
     out->n = int64_t(m);
@@ -1103,6 +1109,7 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     out->nuc_position = c->h_rm_pos.as<int32_t>();
     out->mut_info = c->h_rm_info.as<uint8_t>();
     out->nucs = c->h_rm_nucs.as<uint32_t>();
+    out->mut_info_wire = c->h_rm_wire.as<uint32_t>();
     return PMB_OK;
 }
 

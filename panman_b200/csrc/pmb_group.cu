@@ -354,7 +354,7 @@ int pmb_group_reserve(pmb_group* g, int64_t capacity) {
     }
     release_boxes(g);
     g->capacity = capacity;
-    g->shard_bytes = (size_t(pmb_packed_bytes(g->n_nodes, capacity)) + 255) / 256 * 256;
+    g->shard_bytes = size_t(pmb_packed_bytes(g->n_nodes, capacity));  // a multiple of 16; the stride pmb_merge_packed expects
     g->seq = 0;
     g->have_merged = false;
     for (int i = 0; i < g->n_local; i++) {

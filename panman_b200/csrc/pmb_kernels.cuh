@@ -1696,13 +1696,14 @@ __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_byte
 // the position is not the previous + 1 or the type changes, and every such maximal run greedily into pieces of at most
 // six; a piece becomes one NucMut {nucPosition = first position, mutInfo = (length << 4) + type, nucs = code_k <<
 // 4 (5 - k)}. A piece starts at record i iff (i - start of i's run) % 6 == 0. One warp per node, 32 records per step;
-// `carry` hands the run start across steps. FILL = false counts the pieces, true writes them at out_off[node].
+// `carry` hands the run start across steps. FILL = false counts the pieces, true writes them at out_off[node], together
+// with the wire form of mutInfo (src/panman.cpp:2876: ((nucs >> (24 - 4 length)) << 8) + mutInfo).
 // col_break (optional, indexed by position - col_base): 1 = the column never continues the run of the column before it
 // (PanGraph batches: the first gap slot of every position, src/panman.cpp:1242, 1261).
 template <bool FILL>
 __global__ void merge_runs_kernel(const long long* off, const int32_t* pos, const uint8_t* tc, int n_nodes, unsigned int* counts,
                                   const long long* out_off, int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs,
-                                  const uint8_t* col_break, long long col_base) {
+                                  uint32_t* wire, const uint8_t* col_break, long long col_base) {
     const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (node >= n_nodes) return;
     const long long a = off[node], b = off[node + 1];
@@ -1742,6 +1743,8 @@ __global__ void merge_runs_kernel(const long long* off, const int32_t* pos, cons
             nuc_position[o] = p;
             mut_info[o] = uint8_t((len << 4) + int(t));
             nucs[o] = packed;
+            // the value the reference's capnp writer stores (src/panman.cpp:2876): codes right-aligned above mutInfo
+            wire[o] = ((packed >> (24 - 4 * len)) << 8) + uint32_t((len << 4) + int(t));
         }
         written += __popc(m);
         cnt += __popc(m);

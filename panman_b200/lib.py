@@ -26,7 +26,7 @@ class pmb_result(C.Structure):
 
 class pmb_nucmut_result(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_nodes", C.c_int32), ("reserved", C.c_int32), ("node_offsets", C.c_void_p),
-                ("nuc_position", C.c_void_p), ("mut_info", C.c_void_p), ("nucs", C.c_void_p)]
+                ("nuc_position", C.c_void_p), ("mut_info", C.c_void_p), ("nucs", C.c_void_p), ("mut_info_wire", C.c_void_p)]
 
 
 class pmb_timings(C.Structure):

@@ -28,3 +28,13 @@ def ref():
     if not have_ref():
         pytest.skip("oracle/_ref not built (no /root/reference here and no prebuilt .so)")
     return RefOracle()
+
+
+@pytest.fixture(scope="session")
+def refnm():
+    from oracle.oracle import RefNucMut, build, have_ref_nucmut
+
+    build()
+    if not have_ref_nucmut():
+        pytest.skip("oracle/_ref/libpanman_nucmut.so not built (no /root/reference here and no prebuilt .so)")
+    return RefNucMut()

@@ -147,6 +147,85 @@ def test_run_merge_msa(port):
     assert len(p) == 0
 
 
+def _random_node_list(rng, n_cols=400):
+    """One node's records: stretches of consecutive positions (runs longer than 6 included), type changes inside them."""
+    pos = []
+    p = int(rng.integers(0, 5))
+    while p < n_cols:
+        length = int(rng.choice([1, 1, 2, 3, 5, 6, 7, 12, 13, 19]))
+        pos.extend(range(p, min(n_cols, p + length)))
+        p += length + int(rng.integers(1, 9))
+    pos = np.asarray(pos, np.int32)
+    typ = np.repeat(rng.integers(0, 3, size=len(pos)), 1).astype(np.uint8)
+    same = rng.random(len(pos)) < 0.8
+    for i in range(1, len(pos)):
+        if same[i]:
+            typ[i] = typ[i - 1]
+    code = rng.integers(0, 16, size=len(pos)).astype(np.uint8)
+    return pos, typ, code
+
+
+def test_run_merge_msa_vs_reference_struct(port, refnm):
+    """a13 pinned to executable reference code: the port's MSA run-merge against the reference's OWN NucMut constructor
+    (src/panman.hpp:109-151, compiled from the extracted struct) driven by the loop of src/panman.cpp:1445-1466."""
+    rng = np.random.default_rng(1313)
+    for trial in range(300):
+        pos, typ, code = _random_node_list(rng)
+        if trial % 7 == 0:
+            pos, typ, code = pos[:1], typ[:1], code[:1]
+        shuffle = rng.permutation(len(pos))  # the reference sorts; the port is handed position-sorted lists
+        pb_, sb, rp, gap, info, nucs = refnm.merge_msa(pos[shuffle], typ[shuffle], code[shuffle])
+        p, mi, nu = port.merge_msa(pos, (typ << 4) | code)
+        assert np.array_equal(p, rp) and np.array_equal(mi, info) and np.array_equal(nu, nucs), trial
+        assert (pb_ == 0).all() and (sb == -1).all() and (gap == -1).all()  # the constants pmb_merge_runs documents
+
+
+def test_run_merge_pangraph_vs_reference_struct(port, refnm):
+    """The PanGraph merges (src/panman.cpp:1236-1253 non-gap, :1255-1272 gap; 6-tuple ctor src/panman.hpp:154-189)."""
+    rng = np.random.default_rng(1414)
+    for trial in range(200):
+        blocks, poss, gaps, typs, codes = [], [], [], [], []
+        for b in sorted(rng.choice(12, size=int(rng.integers(1, 5)), replace=False)):
+            pos, typ, code = _random_node_list(rng, n_cols=120)
+            if trial % 2:  # gap list: records (pos, gapPos) with runs along gapPos
+                gp = pos % 17
+                pos = pos // 17
+            else:
+                gp = np.full(len(pos), -1, np.int32)
+            blocks.append(np.full(len(pos), b, np.int32)); poss.append(pos); gaps.append(gp); typs.append(typ); codes.append(code)
+        block, pos, gp, typ, code = (np.concatenate(x) for x in (blocks, poss, gaps, typs, codes))
+        order = np.lexsort((code, typ, gp, pos, block))  # the order std::sort gives the 6-tuples
+        block, pos, gp, typ, code = block[order], pos[order], gp[order], typ[order], code[order]
+        if trial % 2:  # (block, pos, gapPos) must be unique per node, as in a real build
+            key = np.stack([block, pos, gp], 1)
+            keep = np.ones(len(pos), bool)
+            keep[1:] = (key[1:] != key[:-1]).any(1)
+            block, pos, gp, typ, code = block[keep], pos[keep], gp[keep], typ[keep], code[keep]
+        gap = trial % 2
+        shuffle = rng.permutation(len(pos))
+        rb, rsb, rp, rg, rinfo, rnucs = refnm.merge_pangraph(gap, block[shuffle], pos[shuffle], gp[shuffle], typ[shuffle], code[shuffle])
+        ob, op, og, mi, nu = port.merge_pangraph(gap, block, pos, gp, (typ.astype(np.uint8) << 4) | code.astype(np.uint8))
+        assert np.array_equal(ob, rb) and np.array_equal(op, rp) and np.array_equal(og, rg), trial
+        assert np.array_equal(mi, rinfo) and np.array_equal(nu, rnucs) and (rsb == -1).all(), trial
+
+
+def test_wire_form_vs_reference_struct(refnm):
+    """mutInfo on the wire (writer src/panman.cpp:2876) and back through the reader constructor (src/panman.hpp:191-211):
+    the formula pmb_merge_runs' wire output uses, and the round trip it must survive."""
+    from oracle.oracle import wire_mut_info
+
+    rng = np.random.default_rng(1515)
+    for _ in range(500):
+        length = int(rng.integers(1, 7))
+        typ = int(rng.integers(0, 3))
+        codes = [int(c) for c in rng.integers(0, 16, size=length)]
+        nucs = sum(c << (4 * (5 - k)) for k, c in enumerate(codes))
+        info = (length << 4) + typ
+        w, (bp, bi, bn, bl, bt, bc) = refnm.wire(info, nucs, 77)
+        assert w == wire_mut_info(info, nucs)
+        assert (bp, bi, bn, bl, bt) == (77, info, nucs, length, typ) and bc[:length] == codes
+
+
 def test_sankoff_compact_identity(port):
     """the 2-bit excess recurrence used by the CUDA kernels reproduces the literal
     min-plus Sankoff of the port (itself pinned to the verbatim reference above)."""
