@@ -69,7 +69,8 @@ def _nucmut_arrays(r: pmb_nucmut_result):
         return np.ctypeslib.as_array(C.cast(addr, C.POINTER(ctype)), (count,)).astype(dtype, copy=True)
 
     return (view(r.node_offsets, C.c_int64, N + 1, np.int64), view(r.nuc_position, C.c_int32, n, np.int32),
-            view(r.mut_info, C.c_uint8, n, np.uint8), view(r.nucs, C.c_uint32, n, np.uint32))
+            view(r.mut_info, C.c_uint8, n, np.uint8), view(r.nucs, C.c_uint32, n, np.uint32),
+            view(r.mut_info_wire, C.c_uint32, n, np.uint32))
 
 
 def column_range(world: int, n_cols: int, rank: int):
@@ -198,7 +199,8 @@ class Context:
 
     def merge_runs(self, source: int = 0):
         """Greedy <= 6 run-merge of the per-node lists into NucMut fields on the device (pmb_merge_runs); returns host arrays
-        (node_offsets int64[N+1], nuc_position int32, mut_info uint8, nucs uint32). source 1 = the last merge_packed."""
+        (node_offsets int64[N+1], nuc_position int32, mut_info uint8, nucs uint32, mut_info_wire uint32 = the capnp writer's
+        form, src/panman.cpp:2876). source 1 = the last merge_packed."""
         r = pmb_nucmut_result()
         self._check(self.L.pmb_merge_runs(self.h, int(source), 1, C.byref(r)))
         return _nucmut_arrays(r)

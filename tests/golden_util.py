@@ -69,7 +69,9 @@ def concat_shards(parts):
 
 def merge_all_nodes(port, node_offsets, pos, type_code):
     """The oracle's MSA run-merge (reference src/panman.cpp:1445-1466) applied to every node's list: returns
-    (offsets int64[N+1], nucPosition, mutInfo, nucs) in the layout of pmb_merge_runs."""
+    (offsets int64[N+1], nucPosition, mutInfo, nucs, mutInfo on the wire) in the layout of pmb_merge_runs."""
+    from oracle.oracle import wire_mut_info
+
     n_nodes = len(node_offsets) - 1
     off = np.zeros(n_nodes + 1, np.int64)
     ps, mis, nus = [], [], []
@@ -83,4 +85,5 @@ def merge_all_nodes(port, node_offsets, pos, type_code):
             off[v + 1] = len(p)
     off = np.cumsum(off)
     cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
-    return off, cat(ps, np.int32), cat(mis, np.uint8), cat(nus, np.uint32)
+    mi, nu = cat(mis, np.uint8), cat(nus, np.uint32)
+    return off, cat(ps, np.int32), mi, nu, wire_mut_info(mi, nu).astype(np.uint32)

@@ -371,8 +371,11 @@ def _oracle_merge(port, res, n_nodes):
             p, mi, nu = port.merge_msa(res.pos[a:b], res.type_code[a:b])
             P.append(p); M.append(mi); U.append(nu)
         off.append(off[-1] + (len(P[-1]) if b > a else 0))
+    from oracle.oracle import wire_mut_info
+
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
-    return np.asarray(off, np.int64), cat(P, np.int32), cat(M, np.uint8), cat(U, np.uint32)
+    mi, nu = cat(M, np.uint8), cat(U, np.uint32)
+    return np.asarray(off, np.int64), cat(P, np.int32), mi, nu, wire_mut_info(mi, nu).astype(np.uint32)  # wire: src/panman.cpp:2876
 
 
 def test_run_merge_on_device(ctx, port):

@@ -108,7 +108,7 @@ def test_group_capacity_and_staging_errors(port):
     with pytest.raises(pb.PanmanError) as e:
         g.wait()
     assert e.value.code == -9
-    g.reserve(want.n_mut + 16)
+    g.reserve(int(want.node_offsets[-1]) + 16)
     g.run_async(0)
     g.run_async(0)
     g.wait()
