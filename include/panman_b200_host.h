@@ -35,6 +35,14 @@ typedef struct pmh_nucmut {
     uint32_t nucs;            /* code_k << (4 * (5 - k)) */
 } pmh_nucmut;
 
+/* One BlockMut as the reference holds it (src/panman.hpp:429-440; ctor :467-484). */
+typedef struct pmh_blockmut {
+    int32_t primaryBlockId;
+    int32_t secondaryBlockId; /* -1 */
+    uint8_t blockMutInfo;     /* 1 = insertion; 0 = deletion, or an inversion when `inversion` is set */
+    uint8_t inversion;        /* insertion: the block is inserted inverted; else: the present block is inverted */
+} pmh_blockmut;
+
 /* ---- Newick ---- */
 pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len); /* NULL on malformed input */
 void pmh_tree_free(pmh_tree* t);
@@ -47,6 +55,12 @@ const int32_t* pmh_tree_child_offsets(const pmh_tree* t);
 const int32_t* pmh_tree_child_index(const pmh_tree* t);
 const int32_t* pmh_tree_leaf_row(const pmh_tree* t);
 int pmh_tree_has_polytomy(const pmh_tree* t); /* reference src/panman.cpp:621-631 */
+/* Tree::transform (reference src/panman.cpp:5831-5906, called by Tree::reroot src/reroot.cpp:38): a NEW tree in which the
+ * tip `leaf_name` is the first child of a new root "node_<k+1>" and its former ancestors hang below it upside down (each
+ * receives its old parent as its last child; an old root left with one child disappears). A tip that is the root's child
+ * changes nothing. Node ids of the result are a pre-order walk; names and leaf rows travel with the nodes. NULL + err when
+ * the name is unknown or not a tip (src/reroot.cpp:5-13). */
+pmh_tree* pmh_tree_reroot(const pmh_tree* t, const char* leaf_name, char* err, size_t err_len);
 
 /* ---- MSA construction: panmanUtils -M msa.fa -N tree.nwk [--reference id] [--low-mem-mode] ----
  * fasta / newick are the file contents. low_mem_mode = 0: Fitch (reference FILE_TYPE::MSA, src/panman.cpp:1274-1466);
@@ -110,6 +124,18 @@ int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t 
  * ctor src/panman.hpp:154-189): the non-gap pieces of all blocks, then the gap pieces; primaryBlockId = block index. */
 int64_t pmh_pangraph_n_nucmut(const pmh_pangraph* g, int32_t node);
 const pmh_nucmut* pmh_pangraph_nucmut(const pmh_pangraph* g, int32_t node);
+/* Node::blockMutation after pmh_pangraph_run / pmh_pangraph_reroot: BlockMut(blockId, (type, inversion)) of
+ * src/panman.hpp:467-484 as applied at src/panman.cpp:971-980, in ascending block id. */
+int64_t pmh_pangraph_n_blockmut(const pmh_pangraph* g, int32_t node);
+const pmh_blockmut* pmh_pangraph_blockmut(const pmh_pangraph* g, int32_t node);
+/* Tree::reroot (reference src/reroot.cpp:4-261) on the loaded graph, with `leaf_name` as the new root: the tree is
+ * transformed (pmh_tree_reroot), then every block column (src/reroot.cpp:54-122) and every nucleotide column (:134-224) is
+ * inferred again by Fitch with the root forced to the new root's own state (root override on EVERY column), every leaf
+ * taking part with the characters the built PanMAT yields for it (getSequenceFromReference, src/reroot.cpp:19-35: the
+ * mutations of the last pmh_pangraph_run replayed from the root over the consensus -- call that first), and the lists are
+ * run-merged (:226-261).
+ * Afterwards pmh_pangraph_tree / _nucmut / _blockmut / _result describe the re-rooted tree (new node ids). */
+int pmh_pangraph_reroot(pmb_ctx* ctx, pmh_pangraph* g, const char* leaf_name, char* err, size_t err_len);
 /* lists of one batch after pmh_pangraph_run; block = -1: the block-level pass. Returns the record count. */
 int64_t pmh_pangraph_result(const pmh_pangraph* g, int32_t block, const int64_t** node_offsets, const int32_t** pos,
                             const uint8_t** type_code);

@@ -502,8 +502,10 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
             const int32_t nr = std::min(slab_rows, n_rows - r0);
             uint8_t* buf = c->d_tmp_codes.as<uint8_t>() + size_t(k) * slab_bytes;
             if (slab >= 2) PMB_CUDA(cudaStreamWaitEvent(copy, c->ev_slab_packed[k], 0));
-            PMB_CUDA(cudaMemcpyAsync(buf, leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes), size_t(nr) * size_t(row_stride_bytes),
-                                     cudaMemcpyHostToDevice, copy));
+            // the last row is only (n_cols + 1) / 2 bytes long for sure: a caller's column range may start inside a wider
+            // matrix (pmb_group_upload_nuc), and the bytes behind the last row's range then lie outside its buffer
+            PMB_CUDA(cudaMemcpyAsync(buf, leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes),
+                                     size_t(nr - 1) * size_t(row_stride_bytes) + size_t((n_cols + 1) / 2), cudaMemcpyHostToDevice, copy));
             PMB_CUDA(cudaEventRecord(c->ev_slab_copied[k], copy));
             PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_slab_copied[k], 0));
             pack(buf, r0, nr);

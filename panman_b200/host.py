@@ -14,6 +14,10 @@ class pmh_nucmut(C.Structure):
                 ("secondaryBlockId", C.c_int32), ("mutInfo", C.c_uint8), ("nucs", C.c_uint32)]
 
 
+class pmh_blockmut(C.Structure):
+    _fields_ = [("primaryBlockId", C.c_int32), ("secondaryBlockId", C.c_int32), ("blockMutInfo", C.c_uint8), ("inversion", C.c_uint8)]
+
+
 _hlib = None
 
 
@@ -37,6 +41,8 @@ def load_host_library():
     for f in ("pmh_tree_parent", "pmh_tree_child_offsets", "pmh_tree_child_index", "pmh_tree_leaf_row"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.POINTER(C.c_int32)
+    L.pmh_tree_reroot.restype = vp
+    L.pmh_tree_reroot.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
     L.pmh_build_from_msa.restype = vp
     L.pmh_build_from_msa.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
     L.pmh_build_free.argtypes = [vp]
@@ -84,13 +90,27 @@ class HostTree:
             self.h = None
 
 
-def parse_newick(newick: str) -> HostTree:
+def parse_newick(newick: str, keep: bool = False) -> HostTree:
     L = load_host_library()
     err = C.create_string_buffer(256)
     h = L.pmh_tree_from_newick(newick.encode(), err, 256)
     if not h:
         raise ValueError(err.value.decode())
-    return HostTree(h)
+    return HostTree(h, owned=not keep)
+
+
+def reroot_newick(newick: str, leaf_name: str) -> HostTree:
+    """pmh_tree_reroot (reference Tree::transform, src/panman.cpp:5831-5906) on the tree of `newick`."""
+    L = load_host_library()
+    err = C.create_string_buffer(256)
+    h = L.pmh_tree_from_newick(newick.encode(), err, 256)
+    if not h:
+        raise ValueError(err.value.decode())
+    h2 = L.pmh_tree_reroot(h, leaf_name.encode(), err, 256)
+    L.pmh_tree_free(h)
+    if not h2:
+        raise ValueError(err.value.decode())
+    return HostTree(h2)
 
 
 class MsaBuild:
@@ -239,6 +259,42 @@ class PanGraphBuild:
             pos = np.ctypeslib.as_array(pp, (max(n, 1),))[:n].copy()
             tc = np.ctypeslib.as_array(pt, (max(n, 1),))[:n].copy()
             out.append((off, pos, tc))
+        return out
+
+    def _results(self):
+        N = self.tree.n_nodes
+        out = []
+        for b in range(-1, self.n_blocks):
+            po, pp, pt = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)()
+            n = int(self.L.pmh_pangraph_result(self.h, b, C.byref(po), C.byref(pp), C.byref(pt)))
+            off = np.ctypeslib.as_array(po, (N + 1,)).copy()
+            pos = np.ctypeslib.as_array(pp, (max(n, 1),))[:n].copy()
+            tc = np.ctypeslib.as_array(pt, (max(n, 1),))[:n].copy()
+            out.append((off, pos, tc))
+        return out
+
+    def reroot(self, ctx, leaf_name: str):
+        """Tree::reroot (reference src/reroot.cpp) on the built graph; self.tree becomes the re-rooted tree. Returns the lists
+        of the block-level pass followed by every block, as run() does."""
+        self.L.pmh_pangraph_reroot.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        err = C.create_string_buffer(512)
+        rc = self.L.pmh_pangraph_reroot(ctx.h, self.h, leaf_name.encode(), err, 512)
+        if rc:
+            raise RuntimeError(err.value.decode())
+        self.tree = HostTree(self.L.pmh_pangraph_tree(self.h), owned=False)
+        return self._results()
+
+    def blockmut(self):
+        """Node::blockMutation per node: lists of (primaryBlockId, secondaryBlockId, blockMutInfo, inversion)."""
+        self.L.pmh_pangraph_n_blockmut.argtypes = [C.c_void_p, C.c_int32]
+        self.L.pmh_pangraph_n_blockmut.restype = C.c_int64
+        self.L.pmh_pangraph_blockmut.argtypes = [C.c_void_p, C.c_int32]
+        self.L.pmh_pangraph_blockmut.restype = C.POINTER(pmh_blockmut)
+        out = []
+        for v in range(self.tree.n_nodes):
+            k = self.L.pmh_pangraph_n_blockmut(self.h, v)
+            arr = self.L.pmh_pangraph_blockmut(self.h, v)
+            out.append([(arr[i].primaryBlockId, arr[i].secondaryBlockId, int(arr[i].blockMutInfo), int(arr[i].inversion)) for i in range(k)])
         return out
 
     def nucmut(self):

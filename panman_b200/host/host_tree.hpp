@@ -21,6 +21,10 @@ void split_quote_aware(const std::string& s, char delim, std::vector<std::string
 // reference src/panman.cpp:310-450 (createTreeFromNewickString). Returns "" or an error message.
 std::string parse_newick(const std::string& newick, HostTree* out);
 
+// reference Tree::transform (src/panman.cpp:5831-5906): `tip` becomes the first child of a new root. Defined in reroot.cpp.
+std::string reroot_tree(const HostTree& in, int32_t tip, HostTree* out);
+int32_t find_node(const HostTree& t, const std::string& name);
+
 }  // namespace pmh
 
 // the opaque handle of include/panman_b200_host.h

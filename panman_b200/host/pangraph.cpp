@@ -178,7 +178,8 @@ struct pmh_pangraph {
     std::vector<int8_t> block_override; // n_blocks or empty
     BlockBatch block_level;             // results of the block-level pass
     bool has_reference = false;
-    std::vector<std::vector<pmh_nucmut>> nuc;  // Node::nucMutation after the run, in the reference's order
+    std::vector<std::vector<pmh_nucmut>> nuc;      // Node::nucMutation after the run, in the reference's order
+    std::vector<std::vector<pmh_blockmut>> blockmut;  // Node::blockMutation after the run, ascending block id
 };
 
 namespace {
@@ -369,8 +370,16 @@ const int8_t* pmh_pangraph_root_override(const pmh_pangraph* g, int32_t b) { ret
 const int32_t* pmh_pangraph_col_pos(const pmh_pangraph* g, int32_t b) { return g->blocks[b].col_pos.data(); }
 const int32_t* pmh_pangraph_col_gap(const pmh_pangraph* g, int32_t b) { return g->blocks[b].col_gap.data(); }
 
-int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t err_len) {
-    if (!ctx || !g || (algo != PMB_ALGO_FITCH && algo != PMB_ALGO_SANKOFF)) { set_err(err, err_len, "bad argument"); return PMB_ERR_INVALID; }
+// One input of the shared runner: the column batch of a block as the passes see it.
+struct BatchInput {
+    const uint8_t* codes4;
+    const uint8_t* present;        // NULL: every leaf takes part
+    const int8_t* root_override;   // NULL: none
+};
+
+// Block-level pass, one nucleotide pass + device run-merge per block, then Node::blockMutation / Node::nucMutation.
+static int run_batches(pmb_ctx* ctx, pmh_pangraph* g, int algo, const std::vector<BatchInput>& in, const uint8_t* block_states,
+                       const int8_t* block_override, char* err, size_t err_len) {
     const pmh::HostTree& T = g->tree.t;
     int rc = pmb_set_tree(ctx, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data());
     if (rc) { set_err(err, err_len, std::string("pmb_set_tree: ") + pmb_last_error(ctx)); return rc; }
@@ -381,16 +390,29 @@ int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t 
         B.tc.assign(res.type_code, res.type_code + res.n_mut);
     };
     pmb_result res;
-    {   // block-level pass (src/panman.cpp:873-963): one 3-state column per block, parent state "absent"
-        rc = pmb_run_block(ctx, algo, NB, L, g->block_states.data(), g->block_override.empty() ? nullptr : g->block_override.data(), &res);
+    {   // block-level pass (src/panman.cpp:873-963, src/reroot.cpp:54-122): one 3-state column per block, parent state "absent"
+        rc = pmb_run_block(ctx, algo, NB, L, block_states, block_override, &res);
         if (rc) { set_err(err, err_len, std::string("block pass: ") + pmb_last_error(ctx)); return rc; }
         keep(g->block_level, res);
     }
-    for (BlockBatch& B : g->blocks) {
-        // the Sankoff branch guards every override with reference.length(); the Fitch main-column branch does not
-        const bool use_override = B.any_override && (algo == PMB_ALGO_FITCH || g->has_reference);
-        rc = pmb_run_nuc(ctx, algo, B.n_cols, L, B.codes4.data(), B.stride, B.present.data(), B.parent_code.data(),
-                         use_override ? B.root_override_fitch.data() : nullptr, nullptr, 0, 0, &res);
+    // Node::blockMutation: BlockMut(blockId, (type, inversion)) of src/panman.hpp:467-484, applied at src/panman.cpp:971-980
+    // (there in the iteration order of an unordered map; here ascending block id). Records arrive nuc-style: type 2 = block
+    // insertion (code 2 = inserted inverted), type 1 = deletion, type 0 = inversion of a present block = (BD, true).
+    g->blockmut.assign(T.n_nodes(), {});
+    for (int32_t v = 0; v < T.n_nodes(); v++)
+        for (int64_t k = g->block_level.off[v]; k < g->block_level.off[v + 1]; k++) {
+            const uint8_t type = g->block_level.tc[k] >> 4, code = g->block_level.tc[k] & 15;
+            pmh_blockmut m;
+            m.primaryBlockId = g->block_level.pos[k];
+            m.secondaryBlockId = -1;
+            m.blockMutInfo = type == 2;
+            m.inversion = type == 2 ? code == 2 : type == 0;
+            g->blockmut[v].push_back(m);
+        }
+    for (int32_t i = 0; i < NB; i++) {
+        BlockBatch& B = g->blocks[i];
+        rc = pmb_run_nuc(ctx, algo, B.n_cols, L, in[i].codes4, B.stride, in[i].present, B.parent_code.data(), in[i].root_override,
+                         nullptr, 0, 0, &res);
         if (rc) { set_err(err, err_len, "block " + B.id + ": " + pmb_last_error(ctx)); return rc; }
         keep(B, res);
         // greedy <= 6 run-merge on the device (src/panman.cpp:1236-1272): main positions merge on pos + 1, gap slots on equal
@@ -428,6 +450,103 @@ int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t 
         }
     return PMB_OK;
 }
+
+int pmh_pangraph_run(pmb_ctx* ctx, pmh_pangraph* g, int algo, char* err, size_t err_len) {
+    if (!ctx || !g || (algo != PMB_ALGO_FITCH && algo != PMB_ALGO_SANKOFF)) { set_err(err, err_len, "bad argument"); return PMB_ERR_INVALID; }
+    try {
+        std::vector<BatchInput> in;
+        for (BlockBatch& B : g->blocks) {
+            // the Sankoff branch guards every override with reference.length(); the Fitch main-column branch does not
+            const bool use_override = B.any_override && (algo == PMB_ALGO_FITCH || g->has_reference);
+            in.push_back({B.codes4.data(), B.present.data(), use_override ? B.root_override_fitch.data() : nullptr});
+        }
+        return run_batches(ctx, g, algo, in, g->block_states.data(), g->block_override.empty() ? nullptr : g->block_override.data(), err,
+                           err_len);
+    } catch (const std::bad_alloc&) {
+        set_err(err, err_len, "out of host memory");
+        return PMB_ERR_OOM;
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("pmh_pangraph_run: ") + ex.what());
+        return PMB_ERR_INVALID;
+    }
+}
+
+// Tree::reroot (reference src/reroot.cpp:4-261) on the loaded graph: the tree is transformed (pmh::reroot_tree), then EVERY
+// block column and nucleotide column is inferred again by Fitch with the root forced to the new root's own state. Unlike
+// the -P build, every leaf takes part in every column, with the characters the built PanMAT yields for it (the mutations of
+// the last pmh_pangraph_run replayed root -> tip over the consensus), and the state "absent" at block level where it lacks
+// the block. Afterwards pmh_pangraph_tree / _nucmut / _blockmut / _result describe the new tree.
+int pmh_pangraph_reroot(pmb_ctx* ctx, pmh_pangraph* g, const char* leaf_name, char* err, size_t err_len) {
+    if (!ctx || !g || !leaf_name) { set_err(err, err_len, "bad argument"); return PMB_ERR_INVALID; }
+    try {
+        const int32_t tip = pmh::find_node(g->tree.t, leaf_name);
+        if (tip < 0) { set_err(err, err_len, std::string("Sequence with name ") + leaf_name + " not found!"); return PMB_ERR_INVALID; }
+        pmh::HostTree nt;
+        std::string e = pmh::reroot_tree(g->tree.t, tip, &nt);
+        if (!e.empty()) { set_err(err, err_len, e); return PMB_ERR_INVALID; }
+        const int32_t row = g->tree.t.leaf_row[tip];
+        const pmh::HostTree& OT = g->tree.t;  // the tree the PanMAT was built on
+        const int32_t NB = int32_t(g->blocks.size()), L = OT.n_leaves;
+        for (const BlockBatch& B : g->blocks)
+            if (int32_t(B.off.size()) != OT.n_nodes() + 1) { set_err(err, err_len, "reroot works on a built PanMAT: call pmh_pangraph_run first"); return PMB_ERR_NO_INPUT; }
+        std::vector<std::vector<uint8_t>> codes(NB);
+        std::vector<std::vector<int8_t>> over(NB);
+        std::vector<int8_t> block_over(size_t(NB), 0);
+        std::vector<BatchInput> in;
+        for (int32_t i = 0; i < NB; i++) {
+            const BlockBatch& B = g->blocks[i];
+            // The sequences reroot works on are those the PanMAT yields (getSequenceFromReference, src/reroot.cpp:19-35): the
+            // block consensus with the mutations on the path root -> tip applied in order. For a sequence that owns the block
+            // that is its aligned string again; one that lacks it shows its nearest defined ancestor's characters.
+            codes[i].assign(size_t(L) * size_t(B.stride), 0);
+            std::vector<uint8_t> cur(B.parent_code.begin(), B.parent_code.end());
+            struct Undo { int32_t col; uint8_t old; };
+            std::vector<Undo> undo;
+            struct Frame { int32_t node; int32_t next_child; size_t undo_mark; };
+            std::vector<Frame> stack;
+            auto enter = [&](int32_t v) {
+                stack.push_back({v, OT.child_off[v], undo.size()});
+                for (int64_t k = B.off[v]; k < B.off[v + 1]; k++) {
+                    undo.push_back({B.pos[k], cur[B.pos[k]]});
+                    cur[B.pos[k]] = B.tc[k] & 15;  // a deletion carries '-' = 0
+                }
+                if (OT.leaf_row[v] >= 0) {
+                    uint8_t* d = codes[i].data() + size_t(OT.leaf_row[v]) * size_t(B.stride);
+                    for (int64_t c = 0; c < B.n_cols; c++) d[c >> 1] |= uint8_t(cur[c] << (4 * (c & 1)));
+                }
+            };
+            enter(OT.root);
+            while (!stack.empty()) {
+                Frame& f = stack.back();
+                if (f.next_child < OT.child_off[f.node + 1]) {
+                    enter(OT.child_idx[f.next_child++]);
+                } else {
+                    while (undo.size() > f.undo_mark) {
+                        cur[undo.back().col] = undo.back().old;
+                        undo.pop_back();
+                    }
+                    stack.pop_back();
+                }
+            }
+            over[i].resize(size_t(B.n_cols));
+            const uint8_t* nr = codes[i].data() + size_t(row) * size_t(B.stride);
+            for (int64_t c = 0; c < B.n_cols; c++) over[i][c] = int8_t((nr[c >> 1] >> (4 * (c & 1))) & 15);
+            block_over[i] = int8_t(g->block_states[size_t(row) * NB + i]);
+            in.push_back({codes[i].data(), nullptr, over[i].data()});
+        }
+        g->tree.t = std::move(nt);
+        return run_batches(ctx, g, PMB_ALGO_FITCH, in, g->block_states.data(), block_over.data(), err, err_len);
+    } catch (const std::bad_alloc&) {
+        set_err(err, err_len, "out of host memory");
+        return PMB_ERR_OOM;
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("pmh_pangraph_reroot: ") + ex.what());
+        return PMB_ERR_INVALID;
+    }
+}
+
+int64_t pmh_pangraph_n_blockmut(const pmh_pangraph* g, int32_t node) { return node < int32_t(g->blockmut.size()) ? int64_t(g->blockmut[node].size()) : 0; }
+const pmh_blockmut* pmh_pangraph_blockmut(const pmh_pangraph* g, int32_t node) { return g->blockmut[node].data(); }
 
 int64_t pmh_pangraph_n_nucmut(const pmh_pangraph* g, int32_t node) { return int64_t(g->nuc[node].size()); }
 const pmh_nucmut* pmh_pangraph_nucmut(const pmh_pangraph* g, int32_t node) { return g->nuc[node].data(); }
