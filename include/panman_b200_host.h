@@ -98,9 +98,12 @@ const double* pmh_build_seconds(const pmh_build* b);
  * pmh_pangraph_load parses the PanGraph JSON (reference src/panman.cpp:6200-6258) and builds, per block, the column batch
  * the nucleotide passes run on: one column per consensus position 0..len ("main", the last one '-') and one per gap slot
  * (pos, k); a sequence contributes its aligned character (consensus + substitutions / insertions / deletions,
- * src/panman.cpp:1006-1045), sequences whose path lacks the block are omitted (leaf_present). Block order = JSON order;
- * duplicated blocks and circular paths are rejected; the root override follows the rules stated in
- * panman_b200/host/pangraph.cpp. pmh_pangraph_run runs the block-level pass (3 states, PMB_FLAG_BLOCK_MODE,
+ * src/panman.cpp:1006-1045), sequences whose path lacks the block are omitted (leaf_present). Block columns ("blocks" below)
+ * follow the reference's own ordering: the consensus order chain_align builds over the paths (src/chaining.cpp:153-310,
+ * driven by src/panman.cpp:6347-6425), one column per occurrence of a duplicated block with the mutations recorded for
+ * that occurrence ("number"), circular paths rotated against the first path (src/rotation.cpp:14-110); a path entry that
+ * the two-pointer alignment to that order cannot place is dropped as in the reference (src/panman.cpp:6427-6465). The
+ * root override follows the rules stated in panman_b200/host/pangraph.cpp. pmh_pangraph_run runs the block-level pass (3 states, PMB_FLAG_BLOCK_MODE,
  * src/panman.cpp:873-963) and one pmb_run_nuc per block (src/panman.cpp:1048-1232); algo = PMB_ALGO_FITCH for a bifurcating
  * tree, PMB_ALGO_SANKOFF for the reference's polytomy branch. Results are the per-node (position-sorted) lists of every
  * batch; column c of block b is (pmh_pangraph_col_pos[c], pmh_pangraph_col_gap[c]), gap = -1 for main columns. */
@@ -112,6 +115,9 @@ const pmh_tree* pmh_pangraph_tree(const pmh_pangraph* g);
 int32_t pmh_pangraph_n_blocks(const pmh_pangraph* g);
 const char* pmh_pangraph_block_id(const pmh_pangraph* g, int32_t block);
 const uint8_t* pmh_pangraph_block_states(const pmh_pangraph* g); /* n_leaves x n_blocks: 0 absent, 1 forward, 2 reverse */
+/* n_leaves: by how many blocks a circular path was rotated to line up with the first path (what the reference keeps as
+ * Tree::rotationIndexes, src/panman.cpp:835-837, src/rotation.cpp:96); 0 for linear paths */
+const int32_t* pmh_pangraph_rotation_index(const pmh_pangraph* g);
 int64_t pmh_pangraph_n_cols(const pmh_pangraph* g, int32_t block);
 const uint8_t* pmh_pangraph_codes4(const pmh_pangraph* g, int32_t block, int64_t* row_stride);
 const uint8_t* pmh_pangraph_present(const pmh_pangraph* g, int32_t block);

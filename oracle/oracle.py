@@ -37,6 +37,69 @@ def have_ref() -> bool:
     return os.path.exists(REF_SO)
 
 
+PGORDER_SO = os.path.join(HERE, "_ref", "libpanman_pgorder.so")
+
+
+def have_ref_pgorder() -> bool:
+    return os.path.exists(PGORDER_SO)
+
+
+class RefPgOrder:
+    """oracle/_ref/libpanman_pgorder.so: the reference's src/chaining.cpp + src/rotation.cpp compiled verbatim, driven by a
+    restatement of the block-ordering half of Pangraph::Pangraph (oracle/pangraph_ref_driver.cpp). order(pg) takes the parsed
+    PanGraph JSON and returns the block columns (consensus order of chain_align; duplicated blocks repeat) and, per path, which
+    columns it owns, on which strand, and as which occurrence ("number")."""
+    kind = "reference"
+
+    def __init__(self):
+        if not have_ref_pgorder():
+            raise FileNotFoundError(PGORDER_SO)
+        L = C.CDLL(PGORDER_SO)
+        L.refpg_order.restype = C.c_void_p
+        L.refpg_n_topo.restype = C.c_int64
+        L.refpg_n_topo.argtypes = [C.c_void_p]
+        L.refpg_topo_id.restype = C.c_char_p
+        L.refpg_topo_id.argtypes = [C.c_void_p, C.c_int64]
+        L.refpg_visit.restype = C.c_char_p
+        L.refpg_visit.argtypes = [C.c_void_p, C.c_int]
+        L.refpg_rotation_index.argtypes = [C.c_void_p, C.c_char_p]
+        L.refpg_aligned.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refpg_free.argtypes = [C.c_void_p]
+        self.L = L
+
+    def order(self, pg: dict):
+        paths = [p for p in pg["paths"]]
+        names = [p["name"].encode() for p in paths]
+        off = np.zeros(len(paths) + 1, np.int64)
+        ids, strands = [], []
+        for k, p in enumerate(paths):
+            for b in p["blocks"]:
+                ids.append(b["id"].encode())
+                strands.append(1 if b.get("strand", True) else 0)
+            off[k + 1] = len(ids)
+        circ = np.asarray([1 if p.get("circular") else 0 for p in paths], np.int32)
+        strands = np.asarray(strands + [0], np.int32)
+        blk_ids = [b["id"].encode() for b in pg["blocks"]]
+        blk_len = np.asarray([len(b["sequence"]) for b in pg["blocks"]] + [0], np.int32)
+        arr = lambda xs: (C.c_char_p * max(1, len(xs)))(*xs)
+        h = C.c_void_p(self.L.refpg_order(C.c_int(len(paths)), arr(names), _p(off, C.c_int64), arr(ids), _p(strands, C.c_int32),
+                                          _p(circ, C.c_int32), C.c_int(len(blk_ids)), arr(blk_ids), _p(blk_len, C.c_int32)))
+        try:
+            n = int(self.L.refpg_n_topo(h))
+            out = dict(topo_ids=[self.L.refpg_topo_id(h, i).decode() for i in range(n)], aligned={}, strand={}, number={},
+                       rotation_index={}, visit=[])
+            with_blocks = [p["name"] for p in paths if p["blocks"]]
+            out["visit"] = [self.L.refpg_visit(h, k).decode() for k in range(len(set(with_blocks)))]
+            for name in with_blocks:
+                a, s_, nu = (np.empty(max(n, 1), np.int32) for _ in range(3))
+                self.L.refpg_aligned(h, name.encode(), a.ctypes.data, s_.ctypes.data, nu.ctypes.data)
+                out["aligned"][name], out["strand"][name], out["number"][name] = a[:n].copy(), s_[:n].copy(), nu[:n].copy()
+                out["rotation_index"][name] = int(self.L.refpg_rotation_index(h, name.encode()))
+            return out
+        finally:
+            self.L.refpg_free(h)
+
+
 def wire_mut_info(mut_info, nucs):
     """NucMut.mutInfo as the capnp writer stores it (reference src/panman.cpp:2876): the `length` nucleotide codes,
     right-aligned, above the 8-bit mutInfo. Works on ints and numpy arrays."""

@@ -228,6 +228,9 @@ class PanGraphBuild:
         n_leaves = self.tree.n_leaves
         self.block_ids = [L.pmh_pangraph_block_id(self.h, b).decode() for b in range(self.n_blocks)]
         self.block_states = np.ctypeslib.as_array(L.pmh_pangraph_block_states(self.h), (n_leaves, max(self.n_blocks, 1)))[:, :self.n_blocks].copy()
+        L.pmh_pangraph_rotation_index.argtypes = [vp]
+        L.pmh_pangraph_rotation_index.restype = C.POINTER(C.c_int32)
+        self.rotation_index = np.ctypeslib.as_array(L.pmh_pangraph_rotation_index(self.h), (max(n_leaves, 1),))[:n_leaves].copy()
         self.batches = []
         for b in range(self.n_blocks):
             n = int(L.pmh_pangraph_n_cols(self.h, b))

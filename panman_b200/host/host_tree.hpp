@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace pmh {
@@ -20,6 +21,23 @@ void split_quote_aware(const std::string& s, char delim, std::vector<std::string
 
 // reference src/panman.cpp:310-450 (createTreeFromNewickString). Returns "" or an error message.
 std::string parse_newick(const std::string& newick, HostTree* out);
+
+// Block order of a PanGraph build (block_order.cpp; reference src/panman.cpp:6259-6465, src/chaining.cpp, src/rotation.cpp).
+struct PathIn {
+    std::string name;
+    std::vector<std::string> blocks;  // block ids along the path
+    std::vector<int> strands;         // 1 forward, 0 reverse
+    bool circular = false;
+};
+struct BlockOrder {
+    std::vector<std::string> topo_ids;  // block id of every block column, in consensus order (duplicated blocks repeat)
+    // per path: for block column i the column itself or -1 (absent), the strand or -1, the occurrence number ("number" of
+    // the PanGraph JSON) of the path entry that landed there or 0
+    std::unordered_map<std::string, std::vector<int32_t>> aligned, strand, number;
+    std::unordered_map<std::string, int> rotation_index;  // circular paths: blocks the path was rotated by
+    std::vector<std::string> visit;                       // the order in which the paths were chained
+};
+void order_blocks(const std::vector<PathIn>& paths_in_json_order, BlockOrder* out);
 
 // reference Tree::transform (src/panman.cpp:5831-5906): `tip` becomes the first child of a new root. Defined in reroot.cpp.
 std::string reroot_tree(const HostTree& in, int32_t tip, HostTree* out);

@@ -11,9 +11,9 @@
 //     :1048-1232 (one column per main position j and per gap slot (j, k); sequences whose path lacks the block are
 //     OMITTED from the state map; parent state = consensus character, '-' for gap slots)
 // Stand-ins for what the files do not determine (same as tests/golden/make_sars20_golden.py):
-//   * block order = order of "blocks" in the JSON (the reference orders them with chain_align, src/chaining.cpp; only the
-//     block id carried in the stored tuples depends on it, no per-column result);
-//   * duplicated blocks (number > 1) and circular paths (rotation) are rejected, not guessed;
+// Block columns follow the reference: the consensus order of chain_align over the paths, one column per occurrence of a
+// duplicated block, circular paths rotated against the first path (block_order.cpp; src/panman.cpp:6259-6465,
+// src/chaining.cpp, src/rotation.cpp), and a sequence's mutations are those recorded for (block, sequence, occurrence).
 //   * root override: with --reference, the character of the LAST sequence in leaf-row order whose name contains the
 //     reference string (the reference iterates a tbb::concurrent_unordered_map); without it, gap columns and the Sankoff
 //     branch have none (guarded by reference.length()), while the Fitch main-column branch lacks that guard
@@ -87,7 +87,14 @@ struct JParser {
         p++;
         return true;
     }
+    int depth = 0;
     bool value(JValue& v) {
+        struct Depth {
+            int& d;
+            explicit Depth(int& x) : d(x) { d++; }
+            ~Depth() { d--; }
+        } guard(depth);
+        if (depth > 64) return fail("nesting too deep");
         ws();
         if (p >= end) return fail("unexpected end");
         if (*p == '{') {
@@ -178,6 +185,7 @@ struct pmh_pangraph {
     std::vector<int8_t> block_override; // n_blocks or empty
     BlockBatch block_level;             // results of the block-level pass
     bool has_reference = false;
+    std::vector<int32_t> rotation_index;  // per leaf row: blocks a circular path was rotated by (Tree::rotationIndexes)
     std::vector<std::vector<pmh_nucmut>> nuc;      // Node::nucMutation after the run, in the reference's order
     std::vector<std::vector<pmh_blockmut>> blockmut;  // Node::blockMutation after the run, ascending block id
 };
@@ -203,6 +211,7 @@ extern "C" {
 pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* newick, const char* reference_c, char* err,
                                 size_t err_len) {
     if (!json || !newick) { set_err(err, err_len, "null argument"); return nullptr; }
+    try {
     const std::string reference = reference_c ? reference_c : "";
     std::unique_ptr<pmh_pangraph> g(new pmh_pangraph());
     g->has_reference = !reference.empty();
@@ -216,7 +225,7 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
     const pmh::HostTree& T = g->tree.t;
     JValue root;
     {
-        JParser jp{json, json + json_len, ""};
+        JParser jp{json, json + json_len, "", 0};
         if (!jp.value(root)) { set_err(err, err_len, jp.err); return nullptr; }
     }
     const JValue* paths = root.get("paths");
@@ -228,25 +237,41 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
     std::unordered_map<std::string, int32_t> row_of;
     for (int32_t v = 0; v < T.n_nodes(); v++)
         if (T.leaf_row[v] >= 0) row_of[T.names[v]] = T.leaf_row[v];
-    // which sequences own which block, and on which strand (paths, src/panman.cpp:6203-6214)
-    std::unordered_map<std::string, std::map<int32_t, bool>> has_block;  // block id -> leaf row -> strand
+    // paths (src/panman.cpp:6203-6214), in JSON order; a path that is not a leaf of the tree still takes part in the block
+    // ordering (as in the reference, which chains every path) but owns no row
+    std::vector<pmh::PathIn> path_in;
     for (const JValue& path : paths->arr) {
         const JValue* name = path.get("name");
         const JValue* pb = path.get("blocks");
         const JValue* circ = path.get("circular");
-        if (!name || !pb) { set_err(err, err_len, "path without name / blocks"); return nullptr; }
-        if (circ && circ->kind == JValue::Bool && circ->b) { set_err(err, err_len, "circular paths (rotation) are not supported"); return nullptr; }
-        auto it = row_of.find(name->str);
-        if (it == row_of.end()) { set_err(err, err_len, "path " + name->str + " is not a leaf of the tree"); return nullptr; }
-        for (const JValue& b : pb->arr) {
-            const JValue *id = b.get("id"), *strand = b.get("strand"), *number = b.get("number");
-            if (!id) { set_err(err, err_len, "path block without id"); return nullptr; }
-            if ((number && number->num != 1) || has_block[id->str].count(it->second)) {
-                set_err(err, err_len, "duplicated block " + id->str + " in " + name->str + " is not supported");
-                return nullptr;
-            }
-            has_block[id->str][it->second] = !strand || strand->b;
+        if (!name || name->kind != JValue::Str || !pb || pb->kind != JValue::Arr) { set_err(err, err_len, "path without name / blocks"); return nullptr; }
+        pmh::PathIn pi;
+        pi.name = name->str;
+        pi.circular = circ && circ->kind == JValue::Bool && circ->b;
+        for (const JValue& bl : pb->arr) {
+            const JValue *id = bl.get("id"), *strand = bl.get("strand");
+            if (!id || id->kind != JValue::Str) { set_err(err, err_len, "path block without id"); return nullptr; }
+            pi.blocks.push_back(id->str);
+            pi.strands.push_back(!strand || strand->kind != JValue::Bool || strand->b ? 1 : 0);
         }
+        path_in.push_back(std::move(pi));
+    }
+    std::unordered_map<std::string, const JValue*> block_by_id;
+    for (const JValue& blk : blocks->arr) {
+        const JValue *id = blk.get("id"), *seq = blk.get("sequence");
+        if (!id || id->kind != JValue::Str || !seq || seq->kind != JValue::Str) { set_err(err, err_len, "block without id / sequence"); return nullptr; }
+        block_by_id[id->str] = &blk;
+    }
+    for (const pmh::PathIn& pi : path_in)
+        for (const std::string& id : pi.blocks)
+            if (!block_by_id.count(id)) { set_err(err, err_len, "path " + pi.name + " names the unknown block " + id); return nullptr; }
+    // block columns: the consensus order of chain_align, duplicated blocks as columns of their own, circular paths rotated
+    pmh::BlockOrder order;
+    pmh::order_blocks(path_in, &order);
+    g->rotation_index.assign(size_t(T.n_leaves), 0);
+    for (auto& kv : order.rotation_index) {
+        auto it = row_of.find(kv.first);
+        if (it != row_of.end()) g->rotation_index[size_t(it->second)] = kv.second;
     }
     auto matches_reference = [&](int32_t row) {
         if (reference.empty()) return false;
@@ -254,21 +279,28 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
             if (T.leaf_row[v] == row) return T.names[v].find(reference) != std::string::npos;
         return false;
     };
-    const int32_t NB = int32_t(blocks->arr.size()), L = T.n_leaves;
+    const int32_t NB = int32_t(order.topo_ids.size()), L = T.n_leaves;
     g->blocks.resize(NB);
     g->block_states.assign(size_t(L) * NB, 0);
     if (!reference.empty()) g->block_override.assign(NB, -1);
     for (int32_t i = 0; i < NB; i++) {
-        const JValue& blk = blocks->arr[i];
-        const JValue *id = blk.get("id"), *seq = blk.get("sequence"), *gaps = blk.get("gaps");
-        if (!id || !seq) { set_err(err, err_len, "block without id / sequence"); return nullptr; }
+        const JValue& blk = *block_by_id[order.topo_ids[i]];
+        const JValue *seq = blk.get("sequence"), *gaps = blk.get("gaps");
         BlockBatch& B = g->blocks[i];
-        B.id = id->str;
+        B.id = order.topo_ids[i];
         const std::string cons = upper(seq->str);
         const int64_t len = int64_t(cons.size());
         std::map<int64_t, int64_t> gap_len;  // position -> slots, ascending
-        if (gaps)
-            for (auto& kv : gaps->obj) gap_len[std::stoll(kv.first)] = int64_t(kv.second.num);
+        if (gaps && gaps->kind == JValue::Obj)
+            for (auto& kv : gaps->obj) {
+                char* endp = nullptr;
+                const long long pos = std::strtoll(kv.first.c_str(), &endp, 10);
+                if (endp == kv.first.c_str() || *endp || pos < 0 || pos > len || kv.second.kind != JValue::Num || kv.second.num < 0) {
+                    set_err(err, err_len, "block " + B.id + ": bad gap entry \"" + kv.first + "\"");
+                    return nullptr;
+                }
+                gap_len[pos] = int64_t(kv.second.num);
+            }
         // columns: main positions 0..len, then the gap slots in (position, slot) order
         std::map<std::pair<int64_t, int64_t>, int64_t> gap_col;
         for (int64_t j = 0; j <= len; j++) { B.col_pos.push_back(int32_t(j)); B.col_gap.push_back(-1); }
@@ -284,35 +316,49 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
         B.present.assign(L, 0);
         B.parent_code.assign(B.n_cols, 0);
         for (int64_t j = 0; j < len; j++) B.parent_code[j] = code_of((unsigned char)cons[j]);
-        auto& owners = has_block[B.id];
+        // owners of this column: the paths aligned to it, with their strand and which occurrence of the block it is
         std::vector<std::vector<uint8_t>> rows(L);
-        for (auto& ow : owners) {
-            const int32_t r = ow.first;
+        std::vector<int64_t> occurrence(size_t(L), 0);
+        for (const pmh::PathIn& pi : path_in) {
+            auto it = row_of.find(pi.name);
+            if (it == row_of.end()) continue;
+            auto al = order.aligned.find(pi.name);
+            if (al == order.aligned.end() || al->second[size_t(i)] < 0) continue;
+            const int32_t r = it->second;
             B.present[r] = 1;
-            g->block_states[size_t(r) * NB + i] = ow.second ? 1 : 2;
+            g->block_states[size_t(r) * NB + i] = order.strand[pi.name][size_t(i)] ? 1 : 2;
+            occurrence[size_t(r)] = order.number[pi.name][size_t(i)];
             rows[r].assign(B.parent_code.begin(), B.parent_code.end());  // consensus, '-' in every gap slot
         }
+        bool shape_ok = true;
         auto per_seq = [&](const char* field, auto&& fn) -> bool {
             const JValue* arr = blk.get(field);
-            if (!arr) return true;
+            if (!arr || arr->kind != JValue::Arr) return true;
             for (const JValue& e : arr->arr) {
-                if (e.arr.size() != 2) continue;
+                if (e.kind != JValue::Arr || e.arr.size() != 2 || e.arr[1].kind != JValue::Arr) continue;
                 const JValue *name = e.arr[0].get("name"), *number = e.arr[0].get("number");
-                if (!name || (number && number->num != 1)) continue;
+                if (!name || name->kind != JValue::Str) continue;
                 auto it = row_of.find(name->str);
                 if (it == row_of.end() || rows[it->second].empty()) continue;
+                // mutations are keyed by sequence AND occurrence (src/panman.cpp:1030-1044: [block][name][blockCounts])
+                if (int64_t(number && number->kind == JValue::Num ? number->num : 1) != occurrence[size_t(it->second)]) continue;
                 for (const JValue& m : e.arr[1].arr)
                     if (!fn(rows[it->second], m)) return false;
             }
             return true;
         };
+        auto is_num = [](const JValue& v) { return v.kind == JValue::Num; };
         bool ok = per_seq("mutate", [&](std::vector<uint8_t>& row, const JValue& m) {
+            if (m.kind != JValue::Arr || m.arr.size() < 2 || !is_num(m.arr[0]) || m.arr[1].kind != JValue::Str || m.arr[1].str.empty()) return shape_ok = false;
             const int64_t pos = int64_t(m.arr[0].num);
             if (pos < 1 || pos > len + 1) return false;
             row[pos - 1] = code_of((unsigned char)std::toupper((unsigned char)m.arr[1].str[0]));
             return true;
         });
         ok = ok && per_seq("insert", [&](std::vector<uint8_t>& row, const JValue& m) {
+            if (m.kind != JValue::Arr || m.arr.size() < 2 || m.arr[0].kind != JValue::Arr || m.arr[0].arr.size() < 2 || !is_num(m.arr[0].arr[0]) ||
+                !is_num(m.arr[0].arr[1]) || m.arr[1].kind != JValue::Str)
+                return shape_ok = false;
             const int64_t pos = int64_t(m.arr[0].arr[0].num), off = int64_t(m.arr[0].arr[1].num);
             const std::string s = upper(m.arr[1].str);
             for (size_t t = 0; t < s.size(); t++) {
@@ -323,12 +369,16 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
             return true;
         });
         ok = ok && per_seq("delete", [&](std::vector<uint8_t>& row, const JValue& m) {
+            if (m.kind != JValue::Arr || m.arr.size() < 2 || !is_num(m.arr[0]) || !is_num(m.arr[1])) return shape_ok = false;
             const int64_t pos = int64_t(m.arr[0].num), ln = int64_t(m.arr[1].num);
-            if (pos < 1 || pos + ln - 1 > len + 1) return false;
+            if (pos < 1 || ln < 0 || pos + ln - 1 > len + 1) return false;
             for (int64_t j = pos; j < pos + ln; j++) row[j - 1] = 0;
             return true;
         });
-        if (!ok) { set_err(err, err_len, "block " + B.id + ": a mutation lies outside the block"); return nullptr; }
+        if (!ok) {
+            set_err(err, err_len, "block " + B.id + (shape_ok ? ": a mutation lies outside the block" : ": JSON: malformed mutation entry"));
+            return nullptr;
+        }
         int32_t last_present = -1, ref_row = -1;
         for (int32_t r = 0; r < L; r++) {
             if (rows[r].empty()) continue;
@@ -352,6 +402,13 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
         }
     }
     return g.release();
+    } catch (const std::bad_alloc&) {
+        set_err(err, err_len, "out of host memory");
+        return nullptr;
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("PanGraph JSON: ") + ex.what());
+        return nullptr;
+    }
 }
 
 void pmh_pangraph_free(pmh_pangraph* g) { delete g; }
@@ -359,6 +416,7 @@ const pmh_tree* pmh_pangraph_tree(const pmh_pangraph* g) { return &g->tree; }
 int32_t pmh_pangraph_n_blocks(const pmh_pangraph* g) { return int32_t(g->blocks.size()); }
 const char* pmh_pangraph_block_id(const pmh_pangraph* g, int32_t b) { return g->blocks[b].id.c_str(); }
 const uint8_t* pmh_pangraph_block_states(const pmh_pangraph* g) { return g->block_states.data(); }
+const int32_t* pmh_pangraph_rotation_index(const pmh_pangraph* g) { return g->rotation_index.data(); }
 int64_t pmh_pangraph_n_cols(const pmh_pangraph* g, int32_t b) { return g->blocks[b].n_cols; }
 const uint8_t* pmh_pangraph_codes4(const pmh_pangraph* g, int32_t b, int64_t* row_stride) {
     if (row_stride) *row_stride = g->blocks[b].stride;

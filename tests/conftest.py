@@ -38,3 +38,13 @@ def refnm():
     if not have_ref_nucmut():
         pytest.skip("oracle/_ref/libpanman_nucmut.so not built (no /root/reference here and no prebuilt .so)")
     return RefNucMut()
+
+
+@pytest.fixture(scope="session")
+def refpg():
+    from oracle.oracle import RefPgOrder, build, have_ref_pgorder
+
+    build()
+    if not have_ref_pgorder():
+        pytest.skip("oracle/_ref/libpanman_pgorder.so not built (no /root/reference here and no prebuilt .so)")
+    return RefPgOrder()

@@ -13,9 +13,9 @@ aligned strings of a block -- src/panman.cpp:6216-6258 (JSON fields: consensus `
 and one per gap slot (j, k) (parent state '-'); sequences whose path lacks the block are OMITTED (missing-leaf
 semantics), sequences that have it contribute their character ('-' = code 0).
 
-Two inputs of that path are not reproducible from the files alone and get documented stand-ins:
-  * block order: the reference orders blocks with chain_align (chaining.cpp); here blocks keep the JSON order. Only
-    the block id carried in the 6-tuples depends on it, not any per-column result;
+Block columns are in the reference's own order: oracle.RefPgOrder runs the reference's chaining.cpp / rotation.cpp
+(compiled verbatim into oracle/_ref/libpanman_pgorder.so) the way Pangraph::Pangraph drives them (src/panman.cpp:6259-6465).
+One input of that path is not reproducible from the files alone and gets a documented stand-in:
   * root override of MAIN columns without --reference: panman.cpp:1132 lacks the `reference.length()` guard, so the
     root is forced to the state of whichever present sequence a tbb::concurrent_unordered_map iterates last. The
     stand-in is the present sequence with the highest leaf row. Gap columns (guarded, :1057) have no override.
@@ -30,7 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle.oracle import RefOracle, build, parse_newick, ref_run_columns  # noqa: E402
+from oracle.oracle import RefOracle, RefPgOrder, build, parse_newick, ref_run_columns  # noqa: E402
 from tests.pangraph_util import build_batches  # noqa: E402
 
 REF_TEST = "/root/reference/test"
@@ -43,8 +43,11 @@ def main():
     newick = open(os.path.join(REF_TEST, "sars_20.nwk")).readline().strip()
     tree = parse_newick(newick)
     pg = json.load(open(os.path.join(REF_TEST, "sars_20.json")))
-    bcodes, batches = build_batches(pg, tree)
-    out = dict(newick=np.frombuffer(newick.encode(), np.uint8), n_blocks=np.asarray([len(pg["blocks"])], np.int32))
+    order = RefPgOrder().order(pg)
+    print("block columns:", order["topo_ids"])
+    bcodes, batches = build_batches(pg, tree, order)
+    out = dict(newick=np.frombuffer(newick.encode(), np.uint8), n_blocks=np.asarray([len(batches)], np.int32),
+               block_ids=np.frombuffer("\n".join(order["topo_ids"]).encode(), np.uint8))
     # ---- block level: one 3-state column per block (0 absent, 1 forward, 2 reverse); parent state absent; no --reference
     out["blk_codes"] = bcodes
     for algo in (0, 1):

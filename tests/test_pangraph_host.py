@@ -20,35 +20,57 @@ def _same_batches(got, want_states, want_batches):
             assert np.array_equal(g[k], w[k]), (g["id"], k)
 
 
-def test_adaptor_batches_match_restatement():
+@pytest.mark.parametrize("duplicates,circular,shuffle", [(False, False, False), (True, False, False), (False, True, False),
+                                                         (False, False, True), (True, True, True)])
+def test_adaptor_batches_match_restatement(refpg, duplicates, circular, shuffle):
+    """Block columns (the order chain_align gives, duplicated blocks, rotated circular paths: against the reference's own
+    compiled chaining.cpp / rotation.cpp) and the per-column batches (against the Python restatement on that order)."""
     from panman_b200.host import PanGraphBuild
 
-    rng = np.random.default_rng(8)
-    for trial in range(10):
+    rng = np.random.default_rng(8 + 4 * duplicates + 2 * circular + shuffle)
+    for trial in range(12):
         tree = random_tree(int(rng.integers(2, 40)), 8100 + trial, ["binary", "polytomy", "caterpillar"][trial % 3], max_arity=4)
-        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(1, 6)), max_len=int(rng.choice([8, 60, 300])))
-        want_states, want_batches = build_batches(json.loads(text), tree)
+        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(1, 7)), max_len=int(rng.choice([8, 60, 300])),
+                               duplicates=duplicates, circular=circular, shuffle=shuffle)
+        pg = json.loads(text)
+        order = refpg.order(pg)
+        want_states, want_batches = build_batches(pg, tree, order)
         got = PanGraphBuild(text.encode(), tree.to_newick())
         assert got.tree.names == tree.names
+        assert got.block_ids == order["topo_ids"], (trial, "block columns")
+        rows = {tree.names[v]: int(tree.leaf_row[v]) for v in tree.leaves}
+        for name, rot in order["rotation_index"].items():
+            assert got.rotation_index[rows[name]] == rot, (trial, name)
         _same_batches(got, want_states, want_batches)
         got.close()
 
 
-def test_adaptor_rejects_what_it_does_not_model():
+def test_adaptor_reports_malformed_input():
+    """Nothing may abort the host process: malformed JSON, wrong kinds and sizes, unknown blocks come back as errors."""
     from panman_b200.host import PanGraphBuild
 
     tree = random_tree(3, 1, "binary")
     pg = json.loads(random_pangraph(tree, np.random.default_rng(1), n_blocks=2))
-    bad = json.loads(json.dumps(pg))
-    bad["paths"][0]["circular"] = True
-    with pytest.raises(ValueError, match="circular"):
-        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
-    bad = json.loads(json.dumps(pg))
-    bad["paths"][0]["blocks"].append(dict(bad["paths"][0]["blocks"][0]))
-    with pytest.raises(ValueError, match="duplicated"):
-        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
     with pytest.raises(ValueError, match="JSON"):
         PanGraphBuild(b'{"paths": [', tree.to_newick())
+    with pytest.raises(ValueError, match="JSON"):
+        PanGraphBuild(b"[" * 100 + b"]" * 100, tree.to_newick())
+    bad = json.loads(json.dumps(pg))
+    bad["blocks"][0]["gaps"] = {"x7": 2}
+    with pytest.raises(ValueError, match="gap"):
+        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
+    bad = json.loads(json.dumps(pg))
+    bad["blocks"][0]["mutate"] = [[{"name": tree.names[int(tree.leaves[0])], "number": 1}, [[3]]]]
+    with pytest.raises(ValueError, match="malformed"):
+        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
+    bad = json.loads(json.dumps(pg))
+    bad["blocks"][0]["insert"] = [[{"name": tree.names[int(tree.leaves[0])], "number": 1}, [[5, "ACG"]]]]
+    with pytest.raises(ValueError, match="malformed"):
+        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
+    bad = json.loads(json.dumps(pg))
+    bad["paths"][0]["blocks"][0]["id"] = "NOPE"
+    with pytest.raises(ValueError, match="unknown block"):
+        PanGraphBuild(json.dumps(bad).encode(), tree.to_newick())
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/test/sars_20.json"), reason="the reference's test data is not on this machine")
@@ -79,7 +101,8 @@ def test_pangraph_flow_matches_oracle(port, algo):
     ctx = pb.Context(0)
     for trial in range(5):
         tree = random_tree(int(rng.integers(3, 60)), 8200 + trial, ["binary", "polytomy", "caterpillar"][trial % 3], max_arity=4)
-        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(1, 5)), max_len=int(rng.choice([40, 300, 1500])))
+        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(1, 5)), max_len=int(rng.choice([40, 300, 1500])),
+                               duplicates=trial % 2 == 1, circular=trial == 3, shuffle=trial >= 3)
         build = PanGraphBuild(text.encode(), tree.to_newick())
         results = build.run(ctx, algo)
         nb = build.n_blocks
