@@ -246,6 +246,7 @@ def measure_one(pb, synth, torch, name, algo, dev, local, steps, warmup):
     ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro)
     del codes4
     lib = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    lib_end = torch.cuda.ExternalStream(ctx.result_stream_handle(), device=dev)  # a pass ends on its compaction stream
     for _ in range(max(3, warmup)):
         ctx.run_resident_async(algo_i)
     ctx.wait()
@@ -253,7 +254,7 @@ def measure_one(pb, synth, torch, name, algo, dev, local, steps, warmup):
     e0.record(lib)
     for _ in range(steps):
         ctx.run_resident_async(algo_i)
-    e1.record(lib)
+    e1.record(lib_end)
     ctx.wait()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -378,6 +379,7 @@ def run_b200_arm(args):
     if world > 1:
         connect_group(g, dist, n_mut_rank + n_mut_rank // 4 + 4096, device=dev)
     lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    lib_end_stream = torch.cuda.ExternalStream(ctx.result_stream_handle(), device=dev)  # compaction (+ packing) stream: a pass ends here
 
     def barrier():
         g.wait()
@@ -396,7 +398,7 @@ def run_b200_arm(args):
     ev0.record(lib_stream)
     for _ in range(args.steps):
         g.run_async(algo_i)  # one C call per step: pass -> pack into rank 0's mailbox -> signal (-> merge on rank 0)
-    ev1.record(lib_stream)
+    ev1.record(lib_end_stream)
     barrier()  # ends after the last merge on rank 0
     elapsed = time.perf_counter() - t0
     sampler.stop_flag = True

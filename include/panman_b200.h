@@ -202,11 +202,16 @@ int pmb_result_device(pmb_ctx* ctx, pmb_result* out);
  * shards, given in ascending column-range order, into node-major lists: per node the shard lists are concatenated in
  * shard order (each is already in ascending position), nothing is sorted. The reference's <=6 run-merge
  * (src/panman.cpp:1445-1466) must run on the merged lists, never per shard. `capacity` = records the buffer can hold
- * (>= n_mut of every shard); `stream` = CUDA stream (cudaStream_t) to enqueue on, NULL = the context's stream. */
-void* pmb_stream(pmb_ctx* ctx); /* the cudaStream_t the context enqueues on, to order caller work after it */
+ * (>= n_mut of every shard); `stream` = CUDA stream (cudaStream_t) to enqueue on, NULL = pmb_result_stream. */
+void* pmb_stream(pmb_ctx* ctx); /* the cudaStream_t the forward and backward kernels are enqueued on */
+/* The cudaStream_t on which a pass ENDS: the ordered compaction runs on a stream of its own (behind the backward kernel), so
+ * that the next pass' forward kernel starts at once and the compaction fills the SMs that kernel leaves idle while it
+ * drains; only the next backward kernel waits for it. Work that consumes the lists (pmb_pack_result, pmb_merge_runs with
+ * source 0, pmb_download) is enqueued here; order caller work after a pass on THIS stream. */
+void* pmb_result_stream(pmb_ctx* ctx);
 int64_t pmb_packed_bytes(int32_t n_nodes, int64_t capacity);
-/* Stream rules. pmb_pack_result on a stream other than the context's first makes that stream wait for the pass enqueued
- * last (an event), so it may be called right behind pmb_run_resident_async. pmb_merge_packed remembers its stream:
+/* Stream rules. `stream` = NULL means pmb_result_stream. pmb_pack_result on another stream first makes that stream wait for
+ * the pass enqueued last (an event), so it may be called right behind pmb_run_resident_async. pmb_merge_packed remembers its stream:
  * pmb_merge_runs(source = 1) and pmb_merge_status run on / wait for that stream. The destination of pmb_pack_result may be
  * peer memory (another GPU's buffer mapped into this process): the shard is then written over NVLink by the packing
  * kernel itself. A shard that holds more than `capacity` records is packed truncated and flagged in its header; merging

@@ -183,6 +183,9 @@ class Context:
     def stream_handle(self) -> int:
         return int(self.L.pmb_stream(self.h) or 0)
 
+    def result_stream_handle(self) -> int:
+        return int(self.L.pmb_result_stream(self.h) or 0)
+
     def packed_bytes(self, capacity: int) -> int:
         return int(self.L.pmb_packed_bytes(self.n_nodes, int(capacity)))
 

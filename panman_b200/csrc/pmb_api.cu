@@ -92,6 +92,12 @@ struct pmb_ctx {
     unsigned int pack_seq = 0;
     bool async_pending = false;
     bool upload_pending = false;       // pmb_upload_nuc_async: borrowed input buffers are still being read
+    // Compaction runs on a stream of its own: the pass after it starts its forward kernel at once and the compaction
+    // kernels fill the SMs that kernel leaves idle while it drains through the top of the tree; only the NEXT backward
+    // kernel (which refills the staging pool and the directory) waits for them.
+    cudaStream_t cstream = nullptr;
+    cudaEvent_t ev_bwd_done = nullptr, ev_compact_done = nullptr;
+    unsigned int run_seq = 0;             // parity selects the ticket set of a run
     cudaStream_t merge_stream = nullptr;  // stream of the last pmb_merge_packed (never owned)
     cudaEvent_t ev_merge = nullptr, ev_rm = nullptr;
     cudaStream_t rm_stream = nullptr;     // stream of the last pmb_merge_runs
@@ -338,6 +344,14 @@ int pmb_create(pmb_ctx** out, int device) {
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_merge, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_bwd_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_compact_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        // highest priority: its small kernels take the first SM slots that come free beside a draining pass kernel
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->cstream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rm, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         c->err = std::string("stream/event creation failed: ") + cudaGetErrorString(e);
@@ -376,6 +390,12 @@ void pmb_destroy(pmb_ctx* c) {
         }
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         if (c->ev_merge) cudaEventDestroy(c->ev_merge);
+        if (c->ev_bwd_done) cudaEventDestroy(c->ev_bwd_done);
+        if (c->ev_compact_done) cudaEventDestroy(c->ev_compact_done);
+        if (c->cstream) {
+            cudaStreamSynchronize(c->cstream);
+            cudaStreamDestroy(c->cstream);
+        }
         if (c->ev_rm) cudaEventDestroy(c->ev_rm);
         for (int k = 0; k < 2; k++) {
             if (c->ev_slab_copied[k]) cudaEventDestroy(c->ev_slab_copied[k]);
@@ -579,7 +599,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     }
     PMB_CUDA(c->h_counters.ensure(128));
     if (!c->d_ticket.p) c->state_dirty = true;
-    PMB_CUDA(c->d_ticket.ensure(64 * sizeof(unsigned long long)));
+    PMB_CUDA(c->d_ticket.ensure(128 * sizeof(unsigned long long)));  // two sets: consecutive runs overlap (see cstream)
     {
         int rcf;
         if ((rcf = ensure_flags(c, c->d_done, size_t(P.n_internal) * T))) return rcf;
@@ -640,7 +660,8 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     // Per-run device state is left clean by the run before (compact_copy_kernel's last block resets the counters and
     // tickets; directory entries carry a run tag): nothing is cleared on the stream in steady state.
     if (c->state_dirty) {
-        PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 64 * sizeof(unsigned long long), c->stream));
+        PMB_CUDA(cudaStreamSynchronize(c->cstream));  // a compaction of an abandoned run may still be using what is reset here
+        PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 128 * sizeof(unsigned long long), c->stream));
         PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
         unsigned int* init = c->h_counters.as<unsigned int>() + 16;  // pinned
         init[0] = 0xFFFFFFFFu;
@@ -659,6 +680,11 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     rp.epoch = ++c->epoch;
     const unsigned int fwd_epoch = rp.epoch;
+    const int ticket_set = 64 * int(c->run_seq++ & 1u);  // the compaction of the run before resets the other set
+    unsigned int* const run_error = rp.error;
+    // the forward kernel may run beside the previous run's compaction, whose last block snapshots and resets the per-run
+    // error words: its only status, the watchdog bit, goes straight to the sticky word
+    unsigned int* const fwd_error = reinterpret_cast<unsigned int*>(c->d_counters.as<unsigned long long>() + 2);
     for (int attempt = 0;; attempt++) {
         PMB_CUDA(c->d_staging.ensure(size_t(c->staging_cap) * sizeof(uint16_t)));
         PMB_CUDA(c->d_pos.ensure(size_t(c->staging_cap) * sizeof(int32_t)));
@@ -666,10 +692,6 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         rp.staging = c->d_staging.as<uint16_t>();
         rp.staging_cap = c->staging_cap;
         const unsigned int bwd_epoch = ++c->epoch;
-        if (c->dir_clean_epoch == 0 || bwd_epoch - c->dir_clean_epoch >= DIR_TAG_MASK - 8u) {  // new buffer, or the tag would wrap
-            PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, c->d_dir.cap, c->stream));
-            c->dir_clean_epoch = bwd_epoch;
-        }
         rp.dir_tag = bwd_epoch & DIR_TAG_MASK;
         // per-phase events only where somebody reads them: an asynchronous pass on one stream is timed as a whole, and
         // every record between two kernels costs the stream a microsecond or two
@@ -683,34 +705,50 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             rp.trace_base = (unsigned long long)P.chunks.size() * rp.tile_begin;
             if (attempt == 0) {  // the forward result stays valid across a staging-pool retry
                 rp.epoch = fwd_epoch;
-                if ((rc = launch_pass(c, st, 2 * g, rp, algo, true, &n_launches))) return rc;
+                rp.error = fwd_error;
+                if ((rc = launch_pass(c, st, ticket_set + 2 * g, rp, algo, true, &n_launches))) return rc;
+                rp.error = run_error;
             }
             if (phase_events) PMB_CUDA(cudaEventRecord(c->gev_fwd[g], st));
+            // the backward kernel refills the staging pool and the directory the previous compaction reads
+            PMB_CUDA(cudaStreamWaitEvent(st, c->ev_compact_done, 0));
+            if (g == 0 && (c->dir_clean_epoch == 0 || bwd_epoch - c->dir_clean_epoch >= DIR_TAG_MASK - 8u)) {  // new buffer, or the tag would wrap
+                PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, c->d_dir.cap, st));
+                c->dir_clean_epoch = bwd_epoch;
+                if (G > 1) {  // the other groups' backward kernels write the directory too
+                    PMB_CUDA(cudaEventRecord(c->ev_fork, st));
+                    for (int g2 = 1; g2 < G; g2++) PMB_CUDA(cudaStreamWaitEvent(c->gstream[g2], c->ev_fork, 0));
+                }
+            }
             rp.epoch = bwd_epoch;
             rp.trace_base = trace_items + (unsigned long long)P.chunks.size() * rp.tile_begin;
-            if ((rc = launch_pass(c, st, 2 * g + 1 + 32 * (attempt & 1), rp, algo, false, &n_launches))) return rc;
+            if ((rc = launch_pass(c, st, ticket_set + 2 * g + 1 + 32 * (attempt & 1), rp, algo, false, &n_launches))) return rc;
             if (phase_events) PMB_CUDA(cudaEventRecord(c->gev_done[g], st));
             if (G > 1) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->gev_done[g], 0));
         }
         if (phase_events) PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
         c->async_phase_events = phase_events;
+        PMB_CUDA(cudaEventRecord(c->ev_bwd_done, c->stream));
+        PMB_CUDA(cudaStreamWaitEvent(c->cstream, c->ev_bwd_done, 0));
         {
             const unsigned long long n_entries = (unsigned long long)P.n_nodes * (unsigned long long)c->T;
             const unsigned groups = unsigned((n_entries + CPT_GROUP - 1) / CPT_GROUP);
+            if (size_t(groups) * 12 + 16 > c->d_scan_state.cap) PMB_CUDA(cudaStreamSynchronize(c->cstream));
             PMB_CUDA(c->d_scan_state.ensure(size_t(groups) * 12 + 16));
             unsigned long long* gprefix = c->d_scan_state.as<unsigned long long>();
             unsigned int* gtotals = reinterpret_cast<unsigned int*>(gprefix + groups);
-            compact_count_kernel<<<(groups + 7) / 8, 256, 0, c->stream>>>(n_entries, rp.dir, rp.dir_tag, gtotals, groups);
-            compact_scan_kernel<<<1, 1024, 0, c->stream>>>(gtotals, int(groups), gprefix, c->d_offsets.as<long long>() + P.n_nodes);
-            compact_copy_kernel<<<groups, CPT_GROUP, 0, c->stream>>>(
+            compact_count_kernel<<<(groups + 7) / 8, 256, 0, c->cstream>>>(n_entries, rp.dir, rp.dir_tag, gtotals, groups);
+            compact_scan_kernel<<<1, 1024, 0, c->cstream>>>(gtotals, int(groups), gprefix, c->d_offsets.as<long long>() + P.n_nodes);
+            compact_copy_kernel<<<groups, CPT_GROUP, 0, c->cstream>>>(
                 P.n_nodes, c->T, gprefix, c->d_offsets.as<long long>(), rp.dir, rp.dir_tag, rp.staging, c->col_base,
                 c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), c->d_counters.as<unsigned long long>(), rp.staging_cap,
-                c->d_ticket.as<unsigned long long>(), 64);
+                c->d_ticket.as<unsigned long long>() + ticket_set, 64);
             n_launches += 2;
             n_launches += 1;
         }
         PMB_CUDA(cudaGetLastError());
-        PMB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        PMB_CUDA(cudaEventRecord(c->ev[3], c->cstream));
+        PMB_CUDA(cudaEventRecord(c->ev_compact_done, c->cstream));
         c->state_dirty = false;
         if (async) {  // status, overflow handling and timings wait for pmb_wait
             c->async_pending = true;
@@ -723,13 +761,16 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             c->have_result = true;
             return PMB_OK;
         }
-        PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 16, cudaMemcpyDeviceToHost, c->stream));  // snapshot
+        PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 16, cudaMemcpyDeviceToHost, c->cstream));  // snapshot
         PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_offsets.as<long long>() + P.n_nodes, 8, cudaMemcpyDeviceToHost,
-                                 c->stream));
+                                 c->cstream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 24, c->d_counters.as<char>() + 16, 4, cudaMemcpyDeviceToHost, c->cstream));  // sticky
+        PMB_CUDA(cudaStreamSynchronize(c->cstream));  // ordered behind the backward kernels of the main stream
         PMB_CUDA(cudaStreamSynchronize(c->stream));
         c->upload_pending = false;
         unsigned long long total = *c->h_counters.as<unsigned long long>();
         unsigned int eflags = c->h_counters.as<unsigned int>()[2], ecol = c->h_counters.as<unsigned int>()[3];
+        eflags |= c->h_counters.as<unsigned int>()[6] & 2u;  // the forward kernel's watchdog bit
         if (eflags || total > c->staging_cap) c->sticky_dirty = true;
         if (eflags & 2u) return fail(c, PMB_ERR_INTERNAL, "scheduler watchdog fired: a dependency flag never arrived");
         if (eflags & 1u) {
@@ -797,10 +838,11 @@ int pmb_wait(pmb_ctx* c) {
     c->upload_pending = false;
     const int N = c->prog.n_nodes;
     // [0,8) snapshot of the last run's staging reservation, [16,24) sticky status of all runs since the last wait
-    PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 8, cudaMemcpyDeviceToHost, c->stream));
-    PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_counters.as<char>() + 16, 8, cudaMemcpyDeviceToHost, c->stream));
-    PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 32, c->d_offsets.as<long long>() + N, 8, cudaMemcpyDeviceToHost, c->stream));
     PMB_CUDA(cudaStreamSynchronize(c->stream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.p, c->d_counters.as<char>() + 32, 8, cudaMemcpyDeviceToHost, c->cstream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 16, c->d_counters.as<char>() + 16, 8, cudaMemcpyDeviceToHost, c->cstream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_counters.as<char>() + 32, c->d_offsets.as<long long>() + N, 8, cudaMemcpyDeviceToHost, c->cstream));
+    PMB_CUDA(cudaStreamSynchronize(c->cstream));
     c->async_pending = false;
     const unsigned int sticky = c->h_counters.as<unsigned int>()[4], scol = c->h_counters.as<unsigned int>()[5];
     unsigned int sticky_init[2] = {0u, 0xFFFFFFFFu};
@@ -861,10 +903,10 @@ int pmb_download(pmb_ctx* c, pmb_result* out) {
     PMB_CUDA(c->h_offsets.ensure((N + 1) * sizeof(int64_t)));
     PMB_CUDA(c->h_pos.ensure(std::max<size_t>(n, 1) * sizeof(int32_t)));
     PMB_CUDA(c->h_tc.ensure(std::max<size_t>(n, 1)));
-    PMB_CUDA(cudaMemcpyAsync(c->h_offsets.p, c->d_offsets.p, (N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    PMB_CUDA(cudaMemcpyAsync(c->h_offsets.p, c->d_offsets.p, (N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->cstream));
     if (n) {
-        PMB_CUDA(cudaMemcpyAsync(c->h_pos.p, c->d_pos.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        PMB_CUDA(cudaMemcpyAsync(c->h_tc.p, c->d_tc.p, n, cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_pos.p, c->d_pos.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->cstream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_tc.p, c->d_tc.p, n, cudaMemcpyDeviceToHost, c->cstream));
     }
     out->states = nullptr;
     if (c->last_flags & PMB_FLAG_WANT_STATES) {
@@ -872,13 +914,13 @@ int pmb_download(pmb_ctx* c, pmb_result* out) {
         PMB_CUDA(c->d_states_u8.ensure(cells));
         PMB_CUDA(c->h_states.ensure(cells));
         unsigned blocks = unsigned((cells + 255) / 256);
-        unpack_states_kernel<<<blocks, 256, 0, c->stream>>>(c->d_states_planes.as<uint4>(), c->prog.n_nodes, c->n_cols, c->T,
+        unpack_states_kernel<<<blocks, 256, 0, c->cstream>>>(c->d_states_planes.as<uint4>(), c->prog.n_nodes, c->n_cols, c->T,
                                                             c->d_states_u8.as<uint8_t>());
         PMB_CUDA(cudaGetLastError());
-        PMB_CUDA(cudaMemcpyAsync(c->h_states.p, c->d_states_u8.p, cells, cudaMemcpyDeviceToHost, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->h_states.p, c->d_states_u8.p, cells, cudaMemcpyDeviceToHost, c->cstream));
         out->states = c->h_states.as<uint8_t>();
     }
-    PMB_CUDA(cudaStreamSynchronize(c->stream));
+    PMB_CUDA(cudaStreamSynchronize(c->cstream));
     out->n_mut = c->n_mut;
     out->n_nodes = c->prog.n_nodes;
     out->reserved = 0;
@@ -925,6 +967,7 @@ long long pmb_debug_trace(const pmb_ctx* c, unsigned long long* out, long long m
 }
 
 void* pmb_stream(pmb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+void* pmb_result_stream(pmb_ctx* c) { return c ? static_cast<void*>(c->cstream) : nullptr; }
 
 int64_t pmb_packed_bytes(int32_t n_nodes, int64_t capacity) { return int64_t(packed_bytes(n_nodes, capacity)); }
 
@@ -935,8 +978,8 @@ int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v
     if (capacity < 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15u)) return fail(c, PMB_ERR_INVALID, "pmb_pack_result: buffer must be 16-byte aligned");
     if (c->n_mut >= 0 && capacity < c->n_mut) return fail(c, PMB_ERR_CAPACITY, "pmb_pack_result: capacity below the record count");
     PMB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
-    if (st != c->stream) PMB_CUDA(cudaStreamWaitEvent(st, c->ev[3], 0));  // ev[3]: end of the pass enqueued last
+    cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->cstream;  // the lists are produced on the compaction stream
+    if (st != c->cstream) PMB_CUDA(cudaStreamWaitEvent(st, c->ev[3], 0));  // ev[3]: end of the pass enqueued last
     const long long N = c->prog.n_nodes;
     unsigned char* out = static_cast<unsigned char*>(d_packed);
     // everything is read on the device (n_mut = offsets[N] and the overflow status included), so nothing here needs the
@@ -944,9 +987,9 @@ int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v
     pack_result_kernel<<<c->n_sms * 2, 512, 0, st>>>(c->d_offsets.as<long long>(), c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), N,
                                                     capacity, (long long)c->staging_cap, c->d_counters.as<unsigned long long>(), out);
     PMB_CUDA(cudaGetLastError());
-    if (st != c->stream) {  // the next pass overwrites the lists: it must wait for this copy
+    if (st != c->cstream) {  // the next pass' compaction overwrites the lists: it must wait for this copy
         PMB_CUDA(cudaEventRecord(c->ev_fork, st));
-        PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+        PMB_CUDA(cudaStreamWaitEvent(c->cstream, c->ev_fork, 0));
     }
     return PMB_OK;
 }
@@ -957,7 +1000,7 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
     PMB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->stream;
+    cudaStream_t st = stream_v ? static_cast<cudaStream_t>(stream_v) : c->cstream;
     const int N = c->prog.n_nodes;
     const size_t shard_bytes = packed_bytes(N, capacity);
     const size_t total_cap = size_t(n_shards) * size_t(capacity);
@@ -1040,9 +1083,9 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
         int rcw = pmb_wait(c);
         if (rcw) return rcw;
     }
-    // source 0 runs on the context's stream, source 1 on the stream of the pmb_merge_packed that produced the lists; the
-    // output buffers are shared, so a call on the other stream waits for the one before it
-    cudaStream_t st = source == 0 ? c->stream : c->merge_stream;
+    // source 0 runs on the stream the lists are produced on, source 1 on the stream of the pmb_merge_packed that produced
+    // them; the output buffers are shared, so a call on the other stream waits for the one before it
+    cudaStream_t st = source == 0 ? c->cstream : c->merge_stream;
     if (c->rm_stream && c->rm_stream != st) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_rm, 0));
     const int N = c->prog.n_nodes;
     const long long* off = source == 0 ? c->d_offsets.as<long long>() : c->d_moff.as<long long>();

@@ -220,7 +220,9 @@ int enqueue_step(pmb_group* g, int algo, int flags, uint32_t s) {
         int rc = pmb_run_resident_async(l.ctx, algo, flags);
         if (rc) return gctx(g, rc, l);
         G_CUDA(cudaSetDevice(l.device));
-        CUstream st = static_cast<CUstream>(pmb_stream(l.ctx));
+        // the pass ends on its result stream (the compaction's): packing and the hand-shake go there, and the main stream is
+        // free to start the next forward kernel
+        CUstream st = static_cast<CUstream>(pmb_result_stream(l.ctx));
         // the slot of this parity is free again once rank 0 has merged step s - 2
         if (s > 2) G_CU(g->wait32(st, CUdeviceptr(l.box + BOX_CREDIT), s - 2, CU_STREAM_WAIT_VALUE_GEQ));
         rc = pmb_pack_result(l.ctx, l.root_box + BOX_SLOTS + buf + size_t(r) * g->shard_bytes, g->capacity, nullptr);

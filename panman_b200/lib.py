@@ -11,7 +11,7 @@ EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb
            "pmb_run_resident", "pmb_download", "pmb_result_device", "pmb_last_timings", "pmb_algorithmic_bytes", "pmb_version",
            "pmb_packed_bytes", "pmb_pack_result", "pmb_merge_packed", "pmb_stream", "pmb_run_resident_async", "pmb_wait",
            "pmb_host_alloc", "pmb_host_free", "pmb_merge_runs", "pmb_set_column_breaks", "pmb_run_block",
-           "pmb_upload_nuc_async", "pmb_merge_status",
+           "pmb_upload_nuc_async", "pmb_merge_status", "pmb_result_stream",
            "pmb_group_create", "pmb_group_destroy", "pmb_group_last_error", "pmb_group_world", "pmb_group_ctx",
            "pmb_group_column_range", "pmb_group_set_tree", "pmb_group_reserve", "pmb_group_export", "pmb_group_connect",
            "pmb_group_upload_nuc", "pmb_group_upload_shard", "pmb_group_run_async", "pmb_group_wait",
@@ -76,6 +76,8 @@ def load_library():
     L.pmb_version.restype = C.c_char_p
     L.pmb_stream.argtypes = [vp]
     L.pmb_stream.restype = vp
+    L.pmb_result_stream.argtypes = [vp]
+    L.pmb_result_stream.restype = vp
     L.pmb_packed_bytes.argtypes = [i32, i64]
     L.pmb_packed_bytes.restype = i64
     L.pmb_host_alloc.argtypes = [C.c_size_t]
