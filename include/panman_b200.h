@@ -100,7 +100,9 @@ const char* pmb_last_error(const pmb_ctx* ctx);
  * "staging_records" (initial capacity of the mutation staging pool; 0 = chosen from the problem size),
  * "bwd_tail" (tenths of a machine-full of warps whose items form the sorted tail of the backward tickets; default 20),
  * "reserve_sms" (SMs the persistent kernels leave free, e.g. for an NCCL kernel running beside them; default 0),
- * "col_groups" (column-tile groups run on separate streams; default 1), "trace" (debug timeline). */
+ * "col_groups" (column-tile groups run on separate streams; default 1), "overlap" (1 [default]: set matrices up to 4 GB
+ * are double-buffered so that the forward kernel of an asynchronous pass runs beside the backward kernel of the pass
+ * before it; 0: one set matrix, passes strictly one after the other), "trace" (debug timeline). */
 int pmb_set_option(pmb_ctx* ctx, const char* key, int64_t value);
 
 /* Page-locked host memory for the caller's input buffers. pmb_run_nuc / pmb_upload_nuc accept any host pointer, but

@@ -96,7 +96,14 @@ struct pmb_ctx {
     // kernels fill the SMs that kernel leaves idle while it drains through the top of the tree; only the NEXT backward
     // kernel (which refills the staging pool and the directory) waits for them.
     cudaStream_t cstream = nullptr;
-    cudaEvent_t ev_bwd_done = nullptr, ev_compact_done = nullptr;
+    // The backward kernel has a stream of its own as well: with a second set matrix (small problems only, opt_overlap) the
+    // forward kernel of pass i + 1 runs beside the backward kernel of pass i and fills the SMs that one leaves idle while it
+    // drains. Order: fwd(i) -> bwd(i) -> compact(i); bwd(i) also after compact(i - 1) (staging pool, directory); fwd(i)
+    // after compact(i - 2) (same set matrix and ticket set), or after bwd(i - 1) when there is only one set matrix.
+    cudaStream_t bstream = nullptr;
+    cudaEvent_t ev_fwd_done = nullptr, ev_bwd_done = nullptr, ev_compact_done[2] = {nullptr, nullptr};
+    DevBuf d_sets2;
+    int64_t opt_overlap = 1;              // 1 = double-buffer the set matrix when it is small enough (see run_impl)
     unsigned int run_seq = 0;             // parity selects the ticket set of a run
     cudaStream_t merge_stream = nullptr;  // stream of the last pmb_merge_packed (never owned)
     cudaEvent_t ev_merge = nullptr, ev_rm = nullptr;
@@ -344,13 +351,16 @@ int pmb_create(pmb_ctx** out, int device) {
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_merge, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fwd_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_bwd_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_compact_done, cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->ev_compact_done[k], cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int lo = 0, hi = 0;
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        // highest priority: its small kernels take the first SM slots that come free beside a draining pass kernel
+        // highest priority: its small kernels take the first SM slots that come free beside a draining pass kernel; the
+        // backward kernel (older work) goes before the next pass' forward kernel on the default-priority main stream
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->cstream, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rm, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -373,7 +383,7 @@ void pmb_destroy(pmb_ctx* c) {
         cudaStreamSynchronize(c->stream);
         for (DevBuf* b : {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_bwd_order,
                           &c->d_level_order, &c->d_row_slot, &c->d_deps, &c->d_block_sums, &c->d_leaf_planes,
-                          &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_fstore,
+                          &c->d_present, &c->d_colparams, &c->d_tmp_codes, &c->d_tmp_cols, &c->d_sets, &c->d_sets2, &c->d_fstore,
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
@@ -390,12 +400,14 @@ void pmb_destroy(pmb_ctx* c) {
         }
         if (c->ev_fork) cudaEventDestroy(c->ev_fork);
         if (c->ev_merge) cudaEventDestroy(c->ev_merge);
+        if (c->bstream) cudaStreamSynchronize(c->bstream);
+        if (c->cstream) cudaStreamSynchronize(c->cstream);
+        if (c->ev_fwd_done) cudaEventDestroy(c->ev_fwd_done);
         if (c->ev_bwd_done) cudaEventDestroy(c->ev_bwd_done);
-        if (c->ev_compact_done) cudaEventDestroy(c->ev_compact_done);
-        if (c->cstream) {
-            cudaStreamSynchronize(c->cstream);
-            cudaStreamDestroy(c->cstream);
-        }
+        for (int k = 0; k < 2; k++)
+            if (c->ev_compact_done[k]) cudaEventDestroy(c->ev_compact_done[k]);
+        if (c->cstream) cudaStreamDestroy(c->cstream);
+        if (c->bstream) cudaStreamDestroy(c->bstream);
         if (c->ev_rm) cudaEventDestroy(c->ev_rm);
         for (int k = 0; k < 2; k++) {
             if (c->ev_slab_copied[k]) cudaEventDestroy(c->ev_slab_copied[k]);
@@ -433,6 +445,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "reserve_sms") c->opt_reserve_sms = value;
     else if (k == "target_items") c->opt_target_items = value;
     else if (k == "trace") c->opt_trace = value;
+    else if (k == "overlap") c->opt_overlap = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
 }
@@ -470,6 +483,9 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
     if (row_stride_bytes < (n_cols + 1) / 2) return fail(c, PMB_ERR_INVALID, "row_stride_bytes too small");
     if (n_cols > (int64_t(1) << 40)) return fail(c, PMB_ERR_INVALID, "n_cols too large");
     PMB_CUDA(cudaSetDevice(c->device));
+    // passes still in flight on the backward / compaction streams read what is overwritten here
+    PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_bwd_done, 0));
+    for (int k = 0; k < 2; k++) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_compact_done[k], 0));
     c->have_input = false;
     c->have_result = false;
     c->have_col_break = false;
@@ -586,7 +602,16 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     const TreeProgram& P = c->prog;
     const size_t T = size_t(c->T);
     const size_t set_bytes_per = (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
-    PMB_CUDA(c->d_sets.ensure(size_t(P.n_internal) * T * set_bytes_per));
+    const size_t set_bytes = size_t(P.n_internal) * T * set_bytes_per;
+    // a second set matrix lets consecutive passes overlap (see bstream); only where it is cheap: the large problems run at
+    // the HBM roofline anyway and would pay tens of GB for it
+    const bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= (size_t(4) << 30);
+    if (set_bytes > c->d_sets.cap || (overlap && set_bytes > c->d_sets2.cap)) {  // cudaFree of a matrix a running pass uses
+        PMB_CUDA(cudaStreamSynchronize(c->bstream));
+        PMB_CUDA(cudaStreamSynchronize(c->cstream));
+    }
+    PMB_CUDA(c->d_sets.ensure(set_bytes));
+    if (overlap) PMB_CUDA(c->d_sets2.ensure(set_bytes));
     PMB_CUDA(c->d_fstore.ensure(std::max<size_t>(16, size_t(P.n_fslots) * T * FSLOT_WORDS * sizeof(uint32_t))));
     const bool want_states = flags & PMB_FLAG_WANT_STATES;
     if (want_states) PMB_CUDA(c->d_states_planes.ensure(size_t(P.n_nodes) * T * 64 * sizeof(uint4)));
@@ -624,7 +649,8 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     rp.deps = c->d_deps.as<int>();
     rp.leaf_planes = c->d_leaf_planes.as<uint4>();
     rp.leaf_present = c->have_present ? c->d_present.as<uint8_t>() : nullptr;
-    rp.sets = c->d_sets.as<uint4>();
+    const int parity = int(c->run_seq & 1u);
+    rp.sets = (overlap && parity) ? c->d_sets2.as<uint4>() : c->d_sets.as<uint4>();
     rp.fstore = c->d_fstore.as<uint32_t>();
     rp.order = nullptr;
     rp.stage_block = 512;
@@ -660,7 +686,8 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     // Per-run device state is left clean by the run before (compact_copy_kernel's last block resets the counters and
     // tickets; directory entries carry a run tag): nothing is cleared on the stream in steady state.
     if (c->state_dirty) {
-        PMB_CUDA(cudaStreamSynchronize(c->cstream));  // a compaction of an abandoned run may still be using what is reset here
+        PMB_CUDA(cudaStreamSynchronize(c->bstream));  // kernels of an abandoned run may still be using what is reset here
+        PMB_CUDA(cudaStreamSynchronize(c->cstream));
         PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 128 * sizeof(unsigned long long), c->stream));
         PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
         unsigned int* init = c->h_counters.as<unsigned int>() + 16;  // pinned
@@ -677,10 +704,16 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         c->sticky_dirty = false;
     }
     c->state_dirty = true;  // until everything below has been enqueued
+    // forward kernel: after the pass two back has left this set matrix and ticket set, or -- one set matrix -- after the
+    // previous backward kernel
+    PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_compact_done[parity], 0));
+    if (!overlap) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_bwd_done, 0));
     PMB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     rp.epoch = ++c->epoch;
     const unsigned int fwd_epoch = rp.epoch;
-    const int ticket_set = 64 * int(c->run_seq++ & 1u);  // the compaction of the run before resets the other set
+    const int ticket_set = 64 * parity;  // the compaction of the run before resets the other set
+    c->run_seq++;
+    cudaStream_t const bwd_stream = G == 1 ? c->bstream : c->stream;
     unsigned int* const run_error = rp.error;
     // the forward kernel may run beside the previous run's compaction, whose last block snapshots and resets the per-run
     // error words: its only status, the watchdog bit, goes straight to the sticky word
@@ -710,8 +743,13 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
                 rp.error = run_error;
             }
             if (phase_events) PMB_CUDA(cudaEventRecord(c->gev_fwd[g], st));
+            if (G == 1) {  // the backward kernel continues on its own stream
+                PMB_CUDA(cudaEventRecord(c->ev_fwd_done, st));
+                st = bwd_stream;
+                PMB_CUDA(cudaStreamWaitEvent(st, c->ev_fwd_done, 0));
+            }
             // the backward kernel refills the staging pool and the directory the previous compaction reads
-            PMB_CUDA(cudaStreamWaitEvent(st, c->ev_compact_done, 0));
+            for (int k = 0; k < 2; k++) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_compact_done[k], 0));
             if (g == 0 && (c->dir_clean_epoch == 0 || bwd_epoch - c->dir_clean_epoch >= DIR_TAG_MASK - 8u)) {  // new buffer, or the tag would wrap
                 PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, c->d_dir.cap, st));
                 c->dir_clean_epoch = bwd_epoch;
@@ -726,9 +764,9 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             if (phase_events) PMB_CUDA(cudaEventRecord(c->gev_done[g], st));
             if (G > 1) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->gev_done[g], 0));
         }
-        if (phase_events) PMB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+        if (phase_events) PMB_CUDA(cudaEventRecord(c->ev[2], bwd_stream));
         c->async_phase_events = phase_events;
-        PMB_CUDA(cudaEventRecord(c->ev_bwd_done, c->stream));
+        PMB_CUDA(cudaEventRecord(c->ev_bwd_done, bwd_stream));
         PMB_CUDA(cudaStreamWaitEvent(c->cstream, c->ev_bwd_done, 0));
         {
             const unsigned long long n_entries = (unsigned long long)P.n_nodes * (unsigned long long)c->T;
@@ -748,7 +786,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         }
         PMB_CUDA(cudaGetLastError());
         PMB_CUDA(cudaEventRecord(c->ev[3], c->cstream));
-        PMB_CUDA(cudaEventRecord(c->ev_compact_done, c->cstream));
+        PMB_CUDA(cudaEventRecord(c->ev_compact_done[parity], c->cstream));
         c->state_dirty = false;
         if (async) {  // status, overflow handling and timings wait for pmb_wait
             c->async_pending = true;
