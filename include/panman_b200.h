@@ -102,7 +102,8 @@ const char* pmb_last_error(const pmb_ctx* ctx);
  * "reserve_sms" (SMs the persistent kernels leave free, e.g. for an NCCL kernel running beside them; default 0),
  * "col_groups" (column-tile groups run on separate streams; default 1), "overlap" (1 [default]: set matrices up to 4 GB
  * are double-buffered so that the forward kernel of an asynchronous pass runs beside the backward kernel of the pass
- * before it; 0: one set matrix, passes strictly one after the other), "trace" (debug timeline). */
+ * before it; 0: one set matrix, passes strictly one after the other), "grid_pct" (share of the resident block slots a
+ * persistent kernel takes; 0 = automatic: 80 for overlapping asynchronous passes, 100 otherwise), "trace" (debug timeline). */
 int pmb_set_option(pmb_ctx* ctx, const char* key, int64_t value);
 
 /* Page-locked host memory for the caller's input buffers. pmb_run_nuc / pmb_upload_nuc accept any host pointer, but

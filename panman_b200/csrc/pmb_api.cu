@@ -103,6 +103,8 @@ struct pmb_ctx {
     cudaStream_t bstream = nullptr;
     cudaEvent_t ev_fwd_done = nullptr, ev_bwd_done = nullptr, ev_compact_done[2] = {nullptr, nullptr};
     DevBuf d_sets2;
+    int64_t opt_grid_pct = 0;             // persistent kernels take at most this share of the resident block slots (0 = auto)
+    int cur_grid_pct = 100;
     int64_t opt_overlap = 1;              // 1 = double-buffer the set matrix when it is small enough (see run_impl)
     unsigned int run_seq = 0;             // parity selects the ticket set of a run
     cudaStream_t merge_stream = nullptr;  // stream of the last pmb_merge_packed (never owned)
@@ -180,6 +182,12 @@ int32_t pick_chunk_nodes(const pmb_ctx* c) {
     int64_t want_chunks = std::max<int64_t>(1, (target_warps + c->T - 1) / std::max(1, c->T));
     int64_t n_internal = 0;
     for (int32_t v = 0; v < c->n_nodes; v++) n_internal += c->child_off[v + 1] > c->child_off[v];
+    // Few column tiles: more than ~160 chunks only deepen the chunk tree -- every level is a dependent hop between warps --
+    // and consecutive passes of such small problems overlap anyway (second set matrix), so the items they would add are
+    // not missed (measured, tools/sweep.py: 10k leaves x 15 tiles 0.201 -> 0.187 ms per pipelined pass at 62 instead of 31
+    // ops per chunk; 20k leaves x 30 tiles unchanged at ~126)
+    if (c->opt_target_items <= 0 && c->opt_overlap > 0 && size_t(n_internal) * size_t(c->T) * 4096 <= (size_t(4) << 30))
+        want_chunks = std::min<int64_t>(want_chunks, 160);
     int64_t k = n_internal / want_chunks;
     // never beyond 512: with thousands of column tiles there are items enough, and a warp walking thousands of ops in
     // one item overflows its parent-state stack into global memory (config 4: 18.8 ms with one 4 000-op chunk, 16.1 ms
@@ -248,6 +256,7 @@ int launch_kernel(pmb_ctx* c, cudaStream_t stream, K kernel, size_t smem, const 
         }
         const long long sms = std::max<long long>(1, c->n_sms - std::max<int64_t>(0, std::min<int64_t>(c->opt_reserve_sms, c->n_sms - 1)));
         long long resident = (long long)std::max(1, per_sm) * sms;
+        resident = std::max<long long>(sms, resident * std::max(1, std::min(100, c->cur_grid_pct)) / 100);
         blocks = unsigned(std::min<long long>(resident, (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
         // the ticket is zero: compact_copy_kernel of the previous run (or the initial clearing) left it so
     } else {
@@ -446,6 +455,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "target_items") c->opt_target_items = value;
     else if (k == "trace") c->opt_trace = value;
     else if (k == "overlap") c->opt_overlap = value;
+    else if (k == "grid_pct") c->opt_grid_pct = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
 }
@@ -714,6 +724,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     const int ticket_set = 64 * parity;  // the compaction of the run before resets the other set
     c->run_seq++;
     cudaStream_t const bwd_stream = G == 1 ? c->bstream : c->stream;
+    // Overlapping passes share the machine: each persistent kernel then takes 80 % of the block slots it could hold, so
+    // that the blocks of the pass behind it find room before it has drained completely (measured, tools/sweep.py: 20k x 30k
+    // 0.544 -> 0.538 ms, 10k x 15k 0.201 -> 0.191 ms per pipelined pass; alone, a kernel is 3-4 % slower at 80 %)
+    c->cur_grid_pct = c->opt_grid_pct > 0 ? int(c->opt_grid_pct) : (async && overlap ? 80 : 100);
     unsigned int* const run_error = rp.error;
     // the forward kernel may run beside the previous run's compaction, whose last block snapshots and resets the per-run
     // error words: its only status, the watchdog bit, goes straight to the sticky word
