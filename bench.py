@@ -399,7 +399,19 @@ def run_b200_arm(args):
     for _ in range(args.steps):
         g.run_async(algo_i)  # one C call per step: pass -> pack into rank 0's mailbox -> signal (-> merge on rank 0)
     ev1.record(lib_end_stream)
-    barrier()  # ends after the last merge on rank 0
+    if os.environ.get("PMB_BENCH_DEBUG"):
+        ta = time.perf_counter()
+        g.wait()
+        tb = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        tc = time.perf_counter()
+        torch.cuda.synchronize()
+        td = time.perf_counter()
+        print(f"[rank {rank}] enqueue {1e3 * (ta - t0):.3f} ms, g.wait {1e3 * (tb - ta):.3f}, dist.barrier {1e3 * (tc - tb):.3f}, "
+              f"sync {1e3 * (td - tc):.3f}, device {ev0.elapsed_time(ev1):.3f}", file=sys.stderr, flush=True)
+    else:
+        barrier()  # ends after the last merge on rank 0
     elapsed = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join()

@@ -613,9 +613,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     const size_t T = size_t(c->T);
     const size_t set_bytes_per = (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
     const size_t set_bytes = size_t(P.n_internal) * T * set_bytes_per;
-    // a second set matrix lets consecutive passes overlap (see bstream); only where it is cheap: the large problems run at
-    // the HBM roofline anyway and would pay tens of GB for it
-    const bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= (size_t(4) << 30);
+    // a second set matrix lets consecutive passes overlap (see bstream); only where it is cheap (up to 12 GB: that covers a
+    // quarter or an eighth of BASELINE.json's config 4 on 4 or 8 GPUs and config 5): the largest problems run at the HBM
+    // roofline anyway and would pay tens of GB for it
+    const bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= (size_t(12) << 30);
     if (set_bytes > c->d_sets.cap || (overlap && set_bytes > c->d_sets2.cap)) {  // cudaFree of a matrix a running pass uses
         PMB_CUDA(cudaStreamSynchronize(c->bstream));
         PMB_CUDA(cudaStreamSynchronize(c->cstream));
@@ -1078,7 +1079,7 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_mblock_sums.as<unsigned long long>());
     scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_mblock_sums.as<unsigned long long>(),
                                                            c->d_moff.as<long long>());
-    merge_copy_kernel<<<unsigned(((long long)N * 32 + 255) / 256), 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity,
+    merge_copy_kernel<<<unsigned(c->n_sms * 8), 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity,
                                                                                   c->d_moff.as<long long>(), c->d_mpos.as<int32_t>(),
                                                                                   c->d_mtc.as<uint8_t>());
     PMB_CUDA(cudaGetLastError());

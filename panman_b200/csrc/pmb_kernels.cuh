@@ -1658,35 +1658,36 @@ __global__ void merge_count_kernel(const unsigned char* packed, size_t shard_byt
     counts[v] = c;
 }
 
-// warp per node: the lanes first fetch the node's segment bounds in all shards at once (one round trip instead of one
-// per shard -- with 8 shards on the few SMs the pass kernels leave free this kernel was what limited rank 0), then the
-// segments are copied one after the other with the lanes across the records
+// One thread per OUTPUT record (grid stride): its node by binary search in the merged offsets, its shard by walking the
+// node's per-shard segment lengths. Per-node lists are very uneven -- the nodes next to the root of a gappy alignment hold
+// tens of thousands of records, most nodes a few dozen -- and the earlier warp-per-node copy spent a millisecond in the few
+// long ones (measured at 2 shards x 0.66 M records: 1.2 ms; rank 0's merge then no longer hid behind a 2 ms pass). Threads
+// of a warp mostly share node and shard, so the offset loads hit L1 and the record loads / stores coalesce.
 __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, long long cap,
                                   const long long* merged_off, int32_t* pos, uint8_t* type_code) {
-    int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (v >= n_nodes) return;
-    long long run = merged_off[v];
-    if (merged_off[v + 1] == run) return;
+    const long long total = merged_off[n_nodes];
     const size_t po = packed_pos_offset(n_nodes), to = packed_tc_offset(n_nodes, cap);
-    for (int k0 = 0; k0 < n_shards; k0 += 32) {
-        const int k = k0 + lane;
-        long long a = 0, len = 0;
-        if (k < n_shards && shard_ok(packed + k * shard_bytes, n_nodes, cap)) {
-            const long long* off = reinterpret_cast<const long long*>(packed + k * shard_bytes + 16);
-            a = off[v];
-            len = off[v + 1] - a;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int lo = 0, hi = n_nodes;  // the node v with merged_off[v] <= i < merged_off[v + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(merged_off + mid) <= i) lo = mid;
+            else hi = mid;
         }
-        const int nk = min(32, n_shards - k0);
-        for (int j = 0; j < nk; j++) {
-            const long long aj = __shfl_sync(FULL, a, j), lj = __shfl_sync(FULL, len, j);
-            const unsigned char* sh = packed + (size_t)(k0 + j) * shard_bytes;
-            const int32_t* sp = reinterpret_cast<const int32_t*>(sh + po) + aj;
-            const uint8_t* st = sh + to + aj;
-            for (long long i = lane; i < lj; i += 32) {
-                pos[run + i] = sp[i];
-                type_code[run + i] = st[i];
+        const int v = lo;
+        long long local = i - __ldg(merged_off + v);
+        for (int k = 0; k < n_shards; k++) {
+            const unsigned char* sh = packed + (size_t)k * shard_bytes;
+            if (!shard_ok(sh, n_nodes, cap)) continue;
+            const long long* off = reinterpret_cast<const long long*>(sh + 16);
+            const long long a = off[v], len = off[v + 1] - a;
+            if (local < len) {
+                pos[i] = reinterpret_cast<const int32_t*>(sh + po)[a + local];
+                type_code[i] = sh[to + a + local];
+                break;
             }
-            run += lj;
+            local -= len;
         }
     }
 }
