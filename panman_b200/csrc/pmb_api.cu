@@ -298,7 +298,7 @@ int launch_pass(pmb_ctx* c, cudaStream_t stream, int ticket_slot, const RunParam
     const TreeProgram& P = c->prog;
     const size_t fwd_smem = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 4) * 32 + FWD_META_U4) * sizeof(uint4);
     const size_t fwd_smem_s = size_t(WARPS_PER_BLOCK) * (FWD_DEPTH * (2 + 5) * 32 + FWD_META_U4) * sizeof(uint4);
-    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (4 + 2) * 32 + BWD_META_U4 + BWD_STACK_U4) * sizeof(uint4);
+    const size_t bwd_smem_f = size_t(WARPS_PER_BLOCK) * FITCH_BWD_PER_WARP * sizeof(uint4);  // + the mbarriers of the bulk variant
     const size_t bwd_smem_s = size_t(WARPS_PER_BLOCK) * (BWD_DEPTH * (8 + 2) * 32 + BWD_META_U4 + BWD_STACK_U4) * sizeof(uint4);
     if (algo == PMB_ALGO_FITCH) {
         if (P.n_chain_segments > 0)

@@ -170,13 +170,18 @@ __device__ __noinline__ bool wait_flag_slow(const unsigned* flag, unsigned epoch
         }
         *waited += unsigned(global_ns() - t0);
     }
-    return __shfl_sync(FULL, ok, 0) != 0;
+    ok = __shfl_sync(FULL, ok, 0);
+    __syncwarp();  // the other lanes' reads of the published rows are ordered behind lane 0's acquire
+    return ok != 0;
 }
 __device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned epoch, unsigned* error, int lane, TraceItem& tr) {
     unsigned v = 0;
     if (lane == 0) v = ld_acquire(flag);
     v = __shfl_sync(FULL, v, 0);
-    if (v == epoch) return true;
+    if (v == epoch) {
+        __syncwarp();  // a shuffle is no memory ordering: the barrier is what puts every lane's reads behind the acquire
+        return true;
+    }
     return wait_flag_slow(flag, epoch, error, lane, &tr.waited);
 }
 // Forward dependencies: a chunk lists the external rows it reads in consumption order (Chunk::dep_*), and an
@@ -211,6 +216,7 @@ __device__ __forceinline__ bool wait_dep(const RunParams& p, const Chunk& ck, co
         }
     }
     if (spins) tr.waited += unsigned(global_ns() - t0);
+    __syncwarp();  // each flag was acquired by ONE lane; all lanes read the rows
     return true;
 }
 // row of a set reference: direct, or through the dependency list for an external ref
@@ -310,6 +316,42 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {  // at most n gro
     case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
     default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
     }
+}
+
+// ------------------------------------------------------------------ bulk-copy ring (experiment, -DPMB_BULK=1)
+// The same ring filled by the bulk asynchronous copy unit instead of per-lane LDGSTS: ONE elected lane issues one
+// cp.async.bulk per row (a set row is 2 KB contiguous in the tile-major layout, a leaf row 512 B) and the bytes are
+// counted on an mbarrier per stage; all lanes wait on the barrier's phase. Fewer instructions per op (1 + rows instead of
+// 32 x rows + commit + wait), at the price of a warp barrier before a stage is refilled (the per-lane ring needs none:
+// every lane copies and reads only its own 16 bytes). Built with `make VARIANT=_bulk EXTRA=-DPMB_BULK=1`; result in
+// profiles/r02_summary.md.
+#ifndef PMB_BULK
+#define PMB_BULK 0
+#endif
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // Measured on B200 (tools/sweep.py, profiles/r01_v8_summary.md): shallower rings and smaller windows win because shared
@@ -749,6 +791,21 @@ __device__ __forceinline__ void bwd_issue(const BwdMeta& m, const TileCtx& tc, u
     cp_async_commit();
 }
 
+// bulk variant: `stage_base` / `sets_base` / `leaf_base` carry NO lane offset; the elected lane issues the rows of one op
+template <int J>
+__device__ __forceinline__ void bwd_issue_bulk(const BwdMeta& m, const uint4* sets_base, const uint4* leaf_base, uint4* stage_base,
+                                               unsigned long long* bar, int op, int lane) {
+    __syncwarp();  // every lane has consumed what this stage held
+    if (lane == 0) {
+        const int4 b1 = m.ops[2 * (op - m.lo) + 1];  // n_leaves, flags, leaf0 slot, leaf1 slot
+        const int nl = min(b1.x, 2);
+        mbar_expect_tx(bar, unsigned(J * 512 + nl * 512));
+        bulk_copy(stage_base, sets_base + (size_t)op * (J * 32), J * 512, bar);
+        if (nl > 0) bulk_copy(stage_base + J * 32, leaf_base + (size_t)b1.z * 32, 512, bar);
+        if (nl > 1) bulk_copy(stage_base + (J + 1) * 32, leaf_base + (size_t)b1.w * 32, 512, bar);
+    }
+}
+
 // parent's assigned state from its parked slot (possibly written by another chunk)
 __device__ __forceinline__ bool bwd_parent_slot(const RunParams& p, const BwdHead& h, int tile, int lane, uint32_t P[4],
                                                 uint32_t& pvis, TraceItem& tr) {
@@ -817,16 +874,23 @@ __device__ __forceinline__ void bwd_finish_op(const RunParams& p, const BwdMeta&
 }
 
 // ------------------------------------------------------------------ Fitch backward + mutation detection
-constexpr int FITCH_BWD_STAGE = (4 + 2) * 32, FITCH_BWD_PER_WARP = BWD_DEPTH * FITCH_BWD_STAGE + BWD_META_U4 + BWD_STACK_U4;
+constexpr int FITCH_BWD_STAGE = (4 + 2) * 32,
+              FITCH_BWD_PER_WARP = BWD_DEPTH * FITCH_BWD_STAGE + BWD_META_U4 + BWD_STACK_U4 + (PMB_BULK ? (BWD_DEPTH * 8 + 15) / 16 : 0);
+// `phases`: bit s = the parity the next wait on stage s's mbarrier expects (bulk variant; lives across items)
 template <bool SPEC>
 __device__ __forceinline__ bool fitch_backward_item(const RunParams& p, uint4* ring, StageCursor& sc, int chunk, int tile, int lane,
-                                                    TraceItem& tr) {
+                                                    TraceItem& tr, unsigned& phases) {
     constexpr int J = 4, STAGE = FITCH_BWD_STAGE;
     BwdMeta m;
     m.ops = reinterpret_cast<int4*>(ring + BWD_DEPTH * STAGE);
     m.leaves = reinterpret_cast<int2*>(m.ops + 2 * META_OPS);
     uint32_t* stack = reinterpret_cast<uint32_t*>(ring + BWD_DEPTH * STAGE + BWD_META_U4);
     uint4* const ring_l = ring + lane;
+#if PMB_BULK
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(ring + BWD_DEPTH * STAGE + BWD_META_U4 + BWD_STACK_U4);
+    const uint4* const sets_base = p.sets + (size_t)tile * p.n_ops * (J * 32);
+    const uint4* const leaf_base = p.leaf_planes + (size_t)tile * p.n_rows * 32;
+#endif
     {
         const Chunk ck = p.chunks[chunk];
         const TileCtx tc = tile_ctx<J>(p, tile, lane);
@@ -862,7 +926,11 @@ __device__ __forceinline__ bool fitch_backward_item(const RunParams& p, uint4* r
         const int hi = range == 0 ? resolved : last;
         const int lo = (range == 1 && resolved >= 0) ? resolved : ck.op_begin;
         bwd_meta_load(p, m, hi, lo, lane);
+#if PMB_BULK
+        for (int i = 0; i < BWD_DEPTH && hi - i >= lo; i++) bwd_issue_bulk<J>(m, sets_base, leaf_base, ring + i * STAGE, bars + i, hi - i, lane);
+#else
         for (int i = 0; i < BWD_DEPTH && hi - i >= lo; i++) bwd_issue<J>(m, tc, ring_l + i * STAGE, hi - i);
+#endif
         int stage = 0;
         for (int op = hi; op >= lo; op--) {
             if (op - BWD_DEPTH < m.lo && m.lo > lo) bwd_meta_load(p, m, op, lo, lane);
@@ -883,7 +951,12 @@ __device__ __forceinline__ bool fitch_backward_item(const RunParams& p, uint4* r
             } else if (h.b0.y >= 0) {
                 if (!bwd_parent_slot(p, h, tile, lane, P, pvis, tr)) return false;
             }
+#if PMB_BULK
+            mbar_wait(bars + stage, (phases >> stage) & 1u);
+            phases ^= 1u << stage;
+#else
             cp_async_wait_stage<BWD_DEPTH>(op - lo);
+#endif
             uint4* st = ring_l + stage * STAGE;
             uint32_t S[16];
 #pragma unroll
@@ -916,7 +989,11 @@ __device__ __forceinline__ bool fitch_backward_item(const RunParams& p, uint4* r
             if (own_only) emit(p, sc, h.b0.x, tile, lane, vis & differs4(F, P), P, F);
             else bwd_finish_op(p, m, tc, sc, h, st + J * 32, stack, tile, lane, P, F, vis, false, !given);
             // this stage has been consumed by this lane: refill it for the op BWD_DEPTH further down
+#if PMB_BULK
+            if (op - BWD_DEPTH >= lo) bwd_issue_bulk<J>(m, sets_base, leaf_base, ring + stage * STAGE, bars + stage, op - BWD_DEPTH, lane);
+#else
             if (op - BWD_DEPTH >= lo) bwd_issue<J>(m, tc, st, op - BWD_DEPTH);
+#endif
             stage = (stage + 1 == BWD_DEPTH) ? 0 : stage + 1;
             accF[0] = F[0]; accF[1] = F[1]; accF[2] = F[2]; accF[3] = F[3];
             accVis = vis;
@@ -932,12 +1009,23 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) fitch_backward_kernel(Ru
     extern __shared__ uint4 smem[];
     const int lane = threadIdx.x & 31;
     uint4* ring = smem + (size_t)(threadIdx.x >> 5) * FITCH_BWD_PER_WARP;
+    unsigned phases = 0;
+#if PMB_BULK
+    {
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + BWD_DEPTH * FITCH_BWD_STAGE + BWD_META_U4 + BWD_STACK_U4);
+        if (lane == 0) {
+            for (int s = 0; s < BWD_DEPTH; s++) mbar_init(bars + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+#endif
     ItemIter it;
     TraceItem tr;
     StageCursor sc;
     int chunk, tile;
     while (next_item(p, it, chunk_begin, n_chunks, chunk, tile, lane, tr))
-        if (!fitch_backward_item<SPEC>(p, ring, sc, chunk, tile, lane, tr)) return;
+        if (!fitch_backward_item<SPEC>(p, ring, sc, chunk, tile, lane, tr, phases)) return;
 }
 
 // ------------------------------------------------------------------ Sankoff forward
