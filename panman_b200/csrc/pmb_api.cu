@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,22 +18,58 @@ using namespace pmb;
 
 namespace {
 
+// PMB_DEBUG_CANARY=1 (environment, read once): every device buffer gets 256 guard bytes on either side filled with 0xC5 and
+// a body poisoned with 0xAB instead of whatever the allocator returns; pmb_debug_check_canaries() counts guard bytes that
+// changed. compute-sanitizer is not available on every pool: this is the library's own out-of-bounds-write / uninitialised-
+// read check (tools/sanitize_small.py runs every kernel path under it and compares the results with the oracle).
+struct DevBuf;
+static bool g_canary = getenv("PMB_DEBUG_CANARY") != nullptr && getenv("PMB_DEBUG_CANARY")[0] == '1';
+static std::vector<DevBuf*> g_canary_bufs;
+constexpr size_t CANARY = 256;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    void* raw = nullptr;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
+        release();
+        if (!g_canary) {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e == cudaSuccess) cap = bytes;
+            return e;
+        }
+        const size_t body = (bytes + 255) / 256 * 256;
+        cudaError_t e = cudaMalloc(&raw, body + 2 * CANARY);
+        if (e != cudaSuccess) return e;
+        cudaMemset(raw, 0xC5, CANARY);
+        cudaMemset(static_cast<char*>(raw) + CANARY, 0xAB, body);
+        cudaMemset(static_cast<char*>(raw) + CANARY + body, 0xC5, CANARY);
+        cudaDeviceSynchronize();
+        p = static_cast<char*>(raw) + CANARY;
+        cap = bytes;
+        g_canary_bufs.push_back(this);
+        return cudaSuccess;
     }
     void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
+        if (raw) {
+            cudaFree(raw);
+            g_canary_bufs.erase(std::remove(g_canary_bufs.begin(), g_canary_bufs.end(), this), g_canary_bufs.end());
+        } else if (p) {
+            cudaFree(p);
+        }
+        p = raw = nullptr;
         cap = 0;
+    }
+    long long bad_guard_bytes() const {
+        if (!raw) return 0;
+        const size_t body = (cap + 255) / 256 * 256;
+        std::vector<unsigned char> g(2 * CANARY);
+        cudaMemcpy(g.data(), raw, CANARY, cudaMemcpyDeviceToHost);
+        cudaMemcpy(g.data() + CANARY, static_cast<char*>(raw) + CANARY + body, CANARY, cudaMemcpyDeviceToHost);
+        long long bad = 0;
+        for (unsigned char c : g) bad += c != 0xC5;
+        return bad;
     }
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
@@ -1017,6 +1054,16 @@ long long pmb_debug_trace(const pmb_ctx* c, unsigned long long* out, long long m
     long long n = std::min<long long>(max_words, (long long)c->h_trace.size());
     std::memcpy(out, c->h_trace.data(), size_t(n) * sizeof(unsigned long long));
     return n;
+}
+
+// Debug only (not part of include/panman_b200.h): with PMB_DEBUG_CANARY=1, the number of guard bytes around ALL live device
+// buffers of the process that no longer hold their fill value (0 = no kernel wrote outside its buffers); -1 without canaries.
+long long pmb_debug_check_canaries(void) {
+    if (!g_canary) return -1;
+    cudaDeviceSynchronize();
+    long long bad = 0;
+    for (const DevBuf* b : g_canary_bufs) bad += b->bad_guard_bytes();
+    return bad;
 }
 
 void* pmb_stream(pmb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }

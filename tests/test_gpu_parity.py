@@ -212,9 +212,10 @@ def _sorted_within_nodes(res):
 @pytest.mark.parametrize("name,slice_cols", [("caterpillar100k", 2048), ("ecoli4k", 16384)])
 def test_full_size_deep_and_wide_configs(port, name, slice_cols):
     """BASELINE.json configs[4] (100k-leaf caterpillar-heavy tree x 30k columns: depth, chain segments) and configs[3]
-    (4k leaves x 5M columns: volume, 4883 column tiles) at FULL size on one GPU. The oracle checks a column slice taken
-    from the middle -- the generator is stateless per cell, so the slice is reproduced in isolation -- and the whole
-    result must be position-sorted per node and consistent in its counts."""
+    (4k leaves x 5M columns: volume, 4883 column tiles) at FULL size on one GPU, Fitch AND Sankoff (the latter with the root
+    forced to leaf 0's character, as --reference does: SURVEY 8d). The oracle checks a column slice taken from the middle --
+    the generator is stateless per cell, so the slice is reproduced in isolation -- and the whole result must be
+    position-sorted per node and consistent in its counts."""
     import torch
 
     cfg = synth.CONFIGS[name]
@@ -222,26 +223,31 @@ def test_full_size_deep_and_wide_configs(port, name, slice_cols):
     spec = synth.MsaSpec(cfg["seed"], cfg["p_sub"], cfg["f_gap"], cfg["p_N"])
     C = cfg["n_cols"]
     codes4, pc = synth.simulate_msa(tree, 0, C, spec, device="cuda")
-    c = pb.Context(0)
-    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
-    c.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc)
-    del codes4
-    torch.cuda.empty_cache()
-    t = c.run_resident(0)
-    res = c.download()
-    assert res.n_mut == res.node_offsets[-1] == len(res.pos) and t.total_ms > 0
-    assert res.pos.min() >= 0 and res.pos.max() < C
-    assert _sorted_within_nodes(res)
+    ro_full = synth.unpack_nibbles(codes4[:1], C)[0].to(torch.int8).contiguous()  # leaf 0's character per column
     a = (C // 2 // 1024) * 1024 + 96          # not tile aligned on purpose
     b = a + slice_cols
     s4, spc = synth.simulate_msa(tree, a, b, spec, device="cuda")
     codes = synth.unpack_nibbles(s4, b - a).cpu().numpy()
     # the slice's parent codes are those of the full run (consensus = first non-gap leaf, a per-column rule)
     assert np.array_equal(spc.cpu().numpy(), pc[a:b].cpu().numpy())
-    want, _ = port.run(tree, 0, codes, spc.cpu().numpy(), n_threads=16)
-    off, pos, tc = _slice_lists(res, tree.n_nodes, a, b)
-    assert np.array_equal(off, want.node_offsets)
-    assert np.array_equal(pos, want.pos + a) and np.array_equal(tc, want.type_code)
+    c = pb.Context(0)
+    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    for algo in (0, 1):
+        c.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro_full if algo == 1 else None)
+        if algo == 1:
+            del codes4
+            torch.cuda.empty_cache()
+        t = c.run_resident(algo)
+        res = c.download()
+        assert res.n_mut == res.node_offsets[-1] == len(res.pos) and t.total_ms > 0
+        assert res.pos.min() >= 0 and res.pos.max() < C
+        assert _sorted_within_nodes(res)
+        ro = codes[0].astype(np.int8) if algo == 1 else None
+        want, _ = port.run(tree, algo, codes, spc.cpu().numpy(), ro, None, None, 0, n_threads=16)
+        off, pos, tc = _slice_lists(res, tree.n_nodes, a, b)
+        assert np.array_equal(off, want.node_offsets), (name, algo)
+        assert np.array_equal(pos, want.pos + a) and np.array_equal(tc, want.type_code), (name, algo)
+        del res
     c.close()
 
 

@@ -1,8 +1,15 @@
 #!/usr/bin/env python
-"""Small end-to-end cases for compute-sanitizer (memcheck): every kernel path once -- Fitch / Sankoff, plain / presence
-mask / block mode / states, chain segments (speculating and waiting), level schedule, overflow retry, shard merge."""
+"""Small end-to-end cases, every kernel path once -- Fitch / Sankoff, plain / presence mask / block mode / states, chain
+segments (speculating and waiting), level schedule, overflow retry, shard pack / merge, run-merge, the multi-rank group --
+for compute-sanitizer where the pool allows it, and always under the library's own guard bytes: PMB_DEBUG_CANARY=1 puts 256
+guard bytes around every device buffer and poisons its body, pmb_debug_check_canaries() counts the guard bytes a kernel
+overwrote (out-of-bounds writes), and the comparison with the oracle catches reads of memory nobody initialised.
+  python tools/sanitize_small.py > profiles/r02_canary_check.log"""
+import ctypes
 import os
 import sys
+
+os.environ.setdefault("PMB_DEBUG_CANARY", "1")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -60,9 +67,41 @@ def main():
     for k in range(2):
         ctx.pack_result(buf[k * ctx.packed_bytes(cap):(k + 1) * ctx.packed_bytes(cap)], cap)
     ctx.merge_packed(2, buf, cap)
+    ctx.merge_status()
+    ctx.merge_runs(source=1)
+    ctx.run_resident(0)
+    ctx.merge_runs(source=0)
     torch.cuda.synchronize()
+    lib = pb.load_library()
+    lib.pmb_debug_check_canaries.restype = ctypes.c_longlong
+    bad = lib.pmb_debug_check_canaries()
+    print(f"single-context paths: guard bytes overwritten = {bad} (-1 = canaries off)")
+    assert bad in (0, -1)
     ctx.close()
-    print("sanitize_small ok")
+    # column-sharded group: three ranks on this GPU, asynchronous steps back to back (mailbox slots of both parities, the
+    # stream-memory-operation hand-shake, the record-parallel merge), then the run-merge of the merged lists
+    codes = rng.integers(0, 5, size=(tree.n_leaves, 3500)).astype(np.uint8)
+    codes = np.where(rng.random(codes.shape) < 0.9, codes[:1], codes).astype(np.uint8)
+    pc = codes[0].copy()
+    c4 = pb.pack_nibbles(codes)
+    for algo in (0, 1):
+        want, _ = port.run(tree, algo, codes, pc, codes[0].astype(np.int8) if algo else None, None, None, 0, n_threads=2)
+        g = pb.Group([0, 0, 0])
+        g.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+        res = g.run_nuc(algo, 3500, tree.n_leaves, c4, c4.shape[1], pc, codes[0].astype(np.int8) if algo else None)
+        assert np.array_equal(res.pos, want.pos) and np.array_equal(res.type_code, want.type_code)
+        g.upload(3500, tree.n_leaves, c4, c4.shape[1], pc, codes[0].astype(np.int8) if algo else None)
+        for _ in range(4):
+            g.run_async(algo)
+        g.wait()
+        res = g.download()
+        assert np.array_equal(res.pos, want.pos) and np.array_equal(res.type_code, want.type_code)
+        g.merge_runs()
+        bad = ctypes.c_longlong(pb.load_library().pmb_debug_check_canaries()).value
+        print(f"group algo {algo}: guard bytes overwritten = {bad}")
+        assert bad in (0, -1)
+        g.close()
+    print("sanitize_small ok; PMB_DEBUG_CANARY =", os.environ.get("PMB_DEBUG_CANARY"))
 
 
 if __name__ == "__main__":
