@@ -497,8 +497,8 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     return PMB_OK;
 }
 
-int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child_offsets, const int32_t* child_index,
-                 const int32_t* leaf_row) {
+static int set_tree_impl(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child_offsets, const int32_t* child_index,
+                         const int32_t* leaf_row) {
     if (!c) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device (pmb_create failed); there is no CPU fallback");
     if (n_nodes < 2 || !child_offsets || !child_index || !leaf_row) return fail(c, PMB_ERR_INVALID, "bad tree arguments");
@@ -517,6 +517,21 @@ int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child
     c->have_input = false;
     c->have_result = false;
     return PMB_OK;
+}
+
+// The C ABI never lets an exception out: host allocations (tree program, staging vectors) that fail come back as codes.
+#define PMB_GUARDED(c, expr)                                                       \
+    try {                                                                          \
+        return (expr);                                                             \
+    } catch (const std::bad_alloc&) {                                              \
+        return fail((c), PMB_ERR_OOM, "out of host memory");                       \
+    } catch (const std::exception& ex) {                                           \
+        return fail((c), PMB_ERR_INVALID, std::string("internal: ") + ex.what()); \
+    }
+
+int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child_offsets, const int32_t* child_index,
+                 const int32_t* leaf_row) {
+    PMB_GUARDED(c, set_tree_impl(c, n_nodes, root, child_offsets, child_index, leaf_row))
 }
 
 static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
@@ -627,15 +642,15 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
 int pmb_upload_nuc(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
                    const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
                    const int8_t* fwd_root_ref, int64_t col_base) {
-    return upload_impl(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override, fwd_root_ref,
-                       col_base, true);
+    PMB_GUARDED(c, upload_impl(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override,
+                               fwd_root_ref, col_base, true))
 }
 
 int pmb_upload_nuc_async(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
                          const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
                          const int8_t* fwd_root_ref, int64_t col_base) {
-    return upload_impl(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override, fwd_root_ref,
-                       col_base, false);
+    PMB_GUARDED(c, upload_impl(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override,
+                               fwd_root_ref, col_base, false))
 }
 
 static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
@@ -764,8 +779,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     cudaStream_t const bwd_stream = G == 1 ? c->bstream : c->stream;
     // Overlapping passes share the machine: each persistent kernel then takes 80 % of the block slots it could hold, so
     // that the blocks of the pass behind it find room before it has drained completely (measured, tools/sweep.py: 20k x 30k
-    // 0.544 -> 0.538 ms, 10k x 15k 0.201 -> 0.191 ms per pipelined pass; alone, a kernel is 3-4 % slower at 80 %)
-    c->cur_grid_pct = c->opt_grid_pct > 0 ? int(c->opt_grid_pct) : (async && overlap ? 80 : 100);
+    // 0.544 -> 0.538 ms, 10k x 15k 0.201 -> 0.191 ms, 4k x 625k 2.048 -> 2.012 ms per pipelined pass; alone, a kernel is
+    // 3-4 % slower at 80 %). Deep trees keep the full grid: their chain segments need every slot to run side by side
+    // (100k-leaf caterpillar x 30k: 2.569 ms at 100 %, 2.591 ms at 80 %).
+    c->cur_grid_pct = c->opt_grid_pct > 0 ? int(c->opt_grid_pct) : (async && overlap && P.n_chain_segments == 0 ? 80 : 100);
     unsigned int* const run_error = rp.error;
     // the forward kernel may run beside the previous run's compaction, whose last block snapshots and resets the per-run
     // error words: its only status, the watchdog bit, goes straight to the sticky word
@@ -1031,8 +1048,8 @@ int pmb_run_nuc(pmb_ctx* c, int algo, int64_t n_cols, int32_t n_rows, const uint
     return pmb_download(c, out);
 }
 
-int pmb_run_block(pmb_ctx* c, int algo, int64_t n_blocks, int32_t n_rows, const uint8_t* leaf_block_state, const int8_t* root_override,
-                  pmb_result* out) {
+static int run_block_impl(pmb_ctx* c, int algo, int64_t n_blocks, int32_t n_rows, const uint8_t* leaf_block_state,
+                          const int8_t* root_override, pmb_result* out) {
     if (!c || !leaf_block_state || !out || n_blocks <= 0 || n_rows <= 0) return c ? fail(c, PMB_ERR_INVALID, "bad block arguments") : PMB_ERR_INVALID;
     const int64_t stride = (n_blocks + 1) / 2;
     std::vector<uint8_t> codes4(size_t(n_rows) * size_t(stride), 0), parent(size_t(n_blocks), 0);  // parent state: absent
@@ -1044,6 +1061,11 @@ int pmb_run_block(pmb_ctx* c, int algo, int64_t n_blocks, int32_t n_rows, const 
         }
     return pmb_run_nuc(c, algo, n_blocks, n_rows, codes4.data(), stride, nullptr, parent.data(), root_override, nullptr, 0,
                        PMB_FLAG_BLOCK_MODE, out);
+}
+
+int pmb_run_block(pmb_ctx* c, int algo, int64_t n_blocks, int32_t n_rows, const uint8_t* leaf_block_state, const int8_t* root_override,
+                  pmb_result* out) {
+    PMB_GUARDED(c, run_block_impl(c, algo, n_blocks, n_rows, leaf_block_state, root_override, out))
 }
 
 // Debug only (not part of include/panman_b200.h): the per-item timeline of the last run made with option "trace".

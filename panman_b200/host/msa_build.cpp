@@ -210,7 +210,7 @@ pmh_build::~pmh_build() { pin_release(codes4, codes_cached); }
 
 extern "C" {
 
-pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len) {
+static pmh_tree* tree_from_newick_impl(const char* newick, char* err, size_t err_len) {
     if (!newick) { set_err(err, err_len, "null newick"); return nullptr; }
     pmh_tree* t = new pmh_tree();
     std::string e = pmh::parse_newick(newick, &t->t);
@@ -232,7 +232,7 @@ const int32_t* pmh_tree_child_index(const pmh_tree* t) { return t->t.child_idx.d
 const int32_t* pmh_tree_leaf_row(const pmh_tree* t) { return t->t.leaf_row.data(); }
 int pmh_tree_has_polytomy(const pmh_tree* t) { return t->t.has_polytomy() ? 1 : 0; }
 
-pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newick, const char* reference_c, int low_mem_mode,
+static pmh_build* msa_prepare_impl(const char* fasta, size_t fasta_len, const char* newick, const char* reference_c, int low_mem_mode,
                            char* err, size_t err_len) {
     if (!fasta || !newick) { set_err(err, err_len, "null argument"); return nullptr; }
     const std::string reference = reference_c ? reference_c : "";
@@ -357,7 +357,7 @@ pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newi
     return b;
 }
 
-int pmh_msa_run(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
+static int msa_run_impl(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
     if (!ctx || !b) { set_err(err, err_len, "null argument"); return PMB_ERR_INVALID; }
     auto fail = [&](const std::string& m) -> int {
         set_err(err, err_len, m);
@@ -426,6 +426,35 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
     return b;
 }
 
+// The C ABI never lets an exception out (a bad input file must come back as an error, not abort the host process).
+pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len) {
+    try {
+        return tree_from_newick_impl(newick, err, err_len);
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("Newick: ") + ex.what());
+        return nullptr;
+    }
+}
+pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newick, const char* reference, int low_mem_mode, char* err,
+                           size_t err_len) {
+    try {
+        return msa_prepare_impl(fasta, fasta_len, newick, reference, low_mem_mode, err, err_len);
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("MSA input: ") + ex.what());
+        return nullptr;
+    }
+}
+int pmh_msa_run(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
+    try {
+        return msa_run_impl(ctx, b, err, err_len);
+    } catch (const std::bad_alloc&) {
+        set_err(err, err_len, "out of host memory");
+        return PMB_ERR_OOM;
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("pmh_msa_run: ") + ex.what());
+        return PMB_ERR_INVALID;
+    }
+}
 void pmh_build_free(pmh_build* b) { delete b; }
 void pmh_set_reader_parallel_bytes(int64_t bytes) { g_reader_parallel_bytes = bytes < 0 ? 0 : size_t(bytes); }
 int64_t pmh_build_n_cols(const pmh_build* b) { return b->n_cols; }
