@@ -168,7 +168,7 @@ def host_threads():
 
 
 def sample_columns(n_leaves, n_cols):
-    return int(min(n_cols, 65536, max(512, 400_000_000 // n_leaves)))  # bounded by host memory
+    return int(min(n_cols, 262144, max(512, 1_200_000_000 // n_leaves)))  # bounded by host memory (about 1 GB of codes)
 
 
 # ----------------------------------------------------------------------------- reference arm
