@@ -169,7 +169,7 @@ struct pmb_ctx {
     // work + result
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
     DevBuf d_mcounts, d_moff, d_mpos, d_mtc;  // merged shards
-    DevBuf d_rm_counts, d_rm_off, d_rm_pos, d_rm_info, d_rm_nucs, d_rm_wire;  // run-merge (pmb_merge_runs)
+    DevBuf d_rm_counts, d_rm_off, d_rm_pos, d_rm_info, d_rm_nucs, d_rm_wire, d_rm_flags, d_rm_oidx;  // run-merge (pmb_merge_runs)
     DevBuf d_col_break;
     bool have_col_break = false;
     HostBuf h_rm_off, h_rm_pos, h_rm_info, h_rm_nucs, h_rm_wire;
@@ -433,7 +433,7 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
-                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums})
+                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
                            &c->h_rm_info, &c->h_rm_nucs, &c->h_rm_wire}) b->release();
@@ -1215,29 +1215,36 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     const uint8_t* tc = source == 0 ? c->d_tc.as<uint8_t>() : c->d_mtc.as<uint8_t>();
     // pieces <= records; the record count of merged shards is only known on the device, their capacity on the host
     const size_t cap = std::max<size_t>(1, source == 0 ? size_t(c->n_mut) : c->d_mtc.cap);
-    const int scan_blocks = (N + SCAN_TILE - 1) / SCAN_TILE;
-    const bool grow = size_t(N) * sizeof(unsigned int) > c->d_rm_counts.cap || size_t(N + 1) * sizeof(long long) > c->d_rm_off.cap ||
-                      cap * sizeof(int32_t) > c->d_rm_pos.cap || cap > c->d_rm_info.cap || cap * sizeof(uint32_t) > c->d_rm_nucs.cap ||
-                      cap * sizeof(uint32_t) > c->d_rm_wire.cap;
+    const size_t n_blocks = (cap + RM_BLOCK - 1) / RM_BLOCK;  // cap >= the record count (known on the device for merged shards)
+    const size_t scratch_bytes = n_blocks * (8 + 8 + 8 + 4) + 64;
+    const bool grow = size_t(N + 1) * sizeof(long long) > c->d_rm_off.cap || cap * sizeof(int32_t) > c->d_rm_pos.cap ||
+                      cap > c->d_rm_info.cap || cap * sizeof(uint32_t) > c->d_rm_nucs.cap || cap * sizeof(uint32_t) > c->d_rm_wire.cap ||
+                      cap > c->d_rm_flags.cap || cap * sizeof(long long) > c->d_rm_oidx.cap || scratch_bytes > c->d_rm_counts.cap;
     if (grow && c->rm_stream) PMB_CUDA(cudaStreamSynchronize(c->rm_stream));
-    PMB_CUDA(c->d_rm_counts.ensure(size_t(N) * sizeof(unsigned int)));
     PMB_CUDA(c->d_rm_off.ensure(size_t(N + 1) * sizeof(long long)));
     PMB_CUDA(c->d_rm_pos.ensure(cap * sizeof(int32_t)));
     PMB_CUDA(c->d_rm_info.ensure(cap));
     PMB_CUDA(c->d_rm_nucs.ensure(cap * sizeof(uint32_t)));
     PMB_CUDA(c->d_rm_wire.ensure(cap * sizeof(uint32_t)));
-    DevBuf& sums = source == 0 ? c->d_block_sums : c->d_mblock_sums;
-    PMB_CUDA(sums.ensure(size_t(scan_blocks) * sizeof(unsigned long long)));
-    const unsigned blocks = unsigned(((long long)N * 32 + 255) / 256);
+    PMB_CUDA(c->d_rm_flags.ensure(cap));
+    PMB_CUDA(c->d_rm_oidx.ensure(cap * sizeof(long long)));
+    PMB_CUDA(c->d_rm_counts.ensure(scratch_bytes));
+    long long* last = c->d_rm_counts.as<long long>();
+    long long* carry = last + n_blocks;
+    unsigned long long* base = reinterpret_cast<unsigned long long*>(carry + n_blocks);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(base + n_blocks);
+    uint8_t* flags = c->d_rm_flags.as<uint8_t>();
     const uint8_t* brk = (source == 0 && c->have_col_break) ? c->d_col_break.as<uint8_t>() : nullptr;
-    merge_runs_kernel<false><<<blocks, 256, 0, st>>>(off, pos, tc, N, c->d_rm_counts.as<unsigned int>(), nullptr, nullptr, nullptr, nullptr,
-                                                    nullptr, brk, c->col_base);
-    scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_rm_counts.as<unsigned int>(), N, sums.as<unsigned long long>());
-    scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_rm_counts.as<unsigned int>(), N, sums.as<unsigned long long>(),
-                                                          c->d_rm_off.as<long long>());
-    merge_runs_kernel<true><<<blocks, 256, 0, st>>>(off, pos, tc, N, nullptr, c->d_rm_off.as<long long>(), c->d_rm_pos.as<int32_t>(),
-                                                   c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(), c->d_rm_wire.as<uint32_t>(), brk,
-                                                   c->col_base);
+    PMB_CUDA(cudaMemsetAsync(flags, 0, cap, st));
+    rm_mark_starts_kernel<<<(N + 255) / 256, 256, 0, st>>>(off, N, flags);
+    rm_block_last_kernel<<<unsigned(n_blocks), RM_THREADS, 0, st>>>(off, N, pos, tc, flags, brk, c->col_base, last);
+    rm_scan_max_kernel<<<1, 1024, 0, st>>>(last, int(n_blocks), carry);
+    rm_flags_kernel<<<unsigned(n_blocks), RM_THREADS, 0, st>>>(off, N, pos, tc, flags, brk, c->col_base, carry, counts);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(counts, int(n_blocks), base, c->d_rm_off.as<long long>() + N);
+    rm_fill_kernel<<<unsigned(n_blocks), RM_THREADS, 0, st>>>(off, N, pos, tc, flags, base, c->d_rm_oidx.as<long long>(),
+                                                             c->d_rm_pos.as<int32_t>(), c->d_rm_info.as<uint8_t>(), c->d_rm_nucs.as<uint32_t>(),
+                                                             c->d_rm_wire.as<uint32_t>());
+    rm_node_offsets_kernel<<<(N + 255) / 256, 256, 0, st>>>(off, N, c->d_rm_oidx.as<long long>(), c->d_rm_off.as<long long>());
     PMB_CUDA(cudaGetLastError());
     PMB_CUDA(cudaEventRecord(c->ev_rm, st));
     c->rm_stream = st;

@@ -1784,62 +1784,166 @@ __global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_byte
 // reference src/panman.cpp:1445-1466 + NucMut ctor src/panman.hpp:109-151: a node's position-sorted records are cut where
 // the position is not the previous + 1 or the type changes, and every such maximal run greedily into pieces of at most
 // six; a piece becomes one NucMut {nucPosition = first position, mutInfo = (length << 4) + type, nucs = code_k <<
-// 4 (5 - k)}. A piece starts at record i iff (i - start of i's run) % 6 == 0. One warp per node, 32 records per step;
-// `carry` hands the run start across steps. FILL = false counts the pieces, true writes them at out_off[node], together
-// with the wire form of mutInfo (src/panman.cpp:2876: ((nucs >> (24 - 4 length)) << 8) + mutInfo).
+// 4 (5 - k)}, plus the wire form of mutInfo (src/panman.cpp:2876: ((nucs >> (24 - 4 length)) << 8) + mutInfo).
 // col_break (optional, indexed by position - col_base): 1 = the column never continues the run of the column before it
 // (PanGraph batches: the first gap slot of every position, src/panman.cpp:1242, 1261).
-template <bool FILL>
-__global__ void merge_runs_kernel(const long long* off, const int32_t* pos, const uint8_t* tc, int n_nodes, unsigned int* counts,
-                                  const long long* out_off, int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs,
-                                  uint32_t* wire, const uint8_t* col_break, long long col_base) {
-    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (node >= n_nodes) return;
-    const long long a = off[node], b = off[node + 1];
-    long long carry = a;
-    long long written = FILL ? out_off[node] : 0;
-    unsigned cnt = 0;
-    for (long long base = a; base < b; base += 32) {
-        const long long i = base + lane;
-        const bool valid = i < b;
-        const int32_t p = valid ? pos[i] : 0;
-        const uint32_t t = valid ? uint32_t(tc[i]) >> 4 : 0u;
-        int32_t pp = __shfl_up_sync(FULL, p, 1);
-        uint32_t pt = __shfl_up_sync(FULL, t, 1);
-        if (lane == 0 && valid && i > a) {
-            pp = pos[i - 1];
-            pt = uint32_t(tc[i - 1]) >> 4;
-        }
-        const bool brk = valid && (i == a || p != pp + 1 || t != pt || (col_break && col_break[p - col_base]));
-        long long rs = brk ? i : -1;  // start of the run this record belongs to: latest break at or before it
+//
+// Record-parallel over the WHOLE node-major list (round 1 walked each node with one warp: the few nodes with tens of
+// thousands of records -- next to the root of a gappy alignment -- took 7.8 ms on 5.3 M records, 99 % of it in a dozen
+// warps). A record starts a piece iff (index - start of its run) % 6 == 0, and the start of its run is the latest "break"
+// at or before it: a max-scan. Breaks include the first record of every node, so runs never cross nodes and the pieces
+// of all nodes, numbered by a prefix sum over the piece flags, come out node-major in order; a node's offset is the
+// piece number of its first record. Blocks of RM_BLOCK records; two tiny one-block scans carry the latest break and
+// the piece counts across blocks. flags[i]: bit 0 = first record of a node, bit 1 = starts a piece.
+constexpr int RM_THREADS = 256, RM_ITEMS = 8, RM_BLOCK = RM_THREADS * RM_ITEMS;
+
+__global__ void rm_mark_starts_kernel(const long long* off, int n_nodes, uint8_t* flags) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_nodes && off[v] < off[v + 1]) flags[off[v]] = 1;
+}
+__device__ __forceinline__ bool rm_is_break(long long i, const int32_t* pos, const uint8_t* tc, const uint8_t* flags,
+                                            const uint8_t* col_break, long long col_base) {
+    if (flags[i] & 1) return true;  // includes record 0
+    const int32_t p = pos[i];
+    return p != pos[i - 1] + 1 || (tc[i] >> 4) != (tc[i - 1] >> 4) || (col_break && col_break[p - col_base]);
+}
+// last[b] = index of the latest break inside block b, or -1
+__global__ void __launch_bounds__(RM_THREADS) rm_block_last_kernel(const long long* off, int n_nodes, const int32_t* pos, const uint8_t* tc,
+                                                                   const uint8_t* flags, const uint8_t* col_break, long long col_base,
+                                                                   long long* last) {
+    __shared__ long long s_w[RM_THREADS / 32];
+    const long long n = off[n_nodes], i0 = ((long long)blockIdx.x * RM_THREADS + threadIdx.x) * RM_ITEMS;
+    long long m = -1;
+    for (int k = 0; k < RM_ITEMS; k++)
+        if (i0 + k < n && rm_is_break(i0 + k, pos, tc, flags, col_break, col_base)) m = i0 + k;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_down_sync(FULL, m, d));
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RM_THREADS / 32; w++) m = max(m, s_w[w]);
+        last[blockIdx.x] = m;
+    }
+}
+// carry[b] = latest break in any block before b (exclusive max-scan), one block
+__global__ void __launch_bounds__(1024) rm_scan_max_kernel(const long long* last, int n_blocks, long long* carry) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = -1;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int b = b0 + tid;
+        const long long v = b < n_blocks ? last[b] : -1;
+        long long incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const long long o = __shfl_up_sync(FULL, rs, d);
-            if (lane >= d) rs = max(rs, o);
+            const long long t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl = max(incl, t);
         }
-        rs = max(rs, carry);
-        const bool piece = valid && ((i - rs) % 6 == 0);
-        const unsigned m = __ballot_sync(FULL, piece);
-        if (FILL && piece) {
-            const long long o = written + __popc(m & ((1u << lane) - 1u));
-            uint32_t packed = (uint32_t(tc[i]) & 15u) << 20;
-            int len = 1;
-            for (; len < 6 && i + len < b; len++) {
-                const uint32_t q = tc[i + len];
-                if (pos[i + len] != p + len || (q >> 4) != t || (col_break && col_break[p + len - col_base])) break;
-                packed += (q & 15u) << (4 * (5 - len));
-            }
-            nuc_position[o] = p;
-            mut_info[o] = uint8_t((len << 4) + int(t));
-            nucs[o] = packed;
-            // the value the reference's capnp writer stores (src/panman.cpp:2876): codes right-aligned above mutInfo
-            wire[o] = ((packed >> (24 - 4 * len)) << 8) + uint32_t((len << 4) + int(t));
-        }
-        written += __popc(m);
-        cnt += __popc(m);
-        carry = __shfl_sync(FULL, rs, 31);
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        long long before = s_carry;
+        for (int w = 0; w < warp; w++) before = max(before, s_w[w]);
+        long long excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = -1;
+        if (b < n_blocks) carry[b] = max(before, excl);
+        __syncthreads();
+        if (tid == 1023) s_carry = max(before, incl);
+        __syncthreads();
     }
-    if (!FILL && lane == 0) counts[node] = cnt;
+}
+// piece flags (bit 1) and the number of pieces per block
+__global__ void __launch_bounds__(RM_THREADS) rm_flags_kernel(const long long* off, int n_nodes, const int32_t* pos, const uint8_t* tc,
+                                                              uint8_t* flags, const uint8_t* col_break, long long col_base,
+                                                              const long long* carry, unsigned int* counts) {
+    __shared__ long long s_w[RM_THREADS / 32];
+    __shared__ unsigned s_c[RM_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n = off[n_nodes], i0 = ((long long)blockIdx.x * RM_THREADS + tid) * RM_ITEMS;
+    long long rs[RM_ITEMS], m = -1;
+#pragma unroll
+    for (int k = 0; k < RM_ITEMS; k++) {
+        if (i0 + k < n && rm_is_break(i0 + k, pos, tc, flags, col_break, col_base)) m = i0 + k;
+        rs[k] = m;  // latest break at or before the record, within this thread's records
+    }
+    long long incl = m;  // latest break in the threads up to and including this one
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl = max(incl, t);
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    long long before = carry[blockIdx.x];
+    for (int w = 0; w < warp; w++) before = max(before, s_w[w]);
+    long long excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = -1;
+    before = max(before, excl);
+    unsigned cnt = 0;
+#pragma unroll
+    for (int k = 0; k < RM_ITEMS; k++) {
+        const long long i = i0 + k;
+        if (i >= n) break;
+        const long long start = max(rs[k], before);  // >= 0: record 0 is a break
+        const bool piece = (i - start) % 6 == 0;
+        flags[i] = uint8_t((flags[i] & 1) | (piece ? 2 : 0));
+        cnt += piece;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(FULL, cnt, d);
+    if (lane == 0) s_c[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < RM_THREADS / 32; w++) cnt += s_c[w];
+        counts[blockIdx.x] = cnt;
+    }
+}
+// the pieces: output index = pieces of earlier blocks + pieces before the record in this block
+__global__ void __launch_bounds__(RM_THREADS) rm_fill_kernel(const long long* off, int n_nodes, const int32_t* pos, const uint8_t* tc,
+                                                             const uint8_t* flags, const unsigned long long* base, long long* oidx,
+                                                             int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs, uint32_t* wire) {
+    __shared__ unsigned s_c[RM_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n = off[n_nodes], i0 = ((long long)blockIdx.x * RM_THREADS + tid) * RM_ITEMS;
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < RM_ITEMS; k++)
+        if (i0 + k < n && (flags[i0 + k] & 2)) mine++;
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_c[warp] = incl;
+    __syncthreads();
+    unsigned long long o = base[blockIdx.x] + (incl - mine);
+    for (int w = 0; w < warp; w++) o += s_c[w];
+    for (int k = 0; k < RM_ITEMS; k++) {
+        const long long i = i0 + k;
+        if (i >= n) break;
+        const uint8_t f = flags[i];
+        if (!(f & 2)) continue;
+        if (f & 1) oidx[i] = (long long)o;  // a node's first record: its piece number is the node's offset
+        const uint32_t t = uint32_t(tc[i]) >> 4;
+        uint32_t packed = (uint32_t(tc[i]) & 15u) << 20;
+        int len = 1;
+        for (; len < 6 && i + len < n && !(flags[i + len] & 2); len++) packed += (uint32_t(tc[i + len]) & 15u) << (4 * (5 - len));
+        nuc_position[o] = pos[i];
+        mut_info[o] = uint8_t((len << 4) + int(t));
+        nucs[o] = packed;
+        wire[o] = ((packed >> (24 - 4 * len)) << 8) + uint32_t((len << 4) + int(t));
+        o++;
+    }
+}
+// out_off[v] = piece number of the node's first record; a node without records takes the next node's (off[v] is then the
+// first record of the next non-empty node, or the end). out_off[n_nodes] has been written by the scan of the block counts.
+__global__ void rm_node_offsets_kernel(const long long* off, int n_nodes, const long long* oidx, long long* out_off) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const long long a = off[v];
+    out_off[v] = a < off[n_nodes] ? oidx[a] : out_off[n_nodes];
 }
 
 // ------------------------------------------------------------------ ingest

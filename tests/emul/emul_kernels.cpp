@@ -1021,53 +1021,51 @@ extern "C" int emul_prog_check(int n_nodes, int root, const int32_t* child_off, 
     return 0;
 }
 
-// merge_runs_kernel, warp step by warp step (32 records per step, the run start handed across steps): the pieces of one
-// node's position-sorted records. Returns the number of pieces; outputs sized n by the caller.
+// The record-parallel run-merge (rm_*_kernel in pmb_kernels.cuh), block by block as the kernels decompose it, for ONE node's
+// position-sorted records: breaks -> latest break per block -> carry across blocks (exclusive max-scan) -> piece flags
+// ((index - run start) % 6 == 0) -> piece counts per block -> prefix -> pieces filled by looking ahead along the flags.
+// `block` = records per block (the kernels use 2048; the test also uses tiny blocks so that runs straddle many of them).
+// Returns the number of pieces; outputs sized n by the caller.
 extern "C" long long emul_merge_runs(long long n, const int32_t* pos, const uint8_t* tc, const uint8_t* col_break, long long col_base,
-                                     int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs) {
-    const long long a = 0, b = n;
-    long long carry = a, written = 0;
-    for (long long base = a; base < b; base += 32) {
-        long long rs[32];
-        bool valid[32], piece[32];
-        for (int lane = 0; lane < 32; lane++) {
-            const long long i = base + lane;
-            valid[lane] = i < b;
-            bool brk = false;
-            if (valid[lane]) {
-                const int32_t p = pos[i];
-                const uint32_t t = uint32_t(tc[i]) >> 4;
-                brk = i == a || p != pos[i - 1] + 1 || t != (uint32_t(tc[i - 1]) >> 4) || (col_break && col_break[p - col_base]);
+                                     int32_t* nuc_position, uint8_t* mut_info, uint32_t* nucs, long long block) {
+    if (n <= 0) return 0;
+    const long long nb = (n + block - 1) / block;
+    auto is_break = [&](long long i) {
+        if (i == 0) return true;  // the node's first record
+        const int32_t p = pos[i];
+        return p != pos[i - 1] + 1 || (tc[i] >> 4) != (tc[i - 1] >> 4) || (col_break && col_break[p - col_base]);
+    };
+    std::vector<long long> last(nb, -1), carry(nb, -1), base(nb, 0);
+    std::vector<unsigned> counts(nb, 0);
+    std::vector<uint8_t> flags(n, 0);
+    for (long long b = 0; b < nb; b++)
+        for (long long i = b * block; i < std::min(n, (b + 1) * block); i++)
+            if (is_break(i)) last[b] = i;
+    for (long long b = 1; b < nb; b++) carry[b] = std::max(carry[b - 1], last[b - 1]);
+    for (long long b = 0; b < nb; b++) {
+        long long rs = carry[b];
+        for (long long i = b * block; i < std::min(n, (b + 1) * block); i++) {
+            if (is_break(i)) rs = i;
+            if ((i - rs) % 6 == 0) {
+                flags[i] = 2;
+                counts[b]++;
             }
-            rs[lane] = brk ? i : -1;
         }
-        for (int d = 1; d < 32; d <<= 1) {  // inclusive max-scan, as the shuffles do it
-            long long prev[32];
-            for (int lane = 0; lane < 32; lane++) prev[lane] = rs[lane];
-            for (int lane = d; lane < 32; lane++) rs[lane] = std::max(prev[lane], prev[lane - d]);
-        }
-        int rank = 0;
-        for (int lane = 0; lane < 32; lane++) {
-            rs[lane] = std::max(rs[lane], carry);
-            const long long i = base + lane;
-            piece[lane] = valid[lane] && ((i - rs[lane]) % 6 == 0);
-            if (!piece[lane]) continue;
-            const long long o = written + rank++;
-            const int32_t p = pos[i];
+    }
+    for (long long b = 1; b < nb; b++) base[b] = base[b - 1] + counts[b - 1];
+    for (long long b = 0; b < nb; b++) {
+        long long o = base[b];
+        for (long long i = b * block; i < std::min(n, (b + 1) * block); i++) {
+            if (!(flags[i] & 2)) continue;
             const uint32_t t = uint32_t(tc[i]) >> 4;
             uint32_t packed = (uint32_t(tc[i]) & 15u) << 20;
             int len = 1;
-            for (; len < 6 && i + len < b; len++) {
-                const uint32_t q = tc[i + len];
-                if (pos[i + len] != p + len || (q >> 4) != t || (col_break && col_break[p + len - col_base])) break;
-                packed += (q & 15u) << (4 * (5 - len));
-            }
-            nuc_position[o] = p;
+            for (; len < 6 && i + len < n && !(flags[i + len] & 2); len++) packed += (uint32_t(tc[i + len]) & 15u) << (4 * (5 - len));
+            nuc_position[o] = pos[i];
             mut_info[o] = uint8_t((len << 4) + int(t));
             nucs[o] = packed;
+            o++;
         }
-        written += rank;
-        carry = rs[31];
     }
-    return written;
+    return base[nb - 1] + counts[nb - 1];
 }

@@ -102,9 +102,10 @@ def test_emulation_chain_segments(emu, port, noise):
 
 
 def test_run_merge_logic_matches_oracle(emu, port):
-    """The warp-step logic of merge_runs_kernel (pieces start where (index - run start) % 6 == 0, the run start is carried
-    across 32-record steps) against the oracle's greedy merge (reference src/panman.cpp:1445-1466), incl. column breaks
-    checked against the oracle's PanGraph gap-list rule (:1261)."""
+    """The block-decomposed logic of the record-parallel run-merge kernels (pieces start where (index - run start) % 6 == 0;
+    the latest break is carried across blocks by an exclusive max-scan, the piece numbers by a prefix sum; a piece's length
+    is read off the flags ahead of it) against the oracle's greedy merge (reference src/panman.cpp:1445-1466), incl. column
+    breaks checked against the oracle's PanGraph gap-list rule (:1261). Tiny blocks make runs straddle many of them."""
     import ctypes as C
 
     rng = np.random.default_rng(17)
@@ -112,6 +113,7 @@ def test_run_merge_logic_matches_oracle(emu, port):
     f.restype = C.c_longlong
     P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
     for trial in range(300):
+        block = C.c_longlong([3, 8, 64, 2048][trial % 4])
         n = int(rng.integers(1, 200))
         # positions: long consecutive stretches with occasional jumps; types change now and then
         step = np.where(rng.random(n) < [0.05, 0.3, 0.8][trial % 3], rng.integers(2, 9, size=n), 1)
@@ -120,7 +122,7 @@ def test_run_merge_logic_matches_oracle(emu, port):
         tc = ((ty << 4) | rng.integers(0, 16, size=n)).astype(np.uint8)
         out_p, out_i, out_n = np.empty(n, np.int32), np.empty(n, np.uint8), np.empty(n, np.uint32)
         k = f(C.c_longlong(n), P(pos, C.c_int32), P(tc, C.c_uint8), None, C.c_longlong(0), P(out_p, C.c_int32), P(out_i, C.c_uint8),
-              P(out_n, C.c_uint32))
+              P(out_n, C.c_uint32), block)
         wp, wi, wn = port.merge_msa(pos, tc)
         assert k == len(wp) and np.array_equal(out_p[:k], wp) and np.array_equal(out_i[:k], wi) and np.array_equal(out_n[:k], wn), trial
         # gap-slot columns: column c = (gap position j, slot k); consecutive columns merge only inside one position
@@ -132,7 +134,7 @@ def test_run_merge_logic_matches_oracle(emu, port):
         tcc = tc[:len(cols)]
         out_p, out_i, out_n = np.empty(len(cols), np.int32), np.empty(len(cols), np.uint8), np.empty(len(cols), np.uint32)
         k = f(C.c_longlong(len(cols)), P(cols, C.c_int32), P(tcc, C.c_uint8), P(brk, C.c_uint8), C.c_longlong(0), P(out_p, C.c_int32),
-              P(out_i, C.c_uint8), P(out_n, C.c_uint32))
+              P(out_i, C.c_uint8), P(out_n, C.c_uint32), block)
         ob, op_, og, mi, nu = port.merge_pangraph(1, np.zeros(len(cols), np.int32), col_j[cols], col_k[cols], tcc)
         assert k == len(op_) and np.array_equal(col_j[out_p[:k]], op_) and np.array_equal(col_k[out_p[:k]], og), trial
         assert np.array_equal(out_i[:k], mi) and np.array_equal(out_n[:k], nu), trial
