@@ -120,6 +120,7 @@ struct pmb_ctx {
     cudaEvent_t gev_fwd[MAX_GROUPS] = {}, gev_done[MAX_GROUPS] = {}, ev_fork = nullptr;
     cudaEvent_t ev_slab_copied[2] = {nullptr, nullptr}, ev_slab_packed[2] = {nullptr, nullptr};
     int n_sms = 0;
+    size_t total_mem = 0;
     struct Occupancy { const void* kernel; size_t smem; int per_sm; };
     std::vector<Occupancy> occupancy;
     unsigned int epoch = 0;
@@ -418,6 +419,13 @@ int pmb_create(pmb_ctx** out, int device) {
     }
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
     if (c->n_sms <= 0) c->n_sms = 148;
+    {
+        size_t free_b = 0;
+        if (cudaMemGetInfo(&free_b, &c->total_mem) != cudaSuccess) {
+            cudaGetLastError();
+            c->total_mem = size_t(64) << 30;
+        }
+    }
     *out = c;
     return PMB_OK;
 }
@@ -665,10 +673,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     const size_t T = size_t(c->T);
     const size_t set_bytes_per = (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
     const size_t set_bytes = size_t(P.n_internal) * T * set_bytes_per;
-    // a second set matrix lets consecutive passes overlap (see bstream); only where it is cheap (up to 12 GB: that covers a
-    // quarter or an eighth of BASELINE.json's config 4 on 4 or 8 GPUs and config 5): the largest problems run at the HBM
-    // roofline anyway and would pay tens of GB for it
-    const bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= (size_t(12) << 30);
+    // a second set matrix lets consecutive passes overlap (see bstream); only where it is cheap (up to 24 GB and an eighth
+    // of the device's memory: that covers a half, a quarter or an eighth of BASELINE.json's config 4 on 2, 4 or 8 GPUs and
+    // config 5): the largest problems run at the HBM roofline anyway and would pay tens of GB for it
+    const bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= std::min(size_t(24) << 30, c->total_mem / 8);
     if (set_bytes > c->d_sets.cap || (overlap && set_bytes > c->d_sets2.cap)) {  // cudaFree of a matrix a running pass uses
         PMB_CUDA(cudaStreamSynchronize(c->bstream));
         PMB_CUDA(cudaStreamSynchronize(c->cstream));
