@@ -148,7 +148,7 @@ struct pmb_ctx {
     cudaStream_t merge_stream = nullptr;  // stream of the last pmb_merge_packed (never owned)
     cudaEvent_t ev_merge = nullptr, ev_rm = nullptr;
     cudaStream_t rm_stream = nullptr;     // stream of the last pmb_merge_runs
-    DevBuf d_merge_err, d_mblock_sums;
+    DevBuf d_merge_err, d_mblock_sums, d_mrel;
     bool async_phase_events = true;
     int async_groups = 1;
 
@@ -441,7 +441,7 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
-                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums})
+                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums, &c->d_mrel})
             b->release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
                            &c->h_rm_info, &c->h_rm_nucs, &c->h_rm_wire}) b->release();
@@ -1138,9 +1138,11 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     if (c->rm_stream && c->rm_stream != st) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_rm, 0));
     if (c->merge_stream && c->merge_stream != st) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_merge, 0));
     const bool grow = size_t(N) * sizeof(unsigned int) > c->d_mcounts.cap || size_t(N + 1) * sizeof(long long) > c->d_moff.cap ||
+                      size_t(n_shards) * size_t(N) * sizeof(unsigned int) > c->d_mrel.cap ||
                       std::max<size_t>(1, total_cap) * sizeof(int32_t) > c->d_mpos.cap || std::max<size_t>(1, total_cap) > c->d_mtc.cap;
     if (grow && c->merge_stream) PMB_CUDA(cudaStreamSynchronize(c->merge_stream));  // cudaFree of a buffer in use
     PMB_CUDA(c->d_mcounts.ensure(size_t(N) * sizeof(unsigned int)));
+    PMB_CUDA(c->d_mrel.ensure(size_t(n_shards) * size_t(N) * sizeof(unsigned int)));
     PMB_CUDA(c->d_moff.ensure(size_t(N + 1) * sizeof(long long)));
     PMB_CUDA(c->d_mpos.ensure(std::max<size_t>(1, total_cap) * sizeof(int32_t)));
     PMB_CUDA(c->d_mtc.ensure(std::max<size_t>(1, total_cap)));
@@ -1152,13 +1154,13 @@ int pmb_merge_packed(pmb_ctx* c, int32_t n_shards, const void* d_packed_shards, 
     }
     const unsigned char* packed = static_cast<const unsigned char*>(d_packed_shards);
     merge_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity, c->d_mcounts.as<unsigned int>(),
-                                                        c->d_merge_err.as<unsigned int>());
+                                                        c->d_mrel.as<unsigned int>(), c->d_merge_err.as<unsigned int>());
     scan_sums_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_mblock_sums.as<unsigned long long>());
     scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(c->d_mcounts.as<unsigned int>(), N, c->d_mblock_sums.as<unsigned long long>(),
                                                            c->d_moff.as<long long>());
-    merge_copy_kernel<<<unsigned(c->n_sms * 8), 256, 0, st>>>(packed, shard_bytes, n_shards, N, capacity,
-                                                                                  c->d_moff.as<long long>(), c->d_mpos.as<int32_t>(),
-                                                                                  c->d_mtc.as<uint8_t>());
+    merge_copy_kernel<<<dim3(unsigned(c->n_sms * 2), unsigned(n_shards)), 256, 0, st>>>(packed, shard_bytes, N, capacity,
+                                                                                          c->d_moff.as<long long>(), c->d_mrel.as<unsigned int>(),
+                                                                                          c->d_mpos.as<int32_t>(), c->d_mtc.as<uint8_t>());
     PMB_CUDA(cudaGetLastError());
     PMB_CUDA(cudaEventRecord(c->ev_merge, st));
     c->merge_stream = st;

@@ -1728,14 +1728,16 @@ __device__ __forceinline__ bool shard_ok(const unsigned char* shard, int n_nodes
     return hdr[1] == n_nodes && hdr[0] >= 0 && hdr[0] <= cap;
 }
 
-// merge_err: bit 0 = a shard over capacity / flagged by its packer, bit 1 = a shard packed for another tree
+// merge_err: bit 0 = a shard over capacity / flagged by its packer, bit 1 = a shard packed for another tree.
+// rel[k * n_nodes + v] = records of node v in the shards before k = where shard k's segment starts inside the node's list
 __global__ void merge_count_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, long long cap,
-                                   unsigned int* counts, unsigned int* merge_err) {
+                                   unsigned int* counts, unsigned int* rel, unsigned int* merge_err) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
     unsigned int c = 0;
     for (int k = 0; k < n_shards; k++) {
         const unsigned char* sh = packed + k * shard_bytes;
+        rel[(size_t)k * n_nodes + v] = c;
         if (!shard_ok(sh, n_nodes, cap)) {
             if (v == 0) atomicOr(merge_err, reinterpret_cast<const long long*>(sh)[1] == n_nodes ? 1u : 2u);
             continue;
@@ -1746,36 +1748,43 @@ __global__ void merge_count_kernel(const unsigned char* packed, size_t shard_byt
     counts[v] = c;
 }
 
-// One thread per OUTPUT record (grid stride): its node by binary search in the merged offsets, its shard by walking the
-// node's per-shard segment lengths. Per-node lists are very uneven -- the nodes next to the root of a gappy alignment hold
-// tens of thousands of records, most nodes a few dozen -- and the earlier warp-per-node copy spent a millisecond in the few
-// long ones (measured at 2 shards x 0.66 M records: 1.2 ms; rank 0's merge then no longer hid behind a 2 ms pass). Threads
-// of a warp mostly share node and shard, so the offset loads hit L1 and the record loads / stores coalesce.
-__global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_bytes, int n_shards, int n_nodes, long long cap,
-                                  const long long* merged_off, int32_t* pos, uint8_t* type_code) {
-    const long long total = merged_off[n_nodes];
-    const size_t po = packed_pos_offset(n_nodes), to = packed_tc_offset(n_nodes, cap);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        int lo = 0, hi = n_nodes;  // the node v with merged_off[v] <= i < merged_off[v + 1]
+// Source-parallel copy: blockIdx.y = shard, a thread takes four consecutive records of that shard (grid stride). The node of
+// the first one by binary search in the shard's own offsets, the following ones by walking on; destination = node's merged
+// offset + the shard's place inside the node (rel) + the record's place inside the segment. Per-node lists are very uneven
+// -- the nodes next to the root of a gappy alignment hold tens of thousands of records, most nodes a few dozen -- and the
+// round-1 warp-per-node copy spent a millisecond in the few long ones (2 shards x 0.66 M records: 1.2 ms, so that rank 0's
+// merge no longer hid behind a 2 ms pass); a first record-parallel version searched the merged offsets and then walked the
+// shards per OUTPUT record (8 shards, 5.3 M records: 95 us).
+__global__ void merge_copy_kernel(const unsigned char* packed, size_t shard_bytes, int n_nodes, long long cap, const long long* merged_off,
+                                  const unsigned int* rel, int32_t* pos, uint8_t* type_code) {
+    const int k = blockIdx.y;
+    const unsigned char* sh = packed + (size_t)k * shard_bytes;
+    if (!shard_ok(sh, n_nodes, cap)) return;
+    const long long n = reinterpret_cast<const long long*>(sh)[0];
+    const long long* off = reinterpret_cast<const long long*>(sh + 16);
+    const int32_t* spos = reinterpret_cast<const int32_t*>(sh + packed_pos_offset(n_nodes));
+    const uint8_t* stc = sh + packed_tc_offset(n_nodes, cap);
+    const unsigned int* relk = rel + (size_t)k * n_nodes;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; j0 < n; j0 += stride) {
+        int lo = 0, hi = n_nodes;  // the node v with off[v] <= j0 < off[v + 1]
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (__ldg(merged_off + mid) <= i) lo = mid;
+            if (__ldg(off + mid) <= j0) lo = mid;
             else hi = mid;
         }
-        const int v = lo;
-        long long local = i - __ldg(merged_off + v);
-        for (int k = 0; k < n_shards; k++) {
-            const unsigned char* sh = packed + (size_t)k * shard_bytes;
-            if (!shard_ok(sh, n_nodes, cap)) continue;
-            const long long* off = reinterpret_cast<const long long*>(sh + 16);
-            const long long a = off[v], len = off[v + 1] - a;
-            if (local < len) {
-                pos[i] = reinterpret_cast<const int32_t*>(sh + po)[a + local];
-                type_code[i] = sh[to + a + local];
-                break;
+        int v = lo;
+        long long end = __ldg(off + v + 1);
+        long long dst = __ldg(merged_off + v) + __ldg(relk + v) - __ldg(off + v);  // + j = destination of record j of node v
+        const long long j1 = min(n, j0 + 4);
+        for (long long j = j0; j < j1; j++) {
+            while (j >= end) {  // next non-empty node
+                v++;
+                end = __ldg(off + v + 1);
+                dst = __ldg(merged_off + v) + __ldg(relk + v) - __ldg(off + v);
             }
-            local -= len;
+            pos[dst + j] = spos[j];
+            type_code[dst + j] = stc[j];
         }
     }
 }
