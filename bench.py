@@ -12,7 +12,7 @@ part of ONE pmb_group (include/panman_b200.h): the library owns the ranges, the 
 NVLink (the packing kernel's stores into peer memory mapped through CUDA IPC), the hand-shakes (stream memory operations)
 and the merge; torch.distributed (NCCL) only all-gathers the 128-byte mailbox handles once and reduces the timings.
 Prints ONE JSON line (rank 0). At N = 1 the line also carries a `configs` table (every BASELINE.json configuration, both
-algorithms where the survey asks for both) measured the same way.  --impl reference times the reference's own CPU
+algorithms where the survey asks for both) measured the same way (CUDA events over 20 pipelined passes).  --impl reference times the reference's own CPU
 implementation instead.
 """
 import argparse
@@ -525,7 +525,7 @@ def run_b200_arm(args):
             for name, a in (("sars20k", "fitch"), ("indel10k", "fitch"), ("indel10k", "sankoff"), ("caterpillar100k", "fitch"),
                             ("caterpillar100k", "sankoff")):
                 try:
-                    table.append(measure_one(pb, synth, torch, name, a, dev, local, 10, 3))
+                    table.append(measure_one(pb, synth, torch, name, a, dev, local, 20, 3))
                 except Exception as e:  # noqa: BLE001
                     table.append({"config": name, "algo": a, "error": str(e)})
             table.append({"config": args.config, "algo": algo, "leaves": cfg["n_leaves"], "nodes": N, "cols": C, "ms": dev_ms_max,

@@ -790,7 +790,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     // 0.544 -> 0.538 ms, 10k x 15k 0.201 -> 0.191 ms, 4k x 625k 2.048 -> 2.012 ms per pipelined pass; alone, a kernel is
     // 3-4 % slower at 80 %). Deep trees keep the full grid: their chain segments need every slot to run side by side
     // (100k-leaf caterpillar x 30k: 2.569 ms at 100 %, 2.591 ms at 80 %).
-    c->cur_grid_pct = c->opt_grid_pct > 0 ? int(c->opt_grid_pct) : (async && overlap && P.n_chain_segments == 0 ? 80 : 100);
+    // Problems of very few column tiles are latency-bound throughout and gain from a little more room still (10k leaves x
+    // 15 tiles: 0.189 ms at 80 %, 0.184 ms at 70 %).
+    c->cur_grid_pct = c->opt_grid_pct > 0 ? int(c->opt_grid_pct)
+                                          : (async && overlap && P.n_chain_segments == 0 ? (c->T < 24 ? 70 : 80) : 100);
     unsigned int* const run_error = rp.error;
     // the forward kernel may run beside the previous run's compaction, whose last block snapshots and resets the per-run
     // error words: its only status, the watchdog bit, goes straight to the sticky word
