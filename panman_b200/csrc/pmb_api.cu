@@ -158,6 +158,18 @@ struct pmb_ctx {
     std::vector<int32_t> child_off, child_idx, leaf_row;
     TreeProgram prog;
     int32_t prog_chunk_nodes = -1, prog_inline_nodes = -1, prog_tail = -1;
+    // Programs built for other tile counts of the SAME tree (chunk size and backward tail follow the tile count): a PanGraph
+    // build issues one batch per block, each of another width; without the cache every batch would rebuild and re-upload
+    // the program (O(N log N) on the host + nine copies). A handful of entries, least recently used goes first.
+    struct ProgramSlot {
+        int32_t k = -1, inl = -1, tail = -1;
+        unsigned long long used = 0;
+        TreeProgram prog;
+        DevBuf bufs[9];
+    };
+    std::vector<ProgramSlot> prog_cache;
+    unsigned long long prog_clock = 0;
+    static constexpr size_t PROG_CACHE_SLOTS = 6;
     DevBuf d_fwd_ops, d_refs, d_bwd_ops, d_bwd_leaves, d_chunks, d_bwd_order, d_level_order, d_row_slot, d_deps;
 
     // resident input
@@ -240,6 +252,43 @@ int ensure_program(pmb_ctx* c) {
     const int64_t resident_warps = int64_t(c->n_sms) * 5 * WARPS_PER_BLOCK;
     const int32_t tail = int32_t(std::min<int64_t>(1 << 30, std::max<int64_t>(0, c->opt_bwd_tail) * resident_warps / 10 / std::max(1, c->T)));
     if (k == c->prog_chunk_nodes && inl == c->prog_inline_nodes && tail == c->prog_tail) return PMB_OK;
+    {   // park the current program, look for one built earlier for these parameters
+        DevBuf* cur[9] = {&c->d_fwd_ops, &c->d_refs, &c->d_bwd_ops, &c->d_bwd_leaves, &c->d_chunks, &c->d_bwd_order, &c->d_level_order,
+                          &c->d_row_slot, &c->d_deps};
+        auto swap_with = [&](pmb_ctx::ProgramSlot& s) {
+            std::swap(s.prog, c->prog);
+            for (int i = 0; i < 9; i++) std::swap(s.bufs[i], *cur[i]);
+            std::swap(s.k, c->prog_chunk_nodes);
+            std::swap(s.inl, c->prog_inline_nodes);
+            std::swap(s.tail, c->prog_tail);
+            s.used = ++c->prog_clock;
+        };
+        if (c->prog_chunk_nodes >= 0) {
+            if (c->prog_cache.size() < pmb_ctx::PROG_CACHE_SLOTS) {
+                c->prog_cache.emplace_back();
+                swap_with(c->prog_cache.back());
+            } else {
+                size_t lru = 0;
+                for (size_t i = 1; i < c->prog_cache.size(); i++)
+                    if (c->prog_cache[i].used < c->prog_cache[lru].used) lru = i;
+                swap_with(c->prog_cache[lru]);  // the evicted program is now "current" and is overwritten below
+                c->prog_chunk_nodes = -1;
+            }
+        }
+        for (size_t i = 0; i < c->prog_cache.size(); i++) {
+            pmb_ctx::ProgramSlot& s = c->prog_cache[i];
+            if (s.k == k && s.inl == inl && s.tail == tail) {
+                swap_with(s);
+                if (s.k < 0) {  // what came back is not a program: drop the slot (its buffers are idle: the stream was ordered
+                                // behind every earlier pass before the upload got here)
+                    for (DevBuf& b : s.bufs) b.release();
+                    c->prog_cache.erase(c->prog_cache.begin() + long(i));
+                }
+                return PMB_OK;
+            }
+        }
+        c->prog_chunk_nodes = -1;
+    }
     std::string e = build_tree_program(c->n_nodes, c->root, c->child_off.data(), c->child_idx.data(), c->leaf_row.data(), k,
                                        inl, &c->prog, tail);
     if (e.empty() && c->opt_chunk_nodes <= 0 && c->prog.n_chain_segments > 0 && k > 128) {
@@ -443,6 +492,8 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
                           &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums, &c->d_mrel})
             b->release();
+        for (auto& s : c->prog_cache)
+            for (DevBuf& b : s.bufs) b.release();
         for (HostBuf* b : {&c->h_offsets, &c->h_pos, &c->h_tc, &c->h_states, &c->h_counters, &c->h_pack_header, &c->h_rm_off, &c->h_rm_pos,
                            &c->h_rm_info, &c->h_rm_nucs, &c->h_rm_wire}) b->release();
         for (int i = 0; i < 4; i++)
@@ -521,6 +572,12 @@ static int set_tree_impl(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_
     c->leaf_row.assign(leaf_row, leaf_row + n_nodes);
     c->prog = std::move(probe);
     c->prog_chunk_nodes = -1;  // (re)built for the tile count at upload time
+    if (!c->prog_cache.empty()) {  // programs of the previous tree
+        cudaDeviceSynchronize();
+        for (auto& s : c->prog_cache)
+            for (DevBuf& b : s.bufs) b.release();
+        c->prog_cache.clear();
+    }
     c->have_tree = true;
     c->have_input = false;
     c->have_result = false;
