@@ -390,10 +390,12 @@ def run_b200_arm(args):
     W = max(3, args.warmup)
     for _ in range(W):
         g.run_async(algo_i)
-    barrier()
+    # everything that takes a rank-dependent time on the host (NVML start-up of the clock sampler, event creation) happens
+    # BEFORE the barrier, so that the ranks enter the timed loop together
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     t0 = time.perf_counter()
     ev0.record(lib_stream)
     for _ in range(args.steps):
