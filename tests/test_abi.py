@@ -80,3 +80,31 @@ def test_product_never_imports_oracle():
                     if re.search(r"(from|import)\s+oracle|oracle/|liboracle|fs_oracle|libpanman_ref|emul_kernels|libemul", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_group_entries_without_a_device(lib):
+    """The multi-GPU entries behave like the single-context ones on a GPU-less host: creation reports PMB_ERR_CUDA with a
+    message, nothing computes, nothing crashes; the column ranges need no device at all."""
+    import torch
+
+    a, b = C.c_int64(), C.c_int64()
+    assert lib.pmb_group_column_range(8, 5_000_000, 7, C.byref(a), C.byref(b)) == 0 and (a.value, b.value) == (4375552, 5_000_000)
+    assert lib.pmb_group_column_range(0, 10, 0, C.byref(a), C.byref(b)) == -1
+    assert lib.pmb_group_column_range(4, 10, 4, C.byref(a), C.byref(b)) == -1
+    assert lib.pmb_group_last_error(None) == b"null group"
+    assert lib.pmb_group_world(None) == 0
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is for GPU-less hosts")
+    import panman_b200 as pb
+
+    with pytest.raises(pb.PanmanError) as e:
+        pb.Group([0, 1])
+    assert e.value.code == -2 and "CUDA" in str(e.value)
+    h = C.c_void_p()
+    dev = (C.c_int * 2)(0, 1)
+    assert lib.pmb_group_create(C.byref(h), dev, 2, 0, 1) == -1  # more local ranks than the world holds
+    assert lib.pmb_group_create(C.byref(h), dev, 2, 0, 2) == -2
+    assert b"rank 0" in lib.pmb_group_last_error(h)
+    assert lib.pmb_group_run_async(h, 0, 0) == -5   # PMB_ERR_NO_INPUT: nothing was uploaded
+    assert lib.pmb_group_wait(h) == -2
+    lib.pmb_group_destroy(h)
