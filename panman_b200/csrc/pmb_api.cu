@@ -639,18 +639,22 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
         else
             cudaGetLastError();
     }
-    auto pack = [&](const uint8_t* src, int32_t r0, int32_t nr) {
+    auto pack = [&](const uint8_t* src, int64_t src_stride, int32_t r0, int32_t nr) {
         long long total = (long long)nr * c->T * 32;
         unsigned blocks = unsigned((total + 255) / 256);
-        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(src, row_stride_bytes, r0, nr, n_rows, n_cols, c->T,
-                                                          c->d_row_slot.as<int>(), c->d_leaf_planes.as<uint4>());
+        pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(src, src_stride, r0, nr, n_rows, n_cols, c->T, c->d_row_slot.as<int>(),
+                                                          c->d_leaf_planes.as<uint4>());
     };
     if (on_device) {
-        pack(leaf_codes_4bit, 0, n_rows);
+        pack(leaf_codes_4bit, row_stride_bytes, 0, n_rows);
     } else {
+        // Only the batch's own columns cross the link: a slab holds rows of (n_cols + 1) / 2 bytes at a 16-byte pitch, whatever
+        // the caller's row stride is -- a column range of a wider matrix (pmb_group_upload_nuc) is copied as a 2-D region,
+        // not with the other ranges' bytes in between (and nothing behind the last row's range is touched).
+        const size_t row_bytes = size_t((n_cols + 1) / 2), pitch = (row_bytes + 15) / 16 * 16;
         const size_t slab_budget = size_t(32) << 20;
-        const int32_t slab_rows = int32_t(std::max<size_t>(1, std::min<size_t>(size_t(n_rows), slab_budget / size_t(row_stride_bytes))));
-        const size_t slab_bytes = size_t(slab_rows) * size_t(row_stride_bytes);
+        const int32_t slab_rows = int32_t(std::max<size_t>(1, std::min<size_t>(size_t(n_rows), slab_budget / pitch)));
+        const size_t slab_bytes = size_t(slab_rows) * pitch;
         PMB_CUDA(c->d_tmp_codes.ensure(2 * slab_bytes));
         cudaStream_t copy = c->gstream[0];
         for (int k = 0; k < 2; k++) {
@@ -659,19 +663,21 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
         }
         PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // the staging buffer may still be in use by earlier work
         PMB_CUDA(cudaStreamWaitEvent(copy, c->ev_fork, 0));
+        const bool tight = size_t(row_stride_bytes) == pitch;  // rows already lie back to back at the slab's pitch: one flat copy
         int slab = 0;
         for (int32_t r0 = 0; r0 < n_rows; r0 += slab_rows, slab++) {
             const int k = slab & 1;
             const int32_t nr = std::min(slab_rows, n_rows - r0);
             uint8_t* buf = c->d_tmp_codes.as<uint8_t>() + size_t(k) * slab_bytes;
             if (slab >= 2) PMB_CUDA(cudaStreamWaitEvent(copy, c->ev_slab_packed[k], 0));
-            // the last row is only (n_cols + 1) / 2 bytes long for sure: a caller's column range may start inside a wider
-            // matrix (pmb_group_upload_nuc), and the bytes behind the last row's range then lie outside its buffer
-            PMB_CUDA(cudaMemcpyAsync(buf, leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes),
-                                     size_t(nr - 1) * size_t(row_stride_bytes) + size_t((n_cols + 1) / 2), cudaMemcpyHostToDevice, copy));
+            const uint8_t* src = leaf_codes_4bit + size_t(r0) * size_t(row_stride_bytes);
+            if (tight)
+                PMB_CUDA(cudaMemcpyAsync(buf, src, size_t(nr - 1) * pitch + row_bytes, cudaMemcpyHostToDevice, copy));
+            else
+                PMB_CUDA(cudaMemcpy2DAsync(buf, pitch, src, size_t(row_stride_bytes), row_bytes, size_t(nr), cudaMemcpyHostToDevice, copy));
             PMB_CUDA(cudaEventRecord(c->ev_slab_copied[k], copy));
             PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_slab_copied[k], 0));
-            pack(buf, r0, nr);
+            pack(buf, int64_t(pitch), r0, nr);
             PMB_CUDA(cudaEventRecord(c->ev_slab_packed[k], c->stream));
         }
     }
