@@ -317,10 +317,11 @@ class Group:
         self._check(self.L.pmb_group_download(self.h, C.byref(r)))
         return Context._result(None, r, copy)
 
-    def merge_runs(self):
+    def merge_runs(self, to_host: bool = True):
+        """pmb_group_merge_runs. to_host=False leaves the NucMut fields on the device (returns the raw pmb_nucmut_result)."""
         r = pmb_nucmut_result()
-        self._check(self.L.pmb_group_merge_runs(self.h, 1, C.byref(r)))
-        return _nucmut_arrays(r)
+        self._check(self.L.pmb_group_merge_runs(self.h, 1 if to_host else 0, C.byref(r)))
+        return _nucmut_arrays(r) if to_host else r
 
     def run_nuc(self, algo, n_cols, n_rows, codes4, row_stride, parent_code, root_override=None, fwd_root_ref=None,
                 leaf_present=None, flags=0, copy=True) -> Result:
