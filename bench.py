@@ -167,8 +167,11 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def sample_columns(n_leaves, n_cols):
-    return int(min(n_cols, 262144, max(512, 1_200_000_000 // n_leaves)))  # bounded by host memory (about 1 GB of codes)
+def sample_columns(n_leaves, n_cols, seconds=12.0):
+    # enough columns for `seconds` of the reference on all host cores (about 4e6 node x columns / s and thread, with a
+    # margin of 2), bounded by host memory (about 1 GB of codes); generating them costs CPU time too
+    want = int(2.0 * seconds * 4e6 * host_threads() / max(1, 2 * n_leaves - 1))
+    return int(min(n_cols, 262144, max(2048, want), max(512, 1_200_000_000 // n_leaves)))
 
 
 # ----------------------------------------------------------------------------- reference arm
