@@ -169,8 +169,8 @@ def host_threads():
 
 def sample_columns(n_leaves, n_cols, seconds=12.0):
     # enough columns for `seconds` of the reference on all host cores (about 4e6 node x columns / s and thread, with a
-    # margin of 2), bounded by host memory (about 1 GB of codes); generating them costs CPU time too
-    want = int(2.0 * seconds * 4e6 * host_threads() / max(1, 2 * n_leaves - 1))
+    # margin), bounded by host memory (about 1 GB of codes); generating them costs CPU time too
+    want = int(1.3 * seconds * 4e6 * host_threads() / max(1, 2 * n_leaves - 1))
     return int(min(n_cols, 262144, max(2048, want), max(512, 1_200_000_000 // n_leaves)))
 
 
