@@ -190,6 +190,7 @@ struct pmb_ctx {
     DevBuf d_sets, d_fstore, d_states_planes, d_dir, d_staging, d_counters, d_offsets, d_pos, d_tc,
         d_states_u8;
     unsigned long long staging_cap = 0;
+    bool staging_floor_dirty = false;
     bool have_result = false;
     int last_algo = 0, last_flags = 0;
     int64_t n_mut = 0;
@@ -542,7 +543,10 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     if (!c || !key) return PMB_ERR_INVALID;
     std::string k(key);
     if (k == "chunk_nodes") c->opt_chunk_nodes = value;
-    else if (k == "staging_records") c->opt_staging_records = value;
+    else if (k == "staging_records") {
+        c->opt_staging_records = value;
+        c->staging_cap = 0;  // takes effect at the next run
+    }
     else if (k == "inline_nodes") c->opt_inline_nodes = value;
     else if (k == "schedule") c->opt_schedule = value;
     else if (k == "col_groups") c->opt_col_groups = value;
@@ -616,7 +620,7 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
     c->have_input = false;
     c->have_result = false;
     c->have_col_break = false;
-    c->staging_cap = 0;
+    c->staging_floor_dirty = true;  // the pool keeps what it has grown to; the default for the new size is a lower bound
     c->n_cols = n_cols;
     c->col_base = col_base;
     c->T = int32_t((n_cols + TILE_COLS - 1) / TILE_COLS);
@@ -765,13 +769,16 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         if ((rcf = ensure_flags(c, c->d_fdone, size_t(std::max(1, P.n_fslots)) * T))) return rcf;
     }
     PMB_CUDA(c->d_offsets.ensure(size_t(P.n_nodes + 1) * sizeof(long long)));
-    if (c->staging_cap == 0) {
+    if (c->staging_cap == 0 || c->staging_floor_dirty) {
         unsigned long long cells = (unsigned long long)P.n_nodes * (unsigned long long)c->n_cols;
-        // default: one record per 32 cells, plus the part of a reserved block every resident warp may leave unused
+        // default: one record per 32 cells, plus the part of a reserved block every resident warp may leave unused. A pool that
+        // earlier batches have grown stays grown (an asynchronous pass cannot regrow it on the fly: the next batch of a
+        // dense alignment would overflow again after every upload).
         unsigned long long cap = c->opt_staging_records > 0 ? (unsigned long long)c->opt_staging_records
                                                             : std::max<unsigned long long>(1ull << 20, cells / 32) +
                                                                   (unsigned long long)c->n_sms * 8 * WARPS_PER_BLOCK * 512ull;
-        c->staging_cap = cap;
+        c->staging_cap = c->opt_staging_records > 0 && c->staging_cap == 0 ? cap : std::max(c->staging_cap, cap);
+        c->staging_floor_dirty = false;
     }
 
     RunParams rp{};
