@@ -1045,7 +1045,10 @@ int pmb_wait(pmb_ctx* c) {
     }
     if (sticky & 4u) {
         c->have_result = false;
-        c->staging_cap = std::max<unsigned long long>(c->staging_cap * 4, *c->h_counters.as<unsigned long long>());
+        // as in the synchronous retry: what the pass reserved, plus room for one more block per resident warp (which warp
+        // reserves how much differs from run to run)
+        const unsigned long long total = *c->h_counters.as<unsigned long long>();
+        c->staging_cap = std::max<unsigned long long>(c->staging_cap * 4, total + total / 8 + (unsigned long long)c->n_sms * 8 * WARPS_PER_BLOCK * 512ull);
         return fail(c, PMB_ERR_STAGING, "the mutation staging pool overflowed during an asynchronous run; rerun (the pool was grown)");
     }
     c->n_mut = *reinterpret_cast<long long*>(c->h_counters.as<char>() + 32);
