@@ -75,7 +75,30 @@ def main():
         for c in ctxs:
             c.close()
         rounds += 1
-    print(f"soak_async ok: {rounds} rounds, {passes} asynchronous passes ({regrown} reruns after a staging-pool overflow), every result "
+    # the multi-rank hand-shake under the same treatment: hundreds of steps in flight over both mailbox parities
+    steps = 0
+    for trial in range(4):
+        tree = random_tree(int(rng.integers(100, 1500)), 7500 + trial, ["binary", "caterpillar"][trial % 2], max_arity=3)
+        c4, pc, ro = batch(rng, tree, int(rng.choice([5000, 12000])), 0.02)
+        one = pb.Context(0)
+        one.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+        g = pb.Group([0] * int(rng.integers(2, 6)))
+        g.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+        for algo in (0, 1):
+            one.upload(len(pc), tree.n_leaves, c4, c4.shape[1], pc, ro if algo else None)
+            one.run_resident(algo)
+            w = one.download()
+            got = g.run_nuc(algo, len(pc), tree.n_leaves, c4, c4.shape[1], pc, ro if algo else None)
+            assert same(got, w), ("group run_nuc", trial, algo)
+            g.upload(len(pc), tree.n_leaves, c4, c4.shape[1], pc, ro if algo else None)
+            for _ in range(300):
+                g.run_async(algo)
+            steps += 300
+            g.wait()
+            assert same(g.download(), w), ("group", trial, algo)
+        g.close()
+        one.close()
+    print(f"soak_async ok: {steps} group steps identical too; {rounds} rounds, {passes} asynchronous passes ({regrown} reruns after a staging-pool overflow), every result "
           "identical to the synchronous run")
 
 
