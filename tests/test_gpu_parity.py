@@ -444,5 +444,12 @@ def test_async_overflow_is_reported(ctx):
         c.wait()
     assert e.value.code == -8 and "overflow" in str(e.value)  # PMB_ERR_STAGING: its own code, not the watchdog's
     t = c.run_resident(pb.ALGO_FITCH)  # the synchronous entry sizes the pool and succeeds
-    assert c.download().n_mut > 100 and t.total_ms > 0
+    n_mut = c.download().n_mut
+    assert n_mut > 100 and t.total_ms > 0
+    # the pool keeps what it has grown to: the next batch of the same alignment may run asynchronously right away
+    c.upload(2000, tree.n_leaves, c4, c4.shape[1], codes[0].copy())
+    for _ in range(3):
+        c.run_resident_async(pb.ALGO_FITCH)
+    c.wait()
+    assert c.download().n_mut == n_mut
     c.close()
