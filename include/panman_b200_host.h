@@ -43,6 +43,26 @@ typedef struct pmh_blockmut {
     uint8_t inversion;        /* insertion: the block is inserted inverted; else: the present block is inverted */
 } pmh_blockmut;
 
+/* One node's mutations as the reference's writer lays them out (Tree::getNodesPreorder, src/panman.cpp:2854-2929; schema
+ * panman.capnp Mutation / NucMut): the node's NucMut grouped by block in std::map order, every piece with mutInfo in its wire
+ * form ((nucs >> (24 - 4 * length)) << 8) + mutInfo, every group with the node's block mutation of that block if any. This
+ * is the content of the capnp message; the byte encoding itself needs Cap'n Proto and stays the reference's. Nodes are
+ * written in pre-order, which is the node id order of pmh_tree. */
+typedef struct pmh_wire_nuc {
+    int32_t nucPosition;
+    int32_t nucGapPosition; /* 0 when nucGapExist is 0 */
+    uint8_t nucGapExist;
+    uint32_t mutInfo;
+} pmh_wire_nuc;
+typedef struct pmh_wire_mutation {
+    int64_t blockId;        /* (primaryBlockId << 32) + secondaryBlockId, the latter only when blockGapExist */
+    uint8_t blockGapExist;
+    uint8_t blockMutExist;  /* the node has a block mutation for this block */
+    uint8_t blockMutInfo;   /* insertion (1) / deletion or inversion (0); 1 when blockMutExist is 0 (the writer's default) */
+    uint8_t blockInversion; /* 1 when blockMutExist is 0 (the writer's default) */
+    int64_t nuc_begin, nuc_end; /* this group's pieces: [nuc_begin, nuc_end) of the node's pmh_wire_nuc array */
+} pmh_wire_mutation;
+
 /* ---- Newick ---- */
 pmh_tree* pmh_tree_from_newick(const char* newick, char* err, size_t err_len); /* NULL on malformed input */
 void pmh_tree_free(pmh_tree* t);
@@ -86,6 +106,9 @@ const pmh_tree* pmh_build_tree(const pmh_build* b);
 const char* pmh_build_consensus(const pmh_build* b, int64_t* len); /* blocks[0] consensus (src/panman.cpp:1439) */
 int64_t pmh_build_n_nucmut(const pmh_build* b, int32_t node);
 const pmh_nucmut* pmh_build_nucmut(const pmh_build* b, int32_t node); /* Node::nucMutation, in stored order */
+/* the node's Mutation list as the writer would store it (see pmh_wire_mutation); the root carries the block insertion of
+ * the single block (src/panman.cpp:1439-1440). Returns the number of groups. */
+int64_t pmh_build_wire(const pmh_build* b, int32_t node, const pmh_wire_mutation** mutations, const pmh_wire_nuc** nucs);
 /* raw per-node tuples (pos, type, code) before the merge, node-major (debugging / parity) */
 int64_t pmh_build_n_tuples(const pmh_build* b);
 const int64_t* pmh_build_tuple_offsets(const pmh_build* b);
@@ -134,6 +157,9 @@ const pmh_nucmut* pmh_pangraph_nucmut(const pmh_pangraph* g, int32_t node);
  * src/panman.hpp:467-484 as applied at src/panman.cpp:971-980, in ascending block id. */
 int64_t pmh_pangraph_n_blockmut(const pmh_pangraph* g, int32_t node);
 const pmh_blockmut* pmh_pangraph_blockmut(const pmh_pangraph* g, int32_t node);
+/* the node's Mutation list as the writer would store it (see pmh_wire_mutation), after pmh_pangraph_run / _reroot.
+ * Returns the number of groups. */
+int64_t pmh_pangraph_wire(const pmh_pangraph* g, int32_t node, const pmh_wire_mutation** mutations, const pmh_wire_nuc** nucs);
 /* Tree::reroot (reference src/reroot.cpp:4-261) on the loaded graph, with `leaf_name` as the new root: the tree is
  * transformed (pmh_tree_reroot), then every block column (src/reroot.cpp:54-122) and every nucleotide column (:134-224) is
  * inferred again by Fitch with the root forced to the new root's own state (root override on EVERY column), every leaf

@@ -14,6 +14,32 @@ class pmh_nucmut(C.Structure):
                 ("secondaryBlockId", C.c_int32), ("mutInfo", C.c_uint8), ("nucs", C.c_uint32)]
 
 
+class pmh_wire_nuc(C.Structure):
+    _fields_ = [("nucPosition", C.c_int32), ("nucGapPosition", C.c_int32), ("nucGapExist", C.c_uint8), ("mutInfo", C.c_uint32)]
+
+
+class pmh_wire_mutation(C.Structure):
+    _fields_ = [("blockId", C.c_int64), ("blockGapExist", C.c_uint8), ("blockMutExist", C.c_uint8), ("blockMutInfo", C.c_uint8),
+                ("blockInversion", C.c_uint8), ("nuc_begin", C.c_int64), ("nuc_end", C.c_int64)]
+
+
+def _wire_of(fn, handle, node):
+    """-> [(blockId, blockGapExist, blockMutExist, blockMutInfo, blockInversion, [(nucPosition, nucGapPosition, nucGapExist,
+    mutInfo), ...]), ...] = the node's panman.capnp Mutation list as the reference's writer would fill it."""
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.POINTER(pmh_wire_mutation)), C.POINTER(C.POINTER(pmh_wire_nuc))]
+    pm, pn = C.POINTER(pmh_wire_mutation)(), C.POINTER(pmh_wire_nuc)()
+    k = fn(handle, node, C.byref(pm), C.byref(pn))
+    if k < 0:
+        raise RuntimeError("wire form unavailable for this node")
+    out = []
+    for i in range(k):
+        m = pm[i]
+        out.append((m.blockId, int(m.blockGapExist), int(m.blockMutExist), int(m.blockMutInfo), int(m.blockInversion),
+                    [(pn[j].nucPosition, pn[j].nucGapPosition, int(pn[j].nucGapExist), pn[j].mutInfo) for j in range(m.nuc_begin, m.nuc_end)]))
+    return out
+
+
 class pmh_blockmut(C.Structure):
     _fields_ = [("primaryBlockId", C.c_int32), ("secondaryBlockId", C.c_int32), ("blockMutInfo", C.c_uint8), ("inversion", C.c_uint8)]
 
@@ -132,6 +158,7 @@ class MsaBuild:
             arr = L.pmh_build_nucmut(h, v)
             self.nucmut.append([(arr[i].nucPosition, arr[i].nucGapPosition, arr[i].primaryBlockId, arr[i].secondaryBlockId,
                                  arr[i].mutInfo, arr[i].nucs) for i in range(k)])
+        self.wire = [_wire_of(L.pmh_build_wire, h, v) for v in range(self.tree.n_nodes)]
         nt = L.pmh_build_n_tuples(h)
         N = self.tree.n_nodes
         self.tuple_offsets = np.ctypeslib.as_array(L.pmh_build_tuple_offsets(h), (N + 1,)).copy()
@@ -286,6 +313,10 @@ class PanGraphBuild:
             raise RuntimeError(err.value.decode())
         self.tree = HostTree(self.L.pmh_pangraph_tree(self.h), owned=False)
         return self._results()
+
+    def wire(self):
+        """Per node, the Mutation list the reference's writer would store (pmh_pangraph_wire)."""
+        return [_wire_of(self.L.pmh_pangraph_wire, self.h, v) for v in range(self.tree.n_nodes)]
 
     def blockmut(self):
         """Node::blockMutation per node: lists of (primaryBlockId, secondaryBlockId, blockMutInfo, inversion)."""

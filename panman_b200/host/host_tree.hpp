@@ -39,6 +39,16 @@ struct BlockOrder {
 };
 void order_blocks(const std::vector<PathIn>& paths_in_json_order, BlockOrder* out);
 
+// wire.cpp: one node's mutations as Tree::getNodesPreorder writes them (src/panman.cpp:2854-2929)
+}  // namespace pmh
+struct pmh_nucmut;
+struct pmh_blockmut;
+struct pmh_wire_mutation;
+struct pmh_wire_nuc;
+namespace pmh {
+void build_wire(const std::vector<pmh_nucmut>& nuc, const std::vector<pmh_blockmut>& blk, std::vector<pmh_wire_mutation>* muts,
+                std::vector<pmh_wire_nuc>* nucs);
+
 // reference Tree::transform (src/panman.cpp:5831-5906): `tip` becomes the first child of a new root. Defined in reroot.cpp.
 std::string reroot_tree(const HostTree& in, int32_t tip, HostTree* out);
 int32_t find_node(const HostTree& t, const std::string& name);

@@ -29,6 +29,8 @@ struct pmh_build {
     std::vector<int8_t> per_col;  // root_override (low-memory branch) or fwd_root_ref (MSA branch); empty = none
     ~pmh_build();
     std::vector<std::vector<pmh_nucmut>> nuc;
+    mutable std::vector<pmh_wire_mutation> wire_muts;  // scratch of pmh_build_wire (one node at a time)
+    mutable std::vector<pmh_wire_nuc> wire_nucs;
     std::vector<int64_t> tuple_off;
     std::vector<int32_t> tuple_pos;
     std::vector<uint8_t> tuple_tc;
@@ -473,6 +475,19 @@ const char* pmh_build_consensus(const pmh_build* b, int64_t* len) {
 }
 int64_t pmh_build_n_nucmut(const pmh_build* b, int32_t v) { return int64_t(b->nuc[v].size()); }
 const pmh_nucmut* pmh_build_nucmut(const pmh_build* b, int32_t v) { return b->nuc[v].data(); }
+int64_t pmh_build_wire(const pmh_build* b, int32_t node, const pmh_wire_mutation** mutations, const pmh_wire_nuc** nucs) {
+    if (!b || node < 0 || node >= int32_t(b->nuc.size())) return -1;
+    try {
+        std::vector<pmh_blockmut> blk;
+        if (node == b->tree.t.root) blk.push_back(pmh_blockmut{0, -1, 1, 0});  // root->blockMutation.emplace_back(0, (BI, false)), :1439-1440
+        pmh::build_wire(b->nuc[size_t(node)], blk, &b->wire_muts, &b->wire_nucs);
+    } catch (const std::exception&) {
+        return -1;
+    }
+    if (mutations) *mutations = b->wire_muts.data();
+    if (nucs) *nucs = b->wire_nucs.data();
+    return int64_t(b->wire_muts.size());
+}
 int64_t pmh_build_n_tuples(const pmh_build* b) { return int64_t(b->tuple_pos.size()); }
 const int64_t* pmh_build_tuple_offsets(const pmh_build* b) { return b->tuple_off.data(); }
 const int32_t* pmh_build_tuple_pos(const pmh_build* b) { return b->tuple_pos.data(); }

@@ -188,6 +188,8 @@ struct pmh_pangraph {
     std::vector<int32_t> rotation_index;  // per leaf row: blocks a circular path was rotated by (Tree::rotationIndexes)
     std::vector<std::vector<pmh_nucmut>> nuc;      // Node::nucMutation after the run, in the reference's order
     std::vector<std::vector<pmh_blockmut>> blockmut;  // Node::blockMutation after the run, ascending block id
+    mutable std::vector<pmh_wire_mutation> wire_muts;  // scratch of pmh_pangraph_wire (one node at a time)
+    mutable std::vector<pmh_wire_nuc> wire_nucs;
 };
 
 namespace {
@@ -601,6 +603,18 @@ int pmh_pangraph_reroot(pmb_ctx* ctx, pmh_pangraph* g, const char* leaf_name, ch
         set_err(err, err_len, std::string("pmh_pangraph_reroot: ") + ex.what());
         return PMB_ERR_INVALID;
     }
+}
+
+int64_t pmh_pangraph_wire(const pmh_pangraph* g, int32_t node, const pmh_wire_mutation** mutations, const pmh_wire_nuc** nucs) {
+    if (!g || node < 0 || node >= int32_t(g->nuc.size())) return -1;
+    try {
+        pmh::build_wire(g->nuc[size_t(node)], g->blockmut[size_t(node)], &g->wire_muts, &g->wire_nucs);
+    } catch (const std::exception&) {
+        return -1;
+    }
+    if (mutations) *mutations = g->wire_muts.data();
+    if (nucs) *nucs = g->wire_nucs.data();
+    return int64_t(g->wire_muts.size());
 }
 
 int64_t pmh_pangraph_n_blockmut(const pmh_pangraph* g, int32_t node) { return node < int32_t(g->blockmut.size()) ? int64_t(g->blockmut[node].size()) : 0; }

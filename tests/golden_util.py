@@ -87,3 +87,30 @@ def merge_all_nodes(port, node_offsets, pos, type_code):
     cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
     mi, nu = cat(mis, np.uint8), cat(nus, np.uint32)
     return off, cat(ps, np.int32), mi, nu, wire_mut_info(mi, nu).astype(np.uint32)
+
+
+def writer_layout(nucmut, blockmut):
+    """TEST INFRASTRUCTURE: restatement of what Tree::getNodesPreorder (reference src/panman.cpp:2854-2929) puts into one node's
+    Mutation list. nucmut: [(nucPosition, nucGapPosition, primaryBlockId, secondaryBlockId, mutInfo, nucs)] in Node::nucMutation
+    order; blockmut: [(primaryBlockId, secondaryBlockId, blockMutInfo, inversion)]. Returns [(blockId, blockGapExist,
+    blockMutExist, blockMutInfo, blockInversion, [(nucPosition, nucGapPosition, nucGapExist, mutInfo)])] in std::map order."""
+    groups = {}
+    inversion = {}
+    for pos, gap, pb, sb, info, nucs in nucmut:
+        length = info >> 4
+        wire = ((nucs >> (24 - length * 4)) << 8) + info                                     # :2876
+        entry = (pos, gap if gap != -1 else 0, 1 if gap != -1 else 0, wire)                   # :2868-2874
+        g = groups.setdefault((pb, sb), [[], 0])
+        g[0].append(entry)
+        g[1] = 2                                                                               # :2878
+    for pb, sb, info, inv in blockmut:
+        g = groups.setdefault((pb, sb), [[], 0])
+        g[1] = int(bool(info))                                                                 # :2883
+        inversion[(pb, sb)] = int(bool(inv))
+    out = []
+    for (pb, sb), (entries, second) in sorted(groups.items()):                                 # std::map order
+        exist = int(second != 2)
+        inv = inversion.get((pb, sb), 0) if second != 2 else 1                                 # :2893-2897
+        block_id = (pb << 32) + sb if sb != -1 else (pb << 32)                                 # :2901-2908
+        out.append((block_id, int(sb != -1), exist, int(bool(second)), inv, entries))
+    return out

@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+from tests.golden_util import writer_layout
+
 from oracle.oracle import CODE_OF, parse_newick as py_parse_newick, random_tree
 
 
@@ -172,4 +174,6 @@ def test_msa_build_matches_reference_flow(port, ref, low_mem):
             got = build.nucmut[v]
             assert [g[0] for g in got] == list(wp) and [g[4] for g in got] == list(wmi) and [g[5] for g in got] == list(wnu), (trial, v)
             assert all(g[1] == -1 and g[2] == 0 and g[3] == -1 for g in got)
+            # what the writer would store for the node (src/panman.cpp:2854-2929); the root carries the block insertion (:1439-1440)
+            assert build.wire[v] == writer_layout(got, [(0, -1, 1, 0)] if v == tree.root else []), (trial, v)
     ctx.close()

@@ -130,5 +130,11 @@ def test_pangraph_flow_matches_oracle(port, algo):
                                                           np.asarray([t[3] for t in sel], np.uint8))
                 want_v += [(int(op_[i]), int(og[i]), int(ob[i]), -1, int(mi[i]), int(nu[i])) for i in range(len(ob))]
             assert got[v] == want_v, (trial, v)
+        # the Mutation lists the writer would store (src/panman.cpp:2854-2929): grouped by block, wire mutInfo, block mutations
+        from tests.golden_util import writer_layout
+
+        bm = build.blockmut()
+        for v, w in enumerate(build.wire()):
+            assert w == writer_layout(got[v], bm[v]), (trial, v)
         build.close()
     ctx.close()
