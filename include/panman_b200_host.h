@@ -141,6 +141,9 @@ const uint8_t* pmh_pangraph_block_states(const pmh_pangraph* g); /* n_leaves x n
 /* n_leaves: by how many blocks a circular path was rotated to line up with the first path (what the reference keeps as
  * Tree::rotationIndexes, src/panman.cpp:835-837, src/rotation.cpp:96); 0 for linear paths */
 const int32_t* pmh_pangraph_rotation_index(const pmh_pangraph* g);
+/* n_blocks or NULL (no --reference): the state the block-level pass forces the root to (defaultState, src/panman.cpp:881-897),
+ * -1 where no sequence matches */
+const int8_t* pmh_pangraph_block_override(const pmh_pangraph* g);
 int64_t pmh_pangraph_n_cols(const pmh_pangraph* g, int32_t block);
 const uint8_t* pmh_pangraph_codes4(const pmh_pangraph* g, int32_t block, int64_t* row_stride);
 const uint8_t* pmh_pangraph_present(const pmh_pangraph* g, int32_t block);

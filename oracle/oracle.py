@@ -62,6 +62,8 @@ class RefPgOrder:
         L.refpg_topo_id.argtypes = [C.c_void_p, C.c_int64]
         L.refpg_visit.restype = C.c_char_p
         L.refpg_visit.argtypes = [C.c_void_p, C.c_int]
+        L.refpg_aligned_walk.restype = C.c_char_p
+        L.refpg_aligned_walk.argtypes = [C.c_void_p, C.c_int]
         L.refpg_rotation_index.argtypes = [C.c_void_p, C.c_char_p]
         L.refpg_aligned.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refpg_free.argtypes = [C.c_void_p]
@@ -90,6 +92,7 @@ class RefPgOrder:
                        rotation_index={}, visit=[])
             with_blocks = [p["name"] for p in paths if p["blocks"]]
             out["visit"] = [self.L.refpg_visit(h, k).decode() for k in range(len(set(with_blocks)))]
+            out["aligned_walk"] = [self.L.refpg_aligned_walk(h, k).decode() for k in range(len(set(with_blocks)))]
             for name in with_blocks:
                 a, s_, nu = (np.empty(max(n, 1), np.int32) for _ in range(3))
                 self.L.refpg_aligned(h, name.encode(), a.ctypes.data, s_.ctypes.data, nu.ctypes.data)

@@ -34,6 +34,7 @@ struct Order {
     std::unordered_map<size_t, std::string> intIdToStringId;
     std::vector<size_t> topo;
     std::vector<std::string> visit;  // the iteration order of `paths`
+    std::vector<std::string> aligned_walk;  // the iteration order of getAlignedSequences' result
 };
 }  // namespace
 
@@ -142,12 +143,19 @@ void* refpg_order(int n_paths, const char** names, const int64_t* path_off, cons
     }
     for (auto& m : o->intSequences)
         for (auto& s : m.second) s = order_map[s];
+    {   // getAlignedSequences (src/panman.cpp:6447-6465) fills its result map in the iteration order of intSequences; the
+        // block-level driver then walks that map (:881)
+        std::unordered_map<std::string, std::vector<int>> alignedSequences;
+        for (auto p : o->intSequences) alignedSequences[p.first].push_back(0);
+        for (const auto& u : alignedSequences) o->aligned_walk.push_back(u.first);
+    }
     return o;
 }
 
 void refpg_free(void* h) { delete static_cast<Order*>(h); }
 int64_t refpg_n_topo(void* h) { return int64_t(static_cast<Order*>(h)->topo.size()); }
 const char* refpg_topo_id(void* h, int64_t i) { return static_cast<Order*>(h)->intIdToStringId[size_t(i)].c_str(); }
+const char* refpg_aligned_walk(void* h, int k) { return static_cast<Order*>(h)->aligned_walk[size_t(k)].c_str(); }
 const char* refpg_visit(void* h, int k) { return static_cast<Order*>(h)->visit[size_t(k)].c_str(); }
 int refpg_rotation_index(void* h, const char* name) { return static_cast<Order*>(h)->rotationIndexes[name]; }
 int refpg_inverted(void* h, const char* name) { return static_cast<Order*>(h)->sequenceInverted[name] ? 1 : 0; }

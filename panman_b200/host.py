@@ -258,6 +258,10 @@ class PanGraphBuild:
         L.pmh_pangraph_rotation_index.argtypes = [vp]
         L.pmh_pangraph_rotation_index.restype = C.POINTER(C.c_int32)
         self.rotation_index = np.ctypeslib.as_array(L.pmh_pangraph_rotation_index(self.h), (max(n_leaves, 1),))[:n_leaves].copy()
+        L.pmh_pangraph_block_override.argtypes = [vp]
+        L.pmh_pangraph_block_override.restype = C.POINTER(C.c_int8)
+        bo = L.pmh_pangraph_block_override(self.h)
+        self.block_override = np.ctypeslib.as_array(bo, (self.n_blocks,)).copy() if bo and self.n_blocks else None
         self.batches = []
         for b in range(self.n_blocks):
             n = int(L.pmh_pangraph_n_cols(self.h, b))

@@ -272,6 +272,15 @@ void order_blocks(const std::vector<PathIn>& in, BlockOrder* out) {
         renum[consensus_ids[i]] = int(i);
         out->topo_ids.push_back(id_name[consensus_ids[i]]);
     }
+    // The block-level driver walks alignedSequences (src/panman.cpp:881), a std::unordered_map that getAlignedSequences fills
+    // in the iteration order of intSequences, itself filled in the order the paths were visited: the same chain of
+    // containers gives the same walk.
+    {
+        std::unordered_map<std::string, int> int_sequences, aligned_sequences;
+        for (const std::string& name : out->visit) int_sequences[name];
+        for (const auto& kv : int_sequences) aligned_sequences[kv.first];
+        for (const auto& kv : aligned_sequences) out->aligned_walk.push_back(kv.first);
+    }
     const size_t n = out->topo_ids.size();
     for (auto& p : paths) {
         std::vector<int>& ids = seq_ids[p.first];

@@ -36,6 +36,7 @@ struct BlockOrder {
     std::unordered_map<std::string, std::vector<int32_t>> aligned, strand, number;
     std::unordered_map<std::string, int> rotation_index;  // circular paths: blocks the path was rotated by
     std::vector<std::string> visit;                       // the order in which the paths were chained
+    std::vector<std::string> aligned_walk;                // the order in which the block-level driver walks the sequences
 };
 void order_blocks(const std::vector<PathIn>& paths_in_json_order, BlockOrder* out);
 

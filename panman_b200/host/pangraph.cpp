@@ -10,14 +10,18 @@
 //   * the column drivers                            src/panman.cpp:873-963 (blocks: 1 absent / 2 forward / 4 reverse) and
 //     :1048-1232 (one column per main position j and per gap slot (j, k); sequences whose path lacks the block are
 //     OMITTED from the state map; parent state = consensus character, '-' for gap slots)
-// Stand-ins for what the files do not determine (same as tests/golden/make_sars20_golden.py):
-// Block columns follow the reference: the consensus order of chain_align over the paths, one column per occurrence of a
-// duplicated block, circular paths rotated against the first path (block_order.cpp; src/panman.cpp:6259-6465,
-// src/chaining.cpp, src/rotation.cpp), and a sequence's mutations are those recorded for (block, sequence, occurrence).
-//   * root override: with --reference, the character of the LAST sequence in leaf-row order whose name contains the
-//     reference string (the reference iterates a tbb::concurrent_unordered_map); without it, gap columns and the Sankoff
-//     branch have none (guarded by reference.length()), while the Fitch main-column branch lacks that guard
-//     (src/panman.cpp:1132) and forces the root to whichever present sequence iterates last: here the highest leaf row.
+// Which sequence the root is forced to where several qualify follows from the order in which the reference walks its maps:
+//   * block level (src/panman.cpp:881-897, only with --reference): the LAST sequence whose name contains the reference string in
+//     the walk of alignedSequences, a std::unordered_map -- reproduced with the same chain of containers (block_order.cpp);
+//   * nucleotide level: the LAST such sequence in the walk of individualSequences (src/panman.cpp:1021-1022, 1131-1138), a
+//     tbb::concurrent_unordered_map holding the sequences that own the block. Without --reference, gap columns and the
+//     Sankoff branch have no override (guarded by reference.length()), while the Fitch main-column branch lacks that guard
+//     (:1132): std::string::find("") matches everything and the root is forced to whichever owner is walked last.
+//     TBB's map is a split-ordered list: it is walked in ascending order of the BIT-REVERSED hash of the key, whatever the
+//     insertion order, and its default hasher for std::string is h = c ^ (h * 0x9E3779B97F4A7C15) over the characters
+//     (tbb 2019_U9: tbb/internal/_concurrent_unordered_impl.h split_order_key_regular, _tbb_hash_compare_impl.h tbb_hasher).
+//     TBB is not available here, so this rule is restated from its headers as we know them and is NOT pinned by executable
+//     code; everything else of the flow is.
 #include <cctype>
 #include <cstring>
 #include <map>
@@ -147,6 +151,15 @@ struct JParser {
     }
 };
 
+// position of a key in the walk of a tbb::concurrent_unordered_map<std::string, ...> (see the header comment)
+uint64_t tbb_walk_key(const std::string& s) {
+    uint64_t h = 0;
+    for (char ch : s) h = uint64_t(int64_t(ch)) ^ (h * 11400714819323198485ull);
+    uint64_t r = 0;
+    for (int b = 0; b < 64; b++) r |= ((h >> b) & 1ull) << (63 - b);
+    return r | 1ull;
+}
+
 uint8_t code_of(unsigned char c) {  // getCodeFromNucleotide, src/panman.cpp:78-113: anything unlisted (incl. '-') -> 0
     static const struct T {
         uint8_t t[256];
@@ -275,12 +288,10 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
         auto it = row_of.find(kv.first);
         if (it != row_of.end()) g->rotation_index[size_t(it->second)] = kv.second;
     }
-    auto matches_reference = [&](int32_t row) {
-        if (reference.empty()) return false;
-        for (int32_t v = 0; v < T.n_nodes(); v++)
-            if (T.leaf_row[v] == row) return T.names[v].find(reference) != std::string::npos;
-        return false;
-    };
+    std::vector<std::string> name_of_row(size_t(T.n_leaves));
+    for (int32_t v = 0; v < T.n_nodes(); v++)
+        if (T.leaf_row[v] >= 0) name_of_row[size_t(T.leaf_row[v])] = T.names[v];
+    auto matches_reference = [&](int32_t row) { return !reference.empty() && name_of_row[size_t(row)].find(reference) != std::string::npos; };
     const int32_t NB = int32_t(order.topo_ids.size()), L = T.n_leaves;
     g->blocks.resize(NB);
     g->block_states.assign(size_t(L) * NB, 0);
@@ -381,11 +392,14 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
             set_err(err, err_len, "block " + B.id + (shape_ok ? ": a mutation lies outside the block" : ": JSON: malformed mutation entry"));
             return nullptr;
         }
+        // the owner walked last by the nucleotide-level driver, among all owners and among those matching --reference
         int32_t last_present = -1, ref_row = -1;
+        uint64_t last_key = 0, ref_key = 0;
         for (int32_t r = 0; r < L; r++) {
             if (rows[r].empty()) continue;
-            last_present = r;
-            if (matches_reference(r)) ref_row = r;
+            const uint64_t key = tbb_walk_key(name_of_row[size_t(r)]);
+            if (last_present < 0 || key > last_key) { last_present = r; last_key = key; }
+            if (matches_reference(r) && (ref_row < 0 || key > ref_key)) { ref_row = r; ref_key = key; }
             uint8_t* d = B.codes4.data() + size_t(r) * size_t(B.stride);
             for (int64_t c = 0; c < B.n_cols; c++) d[c >> 1] |= uint8_t(rows[r][c] << (4 * (c & 1)));
         }
@@ -396,8 +410,10 @@ pmh_pangraph* pmh_pangraph_load(const char* json, size_t json_len, const char* n
                 for (int64_t c = 0; c < B.n_cols; c++) B.root_override_fitch[c] = int8_t(rows[ref_row][c]);
                 B.any_override = true;
             }
-            for (int32_t r = 0; r < L; r++)
-                if (matches_reference(r)) g->block_override[i] = int8_t(g->block_states[size_t(r) * NB + i]);
+            for (const std::string& name : order.aligned_walk) {  // the last match of the block-level walk wins
+                auto it = row_of.find(name);
+                if (it != row_of.end() && matches_reference(it->second)) g->block_override[i] = int8_t(g->block_states[size_t(it->second) * NB + i]);
+            }
         } else if (last_present >= 0) {
             for (int64_t c = 0; c <= len; c++) B.root_override_fitch[c] = int8_t(rows[last_present][c]);
             B.any_override = true;
@@ -419,6 +435,7 @@ int32_t pmh_pangraph_n_blocks(const pmh_pangraph* g) { return int32_t(g->blocks.
 const char* pmh_pangraph_block_id(const pmh_pangraph* g, int32_t b) { return g->blocks[b].id.c_str(); }
 const uint8_t* pmh_pangraph_block_states(const pmh_pangraph* g) { return g->block_states.data(); }
 const int32_t* pmh_pangraph_rotation_index(const pmh_pangraph* g) { return g->rotation_index.data(); }
+const int8_t* pmh_pangraph_block_override(const pmh_pangraph* g) { return g->block_override.empty() ? nullptr : g->block_override.data(); }
 int64_t pmh_pangraph_n_cols(const pmh_pangraph* g, int32_t b) { return g->blocks[b].n_cols; }
 const uint8_t* pmh_pangraph_codes4(const pmh_pangraph* g, int32_t b, int64_t* row_stride) {
     if (row_stride) *row_stride = g->blocks[b].stride;

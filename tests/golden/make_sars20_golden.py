@@ -15,10 +15,11 @@ semantics), sequences that have it contribute their character ('-' = code 0).
 
 Block columns are in the reference's own order: oracle.RefPgOrder runs the reference's chaining.cpp / rotation.cpp
 (compiled verbatim into oracle/_ref/libpanman_pgorder.so) the way Pangraph::Pangraph drives them (src/panman.cpp:6259-6465).
-One input of that path is not reproducible from the files alone and gets a documented stand-in:
-  * root override of MAIN columns without --reference: panman.cpp:1132 lacks the `reference.length()` guard, so the
-    root is forced to the state of whichever present sequence a tbb::concurrent_unordered_map iterates last. The
-    stand-in is the present sequence with the highest leaf row. Gap columns (guarded, :1057) have no override.
+One rule of that path is pinned by no executable reference code: without --reference the Fitch main-column branch forces
+the root to the state of whichever owner of the block a tbb::concurrent_unordered_map walks last (src/panman.cpp:1131-1138;
+the `reference.length()` guard of :1057 is missing at :1132). TBB is not installed here; the walk order is restated in
+tests/pangraph_util.py (tbb_walk_key: ascending bit-reversed tbb_hasher of the sequence name). Gap columns (guarded) have no
+override.
 The tree is bifurcating, so the reference would run Fitch; the Sankoff lists (its polytomy branch, with the override
 rule of that branch: none without --reference) are stored as well.
 """

@@ -3,13 +3,26 @@ batches (src/panman.cpp:6216-6258 JSON fields; :1006-1045 aligned strings; :873-
 by the golden-fixture generator (tests/golden/make_sars20_golden.py) and the tests of the C++ adaptor
 (panman_b200/host/pangraph.cpp), plus a generator of random PanGraphs in the same JSON layout.
 
-Stand-ins (documented in both places): block order = JSON order; root override of Fitch main columns without --reference =
-the present sequence with the highest leaf row; gap columns / the Sankoff branch have none without --reference."""
+Block columns come from the reference's own compiled ordering code (oracle.RefPgOrder). Which sequence the root is forced to
+where several qualify follows the walk order of the reference's maps (panman_b200/host/pangraph.cpp, header comment): the
+std::unordered_map walk of the block-level driver is taken from the compiled reference containers (order["aligned_walk"]);
+the tbb::concurrent_unordered_map walk of the nucleotide-level driver is restated here (bit-reversed tbb_hasher) and is the
+one rule of the flow that no executable reference code pins (TBB is not installed)."""
 import json
 
 import numpy as np
 
 from oracle.oracle import CODE_OF
+
+
+def tbb_walk_key(name: str) -> int:
+    """Position of a std::string key in the walk of a tbb::concurrent_unordered_map (split-ordered list: ascending bit-reversed
+    hash; tbb_hasher: h = c ^ (h * 0x9E3779B97F4A7C15))."""
+    h = 0
+    for ch in name.encode():
+        c = ch - 256 if ch >= 128 else ch  # char is signed
+        h = ((c & 0xFFFFFFFFFFFFFFFF) ^ ((h * 11400714819323198485) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+    return int(format(h, "064b")[::-1], 2) | 1
 
 
 def code_of(ch: str) -> int:
@@ -38,11 +51,12 @@ def json_order(pg: dict):
     return out
 
 
-def build_batches(pg: dict, tree, order: dict):
+def build_batches(pg: dict, tree, order: dict, reference: str = ""):
     """Returns (block_states uint8 [n_leaves, n_cols_blocks], [batch per block column]); a batch has codes (uint8 [n_leaves,
     n_cols], one code per byte), present, parent_code, root_override (Fitch stand-in), col_j, col_k. `order` = the block
     columns and per-path ownership (oracle.RefPgOrder.order: the reference's chain_align / rotation code)."""
     row_of_name = {tree.names[v]: int(tree.leaf_row[v]) for v in tree.leaves}
+    name_of_row = {r: n for n, r in row_of_name.items()}
     n_leaves = tree.n_leaves
     by_id = {b["id"]: b for b in pg["blocks"]}
     topo = order["topo_ids"]
@@ -87,12 +101,24 @@ def build_batches(pg: dict, tree, order: dict):
                     row[j - 1] = 0
             codes[r] = row
         parent_code = np.asarray([code_of(ch) for ch in main] + [0] * (n_cols - (L + 1)), np.uint8)
+        # the owner the nucleotide-level driver walks last (individualSequences, a tbb::concurrent_unordered_map)
         root_override = np.full(n_cols, -1, np.int8)
-        if present.any():
-            last_row = int(np.nonzero(present)[0].max())
+        owners_rows = [int(r) for r in np.nonzero(present)[0]]
+        if reference:
+            match = [r for r in owners_rows if reference in name_of_row[r]]
+            if match:
+                root_override[:] = codes[max(match, key=lambda r: tbb_walk_key(name_of_row[r]))]
+        elif owners_rows:  # src/panman.cpp:1132: the unguarded find("") of the Fitch main-column branch
+            last_row = max(owners_rows, key=lambda r: tbb_walk_key(name_of_row[r]))
             root_override[:L + 1] = codes[last_row, :L + 1]
         batches.append(dict(id=bid, codes=codes, present=present, parent_code=parent_code, root_override=root_override,
                             col_j=np.asarray(col_j, np.int32), col_k=np.asarray(col_k, np.int32)))
+    if reference:  # block level (src/panman.cpp:881-897): the last match in the walk of alignedSequences
+        block_override = np.full(len(topo), -1, np.int8)
+        for name in order["aligned_walk"]:
+            if name in row_of_name and reference in name:
+                block_override[:] = bcodes[row_of_name[name]]
+        return bcodes, batches, block_override
     return bcodes, batches
 
 

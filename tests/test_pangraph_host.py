@@ -45,6 +45,27 @@ def test_adaptor_batches_match_restatement(refpg, duplicates, circular, shuffle)
         got.close()
 
 
+@pytest.mark.parametrize("reference", ["one", "many"])
+def test_adaptor_reference_overrides(refpg, reference):
+    """--reference: the root is forced to the reference sequence's state on every block and nucleotide column; where the
+    string matches several sequence names, to the one the reference's map walks reach last."""
+    from panman_b200.host import PanGraphBuild
+
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        tree = random_tree(int(rng.integers(3, 30)), 8300 + trial, ["binary", "polytomy"][trial % 2], max_arity=4)
+        text = random_pangraph(tree, rng, n_blocks=int(rng.integers(2, 6)), max_len=40, duplicates=trial % 3 == 0)
+        pg = json.loads(text)
+        names = [tree.names[v] for v in tree.leaves]
+        ref = names[int(rng.integers(0, len(names)))] if reference == "one" else names[0][:1]  # the common first letter
+        order = refpg.order(pg)
+        want_states, want_batches, want_block_override = build_batches(pg, tree, order, ref)
+        got = PanGraphBuild(text.encode(), tree.to_newick(), ref)
+        _same_batches(got, want_states, want_batches)
+        assert np.array_equal(got.block_override, want_block_override), trial
+        got.close()
+
+
 def test_adaptor_reports_malformed_input():
     """Nothing may abort the host process: malformed JSON, wrong kinds and sizes, unknown blocks come back as errors."""
     from panman_b200.host import PanGraphBuild
