@@ -92,6 +92,9 @@ pmh_build* pmh_build_from_msa(pmb_ctx* ctx, const char* fasta, size_t fasta_len,
 pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newick, const char* reference, int low_mem_mode,
                            char* err, size_t err_len);
 int pmh_msa_run(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len);
+/* The same over the GPUs of a box: `group` = a single-process pmb_group (pmb_group_create with all its devices); the columns
+ * of the batch are split into contiguous ranges, one per GPU, and the lists come back merged (include/panman_b200.h). */
+int pmh_msa_run_group(pmb_group* group, pmh_build* b, char* err, size_t err_len);
 int64_t pmh_build_n_cols(const pmh_build* b);
 const uint8_t* pmh_build_codes4(const pmh_build* b, int64_t* row_stride); /* n_leaves rows; NULL once pmh_msa_run consumed it */
 const uint8_t* pmh_build_present(const pmh_build* b);                      /* n_leaves */

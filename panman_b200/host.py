@@ -143,9 +143,22 @@ class MsaBuild:
     """panmanUtils -M msa.fa -N tree.nwk [--reference id] [--low-mem-mode] through libpanman_b200."""
 
     def __init__(self, ctx, fasta: bytes, newick: str, reference: str = "", low_mem_mode: bool = False):
+        """ctx: a Context (one GPU) or a single-process Group (pmh_msa_run_group: column ranges over the GPUs of the box)."""
+        from .api import Group
+
         L = load_host_library()
         err = C.create_string_buffer(512)
-        h = L.pmh_build_from_msa(ctx.h, fasta, len(fasta), newick.encode(), reference.encode(), int(low_mem_mode), err, 512)
+        if isinstance(ctx, Group):
+            vp = C.c_void_p
+            L.pmh_msa_prepare.restype = vp
+            L.pmh_msa_prepare.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+            L.pmh_msa_run_group.argtypes = [vp, vp, C.c_char_p, C.c_size_t]
+            h = L.pmh_msa_prepare(fasta, len(fasta), newick.encode(), reference.encode(), int(low_mem_mode), err, 512)
+            if h and L.pmh_msa_run_group(ctx.h, h, err, 512) != 0:
+                L.pmh_build_free(h)
+                h = None
+        else:
+            h = L.pmh_build_from_msa(ctx.h, fasta, len(fasta), newick.encode(), reference.encode(), int(low_mem_mode), err, 512)
         if not h:
             raise RuntimeError(err.value.decode())
         self.tree = HostTree(L.pmh_build_tree(h), owned=False)

@@ -359,8 +359,10 @@ static pmh_build* msa_prepare_impl(const char* fasta, size_t fasta_len, const ch
     return b;
 }
 
-static int msa_run_impl(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
-    if (!ctx || !b) { set_err(err, err_len, "null argument"); return PMB_ERR_INVALID; }
+// one device (ctx) or the GPUs of a box (grp): the same flow on either engine
+static int msa_run_impl(pmb_ctx* ctx, pmb_group* grp, pmh_build* b, char* err, size_t err_len) {
+    if ((!ctx && !grp) || !b) { set_err(err, err_len, "null argument"); return PMB_ERR_INVALID; }
+    auto engine_error = [&]() { return std::string(grp ? pmb_group_last_error(grp) : pmb_last_error(ctx)); };
     auto fail = [&](const std::string& m) -> int {
         set_err(err, err_len, m);
         return PMB_ERR_INVALID;
@@ -378,13 +380,17 @@ static int msa_run_impl(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
 
     // ---- the passes
     auto t0 = Clock::now();
-    int rc = pmb_set_tree(ctx, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data());
-    if (rc) return fail(std::string("pmb_set_tree: ") + pmb_last_error(ctx));
+    int rc = grp ? pmb_group_set_tree(grp, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data())
+                 : pmb_set_tree(ctx, T.n_nodes(), T.root, T.child_off.data(), T.child_idx.data(), T.leaf_row.data());
+    if (rc) return fail(std::string("pmb_set_tree: ") + engine_error());
     bool all_present = std::all_of(present.begin(), present.end(), [](uint8_t x) { return x != 0; });
     pmb_result res;
-    rc = pmb_run_nuc(ctx, low_mem_mode ? PMB_ALGO_SANKOFF : PMB_ALGO_FITCH, n_cols, T.n_leaves, codes4, stride,
-                     all_present ? nullptr : present.data(), parent_code.data(), root_override, fwd_root_ref, 0, 0, &res);
-    if (rc) return fail(std::string("pmb_run_nuc: ") + pmb_last_error(ctx));
+    const int algo = low_mem_mode ? PMB_ALGO_SANKOFF : PMB_ALGO_FITCH;
+    rc = grp ? pmb_group_run_nuc(grp, algo, n_cols, T.n_leaves, codes4, stride, all_present ? nullptr : present.data(), parent_code.data(),
+                                 root_override, fwd_root_ref, 0, &res)
+             : pmb_run_nuc(ctx, algo, n_cols, T.n_leaves, codes4, stride, all_present ? nullptr : present.data(), parent_code.data(),
+                           root_override, fwd_root_ref, 0, 0, &res);
+    if (rc) return fail(std::string("pmb_run_nuc: ") + engine_error());
     b->seconds[2] = since(t0);
     pin_release(b->codes4, b->codes_cached);  // uploaded: the page-locked buffer can serve the next build
     b->codes4 = nullptr;
@@ -397,8 +403,8 @@ static int msa_run_impl(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
     b->tuple_tc.assign(res.type_code, res.type_code + res.n_mut);
     // greedy <= 6 run-merge on the device (pmb_merge_runs; src/panman.cpp:1445-1466, NucMut ctor src/panman.hpp:109-151)
     pmb_nucmut_result mr;
-    rc = pmb_merge_runs(ctx, /*source*/0, /*to_host*/1, &mr);
-    if (rc) return fail(std::string("pmb_merge_runs: ") + pmb_last_error(ctx));
+    rc = grp ? pmb_group_merge_runs(grp, /*to_host*/1, &mr) : pmb_merge_runs(ctx, /*source*/0, /*to_host*/1, &mr);
+    if (rc) return fail(std::string("pmb_merge_runs: ") + engine_error());
     for (int32_t v = 0; v < T.n_nodes(); v++) {
         const int64_t a = mr.node_offsets[v], z = mr.node_offsets[v + 1];
         b->nuc[v].resize(size_t(z - a));
@@ -446,9 +452,20 @@ pmh_build* pmh_msa_prepare(const char* fasta, size_t fasta_len, const char* newi
         return nullptr;
     }
 }
+int pmh_msa_run_group(pmb_group* group, pmh_build* b, char* err, size_t err_len) {
+    try {
+        return msa_run_impl(nullptr, group, b, err, err_len);
+    } catch (const std::bad_alloc&) {
+        set_err(err, err_len, "out of host memory");
+        return PMB_ERR_OOM;
+    } catch (const std::exception& ex) {
+        set_err(err, err_len, std::string("pmh_msa_run_group: ") + ex.what());
+        return PMB_ERR_INVALID;
+    }
+}
 int pmh_msa_run(pmb_ctx* ctx, pmh_build* b, char* err, size_t err_len) {
     try {
-        return msa_run_impl(ctx, b, err, err_len);
+        return msa_run_impl(ctx, nullptr, b, err, err_len);
     } catch (const std::bad_alloc&) {
         set_err(err, err_len, "out of host memory");
         return PMB_ERR_OOM;

@@ -118,14 +118,16 @@ def test_msa_prepare_on_the_host(low_mem, parallel_bytes):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["ctx", "group"])
 @pytest.mark.parametrize("low_mem", [False, True])
-def test_msa_build_matches_reference_flow(port, ref, low_mem):
+def test_msa_build_matches_reference_flow(port, ref, low_mem, engine):
     """End to end -M flow (reader, consensus, packing, pmb_run_nuc, run-merge) against the restated reference drivers
-    around the verbatim fitchSankoff.cpp and the oracle's run-merge (reference src/panman.cpp:1274-1466, 1467-1649)."""
+    around the verbatim fitchSankoff.cpp and the oracle's run-merge (reference src/panman.cpp:1274-1466, 1467-1649).
+    engine "group": the same through pmh_msa_run_group, the column ranges over a three-rank pmb_group."""
     import panman_b200 as pb
     from panman_b200.host import MsaBuild
 
-    ctx = pb.Context(0)
+    ctx = pb.Context(0) if engine == "ctx" else pb.Group([0, 0, 0])
     rng = np.random.default_rng(21 + int(low_mem))
     alphabet = np.frombuffer(b"ACGTN-ACGTACGTRYKM", np.uint8)
     for trial in range(8):
