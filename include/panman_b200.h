@@ -291,6 +291,53 @@ int pmb_group_run_nuc(pmb_group* group, int algo, int64_t n_cols, int32_t n_rows
                       int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
                       const int8_t* fwd_root_ref, int flags, pmb_result* out);
 
+/* ---- a denser form of the same input at the boundary: the clade-run encoding ("pmb_runs") ----
+ * The nibble matrix above is what crosses PCIe in pmb_run_nuc: 0.5 byte per leaf and column, the end-to-end limit of a
+ * pass that itself runs at the HBM roofline. A phylogenetic alignment is far more regular than that: with the leaves in
+ * depth-first order of the tree a clade is a run of consecutive rows, and inside a column a leaf almost always carries
+ * the code of the leaf before it. pmb_runs_encode walks the rows of a HOST nibble matrix in that order and keeps, per
+ * tile of 1024 columns, only the places where (code XOR parent_code) changes from one leaf to the next -- a few events
+ * per column (in the order of the column's parsimony score) instead of one nibble per leaf. The device rebuilds exactly
+ * the bit-planes pmb_upload_nuc would have produced (expand_runs_kernel), so every result is bit-identical; only the
+ * bytes that cross the link differ. Pure host-side data preparation, like the nibble packing it stands in for: it needs no
+ * device (the buffers are page-locked when there is one) and takes the tree by value, not a context.
+ * The reference has no counterpart (its columns are read out of std::string sequences, src/panman.cpp:1396-1418). */
+typedef struct pmb_runs pmb_runs;
+typedef struct pmb_runs_info {
+    int64_t n_cols;
+    int32_t n_rows, n_tiles, n_segments, seg_rows; /* events are grouped per (tile, segment of seg_rows leaves) */
+    int64_t n_events;
+    int64_t bytes;                /* what an upload of the whole batch moves: events + item offsets */
+    const uint32_t* events;       /* row in segment << 14 | column in tile << 4 | xor nibble */
+    const int64_t* item_offsets;  /* n_tiles * n_segments + 1 */
+} pmb_runs_info;
+/* Tree arguments as pmb_set_tree, matrix arguments as pmb_run_nuc (host memory). n_threads <= 0: all cores. */
+int pmb_runs_encode(int32_t n_nodes, int32_t root, const int32_t* child_offsets, const int32_t* child_index, const int32_t* leaf_row,
+                    int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes, const uint8_t* parent_code,
+                    int n_threads, pmb_runs** out);
+void pmb_runs_free(pmb_runs* runs);
+int pmb_runs_describe(const pmb_runs* runs, pmb_runs_info* out);
+/* As pmb_upload_nuc / pmb_upload_nuc_async / pmb_run_nuc with the leaf codes taken from `runs`: columns
+ * [col_begin, col_begin + n_cols) of the encoded batch (col_begin a multiple of 1024; the range ends on a multiple of 1024 or
+ * with the batch). parent_code / root_override / fwd_root_ref point at the RANGE's first column; parent_code must be the
+ * one the batch was encoded against. The context's tree must be the tree of the encoding (PMB_ERR_INVALID otherwise). */
+int pmb_upload_runs(pmb_ctx* ctx, const pmb_runs* runs, int64_t col_begin, int64_t n_cols, const uint8_t* leaf_present,
+                    const uint8_t* parent_code, const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base);
+int pmb_upload_runs_async(pmb_ctx* ctx, const pmb_runs* runs, int64_t col_begin, int64_t n_cols, const uint8_t* leaf_present,
+                          const uint8_t* parent_code, const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base);
+int pmb_run_runs(pmb_ctx* ctx, int algo, const pmb_runs* runs, const uint8_t* leaf_present, const uint8_t* parent_code,
+                 const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base, int flags, pmb_result* out);
+/* Over a group. pmb_group_upload_runs: `runs` encodes the WHOLE alignment, every local rank takes the tiles of its own
+ * column range (only those events cross its link). pmb_group_upload_shard_runs: `shard_runs` encodes one local rank's
+ * range only (one process per GPU: every rank encodes and uploads its own). pmb_group_run_runs = upload + step + download. */
+int pmb_group_upload_runs(pmb_group* group, const pmb_runs* runs, const uint8_t* leaf_present, const uint8_t* parent_code,
+                          const int8_t* root_override, const int8_t* fwd_root_ref);
+int pmb_group_upload_shard_runs(pmb_group* group, int local_index, int64_t n_cols_total, const pmb_runs* shard_runs,
+                                const uint8_t* leaf_present, const uint8_t* shard_parent_code, const int8_t* shard_root_override,
+                                const int8_t* shard_fwd_root_ref);
+int pmb_group_run_runs(pmb_group* group, int algo, const pmb_runs* runs, const uint8_t* leaf_present, const uint8_t* parent_code,
+                       const int8_t* root_override, const int8_t* fwd_root_ref, int flags, pmb_result* out);
+
 /* ---- introspection ---- */
 int pmb_last_timings(const pmb_ctx* ctx, pmb_timings* out);
 /* Bytes the roofline is computed on, for the resident input and `algo`:

@@ -4,7 +4,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .lib import GROUP_HANDLE_BYTES, load_library, pmb_nucmut_result, pmb_result, pmb_timings
+from .lib import GROUP_HANDLE_BYTES, load_library, pmb_nucmut_result, pmb_result, pmb_runs_info, pmb_timings
 
 ALGO_FITCH, ALGO_SANKOFF = 0, 1
 FLAG_WANT_STATES, FLAG_BLOCK_MODE = 1, 2
@@ -80,6 +80,88 @@ def column_range(world: int, n_cols: int, rank: int):
     if rc != 0:
         raise PanmanError(rc, "pmb_group_column_range: bad arguments")
     return int(a.value), int(b.value)
+
+
+class Runs:
+    """pmb_runs: the clade-run encoding of a HOST nibble matrix for one tree (pmb_runs_encode). Needs no device."""
+
+    def __init__(self, n_nodes, root, child_off, child_idx, leaf_row, n_cols, codes4, row_stride, parent_code, n_threads: int = 0):
+        self.L = load_library()
+        co = np.ascontiguousarray(child_off, np.int32)
+        ci = np.ascontiguousarray(child_idx, np.int32)
+        lr = np.ascontiguousarray(leaf_row, np.int32)
+        n_rows = int((lr >= 0).sum())
+        self.h = C.c_void_p()
+        rc = self.L.pmb_runs_encode(int(n_nodes), int(root), _ptr(co), _ptr(ci), _ptr(lr), int(n_cols), n_rows, _ptr(codes4), int(row_stride),
+                                    _ptr(parent_code), int(n_threads), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise PanmanError(rc, "pmb_runs_encode: bad arguments" if rc == -1 else "pmb_runs_encode failed")
+        self.info = pmb_runs_info()
+        self.L.pmb_runs_describe(self.h, C.byref(self.info))
+        self._tree = (int(n_nodes), int(root), co, ci, lr)
+
+    @classmethod
+    def of_tree(cls, tree, n_cols, codes4, parent_code, n_threads: int = 0):
+        return cls(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row, n_cols, codes4, codes4.shape[1], parent_code,
+                   n_threads)
+
+    n_cols = property(lambda self: int(self.info.n_cols))
+    n_rows = property(lambda self: int(self.info.n_rows))
+    n_events = property(lambda self: int(self.info.n_events))
+    nbytes = property(lambda self: int(self.info.bytes))
+
+    def events(self):
+        n = self.n_events
+        return np.ctypeslib.as_array(C.cast(self.info.events, C.POINTER(C.c_uint32)), (max(n, 1),))[:n]
+
+    def item_offsets(self):
+        n = self.info.n_tiles * self.info.n_segments + 1
+        return np.ctypeslib.as_array(C.cast(self.info.item_offsets, C.POINTER(C.c_int64)), (n,))
+
+    def dfs_rows(self):
+        """The caller's leaf rows in depth-first order of the tree (children in Newick order): the order of the encoding."""
+        _, root, co, ci, lr = self._tree
+        out, stack = [], [root]
+        while stack:
+            v = stack.pop()
+            a, z = int(co[v]), int(co[v + 1])
+            if a == z:
+                out.append(int(lr[v]))
+            else:
+                stack.extend(int(c) for c in ci[a:z][::-1])
+        return np.asarray(out, np.int64)
+
+    def decode(self, parent_code) -> np.ndarray:
+        """The (n_rows, n_cols) code matrix back from the events, the way expand_runs_kernel rebuilds it (test helper)."""
+        I = self.info
+        ev, off, order = self.events(), self.item_offsets(), self.dfs_rows()
+        pc = np.zeros(I.n_tiles * 1024, np.uint8)
+        pc[:I.n_cols] = np.asarray(parent_code, np.uint8)[:I.n_cols] & 15
+        out = np.zeros((I.n_rows, I.n_tiles * 1024), np.uint8)
+        for t in range(I.n_tiles):
+            base = pc[t * 1024:(t + 1) * 1024]
+            for sg in range(I.n_segments):
+                e = ev[off[t * I.n_segments + sg]:off[t * I.n_segments + sg + 1]]
+                r0 = sg * I.seg_rows
+                nr = min(I.seg_rows, I.n_rows - r0)
+                rows, cols, x = (e >> 14).astype(np.int64), ((e >> 4) & 1023).astype(np.int64), (e & 15).astype(np.uint8)
+                assert bool((np.diff(rows) >= 0).all()) and (len(rows) == 0 or rows[-1] < nr)
+                delta = np.zeros((nr, 1024), np.uint8)
+                np.bitwise_xor.at(delta, (rows, cols), x)
+                out[order[r0:r0 + nr], t * 1024:(t + 1) * 1024] = np.bitwise_xor.accumulate(delta, 0) ^ base[None, :]
+        return out[:, :I.n_cols]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pmb_runs_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -216,6 +298,20 @@ class Context:
                                        int(col_base), int(flags), C.byref(r)))
         return self._result(r, copy)
 
+    def upload_runs(self, runs: Runs, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None, col_begin=0, n_cols=None,
+                    col_base=0, sync=True):
+        n = runs.n_cols - int(col_begin) if n_cols is None else int(n_cols)
+        f = self.L.pmb_upload_runs if sync else self.L.pmb_upload_runs_async
+        self._check(f(self.h, runs.h, int(col_begin), n, _ptr(leaf_present), _ptr(parent_code), _ptr(root_override), _ptr(fwd_root_ref),
+                      int(col_base)))
+
+    def run_runs(self, algo, runs: Runs, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None, col_base=0, flags=0,
+                 copy=True) -> Result:
+        r = pmb_result()
+        self._check(self.L.pmb_run_runs(self.h, int(algo), runs.h, _ptr(leaf_present), _ptr(parent_code), _ptr(root_override),
+                                        _ptr(fwd_root_ref), int(col_base), int(flags), C.byref(r)))
+        return self._result(r, copy)
+
     # convenience for tests: unpacked codes, numpy everywhere
     def run_codes(self, tree, algo, codes, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None, block_mode=0,
                   want_states=False, col_base=0) -> Result:
@@ -300,6 +396,21 @@ class Group:
         self._check(self.L.pmb_group_upload_shard(self.h, int(local_index), int(n_cols_total), int(n_rows), _ptr(codes4),
                                                   int(row_stride), _ptr(leaf_present), _ptr(parent_code), _ptr(root_override),
                                                   _ptr(fwd_root_ref)))
+
+    def upload_runs(self, runs: Runs, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None):
+        self._check(self.L.pmb_group_upload_runs(self.h, runs.h, _ptr(leaf_present), _ptr(parent_code), _ptr(root_override),
+                                                 _ptr(fwd_root_ref)))
+
+    def upload_shard_runs(self, local_index, n_cols_total, runs: Runs, parent_code, root_override=None, fwd_root_ref=None,
+                          leaf_present=None):
+        self._check(self.L.pmb_group_upload_shard_runs(self.h, int(local_index), int(n_cols_total), runs.h, _ptr(leaf_present),
+                                                       _ptr(parent_code), _ptr(root_override), _ptr(fwd_root_ref)))
+
+    def run_runs(self, algo, runs: Runs, parent_code, root_override=None, fwd_root_ref=None, leaf_present=None, flags=0, copy=True) -> Result:
+        r = pmb_result()
+        self._check(self.L.pmb_group_run_runs(self.h, int(algo), runs.h, _ptr(leaf_present), _ptr(parent_code), _ptr(root_override),
+                                              _ptr(fwd_root_ref), int(flags), C.byref(r)))
+        return Context._result(None, r, copy)
 
     def run_async(self, algo=ALGO_FITCH, flags=0):
         self._check(self.L.pmb_group_run_async(self.h, int(algo), int(flags)))

@@ -12,6 +12,7 @@
 
 #include "../../include/panman_b200.h"
 #include "pmb_kernels.cuh"
+#include "pmb_runs.h"
 #include "tree_program.h"
 
 using namespace pmb;
@@ -178,6 +179,10 @@ struct pmb_ctx {
     int32_t T = 0;
     bool have_present = false;
     DevBuf d_leaf_planes, d_present, d_colparams, d_tmp_codes, d_tmp_cols;
+    // clade-run encoded input (pmb_upload_runs): the tree's leaves in depth-first order, the events of the resident range
+    std::vector<int32_t> dfs_rows, h_dfs_slot;
+    uint64_t dfs_hash = 0;
+    DevBuf d_run_events, d_run_off, d_dfs_slot;
 
     // work + result
     DevBuf d_done, d_fdone, d_ticket, d_block_sums;
@@ -491,7 +496,8 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_states_planes, &c->d_dir, &c->d_staging, &c->d_counters, &c->d_offsets,
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
-                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums, &c->d_mrel})
+                          &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums, &c->d_mrel,
+                          &c->d_run_events, &c->d_run_off, &c->d_dfs_slot})
             b->release();
         for (auto& s : c->prog_cache)
             for (DevBuf& b : s.bufs) b.release();
@@ -574,6 +580,8 @@ static int set_tree_impl(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_
     c->child_off.assign(child_offsets, child_offsets + n_nodes + 1);
     c->child_idx.assign(child_index, child_index + child_offsets[n_nodes]);
     c->leaf_row.assign(leaf_row, leaf_row + n_nodes);
+    c->dfs_rows = dfs_leaf_rows(n_nodes, root, child_offsets, child_index, leaf_row);
+    c->dfs_hash = leaf_order_hash(c->dfs_rows);
     c->prog = std::move(probe);
     c->prog_chunk_nodes = -1;  // (re)built for the tile count at upload time
     if (!c->prog_cache.empty()) {  // programs of the previous tree
@@ -603,15 +611,24 @@ int pmb_set_tree(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_t* child
     PMB_GUARDED(c, set_tree_impl(c, n_nodes, root, child_offsets, child_index, leaf_row))
 }
 
+// The leaf codes come either as a nibble matrix (leaf_codes_4bit) or clade-run encoded (runs, columns from runs_col_begin on).
 static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
                        const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override,
-                       const int8_t* fwd_root_ref, int64_t col_base, bool sync) {
+                       const int8_t* fwd_root_ref, int64_t col_base, bool sync, const pmb_runs* runs = nullptr,
+                       int64_t runs_col_begin = 0) {
     if (!c) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
-    if (n_cols <= 0 || !leaf_codes_4bit || !parent_code) return fail(c, PMB_ERR_INVALID, "bad input arguments");
+    if (n_cols <= 0 || (!leaf_codes_4bit && !runs) || !parent_code) return fail(c, PMB_ERR_INVALID, "bad input arguments");
     if (n_rows != c->prog.n_rows) return fail(c, PMB_ERR_INVALID, "n_rows does not match the tree's leaf count");
-    if (row_stride_bytes < (n_cols + 1) / 2) return fail(c, PMB_ERR_INVALID, "row_stride_bytes too small");
+    if (!runs && row_stride_bytes < (n_cols + 1) / 2) return fail(c, PMB_ERR_INVALID, "row_stride_bytes too small");
+    if (runs) {
+        if (runs->order_hash != c->dfs_hash || runs->n_rows != n_rows)
+            return fail(c, PMB_ERR_INVALID, "the batch was encoded for another tree (leaf order differs)");
+        if (runs_col_begin < 0 || runs_col_begin % TILE_COLS != 0 || runs_col_begin + n_cols > runs->n_cols ||
+            (runs_col_begin + n_cols != runs->n_cols && n_cols % TILE_COLS != 0))
+            return fail(c, PMB_ERR_INVALID, "a column range of an encoded batch starts on a multiple of 1024 and ends on one or with the batch");
+    }
     if (n_cols > (int64_t(1) << 40)) return fail(c, PMB_ERR_INVALID, "n_cols too large");
     PMB_CUDA(cudaSetDevice(c->device));
     // passes still in flight on the backward / compaction streams read what is overwritten here
@@ -628,6 +645,20 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
     if (rc) return rc;
     const size_t plane_bytes = size_t(n_rows) * c->T * 32 * sizeof(uint4);
     PMB_CUDA(c->d_leaf_planes.ensure(plane_bytes));
+    PMB_CUDA(c->d_tmp_cols.ensure(size_t(n_cols) * 3));
+    uint8_t* t = c->d_tmp_cols.as<uint8_t>();
+    PMB_CUDA(cudaMemcpyAsync(t, parent_code, size_t(n_cols), cudaMemcpyDefault, c->stream));
+    if (root_override) PMB_CUDA(cudaMemcpyAsync(t + n_cols, root_override, size_t(n_cols), cudaMemcpyDefault, c->stream));
+    if (fwd_root_ref) PMB_CUDA(cudaMemcpyAsync(t + 2 * n_cols, fwd_root_ref, size_t(n_cols), cudaMemcpyDefault, c->stream));
+    PMB_CUDA(c->d_colparams.ensure(size_t(c->T) * 128 * sizeof(uint4)));
+    {
+        long long threads = (long long)c->T * 32 * 32;
+        unsigned blocks = unsigned((threads + 255) / 256);
+        pack_colparams_kernel<<<blocks, 256, 0, c->stream>>>(t, root_override ? reinterpret_cast<const int8_t*>(t + n_cols) : nullptr,
+                                                             fwd_root_ref ? reinterpret_cast<const int8_t*>(t + 2 * n_cols) : nullptr,
+                                                             n_cols, c->T, c->d_colparams.as<uint4>());
+    }
+    PMB_CUDA(cudaGetLastError());
     // Where does the nibble matrix live? Device memory and pinned (or registered) host memory are read by the packing
     // kernel in place -- for pinned memory that fuses the host-to-device transfer with the transposition, one pass at
     // PCIe speed and no staging buffer. Pageable host memory is staged through a bounded device buffer.
@@ -636,7 +667,7 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
     // speed of the PCIe copy alone (measured on B200: the kernel reading pinned memory in place reaches 47 GB/s, the copy
     // engine 54 GB/s; tools/e2e_breakdown.py). Pageable memory takes the same path at the driver's staging speed.
     bool on_device = false;
-    {
+    if (!runs) {
         cudaPointerAttributes attr{};
         if (cudaPointerGetAttributes(&attr, leaf_codes_4bit) == cudaSuccess)
             on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
@@ -649,7 +680,24 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
         pack_leaves_kernel<<<blocks, 256, 0, c->stream>>>(src, src_stride, r0, nr, n_rows, n_cols, c->T, c->d_row_slot.as<int>(),
                                                           c->d_leaf_planes.as<uint4>());
     };
-    if (on_device) {
+    if (runs) {
+        // events of the range's tiles -> device, then one kernel rebuilds the planes the dense path would have packed
+        const long long n_items = (long long)c->T * runs->n_seg, item0 = (runs_col_begin / TILE_COLS) * runs->n_seg;
+        const long long ev_base = runs->item_off[item0], n_ev = runs->item_off[item0 + n_items] - ev_base;
+        PMB_CUDA(c->d_run_events.ensure(size_t(std::max<long long>(n_ev, 4)) * sizeof(uint32_t)));
+        PMB_CUDA(c->d_run_off.ensure(size_t(n_items + 1) * sizeof(long long)));
+        PMB_CUDA(c->d_dfs_slot.ensure(size_t(n_rows) * sizeof(int)));
+        c->h_dfs_slot.resize(size_t(n_rows));
+        for (int32_t i = 0; i < n_rows; i++) c->h_dfs_slot[size_t(i)] = c->prog.row_slot[size_t(c->dfs_rows[size_t(i)])];
+        if (n_ev > 0)
+            PMB_CUDA(cudaMemcpyAsync(c->d_run_events.p, runs->events + ev_base, size_t(n_ev) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->d_run_off.p, runs->item_off + item0, size_t(n_items + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->d_dfs_slot.p, c->h_dfs_slot.data(), size_t(n_rows) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        const unsigned blocks = unsigned((n_items * 32 + 255) / 256);
+        expand_runs_kernel<<<blocks, 256, 0, c->stream>>>(c->d_run_events.as<uint32_t>(), c->d_run_off.as<long long>(), ev_base, n_items,
+                                                          runs->n_seg, runs->seg_rows, n_rows, c->d_dfs_slot.as<int>(),
+                                                          c->d_colparams.as<uint4>(), c->d_leaf_planes.as<uint4>());
+    } else if (on_device) {
         pack(leaf_codes_4bit, row_stride_bytes, 0, n_rows);
     } else {
         // Only the batch's own columns cross the link: a slab holds rows of (n_cols + 1) / 2 bytes at a 16-byte pitch, whatever
@@ -694,20 +742,6 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
         PMB_CUDA(c->d_present.ensure(size_t(n_rows)));
         PMB_CUDA(cudaMemcpy(c->d_present.p, by_slot.data(), size_t(n_rows), cudaMemcpyHostToDevice));
     }
-    PMB_CUDA(c->d_tmp_cols.ensure(size_t(n_cols) * 3));
-    uint8_t* t = c->d_tmp_cols.as<uint8_t>();
-    PMB_CUDA(cudaMemcpyAsync(t, parent_code, size_t(n_cols), cudaMemcpyDefault, c->stream));
-    if (root_override) PMB_CUDA(cudaMemcpyAsync(t + n_cols, root_override, size_t(n_cols), cudaMemcpyDefault, c->stream));
-    if (fwd_root_ref) PMB_CUDA(cudaMemcpyAsync(t + 2 * n_cols, fwd_root_ref, size_t(n_cols), cudaMemcpyDefault, c->stream));
-    PMB_CUDA(c->d_colparams.ensure(size_t(c->T) * 128 * sizeof(uint4)));
-    {
-        long long threads = (long long)c->T * 32 * 32;
-        unsigned blocks = unsigned((threads + 255) / 256);
-        pack_colparams_kernel<<<blocks, 256, 0, c->stream>>>(t, root_override ? reinterpret_cast<const int8_t*>(t + n_cols) : nullptr,
-                                                             fwd_root_ref ? reinterpret_cast<const int8_t*>(t + 2 * n_cols) : nullptr,
-                                                             n_cols, c->T, c->d_colparams.as<uint4>());
-    }
-    PMB_CUDA(cudaGetLastError());
     if (sync) PMB_CUDA(cudaStreamSynchronize(c->stream));  // inputs were borrowed: they may be released on return
     c->upload_pending = !sync;
     c->have_input = true;
@@ -1127,6 +1161,29 @@ int pmb_run_nuc(pmb_ctx* c, int algo, int64_t n_cols, int32_t n_rows, const uint
                 const int8_t* fwd_root_ref, int64_t col_base, int flags, pmb_result* out) {
     int rc = pmb_upload_nuc(c, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override,
                             fwd_root_ref, col_base);
+    if (rc) return rc;
+    if ((rc = pmb_run_resident(c, algo, flags))) return rc;
+    return pmb_download(c, out);
+}
+
+int pmb_upload_runs(pmb_ctx* c, const pmb_runs* runs, int64_t col_begin, int64_t n_cols, const uint8_t* leaf_present,
+                    const uint8_t* parent_code, const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base) {
+    if (!runs) return c ? fail(c, PMB_ERR_INVALID, "null runs") : PMB_ERR_INVALID;
+    PMB_GUARDED(c, upload_impl(c, n_cols, runs->n_rows, nullptr, 0, leaf_present, parent_code, root_override, fwd_root_ref, col_base, true,
+                               runs, col_begin))
+}
+
+int pmb_upload_runs_async(pmb_ctx* c, const pmb_runs* runs, int64_t col_begin, int64_t n_cols, const uint8_t* leaf_present,
+                          const uint8_t* parent_code, const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base) {
+    if (!runs) return c ? fail(c, PMB_ERR_INVALID, "null runs") : PMB_ERR_INVALID;
+    PMB_GUARDED(c, upload_impl(c, n_cols, runs->n_rows, nullptr, 0, leaf_present, parent_code, root_override, fwd_root_ref, col_base, false,
+                               runs, col_begin))
+}
+
+int pmb_run_runs(pmb_ctx* c, int algo, const pmb_runs* runs, const uint8_t* leaf_present, const uint8_t* parent_code,
+                 const int8_t* root_override, const int8_t* fwd_root_ref, int64_t col_base, int flags, pmb_result* out) {
+    if (!runs) return c ? fail(c, PMB_ERR_INVALID, "null runs") : PMB_ERR_INVALID;
+    int rc = pmb_upload_runs(c, runs, 0, runs->n_cols, leaf_present, parent_code, root_override, fwd_root_ref, col_base);
     if (rc) return rc;
     if ((rc = pmb_run_resident(c, algo, flags))) return rc;
     return pmb_download(c, out);

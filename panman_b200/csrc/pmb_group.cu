@@ -456,9 +456,12 @@ int pmb_group_connect(pmb_group* g, const void* all_handles) {
     return PMB_OK;
 }
 
-int pmb_group_upload_shard(pmb_group* g, int local_index, int64_t n_cols_total, int32_t n_rows, const uint8_t* shard_codes_4bit,
-                           int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* shard_parent_code,
-                           const int8_t* shard_root_override, const int8_t* shard_fwd_root_ref) {
+// one local rank's range, from a nibble matrix of the range (shard_codes_4bit) or from an encoded batch (runs: the range's
+// columns start at runs_col_begin of it)
+static int upload_shard_impl(pmb_group* g, int local_index, int64_t n_cols_total, int32_t n_rows, const uint8_t* shard_codes_4bit,
+                             int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* shard_parent_code,
+                             const int8_t* shard_root_override, const int8_t* shard_fwd_root_ref, const pmb_runs* runs,
+                             int64_t runs_col_begin) {
     if (!g || local_index < 0 || local_index >= g->n_local || n_cols_total <= 0) return PMB_ERR_INVALID;
     if (!g->have_tree) return gfail(g, PMB_ERR_NO_TREE, "pmb_group_set_tree has not been called");
     if (g->have_input && g->n_cols_total != n_cols_total) {  // a new alignment: every local rank must be given its range again
@@ -473,11 +476,49 @@ int pmb_group_upload_shard(pmb_group* g, int local_index, int64_t n_cols_total, 
     g->have_merged = false;
     l.active = e > b;
     if (l.active) {
-        int rc = pmb_upload_nuc_async(l.ctx, e - b, n_rows, shard_codes_4bit, row_stride_bytes, leaf_present, shard_parent_code,
-                                      shard_root_override, shard_fwd_root_ref, b);
+        int rc = runs ? pmb_upload_runs_async(l.ctx, runs, runs_col_begin, e - b, leaf_present, shard_parent_code, shard_root_override,
+                                              shard_fwd_root_ref, b)
+                      : pmb_upload_nuc_async(l.ctx, e - b, n_rows, shard_codes_4bit, row_stride_bytes, leaf_present, shard_parent_code,
+                                             shard_root_override, shard_fwd_root_ref, b);
         if (rc) return gctx(g, rc, l);
     }
     g->have_input = true;
+    return PMB_OK;
+}
+
+int pmb_group_upload_shard(pmb_group* g, int local_index, int64_t n_cols_total, int32_t n_rows, const uint8_t* shard_codes_4bit,
+                           int64_t row_stride_bytes, const uint8_t* leaf_present, const uint8_t* shard_parent_code,
+                           const int8_t* shard_root_override, const int8_t* shard_fwd_root_ref) {
+    return upload_shard_impl(g, local_index, n_cols_total, n_rows, shard_codes_4bit, row_stride_bytes, leaf_present, shard_parent_code,
+                             shard_root_override, shard_fwd_root_ref, nullptr, 0);
+}
+
+int pmb_group_upload_shard_runs(pmb_group* g, int local_index, int64_t n_cols_total, const pmb_runs* shard_runs, const uint8_t* leaf_present,
+                                const uint8_t* shard_parent_code, const int8_t* shard_root_override, const int8_t* shard_fwd_root_ref) {
+    if (!g || !shard_runs) return g ? gfail(g, PMB_ERR_INVALID, "null runs") : PMB_ERR_INVALID;
+    pmb_runs_info info{};
+    pmb_runs_describe(shard_runs, &info);
+    int64_t b, e;
+    if (local_index >= 0 && local_index < g->n_local) {
+        range_of(g->world, n_cols_total, g->rank_base + local_index, &b, &e);
+        if (e > b && info.n_cols != e - b) return gfail(g, PMB_ERR_INVALID, "the encoded shard does not cover the rank's column range");
+    }
+    return upload_shard_impl(g, local_index, n_cols_total, info.n_rows, nullptr, 0, leaf_present, shard_parent_code, shard_root_override,
+                             shard_fwd_root_ref, shard_runs, 0);
+}
+
+int pmb_group_upload_runs(pmb_group* g, const pmb_runs* runs, const uint8_t* leaf_present, const uint8_t* parent_code,
+                          const int8_t* root_override, const int8_t* fwd_root_ref) {
+    if (!g || !runs || !parent_code) return g ? gfail(g, PMB_ERR_INVALID, "bad input arguments") : PMB_ERR_INVALID;
+    pmb_runs_info info{};
+    pmb_runs_describe(runs, &info);
+    for (int i = 0; i < g->n_local; i++) {
+        int64_t b, e;
+        range_of(g->world, info.n_cols, g->rank_base + i, &b, &e);
+        int rc = upload_shard_impl(g, i, info.n_cols, info.n_rows, nullptr, 0, leaf_present, parent_code + b, root_override ? root_override + b : nullptr,
+                                   fwd_root_ref ? fwd_root_ref + b : nullptr, runs, b);
+        if (rc) return rc;
+    }
     return PMB_OK;
 }
 
@@ -598,6 +639,8 @@ int pmb_group_merge_runs(pmb_group* g, int to_host, pmb_nucmut_result* out) {
     return rc ? gctx(g, rc, g->local[0]) : PMB_OK;
 }
 
+static int step_after_upload(pmb_group* g, int algo, int flags, pmb_result* out);
+
 int pmb_group_run_nuc(pmb_group* g, int algo, int64_t n_cols, int32_t n_rows, const uint8_t* leaf_codes_4bit, int64_t row_stride_bytes,
                       const uint8_t* leaf_present, const uint8_t* parent_code, const int8_t* root_override, const int8_t* fwd_root_ref,
                       int flags, pmb_result* out) {
@@ -605,6 +648,20 @@ int pmb_group_run_nuc(pmb_group* g, int algo, int64_t n_cols, int32_t n_rows, co
     int rc = pmb_group_upload_nuc(g, n_cols, n_rows, leaf_codes_4bit, row_stride_bytes, leaf_present, parent_code, root_override,
                                   fwd_root_ref);
     if (rc) return rc;
+    return step_after_upload(g, algo, flags, out);
+}
+
+int pmb_group_run_runs(pmb_group* g, int algo, const pmb_runs* runs, const uint8_t* leaf_present, const uint8_t* parent_code,
+                       const int8_t* root_override, const int8_t* fwd_root_ref, int flags, pmb_result* out) {
+    if (!g || !out) return PMB_ERR_INVALID;
+    int rc = pmb_group_upload_runs(g, runs, leaf_present, parent_code, root_override, fwd_root_ref);
+    if (rc) return rc;
+    return step_after_upload(g, algo, flags, out);
+}
+
+// one step on the resident input + download, sizing the mailbox on the way where the group can do that by itself
+static int step_after_upload(pmb_group* g, int algo, int flags, pmb_result* out) {
+    int rc;
     if (g->world > 1 && g->capacity == 0) {
         // no mailbox yet: only a single-process group can size one by itself (a first pass, then the largest shard + 25 %)
         if (g->n_local != g->world) return gfail(g, PMB_ERR_NO_INPUT, "pmb_group_reserve / export / connect must precede the first step of a multi-process group");

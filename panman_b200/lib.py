@@ -15,7 +15,9 @@ EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb
            "pmb_group_create", "pmb_group_destroy", "pmb_group_last_error", "pmb_group_world", "pmb_group_ctx",
            "pmb_group_column_range", "pmb_group_set_tree", "pmb_group_reserve", "pmb_group_export", "pmb_group_connect",
            "pmb_group_upload_nuc", "pmb_group_upload_shard", "pmb_group_run_async", "pmb_group_wait",
-           "pmb_group_result_device", "pmb_group_download", "pmb_group_merge_runs", "pmb_group_run_nuc"]
+           "pmb_group_result_device", "pmb_group_download", "pmb_group_merge_runs", "pmb_group_run_nuc",
+           "pmb_runs_encode", "pmb_runs_free", "pmb_runs_describe", "pmb_upload_runs", "pmb_upload_runs_async", "pmb_run_runs",
+           "pmb_group_upload_runs", "pmb_group_upload_shard_runs", "pmb_group_run_runs"]
 GROUP_HANDLE_BYTES = 128
 
 
@@ -27,6 +29,11 @@ class pmb_result(C.Structure):
 class pmb_nucmut_result(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_nodes", C.c_int32), ("reserved", C.c_int32), ("node_offsets", C.c_void_p),
                 ("nuc_position", C.c_void_p), ("mut_info", C.c_void_p), ("nucs", C.c_void_p), ("mut_info_wire", C.c_void_p)]
+
+
+class pmb_runs_info(C.Structure):
+    _fields_ = [("n_cols", C.c_int64), ("n_rows", C.c_int32), ("n_tiles", C.c_int32), ("n_segments", C.c_int32), ("seg_rows", C.c_int32),
+                ("n_events", C.c_int64), ("bytes", C.c_int64), ("events", C.c_void_p), ("item_offsets", C.c_void_p)]
 
 
 class pmb_timings(C.Structure):
@@ -112,5 +119,15 @@ def load_library():
     L.pmb_group_download.argtypes = [vp, C.POINTER(pmb_result)]
     L.pmb_group_merge_runs.argtypes = [vp, C.c_int, C.POINTER(pmb_nucmut_result)]
     L.pmb_group_run_nuc.argtypes = [vp, C.c_int, i64, i32, vp, i64, vp, vp, vp, vp, C.c_int, C.POINTER(pmb_result)]
+    L.pmb_runs_encode.argtypes = [i32, i32, vp, vp, vp, i64, i32, vp, i64, vp, C.c_int, C.POINTER(vp)]
+    L.pmb_runs_free.argtypes = [vp]
+    L.pmb_runs_free.restype = None
+    L.pmb_runs_describe.argtypes = [vp, C.POINTER(pmb_runs_info)]
+    L.pmb_upload_runs.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i64]
+    L.pmb_upload_runs_async.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i64]
+    L.pmb_run_runs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, i64, C.c_int, C.POINTER(pmb_result)]
+    L.pmb_group_upload_runs.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pmb_group_upload_shard_runs.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp]
+    L.pmb_group_run_runs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(pmb_result)]
     _lib = L
     return L
