@@ -689,14 +689,33 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
         PMB_CUDA(c->d_dfs_slot.ensure(size_t(n_rows) * sizeof(int)));
         c->h_dfs_slot.resize(size_t(n_rows));
         for (int32_t i = 0; i < n_rows; i++) c->h_dfs_slot[size_t(i)] = c->prog.row_slot[size_t(c->dfs_rows[size_t(i)])];
-        if (n_ev > 0)
-            PMB_CUDA(cudaMemcpyAsync(c->d_run_events.p, runs->events + ev_base, size_t(n_ev) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         PMB_CUDA(cudaMemcpyAsync(c->d_run_off.p, runs->item_off + item0, size_t(n_items + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
         PMB_CUDA(cudaMemcpyAsync(c->d_dfs_slot.p, c->h_dfs_slot.data(), size_t(n_rows) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        const unsigned blocks = unsigned((n_items * 32 + 255) / 256);
-        expand_runs_kernel<<<blocks, 256, 0, c->stream>>>(c->d_run_events.as<uint32_t>(), c->d_run_off.as<long long>(), ev_base, n_items,
-                                                          runs->n_seg, runs->seg_rows, n_rows, c->d_dfs_slot.as<int>(),
-                                                          c->d_colparams.as<uint4>(), c->d_leaf_planes.as<uint4>());
+        // the events cross the link in a few slabs of whole tiles on the copy stream, each expanded as soon as it is there
+        const int n_slabs = int(std::max<long long>(1, std::min<long long>(std::min<long long>(8, c->T), n_ev * 4 / (4 << 20))));
+        cudaStream_t copy = c->gstream[0];
+        for (int k = 0; k < 2; k++)
+            if (!c->ev_slab_copied[k]) PMB_CUDA(cudaEventCreateWithFlags(&c->ev_slab_copied[k], cudaEventDisableTiming));
+        PMB_CUDA(cudaEventRecord(c->ev_fork, c->stream));  // the event buffer may still be read by an earlier expansion
+        PMB_CUDA(cudaStreamWaitEvent(copy, c->ev_fork, 0));
+        for (int sl = 0; sl < n_slabs; sl++) {
+            const long long ia = (long long)c->T * sl / n_slabs * runs->n_seg, ib = (long long)c->T * (sl + 1) / n_slabs * runs->n_seg;
+            const long long ea = runs->item_off[item0 + ia] - ev_base, eb = runs->item_off[item0 + ib] - ev_base;
+            if (eb > ea) {
+                PMB_CUDA(cudaMemcpyAsync(c->d_run_events.as<uint32_t>() + ea, runs->events + ev_base + ea, size_t(eb - ea) * sizeof(uint32_t),
+                                         cudaMemcpyHostToDevice, copy));
+                PMB_CUDA(cudaEventRecord(c->ev_slab_copied[sl & 1], copy));
+                PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_slab_copied[sl & 1], 0));
+            }
+            if (ib > ia) {
+                const unsigned blocks = unsigned(((ib - ia) * 32 + 255) / 256);
+                expand_runs_kernel<<<blocks, 256, 0, c->stream>>>(c->d_run_events.as<uint32_t>(), c->d_run_off.as<long long>(), ev_base, ia, ib,
+                                                                  runs->n_seg, runs->seg_rows, n_rows, c->d_dfs_slot.as<int>(),
+                                                                  c->d_colparams.as<uint4>(), c->d_leaf_planes.as<uint4>());
+            }
+        }
+        PMB_CUDA(cudaEventRecord(c->ev_fork, copy));  // a later upload's copies into these buffers are ordered behind c->stream anyway;
+        PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));  // this joins the copy stream so that a wait on c->stream covers it
     } else if (on_device) {
         pack(leaf_codes_4bit, row_stride_bytes, 0, n_rows);
     } else {

@@ -2017,44 +2017,44 @@ __global__ void pack_leaves_kernel(const uint8_t* codes, long long row_stride, i
 // order): lane l keeps the running (code ^ parent code) of its 32 columns in four plane words, applies the toggle events
 // of each leaf as it comes to it (the events of an item are sorted by leaf) and stores parent planes ^ running planes as
 // that leaf's row: every row is one coalesced 512-byte store, the kernel is bound by writing the plane matrix.
-__global__ void expand_runs_kernel(const uint32_t* events, const long long* item_off, long long ev_base, long long n_items,
-                                   int n_seg, int seg_rows, int n_rows, const int* dfs_slot, const uint4* colparams, uint4* planes) {
+__global__ void __launch_bounds__(256, 8)
+expand_runs_kernel(const uint32_t* events, const long long* item_off, long long ev_base, long long item_begin, long long item_end,
+                   int n_seg, int seg_rows, int n_rows, const int* dfs_slot, const uint4* colparams, uint4* planes) {
     const int lane = threadIdx.x & 31;
-    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (item >= n_items) return;
+    const long long item = item_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (item >= item_end) return;
     const long long tile = item / n_seg;
     const int seg = int(item % n_seg);
     const int r0 = seg * seg_rows, nr = min(seg_rows, n_rows - r0);
-    const uint4 base = colparams[(size_t)tile * 128 + lane];  // parent code planes of the tile (pack_colparams_kernel)
+    uint4 cur = colparams[(size_t)tile * 128 + lane];  // parent code planes of the tile (pack_colparams_kernel) ^ running xor
     long long k = item_off[item] - ev_base;
     const long long k_end = item_off[item + 1] - ev_base;
     uint32_t ev = (k + lane < k_end) ? events[k + lane] : 0xFFFFFFFFu;  // the all-ones row never comes up: the list's end
     int j = 0;
-    uint4 run = make_uint4(0, 0, 0, 0);
+    uint32_t next_row = __shfl_sync(FULL, ev, 0) >> 14;  // row of the first event not yet applied (warp-uniform)
     uint4* out = planes + (size_t)tile * n_rows * 32 + lane;
     for (int rb = 0; rb < nr; rb += 32) {
         const int my_slot = (rb + lane < nr) ? dfs_slot[r0 + rb + lane] : 0;
         const int lim = min(32, nr - rb);
         for (int i = 0; i < lim; i++) {
-            const uint32_t r = uint32_t(rb + i);
-            for (;;) {
+            while (next_row == uint32_t(rb + i)) {  // a few per column in all, so on most rows not taken
                 const uint32_t e = __shfl_sync(FULL, ev, j);
-                if ((e >> 14) != r) break;
                 if (lane == int((e >> 9) & 31u)) {  // column in tile = bits 4..13; its lane = the upper five of them
                     const uint32_t bit = 1u << ((e >> 4) & 31u);
-                    run.x ^= (e & 1u) ? bit : 0u;
-                    run.y ^= (e & 2u) ? bit : 0u;
-                    run.z ^= (e & 4u) ? bit : 0u;
-                    run.w ^= (e & 8u) ? bit : 0u;
+                    cur.x ^= (e & 1u) ? bit : 0u;
+                    cur.y ^= (e & 2u) ? bit : 0u;
+                    cur.z ^= (e & 4u) ? bit : 0u;
+                    cur.w ^= (e & 8u) ? bit : 0u;
                 }
                 if (++j == 32) {
                     k += 32;
                     ev = (k + lane < k_end) ? events[k + lane] : 0xFFFFFFFFu;
                     j = 0;
                 }
+                next_row = __shfl_sync(FULL, ev, j) >> 14;
             }
             const int slot = __shfl_sync(FULL, my_slot, i);
-            out[(size_t)slot * 32] = make_uint4(base.x ^ run.x, base.y ^ run.y, base.z ^ run.z, base.w ^ run.w);
+            out[(size_t)slot * 32] = cur;
         }
     }
 }

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small end-to-end cases, every kernel path once -- Fitch / Sankoff, plain / presence mask / block mode / states, chain
-segments (speculating and waiting), level schedule, overflow retry, shard pack / merge, run-merge, the multi-rank group --
+segments (speculating and waiting), level schedule, overflow retry, shard pack / merge, run-merge, the multi-rank group,
+clade-run encoded input --
 for compute-sanitizer where the pool allows it, and always under the library's own guard bytes: PMB_DEBUG_CANARY=1 puts 256
 guard bytes around every device buffer and poisons its body, pmb_debug_check_canaries() counts the guard bytes a kernel
 overwrote (out-of-bounds writes), and the comparison with the oracle catches reads of memory nobody initialised.
@@ -46,6 +47,12 @@ def main():
                 res = ctx.run_codes(tree, algo, codes, pc, ro, None, present, 0, want_states=True)
                 assert np.array_equal(res.pos, want.pos) and np.array_equal(res.type_code, want.type_code)
                 assert np.array_equal(res.states, ws)
+                # the same batch clade-run encoded (expand_runs_kernel instead of pack_leaves_kernel)
+                c4 = pb.pack_nibbles(codes)
+                runs = pb.Runs.of_tree(tree, n_cols, c4, pc)
+                r2 = ctx.run_runs(algo, runs, pc, ro, None, present, flags=pb.FLAG_WANT_STATES)
+                assert np.array_equal(r2.pos, want.pos) and np.array_equal(r2.type_code, want.type_code) and np.array_equal(r2.states, ws)
+                runs.close()
         n += 1
     # overflow retry + async + pack/merge
     tree = random_tree(100, 5, "binary")
@@ -97,6 +104,10 @@ def main():
         res = g.download()
         assert np.array_equal(res.pos, want.pos) and np.array_equal(res.type_code, want.type_code)
         g.merge_runs()
+        runs = pb.Runs.of_tree(tree, 3500, c4, pc)
+        res = g.run_runs(algo, runs, pc, codes[0].astype(np.int8) if algo else None)
+        assert np.array_equal(res.pos, want.pos) and np.array_equal(res.type_code, want.type_code)
+        runs.close()
         bad = ctypes.c_longlong(pb.load_library().pmb_debug_check_canaries()).value
         print(f"group algo {algo}: guard bytes overwritten = {bad}")
         assert bad in (0, -1)
