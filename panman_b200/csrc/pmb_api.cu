@@ -126,6 +126,7 @@ struct pmb_ctx {
     std::vector<Occupancy> occupancy;
     unsigned int epoch = 0;
     unsigned int dir_clean_epoch = 0;  // epoch at which the staging directory was last cleared (0 = never)
+    unsigned int dir2_clean_epoch = 0; // the same for the second directory (double-buffered staging, see run_impl)
     bool sticky_dirty = false;         // a synchronous run left a status bit in the sticky words that pmb_wait must not see
     bool state_dirty = true;           // per-run device state (counters, tickets, node counts, directory) must be re-initialised
     unsigned int pack_seq = 0;
@@ -141,7 +142,7 @@ struct pmb_ctx {
     // after compact(i - 2) (same set matrix and ticket set), or after bwd(i - 1) when there is only one set matrix.
     cudaStream_t bstream = nullptr;
     cudaEvent_t ev_fwd_done = nullptr, ev_bwd_done = nullptr, ev_compact_done[2] = {nullptr, nullptr};
-    DevBuf d_sets2;
+    DevBuf d_sets2, d_dir2, d_staging2;
     int64_t opt_grid_pct = 0;             // persistent kernels take at most this share of the resident block slots (0 = auto)
     int cur_grid_pct = 100;
     int64_t opt_overlap = 1;              // 1 = double-buffer the set matrix when it is small enough (see run_impl)
@@ -497,7 +498,7 @@ void pmb_destroy(pmb_ctx* c) {
                           &c->d_pos, &c->d_tc, &c->d_states_u8, &c->d_done, &c->d_fdone, &c->d_ticket, &c->d_mcounts, &c->d_moff,
                           &c->d_mpos, &c->d_mtc, &c->d_scan_state, &c->d_trace, &c->d_rm_counts, &c->d_rm_off, &c->d_rm_pos,
                           &c->d_rm_info, &c->d_rm_nucs, &c->d_rm_wire, &c->d_rm_flags, &c->d_rm_oidx, &c->d_col_break, &c->d_merge_err, &c->d_mblock_sums, &c->d_mrel,
-                          &c->d_run_events, &c->d_run_off, &c->d_dfs_slot})
+                          &c->d_run_events, &c->d_run_off, &c->d_dfs_slot, &c->d_dir2, &c->d_staging2})
             b->release();
         for (auto& s : c->prog_cache)
             for (DevBuf& b : s.bufs) b.release();
@@ -809,8 +810,16 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     const size_t dir_bytes = size_t(P.n_nodes) * T * sizeof(unsigned long long);
     if (dir_bytes > c->d_dir.cap) c->dir_clean_epoch = 0;
     PMB_CUDA(c->d_dir.ensure(dir_bytes));
+    // With overlapping passes the staging pool, its directory and the run words are double-buffered too: the backward kernel
+    // of pass i then only follows the backward kernel of pass i - 1, not its compaction (a small problem's pass is a chain of
+    // dependent hops, and backward -> compaction -> backward was the longest chain through consecutive passes)
+    const bool dbl = overlap;
+    if (dbl) {
+        if (dir_bytes > c->d_dir2.cap) c->dir2_clean_epoch = 0;
+        PMB_CUDA(c->d_dir2.ensure(dir_bytes));
+    }
     if (!c->d_counters.p) {
-        PMB_CUDA(c->d_counters.ensure(64));
+        PMB_CUDA(c->d_counters.ensure(128));
         c->state_dirty = true;
     }
     PMB_CUDA(c->h_counters.ensure(128));
@@ -844,15 +853,17 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     rp.leaf_planes = c->d_leaf_planes.as<uint4>();
     rp.leaf_present = c->have_present ? c->d_present.as<uint8_t>() : nullptr;
     const int parity = int(c->run_seq & 1u);
+    const bool second = dbl && parity;  // this pass works on the second staging pool / directory / run words
     rp.sets = (overlap && parity) ? c->d_sets2.as<uint4>() : c->d_sets.as<uint4>();
     rp.fstore = c->d_fstore.as<uint32_t>();
     rp.order = nullptr;
     rp.stage_block = 512;
     rp.colparams = c->d_colparams.as<uint4>();
     rp.states = want_states ? c->d_states_planes.as<uint4>() : nullptr;
-    rp.dir = c->d_dir.as<unsigned long long>();
-    rp.pool_count = c->d_counters.as<unsigned long long>();
-    rp.error = reinterpret_cast<unsigned int*>(c->d_counters.as<unsigned long long>() + 1);
+    rp.dir = second ? c->d_dir2.as<unsigned long long>() : c->d_dir.as<unsigned long long>();
+    unsigned long long* const run_words = c->d_counters.as<unsigned long long>() + (second ? 8 : 0);
+    rp.pool_count = run_words;
+    rp.error = reinterpret_cast<unsigned int*>(run_words + 1);
     rp.done = c->d_done.as<unsigned int>();
     rp.fdone = c->d_fdone.as<unsigned int>();
     rp.ticket = nullptr;
@@ -883,12 +894,14 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
         PMB_CUDA(cudaStreamSynchronize(c->bstream));  // kernels of an abandoned run may still be using what is reset here
         PMB_CUDA(cudaStreamSynchronize(c->cstream));
         PMB_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, 128 * sizeof(unsigned long long), c->stream));
-        PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));
+        PMB_CUDA(cudaMemsetAsync(c->d_counters.p, 0, 128, c->stream));
         unsigned int* init = c->h_counters.as<unsigned int>() + 16;  // pinned
         init[0] = 0xFFFFFFFFu;
         PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 12, init, 4, cudaMemcpyHostToDevice, c->stream));
         PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 20, init, 4, cudaMemcpyHostToDevice, c->stream));
+        PMB_CUDA(cudaMemcpyAsync(c->d_counters.as<char>() + 64 + 12, init, 4, cudaMemcpyHostToDevice, c->stream));
         c->dir_clean_epoch = 0;
+        c->dir2_clean_epoch = 0;
     }
     if (c->sticky_dirty && !c->async_pending) {  // synchronous runs report their own status; only asynchronous ones use the sticky words
         unsigned int* init = c->h_counters.as<unsigned int>() + 18;  // pinned
@@ -923,9 +936,10 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     unsigned int* const fwd_error = reinterpret_cast<unsigned int*>(c->d_counters.as<unsigned long long>() + 2);
     for (int attempt = 0;; attempt++) {
         PMB_CUDA(c->d_staging.ensure(size_t(c->staging_cap) * sizeof(uint16_t)));
+        if (dbl) PMB_CUDA(c->d_staging2.ensure(size_t(c->staging_cap) * sizeof(uint16_t)));
         PMB_CUDA(c->d_pos.ensure(size_t(c->staging_cap) * sizeof(int32_t)));
         PMB_CUDA(c->d_tc.ensure(size_t(c->staging_cap)));
-        rp.staging = c->d_staging.as<uint16_t>();
+        rp.staging = second ? c->d_staging2.as<uint16_t>() : c->d_staging.as<uint16_t>();
         rp.staging_cap = c->staging_cap;
         const unsigned int bwd_epoch = ++c->epoch;
         rp.dir_tag = bwd_epoch & DIR_TAG_MASK;
@@ -951,11 +965,15 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
                 st = bwd_stream;
                 PMB_CUDA(cudaStreamWaitEvent(st, c->ev_fwd_done, 0));
             }
-            // the backward kernel refills the staging pool and the directory the previous compaction reads
-            for (int k = 0; k < 2; k++) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_compact_done[k], 0));
-            if (g == 0 && (c->dir_clean_epoch == 0 || bwd_epoch - c->dir_clean_epoch >= DIR_TAG_MASK - 8u)) {  // new buffer, or the tag would wrap
-                PMB_CUDA(cudaMemsetAsync(c->d_dir.p, 0, c->d_dir.cap, st));
-                c->dir_clean_epoch = bwd_epoch;
+            // the backward kernel refills a staging pool and a directory: the compaction that read them last must be through
+            // (the previous pass' when there is one of each, the pass before that when they are double-buffered)
+            for (int k = 0; k < 2; k++)
+                if (!dbl || k == parity) PMB_CUDA(cudaStreamWaitEvent(st, c->ev_compact_done[k], 0));
+            unsigned int& clean_epoch = second ? c->dir2_clean_epoch : c->dir_clean_epoch;
+            if (g == 0 && (clean_epoch == 0 || bwd_epoch - clean_epoch >= DIR_TAG_MASK - 8u)) {  // new buffer, or the tag would wrap
+                DevBuf& dirbuf = second ? c->d_dir2 : c->d_dir;
+                PMB_CUDA(cudaMemsetAsync(dirbuf.p, 0, dirbuf.cap, st));
+                clean_epoch = bwd_epoch;
                 if (G > 1) {  // the other groups' backward kernels write the directory too
                     PMB_CUDA(cudaEventRecord(c->ev_fork, st));
                     for (int g2 = 1; g2 < G; g2++) PMB_CUDA(cudaStreamWaitEvent(c->gstream[g2], c->ev_fork, 0));
@@ -982,7 +1000,7 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
             compact_scan_kernel<<<1, 1024, 0, c->cstream>>>(gtotals, int(groups), gprefix, c->d_offsets.as<long long>() + P.n_nodes);
             compact_copy_kernel<<<groups, CPT_GROUP, 0, c->cstream>>>(
                 P.n_nodes, c->T, gprefix, c->d_offsets.as<long long>(), rp.dir, rp.dir_tag, rp.staging, c->col_base,
-                c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), c->d_counters.as<unsigned long long>(), rp.staging_cap,
+                c->d_pos.as<int32_t>(), c->d_tc.as<uint8_t>(), c->d_counters.as<unsigned long long>(), run_words, rp.staging_cap,
                 c->d_ticket.as<unsigned long long>() + ticket_set, 64);
             n_launches += 2;
             n_launches += 1;

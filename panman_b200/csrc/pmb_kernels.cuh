@@ -1587,12 +1587,13 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned int* 
     if (tid == 0) *offsets_end = (long long)s_carry;
 }
 
-// counters (64 bytes): layout below; [24,28) finished-block count of this kernel
+// counters (128 bytes): layout below; [24,28) finished-block count of this kernel
 __global__ void __launch_bounds__(CPT_GROUP) compact_copy_kernel(int n_nodes, int T, const unsigned long long* group_prefix,
                                                                 long long* offsets, const unsigned long long* dir, unsigned dir_tag,
                                                                 const uint16_t* staging, long long col_base, int32_t* pos,
                                                                 uint8_t* type_code, unsigned long long* counters,
-                                                                unsigned long long staging_cap, unsigned long long* tickets, int n_tickets) {
+                                                                unsigned long long* run_words, unsigned long long staging_cap,
+                                                                unsigned long long* tickets, int n_tickets) {
     __shared__ unsigned s_w[CPT_GROUP / 32];
     __shared__ unsigned s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1624,7 +1625,7 @@ __global__ void __launch_bounds__(CPT_GROUP) compact_copy_kernel(int n_nodes, in
         }
         if (tile == 0) offsets[node] = (long long)at;
         // after a pool overflow nothing is copied: the host grows the pool and reruns the backward pass
-        if (cnt && counters[0] <= staging_cap) {
+        if (cnt && run_words[0] <= staging_cap) {
             const uint16_t* src = staging + (d >> 11);
             const long long cb = col_base + (long long)tile * TILE_COLS;
             for (unsigned q0 = 0; q0 < cnt; q0 += 4) {  // four independent loads in flight
@@ -1650,9 +1651,9 @@ __global__ void __launch_bounds__(CPT_GROUP) compact_copy_kernel(int n_nodes, in
     __syncthreads();
     if (s_last) {
         if (tid == 0) {
-            unsigned int* error = reinterpret_cast<unsigned int*>(counters + 1);
+            unsigned int* error = reinterpret_cast<unsigned int*>(run_words + 1);
             unsigned int* sticky = reinterpret_cast<unsigned int*>(counters + 2);
-            const unsigned long long pool = counters[0];
+            const unsigned long long pool = run_words[0];
             const unsigned int er0 = error[0], er1 = error[1];
             const unsigned int st = er0 | (pool > staging_cap ? 4u : 0u);
             if (st) sticky[0] |= st;
@@ -1660,7 +1661,7 @@ __global__ void __launch_bounds__(CPT_GROUP) compact_copy_kernel(int n_nodes, in
             counters[4] = pool;
             reinterpret_cast<unsigned int*>(counters + 5)[0] = er0;
             reinterpret_cast<unsigned int*>(counters + 5)[1] = er1;
-            counters[0] = 0ull;
+            run_words[0] = 0ull;
             error[0] = 0u;
             error[1] = 0xFFFFFFFFu;
             done_blocks[0] = 0u;
@@ -1669,10 +1670,12 @@ __global__ void __launch_bounds__(CPT_GROUP) compact_copy_kernel(int n_nodes, in
     }
 }
 
-// counters (64 bytes): [0,8) staging records reserved, [8,12) error flags, [12,16) first bad column, [16,20) sticky
-// status, [20,24) sticky first bad column, [24,28) compact_copy_kernel's finished-block count, [32,48) snapshot of
-// [0,16) for the host. compact_copy_kernel's last block folds the status into the sticky words (they survive until
-// pmb_wait), snapshots the per-run counters and resets them and the work tickets.
+// counters (128 bytes): [0,8) staging records reserved, [8,12) error flags, [12,16) first bad column -- the "run words" of
+// a pass; passes of odd parity use [64,80) instead where the staging pool and the directory are double-buffered, so that a
+// backward kernel may run beside the compaction of the pass before it -- [16,20) sticky status, [20,24) sticky first bad
+// column, [24,28) compact_copy_kernel's finished-block count, [32,48) snapshot of the run words for the host.
+// compact_copy_kernel's last block folds the status into the sticky words (they survive until pmb_wait), snapshots the
+// run words and resets them and the work tickets.
 
 // ------------------------------------------------------------------ merging column-range shards (multi-GPU)
 // A packed shard = {int64 n_mut, int64 n_nodes | int64 offsets[N+1] | int32 pos[cap] | uint8 type_code[cap]} (16-byte
