@@ -249,7 +249,6 @@ def measure_one(pb, synth, torch, name, algo, dev, local, steps, warmup):
     ctx.upload(C, tree.n_leaves, codes4, codes4.shape[1], pc, ro)
     del codes4
     lib = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
-    lib_end = torch.cuda.ExternalStream(ctx.result_stream_handle(), device=dev)  # a pass ends on its compaction stream
     for _ in range(max(3, warmup)):
         ctx.run_resident_async(algo_i)
     ctx.wait()
@@ -257,7 +256,8 @@ def measure_one(pb, synth, torch, name, algo, dev, local, steps, warmup):
     e0.record(lib)
     for _ in range(steps):
         ctx.run_resident_async(algo_i)
-    e1.record(lib_end)
+    ctx.join()  # consecutive passes run on several streams (small problems: on two lanes); the main stream now follows them all
+    e1.record(lib)
     ctx.wait()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps

@@ -103,7 +103,10 @@ const char* pmb_last_error(const pmb_ctx* ctx);
  * "col_groups" (column-tile groups run on separate streams; default 1), "overlap" (1 [default]: set matrices up to 4 GB
  * are double-buffered so that the forward kernel of an asynchronous pass runs beside the backward kernel of the pass
  * before it; 0: one set matrix, passes strictly one after the other), "grid_pct" (share of the resident block slots a
- * persistent kernel takes; 0 = automatic: 80 for overlapping asynchronous passes, 100 otherwise), "trace" (debug timeline). */
+ * persistent kernel takes; 0 = automatic: 80 for overlapping asynchronous passes, 100 otherwise), "lanes" (1 [default]:
+ * asynchronous passes of small problems -- set matrix up to 4 GB, no chain segments, no state output -- alternate between two
+ * independent pipelines inside the context, each with its own set matrices, flags, staging and lists, both reading the same
+ * resident input; 0: one pipeline), "trace" (debug timeline). */
 int pmb_set_option(pmb_ctx* ctx, const char* key, int64_t value);
 
 /* Page-locked host memory for the caller's input buffers. pmb_run_nuc / pmb_upload_nuc accept any host pointer, but
@@ -167,6 +170,9 @@ int pmb_run_resident(pmb_ctx* ctx, int algo, int flags);
  * the fly in this mode: an overflow is reported by pmb_wait (and the pool grown for the next attempt). */
 int pmb_run_resident_async(pmb_ctx* ctx, int algo, int flags);
 int pmb_wait(pmb_ctx* ctx);
+/* Orders pmb_stream(ctx) behind every pass enqueued so far (consecutive asynchronous passes run on several streams, small
+ * problems on two lanes): an event recorded on pmb_stream after pmb_join marks the end of all of them. Does not block. */
+int pmb_join(pmb_ctx* ctx);
 int pmb_download(pmb_ctx* ctx, pmb_result* out);
 
 /* ---- post-processing: greedy <= 6 run-merge of the per-node lists into NucMut fields, on the device ----

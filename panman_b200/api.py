@@ -222,6 +222,10 @@ class Context:
     def run_resident_async(self, algo=ALGO_FITCH, flags=0):
         self._check(self.L.pmb_run_resident_async(self.h, int(algo), int(flags)))
 
+    def join(self):
+        """pmb_join: pmb_stream now follows every pass enqueued so far (an event recorded on it marks their end)."""
+        self._check(self.L.pmb_join(self.h))
+
     def wait(self) -> Timings:
         self._check(self.L.pmb_wait(self.h))
         return self.timings()
@@ -281,6 +285,10 @@ class Context:
 
     def merge_status(self):
         self._check(self.L.pmb_merge_status(self.h))
+
+    def set_column_breaks(self, col_break):
+        """pmb_set_column_breaks: n_cols bytes (host or device), 1 = a run never continues INTO this column; None clears."""
+        self._check(self.L.pmb_set_column_breaks(self.h, _ptr(col_break)))
 
     def merge_runs(self, source: int = 0):
         """Greedy <= 6 run-merge of the per-node lists into NucMut fields on the device (pmb_merge_runs); returns host arrays

@@ -180,6 +180,18 @@ struct pmb_ctx {
     int32_t T = 0;
     bool have_present = false;
     DevBuf d_leaf_planes, d_present, d_colparams, d_tmp_codes, d_tmp_cols;
+    // Second pass lane. A small problem's pass is a chain of dependent hops, not a stream of bytes: two INDEPENDENT pipelines
+    // side by side fill the machine where one cannot (measured with two contexts, tools/lanes_probe.py: 10k leaves x 15 tiles
+    // 0.185 -> 0.149 ms per pass, 20k x 30 tiles 0.534 -> 0.503). `lane` is a child context that owns everything a pass writes
+    // (set matrices, flags, staging, lists, streams) and borrows what a pass only reads (program, leaf planes, column
+    // parameters) from this one; asynchronous passes alternate between the two, results are read from the one that ran last.
+    pmb_ctx* lane = nullptr;
+    bool is_lane = false;
+    int64_t opt_lanes = 1;                 // 0: never use the second lane
+    unsigned lane_seq = 0;                 // asynchronous passes dispatched while lanes were in use
+    pmb_ctx* last = nullptr;               // context holding the result of the pass enqueued last (nullptr = this one)
+    unsigned long long input_gen = 1, lane_mirror_gen = 0;  // what this context holds / what the lane mirrors of it
+    cudaEvent_t ev_input_ready = nullptr;  // end of the last upload on `stream`: a lane pass waits for it
     // clade-run encoded input (pmb_upload_runs): the tree's leaves in depth-first order, the events of the resident range
     std::vector<int32_t> dfs_rows, h_dfs_slot;
     uint64_t dfs_hash = 0;
@@ -466,6 +478,7 @@ int pmb_create(pmb_ctx** out, int device) {
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_rm, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_input_ready, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         c->err = std::string("stream/event creation failed: ") + cudaGetErrorString(e);
         cudaGetLastError();
@@ -486,8 +499,28 @@ int pmb_create(pmb_ctx** out, int device) {
     return PMB_OK;
 }
 
+// what a lane borrows from its parent (never freed through the lane)
+static void lane_borrowed(pmb_ctx* L, DevBuf** out) {
+    DevBuf* b[13] = {&L->d_fwd_ops, &L->d_refs, &L->d_bwd_ops, &L->d_bwd_leaves, &L->d_chunks, &L->d_bwd_order, &L->d_level_order,
+                     &L->d_row_slot, &L->d_deps, &L->d_leaf_planes, &L->d_present, &L->d_colparams, &L->d_col_break};
+    for (int i = 0; i < 13; i++) out[i] = b[i];
+}
+
 void pmb_destroy(pmb_ctx* c) {
     if (!c) return;
+    if (c->lane) {
+        DevBuf* b[13];
+        lane_borrowed(c->lane, b);
+        if (c->lane->stream) {
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->lane->stream);
+            cudaStreamSynchronize(c->lane->bstream);
+            cudaStreamSynchronize(c->lane->cstream);
+        }
+        for (DevBuf* x : b) { x->p = nullptr; x->raw = nullptr; x->cap = 0; }
+        pmb_destroy(c->lane);
+        c->lane = nullptr;
+    }
     if (c->stream) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
@@ -522,6 +555,7 @@ void pmb_destroy(pmb_ctx* c) {
         if (c->cstream) cudaStreamDestroy(c->cstream);
         if (c->bstream) cudaStreamDestroy(c->bstream);
         if (c->ev_rm) cudaEventDestroy(c->ev_rm);
+        if (c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
         for (int k = 0; k < 2; k++) {
             if (c->ev_slab_copied[k]) cudaEventDestroy(c->ev_slab_copied[k]);
             if (c->ev_slab_packed[k]) cudaEventDestroy(c->ev_slab_packed[k]);
@@ -563,6 +597,7 @@ int pmb_set_option(pmb_ctx* c, const char* key, int64_t value) {
     else if (k == "trace") c->opt_trace = value;
     else if (k == "overlap") c->opt_overlap = value;
     else if (k == "grid_pct") c->opt_grid_pct = value;
+    else if (k == "lanes") c->opt_lanes = value;
     else return fail(c, PMB_ERR_INVALID, "unknown option " + k);
     return PMB_OK;
 }
@@ -594,6 +629,15 @@ static int set_tree_impl(pmb_ctx* c, int32_t n_nodes, int32_t root, const int32_
     c->have_tree = true;
     c->have_input = false;
     c->have_result = false;
+    c->last = nullptr;
+    c->input_gen++;
+    if (c->lane && c->lane->stream) {  // its passes belong to the previous tree
+        cudaStreamSynchronize(c->lane->stream);
+        cudaStreamSynchronize(c->lane->bstream);
+        cudaStreamSynchronize(c->lane->cstream);
+        c->lane->have_input = false;
+        c->lane->have_result = false;
+    }
     return PMB_OK;
 }
 
@@ -635,6 +679,12 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
     // passes still in flight on the backward / compaction streams read what is overwritten here
     PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_bwd_done, 0));
     for (int k = 0; k < 2; k++) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_compact_done[k], 0));
+    if (c->lane && c->lane->stream) {  // the lane's passes read the same leaf planes and column parameters
+        PMB_CUDA(cudaStreamWaitEvent(c->stream, c->lane->ev_bwd_done, 0));
+        for (int k = 0; k < 2; k++) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->lane->ev_compact_done[k], 0));
+    }
+    c->last = nullptr;
+    c->input_gen++;
     c->have_input = false;
     c->have_result = false;
     c->have_col_break = false;
@@ -762,6 +812,7 @@ static int upload_impl(pmb_ctx* c, int64_t n_cols, int32_t n_rows, const uint8_t
         PMB_CUDA(c->d_present.ensure(size_t(n_rows)));
         PMB_CUDA(cudaMemcpy(c->d_present.p, by_slot.data(), size_t(n_rows), cudaMemcpyHostToDevice));
     }
+    PMB_CUDA(cudaEventRecord(c->ev_input_ready, c->stream));
     if (sync) PMB_CUDA(cudaStreamSynchronize(c->stream));  // inputs were borrowed: they may be released on return
     c->upload_pending = !sync;
     c->have_input = true;
@@ -1072,17 +1123,130 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     return PMB_OK;
 }
 
+static pmb_ctx* result_ctx(pmb_ctx* c) { return c && c->last ? c->last : c; }
+static const pmb_ctx* result_cctx(const pmb_ctx* c) { return c && c->last ? c->last : c; }
+static bool lane_pending(const pmb_ctx* c) { return c && c->lane && (c->lane->async_pending || c->lane->upload_pending); }
+
 int pmb_run_resident(pmb_ctx* c, int algo, int flags) {
-    if (c && c->async_pending) {
+    if (c && (c->async_pending || lane_pending(c))) {
         int rc = pmb_wait(c);
         if (rc) return rc;
     }
+    if (c) c->last = nullptr;
     return run_impl(c, algo, flags, false);
 }
 
-int pmb_run_resident_async(pmb_ctx* c, int algo, int flags) { return run_impl(c, algo, flags, true); }
+// Is this pass one for the two lanes? Asynchronous passes of problems small enough to be latency-bound (set matrix up to
+// 4 GB; the lane holds a second pair), persistent schedule, no chain segments (a deep tree's segments want every block slot
+// for themselves), no state output (kept to one context), and not a rank of a group (its steps are ordered by the mailbox).
+static bool lanes_apply(const pmb_ctx* c, int algo, int flags) {
+    if (!c || !c->stream || c->is_lane || c->opt_lanes <= 0 || !c->have_tree || !c->have_input) return false;
+    if (c->opt_schedule != 1 || c->opt_overlap <= 0 || c->opt_trace || (flags & PMB_FLAG_WANT_STATES)) return false;
+    if (algo != PMB_ALGO_FITCH && algo != PMB_ALGO_SANKOFF) return false;
+    if (c->prog.n_chain_segments > 0 || pick_groups(c) != 1) return false;
+    const size_t set_bytes = size_t(c->prog.n_internal) * size_t(c->T) * (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
+    return set_bytes <= std::min(size_t(4) << 30, c->total_mem / 16);
+}
+
+static int run_on_lane(pmb_ctx* c, int algo, int flags) {
+    if (!c->lane) {
+        pmb_ctx* L = nullptr;
+        int rc = pmb_create(&L, c->device);
+        if (rc) {
+            c->err = std::string("second pass lane: ") + (L ? L->err : std::string("out of memory"));
+            if (L) pmb_destroy(L);
+            return rc;
+        }
+        L->is_lane = true;
+        L->opt_lanes = 0;
+        c->lane = L;
+    }
+    pmb_ctx* L = c->lane;
+    PMB_CUDA(cudaSetDevice(c->device));
+    L->opt_chunk_nodes = c->opt_chunk_nodes;
+    L->opt_staging_records = c->opt_staging_records;
+    L->opt_inline_nodes = c->opt_inline_nodes;
+    L->opt_schedule = c->opt_schedule;
+    L->opt_target_items = c->opt_target_items;
+    L->opt_reserve_sms = c->opt_reserve_sms;
+    L->opt_bwd_tail = c->opt_bwd_tail;
+    L->opt_col_groups = c->opt_col_groups;
+    L->opt_grid_pct = c->opt_grid_pct;
+    L->opt_overlap = c->opt_overlap;
+    if (L->lane_mirror_gen != c->input_gen) {  // another tree, program or batch since the lane last looked
+        L->n_nodes = c->n_nodes;
+        L->root = c->root;
+        L->prog = c->prog;
+        L->have_tree = true;
+        L->n_cols = c->n_cols;
+        L->col_base = c->col_base;
+        L->T = c->T;
+        L->have_present = c->have_present;
+        L->have_input = true;
+        L->staging_floor_dirty = true;
+        DevBuf* dst[13];
+        lane_borrowed(L, dst);
+        DevBuf* src[13];
+        lane_borrowed(c, src);
+        for (int i = 0; i < 13; i++) {
+            dst[i]->p = src[i]->p;
+            dst[i]->cap = src[i]->cap;
+            dst[i]->raw = nullptr;
+        }
+        L->have_col_break = c->have_col_break;
+        L->lane_mirror_gen = c->input_gen;
+    }
+    L->staging_cap = std::max(L->staging_cap, c->staging_cap);  // what this context's pool has grown to, the lane's starts from
+    PMB_CUDA(cudaStreamWaitEvent(L->stream, c->ev_input_ready, 0));  // what the main stream uploaded, not the passes behind it
+    int rc = run_impl(L, algo, flags, true);
+    if (rc) {
+        c->err = L->err;
+        return rc;
+    }
+    c->last = L;
+    c->have_result = true;
+    c->last_algo = algo;
+    c->last_flags = flags;
+    return PMB_OK;
+}
+
+int pmb_run_resident_async(pmb_ctx* c, int algo, int flags) {
+    if (lanes_apply(c, algo, flags)) {
+        if (c->lane_seq++ & 1u) PMB_GUARDED(c, run_on_lane(c, algo, flags))
+    } else if (c) {
+        c->lane_seq = 0;
+    }
+    if (c) c->last = nullptr;
+    return run_impl(c, algo, flags, true);
+}
+
+static int wait_one(pmb_ctx* c);
 
 int pmb_wait(pmb_ctx* c) {
+    if (!c) return PMB_ERR_INVALID;
+    int rc = wait_one(c);
+    if (c->lane && c->lane->stream) {
+        const int rc2 = wait_one(c->lane);
+        if (rc2 && !rc) {
+            c->err = c->lane->err;
+            rc = rc2;
+        }
+    }
+    return rc;
+}
+
+// Orders the context's main stream (pmb_stream) behind every pass enqueued so far, on either lane: an event recorded on
+// pmb_stream after this call marks the end of all of them.
+int pmb_join(pmb_ctx* c) {
+    if (!c) return PMB_ERR_INVALID;
+    if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
+    PMB_CUDA(cudaSetDevice(c->device));
+    PMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev[3], 0));
+    if (c->lane && c->lane->stream) PMB_CUDA(cudaStreamWaitEvent(c->stream, c->lane->ev[3], 0));
+    return PMB_OK;
+}
+
+static int wait_one(pmb_ctx* c) {
     if (!c) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->async_pending) {
@@ -1138,7 +1302,14 @@ int pmb_wait(pmb_ctx* c) {
     return PMB_OK;
 }
 
+static int result_device_one(pmb_ctx* c, pmb_result* out);
 int pmb_result_device(pmb_ctx* c, pmb_result* out) {
+    pmb_ctx* r = result_ctx(c);
+    const int rc = result_device_one(r, out);
+    if (rc && r != c) c->err = r->err;
+    return rc;
+}
+static int result_device_one(pmb_ctx* c, pmb_result* out) {
     if (!c || !out) return PMB_ERR_INVALID;
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
     out->n_mut = c->n_mut;
@@ -1152,12 +1323,24 @@ int pmb_result_device(pmb_ctx* c, pmb_result* out) {
     return PMB_OK;
 }
 
+static int download_one(pmb_ctx* c, pmb_result* out);
 int pmb_download(pmb_ctx* c, pmb_result* out) {
+    if (!c || !out) return PMB_ERR_INVALID;
+    if (c->stream && c->have_result && (c->async_pending || lane_pending(c))) {
+        int rcw = pmb_wait(c);
+        if (rcw) return rcw;
+    }
+    pmb_ctx* r = result_ctx(c);
+    const int rc = download_one(r, out);
+    if (rc && r != c) c->err = r->err;
+    return rc;
+}
+static int download_one(pmb_ctx* c, pmb_result* out) {
     if (!c || !out) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
     if (c->async_pending) {
-        int rcw = pmb_wait(c);
+        int rcw = wait_one(c);
         if (rcw) return rcw;
     }
     PMB_CUDA(cudaSetDevice(c->device));
@@ -1267,11 +1450,18 @@ long long pmb_debug_check_canaries(void) {
 }
 
 void* pmb_stream(pmb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
-void* pmb_result_stream(pmb_ctx* c) { return c ? static_cast<void*>(c->cstream) : nullptr; }
+void* pmb_result_stream(pmb_ctx* c) { return c ? static_cast<void*>(result_ctx(c)->cstream) : nullptr; }
 
 int64_t pmb_packed_bytes(int32_t n_nodes, int64_t capacity) { return int64_t(packed_bytes(n_nodes, capacity)); }
 
+static int pack_result_one(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v);
 int pmb_pack_result(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v) {
+    pmb_ctx* r = result_ctx(c);
+    const int rc = pack_result_one(r, d_packed, capacity, stream_v);
+    if (rc && r != c) c->err = r->err;
+    return rc;
+}
+static int pack_result_one(pmb_ctx* c, void* d_packed, int64_t capacity, void* stream_v) {
     if (!c || !d_packed) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_result) return fail(c, PMB_ERR_NO_INPUT, "no result: call pmb_run_resident first");
@@ -1371,10 +1561,28 @@ int pmb_set_column_breaks(pmb_ctx* c, const uint8_t* col_break) {
     PMB_CUDA(cudaMemcpyAsync(c->d_col_break.p, col_break, size_t(c->n_cols), cudaMemcpyDefault, c->stream));
     PMB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is borrowed
     c->have_col_break = true;
+    c->input_gen++;
     return PMB_OK;
 }
 
+static int merge_runs_one(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out);
 int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) {
+    pmb_ctx* r = source == 0 ? result_ctx(c) : c;
+    if (r != c) {  // the lists of the last pass are the lane's; the column breaks are this context's
+        if (c->async_pending || lane_pending(c)) {
+            int rcw = pmb_wait(c);
+            if (rcw) return rcw;
+        }
+        r->have_col_break = c->have_col_break;
+        r->d_col_break.p = c->d_col_break.p;
+        r->d_col_break.cap = c->d_col_break.cap;
+        r->d_col_break.raw = nullptr;
+    }
+    const int rc = merge_runs_one(r, source, to_host, out);
+    if (rc && r != c) c->err = r->err;
+    return rc;
+}
+static int merge_runs_one(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) {
     if (!c || !out || (source != 0 && source != 1)) return PMB_ERR_INVALID;
     if (!c->stream) return fail(c, PMB_ERR_CUDA, "no usable CUDA device; there is no CPU fallback");
     if (!c->have_tree) return fail(c, PMB_ERR_NO_TREE, "pmb_set_tree has not been called");
@@ -1382,7 +1590,7 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
     if (source == 1 && (!c->d_moff.p || !c->merge_stream)) return fail(c, PMB_ERR_NO_INPUT, "no merged shards: call pmb_merge_packed first");
     PMB_CUDA(cudaSetDevice(c->device));
     if (source == 0 && c->async_pending) {
-        int rcw = pmb_wait(c);
+        int rcw = wait_one(c);
         if (rcw) return rcw;
     }
     // source 0 runs on the stream the lists are produced on, source 1 on the stream of the pmb_merge_packed that produced
@@ -1469,7 +1677,7 @@ int pmb_merge_runs(pmb_ctx* c, int source, int to_host, pmb_nucmut_result* out) 
 
 int pmb_last_timings(const pmb_ctx* c, pmb_timings* out) {
     if (!c || !out) return PMB_ERR_INVALID;
-    *out = c->timings;
+    *out = result_cctx(c)->timings;
     return PMB_OK;
 }
 
@@ -1477,7 +1685,8 @@ int64_t pmb_algorithmic_bytes(const pmb_ctx* c, int algo) {
     if (!c || !c->have_tree || !c->have_input) return 0;
     const int64_t L = c->prog.n_rows, I = c->prog.n_internal;
     const int64_t per_col = L + (algo == PMB_ALGO_SANKOFF ? 8 : 4) * I;
-    return c->n_cols * per_col + 8 * (c->have_result ? c->n_mut : 0);
+    const pmb_ctx* r = result_cctx(c);
+    return c->n_cols * per_col + 8 * (r->have_result ? std::max<int64_t>(0, r->n_mut) : 0);
 }
 
 }  // extern "C"

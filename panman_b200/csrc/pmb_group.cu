@@ -289,6 +289,7 @@ int pmb_group_create(pmb_group** out, const int* devices, int n_local, int rank_
         g->local[i].device = devices[i];
         int rc = pmb_create(&g->local[i].ctx, devices[i]);
         if (rc) return gctx(g, rc, g->local[i]);  // the group stays alive so that pmb_group_last_error can say why
+        pmb_set_option(g->local[i].ctx, "lanes", 0);  // a rank's steps are ordered by the mailbox hand-shake: one pipeline each
     }
     if (g->has_root() && world > 1) {
         G_CUDA(cudaSetDevice(g->local[0].device));

@@ -17,7 +17,7 @@ EXPORTS = ["pmb_create", "pmb_destroy", "pmb_last_error", "pmb_set_option", "pmb
            "pmb_group_upload_nuc", "pmb_group_upload_shard", "pmb_group_run_async", "pmb_group_wait",
            "pmb_group_result_device", "pmb_group_download", "pmb_group_merge_runs", "pmb_group_run_nuc",
            "pmb_runs_encode", "pmb_runs_free", "pmb_runs_describe", "pmb_upload_runs", "pmb_upload_runs_async", "pmb_run_runs",
-           "pmb_group_upload_runs", "pmb_group_upload_shard_runs", "pmb_group_run_runs"]
+           "pmb_group_upload_runs", "pmb_group_upload_shard_runs", "pmb_group_run_runs", "pmb_join"]
 GROUP_HANDLE_BYTES = 128
 
 
@@ -75,6 +75,7 @@ def load_library():
     L.pmb_run_resident.argtypes = [vp, C.c_int, C.c_int]
     L.pmb_run_resident_async.argtypes = [vp, C.c_int, C.c_int]
     L.pmb_wait.argtypes = [vp]
+    L.pmb_join.argtypes = [vp]
     L.pmb_download.argtypes = [vp, C.POINTER(pmb_result)]
     L.pmb_result_device.argtypes = [vp, C.POINTER(pmb_result)]
     L.pmb_last_timings.argtypes = [vp, C.POINTER(pmb_timings)]

@@ -453,3 +453,81 @@ def test_async_overflow_is_reported(ctx):
     c.wait()
     assert c.download().n_mut == n_mut
     c.close()
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_two_lanes_of_asynchronous_passes(port, algo):
+    """Asynchronous passes of a small problem alternate between two pipelines inside the context ("lanes" option): whichever
+    lane ran last, download / result_device / merge_runs (with this context's column breaks) / pack_result see its lists;
+    uploads slipped in between are ordered behind both lanes' readers; an error of a lane pass comes out of pmb_wait."""
+    import torch
+
+    rng = np.random.default_rng(70 + algo)
+    tree = random_tree(250, 81, "binary")
+    batches = []
+    for n_cols in (3000, 1500, 4100):
+        base = rng.integers(1, 5, size=n_cols)
+        codes = np.repeat(base[None, :], tree.n_leaves, 0)
+        codes = np.where(rng.random(codes.shape) < 0.05, rng.integers(0, 16, size=codes.shape), codes).astype(np.uint8)
+        pc = base.astype(np.uint8)
+        ro = codes[0].astype(np.int8) if algo else None
+        want, _ = port.run(tree, algo, codes, pc, ro, None, None, 0, n_threads=4)
+        batches.append((n_cols, pb.pack_nibbles(codes), pc, ro, want))
+    c = pb.Context(0)
+    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
+    for lanes in (1, 0, 1):
+        c.set_option("lanes", lanes)
+        for k, (n_cols, c4, pc, ro, want) in enumerate(batches):
+            c.upload(n_cols, tree.n_leaves, c4, c4.shape[1], pc, ro)
+            for n_async in (1, 2, 5):  # the last pass on the main lane, on the second lane, on the main lane again
+                for _ in range(n_async):
+                    c.run_resident_async(algo)
+                assert _same(c.download(), want), (lanes, k, n_async)
+            brk = np.zeros(n_cols, np.uint8)
+            brk[::7] = 1
+            for n_async in (1, 2):
+                for _ in range(n_async):
+                    c.run_resident_async(algo)
+                c.set_column_breaks(brk)
+                got = c.merge_runs()
+                # the same call on one lane only is the reference for the other
+                c.set_option("lanes", 0)
+                c.run_resident_async(algo)
+                c.set_column_breaks(brk)
+                one = c.merge_runs()
+                c.set_option("lanes", lanes)
+                for x, y in zip(got, one):
+                    assert np.array_equal(x, y), (lanes, k, n_async, "merge_runs")
+            # shard packing reads the lists of whichever lane ran last
+            for n_async in (1, 2):
+                for _ in range(n_async):
+                    c.run_resident_async(algo)
+                c.wait()
+                cap = int(c.result_device().n_mut) + 8
+                buf = torch.empty(c.packed_bytes(cap), dtype=torch.uint8, device="cuda")
+                c.pack_result(buf, cap)
+                c.wait()
+                torch.cuda.synchronize()
+                hdr = buf[:16].cpu().numpy().view(np.int64)
+                assert int(hdr[0]) == int(want.node_offsets[-1]) and int(hdr[1]) == tree.n_nodes, (lanes, k, n_async, "pack_result")
+        # a new batch right behind passes still in flight on both lanes, no wait in between
+        n0, c40, pc0, ro0, want0 = batches[0]
+        n1, c41, pc1, ro1, want1 = batches[1]
+        c.upload(n0, tree.n_leaves, c40, c40.shape[1], pc0, ro0)
+        for _ in range(4):
+            c.run_resident_async(algo)
+        c.upload(n1, tree.n_leaves, c41, c41.shape[1], pc1, ro1)
+        for _ in range(3):
+            c.run_resident_async(algo)
+        assert _same(c.download(), want1), (lanes, "upload behind passes in flight")
+    if algo == 1:  # a Sankoff root without a finite cost, met by the pass on the second lane
+        n_cols, c4, pc, _, _ = batches[0]
+        bad = np.zeros((tree.n_leaves, n_cols), np.uint8)
+        lp = np.zeros(tree.n_leaves, np.uint8)  # every leaf omitted, no override (fitchSankoff.cpp:505)
+        c.upload(n_cols, tree.n_leaves, pb.pack_nibbles(bad), (n_cols + 1) // 2, pc, None, None, lp)
+        c.run_resident_async(1)
+        c.run_resident_async(1)
+        with pytest.raises(pb.PanmanError) as e:
+            c.wait()
+        assert e.value.code == -4
+    c.close()

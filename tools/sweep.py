@@ -73,7 +73,8 @@ def main():
         e0.record(lib)
         for _ in range(20):
             ctx.run_resident_async(algo)
-        e1.record(lib_end)
+        ctx.join()
+        e1.record(lib)
         ctx.wait()
         torch.cuda.synchronize()
         piped = e0.elapsed_time(e1) / 20
