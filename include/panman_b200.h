@@ -100,9 +100,10 @@ const char* pmb_last_error(const pmb_ctx* ctx);
  * "staging_records" (initial capacity of the mutation staging pool; 0 = chosen from the problem size),
  * "bwd_tail" (tenths of a machine-full of warps whose items form the sorted tail of the backward tickets; default 20),
  * "reserve_sms" (SMs the persistent kernels leave free, e.g. for an NCCL kernel running beside them; default 0),
- * "col_groups" (column-tile groups run on separate streams; default 1), "overlap" (1 [default]: set matrices up to 4 GB
- * are double-buffered so that the forward kernel of an asynchronous pass runs beside the backward kernel of the pass
- * before it; 0: one set matrix, passes strictly one after the other), "grid_pct" (share of the resident block slots a
+ * "col_groups" (column-tile groups run on separate streams; default 1), "overlap" (1 [default]: set matrices up to 48 GB
+ * and a quarter of the device's memory are double-buffered -- with the staging pool and its directory -- so that the forward
+ * kernel of an asynchronous pass runs beside the backward kernel of the pass before it; 0: one set matrix, passes strictly
+ * one after the other), "grid_pct" (share of the resident block slots a
  * persistent kernel takes; 0 = automatic: 80 for overlapping asynchronous passes, 100 otherwise), "lanes" (1 [default]:
  * asynchronous passes of small problems -- set matrix up to 4 GB, no chain segments, no state output -- alternate between two
  * independent pipelines inside the context, each with its own set matrices, flags, staging and lists, both reading the same

@@ -845,10 +845,20 @@ static int run_impl(pmb_ctx* c, int algo, int flags, bool async) {
     const size_t T = size_t(c->T);
     const size_t set_bytes_per = (algo == PMB_ALGO_FITCH ? 128 : 256) * sizeof(uint4);
     const size_t set_bytes = size_t(P.n_internal) * T * set_bytes_per;
-    // a second set matrix lets consecutive passes overlap (see bstream); only where it is cheap (up to 24 GB and an eighth
-    // of the device's memory: that covers a half, a quarter or an eighth of BASELINE.json's config 4 on 2, 4 or 8 GPUs and
-    // config 5): the largest problems run at the HBM roofline anyway and would pay tens of GB for it
-    const bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= std::min(size_t(24) << 30, c->total_mem / 8);
+    // a second set matrix lets consecutive passes overlap (see bstream): up to 48 GB and a quarter of the device's memory --
+    // BASELINE.json's config 4 whole on one B200 (40 GB; measured on its halves: 0.973 of the roofline overlapping, 0.948
+    // without) -- and a large one only where the device clearly has the room for it beside everything else of the pass
+    bool overlap = c->opt_overlap > 0 && c->opt_schedule == 1 && pick_groups(c) == 1 && set_bytes <= std::min(size_t(48) << 30, c->total_mem / 4);
+    if (overlap && set_bytes > c->d_sets2.cap && set_bytes > (size_t(8) << 30)) {
+        size_t free_b = 0, total_b = 0;
+        const size_t need = set_bytes + (set_bytes > c->d_sets.cap ? set_bytes - c->d_sets.cap : 0) + (size_t(16) << 30);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            cudaGetLastError();
+            overlap = false;
+        } else if (free_b + c->d_sets2.cap < need) {
+            overlap = false;
+        }
+    }
     if (set_bytes > c->d_sets.cap || (overlap && set_bytes > c->d_sets2.cap)) {  // cudaFree of a matrix a running pass uses
         PMB_CUDA(cudaStreamSynchronize(c->bstream));
         PMB_CUDA(cudaStreamSynchronize(c->cstream));
