@@ -506,21 +506,10 @@ static void lane_borrowed(pmb_ctx* L, DevBuf** out) {
     for (int i = 0; i < 13; i++) out[i] = b[i];
 }
 
+static void drop_lane(pmb_ctx* c);
 void pmb_destroy(pmb_ctx* c) {
     if (!c) return;
-    if (c->lane) {
-        DevBuf* b[13];
-        lane_borrowed(c->lane, b);
-        if (c->lane->stream) {
-            cudaSetDevice(c->device);
-            cudaStreamSynchronize(c->lane->stream);
-            cudaStreamSynchronize(c->lane->bstream);
-            cudaStreamSynchronize(c->lane->cstream);
-        }
-        for (DevBuf* x : b) { x->p = nullptr; x->raw = nullptr; x->cap = 0; }
-        pmb_destroy(c->lane);
-        c->lane = nullptr;
-    }
+    drop_lane(c);
     if (c->stream) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
@@ -1220,9 +1209,40 @@ static int run_on_lane(pmb_ctx* c, int algo, int flags) {
     return PMB_OK;
 }
 
+static void drop_lane(pmb_ctx* c) {
+    if (!c->lane) return;
+    pmb_ctx* L = c->lane;
+    if (L->stream) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(L->stream);
+        cudaStreamSynchronize(L->bstream);
+        cudaStreamSynchronize(L->cstream);
+    }
+    DevBuf* b[13];
+    lane_borrowed(L, b);
+    for (DevBuf* x : b) { x->p = nullptr; x->raw = nullptr; x->cap = 0; }
+    if (c->last == L) c->last = nullptr;
+    c->lane = nullptr;
+    pmb_destroy(L);
+}
+
 int pmb_run_resident_async(pmb_ctx* c, int algo, int flags) {
     if (lanes_apply(c, algo, flags)) {
-        if (c->lane_seq++ & 1u) PMB_GUARDED(c, run_on_lane(c, algo, flags))
+        if (c->lane_seq++ & 1u) {
+            int rc;
+            try {
+                rc = run_on_lane(c, algo, flags);
+            } catch (const std::bad_alloc&) {
+                rc = PMB_ERR_OOM;
+            } catch (const std::exception& ex) {
+                return fail(c, PMB_ERR_INVALID, std::string("internal: ") + ex.what());
+            }
+            if (rc != PMB_ERR_OOM) return rc;
+            // no room for a second set of pass buffers: one pipeline it is (nothing of the lane's pass has been enqueued)
+            drop_lane(c);
+            c->opt_lanes = 0;
+            c->err.clear();
+        }
     } else if (c) {
         c->lane_seq = 0;
     }

@@ -520,6 +520,20 @@ def test_two_lanes_of_asynchronous_passes(port, algo):
         for _ in range(3):
             c.run_resident_async(algo)
         assert _same(c.download(), want1), (lanes, "upload behind passes in flight")
+    # another tree while passes of the old one are still in flight on both lanes, then straight on
+    tree2 = random_tree(180, 82, "polytomy", max_arity=5)
+    codes2 = rng.integers(0, 16, size=(tree2.n_leaves, 2500)).astype(np.uint8)
+    codes2 = np.where(rng.random(codes2.shape) < 0.9, codes2[:1], codes2).astype(np.uint8)
+    want2, _ = port.run(tree2, algo, codes2, codes2[0].copy(), codes2[0].astype(np.int8) if algo else None, None, None, 0, n_threads=4)
+    for _ in range(3):
+        c.run_resident_async(algo)
+    c.set_tree(tree2.n_nodes, tree2.root, tree2.child_off, tree2.child_idx, tree2.leaf_row)
+    c42 = pb.pack_nibbles(codes2)
+    c.upload(2500, tree2.n_leaves, c42, c42.shape[1], codes2[0].copy(), codes2[0].astype(np.int8) if algo else None)
+    for _ in range(4):
+        c.run_resident_async(algo)
+    assert _same(c.download(), want2), "after set_tree"
+    c.set_tree(tree.n_nodes, tree.root, tree.child_off, tree.child_idx, tree.leaf_row)
     if algo == 1:  # a Sankoff root without a finite cost, met by the pass on the second lane
         n_cols, c4, pc, _, _ = batches[0]
         bad = np.zeros((tree.n_leaves, n_cols), np.uint8)
@@ -530,4 +544,9 @@ def test_two_lanes_of_asynchronous_passes(port, algo):
         with pytest.raises(pb.PanmanError) as e:
             c.wait()
         assert e.value.code == -4
+    else:  # destroyed with passes in flight on both lanes
+        n_cols, c4, pc, ro, _ = batches[2]
+        c.upload(n_cols, tree.n_leaves, c4, c4.shape[1], pc, ro)
+        for _ in range(4):
+            c.run_resident_async(algo)
     c.close()
