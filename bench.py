@@ -518,6 +518,7 @@ def run_b200_arm(args):
                 "value": N * C * runs_steps / float(e3max[0]), "unit": "node*col/s", "ms_per_step": 1e3 * float(e3max[0]) / runs_steps,
                 "steps": runs_steps, "h2d_bytes_per_step": int(e3[2]), "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
                 "host_encode_seconds_once": float(e3max[1]), "events_per_column": runs.n_events / max(1, c1 - c0),
+                "ms_per_step_if_encoded_every_step": 1e3 * float(e3max[1]) + 1e3 * float(e3max[0]) / runs_steps,
                 "lists_identical_to_the_matrix_entry": same,
                 "api": "pmb_runs_encode once (host, outside the timed region); per step pmb_group_upload_shard_runs (page-locked events) "
                        "+ pmb_group_run_async + pmb_group_download on every rank",
