@@ -487,10 +487,19 @@ def run_b200_arm(args):
         # ---- the same through the denser boundary format: this rank's range clade-run encoded (pmb_runs_encode, once, on the
         # host, outside the timed region -- as the nibble packing of h_codes is), then per step: events host -> device,
         # expansion into the same bit-planes on the device, the pass, lists device -> host
-        try:
+        runs, enc_s, setup_error = None, 0.0, None
+        try:  # a rank that cannot encode (host memory) must not leave the others waiting in a barrier
             t_enc = time.perf_counter()
             runs = pb.Runs.of_tree(tree, c1 - c0, h_codes.numpy(), h_pc.numpy())
             enc_s = time.perf_counter() - t_enc
+        except Exception as e:  # noqa: BLE001
+            setup_error = str(e)
+        ok = torch.tensor([0.0 if setup_error else 1.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        try:
+            if float(ok[0]) < 1.0:
+                raise RuntimeError(setup_error or "pmb_runs_encode failed on another rank")
 
             def runs_step():
                 g.upload_shard_runs(0, C, runs, h_pc, h_ro)
@@ -524,9 +533,10 @@ def run_b200_arm(args):
                        "+ pmb_group_run_async + pmb_group_download on every rank",
                 "note": "same pass, same results; only the form in which the leaf codes cross PCIe differs. `e2e.value` above stays the "
                         "nibble-matrix entry (the conservative figure)"}
-            runs.close()
         except Exception as e:  # noqa: BLE001
             e2e["clade_runs"] = {"error": str(e)}
+        if runs is not None:
+            runs.close()
         del h_codes, h_pc
 
     if rank != 0:
