@@ -58,3 +58,19 @@ class Emulator:
         states = np.empty((tree.n_nodes, n_cols), np.uint8) if want_states else None
         n = call(pos, tc, states)
         return 0, MutLists(off.copy(), pos[:n].copy(), tc[:n].copy()), states, stats
+
+
+def expand_runs_mismatches(tree, codes, parent_code, runs, chunk_nodes=8, inline_nodes=3):
+    """Plane words in which the emulated expand_runs_kernel (on `runs`, a panman_b200.Runs of `codes`) differs from the emulated
+    pack_leaves_kernel: 0 = both ingest paths build the same leaf matrix for this tree program."""
+    build()
+    L = C.CDLL(SO)
+    L.emul_expand_runs.restype = C.c_longlong
+    codes = np.ascontiguousarray(codes, np.uint8)
+    pc = np.ascontiguousarray(parent_code, np.uint8)
+    ev = np.ascontiguousarray(runs.events(), np.uint32) if runs.n_events else np.zeros(1, np.uint32)
+    off = np.ascontiguousarray(runs.item_offsets(), np.int64)
+    return int(L.emul_expand_runs(C.c_int(tree.n_nodes), C.c_int(tree.root), _p(tree.child_off, C.c_int32), _p(tree.child_idx, C.c_int32),
+                                  _p(tree.leaf_row, C.c_int32), C.c_int(chunk_nodes), C.c_int(inline_nodes), C.c_longlong(codes.shape[1]),
+                                  _p(codes, C.c_uint8), _p(pc, C.c_uint8), _p(ev, C.c_uint32), _p(off, C.c_longlong),
+                                  C.c_int(runs.info.n_segments), C.c_int(runs.info.seg_rows)))

@@ -1069,3 +1069,90 @@ extern "C" long long emul_merge_runs(long long n, const int32_t* pos, const uint
     }
     return base[nb - 1] + counts[nb - 1];
 }
+
+// expand_runs_kernel (clade-run encoded leaves -> code planes), lane by lane, against pack_leaves_kernel's planes of the same
+// matrix: returns the number of plane words that differ (0 = the two ingest paths build the same leaf matrix), -1 on a bad
+// tree. events / item_off / n_seg / seg_rows: what pmb_runs_describe reports for the encoding of leaf_codes.
+extern "C" long long emul_expand_runs(int n_nodes, int root, const int32_t* child_off, const int32_t* child_idx, const int32_t* leaf_row,
+                                      int chunk_nodes, int inline_nodes, long long n_cols, const uint8_t* leaf_codes /* n_rows x n_cols */,
+                                      const uint8_t* parent_code, const uint32_t* events, const long long* item_off, int n_seg,
+                                      int seg_rows) {
+    TreeProgram P;
+    if (!build_tree_program(n_nodes, root, child_off, child_idx, leaf_row, chunk_nodes, inline_nodes, &P).empty()) return -1;
+    const int T = int((n_cols + TILE_COLS - 1) / TILE_COLS), n_rows = P.n_rows;
+    std::vector<U4> want((size_t)n_rows * T * 32, U4{0, 0, 0, 0}), got((size_t)n_rows * T * 32, U4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+    std::vector<U4> colparams((size_t)T * 128, U4{0, 0, 0, 0});
+    auto setcode = [](U4& u, uint32_t code, uint32_t bit) {
+        if (code & 1) u.x |= bit;
+        if (code & 2) u.y |= bit;
+        if (code & 4) u.z |= bit;
+        if (code & 8) u.w |= bit;
+    };
+    for (long long c = 0; c < n_cols; c++) {
+        const uint32_t bit = 1u << (c & 31);
+        const size_t tile = size_t(c / TILE_COLS), lane = size_t((c % TILE_COLS) >> 5);
+        setcode(colparams[tile * 128 + lane], parent_code[c] & 15u, bit);
+        for (int r = 0; r < n_rows; r++)
+            setcode(want[(tile * n_rows + P.row_slot[r]) * 32 + lane], leaf_codes[(size_t)r * n_cols + c] & 15u, bit);
+    }
+    // the leaves in depth-first order (children in Newick order) -> their slots
+    std::vector<int32_t> dfs_slot;
+    {
+        std::vector<int32_t> stack{root};
+        while (!stack.empty()) {
+            const int32_t v = stack.back();
+            stack.pop_back();
+            if (child_off[v] == child_off[v + 1]) {
+                dfs_slot.push_back(P.row_slot[leaf_row[v]]);
+                continue;
+            }
+            for (int32_t e = child_off[v + 1] - 1; e >= child_off[v]; e--) stack.push_back(child_idx[e]);
+        }
+        if (int(dfs_slot.size()) != n_rows) return -1;
+    }
+    const long long n_items = (long long)T * n_seg;
+    for (long long item = 0; item < n_items; item++) {  // one warp each
+        const long long tile = item / n_seg;
+        const int seg = int(item % n_seg);
+        const int r0 = seg * seg_rows, nr = std::min(seg_rows, n_rows - r0);
+        U4 cur[32];
+        for (int lane = 0; lane < 32; lane++) cur[lane] = colparams[(size_t)tile * 128 + lane];
+        long long k = item_off[item];
+        const long long k_end = item_off[item + 1];
+        uint32_t ev[32];
+        auto load = [&]() {
+            for (int lane = 0; lane < 32; lane++) ev[lane] = (k + lane < k_end) ? events[k + lane] : 0xFFFFFFFFu;
+        };
+        load();
+        int j = 0;
+        uint32_t next_row = ev[0] >> 14;
+        for (int rb = 0; rb < nr; rb += 32) {
+            int my_slot[32];
+            for (int lane = 0; lane < 32; lane++) my_slot[lane] = (rb + lane < nr) ? dfs_slot[size_t(r0 + rb + lane)] : 0;
+            const int lim = std::min(32, nr - rb);
+            for (int i = 0; i < lim; i++) {
+                while (next_row == uint32_t(rb + i)) {
+                    const uint32_t e = ev[j];
+                    const int lane = int((e >> 9) & 31u);
+                    const uint32_t bit = 1u << ((e >> 4) & 31u);
+                    cur[lane].x ^= (e & 1u) ? bit : 0u;
+                    cur[lane].y ^= (e & 2u) ? bit : 0u;
+                    cur[lane].z ^= (e & 4u) ? bit : 0u;
+                    cur[lane].w ^= (e & 8u) ? bit : 0u;
+                    if (++j == 32) {
+                        k += 32;
+                        load();
+                        j = 0;
+                    }
+                    next_row = ev[j] >> 14;
+                }
+                const int slot = my_slot[i];
+                for (int lane = 0; lane < 32; lane++) got[((size_t)tile * n_rows + slot) * 32 + lane] = cur[lane];
+            }
+        }
+    }
+    long long bad = 0;
+    for (size_t i = 0; i < want.size(); i++)
+        bad += (want[i].x != got[i].x) + (want[i].y != got[i].y) + (want[i].z != got[i].z) + (want[i].w != got[i].w);
+    return bad;
+}

@@ -50,6 +50,23 @@ def test_encode_round_trip(kind):
         r.close()
 
 
+@pytest.mark.parametrize("kind", ["binary", "polytomy", "caterpillar"])
+def test_expansion_builds_the_planes_of_the_matrix_path(kind):
+    """expand_runs_kernel restated lane by lane (tests/emul) on the encoder's events against pack_leaves_kernel's planes, with the
+    leaf slots of real tree programs (several chunk sizes): the two ingest paths hand the pass kernels the same leaf matrix."""
+    from tests.emul.emul import expand_runs_mismatches
+
+    rng = np.random.default_rng(11)
+    for trial in range(5):
+        tree = random_tree(int(rng.integers(2, 500)), 300 + trial, kind, max_arity=[3, 12][trial % 2])
+        n_cols = int(rng.choice([5, 1000, 1024, 1025, 2500]))
+        codes, pc = _matrix(rng, tree, n_cols, [0.01, 0.3, 1.0][trial % 3])
+        runs = pb.Runs.of_tree(tree, n_cols, pb.pack_nibbles(codes), pc)
+        for chunk_nodes, inline_nodes in ((8, 3), (1, 0), (64, 2)):
+            assert expand_runs_mismatches(tree, codes, pc, runs, chunk_nodes, inline_nodes) == 0, (kind, trial, chunk_nodes)
+        runs.close()
+
+
 def test_encode_is_small_on_clade_structured_columns():
     """A substitution on a branch changes a whole clade = one run of consecutive leaves in depth-first order: two events."""
     from panman_b200 import synth
